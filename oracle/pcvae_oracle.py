@@ -1,0 +1,359 @@
+"""CPU oracle for the partial-VAE posterior-consistency hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package
+(`vae_posterior_consistency_b200/`) imports this file; only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
+legs may use it, and there only as the checker / the timed CPU baseline.
+
+It is a closed-form restatement (torch CPU tensors, dtype-generic so the same
+code runs in fp32 and fp64) of the reference's arithmetic.  All citations are
+relative to the reference repo root (`src/...`).
+
+Parity status: the reference ships no tests, golden vectors or seeds
+(SURVEY.md section 4), so the oracle is pinned against outputs of the reference
+itself, generated in the build container by `tests/golden/make_golden.py`
+(imports the unmodified reference, records its inputs, noise draws and outputs)
+and committed as `tests/golden/*.pt`.  `tests/test_oracle_golden.py` checks the
+oracle against every one of those fixtures.
+
+Parameter containers are plain dicts keyed by the reference's state_dict names
+(SURVEY.md A.1), e.g. `seq_encoder.0.weight`.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
+#: fixed decoder log-variance log((0.1*sqrt(2))^2)=log 0.02, src/models/VAE.py:379
+X_LOGVAR = math.log((0.1 * math.sqrt(2.0)) ** 2)
+LATENT = 10
+BETA_MAX_EPOCH = 2800  # src/models/VAE.py:384
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+
+def _lin(h: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    return h @ w.t() + b
+
+
+def _as(m: Tensor, like: Tensor) -> Tensor:
+    return m.to(like.dtype)
+
+
+def is_pnp(p: Params) -> bool:
+    return "type_pars1" in p
+
+
+def init_params(family: str, obs_dim: int, K: int = 20, latent: int = LATENT,
+                seed: int = 0, dtype=torch.float32) -> Params:
+    """Random parameters with the reference's shapes and init distributions
+    (nn.Linear default init; Xavier-uniform for the PNP embeddings,
+    src/models/VAE.py:366-376, 687-709).  Used for synthetic benchmarks and
+    tests; the values are not meant to match any particular torch seed."""
+    g = torch.Generator().manual_seed(seed)
+
+    def linear(out_f, in_f):
+        bound = 1.0 / math.sqrt(in_f)
+        w = (torch.rand(out_f, in_f, generator=g, dtype=torch.float64) * 2 - 1) * bound
+        b = (torch.rand(out_f, generator=g, dtype=torch.float64) * 2 - 1) * bound
+        return w.to(dtype), b.to(dtype)
+
+    def xavier(r, c):
+        bound = math.sqrt(6.0 / (r + c))
+        return ((torch.rand(r, c, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+
+    p: Params = {}
+    if family in ("pnp", "eddi"):
+        p["type_pars1"] = xavier(obs_dim, K)
+        p["type_bias1"] = xavier(obs_dim, 1)
+        p["pnp_encoder1.0.weight"], p["pnp_encoder1.0.bias"] = linear(K, K + 2)
+        enc, first_in = "pnp_encoder2", K
+    elif family in ("mlp", "vae"):
+        enc, first_in = "seq_encoder", obs_dim
+    else:
+        raise ValueError(family)
+    p["prior_mean"] = torch.zeros(latent, dtype=dtype)
+    p["prior_std"] = torch.ones(latent, dtype=dtype)
+    for idx, (o, i) in zip((0, 2, 4), ((100, first_in), (50, 100), (2 * latent, 50))):
+        p[f"{enc}.{idx}.weight"], p[f"{enc}.{idx}.bias"] = linear(o, i)
+    for idx, (o, i) in zip((0, 2, 4), ((50, latent), (100, 50), (obs_dim, 100))):
+        p[f"seq_decoder.{idx}.weight"], p[f"seq_decoder.{idx}.bias"] = linear(o, i)
+    return p
+
+
+# --------------------------------------------------------------------------
+# encoders / decoder
+# --------------------------------------------------------------------------
+
+def mlp_first_layer_pre(p: Params, x: Tensor, mask: Tensor) -> Tensor:
+    """W1 (x*mask) + b1, the pre-activation the reward's incremental form builds on."""
+    return _lin(x * _as(mask, x), p["seq_encoder.0.weight"], p["seq_encoder.0.bias"])
+
+
+def mlp_tail(p: Params, h_pre: Tensor, prefix: str = "seq_encoder") -> Tuple[Tensor, Tensor]:
+    h1 = torch.relu(h_pre)
+    h2 = torch.relu(_lin(h1, p[f"{prefix}.2.weight"], p[f"{prefix}.2.bias"]))
+    o = _lin(h2, p[f"{prefix}.4.weight"], p[f"{prefix}.4.bias"])
+    L = o.shape[1] // 2
+    return o[:, :L], o[:, L:]
+
+
+def mlp_encoder_stats(p: Params, x: Tensor, mask: Tensor) -> Tuple[Tensor, Tensor]:
+    """Zero-imputation encoder, src/models/VAE.py:387-388 (nets :366-372)."""
+    return mlp_tail(p, mlp_first_layer_pre(p, x, mask))
+
+
+def pnp_embed_as_written(p: Params, x: Tensor) -> Tensor:
+    """Per-feature embedding ReLU(W_e [x_d, x_d E_d, b_d] + b_e), as written at
+    src/models/VAE.py:726-733.  Returns [B, D, K]."""
+    B, D = x.shape
+    E, bE = p["type_pars1"], p["type_bias1"]
+    We, be = p["pnp_encoder1.0.weight"], p["pnp_encoder1.0.bias"]
+    xf = x.reshape(B, D, 1)
+    feat = torch.cat([xf, xf * E.unsqueeze(0), bE.unsqueeze(0).expand(B, D, 1)], dim=2)
+    return torch.relu(feat @ We.t() + be)
+
+
+def pnp_collapse(p: Params) -> Tuple[Tensor, Tensor]:
+    """A, C of SURVEY.md A.3: W_e [x, x E_d, b_d] + b_e == x*A_d + C_d."""
+    E, bE = p["type_pars1"], p["type_bias1"]
+    We, be = p["pnp_encoder1.0.weight"], p["pnp_encoder1.0.bias"]
+    K = E.shape[1]
+    A = We[:, 0].unsqueeze(0) + E @ We[:, 1:K + 1].t()
+    C = bE * We[:, K + 1].unsqueeze(0) + be.unsqueeze(0)
+    return A, C
+
+
+def pnp_aggregate(p: Params, x: Tensor, mask: Tensor, collapsed: bool = False) -> Tensor:
+    """agg_b = sum_d mask_bd * e_bd, src/models/VAE.py:731-733."""
+    if collapsed:
+        A, C = pnp_collapse(p)
+        emb = torch.relu(x.unsqueeze(2) * A.unsqueeze(0) + C.unsqueeze(0))
+    else:
+        emb = pnp_embed_as_written(p, x)
+    return (_as(mask, x).unsqueeze(2) * emb).sum(1)
+
+
+def pnp_tail(p: Params, agg: Tensor) -> Tuple[Tensor, Tensor]:
+    h1_pre = _lin(agg, p["pnp_encoder2.0.weight"], p["pnp_encoder2.0.bias"])
+    return mlp_tail(p, h1_pre, prefix="pnp_encoder2")
+
+
+def pnp_encoder_stats(p: Params, x: Tensor, mask: Tensor, collapsed: bool = False):
+    """PNP/EDDI set encoder, src/models/VAE.py:719-734."""
+    return pnp_tail(p, pnp_aggregate(p, x, mask, collapsed))
+
+
+def encoder_stats(p: Params, x: Tensor, mask: Tensor, collapsed: bool = False):
+    if is_pnp(p):
+        return pnp_encoder_stats(p, x, mask, collapsed)
+    return mlp_encoder_stats(p, x, mask)
+
+
+def reparam(mu: Tensor, logvar: Tensor, eps: Tensor) -> Tensor:
+    """Normal(mu, exp(logvar/2)).rsample() == mu + eps*std, src/models/VAE.py:390-392."""
+    return mu + eps * torch.exp(logvar / 2)
+
+
+def decoder(p: Params, z: Tensor) -> Tensor:
+    """src/models/VAE.py:397-401 (nets :374-376)."""
+    g1 = torch.relu(_lin(z, p["seq_decoder.0.weight"], p["seq_decoder.0.bias"]))
+    g2 = torch.relu(_lin(g1, p["seq_decoder.2.weight"], p["seq_decoder.2.bias"]))
+    return torch.sigmoid(_lin(g2, p["seq_decoder.4.weight"], p["seq_decoder.4.bias"]))
+
+
+# --------------------------------------------------------------------------
+# loss terms
+# --------------------------------------------------------------------------
+
+def masked_nll(x: Tensor, xhat: Tensor, m: Tensor, x_logvar: float = X_LOGVAR) -> Tensor:
+    """sum(-Normal(xhat*m, exp(lv*m/2)).log_prob(x*m)), src/models/VAE.py:422-423,488-490.
+    Masked-out entries still contribute 0.5*log(2*pi) each."""
+    mf = _as(m, x)
+    lv = x_logvar * mf
+    scale = torch.exp(lv / 2)
+    diff = x * mf - xhat * mf
+    return torch.sum(diff * diff / (2 * scale * scale) + torch.log(scale) + HALF_LOG_2PI)
+
+
+def kl_std_normal(mu: Tensor, logvar: Tensor) -> Tensor:
+    """sum KL(N(mu, e^{lv/2}) || N(0,1)), src/models/VAE.py:476-478."""
+    return 0.5 * torch.sum(torch.exp(logvar) + mu * mu - 1.0 - logvar)
+
+
+def kl_normal_normal(mu_q, lv_q, mu_p, lv_p) -> Tensor:
+    """sum KL(N_q || N_p), src/models/VAE.py:469-474."""
+    var_ratio = torch.exp(lv_q - lv_p)
+    t1 = (mu_q - mu_p) ** 2 / torch.exp(lv_p)
+    return 0.5 * torch.sum(var_ratio + t1 - 1.0 - (lv_q - lv_p))
+
+
+def reg_loss_terms(x, xh_p, mu_p, lv_p, xh_q, mu_q, lv_q, mask, mask_p):
+    mb, mpb = mask.bool(), mask_p.bool()
+    return dict(
+        RE_q=masked_nll(x, xh_q, mb), RE_p=masked_nll(x, xh_p, mpb),
+        KL_q=kl_std_normal(mu_q, lv_q), KL_p=kl_std_normal(mu_p, lv_p),
+        KL_reg=kl_normal_normal(mu_q, lv_q, mu_p, lv_p),
+        RE_d=masked_nll(x, xh_q, mb & ~mpb), RE_imp=masked_nll(x, xh_q, ~mb))
+
+
+def reg_loss(x, xh_p, mu_p, lv_p, xh_q, mu_q, lv_q, mask, mask_p, epoch=1,
+             beta=1.0, alpha=1.0, beta_annealing=False, stage="train"):
+    """Reg_VAE.loss / Reg_EDDI.loss with reg_type='kl_reg', src/models/VAE.py:403-467, 749-817.
+    Returns (train_loss, RE_q/B, RE_q_imputed/B)."""
+    B = x.shape[0]
+    t = reg_loss_terms(x, xh_p, mu_p, lv_p, xh_q, mu_q, lv_q, mask, mask_p)
+    bw = beta * (epoch / BETA_MAX_EPOCH) if beta_annealing else beta
+    loss_q = t["RE_q"] + bw * t["KL_q"]
+    if stage == "evaluate":
+        return loss_q / B, t["RE_q"] / B, t["RE_imp"] / B
+    loss_p = t["RE_p"] + bw * t["KL_p"]
+    loss = loss_q + alpha * (t["KL_reg"] - loss_q + loss_p + t["RE_d"])
+    return loss / B, t["RE_q"] / B, torch.zeros((), dtype=x.dtype)
+
+
+def vanilla_loss(x, xh_q, mu_q, lv_q, mask, epoch=1, beta=1.0, beta_annealing=False):
+    """vanilla_VAE.loss / vanilla_EDDI.loss, src/models/VAE.py:1171-1208, 933-964.
+    Returns (train_loss, RE_q/B, RE_q_imputed/B)."""
+    B = x.shape[0]
+    mb = mask.bool()
+    RE_q = masked_nll(x, xh_q, mb)
+    RE_imp = masked_nll(x, xh_q, ~mb)
+    bw = beta * (epoch / BETA_MAX_EPOCH) if beta_annealing else beta
+    return (RE_q + bw * kl_std_normal(mu_q, lv_q)) / B, RE_q / B, RE_imp / B
+
+
+# --------------------------------------------------------------------------
+# whole training step (forward + loss + backward) and Adam
+# --------------------------------------------------------------------------
+
+def trainable_names(p: Params) -> Sequence[str]:
+    return [k for k in p if not k.startswith("prior_")]
+
+
+def train_step(p: Params, x, mask, mask_p, eps_q, eps_p, alpha=1.0, beta=1.0,
+               regularised=True, collapsed=False):
+    """One reference step: model.forward -> model.loss -> backward
+    (src/experiment_main/train.py:87-116).  Returns (train_loss, grads dict, aux)."""
+    names = trainable_names(p)
+    q = {k: (v.detach().clone().requires_grad_(True) if k in names else v) for k, v in p.items()}
+    mu_q, lv_q = encoder_stats(q, x, mask, collapsed)
+    xh_q = decoder(q, reparam(mu_q, lv_q, eps_q))
+    if regularised:
+        mu_p, lv_p = encoder_stats(q, x, mask_p, collapsed)
+        xh_p = decoder(q, reparam(mu_p, lv_p, eps_p))
+        loss, _, _ = reg_loss(x, xh_p, mu_p, lv_p, xh_q, mu_q, lv_q, mask, mask_p,
+                              beta=beta, alpha=alpha)
+        aux = dict(mu_q=mu_q, lv_q=lv_q, xh_q=xh_q, mu_p=mu_p, lv_p=lv_p, xh_p=xh_p)
+    else:
+        loss, _, _ = vanilla_loss(x, xh_q, mu_q, lv_q, mask, beta=beta)
+        aux = dict(mu_q=mu_q, lv_q=lv_q, xh_q=xh_q)
+    grads = torch.autograd.grad(loss, [q[k] for k in names], allow_unused=True)
+    gd = {k: (g if g is not None else torch.zeros_like(q[k])) for k, g in zip(names, grads)}
+    return loss.detach(), gd, {k: v.detach() for k, v in aux.items()}
+
+
+def adam_step(param, grad, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam defaults (src/experiment_main/train.py:21), single-tensor form."""
+    m = b1 * m + (1 - b1) * grad
+    v = b2 * v + (1 - b2) * grad * grad
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    return param - (lr / bc1) * (m / denom), m, v
+
+
+# --------------------------------------------------------------------------
+# evaluation metrics
+# --------------------------------------------------------------------------
+
+def rmse_unobserved(xh_q, x, mask):
+    """src/experiment_main/evaluate.py:232-234."""
+    nm = ~mask.bool()
+    return torch.sqrt(torch.sum((xh_q * nm - x * nm) ** 2) / torch.sum(nm))
+
+
+# --------------------------------------------------------------------------
+# active-selection reward
+# --------------------------------------------------------------------------
+
+def _reward_kl(mu_i, lv_i, mu, lv):
+    """0.5*sum((mu_i-mu)^2/std + var_i/var - 1 - lv_i + lv), src/experiment_main/evaluate.py:582-583,631-632.
+    NOTE divides by std, not variance."""
+    return 0.5 * torch.sum((mu_i - mu) ** 2 / torch.exp(lv / 2)
+                           + torch.exp(lv_i) / torch.exp(lv) - 1.0 - lv_i + lv, 1)
+
+
+def reward_chain_as_written(p: Params, i: int, x, mask, im, loc) -> Tensor:
+    """R_lindley_chain with chaini_I / chaini_II exactly as the reference loops
+    (src/experiment_main/evaluate.py:514-634): 4 full encoder calls per sample."""
+    M = im.shape[0]
+    temp_x = x.clone()
+    acc = torch.zeros(len(loc), dtype=x.dtype)
+    mloc = mask[loc].to(x.dtype)
+    for m in range(M):
+        temp_x[loc, i] = im[m, loc, i]
+        xs = temp_x[loc]
+        m0 = mloc.clone()
+        mu, lv = encoder_stats(p, xs, m0)
+        m0[:, i] = 1
+        mu_i, lv_i = encoder_stats(p, xs, m0)
+        acc = acc + _reward_kl(mu_i, lv_i, mu, lv)
+        temp_x[loc, -1] = im[m, loc, -1]
+        xs = temp_x[loc]
+        m1 = mloc.clone()
+        m1[:, -1] = 1
+        mu, lv = encoder_stats(p, xs, m1)
+        m1[:, i] = 1
+        mu_i, lv_i = encoder_stats(p, xs, m1)
+        acc = acc - _reward_kl(mu_i, lv_i, mu, lv)
+    return acc / M
+
+
+def reward_all(p: Params, x, mask, im, incremental: bool = True) -> Tensor:
+    """Reward matrix R[N, D-1] for one active-learning step: candidates with
+    mask[n,u]==0 get the chain reward, the rest keep -1e4
+    (src/experiment_main/evaluate.py:391,416-425).  `incremental=True` uses the
+    rank-1 restatement of SURVEY.md A.5 (what the CUDA kernel implements)."""
+    M, N, D = im.shape
+    R = torch.full((N, D - 1), -1e4, dtype=x.dtype)
+    maskf = mask.to(x.dtype)
+    if not incremental:
+        for u in range(D - 1):
+            loc = torch.nonzero(maskf[:, u] == 0).flatten()
+            if len(loc):
+                R[loc, u] = reward_chain_as_written(p, u, x, maskf, im, loc)
+        return R
+    pnp = is_pnp(p)
+    if pnp:
+        A, C = pnp_collapse(p)
+        base_in = pnp_aggregate(p, x, maskf, collapsed=True)       # agg0 [N,K]
+        tail = lambda h: pnp_tail(p, h)
+        delta = lambda v, col: torch.relu(v.unsqueeze(1) * A[col].unsqueeze(0) + C[col].unsqueeze(0))
+    else:
+        W1 = p["seq_encoder.0.weight"]
+        base_in = mlp_first_layer_pre(p, x, maskf)                  # h0 [N,100]
+        tail = lambda h: mlp_tail(p, h)
+        delta = lambda v, col: v.unsqueeze(1) * W1[:, col].unsqueeze(0)
+    mu0, lv0 = tail(base_in)
+    acc = torch.zeros(N, D - 1, dtype=x.dtype)
+    for m in range(M):
+        hT = base_in + delta(im[m, :, D - 1], D - 1)
+        muT, lvT = tail(hT)
+        for u in range(D - 1):
+            du = delta(im[m, :, u], u)
+            mu_a, lv_a = tail(base_in + du)
+            mu_b, lv_b = tail(hT + du)
+            acc[:, u] = acc[:, u] + _reward_kl(mu_a, lv_a, mu0, lv0)
+            acc[:, u] = acc[:, u] - _reward_kl(mu_b, lv_b, muT, lvT)
+    sel = maskf[:, :D - 1] == 0
+    R[sel] = (acc / M)[sel]
+    return R

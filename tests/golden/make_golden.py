@@ -1,0 +1,195 @@
+"""Generate golden fixtures from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference
+
+The reference has no tests, seeds or golden vectors of its own,
+so parity is pinned against the reference *executed here*: this script imports
+`src.models.VAE` / `src.experiment_main.evaluate` from /root/reference, fixes
+seeds, records every input, every N(0,1) draw (`_standard_normal`) and every
+output, and writes small `.pt` files next to itself.  The fixtures travel to the
+GPU box; /root/reference does not.  Nothing under tests/ or the package reads
+/root/reference at test time.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("PCVAE_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+    # matplotlib is imported (unused) at src/experiment_main/evaluate.py:10 and is not installed
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", mpl.pyplot)
+    import src.models.VAE as V
+    import src.experiment_main.evaluate as E
+    return V, E
+
+
+class NoiseTape:
+    """Records every standard-normal draw Normal.rsample makes (order matters)."""
+
+    def __init__(self):
+        import torch.distributions.normal as tdn
+        self.tdn = tdn
+        self.orig = tdn._standard_normal
+        self.draws = []
+
+    def __enter__(self):
+        def rec(shape, dtype, device):
+            e = self.orig(shape, dtype=dtype, device=device)
+            self.draws.append(e.clone())
+            return e
+        self.tdn._standard_normal = rec
+        return self
+
+    def __exit__(self, *a):
+        self.tdn._standard_normal = self.orig
+
+
+def sd_clone(model):
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def synth(B, D, seed, missing=0.3, sub=0.3):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, D, generator=g)
+    mask = torch.rand(B, D, generator=g) < (1 - missing)
+    mask_p = mask & (torch.rand(B, D, generator=g) < (1 - sub))
+    return x, mask, mask_p
+
+
+def reg_case(V, cls_name, B, D, K, seed, alpha):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    cls = getattr(V, cls_name)
+    model = cls(D, 500, K, 10, {"batch_size": B, "patience": 100}, "exp", "kl_reg", 1, 10)
+    x, mask, mask_p = synth(B, D, seed + 1)
+    with NoiseTape() as tape:
+        out = model.forward(x, mask, mask_p, stage="train")
+    eps_q, eps_p = tape.draws
+    mean_p, logvar_p, xh_p, lv_p, mean_q, logvar_q, xh_q, lv_q = out
+    _, train_loss = model.loss(x, xh_p, lv_p, mean_p, logvar_p, xh_q, lv_q, mean_q, logvar_q,
+                               mask, mask_p, 1, beta_annealing=False, beta=1.0, alpha=alpha,
+                               alpha_annealing=True, stage="train")
+    model.zero_grad()
+    train_loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        _, ev_loss, negl, negl_imp = model.loss(x, xh_p, lv_p, mean_p, logvar_p, xh_q, lv_q, mean_q,
+                                                logvar_q, mask, mask_p, 1, llh_eval=True, beta=1.0,
+                                                alpha=alpha, stage="evaluate")
+        rmse = torch.sqrt(torch.sum(torch.square(xh_q * ~mask - x * ~mask)) / torch.sum(~mask))
+    return dict(cls=cls_name, D=D, K=K, alpha=alpha, state_dict=sd_clone(model), x=x, mask=mask,
+                mask_p=mask_p, eps_q=eps_q, eps_p=eps_p,
+                mean_p=mean_p.detach(), logvar_p=logvar_p.detach(), xh_p=xh_p.detach(),
+                mean_q=mean_q.detach(), logvar_q=logvar_q.detach(), xh_q=xh_q.detach(),
+                x_logvar=lv_q.clone(), train_loss=train_loss.detach(), grads=grads,
+                eval_loss=ev_loss, negl=negl, negl_imp=negl_imp, rmse=rmse)
+
+
+def vanilla_case(V, cls_name, B, D, K, seed):
+    torch.manual_seed(seed)
+    cls = getattr(V, cls_name)
+    model = cls(D, 500, K, 10, {"batch_size": B, "patience": 100}, "exp", 1, 10)
+    x, mask, _ = synth(B, D, seed + 1)
+    maskf = mask * torch.ones(x.shape)            # train.py:58,97 -> float32 mask
+    with NoiseTape() as tape:
+        mean_q, logvar_q, xh_q, lv = model.forward(x, maskf)
+    (eps_q,) = tape.draws
+    _, train_loss = model.loss(x, xh_q, lv, mean_q, logvar_q, 1, maskf, beta_annealing=False,
+                               beta=1.0, stage="train")
+    model.zero_grad()
+    train_loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        _, ev_loss, negl, negl_imp = model.loss(x, xh_q, lv, mean_q, logvar_q, 1, mask, llh_eval=True,
+                                                beta=1.0, stage="evaluate")
+    return dict(cls=cls_name, D=D, K=K, state_dict=sd_clone(model), x=x, mask=mask, eps_q=eps_q,
+                mean_q=mean_q.detach(), logvar_q=logvar_q.detach(), xh_q=xh_q.detach(),
+                train_loss=train_loss.detach(), grads=grads, eval_loss=ev_loss, negl=negl,
+                negl_imp=negl_imp)
+
+
+def train_traj_case(V, cls_name, B, D, K, seed, steps):
+    """A few full reference steps (forward, loss, backward, Adam) with recorded noise."""
+    torch.manual_seed(seed)
+    cls = getattr(V, cls_name)
+    model = cls(D, 500, K, 10, {"batch_size": B, "patience": 100}, "exp", "kl_reg", 1, 10)
+    sd0 = sd_clone(model)
+    opt = torch.optim.Adam(model.parameters(), lr=0.001)
+    xs, ms, mps, eqs, eps_, losses = [], [], [], [], [], []
+    for s in range(steps):
+        x, mask, mask_p = synth(B, D, seed + 10 + s)
+        with NoiseTape() as tape:
+            out = model.forward(x, mask, mask_p, stage="train")
+        mean_p, logvar_p, xh_p, lv_p, mean_q, logvar_q, xh_q, lv_q = out
+        _, loss = model.loss(x, xh_p, lv_p, mean_p, logvar_p, xh_q, lv_q, mean_q, logvar_q, mask,
+                             mask_p, s + 1, beta=1.0, alpha=1.0, stage="train")
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        xs.append(x); ms.append(mask); mps.append(mask_p)
+        eqs.append(tape.draws[0]); eps_.append(tape.draws[1]); losses.append(loss.detach())
+    return dict(cls=cls_name, D=D, K=K, state_dict0=sd0, state_dict_end=sd_clone(model),
+                x=torch.stack(xs), mask=torch.stack(ms), mask_p=torch.stack(mps),
+                eps_q=torch.stack(eqs), eps_p=torch.stack(eps_), losses=torch.stack(losses))
+
+
+def reward_case(V, E, cls_name, N, D, K, M, seed, n_selected):
+    torch.manual_seed(seed)
+    cls = getattr(V, cls_name)
+    model = cls(D, 500, K, 10, {"batch_size": 64, "patience": 100}, "exp", "kl_reg", 1, 10)
+    # make the encoder less degenerate than a fresh init so rewards are not ~0
+    with torch.no_grad():
+        for prm in model.parameters():
+            prm.mul_(2.0)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(N, D, generator=g)
+    mask = torch.zeros(N, D)
+    for n in range(N):                               # rows have different selected sets
+        k = int(torch.randint(0, n_selected + 1, (1,), generator=g))
+        sel = torch.randperm(D - 1, generator=g)[:k]
+        mask[n, sel] = 1.0
+    mask_p = torch.zeros(N, D)
+    with torch.no_grad():
+        with NoiseTape() as tape:
+            ims = [model.forward(x, mask, mask_p, stage="evaluate")[6] for _ in range(M)]
+        im = torch.stack(ims, 0)
+        R = -1e4 * torch.ones(N, D - 1)
+        for u in range(D - 1):
+            loc = np.where(mask[:, u] == 0)[0]
+            R[loc, u] = E.R_lindley_chain(u, x, mask, M, model, im, loc).float()
+    return dict(cls=cls_name, D=D, K=K, M=M, state_dict=sd_clone(model), x=x, mask=mask, im=im,
+                im_eps_q=torch.stack(tape.draws[0::2]), R=R)
+
+
+def main():
+    V, E = _import_reference()
+    torch.set_num_threads(1)
+    fx = {}
+    fx["reg_vae_b64_d13"] = reg_case(V, "Reg_VAE", 64, 13, 20, 0, 1.0)
+    fx["reg_vae_b37_d20_a05"] = reg_case(V, "Reg_VAE", 37, 20, 20, 1, 0.5)
+    fx["reg_eddi_b64_d13_k20"] = reg_case(V, "Reg_EDDI", 64, 13, 20, 2, 1.0)
+    fx["reg_eddi_b33_d7_k10_a07"] = reg_case(V, "Reg_EDDI", 33, 7, 10, 3, 0.7)
+    fx["vanilla_vae_b64_d13"] = vanilla_case(V, "vanilla_VAE", 64, 13, 20, 4)
+    fx["vanilla_eddi_b64_d13_k20"] = vanilla_case(V, "vanilla_EDDI", 64, 13, 20, 5)
+    fx["traj_reg_vae_b32_d13"] = train_traj_case(V, "Reg_VAE", 32, 13, 20, 6, 4)
+    fx["traj_reg_eddi_b32_d13_k10"] = train_traj_case(V, "Reg_EDDI", 32, 13, 10, 7, 4)
+    fx["reward_reg_vae_n24_d8_m5"] = reward_case(V, E, "Reg_VAE", 24, 8, 20, 5, 8, 3)
+    fx["reward_reg_eddi_n24_d8_k10_m5"] = reward_case(V, E, "Reg_EDDI", 24, 8, 10, 5, 9, 3)
+    for name, d in fx.items():
+        path = os.path.join(HERE, name + ".pt")
+        torch.save(d, path)
+        print(f"{name}: {os.path.getsize(path) / 1024:.1f} KB")
+
+
+if __name__ == "__main__":
+    main()

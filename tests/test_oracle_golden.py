@@ -1,0 +1,95 @@
+"""The oracle (oracle/pcvae_oracle.py) against every golden fixture recorded from the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from oracle import pcvae_oracle as O
+
+RTOL = 1e-4  # north_star: fp32 losses / ELBO / RMSE within 1e-4 relative
+
+
+def close(a, b, rtol=RTOL, atol=1e-6):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+REG = ["reg_vae_b64_d13", "reg_vae_b37_d20_a05", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07"]
+VAN = ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20"]
+
+
+@pytest.mark.parametrize("name", REG)
+@pytest.mark.parametrize("collapsed", [False, True])
+def test_reg_forward_loss_grads(golden, name, collapsed):
+    g = golden(name)
+    p = g["state_dict"]
+    mu_q, lv_q = O.encoder_stats(p, g["x"], g["mask"], collapsed)
+    mu_p, lv_p = O.encoder_stats(p, g["x"], g["mask_p"], collapsed)
+    close(mu_q, g["mean_q"]); close(lv_q, g["logvar_q"])
+    close(mu_p, g["mean_p"]); close(lv_p, g["logvar_p"])
+    xh_q = O.decoder(p, O.reparam(mu_q, lv_q, g["eps_q"]))
+    xh_p = O.decoder(p, O.reparam(mu_p, lv_p, g["eps_p"]))
+    close(xh_q, g["xh_q"]); close(xh_p, g["xh_p"])
+    assert abs(float(g["x_logvar"]) - O.X_LOGVAR) < 1e-6
+    loss, grads, _ = O.train_step(p, g["x"], g["mask"], g["mask_p"], g["eps_q"], g["eps_p"],
+                                  alpha=g["alpha"], collapsed=collapsed)
+    close(loss, g["train_loss"])
+    for k, ref in g["grads"].items():
+        torch.testing.assert_close(grads[k], ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max() + 1e-3))
+    ev, negl, negl_imp = O.reg_loss(g["x"], xh_p, mu_p, lv_p, xh_q, mu_q, lv_q, g["mask"], g["mask_p"],
+                                    alpha=g["alpha"], stage="evaluate")
+    close(ev, g["eval_loss"]); close(negl, g["negl"]); close(negl_imp, g["negl_imp"])
+    close(O.rmse_unobserved(xh_q, g["x"], g["mask"]), g["rmse"])
+
+
+@pytest.mark.parametrize("name", VAN)
+def test_vanilla(golden, name):
+    g = golden(name)
+    p = g["state_dict"]
+    loss, grads, aux = O.train_step(p, g["x"], g["mask"], None, g["eps_q"], None, regularised=False)
+    close(aux["mu_q"], g["mean_q"]); close(aux["xh_q"], g["xh_q"])
+    close(loss, g["train_loss"])
+    for k, ref in g["grads"].items():
+        torch.testing.assert_close(grads[k], ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max() + 1e-3))
+    ev, negl, negl_imp = O.vanilla_loss(g["x"], aux["xh_q"], aux["mu_q"], aux["lv_q"], g["mask"])
+    close(ev, g["eval_loss"]); close(negl, g["negl"]); close(negl_imp, g["negl_imp"])
+
+
+@pytest.mark.parametrize("name", ["traj_reg_vae_b32_d13", "traj_reg_eddi_b32_d13_k10"])
+def test_training_trajectory(golden, name):
+    g = golden(name)
+    p = {k: v.clone() for k, v in g["state_dict0"].items()}
+    names = O.trainable_names(p)
+    m = {k: torch.zeros_like(p[k]) for k in names}
+    v = {k: torch.zeros_like(p[k]) for k in names}
+    for s in range(g["x"].shape[0]):
+        loss, grads, _ = O.train_step(p, g["x"][s], g["mask"][s], g["mask_p"][s], g["eps_q"][s], g["eps_p"][s])
+        close(loss, g["losses"][s])
+        for k in names:
+            p[k], m[k], v[k] = O.adam_step(p[k], grads[k], m[k], v[k], s + 1)
+    for k in names:
+        torch.testing.assert_close(p[k], g["state_dict_end"][k], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["reward_reg_vae_n24_d8_m5", "reward_reg_eddi_n24_d8_k10_m5"])
+@pytest.mark.parametrize("incremental", [False, True])
+def test_reward(golden, name, incremental):
+    g = golden(name)
+    R = O.reward_all(g["state_dict"], g["x"], g["mask"], g["im"], incremental=incremental)
+    ref = g["R"]
+    sel = g["mask"][:, :-1] != 0
+    assert torch.all(R[sel] == -1e4) and torch.all(ref[sel] == -1e4)
+    # reward is a cancellation of two KLs: absolute floor per SURVEY.md 7.3 item 2
+    torch.testing.assert_close(R[~sel], ref[~sel], rtol=1e-4, atol=2e-6)
+    assert ref[~sel].abs().max() > 1e-4  # the case is not degenerate
+    # the im fixture is the q-branch decoder mean of the recorded draws
+    p = g["state_dict"]
+    mu, lv = O.encoder_stats(p, g["x"], g["mask"])
+    im0 = O.decoder(p, O.reparam(mu, lv, g["im_eps_q"][0]))
+    close(im0, g["im"][0])
+
+
+def test_reward_fp64_agrees_with_fp32_within_floor(golden):
+    g = golden("reward_reg_vae_n24_d8_m5")
+    p64 = {k: v.double() for k, v in g["state_dict"].items()}
+    R64 = O.reward_all(p64, g["x"].double(), g["mask"].double(), g["im"].double())
+    sel = g["mask"][:, :-1] == 0
+    assert (R64[sel].float() - g["R"][sel]).abs().max() < 2e-6
