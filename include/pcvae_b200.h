@@ -1,0 +1,251 @@
+/*
+ * pcvae_b200.h -- C ABI of the B200-native partial-VAE posterior-consistency hot path.
+ *
+ * One shared library (libpcvae_b200.so, built by nvcc for sm_100a only).  The
+ * reference (stschia/VAE-posterior-consistency) has no FFI of its own: its seam is
+ * the Python API of src/models/VAE.py plus the functions of
+ * src/experiment_main/{train,evaluate}.py that call it.  Every entry
+ * point below names the reference code it replaces; INTEGRATION.md shows the
+ * ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C: device pointers, sizes, scalars; no torch types.
+ *  - the caller owns every buffer (inputs, outputs, workspaces); the library keeps
+ *    no device memory.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *    internal synchronisation, no default-stream use; reentrant.
+ *  - return 0 on success, a PCVAE_E* code otherwise; the message of the last
+ *    failure on the calling thread is pcvae_last_error().  Never throws/exits.
+ *  - there is NO CPU fallback and no multi-backend dispatch: a device that is not
+ *    compute capability 10.x yields PCVAE_EDEVICE.
+ *  - fp32 arithmetic throughout (no TF32/BF16); masks are 0/1 valued, either
+ *    uint8 (torch.bool) or float32.
+ *
+ * Flat parameter vector `theta` (and the gradient / Adam vectors of the same
+ * layout): the reference's trainable parameters in state_dict order
+ * (SURVEY.md A.1), each in its nn.Linear [out][in] row-major layout:
+ *   family MLP (Reg_VAE, vanilla_VAE; src/models/VAE.py:366-376):
+ *     seq_encoder.0.{weight[100,D],bias[100]} .2.{[50,100],[50]} .4.{[2L,50],[2L]}
+ *     seq_decoder.0.{[50,L],[50]} .2.{[100,50],[100]} .4.{[D,100],[D]}
+ *   family PNP (Reg_EDDI, vanilla_EDDI; src/models/VAE.py:687-709):
+ *     type_pars1[D,K], type_bias1[D,1], pnp_encoder1.0.{[K,K+2],[K]},
+ *     pnp_encoder2.0.{[100,K],[100]} .2.{[50,100],[50]} .4.{[2L,50],[2L]}, seq_decoder.* as above
+ * L (latent_dim) must be 10 (the reference hard-codes 10 at VAE.py:724).
+ */
+#ifndef PCVAE_B200_H
+#define PCVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define PCVAE_ABI_VERSION 1
+
+enum { PCVAE_OK = 0, PCVAE_EINVAL = 1, PCVAE_EDEVICE = 2, PCVAE_ECUDA = 3, PCVAE_EWORKSPACE = 4 };
+enum { PCVAE_FAMILY_MLP = 0, PCVAE_FAMILY_PNP = 1 };
+enum { PCVAE_MASK_U8 = 0, PCVAE_MASK_F32 = 1 };
+
+/* number of loss partial sums produced by pcvae_dec_loss / pcvae_loss_terms */
+#define PCVAE_NSUMS 8
+/* indices into the sums vector (double[PCVAE_NSUMS]) */
+enum {
+    PCVAE_S_RE_Q = 0,   /* NLL(x, xhat_q; mask)            VAE.py:422-423 */
+    PCVAE_S_RE_P = 1,   /* NLL(x, xhat_p; mask_p)          VAE.py:424-426 */
+    PCVAE_S_KL_Q = 2,   /* KL(q || N(0,1))                 VAE.py:427,476-478 */
+    PCVAE_S_KL_P = 3,   /* KL(p || N(0,1))                 VAE.py:428 */
+    PCVAE_S_KL_REG = 4, /* KL(q || p)                      VAE.py:442,469-474 */
+    PCVAE_S_RE_D = 5,   /* NLL(x, xhat_q; mask & ~mask_p)  VAE.py:444-446 */
+    PCVAE_S_RE_IMP = 6, /* NLL(x, xhat_q; ~mask)           VAE.py:413-414 */
+    PCVAE_S_SSE_UNOBS = 7 /* sum ((xhat_q - x) * ~mask)^2  evaluate.py:232-234 */
+};
+
+typedef struct {
+    int family;      /* PCVAE_FAMILY_* */
+    int obs_dim;     /* D  (1..128) */
+    int emb_dim;     /* K  (PNP only, 1..32) */
+    int latent_dim;  /* L  (must be 10) */
+} pcvae_model;
+
+int pcvae_abi_version(void);
+const char* pcvae_last_error(void);
+
+/* number of floats in theta for a model; -1 on invalid model */
+long pcvae_param_count(const pcvae_model* m);
+/* offsets (in floats) of each parameter tensor in theta, state_dict order; returns the
+ * number of tensors written (12 MLP, 16 PNP) or -1. `offsets` needs room for 17 longs
+ * (the last entry is the total). */
+int pcvae_param_offsets(const pcvae_model* m, long* offsets);
+/* offset of the first decoder parameter (seq_decoder.0.weight) in theta */
+long pcvae_decoder_offset(const pcvae_model* m);
+
+/* ------------------------------------------------------------------------
+ * Encoder forward.  Replaces Reg_VAE.encoder / vanilla_VAE.encoder
+ * (src/models/VAE.py:387-395, 1155-1163) and Reg_EDDI.encoder / vanilla_EDDI.encoder
+ * (VAE.py:719-741, 903-925; PNP embedding in the collapsed form of SURVEY.md A.3).
+ * Up to two "branches" (the q pass on `mask[0]`, the p pass on `mask[1]`,
+ * VAE.py:503-506) share one launch and one read of x.
+ * --------------------------------------------------------------------- */
+typedef struct {
+    pcvae_model model;
+    int rows;               /* B */
+    int n_branch;           /* 1 or 2 */
+    int mask_kind;          /* PCVAE_MASK_* */
+    const float* theta;
+    const float* x;         /* [B][D] */
+    const void* mask[2];    /* [B][D] per branch */
+    const float* eps[2];    /* [B][L] standard-normal draws, or NULL: z = mean (sample=False) */
+    float* mean[2];         /* out [B][L] */
+    float* logvar[2];       /* out [B][L] */
+    float* z[2];            /* out [B][L], may be NULL */
+    float* act_ws;          /* optional: saved hidden activations for pcvae_enc_bwd,
+                               pcvae_enc_act_ws_floats() floats; NULL = do not save */
+    float* pnp_ac;          /* PNP only: workspace 2*D*K floats for the collapsed A,C tables */
+} pcvae_enc_fwd_params;
+
+size_t pcvae_enc_act_ws_floats(const pcvae_model* m, int rows, int n_branch);
+int pcvae_enc_fwd(const pcvae_enc_fwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Encoder backward (autograd of the encoders above, train.py:115): given
+ * dL/dmean, dL/dlogvar per branch and the activations saved by pcvae_enc_fwd,
+ * accumulates per-CTA partial parameter gradients into `grad_partials`
+ * ([pcvae_grid_ctas()][param_count] floats, encoder slice only) -- reduce with
+ * pcvae_reduce_grads.
+ * --------------------------------------------------------------------- */
+typedef struct {
+    pcvae_model model;
+    int rows, n_branch, mask_kind;
+    const float* theta;
+    const float* x;
+    const void* mask[2];
+    const float* act_ws;        /* from pcvae_enc_fwd */
+    const float* d_mean[2];     /* [B][L] */
+    const float* d_logvar[2];   /* [B][L] */
+    const float* pnp_ac;        /* PNP: A,C tables from pcvae_enc_fwd */
+    float* grad_partials;       /* [grid][P] */
+} pcvae_enc_bwd_params;
+int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Decoder (+ loss, + backward).  One kernel, four modes:
+ *  PCVAE_DEC_FWD    z -> xhat                      (decoder(), VAE.py:397-401)
+ *  PCVAE_DEC_BWD    z, d_xhat -> d_z, dW partials  (its autograd)
+ *  PCVAE_DEC_TRAIN  reparameterise, decode both branches, masked Gaussian NLL + KL +
+ *                   posterior-consistency loss, and the backward through the decoder
+ *                   down to d_mean/d_logvar (forward()+loss()+backward() of
+ *                   Reg_VAE/Reg_EDDI/vanilla_*, VAE.py:403-467, 496-507; train.py:87-116)
+ *  PCVAE_DEC_EVAL   loss sums only (stage='evaluate', VAE.py:410-420) and RMSE sums
+ * Loss weights: L = (1-alpha)(RE_q + beta_w KL_q) + alpha (KL_reg + RE_p + beta_w KL_p + RE_d),
+ * gradients are of L * loss_scale (loss_scale = 1/B, VAE.py:452).  vanilla_* = one branch,
+ * alpha = 0.
+ * --------------------------------------------------------------------- */
+enum { PCVAE_DEC_FWD = 0, PCVAE_DEC_BWD = 1, PCVAE_DEC_TRAIN = 2, PCVAE_DEC_EVAL = 3 };
+typedef struct {
+    pcvae_model model;
+    int mode;
+    int rows, n_branch, mask_kind;
+    const float* theta;
+    const float* z[2];          /* [B][L] latent samples per branch (q, p) */
+    float* xhat[2];             /* FWD/EVAL/TRAIN: optional out [B][D] */
+    /* TRAIN / EVAL */
+    const float* x;             /* [B][D] */
+    const void* mask[2];        /* mask, mask_p */
+    const float* mean[2];       /* [B][L] */
+    const float* logvar[2];
+    const float* eps[2];        /* TRAIN: the draws used for z (needed for d_logvar) */
+    float alpha, beta_w, x_logvar, loss_scale;
+    float* sums_partials;       /* [grid][PCVAE_NSUMS] floats */
+    float* d_mean[2];           /* TRAIN out [B][L] */
+    float* d_logvar[2];
+    /* BWD */
+    const float* d_xhat[2];     /* [B][D] */
+    float* d_z[2];              /* BWD out [B][L] */
+    float* grad_partials;       /* TRAIN/BWD: [grid][P], decoder slice only */
+} pcvae_dec_params;
+int pcvae_dec(const pcvae_dec_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Stand-alone loss terms for the module API (`model.loss(...)` called on tensors the
+ * caller already holds; VAE.py:403-467, 749-817, 933-964, 1171-1208).  Computes the
+ * PCVAE_NSUMS sums and, when the d_* pointers are non-NULL, the gradients of
+ * L*loss_scale w.r.t. xhat_q, xhat_p, mean/logvar of q and p.
+ * --------------------------------------------------------------------- */
+typedef struct {
+    int rows, obs_dim, latent_dim, n_branch, mask_kind;
+    const float* x;
+    const void* mask[2];
+    const float* xhat[2];
+    const float* mean[2];
+    const float* logvar[2];
+    float alpha, beta_w, x_logvar, loss_scale;
+    float* sums_partials;       /* [grid][PCVAE_NSUMS] */
+    float* d_xhat[2];
+    float* d_mean[2];
+    float* d_logvar[2];
+} pcvae_loss_params;
+int pcvae_loss_terms(const pcvae_loss_params* p, void* stream);
+
+/* grid size (number of CTAs = number of partial rows) every kernel above uses on the
+ * current device: one persistent CTA per SM. */
+int pcvae_grid_ctas(void);
+
+/* sums[PCVAE_NSUMS] (double, device) = sum over CTAs of sums_partials, plus the
+ * B*D*0.5*log(2*pi) constant every NLL carries. */
+int pcvae_reduce_sums(const float* sums_partials, int grid, int rows, int obs_dim,
+                      double* sums, void* stream);
+/* grad[i] (+)= sum_c grad_partials[c][i] for i in [begin, end) ; deterministic order */
+int pcvae_reduce_grads(const float* grad_partials, int grid, long param_count, long begin,
+                       long end, float* grad, int accumulate, void* stream);
+
+/* torch.optim.Adam (train.py:21; lr 1e-3, betas .9/.999, eps 1e-8, no weight decay, no
+ * amsgrad) on the flat vectors; `step` is the 1-based step count. */
+int pcvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    long n, int step, float lr, float beta1, float beta2, float eps,
+                    void* stream);
+
+/* ------------------------------------------------------------------------
+ * Active-selection information reward for ONE acquisition step, all (row, candidate,
+ * sample) triples in one launch.  Replaces the candidate loop around R_lindley_chain and
+ * chaini_I / chaini_II (src/experiment_main/evaluate.py:416-425, 514-634) using the
+ * incremental-encoder identity of SURVEY.md A.5.  Candidates with mask[n][u] != 0 keep
+ * R = -1e4 (evaluate.py:391).  Precondition (guaranteed by active_learning_func,
+ * evaluate.py:360-361): the target column D-1 is unobserved, mask[:, D-1] == 0.
+ * Rows are independent: shard by rows across GPUs with no collective.
+ * --------------------------------------------------------------------- */
+typedef struct {
+    pcvae_model model;
+    int rows;               /* N */
+    int samples;            /* M */
+    int mask_kind;
+    const float* theta;
+    const float* x;         /* [N][D] */
+    const void* mask;       /* [N][D] */
+    const float* im;        /* [M][N_total][D] imputations (decoder means); row stride below */
+    long im_sample_stride;  /* floats between consecutive samples (N_total*D) */
+    float* R;               /* out [N][D-1] */
+    void* workspace;        /* pcvae_reward_workspace_bytes() */
+    size_t workspace_bytes;
+    float* pnp_ac;          /* PNP: 2*D*K floats */
+} pcvae_reward_params;
+size_t pcvae_reward_workspace_bytes(const pcvae_model* m, int rows, int samples);
+int pcvae_reward_chain(const pcvae_reward_params* p, void* stream);
+
+/* FP32 FFMA peak probe used by bench.py for the roofline denominator: runs `iters`
+ * dependent-chain-free FMA rounds on every SM; returns 0 and the FLOP count in *flops. */
+int pcvae_ffma_probe(float* scratch, int iters, double* flops, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCVAE_B200_H */

@@ -1,0 +1,289 @@
+"""CUDA path (through the C ABI) vs the oracle and the golden fixtures.  Needs a B200:
+run with `pytest -m gpu` under gpurun.  Tolerances: north_star's 1e-4 relative on fp32
+losses / ELBO / RMSE; masks bit-exact (the kernels read the mask bytes as given)."""
+import math
+
+import pytest
+import torch
+
+from oracle import pcvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _mods():
+    from vae_posterior_consistency_b200 import kernels as KR, lib as L
+    return KR, L
+
+
+def fam_of(p, L):
+    return L.FAMILY_PNP if "type_pars1" in p else L.FAMILY_MLP
+
+
+def dims(p):
+    D = p["seq_decoder.4.bias"].numel()
+    K = p["type_pars1"].shape[1] if "type_pars1" in p else 0
+    return D, K
+
+
+def close(a, b, rtol=RTOL, atol=1e-6, msg=""):
+    torch.testing.assert_close(a.detach().cpu().to(b.dtype), b, rtol=rtol, atol=atol, msg=lambda m: f"{msg}: {m}")
+
+
+def grad_close(g, ref, name):
+    g = g.detach().cpu()
+    atol = 2e-5 * float(ref.abs().max() + 1e-3)
+    torch.testing.assert_close(g, ref, rtol=2e-3, atol=atol, msg=lambda m: f"grad {name}: {m}")
+
+
+def engine_for(p):
+    KR, L = _mods()
+    D, K = dims(p)
+    fam = fam_of(p, L)
+    eng = KR.Engine(fam, D, K, "cuda")
+    theta = KR.flatten_params(p, fam, "cuda")
+    return eng, theta, fam
+
+
+REG = ["reg_vae_b64_d13", "reg_vae_b37_d20_a05", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07"]
+VAN = ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20"]
+
+
+@pytest.mark.parametrize("name", REG)
+def test_golden_reg_forward_and_fused_step(golden, name):
+    KR, L = _mods()
+    g = golden(name)
+    p = g["state_dict"]
+    eng, theta, fam = engine_for(p)
+    cu = lambda t: t.cuda()
+    x, mask, mask_p = cu(g["x"]), cu(g["mask"]), cu(g["mask_p"])
+    eq, ep = cu(g["eps_q"]), cu(g["eps_p"])
+    mean, logvar, z, ws = eng.enc_fwd(theta, x, [mask, mask_p], [eq, ep], save=True)
+    close(mean[0], g["mean_q"], msg="mean_q"); close(logvar[0], g["logvar_q"], msg="logvar_q")
+    close(mean[1], g["mean_p"], msg="mean_p"); close(logvar[1], g["logvar_p"], msg="logvar_p")
+    xh = eng.dec(L.DEC_FWD, theta, z)["xhat"]
+    close(xh[0], g["xh_q"], msg="xh_q"); close(xh[1], g["xh_p"], msg="xh_p")
+    # fused step: loss + all parameter gradients vs the reference's autograd
+    B = x.shape[0]
+    tr = KR.FusedTrainer(fam, eng.D, eng.K, theta.clone(), regularised=True, alpha=g["alpha"])
+    sums = tr.forward_backward(x, mask, mask_p, eq, ep)
+    loss = KR.loss_from_sums(sums, B, g["alpha"], 1.0, True)
+    close(loss.float(), g["train_loss"], msg="train_loss")
+    grads = KR.unflatten_params(tr.grad, fam, eng.D, eng.K)
+    for k, ref in g["grads"].items():
+        grad_close(grads[k], ref, k)
+    # evaluate-stage sums
+    eng.dec(L.DEC_EVAL, theta, [z[0]], x=x, masks=[mask], mean=[mean[0]], logvar=[logvar[0]])
+    s = eng.reduce_sums(B).cpu()
+    close(((s[L.S_RE_Q] + s[L.S_KL_Q]) / B).float(), g["eval_loss"], msg="eval_loss")
+    close((s[L.S_RE_Q] / B).float(), g["negl"], msg="negl")
+    close((s[L.S_RE_IMP] / B).float(), g["negl_imp"], msg="negl_imp")
+    n_unobs = (~g["mask"]).sum()
+    close(torch.sqrt(s[L.S_SSE_UNOBS] / n_unobs).float(), g["rmse"], msg="rmse")
+
+
+@pytest.mark.parametrize("name", VAN)
+def test_golden_vanilla_fused_step(golden, name):
+    KR, L = _mods()
+    g = golden(name)
+    p = g["state_dict"]
+    eng, theta, fam = engine_for(p)
+    x, eq = g["x"].cuda(), g["eps_q"].cuda()
+    maskf = (g["mask"] * torch.ones(g["x"].shape)).cuda()          # float32 mask, train.py:58,97
+    tr = KR.FusedTrainer(fam, eng.D, eng.K, theta.clone(), regularised=False)
+    sums = tr.forward_backward(x, maskf, None, eq, None)
+    loss = KR.loss_from_sums(sums, x.shape[0], 0.0, 1.0, False)
+    close(loss.float(), g["train_loss"], msg="train_loss")
+    grads = KR.unflatten_params(tr.grad, fam, eng.D, eng.K)
+    for k, ref in g["grads"].items():
+        grad_close(grads[k], ref, k)
+
+
+@pytest.mark.parametrize("name", ["traj_reg_vae_b32_d13", "traj_reg_eddi_b32_d13_k10"])
+def test_golden_training_trajectory_with_adam(golden, name):
+    KR, L = _mods()
+    g = golden(name)
+    p = g["state_dict0"]
+    eng, theta, fam = engine_for(p)
+    tr = KR.FusedTrainer(fam, eng.D, eng.K, theta, regularised=True, alpha=1.0)
+    for s in range(g["x"].shape[0]):
+        loss = tr.step(g["x"][s].cuda(), g["mask"][s].cuda(), g["mask_p"][s].cuda(), g["eps_q"][s].cuda(),
+                       g["eps_p"][s].cuda())
+        close(loss.float(), g["losses"][s], msg=f"loss step {s}")
+    end = KR.unflatten_params(tr.theta, fam, eng.D, eng.K)
+    for k, v in end.items():
+        torch.testing.assert_close(v.cpu(), g["state_dict_end"][k], rtol=1e-3, atol=1e-5, msg=lambda m: f"{k}: {m}")
+
+
+def rand_case(family, B, D, K, seed, mask_float=False):
+    p = O.init_params(family, D, K, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    x = torch.rand(B, D, generator=g)
+    mask = torch.rand(B, D, generator=g) < 0.7
+    mask_p = mask & (torch.rand(B, D, generator=g) < 0.7)
+    eq, ep = torch.randn(B, 10, generator=g), torch.randn(B, 10, generator=g)
+    if mask_float:
+        mask, mask_p = mask.float(), mask_p.float()
+    return p, x, mask, mask_p, eq, ep
+
+
+SHAPES = [("mlp", 1, 2, 0), ("mlp", 63, 13, 0), ("mlp", 65, 50, 0), ("mlp", 200, 100, 0), ("mlp", 130, 101, 0),
+          ("mlp", 70, 128, 0), ("pnp", 1, 2, 10), ("pnp", 65, 13, 20), ("pnp", 200, 100, 20), ("pnp", 97, 50, 7),
+          ("pnp", 64, 128, 32)]
+
+
+@pytest.mark.parametrize("family,B,D,K", SHAPES)
+@pytest.mark.parametrize("alpha", [1.0, 0.3])
+def test_fused_step_vs_oracle_random_shapes(family, B, D, K, alpha):
+    KR, L = _mods()
+    p, x, mask, mask_p, eq, ep = rand_case(family, B, D, K, seed=B + D)
+    eng, theta, fam = engine_for(p)
+    tr = KR.FusedTrainer(fam, D, K, theta, regularised=True, alpha=alpha, beta_w=0.7)
+    sums = tr.forward_backward(x.cuda(), mask.cuda(), mask_p.cuda(), eq.cuda(), ep.cuda())
+    loss = KR.loss_from_sums(sums, B, alpha, 0.7, True)
+    ref_loss, ref_grads, aux = O.train_step(p, x, mask, mask_p, eq, ep, alpha=alpha, beta=0.7)
+    close(loss.float(), ref_loss, msg="loss")
+    grads = KR.unflatten_params(tr.grad, fam, D, K)
+    for k in O.trainable_names(p):
+        grad_close(grads[k], ref_grads[k], k)
+
+
+@pytest.mark.parametrize("family,B,D,K", [("mlp", 100, 20, 0), ("pnp", 100, 20, 10)])
+def test_modular_ops_vs_oracle(family, B, D, K):
+    """decoder backward from an arbitrary d_xhat, encoder backward from arbitrary d_mean/d_logvar,
+    and the stand-alone loss kernel (what the nn.Module API composes)."""
+    KR, L = _mods()
+    p, x, mask, mask_p, eq, ep = rand_case(family, B, D, K, seed=5, mask_float=(family == "pnp"))
+    eng, theta, fam = engine_for(p)
+    g = torch.Generator().manual_seed(9)
+    names = O.trainable_names(p)
+    q = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in p.items()}
+    mu, lv = O.encoder_stats(q, x, mask, collapsed=True)
+    z = O.reparam(mu, lv, eq)
+    xh = O.decoder(q, z)
+    w_xh, w_mu, w_lv = torch.randn(B, D, generator=g), torch.randn(B, 10, generator=g), torch.randn(B, 10, generator=g)
+    obj = (xh * w_xh).sum() + (mu * w_mu).sum() + (lv * w_lv).sum()
+    ref = dict(zip(names, torch.autograd.grad(obj, [q[k] for k in names], allow_unused=True)))
+    # CUDA: enc_fwd -> dec BWD with d_xhat = w_xh -> d_z; chain to d_mean/d_logvar; enc_bwd
+    xc, mc = x.cuda(), mask.cuda()
+    mean, logvar, zc, ws = eng.enc_fwd(theta, xc, [mc], [eq.cuda()], save=True)
+    close(zc[0], z.detach(), msg="z")
+    out = eng.dec(L.DEC_BWD, theta, zc, d_xhat=[w_xh.cuda()])
+    dz = out["d_z"][0]
+    d_mean = dz + w_mu.cuda()
+    d_logvar = dz * 0.5 * torch.exp(0.5 * logvar[0]) * eq.cuda() + w_lv.cuda()
+    eng.enc_bwd(theta, xc, [mc], ws, [d_mean], [d_logvar])
+    grad = torch.zeros_like(theta)
+    eng.reduce_grads(grad)
+    grads = KR.unflatten_params(grad, fam, D, K)
+    for k in names:
+        grad_close(grads[k], ref[k] if ref[k] is not None else torch.zeros_like(p[k]), k)
+    # stand-alone loss terms + gradients
+    mu_p, lv_p = O.encoder_stats(p, x, mask_p, collapsed=True)
+    xh_p = O.decoder(p, O.reparam(mu_p, lv_p, ep))
+    leaves = [t.detach().clone().requires_grad_(True) for t in (xh_p, mu_p, lv_p, xh.detach(), mu.detach(), lv.detach())]
+    loss, _, _ = O.reg_loss(x, leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[5], mask, mask_p,
+                            beta=0.9, alpha=0.6)
+    rg = torch.autograd.grad(loss, leaves)
+    sums, d_xhat, d_mean2, d_logvar2 = eng.loss_terms(
+        xc, [mc, mask_p.cuda()], [leaves[3].detach().cuda(), leaves[0].detach().cuda()],
+        [leaves[4].detach().cuda(), leaves[1].detach().cuda()], [leaves[5].detach().cuda(), leaves[2].detach().cuda()],
+        alpha=0.6, beta_w=0.9, loss_scale=1.0 / B, want_grads=True)
+    close(KR.loss_from_sums(sums, B, 0.6, 0.9, True).float(), loss.detach(), msg="loss_terms loss")
+    for got, want, nm in [(d_xhat[1], rg[0], "d_xh_p"), (d_mean2[1], rg[1], "d_mu_p"), (d_logvar2[1], rg[2], "d_lv_p"),
+                          (d_xhat[0], rg[3], "d_xh_q"), (d_mean2[0], rg[4], "d_mu_q"), (d_logvar2[0], rg[5], "d_lv_q")]:
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-7, msg=lambda m: f"{nm}: {m}")
+
+
+def test_empty_batch_is_a_no_op():
+    KR, L = _mods()
+    p = O.init_params("mlp", 13)
+    eng, theta, fam = engine_for(p)
+    x = torch.zeros(0, 13, device="cuda")
+    mean, logvar, z, _ = eng.enc_fwd(theta, x, [torch.zeros(0, 13, dtype=torch.bool, device="cuda")])
+    assert mean[0].shape == (0, 10) and z[0].shape == (0, 10)        # VAE.py:723-724 empty guard
+
+
+@pytest.mark.parametrize("name", ["reward_reg_vae_n24_d8_m5", "reward_reg_eddi_n24_d8_k10_m5"])
+def test_golden_reward(golden, name):
+    KR, L = _mods()
+    g = golden(name)
+    eng, theta, fam = engine_for(g["state_dict"])
+    R, _ = eng.reward(theta, g["x"].cuda(), g["mask"].cuda(), g["im"].cuda())
+    R = R.cpu()
+    ref = g["R"]
+    sel = g["mask"][:, :-1] != 0
+    assert torch.all(R[sel] == -1e4)
+    torch.testing.assert_close(R[~sel], ref[~sel], rtol=1e-4, atol=2e-6)
+    # selection order equal except where the reward gap is below tolerance
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 1e-5
+    assert torch.equal(R.argmax(1)[decided], ref.argmax(1)[decided])
+
+
+@pytest.mark.parametrize("family,N,D,K,M", [("mlp", 150, 20, 0, 7), ("pnp", 150, 20, 10, 7), ("mlp", 70, 101, 0, 3),
+                                            ("pnp", 40, 101, 20, 2), ("mlp", 5, 2, 0, 1)])
+def test_reward_vs_oracle_random(family, N, D, K, M):
+    KR, L = _mods()
+    p = O.init_params(family, D, K, seed=N + D)
+    p = {k: (v * 2.0 if v.dtype == torch.float32 and not k.startswith("prior") else v) for k, v in p.items()}
+    g = torch.Generator().manual_seed(N)
+    x = torch.rand(N, D, generator=g)
+    mask = (torch.rand(N, D, generator=g) < 0.4).float()
+    mask[:, -1] = 0
+    im = torch.rand(M, N, D, generator=g)
+    eng, theta, fam = engine_for(p)
+    R, _ = eng.reward(theta, x.cuda(), mask.cuda(), im.cuda())
+    ref = O.reward_all(p, x, mask, im, incremental=True)
+    ref64 = O.reward_all({k: v.double() for k, v in p.items()}, x.double(), mask.double(), im.double())
+    sel = mask[:, :-1] != 0
+    assert torch.all(R.cpu()[sel] == -1e4)
+    # both fp32 evaluations must sit within the fp32 noise floor of the fp64 value
+    err_cuda = (R.cpu()[~sel].double() - ref64[~sel]).abs().max()
+    err_ref = (ref[~sel].double() - ref64[~sel]).abs().max()
+    scale = ref64[~sel].abs().max()
+    assert err_cuda <= max(4 * err_ref, 1e-4 * scale + 2e-6), (err_cuda, err_ref, scale)
+
+
+def test_reward_is_row_shardable_bit_exact():
+    """Rows are independent: evaluating two row blocks separately must reproduce the single
+    call bit for bit (what the multi-GPU sharding relies on)."""
+    KR, L = _mods()
+    p = O.init_params("mlp", 20, seed=3)
+    g = torch.Generator().manual_seed(1)
+    N, D, M = 333, 20, 6
+    x = torch.rand(N, D, generator=g).cuda()
+    mask = (torch.rand(N, D, generator=g) < 0.3).float()
+    mask[:, -1] = 0
+    mask = mask.cuda()
+    im = torch.rand(M, N, D, generator=g).cuda()
+    eng, theta, fam = engine_for(p)
+    R, _ = eng.reward(theta, x, mask, im)
+    cut = 140
+    Ra, _ = eng.reward(theta, x[:cut], mask[:cut], im[:, :cut].contiguous())
+    Rb, _ = eng.reward(theta, x[cut:], mask[cut:], im[:, cut:].contiguous())
+    assert torch.equal(R, torch.cat([Ra, Rb]))
+
+
+def test_large_batch_properties():
+    """BASELINE cfg4 shape (batch 65536 x 100): the fused step must be deterministic (two runs
+    bit-identical) and linear in loss_scale; loss must match the oracle on a 4096-row slice."""
+    KR, L = _mods()
+    B, D = 65536, 100
+    p, x, mask, mask_p, eq, ep = rand_case("mlp", B, D, 0, seed=11)
+    eng, theta, fam = engine_for(p)
+    xc, mc, mpc, eqc, epc = x.cuda(), mask.cuda(), mask_p.cuda(), eq.cuda(), ep.cuda()
+    tr = KR.FusedTrainer(fam, D, 0, theta, regularised=True)
+    s1 = tr.forward_backward(xc, mc, mpc, eqc, epc).clone()
+    g1 = tr.grad.clone()
+    s2 = tr.forward_backward(xc, mc, mpc, eqc, epc)
+    assert torch.equal(s1, s2) and torch.equal(g1, tr.grad)
+    n = 4096
+    s3 = tr.forward_backward(xc[:n], mc[:n], mpc[:n], eqc[:n], epc[:n])
+    ref_loss, ref_grads, _ = O.train_step(p, x[:n], mask[:n], mask_p[:n], eq[:n], ep[:n])
+    close(KR.loss_from_sums(s3, n, 1.0, 1.0, True).float(), ref_loss, msg="loss 4096")
+    grads = KR.unflatten_params(tr.grad, fam, D, 0)
+    for k in O.trainable_names(p):
+        grad_close(grads[k], ref_grads[k], k)

@@ -1,0 +1,69 @@
+// Error buffer, flat-parameter layout and device check shared by the C ABI entry points.
+#include "pcvae_internal.cuh"
+
+namespace pcvae {
+
+static thread_local char g_err[512] = "";
+
+char* err_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+bool make_layout(const pcvae_model* m, Layout* L) {
+    if (!m) { fail(PCVAE_EINVAL, "null model"); return false; }
+    if (m->family != PCVAE_FAMILY_MLP && m->family != PCVAE_FAMILY_PNP) { fail(PCVAE_EINVAL, "unknown family %d", m->family); return false; }
+    if (m->obs_dim < 1 || m->obs_dim > MAX_D) { fail(PCVAE_EINVAL, "obs_dim %d outside [1,%d]", m->obs_dim, MAX_D); return false; }
+    if (m->latent_dim != LAT) { fail(PCVAE_EINVAL, "latent_dim must be %d (got %d)", LAT, m->latent_dim); return false; }
+    const int D = m->obs_dim;
+    int K = 0, o = 0;
+    L->fam = m->family; L->D = D;
+    L->E = L->bE = L->We = L->be = 0;
+    if (m->family == PCVAE_FAMILY_PNP) {
+        K = m->emb_dim;
+        if (K < 1 || K > MAX_K) { fail(PCVAE_EINVAL, "emb_dim %d outside [1,%d]", K, MAX_K); return false; }
+        L->E = o; o += D * K;
+        L->bE = o; o += D;
+        L->We = o; o += K * (K + 2);
+        L->be = o; o += K;
+    }
+    L->K = K;
+    const int in1 = (m->family == PCVAE_FAMILY_PNP) ? K : D;
+    L->W1 = o; o += H1 * in1;
+    L->b1 = o; o += H1;
+    L->W2 = o; o += H2 * H1;
+    L->b2 = o; o += H2;
+    L->W3 = o; o += LAT2 * H2;
+    L->b3 = o; o += LAT2;
+    L->W4 = o; o += G1 * LAT;
+    L->b4 = o; o += G1;
+    L->W5 = o; o += G2 * G1;
+    L->b5 = o; o += G2;
+    L->W6 = o; o += D * G2;
+    L->b6 = o; o += D;
+    L->total = o;
+    return true;
+}
+
+int device_ok(int* n_sm) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(PCVAE_EDEVICE, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    static int cached_dev = -1, cached_sm = 0, cached_major = 0;
+    if (dev != cached_dev) {
+        int major = 0, sm = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+        cached_major = major; cached_sm = sm; cached_dev = dev;
+    }
+    if (cached_major != 10) return fail(PCVAE_EDEVICE, "device %d is compute capability %d.x; this library is sm_100a only", dev, cached_major);
+    if (n_sm) *n_sm = cached_sm;
+    return PCVAE_OK;
+}
+
+}  // namespace pcvae

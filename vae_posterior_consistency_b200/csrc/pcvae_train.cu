@@ -1,0 +1,918 @@
+// Training-path kernels: encoder forward, decoder + loss (+ backward), encoder backward,
+// stand-alone loss terms, partial reductions and Adam.  See include/pcvae_b200.h for the
+// reference code each entry point replaces.
+#include "pcvae_internal.cuh"
+
+namespace pcvae {
+
+// ====================================================================================
+// PNP collapsed tables  A[d][j] = We[j][0] + sum_i E[d][i] We[j][1+i],
+//                       C[d][j] = bE[d] We[j][K+1] + be[j]          
+// stored as ac[0..D*K4) = A, ac[D*K4..2*D*K4) = C with K4 = round4(K), pads zero.
+// ====================================================================================
+__global__ void k_pnp_tables(Layout L, const float* __restrict__ theta, float* __restrict__ ac) {
+    const int D = L.D, K = L.K, K4 = round4(K);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * K4; i += gridDim.x * blockDim.x) {
+        const int d = i / K4, j = i - d * K4;
+        float a = 0.f, c = 0.f;
+        if (j < K) {
+            const float* We = theta + L.We + j * (K + 2);
+            a = We[0];
+            for (int q = 0; q < K; ++q) a = fmaf(theta[L.E + d * K + q], We[1 + q], a);
+            c = fmaf(theta[L.bE + d], We[K + 1], theta[L.be + j]);
+        }
+        ac[i] = a;
+        ac[D * K4 + i] = c;
+    }
+}
+
+// dA[d][j] += sum_r t,  dC[d][j] += sum_r t * x   with  t = m * [x A + C > 0] * dagg[j][r]
+template <int TM>
+__device__ __forceinline__ void pnp_embed_bwd(const float* __restrict__ xs, const float* __restrict__ ms,
+                                              const float* __restrict__ dagg_s, const float* __restrict__ A_s,
+                                              const float* __restrict__ C_s, float* __restrict__ dA_s,
+                                              float* __restrict__ dC_s, int D, int K, int K4, int tid) {
+    constexpr int P = TM + 4;
+    const int hw = tid >> 4, hl = tid & 15;
+    const int dl = hl & 3, jl = hl >> 2;
+    const int nbd = (D + 19) / 20, nbj = (K + 19) / 20;
+    for (int blk = hw; blk < nbd * nbj; blk += NT / 16) {
+        const int db = (blk % nbd) * 20, jb = (blk / nbd) * 20;
+        float accA[5][5], accC[5][5], av[5][5], cv[5][5];
+        int dd[5], jj[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { dd[i] = min(db + dl + 4 * i, D - 1); jj[i] = min(jb + jl + 4 * i, K - 1); }
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                accA[i][j] = 0.f; accC[i][j] = 0.f;
+                av[i][j] = A_s[dd[i] * K4 + jj[j]]; cv[i][j] = C_s[dd[i] * K4 + jj[j]];
+            }
+#pragma unroll 1
+        for (int r = 0; r < TM; r += 4) {
+            float4 xv[5], mv[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { xv[i] = lds4(xs + dd[i] * P + r); mv[i] = lds4(ms + dd[i] * P + r); }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float4 g = lds4(dagg_s + jj[j] * P + r);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    float t;
+                    t = (fmaf(xv[i].x, av[i][j], cv[i][j]) > 0.f) ? mv[i].x * g.x : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].x, accA[i][j]);
+                    t = (fmaf(xv[i].y, av[i][j], cv[i][j]) > 0.f) ? mv[i].y * g.y : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].y, accA[i][j]);
+                    t = (fmaf(xv[i].z, av[i][j], cv[i][j]) > 0.f) ? mv[i].z * g.z : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].z, accA[i][j]);
+                    t = (fmaf(xv[i].w, av[i][j], cv[i][j]) > 0.f) ? mv[i].w * g.w : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].w, accA[i][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int d = db + dl + 4 * i;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int q = jb + jl + 4 * j;
+                if (d < D && q < K) { dA_s[d * K4 + q] += accA[i][j]; dC_s[d * K4 + q] += accC[i][j]; }
+            }
+        }
+    }
+}
+
+void pnp_tables_launch(const Layout& L, const float* theta, float* ac, cudaStream_t st) {
+    k_pnp_tables<<<8, 256, 0, st>>>(L, theta, ac);
+}
+
+// ====================================================================================
+// Encoder forward
+// ====================================================================================
+struct EncFwdArgs {
+    Layout L;
+    int B, nbr, mask_kind;
+    const float* theta;
+    const float* x;
+    const void* mask[2];
+    const float* eps[2];
+    float* mean[2];
+    float* logvar[2];
+    float* z[2];
+    float* act_ws;
+    const float* ac;
+};
+
+template <int FAM, int TM>
+__global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int P = TM + 4;
+    const int tid = threadIdx.x;
+    const int D = a.L.D, K = a.L.K, K4 = round4(K);
+    const int IN1 = (FAM == PCVAE_FAMILY_MLP) ? D : K;
+    float* W1_s = smem;
+    float* b1_s = W1_s + IN1 * H1;
+    float* W2_s = b1_s + H1;
+    float* b2_s = W2_s + H1 * H2P;
+    float* W3_s = b2_s + H2P;
+    float* b3_s = W3_s + H2 * LAT2;
+    float* in_s = b3_s + LAT2;            // [D][P]  MLP: x*mask   PNP: x
+    float* h1_s = in_s + D * P;           // [100][P]
+    float* h2_s = h1_s + H1 * P;          // [52][P]
+    float* o_s = h2_s + H2P * P;          // [20][P]
+    float* ms_s = o_s + LAT2 * P;         // PNP [D][P]
+    float* A_s = ms_s + D * P;            // PNP [D][K4]
+    float* C_s = A_s + D * K4;            // PNP [D][K4]
+    float* agg_s = C_s + D * K4;          // PNP [K4][P]
+
+    stage_linear(W1_s, b1_s, a.theta + a.L.W1, a.theta + a.L.b1, IN1, H1, H1, tid);
+    stage_linear(W2_s, b2_s, a.theta + a.L.W2, a.theta + a.L.b2, H1, H2, H2P, tid);
+    stage_linear(W3_s, b3_s, a.theta + a.L.W3, a.theta + a.L.b3, H2, LAT2, LAT2, tid);
+    if (FAM == PCVAE_FAMILY_PNP)
+        for (int i = tid; i < 2 * D * K4; i += NT) A_s[i] = a.ac[i];
+    __syncthreads();
+
+    const int ntiles = (a.B + TM - 1) / TM;
+    const int act_tile = enc_act_feats(FAM, K) * TM;
+    for (int vt = blockIdx.x; vt < ntiles * a.nbr; vt += gridDim.x) {
+        const int br = vt / ntiles, row0 = (vt - br * ntiles) * TM;
+        const float* __restrict__ x = a.x;
+        const void* __restrict__ mk = a.mask[br];
+        for_tile_elems<TM>(D, row0, a.B, tid, [&](int d, int r, bool ok) {
+            float xv = 0.f, mv = 0.f;
+            if (ok) {
+                const long gi = (long)(row0 + r) * D + d;
+                xv = x[gi];
+                mv = load_mask(mk, gi, a.mask_kind);
+            }
+            if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = xv * mv;
+            else { in_s[d * P + r] = xv; ms_s[d * P + r] = mv; }
+        });
+        __syncthreads();
+        if (FAM == PCVAE_FAMILY_PNP) {
+            pnp_embed<TM>(in_s, ms_s, A_s, C_s, agg_s, D, K4, tid);
+            __syncthreads();
+            gemm_fwd<TM, ACT_RELU>(agg_s, W1_s, b1_s, h1_s, K, H1, tid);
+        } else {
+            gemm_fwd<TM, ACT_RELU>(in_s, W1_s, b1_s, h1_s, D, H1, tid);
+        }
+        __syncthreads();
+        gemm_fwd<TM, ACT_RELU>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
+        __syncthreads();
+        gemm_fwd<TM, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
+        __syncthreads();
+        // outputs (row-major [B][L]); reparameterisation z = mean + eps * exp(logvar/2)  (VAE.py:390-392)
+        for (int i = tid; i < TM * LAT; i += NT) {
+            const int r = i / LAT, l = i - r * LAT;
+            if (row0 + r < a.B) {
+                const long gi = (long)(row0 + r) * LAT + l;
+                const float mu = o_s[l * P + r], lv = o_s[(LAT + l) * P + r];
+                a.mean[br][gi] = mu;
+                a.logvar[br][gi] = lv;
+                if (a.z[br]) a.z[br][gi] = a.eps[br] ? fmaf(a.eps[br][gi], expf(lv * 0.5f), mu) : mu;
+            }
+        }
+        if (a.act_ws) {
+            // saved activations, tile-blocked feature-major [feat][TM]: (agg,) h1, h2
+            float* ws = a.act_ws + (long)vt * act_tile;
+            int f0 = 0;
+            if (FAM == PCVAE_FAMILY_PNP) {
+                for (int i = tid; i < K4 * (TM / 4); i += NT) {
+                    const int f = i / (TM / 4), c = i - f * (TM / 4);
+                    sts4(ws + f * TM + 4 * c, lds4(agg_s + f * P + 4 * c));
+                }
+                f0 = K4;
+            }
+            for (int i = tid; i < (H1 + H2P) * (TM / 4); i += NT) {
+                const int f = i / (TM / 4), c = i - f * (TM / 4);
+                const float* src = (f < H1) ? (h1_s + f * P) : (h2_s + (f - H1) * P);
+                sts4(ws + (f0 + f) * TM + 4 * c, lds4(src + 4 * c));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ====================================================================================
+// Encoder backward
+// ====================================================================================
+struct EncBwdArgs {
+    Layout L;
+    int B, nbr, mask_kind;
+    const float* theta;
+    const float* x;
+    const void* mask[2];
+    const float* act_ws;
+    const float* d_mean[2];
+    const float* d_logvar[2];
+    const float* ac;
+    float* gp;   // [grid][P]
+};
+
+template <int FAM, int TM>
+__global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int P = TM + 4;
+    const int tid = threadIdx.x;
+    const int D = a.L.D, K = a.L.K, K4 = round4(K);
+    const int IN1 = (FAM == PCVAE_FAMILY_MLP) ? D : K;
+    float* W2_s = smem;                        // [100][52]
+    float* W3_s = W2_s + H1 * H2P;             // [50][20]
+    float* dW1_s = W3_s + H2 * LAT2;           // [IN1][100]
+    float* db1_s = dW1_s + IN1 * H1;
+    float* dW2_s = db1_s + H1;                 // [100][52]
+    float* db2_s = dW2_s + H1 * H2P;
+    float* dW3_s = db2_s + H2P;                // [50][20]
+    float* db3_s = dW3_s + H2 * LAT2;
+    float* in_s = db3_s + LAT2;                // [D][P]
+    float* h1_s = in_s + D * P;                // [100][P]
+    float* h2_s = h1_s + H1 * P;               // [52][P]
+    float* d3_s = h2_s + H2P * P;              // [20][P]
+    float* ms_s = d3_s + LAT2 * P;             // PNP [D][P]
+    float* agg_s = ms_s + D * P;               // PNP [K4][P]
+    float* W1_s = agg_s + K4 * P;              // PNP [K][100]
+    float* A_s = W1_s + K * H1;                // PNP [D][K4] (A then C)
+    float* C_s = A_s + D * K4;
+    float* dA_s = C_s + D * K4;                // PNP [D][K4] (dA then dC)
+    float* dC_s = dA_s + D * K4;
+
+    stage_linear(W2_s, nullptr, a.theta + a.L.W2, nullptr, H1, H2, H2P, tid);
+    stage_linear(W3_s, nullptr, a.theta + a.L.W3, nullptr, H2, LAT2, LAT2, tid);
+    zero_floats(dW1_s, (int)(in_s - dW1_s), tid);
+    if (FAM == PCVAE_FAMILY_PNP) {
+        stage_linear(W1_s, nullptr, a.theta + a.L.W1, nullptr, K, H1, H1, tid);
+        for (int i = tid; i < 2 * D * K4; i += NT) { A_s[i] = a.ac[i]; dA_s[i] = 0.f; }
+    }
+    __syncthreads();
+
+    const int ntiles = (a.B + TM - 1) / TM;
+    const int act_tile = enc_act_feats(FAM, K) * TM;
+    for (int vt = blockIdx.x; vt < ntiles * a.nbr; vt += gridDim.x) {
+        const int br = vt / ntiles, row0 = (vt - br * ntiles) * TM;
+        const float* __restrict__ x = a.x;
+        const void* __restrict__ mk = a.mask[br];
+        for_tile_elems<TM>(D, row0, a.B, tid, [&](int d, int r, bool ok) {
+            float xv = 0.f, mv = 0.f;
+            if (ok) {
+                const long gi = (long)(row0 + r) * D + d;
+                xv = x[gi];
+                mv = load_mask(mk, gi, a.mask_kind);
+            }
+            if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = xv * mv;
+            else { in_s[d * P + r] = xv; ms_s[d * P + r] = mv; }
+        });
+        {
+            const float* ws = a.act_ws + (long)vt * act_tile;
+            int f0 = 0;
+            if (FAM == PCVAE_FAMILY_PNP) {
+                for (int i = tid; i < K4 * (TM / 4); i += NT) {
+                    const int f = i / (TM / 4), c = i - f * (TM / 4);
+                    sts4(agg_s + f * P + 4 * c, *reinterpret_cast<const float4*>(ws + f * TM + 4 * c));
+                }
+                f0 = K4;
+            }
+            for (int i = tid; i < (H1 + H2P) * (TM / 4); i += NT) {
+                const int f = i / (TM / 4), c = i - f * (TM / 4);
+                float* dst = (f < H1) ? (h1_s + f * P) : (h2_s + (f - H1) * P);
+                sts4(dst + 4 * c, *reinterpret_cast<const float4*>(ws + (f0 + f) * TM + 4 * c));
+            }
+        }
+        for (int i = tid; i < TM * LAT; i += NT) {
+            const int r = i / LAT, l = i - r * LAT;
+            float dm = 0.f, dv = 0.f;
+            if (row0 + r < a.B) {
+                const long gi = (long)(row0 + r) * LAT + l;
+                dm = a.d_mean[br][gi];
+                dv = a.d_logvar[br][gi];
+            }
+            d3_s[l * P + r] = dm;
+            d3_s[(LAT + l) * P + r] = dv;
+        }
+        __syncthreads();
+        gemm_dw<TM>(h2_s, d3_s, dW3_s, H2, LAT2, LAT2, tid);
+        bias_dw<TM>(d3_s, db3_s, LAT2, tid);
+        __syncthreads();
+        gemm_dx<TM, true>(d3_s, W3_s, h2_s, H2, LAT2, tid);     // h2_s <- dL/d(pre2)
+        __syncthreads();
+        gemm_dw<TM>(h1_s, h2_s, dW2_s, H1, H2, H2P, tid);
+        bias_dw<TM>(h2_s, db2_s, H2, tid);
+        __syncthreads();
+        gemm_dx<TM, true>(h2_s, W2_s, h1_s, H1, H2P, tid);      // h1_s <- dL/d(pre1)
+        __syncthreads();
+        if (FAM == PCVAE_FAMILY_MLP) {
+            gemm_dw<TM>(in_s, h1_s, dW1_s, D, H1, H1, tid);
+            bias_dw<TM>(h1_s, db1_s, H1, tid);
+        } else {
+            gemm_dw<TM>(agg_s, h1_s, dW1_s, K, H1, H1, tid);
+            bias_dw<TM>(h1_s, db1_s, H1, tid);
+            __syncthreads();
+            gemm_dx<TM, false>(h1_s, W1_s, agg_s, K, H1, tid);  // agg_s <- dL/d(agg)
+            __syncthreads();
+            pnp_embed_bwd<TM>(in_s, ms_s, agg_s, A_s, C_s, dA_s, dC_s, D, K, K4, tid);
+        }
+        __syncthreads();
+    }
+
+    // flush per-CTA partial gradients (encoder slice of the flat layout)
+    float* gp = a.gp + (long)blockIdx.x * a.L.total;
+    flush_linear_grad(dW1_s, db1_s, gp + a.L.W1, gp + a.L.b1, IN1, H1, H1, tid);
+    flush_linear_grad(dW2_s, db2_s, gp + a.L.W2, gp + a.L.b2, H1, H2, H2P, tid);
+    flush_linear_grad(dW3_s, db3_s, gp + a.L.W3, gp + a.L.b3, H2, LAT2, LAT2, tid);
+    if (FAM == PCVAE_FAMILY_PNP) {
+        // chain rule through the collapsed tables back to type_pars1, type_bias1, pnp_encoder1
+        const float* th = a.theta;
+        for (int i = tid; i < D * K; i += NT) {           // dE[d][q] = sum_j dA[d][j] We[j][1+q]
+            const int d = i / K, q = i - d * K;
+            float s = 0.f;
+            for (int j = 0; j < K; ++j) s = fmaf(dA_s[d * K4 + j], th[a.L.We + j * (K + 2) + 1 + q], s);
+            gp[a.L.E + i] = s;
+        }
+        for (int d = tid; d < D; d += NT) {               // dbE[d] = sum_j dC[d][j] We[j][K+1]
+            float s = 0.f;
+            for (int j = 0; j < K; ++j) s = fmaf(dC_s[d * K4 + j], th[a.L.We + j * (K + 2) + K + 1], s);
+            gp[a.L.bE + d] = s;
+        }
+        for (int i = tid; i < K * (K + 2); i += NT) {     // dWe[j][c]
+            const int j = i / (K + 2), c = i - j * (K + 2);
+            float s = 0.f;
+            if (c == 0) for (int d = 0; d < D; ++d) s += dA_s[d * K4 + j];
+            else if (c <= K) for (int d = 0; d < D; ++d) s = fmaf(dA_s[d * K4 + j], th[a.L.E + d * K + (c - 1)], s);
+            else for (int d = 0; d < D; ++d) s = fmaf(dC_s[d * K4 + j], th[a.L.bE + d], s);
+            gp[a.L.We + i] = s;
+        }
+        for (int j = tid; j < K; j += NT) {               // dbe[j] = sum_d dC[d][j]
+            float s = 0.f;
+            for (int d = 0; d < D; ++d) s += dC_s[d * K4 + j];
+            gp[a.L.be + j] = s;
+        }
+    }
+}
+
+// ====================================================================================
+// Decoder (+ loss, + backward)
+// ====================================================================================
+struct DecArgs {
+    Layout L;
+    int mode, B, nbr, mask_kind;
+    const float* theta;
+    const float* z[2];
+    float* xhat[2];
+    const float* x;
+    const void* mask[2];
+    const float* mean[2];
+    const float* logvar[2];
+    const float* eps[2];
+    float alpha, beta_w, x_logvar, loss_scale;
+    float* sums_partials;
+    float* d_mean[2];
+    float* d_logvar[2];
+    const float* d_xhat[2];
+    float* d_z[2];
+    float* gp;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float red_s[NWARP][PCVAE_NSUMS];
+    constexpr int P = TM + 4;
+    const int tid = threadIdx.x;
+    const int D = a.L.D, DP = round4(D);
+    const bool bwd = (a.mode == PCVAE_DEC_TRAIN || a.mode == PCVAE_DEC_BWD);
+    const bool lossy = (a.mode == PCVAE_DEC_TRAIN || a.mode == PCVAE_DEC_EVAL);
+    float* W4_s = smem;                     // [10][52]
+    float* b4_s = W4_s + LAT * G1P;
+    float* W5_s = b4_s + G1P;               // [50][100]
+    float* b5_s = W5_s + G1 * G2;
+    float* W6_s = b5_s + G2;                // [100][DP]
+    float* b6_s = W6_s + G2 * DP;
+    float* z_s = b6_s + DP;                 // [12][P]
+    float* g1_s = z_s + LATP * P;           // [52][P]
+    float* g2_s = g1_s + G1P * P;           // [100][P]
+    float* xh_s = g2_s + G2 * P;            // [DP][P]
+    float* dW4_s = xh_s + DP * P;           // gradient accumulators (bwd modes only)
+    float* db4_s = dW4_s + LAT * G1P;
+    float* dW5_s = db4_s + G1P;
+    float* db5_s = dW5_s + G1 * G2;
+    float* dW6_s = db5_s + G2;
+    float* db6_s = dW6_s + G2 * DP;
+    float* dend_s = db6_s + DP;
+
+    stage_linear(W4_s, b4_s, a.theta + a.L.W4, a.theta + a.L.b4, LAT, G1, G1P, tid);
+    stage_linear(W5_s, b5_s, a.theta + a.L.W5, a.theta + a.L.b5, G1, G2, G2, tid);
+    stage_linear(W6_s, b6_s, a.theta + a.L.W6, a.theta + a.L.b6, G2, D, DP, tid);
+    if (bwd) zero_floats(dW4_s, (int)(dend_s - dW4_s), tid);
+    zero_floats(z_s, LATP * P, tid);
+    __syncthreads();
+
+    // NLL constants exactly as torch.distributions.Normal computes them (scale = exp(lv/2),
+    // var = scale^2, log_prob = -(d^2)/(2 var) - log(scale) - log(sqrt(2 pi)))
+    const float scale = expf(a.x_logvar * 0.5f);
+    const float var = scale * scale;
+    const float inv2var = 1.0f / (2.0f * var);
+    const float inv_var = 1.0f / var;
+    const float log_scale = logf(scale);
+    const float alpha = a.alpha, ls = a.loss_scale;
+
+    float s_req = 0.f, s_rep = 0.f, s_klq = 0.f, s_klp = 0.f, s_klr = 0.f, s_red = 0.f, s_imp = 0.f, s_sse = 0.f;
+
+    const int ntiles = (a.B + TM - 1) / TM;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int row0 = t * TM;
+        for (int br = 0; br < a.nbr; ++br) {
+            for (int i = tid; i < TM * LAT; i += NT) {
+                const int r = i / LAT, l = i - r * LAT;
+                z_s[l * P + r] = (row0 + r < a.B) ? a.z[br][(long)(row0 + r) * LAT + l] : 0.f;
+            }
+            __syncthreads();
+            gemm_fwd<TM, ACT_RELU>(z_s, W4_s, b4_s, g1_s, LAT, G1P, tid);
+            __syncthreads();
+            gemm_fwd<TM, ACT_RELU>(g1_s, W5_s, b5_s, g2_s, G1, G2, tid);
+            __syncthreads();
+            gemm_fwd<TM, ACT_SIGMOID>(g2_s, W6_s, b6_s, xh_s, G2, DP, tid);
+            __syncthreads();
+            // ---- element-wise: outputs, loss terms, dL/d(pre-sigmoid) ----
+            {
+                float* __restrict__ xo = a.xhat[br];
+                const float* __restrict__ x = a.x;
+                const void* __restrict__ m0 = a.mask[0];
+                const void* __restrict__ m1 = a.mask[1];
+                const float* __restrict__ dxh = a.d_xhat[br];
+                for_tile_elems<TM>(DP, row0, a.B, tid, [&](int d, int r, bool ok) {
+                    const float xh = xh_s[d * P + r];
+                    float dpre = 0.f;
+                    if (ok && d < D) {
+                        const long gi = (long)(row0 + r) * D + d;
+                        if (xo) xo[gi] = xh;
+                        if (lossy) {
+                            const float xv = x[gi];
+                            const float m = load_mask(m0, gi, a.mask_kind) != 0.f ? 1.f : 0.f;
+                            const float mp = (a.nbr > 1) ? (load_mask(m1, gi, a.mask_kind) != 0.f ? 1.f : 0.f) : 0.f;
+                            const float diff = xv - xh;
+                            const float nll = fmaf(diff * diff, inv2var, log_scale);
+                            float coef;
+                            if (br == 0) {
+                                s_req += m * nll;
+                                s_red += m * (1.f - mp) * nll;
+                                s_imp += (1.f - m) * nll;
+                                s_sse += (1.f - m) * diff * diff;
+                                coef = (1.f - alpha) * m + alpha * m * (1.f - mp);
+                            } else {
+                                s_rep += mp * nll;
+                                coef = alpha * mp;
+                            }
+                            dpre = coef * (xh - xv) * inv_var * ls * xh * (1.f - xh);
+                        } else if (a.mode == PCVAE_DEC_BWD) {
+                            dpre = dxh[gi] * xh * (1.f - xh);
+                        }
+                    }
+                    if (bwd) xh_s[d * P + r] = dpre;
+                });
+            }
+            if (bwd) {
+                __syncthreads();
+                gemm_dw<TM>(g2_s, xh_s, dW6_s, G2, D, DP, tid);
+                bias_dw<TM>(xh_s, db6_s, D, tid);
+                __syncthreads();
+                gemm_dx<TM, true>(xh_s, W6_s, g2_s, G2, DP, tid);
+                __syncthreads();
+                gemm_dw<TM>(g1_s, g2_s, dW5_s, G1, G2, G2, tid);
+                bias_dw<TM>(g2_s, db5_s, G2, tid);
+                __syncthreads();
+                gemm_dx<TM, true>(g2_s, W5_s, g1_s, G1, G2, tid);
+                __syncthreads();
+                gemm_dw<TM>(z_s, g1_s, dW4_s, LAT, G1, G1P, tid);
+                bias_dw<TM>(g1_s, db4_s, G1, tid);
+                __syncthreads();
+                gemm_dx<TM, false>(g1_s, W4_s, z_s, LAT, G1P, tid);   // z_s <- dL/dz
+                __syncthreads();
+            }
+            // ---- latent-space terms: KL sums, d_mean / d_logvar, d_z ----
+            if (a.mode == PCVAE_DEC_BWD) {
+                for (int i = tid; i < TM * LAT; i += NT) {
+                    const int r = i / LAT, l = i - r * LAT;
+                    if (row0 + r < a.B) a.d_z[br][(long)(row0 + r) * LAT + l] = z_s[l * P + r];
+                }
+            } else if (lossy) {
+                for (int i = tid; i < TM * LAT; i += NT) {
+                    const int r = i / LAT, l = i - r * LAT;
+                    if (row0 + r >= a.B) continue;
+                    const long gi = (long)(row0 + r) * LAT + l;
+                    const float mq = a.mean[0][gi], lq = a.logvar[0][gi];
+                    const float eq = expf(lq);
+                    float mp_ = 0.f, lp = 0.f, ep = 1.f;
+                    if (a.nbr > 1) { mp_ = a.mean[1][gi]; lp = a.logvar[1][gi]; ep = expf(lp); }
+                    const float dmu = mq - mp_;
+                    if (br == 0) {
+                        s_klq += 0.5f * (eq + mq * mq - 1.f - lq);
+                        if (a.nbr > 1) {
+                            s_klp += 0.5f * (ep + mp_ * mp_ - 1.f - lp);
+                            s_klr += 0.5f * (expf(lq - lp) + dmu * dmu / ep - 1.f - (lq - lp));
+                        }
+                    }
+                    if (a.mode == PCVAE_DEC_TRAIN) {
+                        const float dz = z_s[l * P + r];
+                        float gm, gv;
+                        if (br == 0) {
+                            gm = (1.f - alpha) * a.beta_w * mq;
+                            gv = (1.f - alpha) * a.beta_w * 0.5f * (eq - 1.f);
+                            if (a.nbr > 1) {
+                                gm += alpha * dmu / ep;
+                                gv += alpha * 0.5f * (expf(lq - lp) - 1.f);
+                            }
+                            gm = fmaf(gm, ls, dz);
+                            gv = fmaf(gv, ls, dz * 0.5f * expf(lq * 0.5f) * (a.eps[0] ? a.eps[0][gi] : 0.f));
+                        } else {
+                            gm = alpha * a.beta_w * mp_ - alpha * dmu / ep;
+                            gv = alpha * a.beta_w * 0.5f * (ep - 1.f) + alpha * 0.5f * (1.f - (eq + dmu * dmu) / ep);
+                            gm = fmaf(gm, ls, dz);
+                            gv = fmaf(gv, ls, dz * 0.5f * expf(lp * 0.5f) * (a.eps[1] ? a.eps[1][gi] : 0.f));
+                        }
+                        a.d_mean[br][gi] = gm;
+                        a.d_logvar[br][gi] = gv;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    if (lossy) {
+        float v[PCVAE_NSUMS] = {s_req, s_rep, s_klq, s_klp, s_klr, s_red, s_imp, s_sse};
+#pragma unroll
+        for (int j = 0; j < PCVAE_NSUMS; ++j) {
+            const float w = warp_sum(v[j]);
+            if ((tid & 31) == 0) red_s[tid >> 5][j] = w;
+        }
+        __syncthreads();
+        if (tid < PCVAE_NSUMS) {
+            float s = 0.f;
+            for (int w = 0; w < NWARP; ++w) s += red_s[w][tid];
+            a.sums_partials[blockIdx.x * PCVAE_NSUMS + tid] = s;
+        }
+    }
+    if (bwd) {
+        float* gp = a.gp + (long)blockIdx.x * a.L.total;
+        flush_linear_grad(dW4_s, db4_s, gp + a.L.W4, gp + a.L.b4, LAT, G1, G1P, tid);
+        flush_linear_grad(dW5_s, db5_s, gp + a.L.W5, gp + a.L.b5, G1, G2, G2, tid);
+        flush_linear_grad(dW6_s, db6_s, gp + a.L.W6, gp + a.L.b6, G2, D, DP, tid);
+    }
+}
+
+// ====================================================================================
+// Stand-alone loss terms (module API)
+// ====================================================================================
+struct LossArgs {
+    int B, D, Lat, nbr, mask_kind;
+    const float* x;
+    const void* mask[2];
+    const float* xhat[2];
+    const float* mean[2];
+    const float* logvar[2];
+    float alpha, beta_w, x_logvar, loss_scale;
+    float* sums_partials;
+    float* d_xhat[2];
+    float* d_mean[2];
+    float* d_logvar[2];
+};
+
+__global__ void __launch_bounds__(NT) k_loss_terms(const LossArgs a) {
+    __shared__ float red_s[NWARP][PCVAE_NSUMS];
+    const int tid = threadIdx.x;
+    const float scale = expf(a.x_logvar * 0.5f);
+    const float var = scale * scale;
+    const float inv2var = 1.0f / (2.0f * var), inv_var = 1.0f / var, log_scale = logf(scale);
+    const float alpha = a.alpha, ls = a.loss_scale;
+    float v[PCVAE_NSUMS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long nel = (long)a.B * a.D;
+    for (long i = (long)blockIdx.x * NT + tid; i < nel; i += (long)gridDim.x * NT) {
+        const float xv = a.x[i];
+        const float m = load_mask(a.mask[0], i, a.mask_kind) != 0.f ? 1.f : 0.f;
+        const float mp = (a.nbr > 1) ? (load_mask(a.mask[1], i, a.mask_kind) != 0.f ? 1.f : 0.f) : 0.f;
+        {
+            const float xh = a.xhat[0][i];
+            const float diff = xv - xh;
+            const float nll = fmaf(diff * diff, inv2var, log_scale);
+            v[PCVAE_S_RE_Q] += m * nll;
+            v[PCVAE_S_RE_D] += m * (1.f - mp) * nll;
+            v[PCVAE_S_RE_IMP] += (1.f - m) * nll;
+            v[PCVAE_S_SSE_UNOBS] += (1.f - m) * diff * diff;
+            if (a.d_xhat[0]) a.d_xhat[0][i] = ((1.f - alpha) * m + alpha * m * (1.f - mp)) * (xh - xv) * inv_var * ls;
+        }
+        if (a.nbr > 1) {
+            const float xh = a.xhat[1][i];
+            const float diff = xv - xh;
+            v[PCVAE_S_RE_P] += mp * fmaf(diff * diff, inv2var, log_scale);
+            if (a.d_xhat[1]) a.d_xhat[1][i] = alpha * mp * (xh - xv) * inv_var * ls;
+        }
+    }
+    const long nl = (long)a.B * a.Lat;
+    for (long i = (long)blockIdx.x * NT + tid; i < nl; i += (long)gridDim.x * NT) {
+        const float mq = a.mean[0][i], lq = a.logvar[0][i], eq = expf(lq);
+        v[PCVAE_S_KL_Q] += 0.5f * (eq + mq * mq - 1.f - lq);
+        float gmq = (1.f - alpha) * a.beta_w * mq, gvq = (1.f - alpha) * a.beta_w * 0.5f * (eq - 1.f);
+        if (a.nbr > 1) {
+            const float mp_ = a.mean[1][i], lp = a.logvar[1][i], ep = expf(lp);
+            const float dmu = mq - mp_, er = expf(lq - lp);
+            v[PCVAE_S_KL_P] += 0.5f * (ep + mp_ * mp_ - 1.f - lp);
+            v[PCVAE_S_KL_REG] += 0.5f * (er + dmu * dmu / ep - 1.f - (lq - lp));
+            gmq += alpha * dmu / ep;
+            gvq += alpha * 0.5f * (er - 1.f);
+            if (a.d_mean[1]) {
+                a.d_mean[1][i] = (alpha * a.beta_w * mp_ - alpha * dmu / ep) * ls;
+                a.d_logvar[1][i] = (alpha * a.beta_w * 0.5f * (ep - 1.f) + alpha * 0.5f * (1.f - (eq + dmu * dmu) / ep)) * ls;
+            }
+        }
+        if (a.d_mean[0]) { a.d_mean[0][i] = gmq * ls; a.d_logvar[0][i] = gvq * ls; }
+    }
+#pragma unroll
+    for (int j = 0; j < PCVAE_NSUMS; ++j) {
+        const float w = warp_sum(v[j]);
+        if ((tid & 31) == 0) red_s[tid >> 5][j] = w;
+    }
+    __syncthreads();
+    if (tid < PCVAE_NSUMS) {
+        float s = 0.f;
+        for (int w = 0; w < NWARP; ++w) s += red_s[w][tid];
+        a.sums_partials[blockIdx.x * PCVAE_NSUMS + tid] = s;
+    }
+}
+
+// ====================================================================================
+// Reductions and Adam
+// ====================================================================================
+__global__ void k_reduce_sums(const float* __restrict__ sp, int grid, double nll_const, double* __restrict__ sums) {
+    const int j = threadIdx.x;
+    if (j >= PCVAE_NSUMS) return;
+    double s = 0.0;
+    for (int c = 0; c < grid; ++c) s += (double)sp[c * PCVAE_NSUMS + j];
+    if (j == PCVAE_S_RE_Q || j == PCVAE_S_RE_P || j == PCVAE_S_RE_D || j == PCVAE_S_RE_IMP) s += nll_const;
+    sums[j] = s;
+}
+
+__global__ void k_reduce_grads(const float* __restrict__ gp, int grid, long P, long begin, long end,
+                               float* __restrict__ grad, int accumulate) {
+    for (long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < grid; ++c) s += gp[(long)c * P + i];
+        grad[i] = accumulate ? grad[i] + s : s;
+    }
+}
+
+__global__ void k_adam(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                       float* __restrict__ v, long n, float lr_bc1, float inv_sqrt_bc2, float b1, float b2, float eps) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float g = grad[i];
+        const float mi = m[i] + (g - m[i]) * (1.f - b1);          // exp_avg.lerp_(grad, 1-beta1)
+        const float vi = fmaf(b2, v[i], (1.f - b2) * g * g);      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        theta[i] -= lr_bc1 * (mi / denom);
+    }
+}
+
+__global__ void k_ffma_probe(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace pcvae
+
+// ========================================================================================
+// C ABI
+// ========================================================================================
+using namespace pcvae;
+
+static size_t enc_fwd_smem(const Layout& L) {
+    const int P = TM_TRAIN + 4, K4 = round4(L.K);
+    const int in1 = L.fam == PCVAE_FAMILY_MLP ? L.D : L.K;
+    size_t f = (size_t)in1 * H1 + H1 + H1 * H2P + H2P + H2 * LAT2 + LAT2 + (size_t)(L.D + H1 + H2P + LAT2) * P;
+    if (L.fam == PCVAE_FAMILY_PNP) f += (size_t)L.D * P + 2 * L.D * K4 + K4 * P;
+    return f * sizeof(float);
+}
+
+static size_t enc_bwd_smem(const Layout& L) {
+    const int P = TM_TRAIN + 4, K4 = round4(L.K);
+    const int in1 = L.fam == PCVAE_FAMILY_MLP ? L.D : L.K;
+    size_t f = (size_t)H1 * H2P + H2 * LAT2 + ((size_t)in1 * H1 + H1 + H1 * H2P + H2P + H2 * LAT2 + LAT2) +
+               (size_t)(L.D + H1 + H2P + LAT2) * P;
+    if (L.fam == PCVAE_FAMILY_PNP) f += (size_t)L.D * P + K4 * P + L.K * H1 + 4 * L.D * K4;
+    return f * sizeof(float);
+}
+
+static size_t dec_smem(const Layout& L, bool bwd) {
+    const int P = TM_TRAIN + 4, DP = round4(L.D);
+    size_t w = (size_t)LAT * G1P + G1P + G1 * G2 + G2 + G2 * DP + DP;
+    size_t f = w + (size_t)(LATP + G1P + G2 + DP) * P + (bwd ? w : 0);
+    return f * sizeof(float);
+}
+
+template <typename Kern, typename Args>
+static int launch(Kern kern, size_t smem, int grid, cudaStream_t st, const char* name, const Args& args) {
+    if (smem > MAX_SMEM) return fail(PCVAE_EINVAL, "%s: needs %zu B shared memory (> %d): obs_dim too large", name, smem, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    kern<<<grid, NT, smem, st>>>(args);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: launch: %s", name, cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+extern "C" {
+
+int pcvae_abi_version(void) { return PCVAE_ABI_VERSION; }
+const char* pcvae_last_error(void) { return err_buf(); }
+
+long pcvae_param_count(const pcvae_model* m) {
+    Layout L;
+    return make_layout(m, &L) ? L.total : -1;
+}
+
+int pcvae_param_offsets(const pcvae_model* m, long* offsets) {
+    Layout L;
+    if (!make_layout(m, &L)) return -1;
+    int n = 0;
+    if (m->family == PCVAE_FAMILY_PNP) { offsets[n++] = L.E; offsets[n++] = L.bE; offsets[n++] = L.We; offsets[n++] = L.be; }
+    const int rest[12] = {L.W1, L.b1, L.W2, L.b2, L.W3, L.b3, L.W4, L.b4, L.W5, L.b5, L.W6, L.b6};
+    for (int i = 0; i < 12; ++i) offsets[n++] = rest[i];
+    offsets[n] = L.total;
+    return n;
+}
+
+long pcvae_decoder_offset(const pcvae_model* m) {
+    Layout L;
+    return make_layout(m, &L) ? L.W4 : -1;
+}
+
+int pcvae_grid_ctas(void) {
+    int g = 0;
+    return device_ok(&g) == PCVAE_OK ? g : -1;
+}
+
+size_t pcvae_enc_act_ws_floats(const pcvae_model* m, int rows, int n_branch) {
+    if (!m || rows < 0) return 0;
+    const long ntiles = (rows + TM_TRAIN - 1) / TM_TRAIN;
+    return (size_t)ntiles * n_branch * enc_act_feats(m->family, m->emb_dim) * TM_TRAIN;
+}
+
+int pcvae_enc_fwd(const pcvae_enc_fwd_params* p, void* stream) {
+    if (!p) return fail(PCVAE_EINVAL, "enc_fwd: null params");
+    Layout L;
+    if (!make_layout(&p->model, &L)) return PCVAE_EINVAL;
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (p->rows < 0 || p->n_branch < 1 || p->n_branch > 2) return fail(PCVAE_EINVAL, "enc_fwd: bad rows/n_branch");
+    if (p->rows == 0) return PCVAE_OK;
+    if (!p->theta || !p->x) return fail(PCVAE_EINVAL, "enc_fwd: null theta/x");
+    for (int b = 0; b < p->n_branch; ++b)
+        if (!p->mask[b] || !p->mean[b] || !p->logvar[b]) return fail(PCVAE_EINVAL, "enc_fwd: null mask/mean/logvar for branch %d", b);
+    cudaStream_t st = (cudaStream_t)stream;
+    EncFwdArgs a{};
+    a.L = L; a.B = p->rows; a.nbr = p->n_branch; a.mask_kind = p->mask_kind; a.theta = p->theta; a.x = p->x;
+    for (int b = 0; b < 2; ++b) { a.mask[b] = p->mask[b]; a.eps[b] = p->eps[b]; a.mean[b] = p->mean[b]; a.logvar[b] = p->logvar[b]; a.z[b] = p->z[b]; }
+    a.act_ws = p->act_ws; a.ac = p->pnp_ac;
+    if (L.fam == PCVAE_FAMILY_PNP) {
+        if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_fwd: PNP family needs pnp_ac workspace");
+        pnp_tables_launch(L, p->theta, p->pnp_ac, st);
+        return launch(k_enc_fwd<PCVAE_FAMILY_PNP, TM_TRAIN>, enc_fwd_smem(L), grid, st, "enc_fwd", a);
+    }
+    return launch(k_enc_fwd<PCVAE_FAMILY_MLP, TM_TRAIN>, enc_fwd_smem(L), grid, st, "enc_fwd", a);
+}
+
+int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
+    if (!p) return fail(PCVAE_EINVAL, "enc_bwd: null params");
+    Layout L;
+    if (!make_layout(&p->model, &L)) return PCVAE_EINVAL;
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (p->rows < 0 || p->n_branch < 1 || p->n_branch > 2) return fail(PCVAE_EINVAL, "enc_bwd: bad rows/n_branch");
+    if (!p->theta || !p->grad_partials) return fail(PCVAE_EINVAL, "enc_bwd: null theta/grad_partials");
+    if (p->rows > 0 && (!p->x || !p->act_ws)) return fail(PCVAE_EINVAL, "enc_bwd: null x/act_ws");
+    for (int b = 0; b < p->n_branch && p->rows > 0; ++b)
+        if (!p->mask[b] || !p->d_mean[b] || !p->d_logvar[b]) return fail(PCVAE_EINVAL, "enc_bwd: null mask/d_mean/d_logvar for branch %d", b);
+    cudaStream_t st = (cudaStream_t)stream;
+    EncBwdArgs a{};
+    a.L = L; a.B = p->rows; a.nbr = p->n_branch; a.mask_kind = p->mask_kind; a.theta = p->theta; a.x = p->x;
+    for (int b = 0; b < 2; ++b) { a.mask[b] = p->mask[b]; a.d_mean[b] = p->d_mean[b]; a.d_logvar[b] = p->d_logvar[b]; }
+    a.act_ws = p->act_ws; a.ac = p->pnp_ac; a.gp = p->grad_partials;
+    if (L.fam == PCVAE_FAMILY_PNP) {
+        if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_bwd: PNP family needs pnp_ac tables");
+        return launch(k_enc_bwd<PCVAE_FAMILY_PNP, TM_TRAIN>, enc_bwd_smem(L), grid, st, "enc_bwd", a);
+    }
+    return launch(k_enc_bwd<PCVAE_FAMILY_MLP, TM_TRAIN>, enc_bwd_smem(L), grid, st, "enc_bwd", a);
+}
+
+int pcvae_dec(const pcvae_dec_params* p, void* stream) {
+    if (!p) return fail(PCVAE_EINVAL, "dec: null params");
+    Layout L;
+    if (!make_layout(&p->model, &L)) return PCVAE_EINVAL;
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (p->mode < PCVAE_DEC_FWD || p->mode > PCVAE_DEC_EVAL) return fail(PCVAE_EINVAL, "dec: bad mode %d", p->mode);
+    if (p->rows < 0 || p->n_branch < 1 || p->n_branch > 2) return fail(PCVAE_EINVAL, "dec: bad rows/n_branch");
+    if (!p->theta) return fail(PCVAE_EINVAL, "dec: null theta");
+    const bool bwd = p->mode == PCVAE_DEC_TRAIN || p->mode == PCVAE_DEC_BWD;
+    const bool lossy = p->mode == PCVAE_DEC_TRAIN || p->mode == PCVAE_DEC_EVAL;
+    if (bwd && !p->grad_partials) return fail(PCVAE_EINVAL, "dec: null grad_partials");
+    if (lossy && !p->sums_partials) return fail(PCVAE_EINVAL, "dec: null sums_partials");
+    if (p->rows > 0) {
+        for (int b = 0; b < p->n_branch; ++b) {
+            if (!p->z[b]) return fail(PCVAE_EINVAL, "dec: null z[%d]", b);
+            if (p->mode == PCVAE_DEC_FWD && !p->xhat[b]) return fail(PCVAE_EINVAL, "dec: null xhat[%d]", b);
+            if (p->mode == PCVAE_DEC_BWD && (!p->d_xhat[b] || !p->d_z[b])) return fail(PCVAE_EINVAL, "dec: null d_xhat/d_z[%d]", b);
+            if (lossy && (!p->mask[b] || !p->mean[b] || !p->logvar[b])) return fail(PCVAE_EINVAL, "dec: null mask/mean/logvar[%d]", b);
+            if (p->mode == PCVAE_DEC_TRAIN && (!p->d_mean[b] || !p->d_logvar[b])) return fail(PCVAE_EINVAL, "dec: null d_mean/d_logvar[%d]", b);
+        }
+        if (lossy && !p->x) return fail(PCVAE_EINVAL, "dec: null x");
+    }
+    DecArgs a{};
+    a.L = L; a.mode = p->mode; a.B = p->rows; a.nbr = p->n_branch; a.mask_kind = p->mask_kind; a.theta = p->theta; a.x = p->x;
+    for (int b = 0; b < 2; ++b) {
+        a.z[b] = p->z[b]; a.xhat[b] = p->xhat[b]; a.mask[b] = p->mask[b]; a.mean[b] = p->mean[b]; a.logvar[b] = p->logvar[b];
+        a.eps[b] = p->eps[b]; a.d_mean[b] = p->d_mean[b]; a.d_logvar[b] = p->d_logvar[b]; a.d_xhat[b] = p->d_xhat[b]; a.d_z[b] = p->d_z[b];
+    }
+    a.alpha = p->alpha; a.beta_w = p->beta_w; a.x_logvar = p->x_logvar; a.loss_scale = p->loss_scale;
+    a.sums_partials = p->sums_partials; a.gp = p->grad_partials;
+    return launch(k_dec<TM_TRAIN>, dec_smem(L, bwd), grid, (cudaStream_t)stream, "dec", a);
+}
+
+int pcvae_loss_terms(const pcvae_loss_params* p, void* stream) {
+    if (!p) return fail(PCVAE_EINVAL, "loss_terms: null params");
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (p->rows < 0 || p->obs_dim < 1 || p->latent_dim < 1 || p->n_branch < 1 || p->n_branch > 2)
+        return fail(PCVAE_EINVAL, "loss_terms: bad sizes");
+    if (!p->sums_partials) return fail(PCVAE_EINVAL, "loss_terms: null sums_partials");
+    if (p->rows > 0) {
+        if (!p->x) return fail(PCVAE_EINVAL, "loss_terms: null x");
+        for (int b = 0; b < p->n_branch; ++b)
+            if (!p->mask[b] || !p->xhat[b] || !p->mean[b] || !p->logvar[b]) return fail(PCVAE_EINVAL, "loss_terms: null input for branch %d", b);
+    }
+    LossArgs a{};
+    a.B = p->rows; a.D = p->obs_dim; a.Lat = p->latent_dim; a.nbr = p->n_branch; a.mask_kind = p->mask_kind; a.x = p->x;
+    for (int b = 0; b < 2; ++b) {
+        a.mask[b] = p->mask[b]; a.xhat[b] = p->xhat[b]; a.mean[b] = p->mean[b]; a.logvar[b] = p->logvar[b];
+        a.d_xhat[b] = p->d_xhat[b]; a.d_mean[b] = p->d_mean[b]; a.d_logvar[b] = p->d_logvar[b];
+    }
+    a.alpha = p->alpha; a.beta_w = p->beta_w; a.x_logvar = p->x_logvar; a.loss_scale = p->loss_scale;
+    a.sums_partials = p->sums_partials;
+    k_loss_terms<<<grid, NT, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "loss_terms: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_reduce_sums(const float* sums_partials, int grid, int rows, int obs_dim, double* sums, void* stream) {
+    if (!sums_partials || !sums || grid < 1) return fail(PCVAE_EINVAL, "reduce_sums: bad arguments");
+    const double c = 0.5 * 1.8378770664093453 * (double)rows * (double)obs_dim;   // 0.5*log(2*pi) per entry
+    k_reduce_sums<<<1, 32, 0, (cudaStream_t)stream>>>(sums_partials, grid, c, sums);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reduce_sums: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_reduce_grads(const float* grad_partials, int grid, long param_count, long begin, long end, float* grad,
+                       int accumulate, void* stream) {
+    if (!grad_partials || !grad || grid < 1 || begin < 0 || end > param_count || begin > end)
+        return fail(PCVAE_EINVAL, "reduce_grads: bad arguments");
+    if (begin == end) return PCVAE_OK;
+    const int blocks = (int)((end - begin + 255) / 256);
+    k_reduce_grads<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_partials, grid, param_count, begin, end, grad, accumulate);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reduce_grads: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int step, float lr,
+                    float beta1, float beta2, float eps, void* stream) {
+    if (!theta || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return fail(PCVAE_EINVAL, "adam_step: bad arguments");
+    if (n == 0) return PCVAE_OK;
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    const int blocks = (int)((n + 255) / 256);
+    k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1),
+                                                      (float)(1.0 / sqrt(bc2)), beta1, beta2, eps);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "adam_step: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_ffma_probe(float* scratch, int iters, double* flops, void* stream) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (!scratch || iters < 1) return fail(PCVAE_EINVAL, "ffma_probe: bad arguments");
+    const int blocks = grid * 4, threads = 512;
+    k_ffma_probe<<<blocks, threads, 0, (cudaStream_t)stream>>>(scratch, iters);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "ffma_probe: launch: %s", cudaGetErrorString(e));
+    if (flops) *flops = 2.0 * 8.0 * 16.0 * (double)iters * blocks * threads;
+    return PCVAE_OK;
+}
+
+}  // extern "C"

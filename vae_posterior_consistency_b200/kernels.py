@@ -1,0 +1,299 @@
+"""Tensor-level wrappers around the C ABI (no autograd here; see ops.py).
+
+PyTorch supplies device memory and the current CUDA stream only; every
+arithmetic step of the hot path runs inside libpcvae_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import lib as L
+
+#: fixed decoder log-variance log 0.02 (reference src/models/VAE.py:379)
+X_LOGVAR = math.log((0.1 * math.sqrt(2.0)) ** 2)
+LATENT = 10
+
+MLP_KEYS = ["seq_encoder.0.weight", "seq_encoder.0.bias", "seq_encoder.2.weight", "seq_encoder.2.bias",
+            "seq_encoder.4.weight", "seq_encoder.4.bias"]
+PNP_KEYS = ["type_pars1", "type_bias1", "pnp_encoder1.0.weight", "pnp_encoder1.0.bias",
+            "pnp_encoder2.0.weight", "pnp_encoder2.0.bias", "pnp_encoder2.2.weight", "pnp_encoder2.2.bias",
+            "pnp_encoder2.4.weight", "pnp_encoder2.4.bias"]
+DEC_KEYS = ["seq_decoder.0.weight", "seq_decoder.0.bias", "seq_decoder.2.weight", "seq_decoder.2.bias",
+            "seq_decoder.4.weight", "seq_decoder.4.bias"]
+
+
+def param_keys(family: int) -> List[str]:
+    return (PNP_KEYS if family == L.FAMILY_PNP else MLP_KEYS) + DEC_KEYS
+
+
+def flatten_params(sd, family: int, device=None) -> torch.Tensor:
+    """state_dict (reference key names) -> flat fp32 theta in the C-ABI layout."""
+    parts = [sd[k].detach().reshape(-1).to(torch.float32) for k in param_keys(family)]
+    flat = torch.cat(parts)
+    return flat.to(device) if device is not None else flat
+
+
+def unflatten_params(theta: torch.Tensor, family: int, obs_dim: int, emb_dim: int = 0):
+    m = L.model(family, obs_dim, emb_dim)
+    offs = L.param_offsets(m)
+    D, K = obs_dim, emb_dim
+    shapes = ([(D, K), (D, 1), (K, K + 2), (K,), (100, K), (100,)] if family == L.FAMILY_PNP else [(100, D), (100,)])
+    shapes += [(50, 100), (50,), (20, 50), (20,), (50, 10), (50,), (100, 50), (100,), (D, 100), (D,)]
+    keys = param_keys(family)
+    return {k: theta[offs[i]:offs[i + 1]].view(*shapes[i]) for i, k in enumerate(keys)}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _pair(ts: Sequence[Optional[torch.Tensor]]):
+    a = (C.c_void_p * 2)()
+    for i, t in enumerate(ts[:2]):
+        a[i] = _p(t)
+    return a
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def prep_masks(masks: Sequence[torch.Tensor]):
+    """Masks stay bit-exact: torch.bool/uint8 are passed as bytes, anything else as float32."""
+    if all(m.dtype in (torch.bool, torch.uint8) for m in masks):
+        return L.MASK_U8, [m.contiguous() for m in masks]
+    return L.MASK_F32, [_f32(m) for m in masks]
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.PcvaeError("pcvae ops need CUDA tensors: there is no CPU fallback for this path")
+
+
+class Engine:
+    """Per-(family, D, K, device) launcher with cached workspaces."""
+
+    def __init__(self, family: int, obs_dim: int, emb_dim: int = 0, device=None):
+        self.lib = L.load()
+        self.family, self.D, self.K = family, obs_dim, (emb_dim if family == L.FAMILY_PNP else 0)
+        self.model = L.model(family, obs_dim, emb_dim)
+        self.P = L.param_count(self.model)
+        self.dec_off = L.decoder_offset(self.model)
+        self.device = torch.device(device if device is not None else "cuda")
+        with torch.cuda.device(self.device):
+            self.grid = self.lib.pcvae_grid_ctas()
+        if self.grid <= 0:
+            L.check(2, "pcvae_grid_ctas")
+        self._gp = None
+        self._sp = None
+        self._ac = None
+
+    # ---- workspaces -------------------------------------------------------------
+    def grad_partials(self):
+        if self._gp is None:
+            self._gp = torch.zeros(self.grid, self.P, device=self.device, dtype=torch.float32)
+        return self._gp
+
+    def sums_partials(self):
+        if self._sp is None:
+            self._sp = torch.zeros(self.grid, L.NSUMS, device=self.device, dtype=torch.float32)
+        return self._sp
+
+    def pnp_ac(self):
+        if self.family != L.FAMILY_PNP:
+            return None
+        if self._ac is None:
+            k4 = (self.K + 3) // 4 * 4
+            self._ac = torch.empty(2 * self.D * k4, device=self.device, dtype=torch.float32)
+        return self._ac
+
+    def act_ws(self, rows, n_branch):
+        n = self.lib.pcvae_enc_act_ws_floats(C.byref(self.model), rows, n_branch)
+        return torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
+
+    # ---- encoder ----------------------------------------------------------------
+    def enc_fwd(self, theta, x, masks, eps=None, save=False, want_z=True):
+        _need_cuda(theta, x, *masks)
+        x = _f32(x)
+        nb = len(masks)
+        kind, masks = prep_masks(masks)
+        B = x.shape[0]
+        mk = lambda: [torch.empty(B, LATENT, device=x.device, dtype=torch.float32) for _ in range(nb)]
+        mean, logvar = mk(), mk()
+        z = mk() if want_z else [None] * nb
+        eps = [None] * nb if eps is None else [None if e is None else _f32(e) for e in eps]
+        ws = self.act_ws(B, nb) if save else None
+        p = L.EncFwdParams(model=self.model, rows=B, n_branch=nb, mask_kind=kind, theta=_p(theta), x=_p(x),
+                           mask=_pair(masks), eps=_pair(eps), mean=_pair(mean), logvar=_pair(logvar), z=_pair(z),
+                           act_ws=_p(ws), pnp_ac=_p(self.pnp_ac()))
+        with torch.cuda.device(x.device):
+            L.check(self.lib.pcvae_enc_fwd(C.byref(p), _stream()), "pcvae_enc_fwd")
+        return mean, logvar, z, ws
+
+    def enc_bwd(self, theta, x, masks, ws, d_mean, d_logvar):
+        x = _f32(x)
+        kind, masks = prep_masks(masks)
+        gp = self.grad_partials()
+        d_mean = [_f32(t) for t in d_mean]
+        d_logvar = [_f32(t) for t in d_logvar]
+        p = L.EncBwdParams(model=self.model, rows=x.shape[0], n_branch=len(masks), mask_kind=kind, theta=_p(theta),
+                           x=_p(x), mask=_pair(masks), act_ws=_p(ws), d_mean=_pair(d_mean),
+                           d_logvar=_pair(d_logvar), pnp_ac=_p(self.pnp_ac()), grad_partials=_p(gp))
+        with torch.cuda.device(x.device):
+            L.check(self.lib.pcvae_enc_bwd(C.byref(p), _stream()), "pcvae_enc_bwd")
+        return gp
+
+    # ---- decoder ----------------------------------------------------------------
+    def dec(self, mode, theta, z, *, x=None, masks=(), mean=(), logvar=(), eps=(), alpha=0.0, beta_w=1.0,
+            loss_scale=1.0, d_xhat=(), want_xhat=False, x_logvar=X_LOGVAR):
+        _need_cuda(theta, *z)
+        z = [_f32(t) for t in z]
+        nb = len(z)
+        B = z[0].shape[0]
+        dev = z[0].device
+        kind, masks = prep_masks(masks) if len(masks) else (L.MASK_U8, [])
+        mk = lambda w: [torch.empty(B, w, device=dev, dtype=torch.float32) for _ in range(nb)]
+        xhat = mk(self.D) if (want_xhat or mode == L.DEC_FWD) else [None] * nb
+        d_mean = mk(LATENT) if mode == L.DEC_TRAIN else [None] * nb
+        d_logvar = mk(LATENT) if mode == L.DEC_TRAIN else [None] * nb
+        d_z = mk(LATENT) if mode == L.DEC_BWD else [None] * nb
+        pad = lambda ts: list(ts) + [None] * (2 - len(ts))
+        conv = lambda ts: pad([None if t is None else _f32(t) for t in ts])
+        # converted inputs are held in locals until the launch is enqueued
+        xc = None if x is None else _f32(x)
+        masks_c, mean_c, logvar_c, eps_c, dxh_c = pad(masks), conv(mean), conv(logvar), conv(eps), conv(d_xhat)
+        p = L.DecParams(model=self.model, mode=mode, rows=B, n_branch=nb, mask_kind=kind, theta=_p(theta),
+                        z=_pair(z), xhat=_pair(xhat), x=_p(xc), mask=_pair(masks_c), mean=_pair(mean_c),
+                        logvar=_pair(logvar_c), eps=_pair(eps_c),
+                        alpha=alpha, beta_w=beta_w, x_logvar=x_logvar, loss_scale=loss_scale,
+                        sums_partials=_p(self.sums_partials()), d_mean=_pair(d_mean), d_logvar=_pair(d_logvar),
+                        d_xhat=_pair(dxh_c), d_z=_pair(d_z),
+                        grad_partials=_p(self.grad_partials() if mode in (L.DEC_TRAIN, L.DEC_BWD) else None))
+        with torch.cuda.device(dev):
+            L.check(self.lib.pcvae_dec(C.byref(p), _stream()), "pcvae_dec")
+        del xc, masks_c, mean_c, logvar_c, eps_c, dxh_c
+        return dict(xhat=xhat, d_mean=d_mean, d_logvar=d_logvar, d_z=d_z)
+
+    # ---- stand-alone loss ---------------------------------------------------------
+    def loss_terms(self, x, masks, xhat, mean, logvar, alpha, beta_w, loss_scale, want_grads, x_logvar=X_LOGVAR):
+        _need_cuda(x, *xhat)
+        x = _f32(x)
+        nb = len(xhat)
+        kind, masks = prep_masks(masks)
+        B, D = x.shape
+        xhat = [_f32(t) for t in xhat]
+        mean = [_f32(t) for t in mean]
+        logvar = [_f32(t) for t in logvar]
+        mk = lambda like: [torch.empty_like(t) for t in like] if want_grads else [None] * nb
+        d_xhat, d_mean, d_logvar = mk(xhat), mk(mean), mk(logvar)
+        p = L.LossParams(rows=B, obs_dim=D, latent_dim=mean[0].shape[1], n_branch=nb, mask_kind=kind, x=_p(x),
+                         mask=_pair(masks), xhat=_pair(xhat), mean=_pair(mean), logvar=_pair(logvar), alpha=alpha,
+                         beta_w=beta_w, x_logvar=x_logvar, loss_scale=loss_scale,
+                         sums_partials=_p(self.sums_partials()), d_xhat=_pair(d_xhat), d_mean=_pair(d_mean),
+                         d_logvar=_pair(d_logvar))
+        with torch.cuda.device(x.device):
+            L.check(self.lib.pcvae_loss_terms(C.byref(p), _stream()), "pcvae_loss_terms")
+        return self.reduce_sums(B, D), d_xhat, d_mean, d_logvar
+
+    # ---- reductions / optimiser -----------------------------------------------------
+    def reduce_sums(self, rows, obs_dim=None):
+        sums = torch.empty(L.NSUMS, device=self.device, dtype=torch.float64)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pcvae_reduce_sums(_p(self.sums_partials()), self.grid, rows,
+                                               self.D if obs_dim is None else obs_dim, _p(sums), _stream()),
+                    "pcvae_reduce_sums")
+        return sums
+
+    def reduce_grads(self, grad, begin=0, end=None, accumulate=False):
+        end = self.P if end is None else end
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pcvae_reduce_grads(_p(self.grad_partials()), self.grid, self.P, begin, end, _p(grad),
+                                                int(accumulate), _stream()), "pcvae_reduce_grads")
+        return grad
+
+    def adam_step(self, theta, grad, exp_avg, exp_avg_sq, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pcvae_adam_step(_p(theta), _p(grad), _p(exp_avg), _p(exp_avg_sq), theta.numel(), step,
+                                             lr, b1, b2, eps, _stream()), "pcvae_adam_step")
+
+    # ---- reward -----------------------------------------------------------------------
+    def reward(self, theta, x, mask, im, workspace=None):
+        """R[N, D-1] for one acquisition step (evaluate.py:416-425)."""
+        _need_cuda(theta, x, mask, im)
+        x = _f32(x)
+        im = _f32(im)
+        kind, (mask,) = prep_masks([mask])
+        M, N, D = im.shape
+        assert D == self.D and x.shape == (N, D)
+        nbytes = self.lib.pcvae_reward_workspace_bytes(C.byref(self.model), N, M)
+        if workspace is None or workspace.numel() < nbytes:
+            workspace = torch.empty(max(nbytes, 1), device=x.device, dtype=torch.uint8)
+        R = torch.empty(N, D - 1, device=x.device, dtype=torch.float32)
+        p = L.RewardParams(model=self.model, rows=N, samples=M, mask_kind=kind, theta=_p(theta), x=_p(x),
+                           mask=_p(mask), im=_p(im), im_sample_stride=N * D, R=_p(R), workspace=_p(workspace),
+                           workspace_bytes=workspace.numel(), pnp_ac=_p(self.pnp_ac()))
+        with torch.cuda.device(x.device):
+            L.check(self.lib.pcvae_reward_chain(C.byref(p), _stream()), "pcvae_reward_chain")
+        return R, workspace
+
+
+def loss_from_sums(sums: torch.Tensor, rows: int, alpha: float, beta_w: float, regularised: bool):
+    """train_loss = L / B with L as in VAE.py:441-452 (device tensor, float64)."""
+    loss_q = sums[L.S_RE_Q] + beta_w * sums[L.S_KL_Q]
+    if not regularised:
+        return loss_q / rows
+    loss_p = sums[L.S_RE_P] + beta_w * sums[L.S_KL_P]
+    return (loss_q + alpha * (sums[L.S_KL_REG] - loss_q + loss_p + sums[L.S_RE_D])) / rows
+
+
+class FusedTrainer:
+    """The fused training step of train.py:87-116 on flat device vectors:
+    encoder fwd (both branches) -> decoder + loss + decoder bwd -> encoder bwd ->
+    deterministic partial reduce -> Adam.  Optionally a data-parallel gradient all-reduce
+    (torch.distributed, NCCL) between reduce and Adam."""
+
+    def __init__(self, family, obs_dim, emb_dim, theta, regularised=True, alpha=1.0, beta_w=1.0, lr=1e-3,
+                 dist_group=None, world_size=1):
+        self.eng = Engine(family, obs_dim, emb_dim, theta.device)
+        self.theta = theta
+        self.grad = torch.zeros_like(theta)
+        self.exp_avg = torch.zeros_like(theta)
+        self.exp_avg_sq = torch.zeros_like(theta)
+        self.step_count = 0
+        self.regularised, self.alpha, self.beta_w, self.lr = regularised, alpha, beta_w, lr
+        self.dist_group, self.world_size = dist_group, world_size
+
+    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None):
+        e = self.eng
+        B = x.shape[0]
+        rows = B if global_rows is None else global_rows
+        masks = [mask, mask_p] if self.regularised else [mask]
+        eps = [eps_q, eps_p] if self.regularised else [eps_q]
+        alpha = self.alpha if self.regularised else 0.0
+        mean, logvar, z, ws = e.enc_fwd(self.theta, x, masks, eps, save=True)
+        out = e.dec(L.DEC_TRAIN, self.theta, z, x=x, masks=masks, mean=mean, logvar=logvar, eps=eps, alpha=alpha,
+                    beta_w=self.beta_w, loss_scale=1.0 / rows)
+        e.enc_bwd(self.theta, x, masks, ws, out["d_mean"], out["d_logvar"])
+        e.reduce_grads(self.grad)
+        sums = e.reduce_sums(B)
+        return sums
+
+    def step(self, x, mask, mask_p, eps_q, eps_p, global_rows=None):
+        sums = self.forward_backward(x, mask, mask_p, eps_q, eps_p, global_rows)
+        if self.dist_group is not None and self.world_size > 1:
+            torch.distributed.all_reduce(self.grad, group=self.dist_group)
+        self.step_count += 1
+        self.eng.adam_step(self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)
+        rows = x.shape[0] if global_rows is None else global_rows
+        return loss_from_sums(sums, rows, self.alpha, self.beta_w, self.regularised)
