@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""Benchmark of the partial-VAE posterior-consistency hot path (BASELINE.json metric:
+train rows/s (fwd+bwd) and active-selection rewards/s).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W      # reference CPU path (oracle port)
+
+One JSON line on rank 0.  `value` = consistency-regularised training rows/s (Reg_VAE,
+1M x 100 synthetic table, batch 65 536 rows per GPU, fwd + bwd + Adam, inputs resident in
+HBM); `secondary` = active-selection reward triples/s (100k rows x 100 candidates x 50
+samples, rows sharded over the GPUs).  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_TRAIN = 100
+D_REWARD = 101
+# algorithmic FLOP per unit (FLOP = 2*MAC, transcendental work excluded)
+FLOP_TRAIN_ROW = 338_000          # Reg_VAE D=100 fwd+bwd, both branches
+MAC_DEC_BRANCH_ROW = 46_500       # decoder fwd 15 500 + dX 15 500 + dW 15 500 (one branch)
+FLOP_REWARD_TRIPLE = 24_460       # Reg_VAE incremental form
+MAC_REWARD_MAIN_TRIPLE = 12_000   # 2 tail evaluations x (100x50 + 50x20)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [s.strip() for s in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------
+
+def cpu_train_rows_per_s(batch, steps, warmup):
+    from oracle import pcvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = O.init_params("mlp", D_TRAIN, seed=0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(batch, D_TRAIN, generator=g)
+    mask = torch.rand(batch, D_TRAIN, generator=g) < 0.7
+    names = O.trainable_names(p)
+    m = {k: torch.zeros_like(p[k]) for k in names}
+    v = {k: torch.zeros_like(p[k]) for k in names}
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        mask_p = mask & (torch.rand(batch, D_TRAIN) < 0.7)             # train.py:53-55
+        eq, ep = torch.randn(batch, 10), torch.randn(batch, 10)        # the two rsample() draws
+        _, grads, _ = O.train_step(p, x, mask, mask_p, eq, ep)
+        for k in names:
+            p[k], m[k], v[k] = O.adam_step(p[k], grads[k], m[k], v[k], s + 1)
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warmup:]) / steps
+    return batch / t, t * 1e3
+
+
+def cpu_reward_triples_per_s(n_rows, n_cand, samples, reps=1):
+    from oracle import pcvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = O.init_params("mlp", D_REWARD, seed=0)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(n_rows, D_REWARD, generator=g)
+    mask = torch.zeros(n_rows, D_REWARD)
+    im = torch.rand(samples, n_rows, D_REWARD, generator=g)
+    loc = torch.arange(n_rows)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(reps):
+            for u in range(n_cand):
+                O.reward_chain_as_written(p, u, x, mask, im, loc)       # evaluate.py:514-634, as written
+    dt = (time.perf_counter() - t0) / reps
+    return n_rows * n_cand * samples / dt, dt * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    batch = args.batch
+    rows_s, ms = cpu_train_rows_per_s(batch, args.steps, args.warmup)
+    tr_s, tr_ms = cpu_reward_triples_per_s(2000, 2, 50)
+    line = {
+        "impl": "reference", "metric": "train rows/s (fwd+bwd+Adam), consistency-regularised partial VAE",
+        "value": rows_s, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"Reg_VAE D={D_TRAIN}, synthetic 1M x 100 table, batch {batch} rows/step (cfg4)",
+                   "batch": batch},
+        "cpu_baseline": {"value": rows_s, "unit": "rows/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of one {batch}-row batch, oracle port of "
+                                   "forward+loss+backward+Adam (train.py:87-116), torch CPU eager"},
+        "e2e": {"value": rows_s, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "secondary": {"metric": "active-selection rewards/s", "value": tr_s, "unit": "triples/s",
+                      "sample": "R_lindley_chain as written, 2000 rows x 2 candidates x 50 samples, D=101",
+                      "ms": tr_ms},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import ctypes as C
+    world, rank, local = dist_setup(args.gpus)
+    from oracle import pcvae_oracle as O
+    from vae_posterior_consistency_b200 import kernels as KR, lib as L
+
+    dev = torch.device("cuda", local)
+    lib = L.load()
+    stream = lambda: torch.cuda.current_stream().cuda_stream
+    hbm_peak, peak_src = peaks()
+
+    # ---- FP32 FFMA peak of this box (roofline denominator of the FFMA-bound kernels) ----
+    scratch = torch.empty(148 * 4 * 512 * 2, device=dev)
+    ffma_tflops = 0.0
+    for _ in range(5):
+        fl = C.c_double(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(lib.pcvae_ffma_probe(scratch.data_ptr(), 4000, C.byref(fl), stream()), "ffma_probe")
+        e1.record()
+        torch.cuda.synchronize()
+        ffma_tflops = max(ffma_tflops, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+
+    # =========================== training (cfg4) ===========================
+    B, D, T = args.batch, D_TRAIN, args.table_rows
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    table = torch.rand(T, D, device=dev, generator=g)
+    mtable = torch.rand(T, D, device=dev, generator=g) < 0.7                 # MCAR 30 % missing, bool
+    p = O.init_params("mlp", D, seed=0)
+    theta = KR.flatten_params(p, L.FAMILY_MLP, dev)
+    dist_group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist_group = dist.group.WORLD
+    tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, theta, regularised=True, alpha=1.0, dist_group=dist_group,
+                         world_size=world)
+    eng = tr.eng
+    n_total = args.warmup + args.steps
+    perm = torch.cat([torch.randperm(T, device=dev, generator=g) for _ in range((n_total * B + T - 1) // T + 1)])
+    x = torch.empty(B, D, device=dev)
+    mask = torch.empty(B, D, device=dev, dtype=torch.bool)
+    mask_p = torch.empty(B, D, device=dev, dtype=torch.bool)
+    eps = torch.empty(2, B, 10, device=dev)
+    dec_ev = []
+    launches = [0]
+
+    def prep_step(s, xs, ms):
+        """device-side batch preparation: gather by the sampler permutation, draw sub-mask and noise"""
+        idx = perm[s * B:(s + 1) * B]
+        L.check(lib.pcvae_gather_rows(table.data_ptr(), mtable.data_ptr(), idx.data_ptr(), xs.data_ptr(),
+                                      ms.data_ptr(), B, D, L.MASK_U8, stream()), "gather_rows")
+        launches[0] += 1
+
+    def draw_step(s, ms):
+        L.check(lib.pcvae_draw_submask(ms.data_ptr(), mask_p.data_ptr(), B * D, 0.7, 99, s * 4, stream()), "draw_submask")
+        L.check(lib.pcvae_draw_normal(eps.data_ptr(), 2 * B * 10, 77, s * 4, stream()), "draw_normal")
+        launches[0] += 2
+
+    def train_step(xs, ms, timed):
+        masks, e = [ms, mask_p], [eps[0], eps[1]]
+        mean, logvar, z, ws = eng.enc_fwd(theta, xs, masks, e, save=True)
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        out = eng.dec(L.DEC_TRAIN, theta, z, x=xs, masks=masks, mean=mean, logvar=logvar, eps=e, alpha=1.0,
+                      beta_w=1.0, loss_scale=1.0 / (B * world))
+        if timed:
+            b.record()
+            dec_ev.append((a, b))
+        eng.enc_bwd(theta, xs, masks, ws, out["d_mean"], out["d_logvar"])
+        eng.reduce_grads(tr.grad)
+        sums = eng.reduce_sums(B)
+        if world > 1:
+            torch.distributed.all_reduce(tr.grad, group=dist_group)
+        tr.step_count += 1
+        eng.adam_step(theta, tr.grad, tr.exp_avg, tr.exp_avg_sq, tr.step_count)
+        launches[0] += 6
+        return sums
+
+    for s in range(args.warmup):
+        prep_step(s, x, mask); draw_step(s, mask); train_step(x, mask, False)
+    barrier(world)
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches[0] = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(args.warmup, n_total):
+        prep_step(s, x, mask); draw_step(s, mask); sums = train_step(x, mask, True)
+    t1.record()
+    barrier(world)
+    train_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
+    train_launches = launches[0]
+    clk = clocks.stop()
+    dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / len(dec_ev)
+    loss = float(KR.loss_from_sums(sums, B * world, 1.0, 1.0, True))
+    rows_s = B * world / (train_ms * 1e-3)
+
+    # ---- e2e: host batch (pinned) -> H2D -> step -> D2H loss sums, copies inside the timed region ----
+    nbuf = 2
+    hx = [torch.rand(B, D).pin_memory() for _ in range(nbuf)]
+    hm = [(torch.rand(B, D) < 0.7).pin_memory() for _ in range(nbuf)]
+    dx = [torch.empty(B, D, device=dev) for _ in range(nbuf)]
+    dm = [torch.empty(B, D, device=dev, dtype=torch.bool) for _ in range(nbuf)]
+    hsum = torch.empty(args.steps + args.warmup, L.NSUMS, dtype=torch.float64).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    ready = [torch.cuda.Event() for _ in range(nbuf)]
+    freed = [torch.cuda.Event() for _ in range(nbuf)]
+
+    def e2e_loop(first, count):
+        for i in range(first, first + count):
+            b = i % nbuf
+            with torch.cuda.stream(copy_stream):
+                if i >= first + nbuf:
+                    copy_stream.wait_event(freed[b])
+                dx[b].copy_(hx[b], non_blocking=True)
+                dm[b].copy_(hm[b], non_blocking=True)
+                ready[b].record(copy_stream)
+            main.wait_event(ready[b])
+            draw_step(i, dm[b])
+            s_ = train_step(dx[b], dm[b], False)
+            freed[b].record(main)
+            hsum[i].copy_(s_, non_blocking=True)
+
+    e2e_loop(0, args.warmup)
+    barrier(world)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(args.warmup, args.steps)
+    t1.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
+    e2e_rows_s = B * world / (e2e_ms * 1e-3)
+    h2d = B * D * 4 + B * D
+    d2h = L.NSUMS * 8
+    del table, mtable, perm, hx, hm, dx, dm
+    torch.cuda.empty_cache()
+
+    # =========================== reward (cfg5) ===========================
+    sec = None
+    if args.reward_rows > 0:
+        Dr, M = D_REWARD, args.reward_samples
+        Nloc = args.reward_rows // world
+        pr = O.init_params("mlp", Dr, seed=3)
+        pr = {k: (v * 2.0 if not k.startswith("prior") else v) for k, v in pr.items()}
+        theta_r = KR.flatten_params(pr, L.FAMILY_MLP, dev)
+        er = KR.Engine(L.FAMILY_MLP, Dr, 0, dev)
+        gx = torch.Generator(device=dev).manual_seed(5 + rank)
+        xr = torch.rand(Nloc, Dr, device=dev, generator=gx)
+        mr = torch.zeros(Nloc, Dr, device=dev)                              # step t=0: nothing selected
+        im = torch.rand(M, Nloc, Dr, device=dev, generator=gx)
+        ws = None
+        R, ws = er.reward(theta_r, xr, mr, im, ws)
+        barrier(world)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.reward_steps):
+            R, ws = er.reward(theta_r, xr, mr, im, ws)
+        t1.record()
+        barrier(world)
+        r_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.reward_steps
+        triples = Nloc * world * (Dr - 1) * M
+        # e2e: host x / mask / im -> device -> R back on the host
+        hxr, hmr, him = xr.cpu().pin_memory(), mr.cpu().pin_memory(), im.cpu().pin_memory()
+        hR = torch.empty(Nloc, Dr - 1).pin_memory()
+        barrier(world)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        xr.copy_(hxr, non_blocking=True); mr.copy_(hmr, non_blocking=True); im.copy_(him, non_blocking=True)
+        R, ws = er.reward(theta_r, xr, mr, im, ws)
+        hR.copy_(R, non_blocking=True)
+        t1.record()
+        barrier(world)
+        re2e_ms = max_over_ranks(t0.elapsed_time(t1), world)
+        sec = {
+            "metric": "active-selection rewards/s", "value": triples / (r_ms * 1e-3), "unit": "triples/s",
+            "ms_per_step": r_ms, "steps": args.reward_steps, "scaling": "strong",
+            "config": {"workload": f"Reg_VAE reward sweep {Nloc * world} rows x {Dr - 1} candidates x {M} samples "
+                                   f"(cfg5), rows sharded over {world} GPU(s), no collective"},
+            "e2e": {"value": triples / (re2e_ms * 1e-3), "unit": "triples/s",
+                    "h2d_bytes_per_step": int(hxr.numel() * 4 + hmr.numel() * 4 + him.numel() * 4),
+                    "d2h_bytes_per_step": int(hR.numel() * 4)},
+            "roofline": {"bound": "fp32_ffma", "kernel": "k_reward_main+k_reward_prep (whole pcvae_reward_chain call)",
+                         "achieved": triples / world * FLOP_REWARD_TRIPLE / (r_ms * 1e-3) / 1e12,
+                         "peak": ffma_tflops, "unit": "TFLOP/s",
+                         "frac": triples / world * FLOP_REWARD_TRIPLE / (r_ms * 1e-3) / 1e12 / ffma_tflops,
+                         "traffic": None},
+            "gpu_launches": 4 * args.reward_steps,
+        }
+
+    if rank == 0:
+        dec_flops = 2 * MAC_DEC_BRANCH_ROW * 2 * B
+        achieved = dec_flops / (dec_ms * 1e-3) / 1e12
+        line = {
+            "metric": "train rows/s (fwd+bwd+Adam), consistency-regularised partial VAE",
+            "value": rows_s, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": train_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Reg_VAE D={D}, synthetic {T} x {D} table resident in HBM, batch {B} rows per GPU "
+                                   f"per step (cfg4), device-side gather + Philox sub-mask/noise, "
+                                   f"{'NCCL grad all-reduce, ' if world > 1 else ''}Adam",
+                       "batch_per_gpu": B, "global_batch": B * world, "table_rows": T,
+                       "l2": "inputs larger than L2 (500 MB table, a fresh 33 MB batch gathered every step)",
+                       "final_loss": loss},
+            "e2e": {"value": e2e_rows_s, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": train_launches,
+            "clocks": clk,
+            "roofline": {"bound": "fp32_ffma", "kernel": "k_dec<64> (decoder fwd + loss + decoder bwd, both branches)",
+                         "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
+                         "traffic": None, "peak_source": "pcvae_ffma_probe on this GPU (MEASURED_PEAKS.json has no FP32 entry)",
+                         "step_achieved": FLOP_TRAIN_ROW * B / (train_ms * 1e-3) / 1e12,
+                         "step_frac": FLOP_TRAIN_ROW * B / (train_ms * 1e-3) / 1e12 / ffma_tflops,
+                         "hbm": {"achieved": (B * D * 10 + B * 2 * 152 * 8) / (train_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "peak_source": peak_src}},
+            "secondary": sec,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            cv, cms = cpu_train_rows_per_s(B, 3, 1)
+            line["cpu_baseline"] = {"value": cv, "unit": "rows/s", "cores": cores, "kind": "port",
+                                    "sample": f"3 steps of one {B}-row batch (oracle port of train.py:87-116, torch CPU)",
+                                    "ms_per_step": cms}
+            if sec is not None:
+                rv, rms = cpu_reward_triples_per_s(2000, 2, 50)
+                sec["cpu_baseline"] = {"value": rv, "unit": "triples/s", "cores": cores, "kind": "port",
+                                       "sample": "R_lindley_chain as written: 2000 rows x 2 candidates x 50 samples, D=101"}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--table-rows", type=int, default=1_000_000)
+    ap.add_argument("--reward-rows", type=int, default=100_000)
+    ap.add_argument("--reward-samples", type=int, default=50)
+    ap.add_argument("--reward-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

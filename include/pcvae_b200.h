@@ -237,6 +237,23 @@ typedef struct {
 size_t pcvae_reward_workspace_bytes(const pcvae_model* m, int rows, int samples);
 int pcvae_reward_chain(const pcvae_reward_params* p, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Throughput-mode batch preparation on the device.
+ *  pcvae_gather_rows  : x[b] = table[idx[b]], mask[b] = mask_table[idx[b]]  -- the batch a
+ *                       DataLoader(shuffle=True) yields (src/utils/loaders.py:342-352,389-397)
+ *                       for the permutation `idx` (int64, from torch's RandomSampler).
+ *  pcvae_draw_submask : mask_p = mask & (u < keep_prob), u ~ U[0,1) Philox4x32-10
+ *                       (create_missing_uci, src/utils/utils.py:36-39; train.py:53-55).
+ *  pcvae_draw_normal  : standard-normal draws for rsample() (VAE.py:390-392).
+ * Philox streams are statistically, not bitwise, equivalent to the reference's NumPy /
+ * torch CPU generators; parity mode passes host-drawn mask_p / eps instead.
+ * --------------------------------------------------------------------- */
+int pcvae_gather_rows(const float* table, const void* mask_table, const long* idx, float* x, void* mask,
+                      int rows, int obs_dim, int mask_kind, void* stream);
+int pcvae_draw_submask(const uint8_t* mask, uint8_t* mask_p, long n, float keep_prob,
+                       unsigned long long seed, unsigned long long offset, void* stream);
+int pcvae_draw_normal(float* out, long n, unsigned long long seed, unsigned long long offset, void* stream);
+
 /* FP32 FFMA peak probe used by bench.py for the roofline denominator: runs `iters`
  * dependent-chain-free FMA rounds on every SM; returns 0 and the FLOP count in *flops. */
 int pcvae_ffma_probe(float* scratch, int iters, double* flops, void* stream);

@@ -24,7 +24,8 @@ SYMBOLS = [
     "pcvae_abi_version", "pcvae_last_error", "pcvae_param_count", "pcvae_param_offsets",
     "pcvae_decoder_offset", "pcvae_enc_act_ws_floats", "pcvae_enc_fwd", "pcvae_enc_bwd", "pcvae_dec",
     "pcvae_loss_terms", "pcvae_grid_ctas", "pcvae_reduce_sums", "pcvae_reduce_grads", "pcvae_adam_step",
-    "pcvae_reward_workspace_bytes", "pcvae_reward_chain", "pcvae_ffma_probe",
+    "pcvae_reward_workspace_bytes", "pcvae_reward_chain", "pcvae_ffma_probe", "pcvae_gather_rows",
+    "pcvae_draw_submask", "pcvae_draw_normal",
 ]
 
 
@@ -111,6 +112,11 @@ def load():
     lib.pcvae_reward_workspace_bytes.restype = C.c_size_t
     lib.pcvae_reward_workspace_bytes.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
     lib.pcvae_reward_chain.argtypes = [C.POINTER(RewardParams), C.c_void_p]
+    lib.pcvae_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_int, C.c_void_p]
+    lib.pcvae_draw_submask.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_ulonglong, C.c_ulonglong,
+                                       C.c_void_p]
+    lib.pcvae_draw_normal.argtypes = [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
     lib.pcvae_ffma_probe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     _lib = lib
     return lib
