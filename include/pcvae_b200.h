@@ -130,6 +130,12 @@ typedef struct {
     const float* d_logvar[2];   /* [B][L] */
     const float* pnp_ac;        /* PNP: A,C tables from pcvae_enc_fwd */
     float* grad_partials;       /* [grid][P] */
+    /* optional reparameterisation backward (z = mean + eps*exp(logvar/2), VAE.py:390-392): when
+       d_z[b] is non-NULL, d_mean += d_z and d_logvar += d_z * 0.5 * exp(logvar/2) * eps are
+       folded in by the kernel (eps[b] NULL means sample=False, z = mean). */
+    const float* d_z[2];        /* [B][L] or NULL */
+    const float* eps[2];        /* [B][L] or NULL */
+    const float* logvar[2];     /* [B][L], required when d_z[b] and eps[b] are given */
 } pcvae_enc_bwd_params;
 int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream);
 

@@ -101,17 +101,21 @@ __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
     const int ntiles = (a.N + TM - 1) / TM;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int row0 = t * TM;
-        for_tile_elems<TM>(D, row0, a.N, tid, [&](int d, int r, bool ok) {
-            float xv = 0.f, mv = 0.f;
-            if (ok) {
-                const long gi = (long)(row0 + r) * D + d;
-                xv = a.x[gi];
-                mv = load_mask(a.mask, gi, a.mask_kind);
-                if (d < D - 1) a.R[(long)(row0 + r) * (D - 1) + d] = -1e4f;     // evaluate.py:391
-            }
-            if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = xv * mv;
-            else { in_s[d * P + r] = xv; ms_s[d * P + r] = mv; }
-        });
+        tile_elems<TM, 16, XM>(D, row0, a.N, tid,
+            [&](int d, int r, bool ok) {
+                XM v{0.f, 0.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * D + d;
+                    v.x = a.x[gi];
+                    v.m = load_mask(a.mask, gi, a.mask_kind);
+                }
+                return v;
+            },
+            [&](int d, int r, bool ok, XM v) {
+                if (ok && d < D - 1) a.R[(long)(row0 + r) * (D - 1) + d] = -1e4f;     // evaluate.py:391
+                if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = v.x * v.m;
+                else { in_s[d * P + r] = v.x; ms_s[d * P + r] = v.m; }
+            });
         // candidate list of each row: features u < D-1 with mask == 0   (evaluate.py:418)
         if (tid < TM && row0 + tid < a.N) {
             const long n = row0 + tid;
@@ -129,15 +133,17 @@ __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
                 const float v = h0_s[k * P + r];
                 h1_s[k * P + r] = fmaxf(v, 0.f);
             }
-            for_tile_elems<TM>(H1, row0, a.N, tid, [&](int k, int r, bool ok) {
-                if (ok) a.base_in[(long)(row0 + r) * INW + k] = h0_s[k * P + r];
-            });
+            tile_elems<TM, 1, int>(H1, row0, a.N, tid, [](int, int, bool) { return 0; },
+                [&](int k, int r, bool ok, int) {
+                    if (ok) a.base_in[(long)(row0 + r) * INW + k] = h0_s[k * P + r];
+                });
         } else {
             pnp_embed<TM>(in_s, ms_s, A_s, C_s, agg_s, D, K4, tid);      // agg0
             __syncthreads();
-            for_tile_elems<TM>(K4, row0, a.N, tid, [&](int j, int r, bool ok) {
-                if (ok) a.base_in[(long)(row0 + r) * INW + j] = agg_s[j * P + r];
-            });
+            tile_elems<TM, 1, int>(K4, row0, a.N, tid, [](int, int, bool) { return 0; },
+                [&](int j, int r, bool ok, int) {
+                    if (ok) a.base_in[(long)(row0 + r) * INW + j] = agg_s[j * P + r];
+                });
             gemm_fwd<TM, ACT_RELU>(agg_s, W1_s, b1_s, h1_s, K, H1, tid);
         }
         __syncthreads();

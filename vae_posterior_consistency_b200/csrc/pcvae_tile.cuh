@@ -261,22 +261,45 @@ __device__ __forceinline__ void flush_linear_grad(const float* dW_s, const float
 }
 
 // ---------------------------------------------------------------------------------
-// Tile loader: global row-major [rows][D] -> shared feature-major [D][P], a warp moving a
-// block of 4 rows x 8 features per step: each row segment is one 32-byte sector of global
-// memory and the 32 shared-memory stores hit 32 distinct banks.
-// f(xv, mv, d, r) receives the value, the mask value (0/1 as float) and the smem index.
+// Tile element visitor: global row-major [rows][D] <-> shared feature-major [D][P].  A warp
+// step covers 4 rows x 8 features: each row segment is one 32-byte sector of global memory
+// and the 32 shared-memory accesses hit 32 distinct banks.  Loads are issued in batches of
+// up to BATCH independent requests before the first use, so a tile costs a couple of memory
+// round trips instead of one per element (the first profile showed `long_scoreboard` as the
+// top stall with one-at-a-time loads).
+//   load(d, r, ok) -> T      (ok: row0 + r < B)          use(d, r, ok, T)
 // ---------------------------------------------------------------------------------
-template <int TM, typename F>
-__device__ __forceinline__ void for_tile_elems(int D, int row0, int B, int tid, F f) {
+template <int TM, int BATCH, typename T, typename LoadF, typename UseF>
+__device__ __forceinline__ void tile_elems(int D, int row0, int B, int tid, LoadF load, UseF use) {
     const int lane = tid & 31, warp = tid >> 5;
     const int dl = lane & 7, rl = lane >> 3;
     const int ndb = (D + 7) >> 3;
-    const int nblk = ndb * (TM / 4);
-    for (int blk = warp; blk < nblk; blk += NWARP) {
-        const int d = (blk % ndb) * 8 + dl;
-        const int r = (blk / ndb) * 4 + rl;
-        if (d < D) f(d, r, (row0 + r) < B);
+    for (int rb = warp; rb < TM / 4; rb += NWARP) {
+        const int r = rb * 4 + rl;
+        const bool ok = (row0 + r) < B;
+        for (int db0 = 0; db0 < ndb; db0 += BATCH) {
+            T v[BATCH];
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                const int d = (db0 + j) * 8 + dl;
+                if (d < D) v[j] = load(d, r, ok);
+            }
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                const int d = (db0 + j) * 8 + dl;
+                if (d < D) use(d, r, ok, v[j]);
+            }
+        }
     }
+}
+
+struct XM { float x, m; };
+
+// prefetch [base, base+bytes) into L2, one request per 128-byte line, spread over the CTA
+__device__ __forceinline__ void prefetch_l2(const void* base, long bytes, int tid) {
+    const char* p = reinterpret_cast<const char*>(base);
+    for (long off = (long)tid * 128; off < bytes; off += (long)NT * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 
 // agg[j][r] = sum_d m[d][r] * relu(x[d][r] * A[d][j] + C[d][j])     (VAE.py:726-733)

@@ -1,6 +1,8 @@
 // Training-path kernels: encoder forward, decoder + loss (+ backward), encoder backward,
 // stand-alone loss terms, partial reductions and Adam.  See include/pcvae_b200.h for the
 // reference code each entry point replaces.
+#include <cuda_pipeline.h>
+
 #include "pcvae_internal.cuh"
 
 namespace pcvae {
@@ -135,16 +137,30 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
         const int br = vt / ntiles, row0 = (vt - br * ntiles) * TM;
         const float* __restrict__ x = a.x;
         const void* __restrict__ mk = a.mask[br];
-        for_tile_elems<TM>(D, row0, a.B, tid, [&](int d, int r, bool ok) {
-            float xv = 0.f, mv = 0.f;
-            if (ok) {
-                const long gi = (long)(row0 + r) * D + d;
-                xv = x[gi];
-                mv = load_mask(mk, gi, a.mask_kind);
+        {   // L2 prefetch of this CTA's next tile while the current one is being processed
+            const int nvt = vt + gridDim.x;
+            if (nvt < ntiles * a.nbr) {
+                const int nbr_ = nvt / ntiles, nrow0 = (nvt - nbr_ * ntiles) * TM;
+                const long nrows = min(TM, a.B - nrow0);
+                prefetch_l2(x + (long)nrow0 * D, nrows * D * 4, tid);
+                const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
+                prefetch_l2((const char*)a.mask[nbr_] + (long)nrow0 * D * msz, nrows * D * msz, tid);
             }
-            if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = xv * mv;
-            else { in_s[d * P + r] = xv; ms_s[d * P + r] = mv; }
-        });
+        }
+        tile_elems<TM, 16, XM>(D, row0, a.B, tid,
+            [&](int d, int r, bool ok) {
+                XM v{0.f, 0.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * D + d;
+                    v.x = x[gi];
+                    v.m = load_mask(mk, gi, a.mask_kind);
+                }
+                return v;
+            },
+            [&](int d, int r, bool, XM v) {
+                if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = v.x * v.m;
+                else { in_s[d * P + r] = v.x; ms_s[d * P + r] = v.m; }
+            });
         __syncthreads();
         if (FAM == PCVAE_FAMILY_PNP) {
             pnp_embed<TM>(in_s, ms_s, A_s, C_s, agg_s, D, K4, tid);
@@ -204,6 +220,9 @@ struct EncBwdArgs {
     const float* d_logvar[2];
     const float* ac;
     float* gp;   // [grid][P]
+    const float* d_z[2];
+    const float* eps[2];
+    const float* logvar[2];
 };
 
 template <int FAM, int TM>
@@ -248,32 +267,48 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
         const int br = vt / ntiles, row0 = (vt - br * ntiles) * TM;
         const float* __restrict__ x = a.x;
         const void* __restrict__ mk = a.mask[br];
-        for_tile_elems<TM>(D, row0, a.B, tid, [&](int d, int r, bool ok) {
-            float xv = 0.f, mv = 0.f;
-            if (ok) {
-                const long gi = (long)(row0 + r) * D + d;
-                xv = x[gi];
-                mv = load_mask(mk, gi, a.mask_kind);
+        {   // L2 prefetch of this CTA's next tile while the current one is being processed
+            const int nvt = vt + gridDim.x;
+            if (nvt < ntiles * a.nbr) {
+                const int nbr_ = nvt / ntiles, nrow0 = (nvt - nbr_ * ntiles) * TM;
+                const long nrows = min(TM, a.B - nrow0);
+                prefetch_l2(x + (long)nrow0 * D, nrows * D * 4, tid);
+                const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
+                prefetch_l2((const char*)a.mask[nbr_] + (long)nrow0 * D * msz, nrows * D * msz, tid);
             }
-            if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = xv * mv;
-            else { in_s[d * P + r] = xv; ms_s[d * P + r] = mv; }
-        });
+        }
+        tile_elems<TM, 16, XM>(D, row0, a.B, tid,
+            [&](int d, int r, bool ok) {
+                XM v{0.f, 0.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * D + d;
+                    v.x = x[gi];
+                    v.m = load_mask(mk, gi, a.mask_kind);
+                }
+                return v;
+            },
+            [&](int d, int r, bool, XM v) {
+                if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = v.x * v.m;
+                else { in_s[d * P + r] = v.x; ms_s[d * P + r] = v.m; }
+            });
         {
             const float* ws = a.act_ws + (long)vt * act_tile;
             int f0 = 0;
             if (FAM == PCVAE_FAMILY_PNP) {
                 for (int i = tid; i < K4 * (TM / 4); i += NT) {
                     const int f = i / (TM / 4), c = i - f * (TM / 4);
-                    sts4(agg_s + f * P + 4 * c, *reinterpret_cast<const float4*>(ws + f * TM + 4 * c));
+                    __pipeline_memcpy_async(agg_s + f * P + 4 * c, ws + f * TM + 4 * c, 16);
                 }
                 f0 = K4;
             }
             for (int i = tid; i < (H1 + H2P) * (TM / 4); i += NT) {
                 const int f = i / (TM / 4), c = i - f * (TM / 4);
                 float* dst = (f < H1) ? (h1_s + f * P) : (h2_s + (f - H1) * P);
-                sts4(dst + 4 * c, *reinterpret_cast<const float4*>(ws + (f0 + f) * TM + 4 * c));
+                __pipeline_memcpy_async(dst + 4 * c, ws + (f0 + f) * TM + 4 * c, 16);
             }
+            __pipeline_commit();
         }
+#pragma unroll
         for (int i = tid; i < TM * LAT; i += NT) {
             const int r = i / LAT, l = i - r * LAT;
             float dm = 0.f, dv = 0.f;
@@ -281,10 +316,16 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
                 const long gi = (long)(row0 + r) * LAT + l;
                 dm = a.d_mean[br][gi];
                 dv = a.d_logvar[br][gi];
+                if (a.d_z[br]) {
+                    const float dz = a.d_z[br][gi];
+                    dm += dz;
+                    if (a.eps[br]) dv = fmaf(dz * 0.5f * expf(a.logvar[br][gi] * 0.5f), a.eps[br][gi], dv);
+                }
             }
             d3_s[l * P + r] = dm;
             d3_s[(LAT + l) * P + r] = dv;
         }
+        __pipeline_wait_prior(0);
         __syncthreads();
         gemm_dw<TM>(h2_s, d3_s, dW3_s, H2, LAT2, LAT2, tid);
         bias_dw<TM>(d3_s, db3_s, LAT2, tid);
@@ -416,7 +457,14 @@ __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
     const int ntiles = (a.B + TM - 1) / TM;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int row0 = t * TM;
+        if (lossy) {
+            const long nrows = min(TM, a.B - row0);
+            const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
+            prefetch_l2(a.x + (long)row0 * D, nrows * D * 4, tid);
+            for (int b = 0; b < a.nbr; ++b) prefetch_l2((const char*)a.mask[b] + (long)row0 * D * msz, nrows * D * msz, tid);
+        }
         for (int br = 0; br < a.nbr; ++br) {
+#pragma unroll
             for (int i = tid; i < TM * LAT; i += NT) {
                 const int r = i / LAT, l = i - r * LAT;
                 z_s[l * P + r] = (row0 + r < a.B) ? a.z[br][(long)(row0 + r) * LAT + l] : 0.f;
@@ -435,36 +483,48 @@ __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
                 const void* __restrict__ m0 = a.mask[0];
                 const void* __restrict__ m1 = a.mask[1];
                 const float* __restrict__ dxh = a.d_xhat[br];
-                for_tile_elems<TM>(DP, row0, a.B, tid, [&](int d, int r, bool ok) {
-                    const float xh = xh_s[d * P + r];
-                    float dpre = 0.f;
-                    if (ok && d < D) {
-                        const long gi = (long)(row0 + r) * D + d;
-                        if (xo) xo[gi] = xh;
-                        if (lossy) {
-                            const float xv = x[gi];
-                            const float m = load_mask(m0, gi, a.mask_kind) != 0.f ? 1.f : 0.f;
-                            const float mp = (a.nbr > 1) ? (load_mask(m1, gi, a.mask_kind) != 0.f ? 1.f : 0.f) : 0.f;
-                            const float diff = xv - xh;
-                            const float nll = fmaf(diff * diff, inv2var, log_scale);
-                            float coef;
-                            if (br == 0) {
-                                s_req += m * nll;
-                                s_red += m * (1.f - mp) * nll;
-                                s_imp += (1.f - m) * nll;
-                                s_sse += (1.f - m) * diff * diff;
-                                coef = (1.f - alpha) * m + alpha * m * (1.f - mp);
-                            } else {
-                                s_rep += mp * nll;
-                                coef = alpha * mp;
+                struct E { float xv, m, mp; };
+                tile_elems<TM, 16, E>(DP, row0, a.B, tid,
+                    [&](int d, int r, bool ok) {
+                        E e{0.f, 0.f, 0.f};
+                        if (ok && d < D) {
+                            const long gi = (long)(row0 + r) * D + d;
+                            if (lossy) {
+                                e.xv = x[gi];
+                                e.m = load_mask(m0, gi, a.mask_kind) != 0.f ? 1.f : 0.f;
+                                if (a.nbr > 1) e.mp = load_mask(m1, gi, a.mask_kind) != 0.f ? 1.f : 0.f;
+                            } else if (a.mode == PCVAE_DEC_BWD) {
+                                e.xv = dxh[gi];
                             }
-                            dpre = coef * (xh - xv) * inv_var * ls * xh * (1.f - xh);
-                        } else if (a.mode == PCVAE_DEC_BWD) {
-                            dpre = dxh[gi] * xh * (1.f - xh);
                         }
-                    }
-                    if (bwd) xh_s[d * P + r] = dpre;
-                });
+                        return e;
+                    },
+                    [&](int d, int r, bool ok, E e) {
+                        const float xh = xh_s[d * P + r];
+                        float dpre = 0.f;
+                        if (ok && d < D) {
+                            if (xo) xo[(long)(row0 + r) * D + d] = xh;
+                            if (lossy) {
+                                const float diff = e.xv - xh;
+                                const float nll = fmaf(diff * diff, inv2var, log_scale);
+                                float coef;
+                                if (br == 0) {
+                                    s_req += e.m * nll;
+                                    s_red += e.m * (1.f - e.mp) * nll;
+                                    s_imp += (1.f - e.m) * nll;
+                                    s_sse += (1.f - e.m) * diff * diff;
+                                    coef = (1.f - alpha) * e.m + alpha * e.m * (1.f - e.mp);
+                                } else {
+                                    s_rep += e.mp * nll;
+                                    coef = alpha * e.mp;
+                                }
+                                dpre = coef * (xh - e.xv) * inv_var * ls * xh * (1.f - xh);
+                            } else if (a.mode == PCVAE_DEC_BWD) {
+                                dpre = e.xv * xh * (1.f - xh);
+                            }
+                        }
+                        if (bwd) xh_s[d * P + r] = dpre;
+                    });
             }
             if (bwd) {
                 __syncthreads();
@@ -800,7 +860,11 @@ int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     EncBwdArgs a{};
     a.L = L; a.B = p->rows; a.nbr = p->n_branch; a.mask_kind = p->mask_kind; a.theta = p->theta; a.x = p->x;
-    for (int b = 0; b < 2; ++b) { a.mask[b] = p->mask[b]; a.d_mean[b] = p->d_mean[b]; a.d_logvar[b] = p->d_logvar[b]; }
+    for (int b = 0; b < 2; ++b) {
+        a.mask[b] = p->mask[b]; a.d_mean[b] = p->d_mean[b]; a.d_logvar[b] = p->d_logvar[b];
+        a.d_z[b] = p->d_z[b]; a.eps[b] = p->eps[b]; a.logvar[b] = p->logvar[b];
+        if (p->d_z[b] && p->eps[b] && !p->logvar[b]) return fail(PCVAE_EINVAL, "enc_bwd: d_z and eps given without logvar for branch %d", b);
+    }
     a.act_ws = p->act_ws; a.ac = p->pnp_ac; a.gp = p->grad_partials;
     if (L.fam == PCVAE_FAMILY_PNP) {
         if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_bwd: PNP family needs pnp_ac tables");

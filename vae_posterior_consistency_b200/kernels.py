@@ -141,15 +141,19 @@ class Engine:
             L.check(self.lib.pcvae_enc_fwd(C.byref(p), _stream()), "pcvae_enc_fwd")
         return mean, logvar, z, ws
 
-    def enc_bwd(self, theta, x, masks, ws, d_mean, d_logvar):
+    def enc_bwd(self, theta, x, masks, ws, d_mean, d_logvar, d_z=None, eps=None, logvar=None):
         x = _f32(x)
         kind, masks = prep_masks(masks)
         gp = self.grad_partials()
+        nb = len(masks)
         d_mean = [_f32(t) for t in d_mean]
         d_logvar = [_f32(t) for t in d_logvar]
-        p = L.EncBwdParams(model=self.model, rows=x.shape[0], n_branch=len(masks), mask_kind=kind, theta=_p(theta),
+        opt = lambda ts: [None] * nb if ts is None else [None if t is None else _f32(t) for t in ts]
+        d_z, eps, logvar = opt(d_z), opt(eps), opt(logvar)
+        p = L.EncBwdParams(model=self.model, rows=x.shape[0], n_branch=nb, mask_kind=kind, theta=_p(theta),
                            x=_p(x), mask=_pair(masks), act_ws=_p(ws), d_mean=_pair(d_mean),
-                           d_logvar=_pair(d_logvar), pnp_ac=_p(self.pnp_ac()), grad_partials=_p(gp))
+                           d_logvar=_pair(d_logvar), pnp_ac=_p(self.pnp_ac()), grad_partials=_p(gp),
+                           d_z=_pair(d_z), eps=_pair(eps), logvar=_pair(logvar))
         with torch.cuda.device(x.device):
             L.check(self.lib.pcvae_enc_bwd(C.byref(p), _stream()), "pcvae_enc_bwd")
         return gp

@@ -49,7 +49,8 @@ class EncFwdParams(C.Structure):
 class EncBwdParams(C.Structure):
     _fields_ = [("model", Model), ("rows", C.c_int), ("n_branch", C.c_int), ("mask_kind", C.c_int),
                 ("theta", C.c_void_p), ("x", C.c_void_p), ("mask", _P2), ("act_ws", C.c_void_p),
-                ("d_mean", _P2), ("d_logvar", _P2), ("pnp_ac", C.c_void_p), ("grad_partials", C.c_void_p)]
+                ("d_mean", _P2), ("d_logvar", _P2), ("pnp_ac", C.c_void_p), ("grad_partials", C.c_void_p),
+                ("d_z", _P2), ("eps", _P2), ("logvar", _P2)]
 
 
 class DecParams(C.Structure):

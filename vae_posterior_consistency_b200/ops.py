@@ -1,0 +1,217 @@
+"""PyTorch custom ops (`torch.library`, namespace `pcvae::`) over the C ABI, with autograd.
+
+These are what the nn.Module mirror in VAE.py composes, so that `model.forward`,
+`model.loss` and `train_loss.backward()` keep working exactly as the reference's callers
+expect (src/experiment_main/train.py:87-116) while every arithmetic step runs in
+libpcvae_b200.so.  All ops take the FLAT parameter vector `theta` (a differentiable
+`torch.cat` of the module's nn.Parameters), so gradients flow back to the individual
+parameters through autograd's own cat/view bookkeeping.
+
+There is no CPU implementation: calling an op with CPU tensors raises PcvaeError.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import kernels as KR
+from . import lib as L
+
+_ENGINES = {}
+
+
+def engine(family: int, D: int, K: int, device) -> KR.Engine:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise L.PcvaeError("pcvae ops need CUDA tensors: there is no CPU fallback for this path")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (family, D, K if family == L.FAMILY_PNP else 0, device.index)
+    if key not in _ENGINES:
+        _ENGINES[key] = KR.Engine(family, D, K, device)
+    return _ENGINES[key]
+
+
+# ------------------------------------------------------------------------------------------
+# encoder
+# ------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("pcvae::encoder", mutates_args=())
+def encoder_op(theta: Tensor, x: Tensor, mask: Tensor, eps: Optional[Tensor], family: int, D: int,
+               K: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(z, mean, logvar, saved activations).  VAE.py:387-395 / 719-741."""
+    eng = engine(family, D, K, x.device)
+    mean, logvar, z, ws = eng.enc_fwd(theta, x, [mask], [eps], save=True)
+    return z[0], mean[0], logvar[0], ws
+
+
+@encoder_op.register_fake
+def _(theta, x, mask, eps, family, D, K):
+    B = x.shape[0]
+    mk = lambda: x.new_empty(B, KR.LATENT, dtype=torch.float32)
+    return mk(), mk(), mk(), x.new_empty(1, dtype=torch.float32)
+
+
+@torch.library.custom_op("pcvae::encoder_bwd", mutates_args=())
+def encoder_bwd_op(theta: Tensor, x: Tensor, mask: Tensor, eps: Optional[Tensor], logvar: Tensor, ws: Tensor,
+                   d_z: Tensor, d_mean: Tensor, d_logvar: Tensor, family: int, D: int, K: int) -> Tensor:
+    eng = engine(family, D, K, x.device)
+    eng.enc_bwd(theta, x, [mask], ws, [d_mean], [d_logvar], d_z=[d_z], eps=[eps], logvar=[logvar])
+    grad = torch.zeros_like(theta)
+    eng.reduce_grads(grad, 0, eng.dec_off)
+    return grad
+
+
+@encoder_bwd_op.register_fake
+def _(theta, x, mask, eps, logvar, ws, d_z, d_mean, d_logvar, family, D, K):
+    return torch.empty_like(theta)
+
+
+def _enc_setup(ctx, inputs, output):
+    theta, x, mask, eps, family, D, K = inputs
+    z, mean, logvar, ws = output
+    ctx.save_for_backward(theta, x, mask, eps, logvar, ws)
+    ctx.cfg = (family, D, K)
+
+
+def _enc_backward(ctx, d_z, d_mean, d_logvar, d_ws):
+    theta, x, mask, eps, logvar, ws = ctx.saved_tensors
+    family, D, K = ctx.cfg
+    zeros = lambda: torch.zeros(x.shape[0], KR.LATENT, device=x.device)
+    d_z = zeros() if d_z is None else d_z
+    d_mean = zeros() if d_mean is None else d_mean
+    d_logvar = zeros() if d_logvar is None else d_logvar
+    g = encoder_bwd_op(theta, x, mask, eps, logvar, ws, d_z.contiguous(), d_mean.contiguous(),
+                       d_logvar.contiguous(), family, D, K)
+    return g, None, None, None, None, None, None
+
+
+torch.library.register_autograd("pcvae::encoder", _enc_backward, setup_context=_enc_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# decoder
+# ------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("pcvae::decoder", mutates_args=())
+def decoder_op(theta: Tensor, z: Tensor, family: int, D: int, K: int) -> Tensor:
+    """xhat = Sigmoid(seq_decoder(z)), VAE.py:397-401."""
+    eng = engine(family, D, K, z.device)
+    return eng.dec(L.DEC_FWD, theta, [z])["xhat"][0]
+
+
+@decoder_op.register_fake
+def _(theta, z, family, D, K):
+    return z.new_empty(z.shape[0], D, dtype=torch.float32)
+
+
+@torch.library.custom_op("pcvae::decoder_bwd", mutates_args=())
+def decoder_bwd_op(theta: Tensor, z: Tensor, d_xhat: Tensor, family: int, D: int, K: int) -> Tuple[Tensor, Tensor]:
+    eng = engine(family, D, K, z.device)
+    out = eng.dec(L.DEC_BWD, theta, [z], d_xhat=[d_xhat])
+    grad = torch.zeros_like(theta)
+    eng.reduce_grads(grad, eng.dec_off, eng.P)
+    return grad, out["d_z"][0]
+
+
+@decoder_bwd_op.register_fake
+def _(theta, z, d_xhat, family, D, K):
+    return torch.empty_like(theta), torch.empty_like(z)
+
+
+def _dec_setup(ctx, inputs, output):
+    theta, z, family, D, K = inputs
+    ctx.save_for_backward(theta, z)
+    ctx.cfg = (family, D, K)
+
+
+def _dec_backward(ctx, d_xhat):
+    theta, z = ctx.saved_tensors
+    family, D, K = ctx.cfg
+    g, dz = decoder_bwd_op(theta, z, d_xhat.contiguous(), family, D, K)
+    return g, dz, None, None, None
+
+
+torch.library.register_autograd("pcvae::decoder", _dec_backward, setup_context=_dec_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# loss
+# ------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("pcvae::vae_loss", mutates_args=())
+def vae_loss_op(x: Tensor, mask: Tensor, mask_p: Optional[Tensor], xhat_q: Tensor, xhat_p: Optional[Tensor],
+                mean_q: Tensor, logvar_q: Tensor, mean_p: Optional[Tensor], logvar_p: Optional[Tensor],
+                alpha: float, beta_w: float, loss_scale: float, x_logvar: float, want_grads: bool
+                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """(loss * loss_scale as a 0-dim fp32 tensor, sums[8] float64, and the gradients of that loss
+    w.r.t. xhat_q, mean_q, logvar_q, xhat_p, mean_p, logvar_p -- empty tensors when not computed).
+    VAE.py:403-467 / 749-817 / 933-964 / 1171-1208."""
+    reg = mask_p is not None
+    D = x.shape[1]
+    eng = engine(L.FAMILY_MLP, D, 0, x.device)          # the loss kernel does not depend on the family
+    masks = [mask, mask_p] if reg else [mask]
+    xh = [xhat_q, xhat_p] if reg else [xhat_q]
+    mu = [mean_q, mean_p] if reg else [mean_q]
+    lv = [logvar_q, logvar_p] if reg else [logvar_q]
+    sums, d_xh, d_mu, d_lv = eng.loss_terms(x, masks, xh, mu, lv, alpha if reg else 0.0, beta_w, loss_scale,
+                                            want_grads, x_logvar=x_logvar)
+    loss = (KR.loss_from_sums(sums, 1, alpha, beta_w, reg) * loss_scale).to(torch.float32)
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    if not want_grads:
+        return loss, sums, e(), e(), e(), e(), e(), e()
+    if not reg:
+        return loss, sums, d_xh[0], d_mu[0], d_lv[0], e(), e(), e()
+    return loss, sums, d_xh[0], d_mu[0], d_lv[0], d_xh[1], d_mu[1], d_lv[1]
+
+
+@vae_loss_op.register_fake
+def _(x, mask, mask_p, xhat_q, xhat_p, mean_q, logvar_q, mean_p, logvar_p, alpha, beta_w, loss_scale, x_logvar,
+      want_grads):
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    g = [e() for _ in range(6)]
+    if want_grads:
+        g[:3] = [torch.empty_like(xhat_q), torch.empty_like(mean_q), torch.empty_like(logvar_q)]
+        if mask_p is not None:
+            g[3:] = [torch.empty_like(xhat_p), torch.empty_like(mean_p), torch.empty_like(logvar_p)]
+    return (x.new_empty((), dtype=torch.float32), x.new_empty(L.NSUMS, dtype=torch.float64), *g)
+
+
+def _loss_setup(ctx, inputs, output):
+    ctx.reg = inputs[2] is not None
+    ctx.has_grads = inputs[13]
+    ctx.save_for_backward(*output[2:])
+
+
+def _loss_backward(ctx, d_loss, *unused):
+    if not ctx.has_grads:
+        raise RuntimeError("pcvae::vae_loss was run with want_grads=False")
+    g = ctx.saved_tensors
+    sc = lambda t: t * d_loss
+    out = [None] * 14
+    out[3], out[5], out[6] = sc(g[0]), sc(g[1]), sc(g[2])
+    if ctx.reg:
+        out[4], out[7], out[8] = sc(g[3]), sc(g[4]), sc(g[5])
+    return tuple(out)
+
+
+torch.library.register_autograd("pcvae::vae_loss", _loss_backward, setup_context=_loss_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# reward
+# ------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("pcvae::reward_chain", mutates_args=())
+def reward_chain_op(theta: Tensor, x: Tensor, mask: Tensor, im: Tensor, family: int, D: int, K: int) -> Tensor:
+    """R[N, D-1] of one acquisition step, evaluate.py:416-425 + 514-634."""
+    eng = engine(family, D, K, x.device)
+    R, _ = eng.reward(theta, x, mask, im)
+    return R
+
+
+@reward_chain_op.register_fake
+def _(theta, x, mask, im, family, D, K):
+    return x.new_empty(x.shape[0], D - 1, dtype=torch.float32)
