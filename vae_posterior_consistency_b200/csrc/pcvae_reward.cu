@@ -60,6 +60,7 @@ __device__ __forceinline__ void write_base(const float* o_s, int P, float* __res
 template <int FAM>
 __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int RB = 1;
     constexpr int TM = TM_TRAIN, P = TM + 4;
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
@@ -91,9 +92,9 @@ __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
     __syncthreads();
 
     auto tail = [&](float* dst, long stride, int row0) {
-        gemm_fwd<TM, ACT_RELU>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
+        gemm_fwd<TM, RB, ACT_RELU>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
         __syncthreads();
-        gemm_fwd<TM, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
+        gemm_fwd<TM, RB, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
         __syncthreads();
         write_base(o_s, P, dst, stride, row0, a.N, TM, tid);
     };
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
         }
         __syncthreads();
         if (FAM == PCVAE_FAMILY_MLP) {
-            gemm_fwd<TM, ACT_NONE>(in_s, W1_s, b1_s, h0_s, D, H1, tid);        // h0 = W1 (x*mask) + b1
+            gemm_fwd<TM, RB, ACT_NONE>(in_s, W1_s, b1_s, h0_s, D, H1, tid);        // h0 = W1 (x*mask) + b1
             __syncthreads();
             for (int i = tid; i < H1 * TM; i += NT) {
                 const int k = i / TM, r = i - k * TM;
@@ -138,13 +139,13 @@ __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
                     if (ok) a.base_in[(long)(row0 + r) * INW + k] = h0_s[k * P + r];
                 });
         } else {
-            pnp_embed<TM>(in_s, ms_s, A_s, C_s, agg_s, D, K4, tid);      // agg0
+            pnp_embed<TM>(in_s, ms_s, A_s, C_s, agg_s, h1_s, (H1 + H2P) * P, D, K4, tid);      // agg0
             __syncthreads();
             tile_elems<TM, 1, int>(K4, row0, a.N, tid, [](int, int, bool) { return 0; },
                 [&](int j, int r, bool ok, int) {
                     if (ok) a.base_in[(long)(row0 + r) * INW + j] = agg_s[j * P + r];
                 });
-            gemm_fwd<TM, ACT_RELU>(agg_s, W1_s, b1_s, h1_s, K, H1, tid);
+            gemm_fwd<TM, RB, ACT_RELU>(agg_s, W1_s, b1_s, h1_s, K, H1, tid);
         }
         __syncthreads();
         tail(a.base0, BASEW, row0);
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
                     aggT_s[j * P + r] = agg_s[j * P + r] + e;
                 }
                 __syncthreads();
-                gemm_fwd<TM, ACT_RELU>(aggT_s, W1_s, b1_s, h1_s, K, H1, tid);
+                gemm_fwd<TM, RB, ACT_RELU>(aggT_s, W1_s, b1_s, h1_s, K, H1, tid);
             }
             __syncthreads();
             tail(a.baseT + (long)m * BASEW, (long)a.M * BASEW, row0);
@@ -204,6 +205,7 @@ __global__ void k_pairs(const int* __restrict__ cnt, const int* __restrict__ off
 template <int FAM>
 __global__ void __launch_bounds__(NT, 1) k_reward_main(const RewardArgs a) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int RB = 1;
     constexpr int TM = TM_REWARD, P = TM + 4, NP_ = NPAIR;
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
@@ -310,12 +312,12 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main(const RewardArgs a) {
                     hin_s[j * P + NP_ + i] = (H0_s[idx] + eT) + eu;
                 }
                 __syncthreads();
-                gemm_fwd<TM, ACT_RELU>(hin_s, W1_s, b1_s, h_s, K, H1, tid);
+                gemm_fwd<TM, RB, ACT_RELU>(hin_s, W1_s, b1_s, h_s, K, H1, tid);
             }
             __syncthreads();
-            gemm_fwd<TM, ACT_RELU>(h_s, W2_s, b2_s, h2_s, H1, H2P, tid);
+            gemm_fwd<TM, RB, ACT_RELU>(h_s, W2_s, b2_s, h2_s, H1, H2P, tid);
             __syncthreads();
-            gemm_fwd<TM, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
+            gemm_fwd<TM, RB, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
             __syncthreads();
             // KL terms, evaluate.py:582-583 / 631-632 (divide by std, not variance)
             for (int idx = tid; idx < 2 * LAT * NP_; idx += NT) {

@@ -12,14 +12,14 @@
 // The dense layers here are 10..128 wide in true FP32 (north_star: masks/indices
 // bit-exact, fp32 losses to 1e-4), so they are register-blocked FFMA mini-GEMMs; each
 // thread keeps an 8x4 (rows x outputs) block and per reduction step issues 3 LDS.128
-// for 32 FFMA.
+// for 32 FFMA (RB=2) or a 4x4 block with 2 LDS.128 per 16 FFMA (RB=1, twice the warps).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace pcvae {
 
-constexpr int NT = 256;          // threads per CTA
+constexpr int NT = 512;          // threads per CTA (16 warps, <= 128 registers each)
 constexpr int NWARP = NT / 32;
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
@@ -60,51 +60,55 @@ __device__ __forceinline__ void zero_floats(float* p, int n, int tid) {
 
 // ---------------------------------------------------------------------------------
 // C[n][r] = act(b[n] + sum_k A[k][r] * W[k][n]),  n < NP (pad outputs get act(0)).
-// lane -> (row group rg, output group); a thread owns rows {4rg..4rg+3} and
-// {TM/2+4rg..+3} and 4 consecutive outputs.
+// lane -> (row group rg, output group); a thread owns RB chunks of 4 rows
+// ({c*TM/RB + 4rg .. +3}, c < RB) and 4 consecutive outputs: per reduction step
+// RB+1 LDS.128 feed 16*RB FFMA.
 // ---------------------------------------------------------------------------------
-template <int TM, int ACT>
+template <int TM, int RB, int ACT>
 __device__ __forceinline__ void gemm_fwd(const float* __restrict__ A_s, const float* __restrict__ W_s,
                                          const float* __restrict__ b_s, float* __restrict__ C_s,
                                          int K, int NP, int tid) {
     constexpr int P = TM + 4;
-    constexpr int RG = TM / 8;       // row groups: 8 (TM=64) / 16 (TM=128)
-    constexpr int NGW = 32 / RG;     // output groups per warp
+    constexpr int RG = TM / (4 * RB);   // row groups
+    constexpr int NGW = 32 / RG;        // output groups per warp
+    constexpr int CS = TM / RB;         // row offset between a thread's chunks
+    static_assert(RG <= 32 && 32 % RG == 0, "row groups must tile a warp");
     const int lane = tid & 31, warp = tid >> 5;
     const int rg = lane % RG, ngl = lane / RG;
-    const int r0 = 4 * rg, r1 = TM / 2 + 4 * rg;
+    const int r0 = 4 * rg;
     for (int ng = warp * NGW + ngl; ng < NP / 4; ng += NWARP * NGW) {
         const int n0 = 4 * ng;
-        float acc[8][4];
+        float acc[4 * RB][4];
         {
             float4 bv = lds4(b_s + n0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
+            for (int i = 0; i < 4 * RB; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
         }
         const float* ap = A_s + r0;
         const float* wp = W_s + n0;
 #pragma unroll 4
         for (int k = 0; k < K; ++k) {
-            const float4 a0 = lds4(ap + k * P);
-            const float4 a1 = lds4(ap + k * P + (r1 - r0));
             const float4 w = lds4(wp + k * NP);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int c = 0; c < RB; ++c) {
+                const float4 a = lds4(ap + k * P + c * CS);
+                const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[4 * c + i][j] = fmaf(av[i], wv[j], acc[4 * c + i][j]);
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 o0, o1;
-            o0.x = act_apply(acc[0][j], ACT); o0.y = act_apply(acc[1][j], ACT);
-            o0.z = act_apply(acc[2][j], ACT); o0.w = act_apply(acc[3][j], ACT);
-            o1.x = act_apply(acc[4][j], ACT); o1.y = act_apply(acc[5][j], ACT);
-            o1.z = act_apply(acc[6][j], ACT); o1.w = act_apply(acc[7][j], ACT);
-            sts4(C_s + (n0 + j) * P + r0, o0);
-            sts4(C_s + (n0 + j) * P + r1, o1);
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < RB; ++c) {
+                float4 o;
+                o.x = act_apply(acc[4 * c + 0][j], ACT); o.y = act_apply(acc[4 * c + 1][j], ACT);
+                o.z = act_apply(acc[4 * c + 2][j], ACT); o.w = act_apply(acc[4 * c + 3][j], ACT);
+                sts4(C_s + (n0 + j) * P + r0 + c * CS, o);
+            }
     }
 }
 
@@ -114,16 +118,17 @@ __device__ __forceinline__ void gemm_fwd(const float* __restrict__ A_s, const fl
 // the ReLU mask) and is overwritten in place.  n runs over NP (pad rows of dY must be
 // finite; pad weights are zero).
 // ---------------------------------------------------------------------------------
-template <int TM, bool RELU_MASK>
+template <int TM, int RB, bool RELU_MASK>
 __device__ __forceinline__ void gemm_dx(const float* __restrict__ dY_s, const float* __restrict__ W_s,
                                         float* __restrict__ out_s, int Kout, int NP, int tid) {
     constexpr int P = TM + 4;
-    constexpr int RG = TM / 8;
+    constexpr int RG = TM / (4 * RB);
     constexpr int NGW = 32 / RG;
+    constexpr int CS = TM / RB;
     constexpr int KB = 4 * NGW;      // outputs (k) covered by one warp per iteration
     const int lane = tid & 31, warp = tid >> 5;
     const int rg = lane % RG, kgl = lane / RG;
-    const int r0 = 4 * rg, r1 = TM / 2 + 4 * rg;
+    const int r0 = 4 * rg;
     for (int kb = warp * KB; kb < Kout; kb += NWARP * KB) {
         int kk[4];
         const float* wrow[4];
@@ -132,12 +137,12 @@ __device__ __forceinline__ void gemm_dx(const float* __restrict__ dY_s, const fl
             kk[j] = kb + kgl + NGW * j;
             wrow[j] = W_s + min(kk[j], Kout - 1) * NP;
         }
-        float acc[8][4];
+        float acc[4 * RB][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4 * RB; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-#pragma unroll 1
+#pragma unroll 2
         for (int n = 0; n < NP; n += 4) {
             float wv[4][4];
 #pragma unroll
@@ -146,31 +151,31 @@ __device__ __forceinline__ void gemm_dx(const float* __restrict__ dY_s, const fl
                 wv[j][0] = w.x; wv[j][1] = w.y; wv[j][2] = w.z; wv[j][3] = w.w;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 a0 = lds4(dY_s + (n + q) * P + r0);
-                const float4 a1 = lds4(dY_s + (n + q) * P + r1);
-                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int c = 0; c < RB; ++c) {
+                    const float4 a = lds4(dY_s + (n + q) * P + r0 + c * CS);
+                    const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j][q], acc[i][j]);
-            }
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[4 * c + i][j] = fmaf(av[i], wv[j][q], acc[4 * c + i][j]);
+                }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (kk[j] < Kout) {
-                float* o = out_s + kk[j] * P;
-                float4 v0 = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
-                float4 v1 = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
-                if (RELU_MASK) {
-                    const float4 h0 = lds4(o + r0), h1 = lds4(o + r1);
-                    v0.x = h0.x > 0.f ? v0.x : 0.f; v0.y = h0.y > 0.f ? v0.y : 0.f;
-                    v0.z = h0.z > 0.f ? v0.z : 0.f; v0.w = h0.w > 0.f ? v0.w : 0.f;
-                    v1.x = h1.x > 0.f ? v1.x : 0.f; v1.y = h1.y > 0.f ? v1.y : 0.f;
-                    v1.z = h1.z > 0.f ? v1.z : 0.f; v1.w = h1.w > 0.f ? v1.w : 0.f;
+                float* o = out_s + kk[j] * P + r0;
+#pragma unroll
+                for (int c = 0; c < RB; ++c) {
+                    float4 v = make_float4(acc[4 * c][j], acc[4 * c + 1][j], acc[4 * c + 2][j], acc[4 * c + 3][j]);
+                    if (RELU_MASK) {
+                        const float4 h = lds4(o + c * CS);
+                        v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f;
+                        v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+                    }
+                    sts4(o + c * CS, v);
                 }
-                sts4(o + r0, v0);
-                sts4(o + r1, v1);
             }
         }
     }
@@ -303,45 +308,60 @@ __device__ __forceinline__ void prefetch_l2(const void* base, long bytes, int ti
 }
 
 // agg[j][r] = sum_d m[d][r] * relu(x[d][r] * A[d][j] + C[d][j])     (VAE.py:726-733)
+// The feature loop is split into SEG segments so that all warps have work; segment partials
+// go to `scratch` ([SEG][K4][P] floats) and are summed in a fixed order (deterministic).
+// Contains __syncthreads(): call from all threads.
 template <int TM>
 __device__ __forceinline__ void pnp_embed(const float* __restrict__ xs, const float* __restrict__ ms,
                                           const float* __restrict__ A_s, const float* __restrict__ C_s,
-                                          float* __restrict__ agg_s, int D, int K4, int tid) {
+                                          float* __restrict__ agg_s, float* __restrict__ scratch, int scratch_floats,
+                                          int D, int K4, int tid) {
     constexpr int P = TM + 4;
-    constexpr int RG = TM / 8;
+    constexpr int RG = TM / 4;
     constexpr int NGW = 32 / RG;
     const int lane = tid & 31, warp = tid >> 5;
     const int rg = lane % RG, ngl = lane / RG;
-    const int r0 = 4 * rg, r1 = TM / 2 + 4 * rg;
-    for (int ng = warp * NGW + ngl; ng < K4 / 4; ng += NWARP * NGW) {
-        const int n0 = 4 * ng;
-        float acc[8][4];
+    const int r0 = 4 * rg;
+    const int ngs = K4 / 4;                               // output groups
+    int seg = (NWARP * NGW) / ngs;                        // feature segments that fit the CTA
+    seg = max(1, min(seg, min(D, scratch_floats / (K4 * P))));
+    const int dper = (D + seg - 1) / seg;
+    for (int item = warp * NGW + ngl; item < ngs * seg; item += NWARP * NGW) {
+        const int ng = item % ngs, sg = item / ngs;
+        const int n0 = 4 * ng, d0 = sg * dper, d1 = min(D, d0 + dper);
+        float acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 2
-        for (int d = 0; d < D; ++d) {
-            const float4 x0 = lds4(xs + d * P + r0), x1 = lds4(xs + d * P + r1);
-            const float4 m0 = lds4(ms + d * P + r0), m1 = lds4(ms + d * P + r1);
+        for (int d = d0; d < d1; ++d) {
+            const float4 x0 = lds4(xs + d * P + r0), m0 = lds4(ms + d * P + r0);
             const float4 a = lds4(A_s + d * K4 + n0), c = lds4(C_s + d * K4 + n0);
-            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const float xv[4] = {x0.x, x0.y, x0.z, x0.w}, mv[4] = {m0.x, m0.y, m0.z, m0.w};
             const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     acc[i][j] = fmaf(mv[i], fmaxf(fmaf(xv[i], av[j], cv[j]), 0.f), acc[i][j]);
         }
+        float* dst = scratch + sg * K4 * P;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            sts4(agg_s + (n0 + j) * P + r0, make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
-            sts4(agg_s + (n0 + j) * P + r1, make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]));
+        for (int j = 0; j < 4; ++j)
+            sts4(dst + (n0 + j) * P + r0, make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
+    }
+    __syncthreads();
+    for (int i = tid; i < K4 * (TM / 4); i += NT) {
+        const int j = i / (TM / 4), c4 = 4 * (i - j * (TM / 4));
+        float4 s = lds4(scratch + j * P + c4);
+        for (int sg = 1; sg < seg; ++sg) {
+            const float4 v = lds4(scratch + sg * K4 * P + j * P + c4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
+        sts4(agg_s + j * P + c4, s);
     }
 }
-
 
 __device__ __forceinline__ float load_mask(const void* __restrict__ m, long idx, int kind) {
     if (kind == 0) return reinterpret_cast<const uint8_t*>(m)[idx] ? 1.0f : 0.0f;

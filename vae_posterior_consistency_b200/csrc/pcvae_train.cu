@@ -28,56 +28,41 @@ __global__ void k_pnp_tables(Layout L, const float* __restrict__ theta, float* _
     }
 }
 
-// dA[d][j] += sum_r t,  dC[d][j] += sum_r t * x   with  t = m * [x A + C > 0] * dagg[j][r]
+// dC[d][j] += sum_r t,  dA[d][j] += sum_r t * x   with  t = m * [x A + C > 0] * dagg[j][r].
+// One thread per (feature d, group of 4 embedding columns): consecutive lanes take consecutive
+// features (conflict-free with the +4 pitch), the dagg loads are warp broadcasts; each (d,j) has
+// exactly one owner, so the shared-memory accumulate is race-free and deterministic.
 template <int TM>
 __device__ __forceinline__ void pnp_embed_bwd(const float* __restrict__ xs, const float* __restrict__ ms,
                                               const float* __restrict__ dagg_s, const float* __restrict__ A_s,
                                               const float* __restrict__ C_s, float* __restrict__ dA_s,
                                               float* __restrict__ dC_s, int D, int K, int K4, int tid) {
     constexpr int P = TM + 4;
-    const int hw = tid >> 4, hl = tid & 15;
-    const int dl = hl & 3, jl = hl >> 2;
-    const int nbd = (D + 19) / 20, nbj = (K + 19) / 20;
-    for (int blk = hw; blk < nbd * nbj; blk += NT / 16) {
-        const int db = (blk % nbd) * 20, jb = (blk / nbd) * 20;
-        float accA[5][5], accC[5][5], av[5][5], cv[5][5];
-        int dd[5], jj[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) { dd[i] = min(db + dl + 4 * i, D - 1); jj[i] = min(jb + jl + 4 * i, K - 1); }
-#pragma unroll
-        for (int i = 0; i < 5; ++i)
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                accA[i][j] = 0.f; accC[i][j] = 0.f;
-                av[i][j] = A_s[dd[i] * K4 + jj[j]]; cv[i][j] = C_s[dd[i] * K4 + jj[j]];
-            }
-#pragma unroll 1
+    const int ngs = K4 / 4;
+    for (int item = tid; item < D * ngs; item += NT) {
+        const int jg = item / D, d = item - jg * D, j0 = 4 * jg;
+        const float4 a4 = lds4(A_s + d * K4 + j0), c4 = lds4(C_s + d * K4 + j0);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+        float accA[4] = {0.f, 0.f, 0.f, 0.f}, accC[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
         for (int r = 0; r < TM; r += 4) {
-            float4 xv[5], mv[5];
+            const float4 x4 = lds4(xs + d * P + r), m4 = lds4(ms + d * P + r);
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { xv[i] = lds4(xs + dd[i] * P + r); mv[i] = lds4(ms + dd[i] * P + r); }
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 g4 = lds4(dagg_s + (j0 + jj) * P + r);
+                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float4 g = lds4(dagg_s + jj[j] * P + r);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    float t;
-                    t = (fmaf(xv[i].x, av[i][j], cv[i][j]) > 0.f) ? mv[i].x * g.x : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].x, accA[i][j]);
-                    t = (fmaf(xv[i].y, av[i][j], cv[i][j]) > 0.f) ? mv[i].y * g.y : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].y, accA[i][j]);
-                    t = (fmaf(xv[i].z, av[i][j], cv[i][j]) > 0.f) ? mv[i].z * g.z : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].z, accA[i][j]);
-                    t = (fmaf(xv[i].w, av[i][j], cv[i][j]) > 0.f) ? mv[i].w * g.w : 0.f; accC[i][j] += t; accA[i][j] = fmaf(t, xv[i].w, accA[i][j]);
+                for (int i = 0; i < 4; ++i) {
+                    const float tval = (fmaf(xv[i], av[jj], cv[jj]) > 0.f) ? mv[i] * gv[i] : 0.f;
+                    accC[jj] += tval;
+                    accA[jj] = fmaf(tval, xv[i], accA[jj]);
                 }
             }
         }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int d = db + dl + 4 * i;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int q = jb + jl + 4 * j;
-                if (d < D && q < K) { dA_s[d * K4 + q] += accA[i][j]; dC_s[d * K4 + q] += accC[i][j]; }
-            }
-        }
+        for (int jj = 0; jj < 4; ++jj)
+            if (j0 + jj < K) { dA_s[d * K4 + j0 + jj] += accA[jj]; dC_s[d * K4 + j0 + jj] += accC[jj]; }
     }
 }
 
@@ -105,6 +90,7 @@ struct EncFwdArgs {
 template <int FAM, int TM>
 __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int RB = 1;   // 4x4 register blocks (see pcvae_tile.cuh)
     constexpr int P = TM + 4;
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
@@ -163,16 +149,16 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
             });
         __syncthreads();
         if (FAM == PCVAE_FAMILY_PNP) {
-            pnp_embed<TM>(in_s, ms_s, A_s, C_s, agg_s, D, K4, tid);
+            pnp_embed<TM>(in_s, ms_s, A_s, C_s, agg_s, h1_s, (H1 + H2P) * P, D, K4, tid);
             __syncthreads();
-            gemm_fwd<TM, ACT_RELU>(agg_s, W1_s, b1_s, h1_s, K, H1, tid);
+            gemm_fwd<TM, RB, ACT_RELU>(agg_s, W1_s, b1_s, h1_s, K, H1, tid);
         } else {
-            gemm_fwd<TM, ACT_RELU>(in_s, W1_s, b1_s, h1_s, D, H1, tid);
+            gemm_fwd<TM, RB, ACT_RELU>(in_s, W1_s, b1_s, h1_s, D, H1, tid);
         }
         __syncthreads();
-        gemm_fwd<TM, ACT_RELU>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
+        gemm_fwd<TM, RB, ACT_RELU>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
         __syncthreads();
-        gemm_fwd<TM, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
+        gemm_fwd<TM, RB, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
         __syncthreads();
         // outputs (row-major [B][L]); reparameterisation z = mean + eps * exp(logvar/2)  (VAE.py:390-392)
         for (int i = tid; i < TM * LAT; i += NT) {
@@ -228,6 +214,7 @@ struct EncBwdArgs {
 template <int FAM, int TM>
 __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int RB = 1;   // 4x4 register blocks (see pcvae_tile.cuh)
     constexpr int P = TM + 4;
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
@@ -330,12 +317,12 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
         gemm_dw<TM>(h2_s, d3_s, dW3_s, H2, LAT2, LAT2, tid);
         bias_dw<TM>(d3_s, db3_s, LAT2, tid);
         __syncthreads();
-        gemm_dx<TM, true>(d3_s, W3_s, h2_s, H2, LAT2, tid);     // h2_s <- dL/d(pre2)
+        gemm_dx<TM, RB, true>(d3_s, W3_s, h2_s, H2, LAT2, tid);     // h2_s <- dL/d(pre2)
         __syncthreads();
         gemm_dw<TM>(h1_s, h2_s, dW2_s, H1, H2, H2P, tid);
         bias_dw<TM>(h2_s, db2_s, H2, tid);
         __syncthreads();
-        gemm_dx<TM, true>(h2_s, W2_s, h1_s, H1, H2P, tid);      // h1_s <- dL/d(pre1)
+        gemm_dx<TM, RB, true>(h2_s, W2_s, h1_s, H1, H2P, tid);      // h1_s <- dL/d(pre1)
         __syncthreads();
         if (FAM == PCVAE_FAMILY_MLP) {
             gemm_dw<TM>(in_s, h1_s, dW1_s, D, H1, H1, tid);
@@ -344,7 +331,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
             gemm_dw<TM>(agg_s, h1_s, dW1_s, K, H1, H1, tid);
             bias_dw<TM>(h1_s, db1_s, H1, tid);
             __syncthreads();
-            gemm_dx<TM, false>(h1_s, W1_s, agg_s, K, H1, tid);  // agg_s <- dL/d(agg)
+            gemm_dx<TM, RB, false>(h1_s, W1_s, agg_s, K, H1, tid);  // agg_s <- dL/d(agg)
             __syncthreads();
             pnp_embed_bwd<TM>(in_s, ms_s, agg_s, A_s, C_s, dA_s, dC_s, D, K, K4, tid);
         }
@@ -412,6 +399,7 @@ struct DecArgs {
 template <int TM>
 __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int RB = 1;   // 4x4 register blocks (see pcvae_tile.cuh)
     __shared__ float red_s[NWARP][PCVAE_NSUMS];
     constexpr int P = TM + 4;
     const int tid = threadIdx.x;
@@ -470,11 +458,11 @@ __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
                 z_s[l * P + r] = (row0 + r < a.B) ? a.z[br][(long)(row0 + r) * LAT + l] : 0.f;
             }
             __syncthreads();
-            gemm_fwd<TM, ACT_RELU>(z_s, W4_s, b4_s, g1_s, LAT, G1P, tid);
+            gemm_fwd<TM, RB, ACT_RELU>(z_s, W4_s, b4_s, g1_s, LAT, G1P, tid);
             __syncthreads();
-            gemm_fwd<TM, ACT_RELU>(g1_s, W5_s, b5_s, g2_s, G1, G2, tid);
+            gemm_fwd<TM, RB, ACT_RELU>(g1_s, W5_s, b5_s, g2_s, G1, G2, tid);
             __syncthreads();
-            gemm_fwd<TM, ACT_SIGMOID>(g2_s, W6_s, b6_s, xh_s, G2, DP, tid);
+            gemm_fwd<TM, RB, ACT_SIGMOID>(g2_s, W6_s, b6_s, xh_s, G2, DP, tid);
             __syncthreads();
             // ---- element-wise: outputs, loss terms, dL/d(pre-sigmoid) ----
             {
@@ -484,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
                 const void* __restrict__ m1 = a.mask[1];
                 const float* __restrict__ dxh = a.d_xhat[br];
                 struct E { float xv, m, mp; };
-                tile_elems<TM, 16, E>(DP, row0, a.B, tid,
+                tile_elems<TM, 7, E>(DP, row0, a.B, tid,
                     [&](int d, int r, bool ok) {
                         E e{0.f, 0.f, 0.f};
                         if (ok && d < D) {
@@ -531,17 +519,17 @@ __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
                 gemm_dw<TM>(g2_s, xh_s, dW6_s, G2, D, DP, tid);
                 bias_dw<TM>(xh_s, db6_s, D, tid);
                 __syncthreads();
-                gemm_dx<TM, true>(xh_s, W6_s, g2_s, G2, DP, tid);
+                gemm_dx<TM, RB, true>(xh_s, W6_s, g2_s, G2, DP, tid);
                 __syncthreads();
                 gemm_dw<TM>(g1_s, g2_s, dW5_s, G1, G2, G2, tid);
                 bias_dw<TM>(g2_s, db5_s, G2, tid);
                 __syncthreads();
-                gemm_dx<TM, true>(g2_s, W5_s, g1_s, G1, G2, tid);
+                gemm_dx<TM, RB, true>(g2_s, W5_s, g1_s, G1, G2, tid);
                 __syncthreads();
                 gemm_dw<TM>(z_s, g1_s, dW4_s, LAT, G1, G1P, tid);
                 bias_dw<TM>(g1_s, db4_s, G1, tid);
                 __syncthreads();
-                gemm_dx<TM, false>(g1_s, W4_s, z_s, LAT, G1P, tid);   // z_s <- dL/dz
+                gemm_dx<TM, RB, false>(g1_s, W4_s, z_s, LAT, G1P, tid);   // z_s <- dL/dz
                 __syncthreads();
             }
             // ---- latent-space terms: KL sums, d_mean / d_logvar, d_z ----
