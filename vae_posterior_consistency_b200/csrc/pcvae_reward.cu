@@ -92,9 +92,9 @@ __global__ void __launch_bounds__(NT, 1) k_reward_prep(const RewardArgs a) {
     __syncthreads();
 
     auto tail = [&](float* dst, long stride, int row0) {
-        gemm_fwd<TM, RB, ACT_RELU>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
+        gemm_fwd<TM, RB, ACT_RELU, 2>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
         __syncthreads();
-        gemm_fwd<TM, RB, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
+        gemm_fwd<TM, RB, ACT_NONE, 2>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
         __syncthreads();
         write_base(o_s, P, dst, stride, row0, a.N, TM, tid);
     };
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main(const RewardArgs a) {
             __syncthreads();
             gemm_fwd<TM, RB, ACT_RELU>(h_s, W2_s, b2_s, h2_s, H1, H2P, tid);
             __syncthreads();
-            gemm_fwd<TM, RB, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
+            gemm_fwd<TM, RB, ACT_NONE, 2>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
             __syncthreads();
             // KL terms, evaluate.py:582-583 / 631-632 (divide by std, not variance)
             for (int idx = tid; idx < 2 * LAT * NP_; idx += NT) {

@@ -64,7 +64,7 @@ __device__ __forceinline__ void zero_floats(float* p, int n, int tid) {
 // ({c*TM/RB + 4rg .. +3}, c < RB) and 4 consecutive outputs: per reduction step
 // RB+1 LDS.128 feed 16*RB FFMA.
 // ---------------------------------------------------------------------------------
-template <int TM, int RB, int ACT>
+template <int TM, int RB, int ACT, int RN = 4>
 __device__ __forceinline__ void gemm_fwd(const float* __restrict__ A_s, const float* __restrict__ W_s,
                                          const float* __restrict__ b_s, float* __restrict__ C_s,
                                          int K, int NP, int tid) {
@@ -73,23 +73,26 @@ __device__ __forceinline__ void gemm_fwd(const float* __restrict__ A_s, const fl
     constexpr int NGW = 32 / RG;        // output groups per warp
     constexpr int CS = TM / RB;         // row offset between a thread's chunks
     static_assert(RG <= 32 && 32 % RG == 0, "row groups must tile a warp");
+    static_assert(RN == 4 || RN == 2, "RN: outputs per thread");
     const int lane = tid & 31, warp = tid >> 5;
     const int rg = lane % RG, ngl = lane / RG;
     const int r0 = 4 * rg;
-    for (int ng = warp * NGW + ngl; ng < NP / 4; ng += NWARP * NGW) {
-        const int n0 = 4 * ng;
-        float acc[4 * RB][4];
-        {
-            float4 bv = lds4(b_s + n0);
+    for (int ng = warp * NGW + ngl; ng < NP / RN; ng += NWARP * NGW) {
+        const int n0 = RN * ng;
+        float acc[4 * RB][RN];
 #pragma unroll
-            for (int i = 0; i < 4 * RB; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
+        for (int j = 0; j < RN; ++j) {
+            const float bv = b_s[n0 + j];
+#pragma unroll
+            for (int i = 0; i < 4 * RB; ++i) acc[i][j] = bv;
         }
         const float* ap = A_s + r0;
         const float* wp = W_s + n0;
 #pragma unroll 4
         for (int k = 0; k < K; ++k) {
-            const float4 w = lds4(wp + k * NP);
-            const float wv[4] = {w.x, w.y, w.z, w.w};
+            float wv[RN];
+            if (RN == 4) { const float4 w = lds4(wp + k * NP); wv[0] = w.x; wv[1] = w.y; wv[RN - 2] = w.z; wv[RN - 1] = w.w; }
+            else { const float2 w = *reinterpret_cast<const float2*>(wp + k * NP); wv[0] = w.x; wv[1] = w.y; }
 #pragma unroll
             for (int c = 0; c < RB; ++c) {
                 const float4 a = lds4(ap + k * P + c * CS);
@@ -97,11 +100,11 @@ __device__ __forceinline__ void gemm_fwd(const float* __restrict__ A_s, const fl
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[4 * c + i][j] = fmaf(av[i], wv[j], acc[4 * c + i][j]);
+                    for (int j = 0; j < RN; ++j) acc[4 * c + i][j] = fmaf(av[i], wv[j], acc[4 * c + i][j]);
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < RN; ++j)
 #pragma unroll
             for (int c = 0; c < RB; ++c) {
                 float4 o;
@@ -118,35 +121,35 @@ __device__ __forceinline__ void gemm_fwd(const float* __restrict__ A_s, const fl
 // the ReLU mask) and is overwritten in place.  n runs over NP (pad rows of dY must be
 // finite; pad weights are zero).
 // ---------------------------------------------------------------------------------
-template <int TM, int RB, bool RELU_MASK>
+template <int TM, int RB, bool RELU_MASK, int KPT = 4>
 __device__ __forceinline__ void gemm_dx(const float* __restrict__ dY_s, const float* __restrict__ W_s,
                                         float* __restrict__ out_s, int Kout, int NP, int tid) {
     constexpr int P = TM + 4;
     constexpr int RG = TM / (4 * RB);
     constexpr int NGW = 32 / RG;
     constexpr int CS = TM / RB;
-    constexpr int KB = 4 * NGW;      // outputs (k) covered by one warp per iteration
+    constexpr int KB = KPT * NGW;    // outputs (k) covered by one warp per iteration
     const int lane = tid & 31, warp = tid >> 5;
     const int rg = lane % RG, kgl = lane / RG;
     const int r0 = 4 * rg;
     for (int kb = warp * KB; kb < Kout; kb += NWARP * KB) {
-        int kk[4];
-        const float* wrow[4];
+        int kk[KPT];
+        const float* wrow[KPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < KPT; ++j) {
             kk[j] = kb + kgl + NGW * j;
             wrow[j] = W_s + min(kk[j], Kout - 1) * NP;
         }
-        float acc[4 * RB][4];
+        float acc[4 * RB][KPT];
 #pragma unroll
         for (int i = 0; i < 4 * RB; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+            for (int j = 0; j < KPT; ++j) acc[i][j] = 0.0f;
 #pragma unroll 2
         for (int n = 0; n < NP; n += 4) {
-            float wv[4][4];
+            float wv[KPT][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < KPT; ++j) {
                 const float4 w = lds4(wrow[j] + n);
                 wv[j][0] = w.x; wv[j][1] = w.y; wv[j][2] = w.z; wv[j][3] = w.w;
             }
@@ -159,11 +162,11 @@ __device__ __forceinline__ void gemm_dx(const float* __restrict__ dY_s, const fl
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[4 * c + i][j] = fmaf(av[i], wv[j][q], acc[4 * c + i][j]);
+                        for (int j = 0; j < KPT; ++j) acc[4 * c + i][j] = fmaf(av[i], wv[j][q], acc[4 * c + i][j]);
                 }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < KPT; ++j) {
             if (kk[j] < Kout) {
                 float* o = out_s + kk[j] * P + r0;
 #pragma unroll
@@ -188,52 +191,69 @@ __device__ __forceinline__ void gemm_dx(const float* __restrict__ dY_s, const fl
 // (k,n) is owned by exactly one thread, so the shared-memory accumulate is race-free.
 // Rows past the end of the table must have dY == 0.
 // ---------------------------------------------------------------------------------
-template <int TM>
+template <int TM, int RS = 1>
 __device__ __forceinline__ void gemm_dw(const float* __restrict__ X_s, const float* __restrict__ dY_s,
                                         float* __restrict__ dW_s, int K, int N, int NP, int tid) {
+    // RS == 2: the tile's rows are split in two halves handled by different half-warps (for layers
+    // with too few 20x20 blocks to occupy the CTA); the halves add into dW_s one after the other,
+    // separated by a __syncthreads(), so the result stays deterministic.  Call from all threads.
     constexpr int P = TM + 4;
+    constexpr int RROWS = TM / RS;
     const int hw = tid >> 4, hl = tid & 15;
     const int kl = hl & 3, nl = hl >> 2;
     const int nbk = (K + 19) / 20, nbn = (N + 19) / 20;
-    for (int blk = hw; blk < nbk * nbn; blk += NT / 16) {
+    const int nblk = nbk * nbn;
+    static_assert(RS == 1 || RS == 2, "row split");
+    for (int it0 = 0; it0 < nblk * RS; it0 += NT / 16) {
+        const int item = it0 + hw;
+        const bool active = item < nblk * RS;
+        const int blk = active ? item % nblk : 0, half = active ? item / nblk : 0;
         const int kb = (blk % nbk) * 20, nb = (blk / nbk) * 20;
-        const float* xr[5];
-        const float* yr[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            xr[i] = X_s + min(kb + kl + 4 * i, K - 1) * P;
-            yr[i] = dY_s + min(nb + nl + 4 * i, N - 1) * P;
-        }
         float acc[5][5];
 #pragma unroll
         for (int i = 0; i < 5; ++i)
 #pragma unroll
             for (int j = 0; j < 5; ++j) acc[i][j] = 0.0f;
+        if (active) {
+            const float* xr[5];
+            const float* yr[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                xr[i] = X_s + min(kb + kl + 4 * i, K - 1) * P + half * RROWS;
+                yr[i] = dY_s + min(nb + nl + 4 * i, N - 1) * P + half * RROWS;
+            }
 #pragma unroll 2
-        for (int r = 0; r < TM; r += 4) {
-            float4 xv[5];
+            for (int r = 0; r < RROWS; r += 4) {
+                float4 xv[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) xv[i] = lds4(xr[i] + r);
+                for (int i = 0; i < 5; ++i) xv[i] = lds4(xr[i] + r);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float4 yv = lds4(yr[j] + r);
+                for (int j = 0; j < 5; ++j) {
+                    const float4 yv = lds4(yr[j] + r);
 #pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    acc[i][j] = fmaf(xv[i].x, yv.x, acc[i][j]);
-                    acc[i][j] = fmaf(xv[i].y, yv.y, acc[i][j]);
-                    acc[i][j] = fmaf(xv[i].z, yv.z, acc[i][j]);
-                    acc[i][j] = fmaf(xv[i].w, yv.w, acc[i][j]);
+                    for (int i = 0; i < 5; ++i) {
+                        acc[i][j] = fmaf(xv[i].x, yv.x, acc[i][j]);
+                        acc[i][j] = fmaf(xv[i].y, yv.y, acc[i][j]);
+                        acc[i][j] = fmaf(xv[i].z, yv.z, acc[i][j]);
+                        acc[i][j] = fmaf(xv[i].w, yv.w, acc[i][j]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int k = kb + kl + 4 * i;
+        for (int h = 0; h < RS; ++h) {
+            if (active && half == h) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int n = nb + nl + 4 * j;
-                if (k < K && n < N) dW_s[k * NP + n] += acc[i][j];
+                for (int i = 0; i < 5; ++i) {
+                    const int k = kb + kl + 4 * i;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int n = nb + nl + 4 * j;
+                        if (k < K && n < N) dW_s[k * NP + n] += acc[i][j];
+                    }
+                }
             }
+            if (RS > 1 && h + 1 < RS) __syncthreads();
         }
     }
 }

@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
             gemm_fwd<TM, RB, ACT_RELU>(in_s, W1_s, b1_s, h1_s, D, H1, tid);
         }
         __syncthreads();
-        gemm_fwd<TM, RB, ACT_RELU>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
+        gemm_fwd<TM, RB, ACT_RELU, 2>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
         __syncthreads();
-        gemm_fwd<TM, RB, ACT_NONE>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
+        gemm_fwd<TM, RB, ACT_NONE, 2>(h2_s, W3_s, b3_s, o_s, H2, LAT2, tid);
         __syncthreads();
         // outputs (row-major [B][L]); reparameterisation z = mean + eps * exp(logvar/2)  (VAE.py:390-392)
         for (int i = tid; i < TM * LAT; i += NT) {
@@ -314,12 +314,12 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
         }
         __pipeline_wait_prior(0);
         __syncthreads();
-        gemm_dw<TM>(h2_s, d3_s, dW3_s, H2, LAT2, LAT2, tid);
+        gemm_dw<TM, 2>(h2_s, d3_s, dW3_s, H2, LAT2, LAT2, tid);
         bias_dw<TM>(d3_s, db3_s, LAT2, tid);
         __syncthreads();
-        gemm_dx<TM, RB, true>(d3_s, W3_s, h2_s, H2, LAT2, tid);     // h2_s <- dL/d(pre2)
+        gemm_dx<TM, RB, true, 2>(d3_s, W3_s, h2_s, H2, LAT2, tid);     // h2_s <- dL/d(pre2)
         __syncthreads();
-        gemm_dw<TM>(h1_s, h2_s, dW2_s, H1, H2, H2P, tid);
+        gemm_dw<TM, 2>(h1_s, h2_s, dW2_s, H1, H2, H2P, tid);
         bias_dw<TM>(h2_s, db2_s, H2, tid);
         __syncthreads();
         gemm_dx<TM, RB, true>(h2_s, W2_s, h1_s, H1, H2P, tid);      // h1_s <- dL/d(pre1)
@@ -328,10 +328,10 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
             gemm_dw<TM>(in_s, h1_s, dW1_s, D, H1, H1, tid);
             bias_dw<TM>(h1_s, db1_s, H1, tid);
         } else {
-            gemm_dw<TM>(agg_s, h1_s, dW1_s, K, H1, H1, tid);
+            gemm_dw<TM, 2>(agg_s, h1_s, dW1_s, K, H1, H1, tid);
             bias_dw<TM>(h1_s, db1_s, H1, tid);
             __syncthreads();
-            gemm_dx<TM, RB, false>(h1_s, W1_s, agg_s, K, H1, tid);  // agg_s <- dL/d(agg)
+            gemm_dx<TM, RB, false, 2>(h1_s, W1_s, agg_s, K, H1, tid);  // agg_s <- dL/d(agg)
             __syncthreads();
             pnp_embed_bwd<TM>(in_s, ms_s, agg_s, A_s, C_s, dA_s, dC_s, D, K, K4, tid);
         }
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
                 z_s[l * P + r] = (row0 + r < a.B) ? a.z[br][(long)(row0 + r) * LAT + l] : 0.f;
             }
             __syncthreads();
-            gemm_fwd<TM, RB, ACT_RELU>(z_s, W4_s, b4_s, g1_s, LAT, G1P, tid);
+            gemm_fwd<TM, RB, ACT_RELU, 2>(z_s, W4_s, b4_s, g1_s, LAT, G1P, tid);
             __syncthreads();
             gemm_fwd<TM, RB, ACT_RELU>(g1_s, W5_s, b5_s, g2_s, G1, G2, tid);
             __syncthreads();
@@ -521,15 +521,15 @@ __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
                 __syncthreads();
                 gemm_dx<TM, RB, true>(xh_s, W6_s, g2_s, G2, DP, tid);
                 __syncthreads();
-                gemm_dw<TM>(g1_s, g2_s, dW5_s, G1, G2, G2, tid);
+                gemm_dw<TM, 2>(g1_s, g2_s, dW5_s, G1, G2, G2, tid);
                 bias_dw<TM>(g2_s, db5_s, G2, tid);
                 __syncthreads();
-                gemm_dx<TM, RB, true>(g2_s, W5_s, g1_s, G1, G2, tid);
+                gemm_dx<TM, RB, true, 2>(g2_s, W5_s, g1_s, G1, G2, tid);
                 __syncthreads();
-                gemm_dw<TM>(z_s, g1_s, dW4_s, LAT, G1, G1P, tid);
+                gemm_dw<TM, 2>(z_s, g1_s, dW4_s, LAT, G1, G1P, tid);
                 bias_dw<TM>(g1_s, db4_s, G1, tid);
                 __syncthreads();
-                gemm_dx<TM, RB, false>(g1_s, W4_s, z_s, LAT, G1P, tid);   // z_s <- dL/dz
+                gemm_dx<TM, RB, false, 2>(g1_s, W4_s, z_s, LAT, G1P, tid);   // z_s <- dL/dz
                 __syncthreads();
             }
             // ---- latent-space terms: KL sums, d_mean / d_logvar, d_z ----

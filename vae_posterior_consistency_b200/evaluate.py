@@ -1,0 +1,199 @@
+"""Mirror of the hot-path callers in the reference's `src/experiment_main/evaluate.py`:
+`eval_vae` (ELBO / RMSE / NLL, evaluate.py:136-297), `active_learning_func` (sequential
+feature acquisition, evaluate.py:300-511) and `R_lindley_chain` (evaluate.py:514-542), with
+identical signatures and identical saved artefacts.
+
+The active-selection loop is embarrassingly parallel by test row: with torch.distributed
+initialised every rank handles a contiguous block of rows, the reward kernel needs no
+collective, the information curve takes one scalar all-reduce per step and the histories are
+gathered to rank 0 at the end.  In parity mode every rank draws the full
+host noise with the same seed and slices it, so N-GPU results are bit-identical to 1 GPU.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import kernels as KR
+from . import lib as L
+from . import ops
+from .loaders import model_loader
+from .utils import create_missing_uci
+from .VAE import draw_noise
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank(), dist.group.WORLD
+    return 1, 0, None
+
+
+def _family_dir(vae_type):
+    return ''.join(c for c in '_'.join(vae_type.split('_')[:2]) if not c.isdigit())
+
+
+def _result_path(kind, experiment_type, data_type, vae_type, stem, missing_rate, alpha, p_missingness, reg_type):
+    base = os.path.join('experiments', experiment_type, data_type, kind, _family_dir(vae_type))
+    os.makedirs(base, exist_ok=True)
+    if 'vanilla' in vae_type:
+        return os.path.join(base, f'{stem}_{missing_rate}_missing_rate_test.pt')
+    return os.path.join(base, f'{stem}_{alpha}_{p_missingness}_{reg_type}_{missing_rate}_missing_rate_full_reg_test.pt')
+
+
+def eval_vae(list_loaders, missing_rate, obs_dim, hid_dim, K, M, latent_dim, data_type, training_parameters,
+             experiment_type, vae_type, max_epochs, valid_k, num_estimates, device=torch.device('cpu'), alpha=0.5,
+             stage='evaluate', p_missingness=30, reg_type='ml_reg', beta=1.0, beta_annealing=False,
+             alpha_annealing=True):
+    """M repeats over every loader; per batch: forward (both branches draw noise, only q is scored),
+    ELBO = (RE_q + beta KL_q)/B, NLL on observed / unobserved entries, RMSE on unobserved entries of the
+    stochastic decoder mean (evaluate.py:209-245); saves four scalars per loader (evaluate.py:247-297)."""
+    device = torch.device(device)
+    with torch.no_grad():
+        model = model_loader('test', obs_dim, hid_dim, K, latent_dim, missing_rate, data_type, training_parameters,
+                             max_epochs, valid_k, num_estimates, experiment_type, reg_type, vae_type, alpha=alpha,
+                             p_missingness=p_missingness)
+        model.to(device)
+        regularised = 'reg' in vae_type
+        theta = model.flat_theta()
+        eng = ops.engine(model.FAMILY, obs_dim, model._emb(), device)
+        beta_w = model._beta_w(beta, beta_annealing, max_epochs)
+        results = {}
+        for loader, loader_stage in list_loaders:
+            recon, res, res_negll, res_negll_imp = [], [], [], []
+            for _ in range(M):
+                rmses, elbos, negls, negls_imp = [], [], [], []
+                for data_sample, mask in loader:
+                    data_sample, mask = data_sample.to(device), mask.to(device)
+                    B = data_sample.shape[0]
+                    create_missing_uci(data_sample.shape, p_missingness)       # drawn for every family, evaluate.py:173
+                    eps_q = draw_noise(B, latent_dim, device, model.noise)
+                    if regularised:
+                        draw_noise(B, latent_dim, device, model.noise)         # the p-branch draw of forward()
+                    mean, logvar, z, _ = eng.enc_fwd(theta, data_sample, [mask], [eps_q])
+                    eng.dec(L.DEC_EVAL, theta, z, x=data_sample, masks=[mask], mean=mean, logvar=logvar,
+                            beta_w=beta_w)
+                    s = eng.reduce_sums(B)
+                    elbos.append((s[L.S_RE_Q] + beta_w * s[L.S_KL_Q]) / B)
+                    negls.append(s[L.S_RE_Q] / B)
+                    negls_imp.append(s[L.S_RE_IMP] / B)
+                    n_unobs = torch.sum(~mask.bool())
+                    rmses.append(torch.sqrt(s[L.S_SSE_UNOBS] / n_unobs))
+                recon.append(torch.stack(rmses).float().mean())
+                res.append(torch.stack(elbos).float().mean())
+                res_negll.append(torch.stack(negls).float().mean())
+                res_negll_imp.append(torch.stack(negls_imp).float().mean())
+            out = {'rmse': torch.stack(recon).mean().cpu(), 'vae_elbo': torch.stack(res).mean().cpu(),
+                   'negative_llh': torch.stack(res_negll).mean().cpu(),
+                   'negative_llh_imputed': torch.stack(res_negll_imp).mean().cpu()}
+            results[loader_stage] = out
+            q = '' if 'vanilla' in vae_type else '_q'
+            names = {'rmse': ('rest', '_rmse'), 'vae_elbo': ('elbos', '_vae_elbo'),
+                     'negative_llh': ('rest', f'_negative_llh{q}'),
+                     'negative_llh_imputed': ('rest', f'_negative_llh{q}_imputed')}
+            for key, (kind, suffix) in names.items():
+                torch.save(out[key], _result_path(kind, experiment_type, data_type, vae_type,
+                                                  f'{loader_stage}_{vae_type}{suffix}', missing_rate, alpha,
+                                                  p_missingness, reg_type))
+        return results
+
+
+def R_lindley_chain(i, x, mask, M, vae, im, loc):
+    """Reward of candidate `i` for the rows `loc` (evaluate.py:514-542).  Kept for API compatibility; it
+    evaluates the all-candidates kernel on the selected rows and returns column `i`."""
+    loc_t = torch.as_tensor(np.asarray(loc), dtype=torch.long, device=x.device)
+    if loc_t.numel() == 0:
+        return torch.empty(0, device=x.device)
+    xs, base = x[loc_t].float(), mask[loc_t].float()
+    R = ops.reward_chain_op(vae.flat_theta().detach(), xs, base, im[:, loc_t].contiguous().float(), vae.FAMILY,
+                            vae.obs_dim, vae._emb())
+    return R[:, i]
+
+
+def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, obs_dim, hid_dim, K, M, latent_dim,
+                         data_type, training_parameters, experiment_type, vae_type, max_epochs, valid_k,
+                         num_estimates, device=torch.device('cpu'), alpha=1.0, stage='evaluate', p_missingness=30,
+                         reg_type='ml_reg', beta=1.0, beta_annealing=False, alpha_annealing=True, Repeat=5):
+    device = torch.device(device)
+    world, rank, group = _dist()
+    n_test = test_data.shape[0]
+    lo, hi = (rank * n_test) // world, ((rank + 1) * n_test) // world     # this rank's row block
+    n_loc = hi - lo
+    C = obs_dim - 1
+    info = torch.zeros(Repeat, n_test, obs_dim)
+    action = torch.zeros(Repeat, n_test, C)
+    R_hist = torch.zeros(Repeat, C, n_test, C)
+    im_hist = torch.zeros(Repeat, C, M, n_test, obs_dim)
+    with torch.no_grad():
+        for r in range(Repeat):
+            model = model_loader('test', obs_dim, hid_dim, K, latent_dim, missing_rate, data_type,
+                                 training_parameters, max_epochs, valid_k, num_estimates, experiment_type, reg_type,
+                                 vae_type, alpha=alpha, p_missingness=p_missingness, alpha_annealing=alpha_annealing)
+            model.to(device)
+            regularised = 'reg' in vae_type
+            theta = model.flat_theta()
+            eng = ops.engine(model.FAMILY, obs_dim, model._emb(), device)
+            create_missing_uci(test_data.shape, p_missingness)       # evaluate.py:351 (feeds the unused p branch)
+            x = test_data[lo:hi].float().to(device)
+            target = x[:, -1].clone()
+            mask = torch.zeros(n_loc, obs_dim, device=device)        # float mask; target column never observed
+            ws = None
+
+            def sample_means():
+                """M x model.forward(x, mask, mask_p)[x_mean_q] (evaluate.py:365-386, 394-415): full-size host
+                noise sliced to this rank's rows; the p-branch draw is made and discarded."""
+                outs = []
+                for _ in range(M):
+                    eps_q = draw_noise(n_test, latent_dim, device, model.noise)[lo:hi]
+                    if regularised:
+                        draw_noise(n_test, latent_dim, device, model.noise)
+                    _, _, z, _ = eng.enc_fwd(theta, x, [mask], [eps_q.contiguous()])
+                    outs.append(eng.dec(L.DEC_FWD, theta, z)["xhat"][0])
+                return torch.stack(outs, 0)
+
+            def target_mse(im):
+                se = ((im[:, :, -1] - target.unsqueeze(0)) ** 2).sum(1)          # [M] local sums
+                if world > 1:
+                    torch.distributed.all_reduce(se, group=group)
+                return (se / n_test).mean()                                       # mean over rows, then over M
+
+            info[r, :, 0] = target_mse(sample_means()).cpu()
+            for t in range(C):
+                print("Repeat = {:.1f}".format(r))
+                print("Strategy = {:.1f}".format(2))
+                print("Step = {:.1f}".format(t))
+                im = sample_means()
+                im_hist[r, t, :, lo:hi] = im.cpu()
+                R, ws = eng.reward(theta, x, mask, im, ws)
+                if model.noise == 'host':
+                    # the reference's chaini_I / chaini_II call encoder(sample=True): 4*M discarded [|loc|, L]
+                    # draws per candidate (evaluate.py:562-626); burn them so the next `im` sees the same RNG state
+                    unsel = (mask[:, :C] == 0).sum(0)
+                    if world > 1:
+                        torch.distributed.all_reduce(unsel, group=group)
+                    for cnt in unsel.cpu().tolist():
+                        for _ in range(4 * M):
+                            torch.empty(int(cnt), latent_dim).normal_()
+                R_hist[r, t, lo:hi] = R.cpu()
+                i_opt = R.argmax(dim=1)
+                action[r, lo:hi, t] = i_opt.float().cpu()
+                mask = mask + torch.eye(obs_dim, device=device)[i_opt]
+                info[r, :, t + 1] = target_mse(sample_means()).cpu()
+    if world > 1:
+        for tns in (action, R_hist, im_hist):
+            t_dev = tns.to(device)
+            torch.distributed.all_reduce(t_dev, group=group)          # row blocks are disjoint: sum == gather
+            tns.copy_(t_dev.cpu())
+    if rank == 0:
+        stems = {'information_curve_CHAI': info, 'action_CHAI': action, 'R_hist_CHAI': R_hist, 'im_CHAI': im_hist}
+        for name, tns in stems.items():
+            if 'vanilla' in vae_type:
+                sep = '_' if name == 'information_curve_CHAI' else '__'
+                fname = f'{vae_type}_{missing_rate}_missing_rate{sep}UCI_{name}_default_test.pt'
+            else:
+                fname = (f'{vae_type}_UCI_{name}_{alpha}_{p_missingness}_{reg_type}_{missing_rate}'
+                         '_missing_rate_default_full_reg_test.pt')
+            base = os.path.join('experiments', experiment_type, data_type, 'rest', _family_dir(vae_type))
+            os.makedirs(base, exist_ok=True)
+            torch.save(tns, os.path.join(base, fname))
+    return info, action, R_hist

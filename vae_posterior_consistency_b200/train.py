@@ -1,0 +1,171 @@
+"""Mirror of the reference's `src/experiment_main/train.py` (same `train(...)` signature,
+positional order and checkpoint side effect), re-supplied because the reference version
+mixes CPU and device tensors (train.py:54-58) and has no data-parallel hook.
+
+Two execution paths, both through libpcvae_b200.so:
+ * fused  -- kl_reg / vanilla training without beta annealing (everything the drivers
+             select): FusedTrainer = encoder fwd -> decoder+loss+decoder bwd -> encoder bwd ->
+             deterministic gradient reduce -> [NCCL all-reduce] -> fused Adam, flat vectors.
+ * module -- anything else (ml_reg, beta annealing): the nn.Module API with autograd and
+             torch.optim.Adam, exactly the reference's loop.
+
+RNG parity: per epoch the DataLoader iterator draws its base seed and the
+RandomSampler its permutation seed from torch's global generator; per regularised step
+`np.random.rand(B, D)` (sub-mask) then two `[B, L]` normal draws (q, then p).  In parity mode
+(`noise='host'`, the default) all of these are drawn on the host in that order.  Setting the
+environment variable PCVAE_MODE=throughput switches to device-side gather + Philox draws.
+"""
+import os
+
+import torch
+from torch import optim
+from tqdm import tqdm
+
+from . import kernels as KR
+from . import lib as L
+from .loaders import checkpoint_path, model_loader
+from .utils import create_missing_uci, create_missing_uci_drop_eddi
+from .VAE import draw_noise
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank(), dist.group.WORLD
+    return 1, 0, None
+
+
+def _family_dir(vae_type):
+    return ''.join(c for c in '_'.join(vae_type.split('_')[:2]) if not c.isdigit())
+
+
+def _save(model, experiment_type, data_type, vae_type, missing_rate, alpha, p_missingness, reg_type):
+    path = checkpoint_path(experiment_type, data_type, vae_type, missing_rate, alpha, p_missingness, reg_type,
+                           _family_dir(vae_type))
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, path)
+    return path
+
+
+def _epoch_batches(loader, device, throughput):
+    """Yield (x, mask) batches on `device` in the order the reference's DataLoader would."""
+    table = getattr(loader, 'pcvae_table', None)
+    if not throughput or table is None or not table[0].is_cuda:
+        for data_sample, mask in loader:
+            yield data_sample.to(device), mask.to(device)
+        return
+    # same RNG consumption as iter(DataLoader): base seed first (dataloader.py), then the sampler's own seed
+    torch.empty((), dtype=torch.int64).random_()
+    lib = L.load()
+    data, mask = table
+    kind = L.MASK_U8 if mask.dtype in (torch.bool, torch.uint8) else L.MASK_F32
+    mask_src = mask if kind == L.MASK_U8 else mask.float()
+    D = data.shape[1]
+    for idx in loader.batch_sampler:
+        idx = torch.as_tensor(idx, dtype=torch.int64).to(device, non_blocking=True)
+        B = idx.numel()
+        x = torch.empty(B, D, device=device)
+        m = torch.empty(B, D, device=device, dtype=mask_src.dtype)
+        with torch.cuda.device(device):
+            L.check(lib.pcvae_gather_rows(data.data_ptr(), mask_src.data_ptr(), idx.data_ptr(), x.data_ptr(),
+                                          m.data_ptr(), B, D, kind, torch.cuda.current_stream().cuda_stream),
+                    "pcvae_gather_rows")
+        yield x, m
+
+
+def _device_submask(mask, keep, step):
+    out = torch.empty_like(mask)
+    lib = L.load()
+    with torch.cuda.device(mask.device):
+        L.check(lib.pcvae_draw_submask(mask.data_ptr(), out.data_ptr(), mask.numel(), keep, 0xC0FFEE, step * 8,
+                                       torch.cuda.current_stream().cuda_stream), "pcvae_draw_submask")
+    return out
+
+
+def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, data_type,
+          training_parameters, experiment_type, vae_type, train_k, num_estimates, max_epochs=1000,
+          device=torch.device('cpu'), alpha=1.0, stage='train', p_missingness=30, reg_type='ml_reg', beta=1.0,
+          beta_annealing=False, alpha_annealing=True, not_miwae_type='changed'):
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise L.PcvaeError("train(): this implementation runs on a CUDA device only (no CPU fallback); "
+                           "the reference's own CPU path is the oracle")
+    model = model_loader('train', obs_dim, hid_dim, K, latent_dim, missing_rate, data_type,
+                         training_parameters, max_epochs, train_k, num_estimates, experiment_type, reg_type, vae_type,
+                         alpha=alpha, p_missingness=p_missingness)
+    model.to(device)
+    if 'notMIWAE' not in vae_type:
+        data_loader_train, _ = data_loader_train
+    throughput = os.environ.get('PCVAE_MODE', 'parity') == 'throughput'
+    model.noise = 'device' if throughput else 'host'
+    regularised = 'reg' in vae_type
+    fused = (not beta_annealing) and (not regularised or reg_type == 'kl_reg')
+    world, rank, group = _dist()
+
+    if fused:
+        theta = model.flat_theta().detach().clone()
+        trainer = KR.FusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, regularised=regularised,
+                                  alpha=float(alpha), beta_w=float(beta), lr=0.001, dist_group=group, world_size=world)
+    else:
+        optimizer = optim.Adam(model.parameters(), lr=0.001)
+    keep = 1 - p_missingness / 100
+    step = 0
+    for i in tqdm(range(max_epochs)):
+        total = torch.zeros((), device=device, dtype=torch.float64)
+        for data_sample, mask in _epoch_batches(data_loader_train, device, throughput):
+            step += 1
+            B = data_sample.shape[0]
+            mask_p = None
+            if 'with_drop' in vae_type:
+                mask_drop = create_missing_uci_drop_eddi(data_sample.shape).to(device)
+            else:
+                if regularised:
+                    if throughput and mask.dtype in (torch.bool, torch.uint8):
+                        mask_p = _device_submask(mask, keep, step)
+                    else:
+                        temp_mask = create_missing_uci(data_sample.shape, p_missingness)     # host, NumPy RNG
+                        mask_p = temp_mask.to(device) * mask
+                mask_drop = torch.ones(data_sample.shape, device=device)
+            if fused:
+                lo, hi = (rank * B) // world, ((rank + 1) * B) // world
+                sl = slice(lo, hi)
+                if regularised:
+                    eps_q = draw_noise(B, latent_dim, device, model.noise)
+                    eps_p = draw_noise(B, latent_dim, device, model.noise)
+                    loss = trainer.step(data_sample[sl], mask[sl], mask_p[sl], eps_q[sl], eps_p[sl], global_rows=B)
+                else:
+                    eps_q = draw_noise(B, latent_dim, device, model.noise)
+                    mk = (mask * mask_drop)                                                   # float32, train.py:97
+                    loss = trainer.step(data_sample[sl], mk[sl], None, eps_q[sl], None, global_rows=B)
+                total += loss
+            else:
+                if regularised:
+                    out = model.forward(data_sample, mask, mask_p, stage=stage)
+                    mean_p, logvar_p, x_mean_p, x_logvar_p, mean_q, logvar_q, x_mean_q, x_logvar_q = out
+                    print_loss, train_loss = model.loss(
+                        data_sample, x_mean_p, x_logvar_p, mean_p, logvar_p, x_mean_q, x_logvar_q, mean_q, logvar_q,
+                        mask, mask_p, i + 1, beta_annealing=beta_annealing, beta=beta, alpha=alpha,
+                        alpha_annealing=alpha_annealing, stage=stage)
+                else:
+                    mean_q, logvar_q, x_mean_q, x_logvar_q = model.forward(data_sample, mask * mask_drop)
+                    print_loss, train_loss = model.loss(data_sample, x_mean_q, x_logvar_q, mean_q, logvar_q, i + 1,
+                                                        mask * mask_drop, beta_annealing=beta_annealing, beta=beta,
+                                                        stage=stage)
+                optimizer.zero_grad()
+                train_loss.backward()
+                optimizer.step()
+                total += train_loss.detach()
+        if world > 1 and fused:
+            torch.distributed.all_reduce(total, group=group)
+        tqdm.write('Epoch: [{}/{}], Total Loss: {}'.format(i, max_epochs, float(total)))
+
+    if fused:
+        with torch.no_grad():
+            flat = KR.unflatten_params(trainer.theta, model.FAMILY, obs_dim, model._emb())
+            params = dict(model.named_parameters())
+            for k, v in flat.items():
+                params[k].copy_(v.view_as(params[k]))
+    if rank == 0:
+        _save(model, experiment_type, data_type, vae_type, missing_rate, alpha, p_missingness, reg_type)
+    print('Training is over!')
+    return model
