@@ -171,6 +171,63 @@ def reward_case(V, E, cls_name, N, D, K, M, seed, n_selected):
                 im_eps_q=torch.stack(tape.draws[0::2]), R=R)
 
 
+def driver_cases(V, E):
+    """Run the reference's own train() / eval_vae() / active_learning_func() (the call sequence of
+    imputation.py:28-59 and active_learning.py:58-74) on a tiny synthetic Data/ tree with fixed seeds
+    and record the artefacts they write."""
+    import glob
+    import tempfile
+    import tqdm as tqdm_mod
+    sys.path.insert(0, os.path.dirname(HERE))
+    from synth import DRIVER_CASES, DRIVER_CFG, make_tree
+    import src.experiment_main.train as T
+    import src.utils.loaders as LD
+    c = DRIVER_CFG
+    out = {}
+    cwd = os.getcwd()
+    for name, vae_type, K in DRIVER_CASES:
+        with tempfile.TemporaryDirectory() as root:
+            make_tree(root, c["data_type"], c["n_rows"], c["obs_dim"], seed=0, missing_rate=c["missing_rate"],
+                      experiment_type=c["experiment_type"])
+            os.chdir(root)
+            try:
+                torch.manual_seed(0); np.random.seed(0)
+                tr, te, obs_dim = LD.data_loader("Data", vae_type, c["missing_rate"], c["batch_size"], c["data_type"])
+                losses = []
+                orig_write = tqdm_mod.tqdm.write
+                tqdm_mod.tqdm.write = staticmethod(lambda s, *a, **k: losses.append(float(s.split("Total Loss:")[1])))
+                try:
+                    T.train(tr, c["missing_rate"], obs_dim, 500, K, 1, 10, c["data_type"],
+                            {"batch_size": c["batch_size"], "patience": 100}, c["experiment_type"], vae_type, 20, 10,
+                            c["epochs"], device=torch.device("cpu"), alpha=c["alpha"],
+                            p_missingness=c["p_missingness"], reg_type=c["reg_type"])
+                finally:
+                    tqdm_mod.tqdm.write = orig_write
+                E.eval_vae([tr, te], c["missing_rate"], obs_dim, 500, K, c["M_eval"], 10, c["data_type"],
+                           {"batch_size": c["batch_size"], "patience": 100}, c["experiment_type"], vae_type,
+                           c["epochs"], 5000, 10, device=torch.device("cpu"), alpha=c["alpha"],
+                           p_missingness=c["p_missingness"], reg_type=c["reg_type"])
+                # active_learning.py:24-74 call sequence (min-max, split, DataLoader, active_learning_func)
+                data = torch.load(os.path.join("Data", c["data_type"], "data.pt"))
+                test_idx = np.loadtxt(os.path.join("Data", c["data_type"], "test_index1.csv"), delimiter=",")
+                mask = torch.load(os.path.join("Data", c["data_type"], f"mask_{c['missing_rate']}_missing1.pt"))
+                norm = (data - data.min(axis=0).values) / (data.max(axis=0).values - data.min(axis=0).values)
+                E.active_learning_func(tr[0], norm[test_idx], mask[test_idx], c["missing_rate"], obs_dim, 500, K,
+                                       c["M_al"], 10, c["data_type"], {"batch_size": c["batch_size"], "patience": 100},
+                                       c["experiment_type"], vae_type, c["epochs"], 5000, 10,
+                                       device=torch.device("cpu"), alpha=c["alpha"], p_missingness=c["p_missingness"],
+                                       reg_type=c["reg_type"], Repeat=1)
+                files = {}
+                for f in glob.glob(os.path.join("experiments", "**", "*.pt"), recursive=True):
+                    if "im_CHAI" in f:
+                        continue
+                    files[os.path.relpath(f, "experiments")] = torch.load(f)
+                out[name] = dict(vae_type=vae_type, K=K, epoch_losses=torch.tensor(losses), files=files)
+            finally:
+                os.chdir(cwd)
+    return out
+
+
 def main():
     V, E = _import_reference()
     torch.set_num_threads(1)
@@ -185,6 +242,8 @@ def main():
     fx["traj_reg_eddi_b32_d13_k10"] = train_traj_case(V, "Reg_EDDI", 32, 13, 10, 7, 4)
     fx["reward_reg_vae_n24_d8_m5"] = reward_case(V, E, "Reg_VAE", 24, 8, 20, 5, 8, 3)
     fx["reward_reg_eddi_n24_d8_k10_m5"] = reward_case(V, E, "Reg_EDDI", 24, 8, 10, 5, 9, 3)
+    if "--skip-drivers" not in sys.argv:
+        fx["drivers_synth_150x6"] = driver_cases(V, E)
     for name, d in fx.items():
         path = os.path.join(HERE, name + ".pt")
         torch.save(d, path)

@@ -1,0 +1,38 @@
+"""Deterministic synthetic `Data/` trees in the layout the reference's loaders expect
+(SURVEY.md section 8c): data.pt, train_index<i>.csv, test_index<i>.csv, mask_<rate>_missing<i>.pt,
+plus the experiments/ output folders the reference never creates itself."""
+import os
+
+import numpy as np
+import torch
+
+
+def make_tree(root, data_type, n_rows, obs_dim, seed=0, missing_rate=30, index="1", test_frac=0.25,
+              experiment_type="UCI_experiments_consistency_missingness"):
+    g = torch.Generator().manual_seed(seed)
+    folder = os.path.join(root, "Data", data_type)
+    os.makedirs(folder, exist_ok=True)
+    data = torch.randn(n_rows, obs_dim, generator=g) * 2 + 1
+    mask = torch.rand(n_rows, obs_dim, generator=g) < (1 - missing_rate / 100)
+    perm = torch.randperm(n_rows, generator=g).numpy()
+    n_test = max(1, int(round(n_rows * test_frac)))
+    torch.save(data, os.path.join(folder, "data.pt"))
+    torch.save(mask, os.path.join(folder, f"mask_{missing_rate}_missing{index}.pt"))
+    np.savetxt(os.path.join(folder, f"test_index{index}.csv"), perm[:n_test].astype(np.float64), delimiter=",")
+    np.savetxt(os.path.join(folder, f"train_index{index}.csv"), perm[n_test:].astype(np.float64), delimiter=",")
+    for kind in ("checkpoints", "rest", "elbos"):
+        for fam in ("reg_vae", "vanilla_vae", "reg_EDDI", "vanilla_EDDI"):
+            os.makedirs(os.path.join(root, "experiments", experiment_type, data_type, kind, fam), exist_ok=True)
+    return folder
+
+
+DRIVER_CASES = [
+    # name, vae_type, K
+    ("reg_vae", "reg_vae1", 20),
+    ("reg_eddi", "reg_EDDI1", 10),
+    ("vanilla_vae", "vanilla_vae1", 20),
+    ("vanilla_eddi", "vanilla_EDDI1", 20),
+]
+DRIVER_CFG = dict(data_type="synth", n_rows=150, obs_dim=6, batch_size=64, epochs=3, M_eval=2, M_al=3,
+                  missing_rate=30, p_missingness=30, alpha=1.0, reg_type="kl_reg",
+                  experiment_type="UCI_experiments_consistency_missingness")

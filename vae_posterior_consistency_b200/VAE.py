@@ -135,9 +135,8 @@ class _PartialVAEBase(nn.Module):
 class _RegMixin:
     """Reg_VAE.loss / Reg_EDDI.loss (identical bodies, VAE.py:403-467, 749-817) and forward (496-507, 842-853)."""
 
-    def loss(self, x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q, mask, mask_p,
-             epoch, vae_elbo=False, llh_eval=False, MI=False, beta_annealing=False, beta=1.0, alpha=0.8,
-             stage='train', alpha_annealing=True):
+    def _reg_loss(self, x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q, mask,
+                  mask_p, epoch, vae_elbo, llh_eval, MI, beta_annealing, beta, alpha, stage, alpha_annealing):
         rows = x.shape[0]
         dev = x_recon_q.device
         x, mask, mask_p = x.to(dev), mask.to(dev), mask_p.to(dev)
@@ -181,8 +180,8 @@ class _RegMixin:
 class _VanillaMixin:
     """vanilla_VAE.loss / vanilla_EDDI.loss (VAE.py:1171-1208, 933-964) and forward (1237-1240, 989-992)."""
 
-    def loss(self, x, x_recon_q, x_logvar_q, mean_q, logvar_q, epoch, mask, vae_elbo=False, llh_eval=False, MI=False,
-             beta_annealing=False, beta=1.0, alpha=0.8, alpha_annealing=True, stage='train'):
+    def _vanilla_loss(self, x, x_recon_q, x_logvar_q, mean_q, logvar_q, epoch, mask, vae_elbo, llh_eval, MI,
+                      beta_annealing, beta, stage):
         rows = x.shape[0]
         dev = x_recon_q.device
         x, mask = x.to(dev), mask.to(dev)
@@ -219,6 +218,14 @@ class Reg_VAE(_RegMixin, _PartialVAEBase):
         self._init_decoder_and_prior()
         self._init_prior()
 
+    def loss(self, x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q, mask, mask_p,
+             epoch,
+             vae_elbo=False, llh_eval=False, MI=False, beta_annealing=False,
+             beta=1.0, alpha=0.8, stage='train', alpha_annealing=True):
+        return self._reg_loss(x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q,
+                              mask, mask_p, epoch, vae_elbo, llh_eval, MI, beta_annealing, beta, alpha, stage,
+                              alpha_annealing)
+
 
 class vanilla_VAE(_VanillaMixin, _PartialVAEBase):
     """Reference VAE.py:1119-1240."""
@@ -234,6 +241,12 @@ class vanilla_VAE(_VanillaMixin, _PartialVAEBase):
         self.seq_encoder = _mlp_encoder(obs_dim, latent_dim)
         self._init_decoder_and_prior()
         self._init_prior()
+
+    def loss(self, x, x_recon_q, x_logvar_q, mean_q, logvar_q, epoch, mask,
+             vae_elbo=False, llh_eval=False, MI=False, beta_annealing=False,
+             beta=1.0, alpha=0.8, alpha_annealing=True, stage='train'):
+        return self._vanilla_loss(x, x_recon_q, x_logvar_q, mean_q, logvar_q, epoch, mask, vae_elbo, llh_eval, MI,
+                                  beta_annealing, beta, stage)
 
 
 def _init_pnp(self, K, training_parameters, xavier):
@@ -262,6 +275,14 @@ class Reg_EDDI(_RegMixin, _PartialVAEBase):
         self.reg_type = reg_type
         _init_pnp(self, K, training_parameters, torch.nn.init.xavier_uniform_)
 
+    def loss(self, x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q, mask, mask_p,
+             epoch,
+             vae_elbo=False, llh_eval=False, MI=False, beta_annealing=False,
+             beta=1.0, alpha=0.5, stage='train', alpha_annealing=False):
+        return self._reg_loss(x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q,
+                              mask, mask_p, epoch, vae_elbo, llh_eval, MI, beta_annealing, beta, alpha, stage,
+                              alpha_annealing)
+
 
 class vanilla_EDDI(_VanillaMixin, _PartialVAEBase):
     """Reference VAE.py:856-992 (its loss always evaluates RE_q_imputed, :941-942)."""
@@ -274,6 +295,12 @@ class vanilla_EDDI(_VanillaMixin, _PartialVAEBase):
         self._init_common(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, num_samples,
                           num_estimates)
         _init_pnp(self, K, training_parameters, torch.nn.init.xavier_uniform_)
+
+    def loss(self, x, x_recon_q, x_logvar_q, mean_q, logvar_q, epoch, mask,
+             vae_elbo=False, llh_eval=False, MI=False, beta_annealing=False,
+             beta=1.0, alpha=0.5, stage='train'):
+        return self._vanilla_loss(x, x_recon_q, x_logvar_q, mean_q, logvar_q, epoch, mask, vae_elbo, llh_eval, MI,
+                                  beta_annealing, beta, stage)
 
 
 IN_SCOPE = {"Reg_VAE": Reg_VAE, "vanilla_VAE": vanilla_VAE, "Reg_EDDI": Reg_EDDI, "vanilla_EDDI": vanilla_EDDI}

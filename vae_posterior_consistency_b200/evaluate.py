@@ -17,16 +17,10 @@ import torch
 from . import kernels as KR
 from . import lib as L
 from . import ops
+from .dist import merge_row_blocks, row_block, world
 from .loaders import model_loader
 from .utils import create_missing_uci
 from .VAE import draw_noise
-
-
-def _dist():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_world_size(), dist.get_rank(), dist.group.WORLD
-    return 1, 0, None
 
 
 def _family_dir(vae_type):
@@ -115,9 +109,9 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                          num_estimates, device=torch.device('cpu'), alpha=1.0, stage='evaluate', p_missingness=30,
                          reg_type='ml_reg', beta=1.0, beta_annealing=False, alpha_annealing=True, Repeat=5):
     device = torch.device(device)
-    world, rank, group = _dist()
+    world_size, rank, group = world()
     n_test = test_data.shape[0]
-    lo, hi = (rank * n_test) // world, ((rank + 1) * n_test) // world     # this rank's row block
+    lo, hi = row_block(n_test, world_size, rank)                           # this rank's row block
     n_loc = hi - lo
     C = obs_dim - 1
     info = torch.zeros(Repeat, n_test, obs_dim)
@@ -153,7 +147,7 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
 
             def target_mse(im):
                 se = ((im[:, :, -1] - target.unsqueeze(0)) ** 2).sum(1)          # [M] local sums
-                if world > 1:
+                if world_size > 1:
                     torch.distributed.all_reduce(se, group=group)
                 return (se / n_test).mean()                                       # mean over rows, then over M
 
@@ -169,7 +163,7 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                     # the reference's chaini_I / chaini_II call encoder(sample=True): 4*M discarded [|loc|, L]
                     # draws per candidate (evaluate.py:562-626); burn them so the next `im` sees the same RNG state
                     unsel = (mask[:, :C] == 0).sum(0)
-                    if world > 1:
+                    if world_size > 1:
                         torch.distributed.all_reduce(unsel, group=group)
                     for cnt in unsel.cpu().tolist():
                         for _ in range(4 * M):
@@ -179,11 +173,9 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                 action[r, lo:hi, t] = i_opt.float().cpu()
                 mask = mask + torch.eye(obs_dim, device=device)[i_opt]
                 info[r, :, t + 1] = target_mse(sample_means()).cpu()
-    if world > 1:
+    if world_size > 1:
         for tns in (action, R_hist, im_hist):
-            t_dev = tns.to(device)
-            torch.distributed.all_reduce(t_dev, group=group)          # row blocks are disjoint: sum == gather
-            tns.copy_(t_dev.cpu())
+            merge_row_blocks(tns, group, device)                       # row blocks are disjoint: sum == gather
     if rank == 0:
         stems = {'information_curve_CHAI': info, 'action_CHAI': action, 'R_hist_CHAI': R_hist, 'im_CHAI': im_hist}
         for name, tns in stems.items():

@@ -23,16 +23,10 @@ from tqdm import tqdm
 
 from . import kernels as KR
 from . import lib as L
+from .dist import merge_row_blocks, row_block, world
 from .loaders import checkpoint_path, model_loader
 from .utils import create_missing_uci, create_missing_uci_drop_eddi
 from .VAE import draw_noise
-
-
-def _dist():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_world_size(), dist.get_rank(), dist.group.WORLD
-    return 1, 0, None
 
 
 def _family_dir(vae_type):
@@ -100,12 +94,12 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
     model.noise = 'device' if throughput else 'host'
     regularised = 'reg' in vae_type
     fused = (not beta_annealing) and (not regularised or reg_type == 'kl_reg')
-    world, rank, group = _dist()
+    world_size, rank, group = world()
 
     if fused:
         theta = model.flat_theta().detach().clone()
         trainer = KR.FusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, regularised=regularised,
-                                  alpha=float(alpha), beta_w=float(beta), lr=0.001, dist_group=group, world_size=world)
+                                  alpha=float(alpha), beta_w=float(beta), lr=0.001, dist_group=group, world_size=world_size)
     else:
         optimizer = optim.Adam(model.parameters(), lr=0.001)
     keep = 1 - p_missingness / 100
@@ -127,7 +121,7 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
                         mask_p = temp_mask.to(device) * mask
                 mask_drop = torch.ones(data_sample.shape, device=device)
             if fused:
-                lo, hi = (rank * B) // world, ((rank + 1) * B) // world
+                lo, hi = row_block(B, world_size, rank)
                 sl = slice(lo, hi)
                 if regularised:
                     eps_q = draw_noise(B, latent_dim, device, model.noise)
@@ -155,7 +149,7 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
                 train_loss.backward()
                 optimizer.step()
                 total += train_loss.detach()
-        if world > 1 and fused:
+        if world_size > 1 and fused:
             torch.distributed.all_reduce(total, group=group)
         tqdm.write('Epoch: [{}/{}], Total Loss: {}'.format(i, max_epochs, float(total)))
 
