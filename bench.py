@@ -42,17 +42,19 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling in the background for the whole run; only the samples whose timestamp falls
+    inside a timed window (train / e2e / reward loops) are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.windows = [], None, index, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -60,24 +62,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc is not None:
+            time.sleep(0.12)
             self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        sm, mx, reasons, power = [], 0, set(), 0.0
+        for ts, r in self.rows:
+            if not any(a - 0.05 <= ts <= b + 0.1 for a, b in self.windows):
+                continue
             f = [s.strip() for s in r.split(",")]
             try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                sm.append(float(f[1])); mx = max(mx, float(f[2])); power = max(power, float(f[3]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": power or None}
 
 
 def dist_setup(n_gpus):
@@ -191,6 +199,8 @@ def run_ours(args):
     from vae_posterior_consistency_b200 import kernels as KR, lib as L
 
     dev = torch.device("cuda", local)
+    clocks = ClockSampler(local)
+    clocks.start()
     lib = L.load()
     stream = lambda: torch.cuda.current_stream().cuda_stream
     hbm_peak, peak_src = peaks()
@@ -266,18 +276,17 @@ def run_ours(args):
     for s in range(args.warmup):
         prep_step(s, x, mask); draw_step(s, mask); train_step(x, mask, False)
     barrier(world)
-    clocks = ClockSampler(local)
-    clocks.start()
     launches[0] = 0
+    w0 = time.time()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for s in range(args.warmup, n_total):
         prep_step(s, x, mask); draw_step(s, mask); sums = train_step(x, mask, True)
     t1.record()
     barrier(world)
+    clocks.window(w0, time.time())
     train_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
     train_launches = launches[0]
-    clk = clocks.stop()
     dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / len(dec_ev)
     loss = float(KR.loss_from_sums(sums, B * world, 1.0, 1.0, True))
     rows_s = B * world / (train_ms * 1e-3)
@@ -311,11 +320,13 @@ def run_ours(args):
 
     e2e_loop(0, args.warmup)
     barrier(world)
+    w0 = time.time()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     e2e_loop(args.warmup, args.steps)
     t1.record()
     barrier(world)
+    clocks.window(w0, time.time())
     e2e_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
     e2e_rows_s = B * world / (e2e_ms * 1e-3)
     h2d = B * D * 4 + B * D
@@ -339,12 +350,14 @@ def run_ours(args):
         ws = None
         R, ws = er.reward(theta_r, xr, mr, im, ws)
         barrier(world)
+        w0 = time.time()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.reward_steps):
             R, ws = er.reward(theta_r, xr, mr, im, ws)
         t1.record()
         barrier(world)
+        clocks.window(w0, time.time())
         r_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.reward_steps
         triples = Nloc * world * (Dr - 1) * M
         # e2e: host x / mask / im -> device -> R back on the host
@@ -375,6 +388,7 @@ def run_ours(args):
             "gpu_launches": 4 * args.reward_steps,
         }
 
+    clk = clocks.stop()
     if rank == 0:
         dec_flops = 2 * MAC_DEC_BRANCH_ROW * 2 * B
         achieved = dec_flops / (dec_ms * 1e-3) / 1e12
@@ -420,14 +434,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--table-rows", type=int, default=1_000_000)
     ap.add_argument("--reward-rows", type=int, default=100_000)
     ap.add_argument("--reward-samples", type=int, default=50)
-    ap.add_argument("--reward-steps", type=int, default=2)
+    ap.add_argument("--reward-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
