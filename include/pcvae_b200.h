@@ -260,6 +260,78 @@ int pcvae_draw_submask(const uint8_t* mask, uint8_t* mask_p, long n, float keep_
                        unsigned long long seed, unsigned long long offset, void* stream);
 int pcvae_draw_normal(float* out, long n, unsigned long long seed, unsigned long long offset, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Generic dense layer y = act(x W^T + b) on row tiles (weights resident in shared memory), forward
+ * and backward.  Building block of the 128-wide not-MIWAE MNAR networks (REG_notMIWAE_v2 /
+ * notMIWAE_myversion, src/models/VAE.py:2342-2363, 2706-2730); in_dim, out_dim <= 128.
+ * `mask` (fp32, optional) fuses the zero-imputation x*mask of the first encoder layer (VAE.py:2378, 2749).
+ * --------------------------------------------------------------------- */
+enum { PCVAE_ACT_NONE = 0, PCVAE_ACT_RELU = 1, PCVAE_ACT_SIGMOID = 2, PCVAE_ACT_ELU = 3,
+       PCVAE_ACT_HARDTANH_M10_0 = 4 /* nn.Hardtanh(-10, 0), VAE.py:2363 */ };
+typedef struct {
+    int rows, in_dim, out_dim, act;
+    const float* x;        /* [rows][in_dim] */
+    const float* mask;     /* optional [rows][in_dim] */
+    const float* W;        /* [out_dim][in_dim] */
+    const float* b;        /* [out_dim] */
+    float* y;              /* out [rows][out_dim] */
+} pcvae_dense_fwd_params;
+int pcvae_dense_fwd(const pcvae_dense_fwd_params* p, void* stream);
+typedef struct {
+    int rows, in_dim, out_dim, act;
+    const float* x;        /* layer input (before the optional mask) */
+    const float* mask;
+    const float* y;        /* layer output (activation derivative is taken from it) */
+    const float* dy;       /* [rows][out_dim] */
+    const float* W;
+    float* dx;             /* optional out [rows][in_dim] */
+    float* dW_partials;    /* [pcvae_grid_ctas()][out_dim*in_dim]; reduce with pcvae_reduce_grads */
+    float* db_partials;    /* [pcvae_grid_ctas()][out_dim] */
+} pcvae_dense_bwd_params;
+int pcvae_dense_bwd(const pcvae_dense_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
+ * not-MIWAE MNAR importance-sampling pieces (S samples per row).
+ *  pcvae_mnar_sample_z      z[b][s][l] = mean[b][l] + exp(logvar[b][l]/2) eps[b][s][l]   (VAE.py:2382-2387)
+ *  pcvae_mnar_sample_z_bwd  d_mean = sum_s d_z, d_logvar = sum_s d_z * 0.5 exp(logvar/2) eps
+ *  pcvae_mnar_loss          REG_notMIWAE_v2.loss (regularised=1, VAE.py:2398-2471) or notMIWAE_myversion.loss
+ *                           (regularised=0, VAE.py:2772-2823): per-(row,sample) masked Gaussian NLL with
+ *                           per-entry variance, KL, Bernoulli self-masking term -softplus(W)(x~-b),
+ *                           logsumexp over samples; llh_eval imputation sum_s softmax(-l_w) xm (VAE.py:2458-2461);
+ *                           and the gradients of the loss w.r.t. every input.
+ * out[0]=loss, out[1]=RE_q.mean(), out[2]=loss_q, out[3]=loss_p (doubles, device).
+ * --------------------------------------------------------------------- */
+int pcvae_mnar_sample_z(const float* mean, const float* logvar, const float* eps, float* z, int rows,
+                        int samples, int latent_dim, void* stream);
+int pcvae_mnar_sample_z_bwd(const float* d_z, const float* logvar, const float* eps, float* d_mean,
+                            float* d_logvar, int rows, int samples, int latent_dim, void* stream);
+typedef struct {
+    int rows, samples, obs_dim, latent_dim, regularised;
+    const float* x;            /* [B][D] */
+    const float* mask;         /* [B][D] fp32 */
+    const float* mask_p;       /* [B][D] fp32 (regularised only) */
+    const float* xm[2];        /* [B][S][D] x_mean head, q and p branch */
+    const float* xlv[2];       /* [B][S][D] x_logvar head */
+    const float* mean[2];      /* [B][L] */
+    const float* logvar[2];    /* [B][L] */
+    const float* eps_kl;       /* regularised=0: the second N(0,1) draw [B][S][L] of the MC KL (VAE.py:2791-2798) */
+    const float* W;            /* [D] self-masking slope (before softplus) */
+    const float* b;            /* [D] self-masking offset */
+    float alpha;
+    void* workspace;           /* pcvae_mnar_loss_workspace_bytes() */
+    size_t workspace_bytes;
+    double* out;               /* [4] */
+    float* xm_imputed;         /* optional [B][D] */
+    float* d_xm[2];            /* optional gradients, NULL = forward only */
+    float* d_xlv[2];
+    float* d_mean[2];
+    float* d_logvar[2];
+    float* d_W;                /* [D] */
+    float* d_b;                /* [D] */
+} pcvae_mnar_loss_params;
+size_t pcvae_mnar_loss_workspace_bytes(int rows, int samples, int obs_dim);
+int pcvae_mnar_loss(const pcvae_mnar_loss_params* p, void* stream);
+
 /* FP32 FFMA peak probe used by bench.py for the roofline denominator: runs `iters`
  * dependent-chain-free FMA rounds on every SM; returns 0 and the FLOP count in *flops. */
 int pcvae_ffma_probe(float* scratch, int iters, double* flops, void* stream);

@@ -357,3 +357,125 @@ def reward_all(p: Params, x, mask, im, incremental: bool = True) -> Tensor:
     sel = maskf[:, :D - 1] == 0
     R[sel] = (acc / M)[sel]
     return R
+
+
+# --------------------------------------------------------------------------
+# not-MIWAE (MNAR self-masking) family: REG_notMIWAE_v2 / notMIWAE_myversion
+# --------------------------------------------------------------------------
+
+def elu(h: Tensor) -> Tensor:
+    return torch.where(h > 0, h, torch.exp(h) - 1.0)
+
+
+def mnar_encoder_stats(p: Params, x: Tensor, mask: Tensor) -> Tuple[Tensor, Tensor]:
+    """seq_encoder (D->128->128, ELU) + q_mu / q_logstd heads, src/models/VAE.py:2377-2380, 2748-2751.
+    Returns per-row (mean, log_var) [B, L] (the reference then repeats them over the S samples)."""
+    h = elu(_lin(x * _as(mask, x), p["seq_encoder.0.weight"], p["seq_encoder.0.bias"]))
+    h = elu(_lin(h, p["seq_encoder.2.weight"], p["seq_encoder.2.bias"]))
+    return _lin(h, p["q_mu.0.weight"], p["q_mu.0.bias"]), _lin(h, p["q_logstd.0.weight"], p["q_logstd.0.bias"])
+
+
+def mnar_decoder(p: Params, z: Tensor) -> Tuple[Tensor, Tensor]:
+    """seq_decoder (L->128->128, ELU) + x_mean (Sigmoid) / x_logvar (Hardtanh[-10,0]) heads, VAE.py:2392-2396."""
+    g = elu(_lin(z, p["seq_decoder.0.weight"], p["seq_decoder.0.bias"]))
+    g = elu(_lin(g, p["seq_decoder.2.weight"], p["seq_decoder.2.bias"]))
+    xm = torch.sigmoid(_lin(g, p["x_mean.0.weight"], p["x_mean.0.bias"]))
+    xlv = torch.clamp(_lin(g, p["x_logvar.0.weight"], p["x_logvar.0.bias"]), -10.0, 0.0)
+    return xm, xlv
+
+
+def _nll_rows(x, xm, xlv, m):
+    """per-(b,s) sum over features of -Normal(xm*m, exp(xlv*m/2)).log_prob(x*m), VAE.py:2491-2493."""
+    scale = torch.exp(xlv * m / 2)
+    diff = x * m - xm * m
+    return torch.sum(diff * diff / (2 * scale * scale) + torch.log(scale) + HALF_LOG_2PI, 2)
+
+
+def _selfmask_logp(p: Params, x, xm, m):
+    """sum_d Bernoulli(logits=-softplus(W)(x~ - b)).log_prob(m), x~ = xm(1-m) + x m; VAE.py:2407,2417,2434-2435."""
+    mixed = xm * (1 - m) + x * m
+    logits = -torch.nn.functional.softplus(p["W"]) * (mixed - p["b"])
+    return torch.sum(-torch.nn.functional.binary_cross_entropy_with_logits(logits, m.expand_as(logits),
+                                                                           reduction="none"), 2)
+
+
+def mnar_reg_loss(p: Params, x, mask, mask_p, mu_q, lv_q, mu_p, lv_p, xm_q, xlv_q, xm_p, xlv_p, alpha=1.0):
+    """REG_notMIWAE_v2.loss, VAE.py:2398-2471.  mu/lv are [B, L]; xm/xlv are [B, S, D].
+    Returns (loss, xm_imputed [B, D], RE_q.mean())."""
+    S = xm_q.shape[1]
+    X, M_, MP = x.unsqueeze(1), mask.to(x.dtype).unsqueeze(1), mask_p.to(x.dtype).unsqueeze(1)
+    RE_q = _nll_rows(X, xm_q, xlv_q, M_)
+    RE_p = _nll_rows(X, xm_p, xlv_p, MP)
+    kl = lambda mu, lv: 0.5 * torch.sum(torch.exp(lv) + mu * mu - 1.0 - lv, 1, keepdim=True)
+    l_w_q = RE_q + kl(mu_q, lv_q) - _selfmask_logp(p, X, xm_q, M_)
+    l_w_p = RE_p + kl(mu_p, lv_p)
+    loss_q = torch.mean(torch.logsumexp(l_w_q, 1) - math.log(float(S)))
+    loss_p = torch.mean(torch.logsumexp(l_w_p, 1) - math.log(float(S)))
+    kl_el = 0.5 * (torch.exp(lv_q - lv_p) + (mu_q - mu_p) ** 2 / torch.exp(lv_p) - 1.0 - (lv_q - lv_p))
+    KL_reg = kl_el.mean()                       # mean over [B,S,L] == mean over [B,L] (copies over S)
+    RE_d = _nll_rows(X, xm_q, xlv_q, M_ * (1 - MP)).mean()
+    loss = loss_q + alpha * (KL_reg - loss_q + loss_p + RE_d)
+    wl = torch.softmax(-l_w_q, 1)
+    return loss, torch.sum(xm_q * wl.unsqueeze(2), 1), RE_q.mean()
+
+
+def mnar_vanilla_loss(p: Params, x, mask, mu, lv, xm, xlv, eps_kl):
+    """notMIWAE_myversion.loss, VAE.py:2772-2823: Monte-Carlo KL from a SECOND draw z' = mu + std*eps_kl
+    (eps_kl [B, S, L]).  Returns (loss, xm_imputed, RE.mean())."""
+    S = xm.shape[1]
+    X, M_ = x.unsqueeze(1), mask.to(x.dtype).unsqueeze(1)
+    RE = _nll_rows(X, xm, xlv, M_)
+    std = torch.exp(lv / 2).unsqueeze(1)
+    z2 = mu.unsqueeze(1) + eps_kl * std
+    log_q = torch.sum(-(z2 - mu.unsqueeze(1)) ** 2 / (2 * std * std) - torch.log(std) - HALF_LOG_2PI, 2)
+    log_p = torch.sum(-z2 * z2 / 2 - HALF_LOG_2PI, 2)
+    l_w = RE + (log_q - log_p) - _selfmask_logp(p, X, xm, M_)
+    loss = torch.mean(torch.logsumexp(l_w, 1) - math.log(float(S)))
+    wl = torch.softmax(-l_w, 1)
+    return loss, torch.sum(xm * wl.unsqueeze(2), 1), RE.mean()
+
+
+def mnar_trainable_names(p: Params) -> Sequence[str]:
+    return [k for k in p if not k.startswith("logits.")]
+
+
+def mnar_train_step(p: Params, x, mask, mask_p, eps_q, eps_p, alpha=1.0, regularised=True, eps_kl=None):
+    """forward + loss + backward of the MNAR families (train.py:87-101); eps_* are [B, S, L]."""
+    names = mnar_trainable_names(p)
+    q = {k: (v.detach().clone().requires_grad_(True) if k in names else v) for k, v in p.items()}
+    mu_q, lv_q = mnar_encoder_stats(q, x, mask)
+    z_q = mu_q.unsqueeze(1) + eps_q * torch.exp(lv_q / 2).unsqueeze(1)
+    xm_q, xlv_q = mnar_decoder(q, z_q)
+    if regularised:
+        mu_p, lv_p = mnar_encoder_stats(q, x, mask_p)
+        z_p = mu_p.unsqueeze(1) + eps_p * torch.exp(lv_p / 2).unsqueeze(1)
+        xm_p, xlv_p = mnar_decoder(q, z_p)
+        loss, xm_imp, re = mnar_reg_loss(q, x, mask, mask_p, mu_q, lv_q, mu_p, lv_p, xm_q, xlv_q, xm_p, xlv_p, alpha)
+    else:
+        loss, xm_imp, re = mnar_vanilla_loss(q, x, mask, mu_q, lv_q, xm_q, xlv_q, eps_kl)
+    grads = torch.autograd.grad(loss, [q[k] for k in names], allow_unused=True)
+    gd = {k: (g if g is not None else torch.zeros_like(q[k])) for k, g in zip(names, grads)}
+    return loss.detach(), gd, dict(xm_imp=xm_imp.detach(), re=re.detach(), xm_q=xm_q.detach(), xlv_q=xlv_q.detach(),
+                                   mu_q=mu_q.detach(), lv_q=lv_q.detach())
+
+
+def init_mnar_params(obs_dim: int, latent: int = LATENT, seed: int = 0, with_logits: bool = True) -> Params:
+    """Random parameters with the shapes of REG_notMIWAE_v2."""
+    g = torch.Generator().manual_seed(seed)
+
+    def linear(out_f, in_f):
+        bound = 1.0 / math.sqrt(in_f)
+        return ((torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound, (torch.rand(out_f, generator=g) * 2 - 1) * bound)
+
+    p: Params = {}
+    bound = math.sqrt(6.0 / (obs_dim + obs_dim))
+    p["W"] = (torch.rand(1, 1, obs_dim, generator=g) * 2 - 1) * bound
+    p["b"] = (torch.rand(1, 1, obs_dim, generator=g) * 2 - 1) * bound
+    for name, (o, i) in (("seq_encoder.0", (128, obs_dim)), ("seq_encoder.2", (128, 128)), ("q_mu.0", (latent, 128)),
+                         ("q_logstd.0", (latent, 128)), ("seq_decoder.0", (128, latent)), ("seq_decoder.2", (128, 128)),
+                         ("x_mean.0", (obs_dim, 128)), ("x_logvar.0", (obs_dim, 128))):
+        p[name + ".weight"], p[name + ".bias"] = linear(o, i)
+    if with_logits:
+        w, b = linear(obs_dim, obs_dim)
+        p["logits.0.weight"], p["logits.0.bias"] = w.double(), b.double()
+    return p

@@ -171,6 +171,41 @@ def reward_case(V, E, cls_name, N, D, K, M, seed, n_selected):
                 im_eps_q=torch.stack(tape.draws[0::2]), R=R)
 
 
+def mnar_case(V, cls_name, B, D, S, seed, alpha):
+    """REG_notMIWAE_v2 / notMIWAE_myversion: forward, loss, backward, llh_eval imputation with recorded noise."""
+    torch.manual_seed(seed)
+    cls = getattr(V, cls_name)
+    model = cls(D, 500, 20, 10, {"batch_size": B, "patience": 100}, S, 10)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(B, D, generator=g)
+    mask = (torch.rand(B, D, generator=g) < 0.7).float()            # MNAR path uses float32 masks
+    mask_p = mask * (torch.rand(B, D, generator=g) < 0.5).float()
+    reg = cls_name == "REG_notMIWAE_v2"
+    with NoiseTape() as tape:
+        if reg:
+            mean_p, logvar_p, xm_p, xlv_p, mean_q, logvar_q, xm_q, xlv_q = model.forward(x, mask, mask_p, stage="train")
+            _, loss = model.loss(x, xm_p, xlv_p, mean_p, logvar_p, xm_q, xlv_q, mean_q, logvar_q, mask, mask_p, 1,
+                                 beta_annealing=False, beta=1.0, alpha=alpha, alpha_annealing=True, stage="train")
+        else:
+            mean_q, logvar_q, xm_q, xlv_q = model.forward(x, mask)
+            _, loss = model.loss(x, xm_q, xlv_q, mean_q, logvar_q, 1, mask, beta_annealing=False, beta=1.0, stage="train")
+    draws = [d.clone() for d in tape.draws]
+    model.zero_grad()
+    loss.backward()
+    grads = {k: prm.grad.detach().clone() for k, prm in model.named_parameters() if prm.grad is not None}
+    with torch.no_grad():
+        if reg:
+            xm_imp, _, re = model.loss(x, xm_p, xlv_p, mean_p, logvar_p, xm_q, xlv_q, mean_q, logvar_q, mask, mask_p, 1,
+                                       llh_eval=True, alpha=alpha, stage="evaluate")
+        else:
+            with NoiseTape() as tape2:
+                xm_imp, _, re = model.loss(x, xm_q, xlv_q, mean_q, logvar_q, 1, mask, llh_eval=True, stage="evaluate")
+            draws.append(tape2.draws[0].clone())
+    return dict(cls=cls_name, D=D, S=S, alpha=alpha, state_dict=sd_clone(model), x=x, mask=mask, mask_p=mask_p,
+                draws=draws, mean_q=mean_q.detach(), logvar_q=logvar_q.detach(), xm_q=xm_q.detach(),
+                xlv_q=xlv_q.detach(), loss=loss.detach(), grads=grads, xm_imp=xm_imp, re=re)
+
+
 def driver_cases(V, E):
     """Run the reference's own train() / eval_vae() / active_learning_func() (the call sequence of
     imputation.py:28-59 and active_learning.py:58-74) on a tiny synthetic Data/ tree with fixed seeds
@@ -228,6 +263,54 @@ def driver_cases(V, E):
     return out
 
 
+def mnar_driver_cases(V, E):
+    """imputation_mnar.py:41-85 call sequence (data_loader_mnar -> train -> eval_vae_mnar) with the reference's
+    own functions on a tiny synthetic MNAR tree."""
+    import glob
+    import tempfile
+    import tqdm as tqdm_mod
+    sys.path.insert(0, os.path.dirname(HERE))
+    from synth import MNAR_CASES, MNAR_CFG, make_tree_mnar
+    import src.experiment_main.train as T
+    import src.utils.loaders as LD
+    c = MNAR_CFG
+    out = {}
+    cwd = os.getcwd()
+    for name, vae_type in MNAR_CASES:
+        with tempfile.TemporaryDirectory() as root:
+            make_tree_mnar(root, c["data_type"], c["n_rows"], c["obs_dim"], seed=3, experiment_type=c["experiment_type"])
+            os.chdir(root)
+            try:
+                torch.manual_seed(0); np.random.seed(0)
+                loader, obs_dim = LD.data_loader_mnar("Data", vae_type, c["missing_rate"], c["batch_size"], c["data_type"])
+                data = torch.load(os.path.join("Data", c["data_type"], "data.pt"))[:, :-1]
+                perm = torch.load(os.path.join("Data", c["data_type"], "rand_perm1.pt")).numpy()
+                data = data[perm, :]
+                mask = torch.load(os.path.join("Data", c["data_type"], "mnar_mask_missing1.pt"))[:, :-1]
+                data = (data - data.min(axis=0).values) / (data.max(axis=0).values - data.min(axis=0).values)
+                tp = {"batch_size": c["batch_size"], "patience": 100}
+                losses = []
+                orig_write = tqdm_mod.tqdm.write
+                tqdm_mod.tqdm.write = staticmethod(lambda s, *a, **k: losses.append(float(s.split("Total Loss:")[1])))
+                try:
+                    T.train(loader, c["missing_rate"], obs_dim, 500, 20, c["M"], 10, c["data_type"], tp,
+                            c["experiment_type"], vae_type, c["train_k"], 10, c["epochs"], device=torch.device("cpu"),
+                            alpha=c["alpha"], p_missingness=c["p_missingness"], reg_type=c["reg_type"],
+                            not_miwae_type="changed")
+                finally:
+                    tqdm_mod.tqdm.write = orig_write
+                E.eval_vae_mnar(data, mask, c["missing_rate"], obs_dim, 500, 20, c["M"], 10, c["data_type"], tp,
+                                c["experiment_type"], vae_type, c["epochs"], c["valid_k"], 10,
+                                device=torch.device("cpu"), alpha=c["alpha"], p_missingness=c["p_missingness"],
+                                reg_type=c["reg_type"], not_miwae_type="changed")
+                files = {os.path.relpath(f, "experiments"): torch.load(f)
+                         for f in glob.glob(os.path.join("experiments", "**", "*.pt"), recursive=True)}
+                out[name] = dict(vae_type=vae_type, epoch_losses=torch.tensor(losses), files=files)
+            finally:
+                os.chdir(cwd)
+    return out
+
+
 def main():
     V, E = _import_reference()
     torch.set_num_threads(1)
@@ -242,8 +325,12 @@ def main():
     fx["traj_reg_eddi_b32_d13_k10"] = train_traj_case(V, "Reg_EDDI", 32, 13, 10, 7, 4)
     fx["reward_reg_vae_n24_d8_m5"] = reward_case(V, E, "Reg_VAE", 24, 8, 20, 5, 8, 3)
     fx["reward_reg_eddi_n24_d8_k10_m5"] = reward_case(V, E, "Reg_EDDI", 24, 8, 10, 5, 9, 3)
+    fx["mnar_reg_v2_b16_d8_s5"] = mnar_case(V, "REG_notMIWAE_v2", 16, 8, 5, 20, 1.0)
+    fx["mnar_reg_v2_b9_d50_s20_a06"] = mnar_case(V, "REG_notMIWAE_v2", 9, 50, 20, 21, 0.6)
+    fx["mnar_vanilla_b16_d8_s5"] = mnar_case(V, "notMIWAE_myversion", 16, 8, 5, 22, 1.0)
     if "--skip-drivers" not in sys.argv:
         fx["drivers_synth_150x6"] = driver_cases(V, E)
+        fx["drivers_mnar_40x6"] = mnar_driver_cases(V, E)
     for name, d in fx.items():
         path = os.path.join(HERE, name + ".pt")
         torch.save(d, path)

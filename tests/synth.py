@@ -36,3 +36,30 @@ DRIVER_CASES = [
 DRIVER_CFG = dict(data_type="synth", n_rows=150, obs_dim=6, batch_size=64, epochs=3, M_eval=2, M_al=3,
                   missing_rate=30, p_missingness=30, alpha=1.0, reg_type="kl_reg",
                   experiment_type="UCI_experiments_consistency_missingness")
+
+
+def make_tree_mnar(root, data_type, n_rows, obs_dim, seed=0, index="1",
+                   experiment_type="UCI_experiments_consistency_missingness"):
+    """MNAR tree (reference loaders.py:357-384): data.pt has a trailing target column that the loader drops,
+    rand_perm<i>.pt, mnar_mask_missing<i>.pt (float32, self-masking: the first D/2 columns are hidden where the
+    value exceeds the column mean -- the rule of reference utils.py:48-60)."""
+    g = torch.Generator().manual_seed(seed)
+    folder = os.path.join(root, "Data", data_type)
+    os.makedirs(folder, exist_ok=True)
+    data = torch.rand(n_rows, obs_dim + 1, generator=g)
+    mask = torch.ones(n_rows, obs_dim + 1)
+    half = obs_dim // 2
+    mask[:, :half] = (data[:, :half] <= data[:, :half].mean(0)).float()
+    torch.save(data, os.path.join(folder, "data.pt"))
+    torch.save(mask, os.path.join(folder, f"mnar_mask_missing{index}.pt"))
+    torch.save(torch.randperm(n_rows, generator=g), os.path.join(folder, f"rand_perm{index}.pt"))
+    for kind in ("checkpoints", "rest", "elbos"):
+        for fam in ("reg_notMIWAE", "vanilla_notMIWAE"):
+            os.makedirs(os.path.join(root, "experiments", experiment_type, data_type, kind, fam), exist_ok=True)
+    return folder
+
+
+MNAR_CASES = [("reg_notmiwae", "reg_notMIWAE1"), ("vanilla_notmiwae", "vanilla_notMIWAE1")]
+MNAR_CFG = dict(data_type="synthmnar", n_rows=40, obs_dim=6, batch_size=16, epochs=2, train_k=4, valid_k=6, M=1,
+                missing_rate=30, p_missingness=50, alpha=1.0, reg_type="kl_reg",
+                experiment_type="UCI_experiments_consistency_missingness")

@@ -1,0 +1,180 @@
+"""not-MIWAE MNAR family (REG_notMIWAE_v2 / notMIWAE_myversion, reference VAE.py:2327-2505, 2691-2847) on a
+B200: generic dense kernels, the (row, sample) loss kernels, the module API with autograd against fixtures
+recorded from the reference, and the imputation_mnar.py call sequence against the reference's artefacts."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from synth import MNAR_CASES, MNAR_CFG, make_tree_mnar  # noqa: E402
+
+
+def _act_ref(v, act):
+    return [lambda t: t, torch.relu, torch.sigmoid, O.elu, lambda t: torch.clamp(t, -10.0, 0.0)][act](v)
+
+
+@pytest.mark.parametrize("R,K,N", [(70, 50, 128), (1, 10, 128), (130, 128, 128), (65, 128, 50), (64, 128, 10), (33, 7, 5)])
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
+def test_dense_layer_forward_backward(R, K, N, act):
+    from vae_posterior_consistency_b200 import kernels as KR
+    g = torch.Generator().manual_seed(R + K + N + act)
+    x = torch.randn(R, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * (3.0 if act == 4 else 0.3) - (3.0 if act == 4 else 0.0)
+    mask = (torch.rand(R, K, generator=g) < 0.7).float() if K == 50 else None
+    dy = torch.randn(R, N, generator=g)
+    xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = _act_ref((xr * mask if mask is not None else xr) @ Wr.t() + br, act)
+    y_ref.backward(dy)
+    y = KR.dense_fwd(x.cuda(), W.cuda(), b.cuda(), act, None if mask is None else mask.cuda())
+    torch.testing.assert_close(y.cpu(), y_ref.detach(), rtol=1e-4, atol=1e-5)
+    dx, dW, db = KR.dense_bwd(x.cuda(), W.cuda(), y, dy.cuda(), act, None if mask is None else mask.cuda())
+    torch.testing.assert_close(dx.cpu(), xr.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dW.cpu(), Wr.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(db.cpu(), br.grad, rtol=1e-3, atol=1e-4)
+
+
+class FeedBSL:
+    def __init__(self, VAE, draws):
+        self.VAE, self.draws, self.i = VAE, list(draws), 0
+
+    def __enter__(self):
+        self.orig = self.VAE.draw_noise_bsl
+
+        def feed(rows, samples, latent, device, mode):
+            e = self.draws[self.i]
+            self.i += 1
+            assert e.shape == (rows, samples, latent)
+            return e.to(device)
+        self.VAE.draw_noise_bsl = feed
+        return self
+
+    def __exit__(self, *a):
+        self.VAE.draw_noise_bsl = self.orig
+
+
+@pytest.mark.parametrize("name", ["mnar_reg_v2_b16_d8_s5", "mnar_reg_v2_b9_d50_s20_a06", "mnar_vanilla_b16_d8_s5"])
+def test_mnar_module_api_matches_reference(golden, name):
+    from vae_posterior_consistency_b200 import VAE
+    g = golden(name)
+    reg = g["cls"] == "REG_notMIWAE_v2"
+    model = getattr(VAE, g["cls"])(g["D"], 500, 20, 10, {"batch_size": 16, "patience": 1}, g["S"], 10)
+    assert list(model.state_dict().keys()) == list(g["state_dict"].keys())
+    model.load_state_dict(g["state_dict"])
+    model.cuda()
+    x, mask, mask_p = g["x"].cuda(), g["mask"].cuda(), g["mask_p"].cuda()
+    with FeedBSL(VAE, g["draws"]):
+        if reg:
+            mean_p, logvar_p, xm_p, xlv_p, mean_q, logvar_q, xm_q, xlv_q = model.forward(x, mask, mask_p, stage="train")
+            _, loss = model.loss(x, xm_p, xlv_p, mean_p, logvar_p, xm_q, xlv_q, mean_q, logvar_q, mask, mask_p, 1,
+                                 beta_annealing=False, beta=1.0, alpha=g["alpha"], alpha_annealing=True, stage="train")
+        else:
+            mean_q, logvar_q, xm_q, xlv_q = model.forward(x, mask)
+            _, loss = model.loss(x, xm_q, xlv_q, mean_q, logvar_q, 1, mask, beta_annealing=False, beta=1.0, stage="train")
+        assert mean_q.shape == g["mean_q"].shape
+        torch.testing.assert_close(mean_q.cpu(), g["mean_q"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(xm_q.detach().cpu(), g["xm_q"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(xlv_q.detach().cpu(), g["xlv_q"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=1e-4, atol=1e-6)
+        model.zero_grad()
+        loss.backward()
+        for k, prm in model.named_parameters():
+            if k in g["grads"]:
+                ref = g["grads"][k]
+                torch.testing.assert_close(prm.grad.cpu(), ref, rtol=2e-3, atol=2e-5 * float(ref.abs().max() + 1e-3),
+                                           msg=lambda m: f"{k}: {m}")
+            else:
+                assert k.startswith("logits.") and prm.grad is None
+        with torch.no_grad():
+            if reg:
+                xm_imp, _, re = model.loss(x, xm_p, xlv_p, mean_p, logvar_p, xm_q, xlv_q, mean_q, logvar_q, mask,
+                                           mask_p, 1, llh_eval=True, alpha=g["alpha"], stage="evaluate")
+            else:
+                xm_imp, _, re = model.loss(x, xm_q, xlv_q, mean_q, logvar_q, 1, mask, llh_eval=True, stage="evaluate")
+        torch.testing.assert_close(xm_imp.cpu(), g["xm_imp"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(re.cpu(), g["re"], rtol=1e-4, atol=1e-6)
+
+
+def test_mnar_loss_kernel_vs_oracle_large_sample_count():
+    """cfg2-like shape (B=128, D=50, S=20) and the evaluation shape (B=3, S=2000): loss + gradients vs the oracle."""
+    from vae_posterior_consistency_b200 import kernels as KR
+    for B, D, S in ((128, 50, 20), (3, 50, 2000)):
+        p = O.init_mnar_params(D, seed=B)
+        g = torch.Generator().manual_seed(S)
+        x = torch.rand(B, D, generator=g)
+        mask = (torch.rand(B, D, generator=g) < 0.6).float()
+        mask_p = mask * (torch.rand(B, D, generator=g) < 0.5).float()
+        eq, ep = torch.randn(B, S, 10, generator=g), torch.randn(B, S, 10, generator=g)
+        mu_q, lv_q = O.mnar_encoder_stats(p, x, mask)
+        mu_p, lv_p = O.mnar_encoder_stats(p, x, mask_p)
+        xm_q, xlv_q = O.mnar_decoder(p, mu_q.unsqueeze(1) + eq * torch.exp(lv_q / 2).unsqueeze(1))
+        xm_p, xlv_p = O.mnar_decoder(p, mu_p.unsqueeze(1) + ep * torch.exp(lv_p / 2).unsqueeze(1))
+        leaves = [t.detach().clone().requires_grad_(True) for t in (xm_q, xlv_q, mu_q, lv_q, xm_p, xlv_p, mu_p, lv_p)]
+        pp = dict(p); pp["W"] = p["W"].clone().requires_grad_(True); pp["b"] = p["b"].clone().requires_grad_(True)
+        loss, xm_imp, re = O.mnar_reg_loss(pp, x, mask, mask_p, leaves[2], leaves[3], leaves[6], leaves[7], leaves[0],
+                                           leaves[1], leaves[4], leaves[5], alpha=0.7)
+        ref = torch.autograd.grad(loss, leaves + [pp["W"], pp["b"]])
+        cu = lambda t: t.detach().cuda()
+        r = KR.mnar_loss(cu(x), cu(mask), cu(mask_p), [cu(xm_q), cu(xm_p)], [cu(xlv_q), cu(xlv_p)], [cu(mu_q), cu(mu_p)],
+                         [cu(lv_q), cu(lv_p)], cu(p["W"]), cu(p["b"]), 0.7, True, want_grads=True, want_imputed=True)
+        torch.testing.assert_close(r["out"][0].float().cpu(), loss.detach(), rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(r["out"][1].float().cpu(), re.detach(), rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(r["xm_imputed"].cpu(), xm_imp.detach(), rtol=1e-4, atol=1e-6)
+        got = [r["d_xm"][0], r["d_xlv"][0], r["d_mean"][0], r["d_logvar"][0], r["d_xm"][1], r["d_xlv"][1], r["d_mean"][1],
+               r["d_logvar"][1], r["d_W"].view(1, 1, -1), r["d_b"].view(1, 1, -1)]
+        for i, (a, b) in enumerate(zip(got, ref)):
+            torch.testing.assert_close(a.cpu(), b, rtol=2e-3, atol=2e-5 * float(b.abs().max() + 1e-6),
+                                       msg=lambda m: f"grad {i} (B={B},S={S}): {m}")
+
+
+@pytest.mark.parametrize("name,vae_type", MNAR_CASES)
+def test_mnar_driver_sequence_matches_reference_artifacts(golden, tmp_path, name, vae_type):
+    from vae_posterior_consistency_b200 import evaluate, loaders, train as train_mod
+    c = MNAR_CFG
+    g = golden("drivers_mnar_40x6")[name]
+    make_tree_mnar(str(tmp_path), c["data_type"], c["n_rows"], c["obs_dim"], seed=3, experiment_type=c["experiment_type"])
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    dev = torch.device("cuda:0")
+    tp = {"batch_size": c["batch_size"], "patience": 100}
+    try:
+        torch.manual_seed(0); np.random.seed(0)
+        loader, obs_dim = loaders.data_loader_mnar("Data", vae_type, c["missing_rate"], c["batch_size"], c["data_type"],
+                                                   device=dev)
+        data = torch.load(os.path.join("Data", c["data_type"], "data.pt"))[:, :-1]
+        perm = torch.load(os.path.join("Data", c["data_type"], "rand_perm1.pt")).numpy()
+        data = data[perm, :]
+        mask = torch.load(os.path.join("Data", c["data_type"], "mnar_mask_missing1.pt"))[:, :-1]
+        data = (data - data.min(axis=0).values) / (data.max(axis=0).values - data.min(axis=0).values)
+        import tqdm as tqdm_mod
+        losses, orig = [], tqdm_mod.tqdm.write
+        tqdm_mod.tqdm.write = staticmethod(lambda s, *a, **k: losses.append(float(s.split("Total Loss:")[1])))
+        try:
+            train_mod.train(loader, c["missing_rate"], obs_dim, 500, 20, c["M"], 10, c["data_type"], tp,
+                            c["experiment_type"], vae_type, c["train_k"], 10, c["epochs"], device=dev, alpha=c["alpha"],
+                            p_missingness=c["p_missingness"], reg_type=c["reg_type"], not_miwae_type="changed")
+        finally:
+            tqdm_mod.tqdm.write = orig
+        torch.testing.assert_close(torch.tensor(losses), g["epoch_losses"], rtol=2e-4, atol=1e-5)
+        evaluate.eval_vae_mnar(data, mask, c["missing_rate"], obs_dim, 500, 20, c["M"], 10, c["data_type"], tp,
+                               c["experiment_type"], vae_type, c["epochs"], c["valid_k"], 10, device=dev,
+                               alpha=c["alpha"], p_missingness=c["p_missingness"], reg_type=c["reg_type"],
+                               not_miwae_type="changed")
+        assert len(g["files"]) == 2
+        for rel, ref in g["files"].items():
+            got = torch.load(os.path.join("experiments", rel))
+            if isinstance(ref, dict):
+                assert list(got.keys()) == list(ref.keys())
+                for k in ref:
+                    assert got[k].dtype == ref[k].dtype, k
+                    torch.testing.assert_close(got[k], ref[k], rtol=2e-3, atol=2e-5, msg=lambda m: f"{rel}:{k}: {m}")
+            else:
+                torch.testing.assert_close(got.float(), ref.float(), rtol=5e-4, atol=1e-5, msg=lambda m: f"{rel}: {m}")
+    finally:
+        os.chdir(cwd)

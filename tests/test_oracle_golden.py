@@ -93,3 +93,33 @@ def test_reward_fp64_agrees_with_fp32_within_floor(golden):
     R64 = O.reward_all(p64, g["x"].double(), g["mask"].double(), g["im"].double())
     sel = g["mask"][:, :-1] == 0
     assert (R64[sel].float() - g["R"][sel]).abs().max() < 2e-6
+
+
+MNAR = ["mnar_reg_v2_b16_d8_s5", "mnar_reg_v2_b9_d50_s20_a06", "mnar_vanilla_b16_d8_s5"]
+
+
+@pytest.mark.parametrize("name", MNAR)
+def test_mnar_families(golden, name):
+    """REG_notMIWAE_v2 / notMIWAE_myversion: forward, loss, every parameter gradient and the importance-weighted
+    imputation of llh_eval against the reference's recorded run (VAE.py:2377-2505, 2748-2847)."""
+    g = golden(name)
+    p = g["state_dict"]
+    reg = g["cls"] == "REG_notMIWAE_v2"
+    d = g["draws"]
+    if reg:
+        loss, grads, aux = O.mnar_train_step(p, g["x"], g["mask"], g["mask_p"], d[0], d[1], alpha=g["alpha"])
+    else:
+        loss, grads, aux = O.mnar_train_step(p, g["x"], g["mask"], None, d[0], None, regularised=False, eps_kl=d[1])
+    S = g["S"]
+    close(aux["mu_q"].unsqueeze(1).expand(-1, S, -1), g["mean_q"])
+    close(aux["xm_q"], g["xm_q"]); close(aux["xlv_q"], g["xlv_q"])
+    close(loss, g["loss"])
+    for k, ref in g["grads"].items():
+        torch.testing.assert_close(grads[k], ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max() + 1e-3))
+    if reg:
+        close(aux["xm_imp"], g["xm_imp"]); close(aux["re"], g["re"])
+        assert "logits.0.weight" in p and p["logits.0.weight"].dtype == torch.float64     # unused float64 Linear (A.1)
+    else:
+        # llh_eval draws a fresh z' for the MC KL: recompute with the recorded third draw
+        _, xm_imp, re = O.mnar_vanilla_loss(p, g["x"], g["mask"], aux["mu_q"], aux["lv_q"], aux["xm_q"], aux["xlv_q"], d[2])
+        close(xm_imp, g["xm_imp"]); close(re, g["re"])

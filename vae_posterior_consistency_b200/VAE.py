@@ -47,6 +47,14 @@ def draw_noise(rows: int, latent: int, device, mode: str) -> torch.Tensor:
     return out
 
 
+def draw_noise_bsl(rows: int, samples: int, latent: int, device, mode: str) -> torch.Tensor:
+    """[B, S, L] standard-normal draw of the not-MIWAE models: Normal(mean[B,S,L], ...).rsample() is one
+    `torch.empty(B, S, L).normal_()` on the host generator in parity mode."""
+    if mode == "host":
+        return torch.empty(rows, samples, latent).normal_().to(device, non_blocking=True)
+    return draw_noise(rows * samples, latent, device, "device").view(rows, samples, latent)
+
+
 class _PartialVAEBase(nn.Module):
     """Shared behaviour; subclasses only differ in encoder family and in the loss signature."""
 
@@ -303,7 +311,147 @@ class vanilla_EDDI(_VanillaMixin, _PartialVAEBase):
                                   beta_annealing, beta, stage)
 
 
-IN_SCOPE = {"Reg_VAE": Reg_VAE, "vanilla_VAE": vanilla_VAE, "Reg_EDDI": Reg_EDDI, "vanilla_EDDI": vanilla_EDDI}
+class _NotMIWAEBase(nn.Module):
+    """Shared parts of the MNAR self-masking models (reference VAE.py:2327-2505, 2691-2847): encoder
+    D->128->128 (ELU) with q_mu / q_logstd heads, S importance samples per row, decoder L->128->128 (ELU)
+    with x_mean (Sigmoid) / x_logvar (Hardtanh[-10,0]) heads, Bernoulli self-masking term."""
+
+    noise = "host"
+
+    def _build(self, obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates, with_logits):
+        self.obs_dim = obs_dim
+        self.hid_dim = hid_dim
+        self.emb_dim = 10
+        self.num_samples = num_samples
+        self.num_estimates = num_estimates
+        self.latent_dim = latent_dim
+        self.batch_size = training_parameters['batch_size']
+        self.K = K
+        self.obs_std = 0.1
+        self.number_components = 500
+        self.training_paramters = training_parameters
+        self.seq_encoder = nn.Sequential(nn.Linear(obs_dim, 128), nn.ELU(), nn.Linear(128, 128), nn.ELU())
+        self.q_mu = nn.Sequential(nn.Linear(128, latent_dim))
+        self.q_logstd = nn.Sequential(nn.Linear(128, latent_dim))
+        self.seq_decoder = nn.Sequential(nn.Linear(latent_dim, 128), nn.ELU(), nn.Linear(128, 128), nn.ELU())
+        self.x_mean = nn.Sequential(nn.Linear(128, obs_dim), nn.Sigmoid())
+        self.x_logvar = nn.Sequential(nn.Linear(128, obs_dim), nn.Hardtanh(min_val=-10.0, max_val=0))
+        emb1 = torch.empty([1, 1, self.obs_dim])
+        nn.init.xavier_uniform_(emb1)
+        self.W = nn.Parameter(emb1, requires_grad=True)
+        emb2 = torch.empty([1, 1, self.obs_dim])
+        nn.init.xavier_uniform_(emb2)
+        self.b = nn.Parameter(emb2, requires_grad=True)
+        self.activation = nn.Softplus()
+        if with_logits:
+            # unused float64 Linear that the reference keeps in its state_dict (VAE.py:2371, SURVEY A.1)
+            self.logits = nn.Sequential(nn.Linear(obs_dim, obs_dim)).double()
+        self.max_epoch = 2800
+
+    def _lin(self, seq, idx, h, act, mask=None):
+        layer = seq[idx]
+        return ops.dense_op(h, layer.weight, layer.bias, mask, act)
+
+    def _stats(self, x, mask):
+        dev = x.device
+        if dev.type != "cuda":
+            raise L.PcvaeError("pcvae modules need CUDA tensors: there is no CPU fallback for this path")
+        h = self._lin(self.seq_encoder, 0, x.float().contiguous(), L.ACT_ELU, mask.to(dev).float().contiguous())
+        h = self._lin(self.seq_encoder, 2, h, L.ACT_ELU)
+        return self._lin(self.q_mu, 0, h, L.ACT_NONE), self._lin(self.q_logstd, 0, h, L.ACT_NONE)
+
+    def encoder(self, x, mask, sample=True):
+        """VAE.py:2377-2390 / 2748-2763: (z, mean, log_var), each [B, S, L]."""
+        mean, log_var = self._stats(x, mask)
+        B, S, Lt = x.shape[0], self.num_samples, self.latent_dim
+        eps = draw_noise_bsl(B, S, Lt, x.device, self.noise) if sample else None
+        z = ops.mnar_sample_z_op(mean, log_var, eps, S)
+        return z, mean.unsqueeze(1).expand(B, S, Lt), log_var.unsqueeze(1).expand(B, S, Lt)
+
+    def decoder(self, z_int):
+        """VAE.py:2392-2396: (x_mean, x_logvar), each [B, S, D]."""
+        shp = z_int.shape
+        h = self._lin(self.seq_decoder, 0, z_int.reshape(-1, shp[-1]).contiguous(), L.ACT_ELU)
+        h = self._lin(self.seq_decoder, 2, h, L.ACT_ELU)
+        xm = self._lin(self.x_mean, 0, h, L.ACT_SIGMOID)
+        xlv = self._lin(self.x_logvar, 0, h, L.ACT_HARDTANH_M10_0)
+        return xm.view(*shp[:-1], self.obs_dim), xlv.view(*shp[:-1], self.obs_dim)
+
+    @staticmethod
+    def _row_stats(t):
+        return t[:, 0, :].contiguous() if t.dim() == 3 else t
+
+    def _mnar_loss(self, x, mask, mask_p, xm_q, xlv_q, xm_p, xlv_p, mean_q, logvar_q, mean_p, logvar_p, alpha,
+                   llh_eval, MI, missing_process):
+        if missing_process != 'selfmasking_known':
+            raise NotImplementedError("only missing_process='selfmasking_known' (the reference default) is built")
+        if MI:
+            raise NotImplementedError("the MI branch of the not-MIWAE losses references undefined names in the "
+                                      "reference (VAE.py:2463-2466) and cannot run there either")
+        dev = xm_q.device
+        reg = mask_p is not None
+        eps_kl = None
+        if not reg:
+            # the second latent draw of notMIWAE_myversion.loss, VAE.py:2791-2793
+            eps_kl = draw_noise_bsl(xm_q.shape[0], xm_q.shape[1], self.latent_dim, dev, self.noise)
+        want = torch.is_grad_enabled() and (xm_q.requires_grad or mean_q.requires_grad)
+        c = lambda t: None if t is None else t.contiguous()
+        out = ops.mnar_loss_op(x.to(dev).float().contiguous(), mask.to(dev).float().contiguous(),
+                               None if mask_p is None else mask_p.to(dev).float().contiguous(), c(xm_q), c(xlv_q),
+                               c(xm_p), c(xlv_p), self._row_stats(mean_q), self._row_stats(logvar_q),
+                               None if mean_p is None else self._row_stats(mean_p),
+                               None if logvar_p is None else self._row_stats(logvar_p), self.W, self.b, eps_kl,
+                               float(alpha), want, bool(llh_eval))
+        loss, stats, xm_imp = out[0], out[1], out[2]
+        if llh_eval:
+            return xm_imp, loss, stats[1].float()
+        return loss, loss
+
+
+class REG_notMIWAE_v2(_NotMIWAEBase):
+    """Regularised not-MIWAE, reference VAE.py:2327-2505."""
+
+    def __init__(self, obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates):
+        super().__init__()
+        self._build(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates, True)
+
+    def loss(self, x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q, mask, mask_p,
+             epoch, vae_elbo=False, llh_eval=False,
+             MI=False,
+             beta_annealing=False, beta=1.0, alpha=1.0, alpha_annealing=False, stage='train',
+             missing_process='selfmasking_known'):
+        return self._mnar_loss(x, mask, mask_p, x_recon_q, x_logvar_q, x_recon_p, x_logvar_p, mean_q, logvar_q,
+                               mean_p, logvar_p, alpha, llh_eval, MI, missing_process)
+
+    def forward(self, data, mask, mask_p, stage='train'):
+        z_q, mean_q, logvar_q = self.encoder(data, mask)
+        x_mean_q, x_logvar_q = self.decoder(z_q)
+        z_p, mean_p, logvar_p = self.encoder(data, mask_p)
+        x_mean_p, x_logvar_p = self.decoder(z_p)
+        return mean_p, logvar_p, x_mean_p, x_logvar_p, mean_q, logvar_q, x_mean_q, x_logvar_q
+
+
+class notMIWAE_myversion(_NotMIWAEBase):
+    """not-MIWAE with a Monte-Carlo KL from a second latent draw, reference VAE.py:2691-2847."""
+
+    def __init__(self, obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates):
+        super().__init__()
+        self._build(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates, False)
+
+    def loss(self, x, x_recon, x_logvar, mean, logvar, epoch, mask, vae_elbo=False, llh_eval=False,
+             MI=False,
+             beta_annealing=False, beta=1.0, stage='train', missing_process='selfmasking_known'):
+        return self._mnar_loss(x, mask, None, x_recon, x_logvar, None, None, mean, logvar, None, None, 1.0, llh_eval,
+                               MI, missing_process)
+
+    def forward(self, data, mask, stage='train'):
+        z, mean, logvar = self.encoder(data, mask)
+        x_mean, x_logvar = self.decoder(z)
+        return mean, logvar, x_mean, x_logvar
+
+
+IN_SCOPE = {"REG_notMIWAE_v2": REG_notMIWAE_v2, "notMIWAE_myversion": notMIWAE_myversion,
+            "Reg_VAE": Reg_VAE, "vanilla_VAE": vanilla_VAE, "Reg_EDDI": Reg_EDDI, "vanilla_EDDI": vanilla_EDDI}
 
 
 def _out_of_scope(name):
@@ -318,6 +466,5 @@ def _out_of_scope(name):
 
 # names src/utils/loaders.py:2-5 imports; the out-of-scope ones fail loudly when instantiated
 for _n in ("Flow", "MIWAE", "Reg_MIWAE", "vanilla_VAE_mask", "Reg_VAE_mask", "notMIWAE", "REG_notMIWAE",
-           "notMIWAE_myversion", "REG_notMIWAE_new_version", "REG_notMIWAE_v2", "REG_VAEFlow", "VAEFlow",
-           "vanilla_EDDI_mnist", "Reg_EDDI_mnist"):
+           "REG_notMIWAE_new_version", "REG_VAEFlow", "VAEFlow", "vanilla_EDDI_mnist", "Reg_EDDI_mnist"):
     globals()[_n] = _out_of_scope(_n)

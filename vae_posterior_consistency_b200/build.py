@@ -7,7 +7,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpcvae_b200.so")
-SOURCES = ["pcvae_common.cu", "pcvae_train.cu", "pcvae_reward.cu", "pcvae_data.cu"]
+SOURCES = ["pcvae_common.cu", "pcvae_train.cu", "pcvae_reward.cu", "pcvae_data.cu", "pcvae_dense.cu",
+           "pcvae_mnar.cu"]
 HEADERS = ["pcvae_internal.cuh", "pcvae_tile.cuh", os.path.join(ROOT, "include", "pcvae_b200.h")]
 
 NVCC_FLAGS = [

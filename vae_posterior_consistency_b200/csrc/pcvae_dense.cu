@@ -1,0 +1,184 @@
+// Generic dense layer on row tiles (weights resident in shared memory) -- forward and backward.
+// Building block of the 128-wide not-MIWAE MNAR networks (src/models/VAE.py:2342-2363, 2706-2730).
+#include "pcvae_internal.cuh"
+
+namespace pcvae {
+
+struct DenseArgs {
+    int R, K, N, act;
+    const float* x;
+    const float* mask;
+    const float* W;
+    const float* b;
+    float* y;
+    const float* yin;
+    const float* dy;
+    float* dx;
+    float* dWp;
+    float* dbp;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(NT, 1) k_dense_fwd(const DenseArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TM = TM_TRAIN, P = TM + 4, RB = 1;
+    const int tid = threadIdx.x, K = a.K, N = a.N, NP = round4(N);
+    float* W_s = smem;                 // [K][NP]
+    float* b_s = W_s + K * NP;         // [NP]
+    float* in_s = b_s + NP;            // [K][P]
+    float* out_s = in_s + K * P;       // [NP][P]
+    stage_linear(W_s, b_s, a.W, a.b, K, N, NP, tid);
+    __syncthreads();
+    const int ntiles = (a.R + TM - 1) / TM;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int row0 = t * TM;
+        tile_elems<TM, 16, XM>(K, row0, a.R, tid,
+            [&](int k, int r, bool ok) {
+                XM v{0.f, 1.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * K + k;
+                    v.x = a.x[gi];
+                    if (a.mask) v.m = a.mask[gi];
+                }
+                return v;
+            },
+            [&](int k, int r, bool, XM v) { in_s[k * P + r] = v.x * v.m; });
+        __syncthreads();
+        gemm_fwd<TM, RB, ACT>(in_s, W_s, b_s, out_s, K, NP, tid);
+        __syncthreads();
+        tile_elems<TM, 1, int>(N, row0, a.R, tid, [](int, int, bool) { return 0; },
+            [&](int n, int r, bool ok, int) { if (ok) a.y[(long)(row0 + r) * N + n] = out_s[n * P + r]; });
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+    if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+    if (act == ACT_SIGMOID) return y * (1.f - y);
+    if (act == ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+    if (act == ACT_HARDTANH) return (y > -10.f && y < 0.f) ? 1.f : 0.f;
+    return 1.f;
+}
+
+__global__ void __launch_bounds__(NT, 1) k_dense_bwd(const DenseArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TM = TM_TRAIN, P = TM + 4, RB = 1;
+    const int tid = threadIdx.x, K = a.K, N = a.N, NP = round4(N);
+    float* W_s = smem;                 // [K][NP]
+    float* dW_s = W_s + K * NP;        // [K][NP]
+    float* db_s = dW_s + K * NP;       // [NP]
+    float* in_s = db_s + NP;           // [K][P]   x*mask, then dx
+    float* dy_s = in_s + K * P;        // [NP][P]  dL/d(pre-activation)
+    stage_linear(W_s, nullptr, a.W, nullptr, K, N, NP, tid);
+    zero_floats(dW_s, K * NP + NP, tid);
+    zero_floats(dy_s, NP * P, tid);
+    __syncthreads();
+    const int ntiles = (a.R + TM - 1) / TM;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int row0 = t * TM;
+        tile_elems<TM, 16, XM>(K, row0, a.R, tid,
+            [&](int k, int r, bool ok) {
+                XM v{0.f, 1.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * K + k;
+                    v.x = a.x[gi];
+                    if (a.mask) v.m = a.mask[gi];
+                }
+                return v;
+            },
+            [&](int k, int r, bool, XM v) { in_s[k * P + r] = v.x * v.m; });
+        tile_elems<TM, 16, XM>(N, row0, a.R, tid,
+            [&](int n, int r, bool ok) {
+                XM v{0.f, 0.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * N + n;
+                    v.x = a.dy[gi];
+                    v.m = a.yin[gi];
+                }
+                return v;
+            },
+            [&](int n, int r, bool ok, XM v) { dy_s[n * P + r] = ok ? v.x * act_grad_from_output(v.m, a.act) : 0.f; });
+        __syncthreads();
+        gemm_dw<TM>(in_s, dy_s, dW_s, K, N, NP, tid);
+        bias_dw<TM>(dy_s, db_s, N, tid);
+        if (a.dx) {
+            __syncthreads();
+            gemm_dx<TM, RB, false>(dy_s, W_s, in_s, K, NP, tid);
+            __syncthreads();
+            tile_elems<TM, 1, int>(K, row0, a.R, tid, [](int, int, bool) { return 0; },
+                [&](int k, int r, bool ok, int) {
+                    if (ok) {
+                        const long gi = (long)(row0 + r) * K + k;
+                        a.dx[gi] = in_s[k * P + r] * (a.mask ? a.mask[gi] : 1.f);
+                    }
+                });
+        }
+        __syncthreads();
+    }
+    flush_linear_grad(dW_s, db_s, a.dWp + (long)blockIdx.x * N * K, a.dbp + (long)blockIdx.x * N, K, N, NP, tid);
+}
+
+}  // namespace pcvae
+
+using namespace pcvae;
+
+static size_t dense_fwd_smem(int K, int N) {
+    const int NP = round4(N), P = TM_TRAIN + 4;
+    return ((size_t)K * NP + NP + (size_t)K * P + (size_t)NP * P) * sizeof(float);
+}
+static size_t dense_bwd_smem(int K, int N) {
+    const int NP = round4(N), P = TM_TRAIN + 4;
+    return (2 * (size_t)K * NP + NP + (size_t)K * P + (size_t)NP * P) * sizeof(float);
+}
+
+template <typename Kern>
+static int launch_dense(Kern kern, size_t smem, int grid, cudaStream_t st, const char* name, const DenseArgs& a) {
+    if (smem > MAX_SMEM) return fail(PCVAE_EINVAL, "%s: needs %zu B shared memory (> %d)", name, smem, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    kern<<<grid, NT, smem, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: launch: %s", name, cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+extern "C" {
+
+int pcvae_dense_fwd(const pcvae_dense_fwd_params* p, void* stream) {
+    if (!p) return fail(PCVAE_EINVAL, "dense_fwd: null params");
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (p->rows < 0 || p->in_dim < 1 || p->in_dim > MAX_D || p->out_dim < 1 || p->out_dim > MAX_D)
+        return fail(PCVAE_EINVAL, "dense_fwd: sizes outside [1,%d]", MAX_D);
+    if (p->rows == 0) return PCVAE_OK;
+    if (!p->x || !p->W || !p->b || !p->y) return fail(PCVAE_EINVAL, "dense_fwd: null pointer");
+    DenseArgs a{};
+    a.R = p->rows; a.K = p->in_dim; a.N = p->out_dim; a.act = p->act; a.x = p->x; a.mask = p->mask; a.W = p->W; a.b = p->b; a.y = p->y;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sm = dense_fwd_smem(a.K, a.N);
+    switch (p->act) {
+        case PCVAE_ACT_NONE: return launch_dense(k_dense_fwd<ACT_NONE>, sm, grid, st, "dense_fwd", a);
+        case PCVAE_ACT_RELU: return launch_dense(k_dense_fwd<ACT_RELU>, sm, grid, st, "dense_fwd", a);
+        case PCVAE_ACT_SIGMOID: return launch_dense(k_dense_fwd<ACT_SIGMOID>, sm, grid, st, "dense_fwd", a);
+        case PCVAE_ACT_ELU: return launch_dense(k_dense_fwd<ACT_ELU>, sm, grid, st, "dense_fwd", a);
+        case PCVAE_ACT_HARDTANH_M10_0: return launch_dense(k_dense_fwd<ACT_HARDTANH>, sm, grid, st, "dense_fwd", a);
+    }
+    return fail(PCVAE_EINVAL, "dense_fwd: unknown activation %d", p->act);
+}
+
+int pcvae_dense_bwd(const pcvae_dense_bwd_params* p, void* stream) {
+    if (!p) return fail(PCVAE_EINVAL, "dense_bwd: null params");
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (p->rows < 0 || p->in_dim < 1 || p->in_dim > MAX_D || p->out_dim < 1 || p->out_dim > MAX_D)
+        return fail(PCVAE_EINVAL, "dense_bwd: sizes outside [1,%d]", MAX_D);
+    if (p->act < PCVAE_ACT_NONE || p->act > PCVAE_ACT_HARDTANH_M10_0) return fail(PCVAE_EINVAL, "dense_bwd: unknown activation %d", p->act);
+    if (!p->W || !p->dW_partials || !p->db_partials) return fail(PCVAE_EINVAL, "dense_bwd: null pointer");
+    if (p->rows > 0 && (!p->x || !p->y || !p->dy)) return fail(PCVAE_EINVAL, "dense_bwd: null x/y/dy");
+    DenseArgs a{};
+    a.R = p->rows; a.K = p->in_dim; a.N = p->out_dim; a.act = p->act; a.x = p->x; a.mask = p->mask; a.W = p->W;
+    a.yin = p->y; a.dy = p->dy; a.dx = p->dx; a.dWp = p->dW_partials; a.dbp = p->db_partials;
+    return launch_dense(k_dense_bwd, dense_bwd_smem(a.K, a.N), grid, (cudaStream_t)stream, "dense_bwd", a);
+}
+
+}  // extern "C"

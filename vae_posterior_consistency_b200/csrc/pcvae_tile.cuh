@@ -22,7 +22,7 @@ namespace pcvae {
 constexpr int NT = 512;          // threads per CTA (16 warps, <= 128 registers each)
 constexpr int NWARP = NT / 32;
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_ELU = 3, ACT_HARDTANH = 4 };
 
 __host__ __device__ constexpr int round4(int v) { return (v + 3) & ~3; }
 
@@ -32,6 +32,8 @@ __device__ __forceinline__ void sts4(float* p, float4 v) { *reinterpret_cast<flo
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == ACT_RELU) return fmaxf(v, 0.0f);
     if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    if (act == ACT_ELU) return v > 0.0f ? v : expm1f(v);
+    if (act == ACT_HARDTANH) return fminf(fmaxf(v, -10.0f), 0.0f);
     return v;
 }
 

@@ -92,6 +92,62 @@ def eval_vae(list_loaders, missing_rate, obs_dim, hid_dim, K, M, latent_dim, dat
         return results
 
 
+def eval_vae_mnar(data_test, mask_test, missing_rate, obs_dim, hid_dim, K, M, latent_dim, data_type,
+                  training_parameters, experiment_type, vae_type, max_epochs, valid_k, num_estimates,
+                  device=torch.device('cpu'), alpha=0.5, stage='evaluate', p_missingness=30, reg_type='ml_reg',
+                  beta=1.0, beta_annealing=False, alpha_annealing=True, not_miwae_type='changed'):
+    """Importance-weighted MNAR imputation RMSE (evaluate.py:13-69).  The reference loops row by row with
+    S = valid_k samples; here rows are processed in blocks while the host noise is
+    still drawn row by row in the reference's order (sub-mask, eps_q, eps_p / eps, eps_kl) so that parity-mode
+    results match bit for bit in their inputs."""
+    device = torch.device(device)
+    with torch.no_grad():
+        model = model_loader('test', obs_dim, hid_dim, K, latent_dim, missing_rate, data_type, training_parameters,
+                             max_epochs, valid_k, num_estimates, experiment_type, reg_type, vae_type, alpha=alpha,
+                             p_missingness=p_missingness, not_miwae_type=not_miwae_type)
+        model.to(device)
+        reg = 'reg_notMIWAE' in vae_type
+        S, Lt = model.num_samples, latent_dim
+        N = data_test.shape[0]
+        x_all, m_all = data_test.float().to(device), mask_test.float().to(device)
+        block = max(1, min(N, (1 << 22) // max(S * obs_dim, 1)))          # ~4M decoder outputs per block
+        recons = []
+        for _ in range(M):
+            XM = torch.zeros(N, obs_dim, device=device)
+            for lo in range(0, N, block):
+                hi = min(N, lo + block)
+                eps_q, eps_kl = [], []
+                for i in range(lo, hi):
+                    create_missing_uci(data_test.shape, p_missingness)          # evaluate.py:31, per row
+                    eps_q.append(torch.empty(1, S, Lt).normal_())
+                    eps_kl.append(torch.empty(1, S, Lt).normal_())              # reg: the p-branch draw; vanilla: z'
+                eps_q = torch.cat(eps_q).to(device)
+                xb, mb = x_all[lo:hi], m_all[lo:hi]
+                mean, log_var = model._stats(xb, mb)
+                z = ops.mnar_sample_z_op(mean, log_var, eps_q, S)
+                xm, xlv = model.decoder(z)
+                if reg:
+                    # llh_eval only needs the q branch (VAE.py:2458-2461); zero p inputs keep the kernel's contract
+                    out = ops.mnar_loss_op(xb, mb, mb, xm, xlv, xm, xlv, mean, log_var, mean, log_var, model.W,
+                                           model.b, None, float(alpha), False, True)
+                else:
+                    out = ops.mnar_loss_op(xb, mb, None, xm, xlv, None, None, mean, log_var, None, None, model.W,
+                                           model.b, torch.cat(eps_kl).to(device), 1.0, False, True)
+                XM[lo:hi] = out[2]
+            miss = 1 - m_all
+            recons.append(torch.sqrt(torch.sum((XM * miss - x_all * miss) ** 2) / torch.sum(miss)))
+        recon = torch.stack(recons).mean().cpu()
+        base = os.path.join('experiments', experiment_type, data_type, 'rest',
+                            ''.join(c for c in vae_type if not c.isdigit()))
+        os.makedirs(base, exist_ok=True)
+        if 'vanilla' in vae_type:
+            fname = f'{vae_type}_rmse_{not_miwae_type}_large_batch_test.pt'
+        else:
+            fname = f'{vae_type}_rmse_{alpha}_{p_missingness}_{reg_type}_full_reg_large_batch_v2_test.pt'
+        torch.save(recon, os.path.join(base, fname))
+        return recon
+
+
 def R_lindley_chain(i, x, mask, M, vae, im, loc):
     """Reward of candidate `i` for the rows `loc` (evaluate.py:514-542).  Kept for API compatibility; it
     evaluates the all-candidates kernel on the selected rows and returns column `i`."""

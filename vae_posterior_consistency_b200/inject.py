@@ -59,10 +59,10 @@ def install():
         parent, leaf = full.rsplit(".", 1)
         setattr(sys.modules[parent], leaf, mod)
     # names the drivers import from src.utils.loaders that this package does not reimplement
-    for missing in ("data_loader_mnar", "data_loader_mnist"):
+    for missing in ("data_loader_mnist",):
         if not hasattr(loaders, missing):
             setattr(loaders, missing, _ais_unavailable)
-    for missing in ("eval_miwae", "eval_vae_mnar"):
+    for missing in ("eval_miwae",):
         if not hasattr(evaluate, missing):
             setattr(evaluate, missing, _ais_unavailable)
     return mods

@@ -252,6 +252,119 @@ class Engine:
         return R, workspace
 
 
+# ------------------------------------------------------------------------------------------------
+# generic dense layers and the not-MIWAE MNAR pieces
+# ------------------------------------------------------------------------------------------------
+
+_GRID = {}
+
+
+def grid_ctas(device) -> int:
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _GRID:
+        with torch.cuda.device(idx):
+            g = L.load().pcvae_grid_ctas()
+        if g <= 0:
+            L.check(2, "pcvae_grid_ctas")
+        _GRID[idx] = g
+    return _GRID[idx]
+
+
+def dense_fwd(x, W, b, act, mask=None):
+    """y = act((x*mask) W^T + b); x [R, K] -> y [R, N]."""
+    _need_cuda(x, W, b)
+    x, W, b = _f32(x), _f32(W), _f32(b)
+    mask = None if mask is None else _f32(mask)
+    R, K = x.shape
+    N = W.shape[0]
+    y = torch.empty(R, N, device=x.device, dtype=torch.float32)
+    p = L.DenseFwdParams(rows=R, in_dim=K, out_dim=N, act=act, x=_p(x), mask=_p(mask), W=_p(W), b=_p(b), y=_p(y))
+    with torch.cuda.device(x.device):
+        L.check(L.load().pcvae_dense_fwd(C.byref(p), _stream()), "pcvae_dense_fwd")
+    return y
+
+
+def dense_bwd(x, W, y, dy, act, mask=None, need_dx=True):
+    """(dx, dW, db) of dense_fwd."""
+    x, W, y, dy = _f32(x), _f32(W), _f32(y), _f32(dy)
+    mask = None if mask is None else _f32(mask)
+    R, K = x.shape
+    N = W.shape[0]
+    lib = L.load()
+    g = grid_ctas(x.device)
+    dWp = torch.empty(g, N * K, device=x.device, dtype=torch.float32)
+    dbp = torch.empty(g, N, device=x.device, dtype=torch.float32)
+    dx = torch.empty(R, K, device=x.device, dtype=torch.float32) if need_dx else None
+    p = L.DenseBwdParams(rows=R, in_dim=K, out_dim=N, act=act, x=_p(x), mask=_p(mask), y=_p(y), dy=_p(dy), W=_p(W),
+                         dx=_p(dx), dW_partials=_p(dWp), db_partials=_p(dbp))
+    dW = torch.empty(N, K, device=x.device, dtype=torch.float32)
+    db = torch.empty(N, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        L.check(lib.pcvae_dense_bwd(C.byref(p), _stream()), "pcvae_dense_bwd")
+        L.check(lib.pcvae_reduce_grads(_p(dWp), g, N * K, 0, N * K, _p(dW), 0, _stream()), "pcvae_reduce_grads")
+        L.check(lib.pcvae_reduce_grads(_p(dbp), g, N, 0, N, _p(db), 0, _stream()), "pcvae_reduce_grads")
+    return dx, dW, db
+
+
+def mnar_sample_z(mean, logvar, eps, samples):
+    """z[b,s,:] = mean[b] + exp(logvar[b]/2) * eps[b,s]; eps None -> z = mean (sample=False)."""
+    mean, logvar = _f32(mean), _f32(logvar)
+    eps = None if eps is None else _f32(eps)
+    B, Lt = mean.shape
+    z = torch.empty(B, samples, Lt, device=mean.device, dtype=torch.float32)
+    with torch.cuda.device(mean.device):
+        L.check(L.load().pcvae_mnar_sample_z(_p(mean), _p(logvar), _p(eps), _p(z), B, samples, Lt, _stream()),
+                "pcvae_mnar_sample_z")
+    return z
+
+
+def mnar_sample_z_bwd(d_z, logvar, eps):
+    d_z, logvar = _f32(d_z), _f32(logvar)
+    eps = None if eps is None else _f32(eps)
+    B, S, Lt = d_z.shape
+    d_mean, d_logvar = torch.empty_like(logvar), torch.empty_like(logvar)
+    with torch.cuda.device(d_z.device):
+        L.check(L.load().pcvae_mnar_sample_z_bwd(_p(d_z), _p(logvar), _p(eps), _p(d_mean), _p(d_logvar), B, S, Lt,
+                                                 _stream()), "pcvae_mnar_sample_z_bwd")
+    return d_mean, d_logvar
+
+
+def mnar_loss(x, mask, mask_p, xm, xlv, mean, logvar, W, b, alpha, regularised, eps_kl=None, want_grads=False,
+              want_imputed=False):
+    """REG_notMIWAE_v2.loss / notMIWAE_myversion.loss.  xm/xlv/mean/logvar are lists over branches (q[, p]).
+    Returns dict(out=[loss, RE_q.mean(), loss_q, loss_p] float64, xm_imputed, grads...)."""
+    x, mask = _f32(x), _f32(mask)
+    mask_p = None if mask_p is None else _f32(mask_p)
+    xm, xlv = [_f32(t) for t in xm], [_f32(t) for t in xlv]
+    mean, logvar = [_f32(t) for t in mean], [_f32(t) for t in logvar]
+    W, b = _f32(W).reshape(-1), _f32(b).reshape(-1)
+    eps_kl = None if eps_kl is None else _f32(eps_kl)
+    B, S, D = xm[0].shape
+    Lt = mean[0].shape[1]
+    dev = x.device
+    lib = L.load()
+    nbytes = lib.pcvae_mnar_loss_workspace_bytes(B, S, D)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    out = torch.empty(4, device=dev, dtype=torch.float64)
+    xm_imp = torch.empty(B, D, device=dev) if want_imputed else None
+    nb = 2 if regularised else 1
+    g = lambda like: [torch.empty_like(t) for t in like[:nb]] if want_grads else [None] * nb
+    d_xm, d_xlv, d_mean, d_logvar = g(xm), g(xlv), g(mean), g(logvar)
+    d_W = torch.empty(D, device=dev) if want_grads else None
+    d_b = torch.empty(D, device=dev) if want_grads else None
+    pad = lambda ts: list(ts) + [None] * (2 - len(ts))
+    p = L.MnarLossParams(rows=B, samples=S, obs_dim=D, latent_dim=Lt, regularised=int(regularised), x=_p(x),
+                         mask=_p(mask), mask_p=_p(mask_p), xm=_pair(pad(xm)), xlv=_pair(pad(xlv)),
+                         mean=_pair(pad(mean)), logvar=_pair(pad(logvar)), eps_kl=_p(eps_kl), W=_p(W), b=_p(b),
+                         alpha=float(alpha), workspace=_p(ws), workspace_bytes=nbytes, out=_p(out),
+                         xm_imputed=_p(xm_imp), d_xm=_pair(pad(d_xm)), d_xlv=_pair(pad(d_xlv)),
+                         d_mean=_pair(pad(d_mean)), d_logvar=_pair(pad(d_logvar)), d_W=_p(d_W), d_b=_p(d_b))
+    with torch.cuda.device(dev):
+        L.check(lib.pcvae_mnar_loss(C.byref(p), _stream()), "pcvae_mnar_loss")
+    return dict(out=out, xm_imputed=xm_imp, d_xm=d_xm, d_xlv=d_xlv, d_mean=d_mean, d_logvar=d_logvar, d_W=d_W, d_b=d_b)
+
+
 def loss_from_sums(sums: torch.Tensor, rows: int, alpha: float, beta_w: float, regularised: bool):
     """train_loss = L / B with L as in VAE.py:441-452 (device tensor, float64)."""
     loss_q = sums[L.S_RE_Q] + beta_w * sums[L.S_KL_Q]

@@ -25,7 +25,8 @@ SYMBOLS = [
     "pcvae_decoder_offset", "pcvae_enc_act_ws_floats", "pcvae_enc_fwd", "pcvae_enc_bwd", "pcvae_dec",
     "pcvae_loss_terms", "pcvae_grid_ctas", "pcvae_reduce_sums", "pcvae_reduce_grads", "pcvae_adam_step",
     "pcvae_reward_workspace_bytes", "pcvae_reward_chain", "pcvae_ffma_probe", "pcvae_gather_rows",
-    "pcvae_draw_submask", "pcvae_draw_normal",
+    "pcvae_draw_submask", "pcvae_draw_normal", "pcvae_dense_fwd", "pcvae_dense_bwd", "pcvae_mnar_sample_z",
+    "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss",
 ]
 
 
@@ -77,6 +78,29 @@ class RewardParams(C.Structure):
                 ("workspace_bytes", C.c_size_t), ("pnp_ac", C.c_void_p)]
 
 
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_ELU, ACT_HARDTANH_M10_0 = range(5)
+
+
+class DenseFwdParams(C.Structure):
+    _fields_ = [("rows", C.c_int), ("in_dim", C.c_int), ("out_dim", C.c_int), ("act", C.c_int), ("x", C.c_void_p),
+                ("mask", C.c_void_p), ("W", C.c_void_p), ("b", C.c_void_p), ("y", C.c_void_p)]
+
+
+class DenseBwdParams(C.Structure):
+    _fields_ = [("rows", C.c_int), ("in_dim", C.c_int), ("out_dim", C.c_int), ("act", C.c_int), ("x", C.c_void_p),
+                ("mask", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("W", C.c_void_p), ("dx", C.c_void_p),
+                ("dW_partials", C.c_void_p), ("db_partials", C.c_void_p)]
+
+
+class MnarLossParams(C.Structure):
+    _fields_ = [("rows", C.c_int), ("samples", C.c_int), ("obs_dim", C.c_int), ("latent_dim", C.c_int),
+                ("regularised", C.c_int), ("x", C.c_void_p), ("mask", C.c_void_p), ("mask_p", C.c_void_p),
+                ("xm", _P2), ("xlv", _P2), ("mean", _P2), ("logvar", _P2), ("eps_kl", C.c_void_p), ("W", C.c_void_p),
+                ("b", C.c_void_p), ("alpha", C.c_float), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("out", C.c_void_p), ("xm_imputed", C.c_void_p), ("d_xm", _P2), ("d_xlv", _P2), ("d_mean", _P2),
+                ("d_logvar", _P2), ("d_W", C.c_void_p), ("d_b", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -118,6 +142,15 @@ def load():
     lib.pcvae_draw_submask.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_ulonglong, C.c_ulonglong,
                                        C.c_void_p]
     lib.pcvae_draw_normal.argtypes = [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
+    lib.pcvae_dense_fwd.argtypes = [C.POINTER(DenseFwdParams), C.c_void_p]
+    lib.pcvae_dense_bwd.argtypes = [C.POINTER(DenseBwdParams), C.c_void_p]
+    lib.pcvae_mnar_sample_z.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p]
+    lib.pcvae_mnar_sample_z_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p]
+    lib.pcvae_mnar_loss_workspace_bytes.restype = C.c_size_t
+    lib.pcvae_mnar_loss_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.pcvae_mnar_loss.argtypes = [C.POINTER(MnarLossParams), C.c_void_p]
     lib.pcvae_ffma_probe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     _lib = lib
     return lib

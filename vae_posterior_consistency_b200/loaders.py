@@ -6,9 +6,9 @@ import torch
 from numpy import loadtxt
 from torch.utils.data import DataLoader
 
-from .VAE import Reg_EDDI, Reg_VAE, vanilla_EDDI, vanilla_VAE
+from .VAE import REG_notMIWAE_v2, Reg_EDDI, Reg_VAE, notMIWAE_myversion, vanilla_EDDI, vanilla_VAE
 
-_OUT_OF_SCOPE = ("flow", "mask_augm", "reg_notMIWAE", "reg_MIWAE", "vanilla_notMIWAE")
+_OUT_OF_SCOPE = ("flow", "mask_augm", "reg_MIWAE")
 
 
 def _strip_digits(s):
@@ -37,6 +37,9 @@ def model_loader(stage, obs_dim, hid_dim, K, latent_dim, missing_rate, data_type
         model = Reg_VAE(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, reg_type, num_samples,
                         num_estimates)
         load_dir = _strip_digits(vae_type)
+    elif 'reg_notMIWAE' in vae_type:
+        model = REG_notMIWAE_v2(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
+        load_dir = _strip_digits(vae_type)
     elif 'reg_EDDI' in vae_type:
         if data_type == 'mnist':
             raise NotImplementedError("the MNIST variants are outside the B200 hot path (SURVEY.md section 2 #16)")
@@ -53,6 +56,9 @@ def model_loader(stage, obs_dim, hid_dim, K, latent_dim, missing_rate, data_type
         model = vanilla_EDDI(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, num_samples,
                              num_estimates)
         load_dir = 'vanilla_EDDI'
+    elif 'vanilla_notMIWAE' in vae_type:
+        model = notMIWAE_myversion(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
+        load_dir = _strip_digits(vae_type)
     else:
         raise NotImplementedError(f"vae_type {vae_type!r}: MIWAE (Student-t) is outside the B200 hot path")
     if stage == 'train':
@@ -106,3 +112,20 @@ def data_loader(data_path, vae_type, missing_rate, batch_size, data_type, device
         loader.pcvae_table = (d, m)
         out.append([loader, name])
     return out[0], out[1], data.shape[1]
+
+
+def data_loader_mnar(data_path, vae_type, missing_rate, batch_size, data_type, device=torch.device('cpu'), shuffle=True,
+                     data_transform='minmax'):
+    """reference loaders.py:357-384: rows permuted by rand_perm<i>.pt, LAST column of data and mask dropped,
+    min-max, one bare DataLoader; returns (loader, obs_dim).  The mask is float32."""
+    index = [c for c in vae_type if c.isdigit()][0]
+    folder = os.path.join(data_path, data_type)
+    data = torch.load(os.path.join(folder, 'data.pt'))
+    perm = torch.load(os.path.join('Data', data_type, f'rand_perm{index}.pt')).numpy()
+    data = data[perm, :][:, :-1]
+    mask = torch.load(os.path.join(folder, f'mnar_mask_missing{index}.pt'))[:, :-1]
+    data = _minmax(data, data_transform)
+    d, m = data.to(device), mask.to(device)
+    loader = DataLoader(ConcatDataset(d, m), batch_size=batch_size, shuffle=shuffle, drop_last=False, num_workers=0)
+    loader.pcvae_table = (d, m)
+    return loader, data.shape[1]

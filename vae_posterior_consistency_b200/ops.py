@@ -215,3 +215,137 @@ def reward_chain_op(theta: Tensor, x: Tensor, mask: Tensor, im: Tensor, family: 
 @reward_chain_op.register_fake
 def _(theta, x, mask, im, family, D, K):
     return x.new_empty(x.shape[0], D - 1, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------
+# generic dense layer + not-MIWAE MNAR pieces (REG_notMIWAE_v2 / notMIWAE_myversion)
+# ------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("pcvae::dense", mutates_args=())
+def dense_op(x: Tensor, W: Tensor, b: Tensor, mask: Optional[Tensor], act: int) -> Tensor:
+    """y = act((x*mask) W^T + b) -- nn.Linear + activation of VAE.py:2342-2363."""
+    return KR.dense_fwd(x, W, b, act, mask)
+
+
+@dense_op.register_fake
+def _(x, W, b, mask, act):
+    return x.new_empty(x.shape[0], W.shape[0], dtype=torch.float32)
+
+
+@torch.library.custom_op("pcvae::dense_bwd", mutates_args=())
+def dense_bwd_op(x: Tensor, W: Tensor, y: Tensor, dy: Tensor, mask: Optional[Tensor], act: int,
+                 need_dx: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    dx, dW, db = KR.dense_bwd(x, W, y, dy, act, mask, need_dx)
+    if dx is None:
+        dx = x.new_empty(0, dtype=torch.float32)
+    return dx, dW, db
+
+
+@dense_bwd_op.register_fake
+def _(x, W, y, dy, mask, act, need_dx):
+    return (torch.empty_like(x) if need_dx else x.new_empty(0)), torch.empty_like(W), W.new_empty(W.shape[0])
+
+
+def _dense_setup(ctx, inputs, output):
+    x, W, b, mask, act = inputs
+    ctx.save_for_backward(x, W, output, mask)
+    ctx.act = act
+    ctx.need_dx = x.requires_grad
+
+
+def _dense_backward(ctx, dy):
+    x, W, y, mask = ctx.saved_tensors
+    dx, dW, db = dense_bwd_op(x, W, y, dy.contiguous(), mask, ctx.act, ctx.need_dx)
+    return (dx if ctx.need_dx else None), dW, db, None, None
+
+
+torch.library.register_autograd("pcvae::dense", _dense_backward, setup_context=_dense_setup)
+
+
+@torch.library.custom_op("pcvae::mnar_sample_z", mutates_args=())
+def mnar_sample_z_op(mean: Tensor, logvar: Tensor, eps: Optional[Tensor], samples: int) -> Tensor:
+    """z [B,S,L] from per-row (mean, logvar) and eps [B,S,L]; VAE.py:2382-2387, 2753-2760."""
+    return KR.mnar_sample_z(mean, logvar, eps, samples)
+
+
+@mnar_sample_z_op.register_fake
+def _(mean, logvar, eps, samples):
+    return mean.new_empty(mean.shape[0], samples, mean.shape[1])
+
+
+@torch.library.custom_op("pcvae::mnar_sample_z_bwd", mutates_args=())
+def mnar_sample_z_bwd_op(d_z: Tensor, logvar: Tensor, eps: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    return KR.mnar_sample_z_bwd(d_z, logvar, eps)
+
+
+@mnar_sample_z_bwd_op.register_fake
+def _(d_z, logvar, eps):
+    return torch.empty_like(logvar), torch.empty_like(logvar)
+
+
+def _sz_setup(ctx, inputs, output):
+    mean, logvar, eps, samples = inputs
+    ctx.save_for_backward(logvar, eps)
+
+
+def _sz_backward(ctx, d_z):
+    logvar, eps = ctx.saved_tensors
+    dm, dv = mnar_sample_z_bwd_op(d_z.contiguous(), logvar, eps)
+    return dm, dv, None, None
+
+
+torch.library.register_autograd("pcvae::mnar_sample_z", _sz_backward, setup_context=_sz_setup)
+
+
+@torch.library.custom_op("pcvae::mnar_loss", mutates_args=())
+def mnar_loss_op(x: Tensor, mask: Tensor, mask_p: Optional[Tensor], xm_q: Tensor, xlv_q: Tensor,
+                 xm_p: Optional[Tensor], xlv_p: Optional[Tensor], mean_q: Tensor, logvar_q: Tensor,
+                 mean_p: Optional[Tensor], logvar_p: Optional[Tensor], W: Tensor, b: Tensor,
+                 eps_kl: Optional[Tensor], alpha: float, want_grads: bool, want_imputed: bool
+                 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor,
+                            Tensor, Tensor]:
+    """(loss fp32, out[4] f64 = loss/RE_q.mean()/loss_q/loss_p, xm_imputed, then gradients of the loss w.r.t.
+    xm_q, xlv_q, mean_q, logvar_q, xm_p, xlv_p, mean_p, logvar_p, W, b).  VAE.py:2398-2471 / 2772-2823."""
+    reg = mask_p is not None
+    r = KR.mnar_loss(x, mask, mask_p, [xm_q, xm_p] if reg else [xm_q], [xlv_q, xlv_p] if reg else [xlv_q],
+                     [mean_q, mean_p] if reg else [mean_q], [logvar_q, logvar_p] if reg else [logvar_q], W, b, alpha,
+                     reg, eps_kl=eps_kl, want_grads=want_grads, want_imputed=want_imputed)
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    o = lambda t: e() if t is None else t
+    loss = r["out"][0].to(torch.float32)
+    g = [e()] * 10
+    if want_grads:
+        g = [r["d_xm"][0], r["d_xlv"][0], r["d_mean"][0], r["d_logvar"][0]]
+        g += [r["d_xm"][1], r["d_xlv"][1], r["d_mean"][1], r["d_logvar"][1]] if reg else [e(), e(), e(), e()]
+        g += [r["d_W"].reshape(W.shape), r["d_b"].reshape(b.shape)]
+    return (loss, r["out"], o(r["xm_imputed"]), *g)
+
+
+@mnar_loss_op.register_fake
+def _(x, mask, mask_p, xm_q, xlv_q, xm_p, xlv_p, mean_q, logvar_q, mean_p, logvar_p, W, b, eps_kl, alpha, want_grads,
+      want_imputed):
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    return (x.new_empty((), dtype=torch.float32), x.new_empty(4, dtype=torch.float64),
+            torch.empty_like(x) if want_imputed else e(), *[e() for _ in range(10)])
+
+
+def _mnar_setup(ctx, inputs, output):
+    ctx.reg = inputs[2] is not None
+    ctx.has_grads = inputs[15]
+    ctx.save_for_backward(*output[3:])
+
+
+def _mnar_backward(ctx, d_loss, *unused):
+    if not ctx.has_grads:
+        raise RuntimeError("pcvae::mnar_loss was run with want_grads=False")
+    g = ctx.saved_tensors
+    sc = lambda t: t * d_loss
+    out = [None] * 17
+    out[3], out[4], out[7], out[8] = sc(g[0]), sc(g[1]), sc(g[2]), sc(g[3])
+    if ctx.reg:
+        out[5], out[6], out[9], out[10] = sc(g[4]), sc(g[5]), sc(g[6]), sc(g[7])
+    out[11], out[12] = sc(g[8]), sc(g[9])
+    return tuple(out)
+
+
+torch.library.register_autograd("pcvae::mnar_loss", _mnar_backward, setup_context=_mnar_setup)

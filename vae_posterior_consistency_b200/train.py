@@ -93,7 +93,7 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
     throughput = os.environ.get('PCVAE_MODE', 'parity') == 'throughput'
     model.noise = 'device' if throughput else 'host'
     regularised = 'reg' in vae_type
-    fused = (not beta_annealing) and (not regularised or reg_type == 'kl_reg')
+    fused = ('notMIWAE' not in vae_type) and (not beta_annealing) and (not regularised or reg_type == 'kl_reg')
     world_size, rank, group = world()
 
     if fused:
