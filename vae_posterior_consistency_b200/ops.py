@@ -313,7 +313,7 @@ def mnar_loss_op(x: Tensor, mask: Tensor, mask_p: Optional[Tensor], xm_q: Tensor
     e = lambda: x.new_empty(0, dtype=torch.float32)
     o = lambda t: e() if t is None else t
     loss = r["out"][0].to(torch.float32)
-    g = [e()] * 10
+    g = [e() for _ in range(10)]
     if want_grads:
         g = [r["d_xm"][0], r["d_xlv"][0], r["d_mean"][0], r["d_logvar"][0]]
         g += [r["d_xm"][1], r["d_xlv"][1], r["d_mean"][1], r["d_logvar"][1]] if reg else [e(), e(), e(), e()]
