@@ -162,6 +162,87 @@ def cpu_reward_triples_per_s(n_rows, n_cand, samples, reps=1):
     return n_rows * n_cand * samples / dt, dt * 1e3
 
 
+FLOP_MNAR_ROW = 7_590_000         # REG_notMIWAE_v2, D=50, S=20, fwd+bwd both branches
+
+
+def cpu_mnar_rows_per_s(batch, samples, steps, warmup):
+    from oracle import pcvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    D = 50
+    p = O.init_mnar_params(D, seed=0)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(batch, D, generator=g)
+    mask = (torch.rand(batch, D, generator=g) < 0.7).float()
+    names = O.mnar_trainable_names(p)
+    m = {k: torch.zeros_like(p[k]) for k in names}
+    v = {k: torch.zeros_like(p[k]) for k in names}
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        mask_p = mask * (torch.rand(batch, D) < 0.5).float()
+        eq, ep = torch.randn(batch, samples, 10), torch.randn(batch, samples, 10)
+        _, grads, _ = O.mnar_train_step(p, x, mask, mask_p, eq, ep)
+        for k in names:
+            p[k], m[k], v[k] = O.adam_step(p[k], grads[k], m[k], v[k], s + 1)
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warmup:]) / steps
+    return batch / t, t * 1e3
+
+
+def gpu_mnar(args, dev, ffma_tflops, with_cpu):
+    """cfg2: REG_notMIWAE_v2 on a synthetic 10 000 x 50 MNAR table, batch 128, S = train_k = 20; a step is
+    model.forward + model.loss + backward (pcvae:: custom ops) + torch.optim.Adam, as train.py:87-116 runs it."""
+    from vae_posterior_consistency_b200 import VAE
+    D, B, S, N = 50, 128, 20, 10_000
+    torch.manual_seed(0)
+    model = VAE.REG_notMIWAE_v2(D, 500, 20, 10, {"batch_size": B, "patience": 100}, S, 10).to(dev)
+    model.noise = "device"
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(9)
+    table = torch.rand(N, D, device=dev, generator=g)
+    mtable = torch.ones(N, D, device=dev)
+    mtable[:, :D // 2] = (table[:, :D // 2] <= table[:, :D // 2].mean(0)).float()     # self-masking MNAR
+    steps, warm = args.mnar_steps, 5
+
+    def step(i):
+        idx = torch.randint(0, N, (B,), device=dev, generator=g)
+        x, mask = table[idx], mtable[idx]
+        mask_p = mask * (torch.rand(B, D, device=dev, generator=g) < 0.5).float()
+        out = model.forward(x, mask, mask_p, stage="train")
+        mean_p, logvar_p, xm_p, xlv_p, mean_q, logvar_q, xm_q, xlv_q = out
+        _, loss = model.loss(x, xm_p, xlv_p, mean_p, logvar_p, xm_q, xlv_q, mean_q, logvar_q, mask, mask_p, i + 1,
+                             alpha=1.0, stage="train")
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        loss = step(i)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    res = {"metric": "MNAR train rows/s (REG_notMIWAE_v2, fwd+bwd+Adam)", "value": B / (ms * 1e-3), "unit": "rows/s",
+           "ms_per_step": ms, "steps": steps,
+           "config": {"workload": f"cfg2: synthetic {N} x {D} self-masking MNAR table, batch {B}, train_k {S}, "
+                                  "module API + autograd over pcvae:: dense / mnar ops, device noise"},
+           "roofline": {"bound": "launch latency (2 560 virtual rows per step; ~60 kernel launches)",
+                        "achieved": FLOP_MNAR_ROW * B / (ms * 1e-3) / 1e12, "peak": ffma_tflops, "unit": "TFLOP/s",
+                        "frac": FLOP_MNAR_ROW * B / (ms * 1e-3) / 1e12 / ffma_tflops},
+           "final_loss": float(loss)}
+    if with_cpu:
+        cv, cms = cpu_mnar_rows_per_s(B, S, 5, 1)
+        res["cpu_baseline"] = {"value": cv, "unit": "rows/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": f"5 steps, batch {B}, S={S}, oracle port of REG_notMIWAE_v2 step + Adam",
+                               "ms_per_step": cms}
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -416,6 +497,8 @@ def run_ours(args):
                                  "unit": "GB/s", "peak_source": peak_src}},
             "secondary": sec,
         }
+        if world == 1 and args.mnar_steps > 0:
+            line["mnar"] = gpu_mnar(args, dev, ffma_tflops, not args.no_cpu)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             cv, cms = cpu_train_rows_per_s(B, 3, 1)
@@ -442,6 +525,7 @@ def main():
     ap.add_argument("--reward-rows", type=int, default=100_000)
     ap.add_argument("--reward-samples", type=int, default=50)
     ap.add_argument("--reward-steps", type=int, default=3)
+    ap.add_argument("--mnar-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -242,6 +242,10 @@ typedef struct {
 } pcvae_reward_params;
 size_t pcvae_reward_workspace_bytes(const pcvae_model* m, int rows, int samples);
 int pcvae_reward_chain(const pcvae_reward_params* p, void* stream);
+/* Select the main reward kernel of the MLP family: 1 = tcgen05 tensor cores with the fp32-accurate
+ * 3xTF32 operand split (csrc/pcvae_reward_tc.cu), 0 = FP32 FFMA (csrc/pcvae_reward.cu).  Both compute the
+ * same function to fp32 accuracy; the PNP family always uses the FFMA kernel.  Returns the previous value. */
+int pcvae_set_reward_tensor_cores(int enable);
 
 /* ------------------------------------------------------------------------
  * Throughput-mode batch preparation on the device.

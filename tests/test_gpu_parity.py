@@ -206,8 +206,17 @@ def test_empty_batch_is_a_no_op():
     assert mean[0].shape == (0, 10) and z[0].shape == (0, 10)        # VAE.py:723-724 empty guard
 
 
+@pytest.fixture(params=[0, 1], ids=["ffma", "tcgen05"])
+def reward_tc(request):
+    """Run the reward tests with both main kernels: FP32 FFMA and tcgen05 3xTF32 (MLP family)."""
+    KR, L = _mods()
+    prev = L.load().pcvae_set_reward_tensor_cores(request.param)
+    yield request.param
+    L.load().pcvae_set_reward_tensor_cores(prev)
+
+
 @pytest.mark.parametrize("name", ["reward_reg_vae_n24_d8_m5", "reward_reg_eddi_n24_d8_k10_m5"])
-def test_golden_reward(golden, name):
+def test_golden_reward(golden, name, reward_tc):
     KR, L = _mods()
     g = golden(name)
     eng, theta, fam = engine_for(g["state_dict"])
@@ -225,7 +234,7 @@ def test_golden_reward(golden, name):
 
 @pytest.mark.parametrize("family,N,D,K,M", [("mlp", 150, 20, 0, 7), ("pnp", 150, 20, 10, 7), ("mlp", 70, 101, 0, 3),
                                             ("pnp", 40, 101, 20, 2), ("mlp", 5, 2, 0, 1)])
-def test_reward_vs_oracle_random(family, N, D, K, M):
+def test_reward_vs_oracle_random(family, N, D, K, M, reward_tc):
     KR, L = _mods()
     p = O.init_params(family, D, K, seed=N + D)
     p = {k: (v * 2.0 if v.dtype == torch.float32 and not k.startswith("prior") else v) for k, v in p.items()}
@@ -247,7 +256,7 @@ def test_reward_vs_oracle_random(family, N, D, K, M):
     assert err_cuda <= max(4 * err_ref, 1e-4 * scale + 2e-6), (err_cuda, err_ref, scale)
 
 
-def test_reward_is_row_shardable_bit_exact():
+def test_reward_is_row_shardable_bit_exact(reward_tc):
     """Rows are independent: evaluating two row blocks separately must reproduce the single
     call bit for bit (what the multi-GPU sharding relies on)."""
     KR, L = _mods()

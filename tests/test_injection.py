@@ -69,6 +69,33 @@ def test_active_learning_driver_binds(injected):
     assert a["test_mask"].dtype.is_floating_point is False
 
 
+def test_mnar_driver_binds(injected, tmp_path):
+    inject, calls = injected
+    from synth import make_tree_mnar
+    from vae_posterior_consistency_b200 import evaluate
+    import inspect as _inspect
+    make_tree_mnar(str(tmp_path), "synthmnar", 30, 6, seed=1)
+    line = json.loads(open(os.path.join(REF, "Data", "imputation_args_mnar.json")).readline())
+    line["vae_type"]["default"] = "reg_notMIWAE1"
+    line["data_type"]["default"] = "synthmnar"
+    with open(tmp_path / "Data" / "imputation_args_mnar.json", "w") as f:
+        f.write(json.dumps(line) + "\n")
+    sig = _inspect.signature(evaluate.eval_vae_mnar)
+    rec = []
+    evaluate.eval_vae_mnar, orig = (lambda *a, **k: rec.append(sig.bind(*a, **k))), evaluate.eval_vae_mnar
+    try:
+        inject.run_driver(os.path.join(DRIVERS, "imputation_mnar.py"))
+    finally:
+        evaluate.eval_vae_mnar = orig
+    assert [n for n, _ in calls] == ["train"] and len(rec) == 1
+    tr = calls[0][1].arguments
+    assert tr["vae_type"] == "reg_notMIWAE1" and tr["obs_dim"] == 6 and tr["p_missingness"] == 50
+    assert tr["not_miwae_type"] == "changed" and tr["train_k"] == line["train_k"]["default"]
+    ev = rec[0].arguments
+    assert ev["data_test"].shape == (30, 6) and ev["mask_test"].dtype.is_floating_point
+    assert ev["valid_k"] == line["valid_k"]["default"]
+
+
 def test_mirror_signatures_equal_reference_signatures():
     sys.path.insert(0, REF)
     import types
@@ -88,6 +115,15 @@ def test_mirror_signatures_equal_reference_signatures():
     assert names(evaluate.R_lindley_chain) == names(RE.R_lindley_chain)
     assert names(loaders.model_loader) == names(RL.model_loader)
     assert names(loaders.data_loader) == names(RL.data_loader)
+    assert names(loaders.data_loader_mnar) == names(RL.data_loader_mnar)
+    assert names(evaluate.eval_vae_mnar) == names(RE.eval_vae_mnar)
+    for cls in ("REG_notMIWAE_v2", "notMIWAE_myversion"):
+        ours, ref = getattr(VAE, cls), getattr(RV, cls)
+        assert names(ours.__init__) == names(ref.__init__), cls
+        for meth in ("encoder", "decoder", "forward", "loss"):
+            assert names(getattr(ours, meth)) == names(getattr(ref, meth)), (cls, meth)
+        dd = lambda f: {k: v.default for k, v in inspect.signature(f).parameters.items()}
+        assert dd(ours.loss) == dd(ref.loss), cls
     for cls in ("Reg_VAE", "vanilla_VAE", "Reg_EDDI", "vanilla_EDDI"):
         ours, ref = getattr(VAE, cls), getattr(RV, cls)
         assert names(ours.__init__) == names(ref.__init__), cls

@@ -16,31 +16,9 @@
 #include <cuda_pipeline.h>
 
 #include "pcvae_internal.cuh"
+#include "pcvae_reward.cuh"
 
 namespace pcvae {
-
-constexpr int BASEW = 40;      // per base: mean[10], logvar[10], 1/std[10], 1/var[10]
-constexpr int CANDP = 128;     // candidate list pitch (bytes)
-constexpr int NPAIR = TM_REWARD / 2;
-
-struct RewardArgs {
-    Layout L;
-    int N, M, mask_kind;
-    const float* theta;
-    const float* x;
-    const void* mask;
-    const float* im;
-    long im_ss;
-    float* R;
-    float* base_in;   // [N][INW]   h0 pre-activation (MLP, INW=100) or agg0 (PNP, INW=K4)
-    float* base0;     // [N][40]
-    float* baseT;     // [N][M][40]
-    int* cnt;         // [N]
-    int* off;         // [N+1]
-    uint8_t* cand;    // [N][CANDP]
-    int* pairs;       // [N*(D-1)]  n*128+u
-    const float* ac;  // PNP tables
-};
 
 __device__ __forceinline__ void write_base(const float* o_s, int P, float* __restrict__ dst, long stride,
                                            int row0, int N, int TM, int tid) {
@@ -396,7 +374,15 @@ static WsPlan plan_ws(const Layout& L, int N, int M) {
 
 using namespace pcvae;
 
+static int g_reward_tc = 0;
+
 extern "C" {
+
+int pcvae_set_reward_tensor_cores(int enable) {
+    const int prev = g_reward_tc;
+    g_reward_tc = enable ? 1 : 0;
+    return prev;
+}
 
 size_t pcvae_reward_workspace_bytes(const pcvae_model* m, int rows, int samples) {
     Layout L;
@@ -443,6 +429,7 @@ int pcvae_reward_chain(const pcvae_reward_params* p, void* stream) {
     k_scan<<<1, 1024, 0, st>>>(a.cnt, a.off, a.N);
     k_pairs<<<(a.N + 255) / 256, 256, 0, st>>>(a.cnt, a.off, a.cand, a.pairs, a.N);
     if (L.fam == PCVAE_FAMILY_PNP) k_reward_main<PCVAE_FAMILY_PNP><<<grid, NT, s2, st>>>(a);
+    else if (g_reward_tc) { if (int rc = reward_main_tc_launch(a, grid, st)) return rc; }
     else k_reward_main<PCVAE_FAMILY_MLP><<<grid, NT, s2, st>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(PCVAE_ECUDA, "reward_chain: main launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;

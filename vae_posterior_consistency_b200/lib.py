@@ -26,7 +26,7 @@ SYMBOLS = [
     "pcvae_loss_terms", "pcvae_grid_ctas", "pcvae_reduce_sums", "pcvae_reduce_grads", "pcvae_adam_step",
     "pcvae_reward_workspace_bytes", "pcvae_reward_chain", "pcvae_ffma_probe", "pcvae_gather_rows",
     "pcvae_draw_submask", "pcvae_draw_normal", "pcvae_dense_fwd", "pcvae_dense_bwd", "pcvae_mnar_sample_z",
-    "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss",
+    "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss", "pcvae_set_reward_tensor_cores",
 ]
 
 
