@@ -461,7 +461,8 @@ def run_ours(args):
             "e2e": {"value": triples / (re2e_ms * 1e-3), "unit": "triples/s",
                     "h2d_bytes_per_step": int(hxr.numel() * 4 + hmr.numel() * 4 + him.numel() * 4),
                     "d2h_bytes_per_step": int(hR.numel() * 4)},
-            "roofline": {"bound": "fp32_ffma", "kernel": "k_reward_main+k_reward_prep (whole pcvae_reward_chain call)",
+            "roofline": {"bound": "fp32_ffma", "kernel": "k_reward_main_tc (tcgen05 3xTF32) + k_reward_prep (whole pcvae_reward_chain call); "
+                                                        "fraction is algorithmic fp32 FLOP over the FP32 FFMA peak, so it can exceed 1",
                          "achieved": triples / world * FLOP_REWARD_TRIPLE / (r_ms * 1e-3) / 1e12,
                          "peak": ffma_tflops, "unit": "TFLOP/s",
                          "frac": triples / world * FLOP_REWARD_TRIPLE / (r_ms * 1e-3) / 1e12 / ffma_tflops,

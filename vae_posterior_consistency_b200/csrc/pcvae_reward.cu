@@ -374,7 +374,7 @@ static WsPlan plan_ws(const Layout& L, int N, int M) {
 
 using namespace pcvae;
 
-static int g_reward_tc = 0;
+static int g_reward_tc = 1;   // tcgen05 path is the default for the MLP family
 
 extern "C" {
 
