@@ -8,18 +8,21 @@
 //   layer 2:  D2[128 x 64]  = A2[128 x 104] * B2[64 x 104]^T     (100 inputs + bias column, 50 -> 64 outputs)
 //   layer 3:  D3[128 x 32]  = A3[128 x 56]  * B3[32 x 56]^T      ( 50 inputs + bias column, 20 -> 32 outputs)
 //
-// with `tcgen05.mma.cta_group::1.kind::tf32` issued by one thread, operands in shared memory in
-// the canonical K-major no-swizzle layout (8-row x 16-byte core matrices), accumulators in TMEM,
-// read back with `tcgen05.ld.32x32b`.  FP32 accuracy is kept by the 3xTF32 split
+// with `tcgen05.mma.cta_group::1.kind::tf32` issued by one thread.  ALL activations live in TMEM
+// (row = TMEM lane, feature = TMEM column): the A operands are read from TMEM, the accumulators are
+// written to TMEM, ReLU(D2) is written back in place as the next A operand (`tcgen05.ld` /
+// `tcgen05.st`); only the weights sit in shared memory (canonical K-major no-swizzle core-matrix
+// layout).  FP32 accuracy is kept by the 3xTF32 split
 //   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,   x_lo = x - trunc_tf32(x)
 // (the tensor core ignores the 13 low mantissa bits of a tf32 operand, so the raw fp32 word serves
 // as x_hi); the reward is a cancellation of two KLs and needs ~1e-6 relative activations.
 // Biases ride along as an extra K column (A[:,100] = 1, B2[n][100] = b2[n]; output column 50 of
 // layer 2 is forced to 1 to become the bias column of layer 3).
 //
-// Per sample m:  construct A2 (registers hold h0 / W1[:,u] of the thread's row for the whole tile)
-//   -> MMA2 (39 instr) -> epilogue 2 (TMEM -> ReLU -> hi/lo split -> A3) -> MMA3 (21 instr)
-//   -> epilogue 3 (TMEM -> KL vs base posteriors) -> in-order accumulate.
+// TMEM columns: [0,104) A2_hi  [104,208) A2_lo  [208,272) D2 -> A3_hi  [272,336) A3_lo  [336,368) D3.
+//
+// Software pipeline over the samples m (two mbarriers):
+//   construct(m) | MMA2(m) || KL-epilogue(m-1) | epilogue2(m) | MMA3(m) || construct(m+1) | ...
 #include <cuda_pipeline.h>
 
 #include "pcvae_reward.cuh"
@@ -28,14 +31,15 @@ namespace pcvae {
 namespace tc {
 
 constexpr int ROWS = 128;                 // UMMA M
-constexpr int K2 = 104, C2 = K2 / 4;      // layer-2 reduction (100 + bias + pad), 16-byte chunks
+constexpr int K2 = 104;                   // layer-2 reduction (100 + bias + pad)
+constexpr int C2 = K2 / 4;                // 16-byte K chunks of B2
 constexpr int N2 = 64;                    // layer-2 outputs (50 + ones column + pad)
 constexpr int K3 = 56, C3 = K3 / 4;       // layer-3 reduction (50 + bias + pad)
-constexpr int C3W = N2 / 4;               // chunks epilogue 2 writes (all 64 columns)
 constexpr int N3 = 32;                    // layer-3 outputs (20 + pad)
-constexpr int TMEM_COLS = 128;
-constexpr int A_CHUNK = ROWS * 4;         // floats per K-chunk of an A operand
-constexpr int MAXCH = (C2 + 3) / 4;       // K-chunks per thread in the construct phase (7)
+constexpr int TMEM_COLS = 512;
+constexpr int COL_A2H = 0, COL_A2L = K2, COL_D2 = 2 * K2, COL_A3L = COL_D2 + N2, COL_D3 = COL_A3L + N2;
+constexpr int KG = K2 / 4;                // features per thread in the construct phase (26)
+constexpr int NBUF = 4;                   // prefetch ring for v / t / baseT
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,12 +59,33 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// A operand from TMEM ("TS" form)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc),
         "r"(accumulate));
 }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -105,24 +130,23 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
     extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = a.L.D;
-    float* A_hi = smem;                              // [C2][128][4]  (layer 3 reuses the first C3W chunks)
-    float* A_lo = A_hi + C2 * A_CHUNK;
-    float* B2_hi = A_lo + C2 * A_CHUNK;              // [C2][64][4]
+    float* B2_hi = smem;                             // [C2][64][4]
     float* B2_lo = B2_hi + C2 * N2 * 4;
     float* B3_hi = B2_lo + C2 * N2 * 4;              // [C3][32][4]
     float* B3_lo = B3_hi + C3 * N3 * 4;
     float* wT_s = B3_lo + C3 * N3 * 4;               // [K2]
     float* b0_s = wT_s + K2;                         // [40][64]
-    float* bT_s = b0_s + BASEW * NPAIR;              // [2][64][40]
-    float* v_s = bT_s + 2 * NPAIR * BASEW;           // [2][64]
-    float* t_s = v_s + 2 * NPAIR;                    // [2][64]
-    float* kl_s = t_s + 2 * NPAIR;                   // [128]
+    float* bT_s = b0_s + BASEW * NPAIR;              // [NBUF][64][40]
+    float* v_s = bT_s + NBUF * NPAIR * BASEW;        // [NBUF][64]
+    float* t_s = v_s + NBUF * NPAIR;                 // [NBUF][64]
+    float* kl_s = t_s + NBUF * NPAIR;                // [128]
     int* pn_s = reinterpret_cast<int*>(kl_s + ROWS); // [64]
     int* pu_s = pn_s + NPAIR;                        // [64]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(pu_s + NPAIR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint64_t* bar2 = reinterpret_cast<uint64_t*>(pu_s + NPAIR);
+    uint64_t* bar3 = bar2 + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar3 + 1);
 
-    // ---- one-time setup: weights (hi / lo, K-major core-matrix layout), barrier, TMEM ----
+    // ---- one-time setup: weights (hi / lo, K-major core-matrix layout), barriers, TMEM ----
     const float* th = a.theta;
     for (int i = tid; i < C2 * N2 * 4; i += NT) {
         const int c = i / (N2 * 4), n = (i >> 2) % N2, k = 4 * c + (i & 3);
@@ -143,7 +167,8 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
     }
     for (int k = tid; k < K2; k += NT) wT_s[k] = (k < H1) ? th[a.L.W1 + (long)k * D + (D - 1)] : 0.f;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar2)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar3)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -155,16 +180,18 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    uint32_t phase = 0;
+    uint32_t ph2 = 0, ph3 = 0;
 
     constexpr uint32_t IDESC2 = make_idesc(ROWS, N2), IDESC3 = make_idesc(ROWS, N3);
-    const uint32_t aHi = smem_u32(A_hi), aLo = smem_u32(A_lo);
     const uint32_t b2Hi = smem_u32(B2_hi), b2Lo = smem_u32(B2_lo), b3Hi = smem_u32(B3_hi), b3Lo = smem_u32(B3_lo);
-    constexpr uint32_t A_LBO = A_CHUNK * 4, SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16;
+    constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16;
 
-    const int row = tid & (ROWS - 1), kq = tid >> 7;     // construct: row of the tile, K-chunk phase
-    const int pi = row & (NPAIR - 1);
+    // thread -> (TMEM lane quarter q, column group cg): row r of the tile, features [KG*cg, KG*cg + KG)
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = 32 * q + lane, pi = row & (NPAIR - 1);
     const bool withT = row >= NPAIR;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    const int k0 = KG * cg;
 
     const int ptot = a.off[a.N];
     const int ntiles = (ptot + NPAIR - 1) / NPAIR;
@@ -177,39 +204,37 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
             pu_s[tid] = u;
         }
         __syncthreads();
-        auto prefetch = [&](int m, int buf) {
-            for (int c = tid; c < NPAIR * (BASEW / 4); c += NT) {
-                const int i = c / (BASEW / 4), q = c - i * (BASEW / 4);
-                __pipeline_memcpy_async(bT_s + (buf * NPAIR + i) * BASEW + 4 * q,
-                                        a.baseT + ((long)pn_s[i] * a.M + m) * BASEW + 4 * q, 16);
+        auto prefetch = [&](int m) {
+            if (m < a.M) {
+                const int buf = m % NBUF;
+                for (int c = tid; c < NPAIR * (BASEW / 4); c += NT) {
+                    const int i = c / (BASEW / 4), qq = c - i * (BASEW / 4);
+                    __pipeline_memcpy_async(bT_s + (buf * NPAIR + i) * BASEW + 4 * qq,
+                                            a.baseT + ((long)pn_s[i] * a.M + m) * BASEW + 4 * qq, 16);
+                }
+                if (tid < NPAIR) {
+                    const float* r = a.im + (long)m * a.im_ss + (long)pn_s[tid] * D;
+                    __pipeline_memcpy_async(v_s + buf * NPAIR + tid, r + pu_s[tid], 4);
+                    __pipeline_memcpy_async(t_s + buf * NPAIR + tid, r + (D - 1), 4);
+                }
             }
-            if (tid < NPAIR) {
-                const float* r = a.im + (long)m * a.im_ss + (long)pn_s[tid] * D;
-                __pipeline_memcpy_async(v_s + buf * NPAIR + tid, r + pu_s[tid], 4);
-                __pipeline_memcpy_async(t_s + buf * NPAIR + tid, r + (D - 1), 4);
-            }
-            __pipeline_commit();
+            __pipeline_commit();       // one group per call (possibly empty) keeps wait_prior counts uniform
         };
-        prefetch(0, 0);
-        // per-thread row state for the whole tile: h0[k] and W1[k][u] of this row's pair, k in the thread's chunks
-        float H0r[MAXCH][4], Ur[MAXCH][4];
+        prefetch(0);
+        prefetch(1);
+        // per-thread row state for the whole tile: h0[k] and W1[k][u] of this row's pair
+        float H0r[KG], Ur[KG];
         {
             const int n = pn_s[pi], u = pu_s[pi];
             const float* h0 = a.base_in + (long)n * H1;
 #pragma unroll
-            for (int j = 0; j < MAXCH; ++j) {
-                const int c = kq + 4 * j;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * c + e;
-                    float hv = 0.f, uv = 0.f;
-                    if (c < C2) {
-                        if (k < H1) { hv = h0[k]; uv = __ldg(th + a.L.W1 + (long)k * D + u); }
-                        else if (k == H1) hv = 1.0f;      // bias column
-                    }
-                    H0r[j][e] = hv;
-                    Ur[j][e] = uv;
-                }
+            for (int j = 0; j < KG; ++j) {
+                const int k = k0 + j;
+                float hv = 0.f, uv = 0.f;
+                if (k < H1) { hv = h0[k]; uv = __ldg(th + a.L.W1 + (long)k * D + u); }
+                else if (k == H1) hv = 1.0f;          // bias column
+                H0r[j] = hv;
+                Ur[j] = uv;
             }
         }
         for (int idx = tid; idx < BASEW * NPAIR; idx += NT) {
@@ -217,116 +242,125 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
             b0_s[idx] = a.base0[(long)pn_s[i] * BASEW + f];
         }
         float acc = 0.f;
-        __pipeline_wait_prior(0);
+
+        // A2(m) = relu(h0 + v w_u [+ t w_T]) -> TMEM as hi / lo tf32 operands
+        auto construct = [&](int m) {
+            const int buf = m % NBUF;
+            const float v = v_s[buf * NPAIR + pi], t = withT ? t_s[buf * NPAIR + pi] : 0.f;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt) {
+                        const float h = fmaxf(fmaf(t, wT_s[k0 + j0 + j], fmaf(v, Ur[j0 + j], H0r[j0 + j])), 0.f);
+                        hi[j] = h;
+                        lo[j] = tf32_lo(h);
+                    }
+                const uint32_t ah = lane_addr + COL_A2H + k0 + j0, al = lane_addr + COL_A2L + k0 + j0;
+                if (part == 0) { tmem_st16(ah, hi); tmem_st16(al, lo); }
+                else if (part == 1) { tmem_st8(ah, hi); tmem_st8(al, lo); }
+                else { tmem_st2(ah, hi); tmem_st2(al, lo); }
+            }
+            tmem_st_wait();
+        };
+        // KL of sample m against the base posteriors (warps 0-3, one tile row per thread)
+        auto kl_epilogue = [&](int m) {
+            const int buf = m % NBUF;
+            mbar_wait(bar3, ph3);
+            tc_fence_after();
+            float o[20];
+            tmem_ld16(lane_addr + COL_D3, o);
+            tmem_ld4(lane_addr + COL_D3 + 16, o + 16);
+            float s = 0.f;
+            if (!withT) {
+#pragma unroll
+                for (int l = 0; l < LAT; ++l) {
+                    const float dm = o[l] - b0_s[l * NPAIR + pi];
+                    s += (((dm * dm) * b0_s[(2 * LAT + l) * NPAIR + pi] + expf(o[LAT + l]) * b0_s[(3 * LAT + l) * NPAIR + pi] - 1.0f) -
+                          o[LAT + l]) + b0_s[(LAT + l) * NPAIR + pi];
+                }
+            } else {
+                const float* bt = bT_s + (buf * NPAIR + pi) * BASEW;
+#pragma unroll
+                for (int l = 0; l < LAT; ++l) {
+                    const float dm = o[l] - bt[l];
+                    s += (((dm * dm) * bt[2 * LAT + l] + expf(o[LAT + l]) * bt[3 * LAT + l] - 1.0f) - o[LAT + l]) + bt[LAT + l];
+                }
+            }
+            kl_s[row] = 0.5f * s;
+            tc_fence_before();
+        };
+
+        __pipeline_wait_prior(1);          // sample 0 landed
+        __syncthreads();
+        construct(0);
+        tc_fence_before();
         __syncthreads();
 
         for (int m = 0; m < a.M; ++m) {
-            const int buf = m & 1;
-            if (m + 1 < a.M) prefetch(m + 1, buf ^ 1);
-            // ---- construct A2 = relu(h0 + v w_u [+ t w_T]) as hi / lo tf32 operands ----
-            {
-                const float v = v_s[buf * NPAIR + pi], t = withT ? t_s[buf * NPAIR + pi] : 0.f;
-#pragma unroll
-                for (int j = 0; j < MAXCH; ++j) {
-                    const int c = kq + 4 * j;
-                    if (c < C2) {
-                        const float4 wt = *reinterpret_cast<const float4*>(wT_s + 4 * c);
-                        float4 hi, lo;
-                        hi.x = fmaxf(fmaf(t, wt.x, fmaf(v, Ur[j][0], H0r[j][0])), 0.f);
-                        hi.y = fmaxf(fmaf(t, wt.y, fmaf(v, Ur[j][1], H0r[j][1])), 0.f);
-                        hi.z = fmaxf(fmaf(t, wt.z, fmaf(v, Ur[j][2], H0r[j][2])), 0.f);
-                        hi.w = fmaxf(fmaf(t, wt.w, fmaf(v, Ur[j][3], H0r[j][3])), 0.f);
-                        lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
-                        *reinterpret_cast<float4*>(A_hi + c * A_CHUNK + row * 4) = hi;
-                        *reinterpret_cast<float4*>(A_lo + c * A_CHUNK + row * 4) = lo;
-                    }
-                }
-            }
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            // ---- layer 2 on the tensor cores ----
+            prefetch(m + 2);
+            // ---- layer 2 on the tensor cores (A from TMEM) ----
             if (tid == 0) {
                 tc_fence_after();
 #pragma unroll 1
                 for (int ks = 0; ks < K2 / 8; ++ks) {
-                    const uint64_t dAh = make_desc(aHi + ks * 2 * A_LBO, A_LBO, SBO), dAl = make_desc(aLo + ks * 2 * A_LBO, A_LBO, SBO);
                     const uint64_t dBh = make_desc(b2Hi + ks * 2 * B2_LBO, B2_LBO, SBO), dBl = make_desc(b2Lo + ks * 2 * B2_LBO, B2_LBO, SBO);
-                    mma_tf32(tmem, dAl, dBh, IDESC2, ks > 0);
-                    mma_tf32(tmem, dAh, dBl, IDESC2, 1);
-                    mma_tf32(tmem, dAh, dBh, IDESC2, 1);
+                    mma_tf32_ts(tmem + COL_D2, tmem + COL_A2L + 8 * ks, dBh, IDESC2, ks > 0);
+                    mma_tf32_ts(tmem + COL_D2, tmem + COL_A2H + 8 * ks, dBl, IDESC2, 1);
+                    mma_tf32_ts(tmem + COL_D2, tmem + COL_A2H + 8 * ks, dBh, IDESC2, 1);
                 }
-                mma_commit(bar);
+                mma_commit(bar2);
             }
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            // ---- overlapped with MMA2(m): KL epilogue of the previous sample ----
+            if (m > 0 && cg == 0) kl_epilogue(m - 1);
+            if (m > 0) ph3 ^= 1;
+            mbar_wait(bar2, ph2);
+            ph2 ^= 1;
             tc_fence_after();
-            // ---- epilogue 2: TMEM -> ReLU -> hi/lo -> A3 (rows = TMEM lanes; 16 columns per thread) ----
+            // ---- epilogue 2: D2 -> ReLU -> hi (in place) / lo: the A operand of layer 3 ----
             {
-                const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;
-                float d[16];
-                tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * cg), d);
+                float d[16], lo[16];
+                tmem_ld16(lane_addr + COL_D2 + 16 * cg, d);
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int c = 4 * cg + jj;
-                    float4 hi, lo;
-                    hi.x = fmaxf(d[4 * jj + 0], 0.f); hi.y = fmaxf(d[4 * jj + 1], 0.f);
-                    hi.z = fmaxf(d[4 * jj + 2], 0.f); hi.w = fmaxf(d[4 * jj + 3], 0.f);
-                    lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
-                    *reinterpret_cast<float4*>(A_hi + c * A_CHUNK + r * 4) = hi;
-                    *reinterpret_cast<float4*>(A_lo + c * A_CHUNK + r * 4) = lo;
-                }
+                for (int j = 0; j < 16; ++j) { d[j] = fmaxf(d[j], 0.f); lo[j] = tf32_lo(d[j]); }
+                tmem_st16(lane_addr + COL_D2 + 16 * cg, d);
+                tmem_st16(lane_addr + COL_A3L + 16 * cg, lo);
+                tmem_st_wait();
             }
-            fence_async_smem();
             tc_fence_before();
             __syncthreads();
+            if (m > 0 && tid < NPAIR) { acc += kl_s[tid]; acc -= kl_s[NPAIR + tid]; }   // approx_KL += KL_I; -= KL_II (sample m-1)
             // ---- layer 3 on the tensor cores ----
             if (tid == 0) {
                 tc_fence_after();
 #pragma unroll 1
                 for (int ks = 0; ks < K3 / 8; ++ks) {
-                    const uint64_t dAh = make_desc(aHi + ks * 2 * A_LBO, A_LBO, SBO), dAl = make_desc(aLo + ks * 2 * A_LBO, A_LBO, SBO);
                     const uint64_t dBh = make_desc(b3Hi + ks * 2 * B3_LBO, B3_LBO, SBO), dBl = make_desc(b3Lo + ks * 2 * B3_LBO, B3_LBO, SBO);
-                    mma_tf32(tmem + N2, dAl, dBh, IDESC3, ks > 0);
-                    mma_tf32(tmem + N2, dAh, dBl, IDESC3, 1);
-                    mma_tf32(tmem + N2, dAh, dBh, IDESC3, 1);
+                    mma_tf32_ts(tmem + COL_D3, tmem + COL_A3L + 8 * ks, dBh, IDESC3, ks > 0);
+                    mma_tf32_ts(tmem + COL_D3, tmem + COL_D2 + 8 * ks, dBl, IDESC3, 1);
+                    mma_tf32_ts(tmem + COL_D3, tmem + COL_D2 + 8 * ks, dBh, IDESC3, 1);
                 }
-                mma_commit(bar);
+                mma_commit(bar3);
             }
-            // ---- epilogue 3 (warps 0-3): TMEM -> KL against the base posterior of the row's variant ----
-            if (warp < 4) {
-                mbar_wait(bar, phase);
-                tc_fence_after();
-                const int r = 32 * warp + lane, i = r & (NPAIR - 1);
-                float o[20];
-                tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)N2, o);
-                tmem_ld4(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(N2 + 16), o + 16);
-                float s = 0.f;
-                if (r < NPAIR) {
-#pragma unroll
-                    for (int l = 0; l < LAT; ++l) {
-                        const float dm = o[l] - b0_s[l * NPAIR + i];
-                        s += (((dm * dm) * b0_s[(2 * LAT + l) * NPAIR + i] + expf(o[LAT + l]) * b0_s[(3 * LAT + l) * NPAIR + i] - 1.0f) -
-                              o[LAT + l]) + b0_s[(LAT + l) * NPAIR + i];
-                    }
-                } else {
-                    const float* bt = bT_s + (buf * NPAIR + i) * BASEW;
-#pragma unroll
-                    for (int l = 0; l < LAT; ++l) {
-                        const float dm = o[l] - bt[l];
-                        s += (((dm * dm) * bt[2 * LAT + l] + expf(o[LAT + l]) * bt[3 * LAT + l] - 1.0f) - o[LAT + l]) + bt[LAT + l];
-                    }
-                }
-                kl_s[r] = 0.5f * s;
-                tc_fence_before();
+            // ---- overlapped with MMA3(m): construct the next sample's A2 ----
+            if (m + 1 < a.M) {
+                __pipeline_wait_prior(1);  // sample m+1 landed (the group of m+2 may still be in flight)
+                __syncthreads();
+                construct(m + 1);
             }
-            phase ^= 1;
-            __syncthreads();
-            if (tid < NPAIR) { acc += kl_s[tid]; acc -= kl_s[NPAIR + tid]; }     // approx_KL += KL_I; approx_KL -= KL_II
-            __pipeline_wait_prior(0);
+            tc_fence_before();
             __syncthreads();
         }
-        if (tid < NPAIR && p0 + tid < ptot) a.R[(long)pn_s[tid] * (D - 1) + pu_s[tid]] = acc / (float)a.M;   // evaluate.py:540
+        if (cg == 0) kl_epilogue(a.M - 1);
+        ph3 ^= 1;
+        __syncthreads();
+        if (tid < NPAIR) {
+            acc += kl_s[tid]; acc -= kl_s[NPAIR + tid];
+            if (p0 + tid < ptot) a.R[(long)pn_s[tid] * (D - 1) + pu_s[tid]] = acc / (float)a.M;   // evaluate.py:540
+        }
+        __pipeline_wait_prior(0);
         __syncthreads();
     }
     tc_fence_before();
@@ -338,8 +372,8 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
 }
 
 static size_t smem_bytes() {
-    size_t f = 2 * (size_t)C2 * A_CHUNK + 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + K2 + BASEW * NPAIR +
-               2 * NPAIR * BASEW + 4 * NPAIR + ROWS + 2 * NPAIR + 8;
+    size_t f = 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + K2 + BASEW * NPAIR + NBUF * NPAIR * BASEW +
+               2 * NBUF * NPAIR + ROWS + 2 * NPAIR + 8;
     return f * sizeof(float) + 128;
 }
 
