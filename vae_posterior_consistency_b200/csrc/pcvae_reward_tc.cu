@@ -8,21 +8,24 @@
 //   layer 2:  D2[128 x 64]  = A2[128 x 104] * B2[64 x 104]^T     (100 inputs + bias column, 50 -> 64 outputs)
 //   layer 3:  D3[128 x 32]  = A3[128 x 56]  * B3[32 x 56]^T      ( 50 inputs + bias column, 20 -> 32 outputs)
 //
-// with `tcgen05.mma.cta_group::1.kind::tf32` issued by one thread.  ALL activations live in TMEM
-// (row = TMEM lane, feature = TMEM column): the A operands are read from TMEM, the accumulators are
-// written to TMEM, ReLU(D2) is written back in place as the next A operand (`tcgen05.ld` /
-// `tcgen05.st`); only the weights sit in shared memory (canonical K-major no-swizzle core-matrix
-// layout).  FP32 accuracy is kept by the 3xTF32 split
+// with `tcgen05.mma.cta_group::1.kind::tf32` issued by one thread.  The layer-2 operand A2 lives in
+// TMEM, double-buffered (row = TMEM lane, feature = TMEM column; written with `tcgen05.st`, read by
+// the MMA in its A-from-TMEM form), accumulators are in TMEM (`tcgen05.ld`), the layer-3 operand
+// ReLU(D2) and the weights sit in shared memory in the canonical K-major no-swizzle core-matrix
+// layout.  FP32 accuracy is kept by the 3xTF32 split
 //   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,   x_lo = x - trunc_tf32(x)
 // (the tensor core ignores the 13 low mantissa bits of a tf32 operand, so the raw fp32 word serves
 // as x_hi); the reward is a cancellation of two KLs and needs ~1e-6 relative activations.
 // Biases ride along as an extra K column (A[:,100] = 1, B2[n][100] = b2[n]; output column 50 of
 // layer 2 is forced to 1 to become the bias column of layer 3).
 //
-// TMEM columns: [0,104) A2_hi  [104,208) A2_lo  [208,272) D2 -> A3_hi  [272,336) A3_lo  [336,368) D3.
+// TMEM columns (all 512): buffer b of A2 at 208*b: [0,104) hi, [104,208) lo;  D2 [416,480);  D3 [480,512).
 //
-// Software pipeline over the samples m (two mbarriers):
-//   construct(m) | MMA2(m) || KL-epilogue(m-1) | epilogue2(m) | MMA3(m) || construct(m+1) | ...
+// Software pipeline over the samples m (two mbarriers): after epilogue2(m) one thread issues MMA3(m) and
+// MMA2(m+1) back to back, so the tensor pipe runs while the CUDA cores do the KL epilogue of sample m
+// and construct the operand of sample m+2:
+//   tensor pipe :  MMA2(m) | MMA3(m) MMA2(m+1) | MMA3(m+1) MMA2(m+2) | ...
+//   CUDA cores  :  ... epilogue2(m) | KL(m) construct(m+2) | epilogue2(m+1) | KL(m+1) construct(m+3) | ...
 #include <cuda_pipeline.h>
 
 #include "pcvae_reward.cuh"
@@ -37,9 +40,13 @@ constexpr int N2 = 64;                    // layer-2 outputs (50 + ones column +
 constexpr int K3 = 56, C3 = K3 / 4;       // layer-3 reduction (50 + bias + pad)
 constexpr int N3 = 32;                    // layer-3 outputs (20 + pad)
 constexpr int TMEM_COLS = 512;
-constexpr int COL_A2H = 0, COL_A2L = K2, COL_D2 = 2 * K2, COL_A3L = COL_D2 + N2, COL_D3 = COL_A3L + N2;
+constexpr int A2_COLS = 2 * K2;           // hi + lo of one A2 buffer
+constexpr int COL_D2 = 2 * A2_COLS, COL_D3 = COL_D2 + N2;
+constexpr int A_CHUNK = ROWS * 4;         // floats per 16-byte K chunk of the layer-3 operand in shared memory
+constexpr int C3W = N2 / 4;               // chunks epilogue 2 writes (all 64 columns of D2)
 constexpr int KG = K2 / 4;                // features per thread in the construct phase (26)
 constexpr int NBUF = 4;                   // prefetch ring for v / t / baseT
+constexpr int ISSUER = 128;               // MMA-issuing thread: lane 0 of warp 4 (warps 0-3 carry the KL epilogue)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -57,6 +64,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
 // instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
+        "r"(accumulate));
 }
 
 // A operand from TMEM ("TS" form)
@@ -134,7 +148,9 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
     float* B2_lo = B2_hi + C2 * N2 * 4;
     float* B3_hi = B2_lo + C2 * N2 * 4;              // [C3][32][4]
     float* B3_lo = B3_hi + C3 * N3 * 4;
-    float* wT_s = B3_lo + C3 * N3 * 4;               // [K2]
+    float* A3_hi = B3_lo + C3 * N3 * 4;              // [C3W][128][4]
+    float* A3_lo = A3_hi + C3W * A_CHUNK;
+    float* wT_s = A3_lo + C3W * A_CHUNK;             // [K2]
     float* b0_s = wT_s + K2;                         // [40][64]
     float* bT_s = b0_s + BASEW * NPAIR;              // [NBUF][64][40]
     float* v_s = bT_s + NBUF * NPAIR * BASEW;        // [NBUF][64]
@@ -183,8 +199,32 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
     uint32_t ph2 = 0, ph3 = 0;
 
     constexpr uint32_t IDESC2 = make_idesc(ROWS, N2), IDESC3 = make_idesc(ROWS, N3);
-    const uint32_t b2Hi = smem_u32(B2_hi), b2Lo = smem_u32(B2_lo), b3Hi = smem_u32(B3_hi), b3Lo = smem_u32(B3_lo);
-    constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16;
+    constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16, A3_LBO = A_CHUNK * 4;
+    // descriptors of k-step 0; a k-step (8 tf32 = two 16-byte chunks) advances the 16-byte-unit address field
+    const uint64_t dB2h = make_desc(smem_u32(B2_hi), B2_LBO, SBO), dB2l = make_desc(smem_u32(B2_lo), B2_LBO, SBO);
+    const uint64_t dB3h = make_desc(smem_u32(B3_hi), B3_LBO, SBO), dB3l = make_desc(smem_u32(B3_lo), B3_LBO, SBO);
+    const uint64_t dA3h = make_desc(smem_u32(A3_hi), A3_LBO, SBO), dA3l = make_desc(smem_u32(A3_lo), A3_LBO, SBO);
+    constexpr uint64_t B2_STEP = (2 * B2_LBO) >> 4, B3_STEP = (2 * B3_LBO) >> 4, A3_STEP = (2 * A3_LBO) >> 4;
+
+    auto issue_mma2 = [&](int buf) {      // D2 = A2[buf] * B2^T, 3xTF32 (single thread)
+        const uint32_t ah = tmem + A2_COLS * buf, al = ah + K2;
+#pragma unroll
+        for (int ks = 0; ks < K2 / 8; ++ks) {
+            mma_tf32_ts(tmem + COL_D2, al + 8 * ks, dB2h + ks * B2_STEP, IDESC2, ks > 0);
+            mma_tf32_ts(tmem + COL_D2, ah + 8 * ks, dB2l + ks * B2_STEP, IDESC2, 1);
+            mma_tf32_ts(tmem + COL_D2, ah + 8 * ks, dB2h + ks * B2_STEP, IDESC2, 1);
+        }
+        mma_commit(bar2);
+    };
+    auto issue_mma3 = [&]() {             // D3 = A3 * B3^T, 3xTF32 (single thread)
+#pragma unroll
+        for (int ks = 0; ks < K3 / 8; ++ks) {
+            mma_tf32_ss(tmem + COL_D3, dA3l + ks * A3_STEP, dB3h + ks * B3_STEP, IDESC3, ks > 0);
+            mma_tf32_ss(tmem + COL_D3, dA3h + ks * A3_STEP, dB3l + ks * B3_STEP, IDESC3, 1);
+            mma_tf32_ss(tmem + COL_D3, dA3h + ks * A3_STEP, dB3h + ks * B3_STEP, IDESC3, 1);
+        }
+        mma_commit(bar3);
+    };
 
     // thread -> (TMEM lane quarter q, column group cg): row r of the tile, features [KG*cg, KG*cg + KG)
     const int q = warp & 3, cg = warp >> 2;
@@ -222,6 +262,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
         };
         prefetch(0);
         prefetch(1);
+        prefetch(2);
         // per-thread row state for the whole tile: h0[k] and W1[k][u] of this row's pair
         float H0r[KG], Ur[KG];
         {
@@ -243,10 +284,11 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
         }
         float acc = 0.f;
 
-        // A2(m) = relu(h0 + v w_u [+ t w_T]) -> TMEM as hi / lo tf32 operands
+        // A2(m) = relu(h0 + v w_u [+ t w_T]) -> TMEM buffer m&1 as hi / lo tf32 operands
         auto construct = [&](int m) {
             const int buf = m % NBUF;
             const float v = v_s[buf * NPAIR + pi], t = withT ? t_s[buf * NPAIR + pi] : 0.f;
+            const uint32_t ah0 = lane_addr + A2_COLS * (m & 1) + k0, al0 = ah0 + K2;
             float hi[16], lo[16];
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
@@ -258,10 +300,9 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
                         hi[j] = h;
                         lo[j] = tf32_lo(h);
                     }
-                const uint32_t ah = lane_addr + COL_A2H + k0 + j0, al = lane_addr + COL_A2L + k0 + j0;
-                if (part == 0) { tmem_st16(ah, hi); tmem_st16(al, lo); }
-                else if (part == 1) { tmem_st8(ah, hi); tmem_st8(al, lo); }
-                else { tmem_st2(ah, hi); tmem_st2(al, lo); }
+                if (part == 0) { tmem_st16(ah0 + j0, hi); tmem_st16(al0 + j0, lo); }
+                else if (part == 1) { tmem_st8(ah0 + j0, hi); tmem_st8(al0 + j0, lo); }
+                else { tmem_st2(ah0 + j0, hi); tmem_st2(al0 + j0, lo); }
             }
             tmem_st_wait();
         };
@@ -293,73 +334,59 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
             tc_fence_before();
         };
 
-        __pipeline_wait_prior(1);          // sample 0 landed
+        // ---- prologue: A2(0), start MMA2(0), A2(1) ----
+        __pipeline_wait_prior(2);          // sample 0 landed
         __syncthreads();
         construct(0);
         tc_fence_before();
         __syncthreads();
+        if (tid == ISSUER) { tc_fence_after(); issue_mma2(0); }
+        if (a.M > 1) {
+            __pipeline_wait_prior(1);      // sample 1 landed
+            __syncthreads();
+            construct(1);
+        }
 
         for (int m = 0; m < a.M; ++m) {
-            prefetch(m + 2);
-            // ---- layer 2 on the tensor cores (A from TMEM) ----
-            if (tid == 0) {
-                tc_fence_after();
-#pragma unroll 1
-                for (int ks = 0; ks < K2 / 8; ++ks) {
-                    const uint64_t dBh = make_desc(b2Hi + ks * 2 * B2_LBO, B2_LBO, SBO), dBl = make_desc(b2Lo + ks * 2 * B2_LBO, B2_LBO, SBO);
-                    mma_tf32_ts(tmem + COL_D2, tmem + COL_A2L + 8 * ks, dBh, IDESC2, ks > 0);
-                    mma_tf32_ts(tmem + COL_D2, tmem + COL_A2H + 8 * ks, dBl, IDESC2, 1);
-                    mma_tf32_ts(tmem + COL_D2, tmem + COL_A2H + 8 * ks, dBh, IDESC2, 1);
-                }
-                mma_commit(bar2);
-            }
-            // ---- overlapped with MMA2(m): KL epilogue of the previous sample ----
-            if (m > 0 && cg == 0) kl_epilogue(m - 1);
-            if (m > 0) ph3 ^= 1;
-            mbar_wait(bar2, ph2);
+            prefetch(m + 3);
+            mbar_wait(bar2, ph2);          // MMA2(m) (and everything issued before it) complete
             ph2 ^= 1;
             tc_fence_after();
-            // ---- epilogue 2: D2 -> ReLU -> hi (in place) / lo: the A operand of layer 3 ----
+            // ---- epilogue 2: D2 -> ReLU -> hi / lo operand of layer 3 in shared memory ----
             {
-                float d[16], lo[16];
+                float d[16];
                 tmem_ld16(lane_addr + COL_D2 + 16 * cg, d);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { d[j] = fmaxf(d[j], 0.f); lo[j] = tf32_lo(d[j]); }
-                tmem_st16(lane_addr + COL_D2 + 16 * cg, d);
-                tmem_st16(lane_addr + COL_A3L + 16 * cg, lo);
-                tmem_st_wait();
-            }
-            tc_fence_before();
-            __syncthreads();
-            if (m > 0 && tid < NPAIR) { acc += kl_s[tid]; acc -= kl_s[NPAIR + tid]; }   // approx_KL += KL_I; -= KL_II (sample m-1)
-            // ---- layer 3 on the tensor cores ----
-            if (tid == 0) {
-                tc_fence_after();
-#pragma unroll 1
-                for (int ks = 0; ks < K3 / 8; ++ks) {
-                    const uint64_t dBh = make_desc(b3Hi + ks * 2 * B3_LBO, B3_LBO, SBO), dBl = make_desc(b3Lo + ks * 2 * B3_LBO, B3_LBO, SBO);
-                    mma_tf32_ts(tmem + COL_D3, tmem + COL_A3L + 8 * ks, dBh, IDESC3, ks > 0);
-                    mma_tf32_ts(tmem + COL_D3, tmem + COL_D2 + 8 * ks, dBl, IDESC3, 1);
-                    mma_tf32_ts(tmem + COL_D3, tmem + COL_D2 + 8 * ks, dBh, IDESC3, 1);
+                for (int jj = 0; jj < 4; ++jj) {
+                    float4 hi, lo;
+                    hi.x = fmaxf(d[4 * jj + 0], 0.f); hi.y = fmaxf(d[4 * jj + 1], 0.f);
+                    hi.z = fmaxf(d[4 * jj + 2], 0.f); hi.w = fmaxf(d[4 * jj + 3], 0.f);
+                    lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
+                    *reinterpret_cast<float4*>(A3_hi + (4 * cg + jj) * A_CHUNK + row * 4) = hi;
+                    *reinterpret_cast<float4*>(A3_lo + (4 * cg + jj) * A_CHUNK + row * 4) = lo;
                 }
-                mma_commit(bar3);
             }
-            // ---- overlapped with MMA3(m): construct the next sample's A2 ----
-            if (m + 1 < a.M) {
-                __pipeline_wait_prior(1);  // sample m+1 landed (the group of m+2 may still be in flight)
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();               // A3(m) and A2(m+1) are complete and visible
+            if (tid == ISSUER) {
+                tc_fence_after();
+                issue_mma3();
+                if (m + 1 < a.M) issue_mma2((m + 1) & 1);
+            }
+            // ---- CUDA cores, overlapped with the tensor pipe: KL of sample m, operand of sample m+2 ----
+            if (cg == 0) kl_epilogue(m);
+            ph3 ^= 1;
+            if (m + 2 < a.M) {
+                __pipeline_wait_prior(1);  // sample m+2 landed
                 __syncthreads();
-                construct(m + 1);
+                construct(m + 2);
             }
             tc_fence_before();
             __syncthreads();
+            if (tid < NPAIR) { acc += kl_s[tid]; acc -= kl_s[NPAIR + tid]; }   // approx_KL += KL_I; approx_KL -= KL_II
         }
-        if (cg == 0) kl_epilogue(a.M - 1);
-        ph3 ^= 1;
-        __syncthreads();
-        if (tid < NPAIR) {
-            acc += kl_s[tid]; acc -= kl_s[NPAIR + tid];
-            if (p0 + tid < ptot) a.R[(long)pn_s[tid] * (D - 1) + pu_s[tid]] = acc / (float)a.M;   // evaluate.py:540
-        }
+        if (tid < NPAIR && p0 + tid < ptot) a.R[(long)pn_s[tid] * (D - 1) + pu_s[tid]] = acc / (float)a.M;   // evaluate.py:540
         __pipeline_wait_prior(0);
         __syncthreads();
     }
@@ -372,8 +399,8 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
 }
 
 static size_t smem_bytes() {
-    size_t f = 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + K2 + BASEW * NPAIR + NBUF * NPAIR * BASEW +
-               2 * NBUF * NPAIR + ROWS + 2 * NPAIR + 8;
+    size_t f = 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + 2 * (size_t)C3W * A_CHUNK + K2 + BASEW * NPAIR +
+               NBUF * NPAIR * BASEW + 2 * NBUF * NPAIR + ROWS + 2 * NPAIR + 8;
     return f * sizeof(float) + 128;
 }
 
