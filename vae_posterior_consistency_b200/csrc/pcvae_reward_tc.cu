@@ -45,8 +45,8 @@ constexpr int COL_D2 = 2 * A2_COLS, COL_D3 = COL_D2 + N2;
 constexpr int A_CHUNK = ROWS * 4;         // floats per 16-byte K chunk of the layer-3 operand in shared memory
 constexpr int C3W = N2 / 4;               // chunks epilogue 2 writes (all 64 columns of D2)
 constexpr int KG = K2 / 4;                // features per thread in the construct phase (26)
-constexpr int NBUF = 4;                   // prefetch ring for v / t / baseT
-constexpr int ISSUER = 128;               // MMA-issuing thread: lane 0 of warp 4 (warps 0-3 carry the KL epilogue)
+constexpr int NBUF = 5;                   // prefetch ring for v / t / baseT
+constexpr int ISSUER_WARP = 4;             // MMA-issuing warp (one elected lane); warps 0-3 carry the KL epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -116,6 +116,13 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     return false;   // bounded: never hang the GPU; the caller's results will be wrong and tests catch it
 }
 
+// one lane of a converged warp (the predicate ptxas recognises for single-thread tcgen05 issue)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -155,8 +162,8 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
     float* bT_s = b0_s + BASEW * NPAIR;              // [NBUF][64][40]
     float* v_s = bT_s + NBUF * NPAIR * BASEW;        // [NBUF][64]
     float* t_s = v_s + NBUF * NPAIR;                 // [NBUF][64]
-    float* kl_s = t_s + NBUF * NPAIR;                // [128]
-    int* pn_s = reinterpret_cast<int*>(kl_s + ROWS); // [64]
+    float* kl_s = t_s + NBUF * NPAIR;                // [2][128]
+    int* pn_s = reinterpret_cast<int*>(kl_s + 2 * ROWS); // [64]
     int* pu_s = pn_s + NPAIR;                        // [64]
     uint64_t* bar2 = reinterpret_cast<uint64_t*>(pu_s + NPAIR);
     uint64_t* bar3 = bar2 + 1;
@@ -330,25 +337,32 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
                     s += (((dm * dm) * bt[2 * LAT + l] + expf(o[LAT + l]) * bt[3 * LAT + l] - 1.0f) - o[LAT + l]) + bt[LAT + l];
                 }
             }
-            kl_s[row] = 0.5f * s;
+            kl_s[(m & 1) * ROWS + row] = 0.5f * s;
             tc_fence_before();
         };
 
         // ---- prologue: A2(0), start MMA2(0), A2(1) ----
-        __pipeline_wait_prior(2);          // sample 0 landed
+        __pipeline_wait_prior(1);          // samples 0 and 1 landed
         __syncthreads();
         construct(0);
         tc_fence_before();
         __syncthreads();
-        if (tid == ISSUER) { tc_fence_after(); issue_mma2(0); }
-        if (a.M > 1) {
-            __pipeline_wait_prior(1);      // sample 1 landed
-            __syncthreads();
-            construct(1);
+        if (warp == ISSUER_WARP) {
+            tc_fence_after();
+            if (elect_one()) issue_mma2(0);
+            __syncwarp();
         }
+        if (a.M > 1) construct(1);
 
+        // One CTA barrier per sample.  In iteration m the tensor pipe runs MMA3(m) and MMA2(m+1) while the CUDA
+        // cores build the operand of sample m+2; the KL epilogue of sample m-1 is hidden under the wait for MMA2(m).
         for (int m = 0; m < a.M; ++m) {
             prefetch(m + 3);
+            __pipeline_wait_prior(1);      // this thread's copies of sample m+2 landed (visible to all after the barrier)
+            if (m > 0) {
+                if (cg == 0) kl_epilogue(m - 1);
+                ph3 ^= 1;
+            }
             mbar_wait(bar2, ph2);          // MMA2(m) (and everything issued before it) complete
             ph2 ^= 1;
             tc_fence_after();
@@ -368,26 +382,32 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
             }
             fence_async_smem();
             tc_fence_before();
-            __syncthreads();               // A3(m) and A2(m+1) are complete and visible
-            if (tid == ISSUER) {
+            __syncthreads();               // A3(m), A2(m+1), kl(m-1) and the prefetched sample m+2 are complete and visible
+            if (warp == ISSUER_WARP) {
                 tc_fence_after();
-                issue_mma3();
-                if (m + 1 < a.M) issue_mma2((m + 1) & 1);
+                if (elect_one()) {
+                    issue_mma3();
+                    if (m + 1 < a.M) issue_mma2((m + 1) & 1);
+                }
+                __syncwarp();
             }
-            // ---- CUDA cores, overlapped with the tensor pipe: KL of sample m, operand of sample m+2 ----
-            if (cg == 0) kl_epilogue(m);
-            ph3 ^= 1;
-            if (m + 2 < a.M) {
-                __pipeline_wait_prior(1);  // sample m+2 landed
-                __syncthreads();
-                construct(m + 2);
+            if (m > 0 && tid < NPAIR) {    // approx_KL += KL_I; approx_KL -= KL_II   (sample m-1)
+                const float* kb = kl_s + ((m - 1) & 1) * ROWS;
+                acc += kb[tid];
+                acc -= kb[NPAIR + tid];
             }
-            tc_fence_before();
-            __syncthreads();
-            if (tid < NPAIR) { acc += kl_s[tid]; acc -= kl_s[NPAIR + tid]; }   // approx_KL += KL_I; approx_KL -= KL_II
+            if (m + 2 < a.M) construct(m + 2);
         }
-        if (tid < NPAIR && p0 + tid < ptot) a.R[(long)pn_s[tid] * (D - 1) + pu_s[tid]] = acc / (float)a.M;   // evaluate.py:540
+        if (cg == 0) kl_epilogue(a.M - 1);
+        ph3 ^= 1;
         __pipeline_wait_prior(0);
+        __syncthreads();
+        if (tid < NPAIR) {
+            const float* kb = kl_s + ((a.M - 1) & 1) * ROWS;
+            acc += kb[tid];
+            acc -= kb[NPAIR + tid];
+            if (p0 + tid < ptot) a.R[(long)pn_s[tid] * (D - 1) + pu_s[tid]] = acc / (float)a.M;   // evaluate.py:540
+        }
         __syncthreads();
     }
     tc_fence_before();
@@ -400,7 +420,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
 
 static size_t smem_bytes() {
     size_t f = 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + 2 * (size_t)C3W * A_CHUNK + K2 + BASEW * NPAIR +
-               NBUF * NPAIR * BASEW + 2 * NBUF * NPAIR + ROWS + 2 * NPAIR + 8;
+               NBUF * NPAIR * BASEW + 2 * NBUF * NPAIR + 2 * ROWS + 2 * NPAIR + 8;
     return f * sizeof(float) + 128;
 }
 
