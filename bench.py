@@ -234,13 +234,44 @@ def gpu_mnar(args, dev, ffma_tflops, with_cpu):
            "roofline": {"bound": "launch latency (2 560 virtual rows per step; ~60 kernel launches)",
                         "achieved": FLOP_MNAR_ROW * B / (ms * 1e-3) / 1e12, "peak": ffma_tflops, "unit": "TFLOP/s",
                         "frac": FLOP_MNAR_ROW * B / (ms * 1e-3) / 1e12 / ffma_tflops},
-           "final_loss": float(loss)}
+           "final_loss": float(loss.detach())}
     if with_cpu:
         cv, cms = cpu_mnar_rows_per_s(B, S, 5, 1)
         res["cpu_baseline"] = {"value": cv, "unit": "rows/s", "cores": os.cpu_count() or 1, "kind": "port",
                                "sample": f"5 steps, batch {B}, S={S}, oracle port of REG_notMIWAE_v2 step + Adam",
                                "ms_per_step": cms}
     return res
+
+
+def gpu_pnp_train(dev, ffma_tflops, batch, steps=10):
+    """Extra line: the same fused step for the PNP/EDDI set-encoder family (Reg_EDDI, K=20, D=100), static batch."""
+    from oracle import pcvae_oracle as O
+    from vae_posterior_consistency_b200 import kernels as KR, lib as L
+    D, K = D_TRAIN, 20
+    p = O.init_params("pnp", D, K, seed=0)
+    theta = KR.flatten_params(p, L.FAMILY_PNP, dev)
+    tr = KR.FusedTrainer(L.FAMILY_PNP, D, K, theta, regularised=True, alpha=1.0)
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.rand(batch, D, device=dev, generator=g)
+    mask = torch.rand(batch, D, device=dev, generator=g) < 0.7
+    mask_p = mask & (torch.rand(batch, D, device=dev, generator=g) < 0.7)
+    eq, ep = torch.randn(batch, 10, device=dev, generator=g), torch.randn(batch, 10, device=dev, generator=g)
+    for _ in range(3):
+        tr.step(x, mask, mask_p, eq, ep)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        loss = tr.step(x, mask, mask_p, eq, ep)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    flop_row = 306_000      # collapsed-form algorithmic FLOP per row (SURVEY.md section 8d)
+    return {"metric": "train rows/s (Reg_EDDI K=20, fused step on a resident batch)", "value": batch / (ms * 1e-3),
+            "unit": "rows/s", "ms_per_step": ms, "steps": steps,
+            "roofline": {"bound": "fp32_ffma", "achieved": flop_row * batch / (ms * 1e-3) / 1e12, "peak": ffma_tflops,
+                         "unit": "TFLOP/s", "frac": flop_row * batch / (ms * 1e-3) / 1e12 / ffma_tflops},
+            "final_loss": float(loss)}
 
 
 def run_reference(args):
@@ -491,7 +522,10 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "fp32_ffma", "kernel": "k_dec<64> (decoder fwd + loss + decoder bwd, both branches)",
                          "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
-                         "traffic": None, "peak_source": "pcvae_ffma_probe on this GPU (MEASURED_PEAKS.json has no FP32 entry)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_dec launch at this shape, from the
+                         # ncu --set full capture summarised in profiles/r01_ncu_summary.md (algorithmic: 65536 rows x
+                         # (400 B x + 200 B masks + 480 B latent stats in/out) = 71 MB)
+                         "traffic": 65.4e6 if B == 65536 else None, "peak_source": "pcvae_ffma_probe on this GPU (MEASURED_PEAKS.json has no FP32 entry)",
                          "step_achieved": FLOP_TRAIN_ROW * B / (train_ms * 1e-3) / 1e12,
                          "step_frac": FLOP_TRAIN_ROW * B / (train_ms * 1e-3) / 1e12 / ffma_tflops,
                          "hbm": {"achieved": (B * D * 10 + B * 2 * 152 * 8) / (train_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -500,6 +534,7 @@ def run_ours(args):
         }
         if world == 1 and args.mnar_steps > 0:
             line["mnar"] = gpu_mnar(args, dev, ffma_tflops, not args.no_cpu)
+            line["pnp"] = gpu_pnp_train(dev, ffma_tflops, B)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             cv, cms = cpu_train_rows_per_s(B, 3, 1)
