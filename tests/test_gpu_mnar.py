@@ -178,3 +178,46 @@ def test_mnar_driver_sequence_matches_reference_artifacts(golden, tmp_path, name
                 torch.testing.assert_close(got.float(), ref.float(), rtol=5e-4, atol=1e-5, msg=lambda m: f"{rel}: {m}")
     finally:
         os.chdir(cwd)
+
+
+@pytest.mark.parametrize("cls", ["REG_notMIWAE_v2", "notMIWAE_myversion"])
+def test_graph_replayed_step_equals_eager_step(cls):
+    """graphed.py: forward + loss + backward + Adam replayed from a CUDA graph gives the same parameters as the
+    same steps launched op by op (same batches, same noise, same capturable Adam)."""
+    from vae_posterior_consistency_b200 import VAE
+    from vae_posterior_consistency_b200.graphed import GraphedTrainer
+    dev = torch.device("cuda")
+    D, B, S = 12, 24, 5
+    reg = cls == "REG_notMIWAE_v2"
+
+    def run(eager_first, n_steps=7):
+        torch.manual_seed(3)
+        model = getattr(VAE, cls)(D, 500, 20, 10, {"batch_size": B, "patience": 100}, S, 10).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+        gn = torch.Generator(device=dev).manual_seed(11)
+        gb = torch.Generator(device=dev).manual_seed(12)
+
+        if reg:
+            def fwd_loss(x, m, mp):
+                mean_p, logvar_p, xm_p, xlv_p, mean_q, logvar_q, xm_q, xlv_q = model.forward(x, m, mp, stage="train")
+                return model.loss(x, xm_p, xlv_p, mean_p, logvar_p, xm_q, xlv_q, mean_q, logvar_q, m, mp, 1, alpha=0.7)[1]
+        else:
+            def fwd_loss(x, m):
+                mean, logvar, xm, xlv = model.forward(x, m)
+                return model.loss(x, xm, xlv, mean, logvar, 1, m)[1]
+        gt = GraphedTrainer(model, lambda: fwd_loss, opt, lambda t: t.normal_(generator=gn), eager_first=eager_first)
+        losses = []
+        for s in range(n_steps):
+            rows = B if s != 4 else B - 5                      # one ragged batch in the middle (runs eagerly)
+            x = torch.rand(rows, D, device=dev, generator=gb)
+            m = (torch.rand(rows, D, device=dev, generator=gb) < 0.7).float()
+            mp = m * (torch.rand(rows, D, device=dev, generator=gb) < 0.5).float()
+            losses.append(float(gt.step(x, m, mp) if reg else gt.step(x, m)))
+        return model, losses, gt.replays
+
+    m_eager, l_eager, r0 = run(10 ** 9)
+    m_graph, l_graph, r1 = run(2)
+    assert r0 == 0 and r1 == 4                                  # steps 2, 3, 5, 6 were graph replays
+    np.testing.assert_allclose(l_graph, l_eager, rtol=1e-6)
+    for (k, a), (_, b) in zip(m_eager.state_dict().items(), m_graph.state_dict().items()):
+        torch.testing.assert_close(b, a, rtol=1e-6, atol=1e-7, msg=k)

@@ -50,9 +50,21 @@ def draw_noise(rows: int, latent: int, device, mode: str) -> torch.Tensor:
 def draw_noise_bsl(rows: int, samples: int, latent: int, device, mode: str) -> torch.Tensor:
     """[B, S, L] standard-normal draw of the not-MIWAE models: Normal(mean[B,S,L], ...).rsample() is one
     `torch.empty(B, S, L).normal_()` on the host generator in parity mode."""
+    if callable(mode):
+        return mode(rows, samples, latent, device)     # static buffers of a CUDA-graph-captured step (graphed.py)
     if mode == "host":
         return torch.empty(rows, samples, latent).normal_().to(device, non_blocking=True)
     return draw_noise(rows * samples, latent, device, "device").view(rows, samples, latent)
+
+
+def fill_normal_(out: torch.Tensor) -> torch.Tensor:
+    """In-place device-side (Philox) standard-normal fill, same stream of offsets as draw_noise(mode='device')."""
+    lib = L.load()
+    _philox_offset[0] += 1
+    with torch.cuda.device(out.device):
+        L.check(lib.pcvae_draw_normal(out.data_ptr(), out.numel(), 0x5EED, _philox_offset[0] * 65536,
+                                      torch.cuda.current_stream().cuda_stream), "pcvae_draw_normal")
+    return out
 
 
 class _PartialVAEBase(nn.Module):

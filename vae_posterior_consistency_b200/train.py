@@ -26,7 +26,8 @@ from . import lib as L
 from .dist import merge_row_blocks, row_block, world
 from .loaders import checkpoint_path, model_loader
 from .utils import create_missing_uci, create_missing_uci_drop_eddi
-from .VAE import draw_noise
+from .VAE import draw_noise, fill_normal_
+from .graphed import GraphedTrainer
 
 
 def _family_dir(vae_type):
@@ -101,7 +102,24 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
         trainer = KR.FusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, regularised=regularised,
                                   alpha=float(alpha), beta_w=float(beta), lr=0.001, dist_group=group, world_size=world_size)
     else:
-        optimizer = optim.Adam(model.parameters(), lr=0.001)
+        # throughput mode: the launch-bound MNAR step is replayed from a CUDA graph (graphed.py)
+        graphed = throughput and 'notMIWAE' in vae_type and not beta_annealing
+        optimizer = optim.Adam(model.parameters(), lr=0.001, capturable=graphed)
+        if graphed:
+            def make_fn():
+                if regularised:
+                    def fn(x, m, mp):
+                        mean_p, logvar_p, xm_p, xlv_p, mean_q, logvar_q, xm_q, xlv_q = model.forward(x, m, mp, stage=stage)
+                        return model.loss(x, xm_p, xlv_p, mean_p, logvar_p, xm_q, xlv_q, mean_q, logvar_q, m, mp, 1,
+                                          beta_annealing=False, beta=beta, alpha=alpha, alpha_annealing=alpha_annealing,
+                                          stage=stage)[1]
+                else:
+                    def fn(x, m):
+                        mean_q, logvar_q, xm_q, xlv_q = model.forward(x, m)
+                        return model.loss(x, xm_q, xlv_q, mean_q, logvar_q, 1, m, beta_annealing=False, beta=beta,
+                                          stage=stage)[1]
+                return fn
+            graph_trainer = GraphedTrainer(model, make_fn, optimizer, fill_normal_)
     keep = 1 - p_missingness / 100
     step = 0
     for i in tqdm(range(max_epochs)):
@@ -116,6 +134,8 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
                 if regularised:
                     if throughput and mask.dtype in (torch.bool, torch.uint8):
                         mask_p = _device_submask(mask, keep, step)
+                    elif throughput:
+                        mask_p = (torch.rand(data_sample.shape, device=device) < keep).to(mask.dtype) * mask
                     else:
                         temp_mask = create_missing_uci(data_sample.shape, p_missingness)     # host, NumPy RNG
                         mask_p = temp_mask.to(device) * mask
@@ -132,6 +152,11 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
                     mk = (mask * mask_drop)                                                   # float32, train.py:97
                     loss = trainer.step(data_sample[sl], mk[sl], None, eps_q[sl], None, global_rows=B)
                 total += loss
+            elif graphed:
+                if regularised:
+                    total += graph_trainer.step(data_sample, mask, mask_p)
+                else:
+                    total += graph_trainer.step(data_sample, mask * mask_drop)
             else:
                 if regularised:
                     out = model.forward(data_sample, mask, mask_p, stage=stage)
