@@ -289,8 +289,11 @@ typedef struct {
     const float* dy;       /* [rows][out_dim] */
     const float* W;
     float* dx;             /* optional out [rows][in_dim] */
-    float* dW_partials;    /* [pcvae_grid_ctas()][out_dim*in_dim]; reduce with pcvae_reduce_grads */
-    float* db_partials;    /* [pcvae_grid_ctas()][out_dim] */
+    float* dW_partials;    /* workspace [pcvae_grid_ctas()][out_dim*in_dim]; only the first
+                              min(pcvae_grid_ctas(), ceil(rows/64)) rows are written */
+    float* db_partials;    /* workspace [pcvae_grid_ctas()][out_dim], same rule */
+    float* dW;             /* optional out [out_dim][in_dim]: when dW and db are both given the call also sums the */
+    float* db;             /* optional out [out_dim]          written partial rows into them, in CTA order         */
 } pcvae_dense_bwd_params;
 int pcvae_dense_bwd(const pcvae_dense_bwd_params* p, void* stream);
 

@@ -436,10 +436,25 @@ class REG_notMIWAE_v2(_NotMIWAEBase):
                                mean_p, logvar_p, alpha, llh_eval, MI, missing_process)
 
     def forward(self, data, mask, mask_p, stage='train'):
-        z_q, mean_q, logvar_q = self.encoder(data, mask)
-        x_mean_q, x_logvar_q = self.decoder(z_q)
-        z_p, mean_p, logvar_p = self.encoder(data, mask_p)
-        x_mean_p, x_logvar_p = self.decoder(z_p)
+        """VAE.py:2473-2482.  The q branch (mask) and the p branch (mask_p) share every weight, so both run in ONE
+        pass over the stacked batch [q rows; p rows]: the same row-tile kernels, half the launches, and the weight
+        gradients of both branches are accumulated inside the kernels.  Noise is drawn q first, then p, as in the
+        reference (encoder(data, mask) ... encoder(data, mask_p))."""
+        B, S, Lt, D = data.shape[0], self.num_samples, self.latent_dim, self.obs_dim
+        dev = data.device
+        if dev.type != "cuda":
+            raise L.PcvaeError("pcvae modules need CUDA tensors: there is no CPU fallback for this path")
+        x2 = torch.cat([data, data]).float()
+        m2 = torch.cat([mask.to(dev).float(), mask_p.to(dev).float()])
+        mean2, logvar2 = self._stats(x2, m2)
+        eps_q = draw_noise_bsl(B, S, Lt, dev, self.noise)
+        eps_p = draw_noise_bsl(B, S, Lt, dev, self.noise)
+        z2 = ops.mnar_sample_z_op(mean2, logvar2, torch.cat([eps_q, eps_p]), S)
+        xm2, xlv2 = self.decoder(z2)
+        x_mean_q, x_mean_p = xm2.view(2, B, S, D).unbind(0)
+        x_logvar_q, x_logvar_p = xlv2.view(2, B, S, D).unbind(0)
+        mean_q, mean_p = (t.unsqueeze(1).expand(B, S, Lt) for t in mean2.view(2, B, Lt).unbind(0))
+        logvar_q, logvar_p = (t.unsqueeze(1).expand(B, S, Lt) for t in logvar2.view(2, B, Lt).unbind(0))
         return mean_p, logvar_p, x_mean_p, x_logvar_p, mean_q, logvar_q, x_mean_q, x_logvar_q
 
 

@@ -118,6 +118,26 @@ __global__ void __launch_bounds__(NT, 1) k_dense_bwd(const DenseArgs a) {
     flush_linear_grad(dW_s, db_s, a.dWp + (long)blockIdx.x * N * K, a.dbp + (long)blockIdx.x * N, K, N, NP, tid);
 }
 
+// dW[i] = sum_c dWp[c][i], db[j] = sum_c dbp[c][j] over the CTAs that ran, in CTA order (deterministic)
+__global__ void k_dense_reduce(const float* __restrict__ dWp, const float* __restrict__ dbp, int live, int nW, int nb,
+                               float* __restrict__ dW, float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nW + nb) return;
+    const float* src = i < nW ? dWp + i : dbp + (i - nW);
+    const long stride = i < nW ? nW : nb;
+    float s = 0.f;
+    int c = 0;
+    for (; c + 8 <= live; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = src[(long)(c + j) * stride];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    for (; c < live; ++c) s += src[(long)c * stride];
+    if (i < nW) dW[i] = s; else db[i - nW] = s;
+}
+
 }  // namespace pcvae
 
 using namespace pcvae;
@@ -129,6 +149,12 @@ static size_t dense_fwd_smem(int K, int N) {
 static size_t dense_bwd_smem(int K, int N) {
     const int NP = round4(N), P = TM_TRAIN + 4;
     return (2 * (size_t)K * NP + NP + (size_t)K * P + (size_t)NP * P) * sizeof(float);
+}
+
+// CTAs that own at least one 64-row tile (one CTA still runs for rows == 0 so that the partials are zeroed)
+static int live_ctas(int grid, int rows) {
+    const int ntiles = (rows + TM_TRAIN - 1) / TM_TRAIN;
+    return ntiles < 1 ? 1 : (ntiles < grid ? ntiles : grid);
 }
 
 template <typename Kern>
@@ -157,11 +183,11 @@ int pcvae_dense_fwd(const pcvae_dense_fwd_params* p, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = dense_fwd_smem(a.K, a.N);
     switch (p->act) {
-        case PCVAE_ACT_NONE: return launch_dense(k_dense_fwd<ACT_NONE>, sm, grid, st, "dense_fwd", a);
-        case PCVAE_ACT_RELU: return launch_dense(k_dense_fwd<ACT_RELU>, sm, grid, st, "dense_fwd", a);
-        case PCVAE_ACT_SIGMOID: return launch_dense(k_dense_fwd<ACT_SIGMOID>, sm, grid, st, "dense_fwd", a);
-        case PCVAE_ACT_ELU: return launch_dense(k_dense_fwd<ACT_ELU>, sm, grid, st, "dense_fwd", a);
-        case PCVAE_ACT_HARDTANH_M10_0: return launch_dense(k_dense_fwd<ACT_HARDTANH>, sm, grid, st, "dense_fwd", a);
+        case PCVAE_ACT_NONE: return launch_dense(k_dense_fwd<ACT_NONE>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
+        case PCVAE_ACT_RELU: return launch_dense(k_dense_fwd<ACT_RELU>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
+        case PCVAE_ACT_SIGMOID: return launch_dense(k_dense_fwd<ACT_SIGMOID>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
+        case PCVAE_ACT_ELU: return launch_dense(k_dense_fwd<ACT_ELU>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
+        case PCVAE_ACT_HARDTANH_M10_0: return launch_dense(k_dense_fwd<ACT_HARDTANH>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
     }
     return fail(PCVAE_EINVAL, "dense_fwd: unknown activation %d", p->act);
 }
@@ -178,7 +204,16 @@ int pcvae_dense_bwd(const pcvae_dense_bwd_params* p, void* stream) {
     DenseArgs a{};
     a.R = p->rows; a.K = p->in_dim; a.N = p->out_dim; a.act = p->act; a.x = p->x; a.mask = p->mask; a.W = p->W;
     a.yin = p->y; a.dy = p->dy; a.dx = p->dx; a.dWp = p->dW_partials; a.dbp = p->db_partials;
-    return launch_dense(k_dense_bwd, dense_bwd_smem(a.K, a.N), grid, (cudaStream_t)stream, "dense_bwd", a);
+    if ((p->dW == nullptr) != (p->db == nullptr)) return fail(PCVAE_EINVAL, "dense_bwd: give both dW and db or neither");
+    const int live = live_ctas(grid, a.R);
+    if (int rc = launch_dense(k_dense_bwd, dense_bwd_smem(a.K, a.N), live, (cudaStream_t)stream, "dense_bwd", a)) return rc;
+    if (p->dW) {
+        const int nW = a.N * a.K, n = nW + a.N;
+        k_dense_reduce<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.dWp, a.dbp, live, nW, a.N, p->dW, p->db);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dense_bwd: reduce launch: %s", cudaGetErrorString(e));
+    }
+    return PCVAE_OK;
 }
 
 }  // extern "C"

@@ -699,7 +699,15 @@ __global__ void k_reduce_grads(const float* __restrict__ gp, int grid, long P, l
                                float* __restrict__ grad, int accumulate) {
     for (long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (long)gridDim.x * blockDim.x) {
         float s = 0.f;
-        for (int c = 0; c < grid; ++c) s += gp[(long)c * P + i];
+        int c = 0;
+        for (; c + 8 <= grid; c += 8) {      // eight loads in flight, summed in CTA order
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gp[(long)(c + j) * P + i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[j];
+        }
+        for (; c < grid; ++c) s += gp[(long)c * P + i];
         grad[i] = accumulate ? grad[i] + s : s;
     }
 }

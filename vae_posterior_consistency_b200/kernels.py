@@ -300,10 +300,9 @@ def dense_bwd(x, W, y, dy, act, mask=None, need_dx=True):
                          dx=_p(dx), dW_partials=_p(dWp), db_partials=_p(dbp))
     dW = torch.empty(N, K, device=x.device, dtype=torch.float32)
     db = torch.empty(N, device=x.device, dtype=torch.float32)
+    p.dW, p.db = _p(dW), _p(db)          # the call reduces the per-CTA partials itself
     with torch.cuda.device(x.device):
         L.check(lib.pcvae_dense_bwd(C.byref(p), _stream()), "pcvae_dense_bwd")
-        L.check(lib.pcvae_reduce_grads(_p(dWp), g, N * K, 0, N * K, _p(dW), 0, _stream()), "pcvae_reduce_grads")
-        L.check(lib.pcvae_reduce_grads(_p(dbp), g, N, 0, N, _p(db), 0, _stream()), "pcvae_reduce_grads")
     return dx, dW, db
 
 

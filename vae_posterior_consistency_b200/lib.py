@@ -89,7 +89,7 @@ class DenseFwdParams(C.Structure):
 class DenseBwdParams(C.Structure):
     _fields_ = [("rows", C.c_int), ("in_dim", C.c_int), ("out_dim", C.c_int), ("act", C.c_int), ("x", C.c_void_p),
                 ("mask", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("W", C.c_void_p), ("dx", C.c_void_p),
-                ("dW_partials", C.c_void_p), ("db_partials", C.c_void_p)]
+                ("dW_partials", C.c_void_p), ("db_partials", C.c_void_p), ("dW", C.c_void_p), ("db", C.c_void_p)]
 
 
 class MnarLossParams(C.Structure):
