@@ -174,8 +174,17 @@ typedef struct {
     const float* d_xhat[2];     /* [B][D] */
     float* d_z[2];              /* BWD out [B][L] */
     float* grad_partials;       /* TRAIN/BWD: [grid][P], decoder slice only */
+    /* TRAIN, optional: scratch of pcvae_dec_tc_workspace_floats() floats.  When given (and tensor cores are
+     * enabled and the shape is supported) the dense products run on tcgen05 in 3xTF32 -- same results to fp32
+     * rounding -- and the pre-activation gradients / activations for the weight-gradient GEMMs go through it. */
+    float* tc_workspace;
+    long tc_workspace_floats;
 } pcvae_dec_params;
 int pcvae_dec(const pcvae_dec_params* p, void* stream);
+/* floats of tc_workspace for `rows` x `n_branch`; 0 when this (family, obs_dim) has no tensor-core decoder */
+long pcvae_dec_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch);
+/* process-wide switch for the tcgen05 training kernels (default 1); returns the previous value */
+int pcvae_set_train_tensor_cores(int enable);
 
 /* ------------------------------------------------------------------------
  * Stand-alone loss terms for the module API (`model.loss(...)` called on tensors the

@@ -47,12 +47,22 @@ def engine_for(p):
     return eng, theta, fam
 
 
+@pytest.fixture(params=[0, 1], ids=["ffma", "tcgen05"])
+def train_tc(request):
+    """Run the fused-step tests with both decoder kernels: FP32 FFMA and tcgen05 3xTF32 (used when obs_dim % 4 == 0
+    and obs_dim <= 104; other shapes take the FFMA kernel under either setting)."""
+    KR, L = _mods()
+    prev = L.load().pcvae_set_train_tensor_cores(request.param)
+    yield request.param
+    L.load().pcvae_set_train_tensor_cores(prev)
+
+
 REG = ["reg_vae_b64_d13", "reg_vae_b37_d20_a05", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07"]
 VAN = ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20"]
 
 
 @pytest.mark.parametrize("name", REG)
-def test_golden_reg_forward_and_fused_step(golden, name):
+def test_golden_reg_forward_and_fused_step(golden, name, train_tc):
     KR, L = _mods()
     g = golden(name)
     p = g["state_dict"]
@@ -102,7 +112,7 @@ def test_golden_vanilla_fused_step(golden, name):
 
 
 @pytest.mark.parametrize("name", ["traj_reg_vae_b32_d13", "traj_reg_eddi_b32_d13_k10"])
-def test_golden_training_trajectory_with_adam(golden, name):
+def test_golden_training_trajectory_with_adam(golden, name, train_tc):
     KR, L = _mods()
     g = golden(name)
     p = g["state_dict0"]
@@ -129,14 +139,15 @@ def rand_case(family, B, D, K, seed, mask_float=False):
     return p, x, mask, mask_p, eq, ep
 
 
-SHAPES = [("mlp", 1, 2, 0), ("mlp", 63, 13, 0), ("mlp", 65, 50, 0), ("mlp", 200, 100, 0), ("mlp", 130, 101, 0),
+SHAPES = [("mlp", 1, 4, 0), ("mlp", 129, 8, 0), ("mlp", 300, 100, 0), ("mlp", 257, 104, 0), ("pnp", 131, 12, 10),
+          ("mlp", 1, 2, 0), ("mlp", 63, 13, 0), ("mlp", 65, 50, 0), ("mlp", 200, 100, 0), ("mlp", 130, 101, 0),
           ("mlp", 70, 128, 0), ("pnp", 1, 2, 10), ("pnp", 65, 13, 20), ("pnp", 200, 100, 20), ("pnp", 97, 50, 7),
           ("pnp", 64, 128, 20)]
 
 
 @pytest.mark.parametrize("family,B,D,K", SHAPES)
 @pytest.mark.parametrize("alpha", [1.0, 0.3])
-def test_fused_step_vs_oracle_random_shapes(family, B, D, K, alpha):
+def test_fused_step_vs_oracle_random_shapes(family, B, D, K, alpha, train_tc):
     KR, L = _mods()
     p, x, mask, mask_p, eq, ep = rand_case(family, B, D, K, seed=B + D)
     eng, theta, fam = engine_for(p)
@@ -195,6 +206,30 @@ def test_modular_ops_vs_oracle(family, B, D, K):
     for got, want, nm in [(d_xhat[1], rg[0], "d_xh_p"), (d_mean2[1], rg[1], "d_mu_p"), (d_logvar2[1], rg[2], "d_lv_p"),
                           (d_xhat[0], rg[3], "d_xh_q"), (d_mean2[0], rg[4], "d_mu_q"), (d_logvar2[0], rg[5], "d_lv_q")]:
         torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-7, msg=lambda m: f"{nm}: {m}")
+
+
+@pytest.mark.parametrize("B,D", [(1, 4), (127, 12), (129, 20), (1000, 100), (513, 104)])
+@pytest.mark.parametrize("regularised,mask_float", [(True, False), (False, True), (True, True)])
+def test_tcgen05_decoder_matches_ffma_decoder(B, D, regularised, mask_float):
+    """Same fused step through k_dec (FFMA) and k_dec_tc + k_wgrad_tc (3xTF32): loss sums, every gradient and the
+    Adam update must agree to fp32 rounding; covers one-branch (vanilla) training and float masks."""
+    KR, L = _mods()
+    p, x, mask, mask_p, eq, ep = rand_case("mlp", B, D, 0, seed=3 * B + D, mask_float=mask_float)
+    lib = L.load()
+    out = []
+    for tc in (0, 1):
+        prev = lib.pcvae_set_train_tensor_cores(tc)
+        try:
+            eng, theta, fam = engine_for(p)
+            tr = KR.FusedTrainer(fam, D, 0, theta, regularised=regularised, alpha=0.6, beta_w=0.9)
+            sums = tr.forward_backward(x.cuda(), mask.cuda(), mask_p.cuda() if regularised else None, eq.cuda(),
+                                       ep.cuda() if regularised else None).cpu()
+            out.append((sums, tr.grad.cpu().clone()))
+        finally:
+            lib.pcvae_set_train_tensor_cores(prev)
+    (s0, g0), (s1, g1) = out
+    torch.testing.assert_close(s1, s0, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(g1, g0, rtol=2e-4, atol=2e-6 * float(g0.abs().max()))
 
 
 def test_empty_batch_is_a_no_op():
@@ -276,7 +311,7 @@ def test_reward_is_row_shardable_bit_exact(reward_tc):
     assert torch.equal(R, torch.cat([Ra, Rb]))
 
 
-def test_large_batch_properties():
+def test_large_batch_properties(train_tc):
     """BASELINE cfg4 shape (batch 65536 x 100): the fused step must be deterministic (two runs
     bit-identical) and linear in loss_scale; loss must match the oracle on a 4096-row slice."""
     KR, L = _mods()

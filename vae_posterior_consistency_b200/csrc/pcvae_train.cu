@@ -4,6 +4,7 @@
 #include <cuda_pipeline.h>
 
 #include "pcvae_internal.cuh"
+#include "pcvae_train.cuh"
 
 namespace pcvae {
 
@@ -376,25 +377,6 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
 // ====================================================================================
 // Decoder (+ loss, + backward)
 // ====================================================================================
-struct DecArgs {
-    Layout L;
-    int mode, B, nbr, mask_kind;
-    const float* theta;
-    const float* z[2];
-    float* xhat[2];
-    const float* x;
-    const void* mask[2];
-    const float* mean[2];
-    const float* logvar[2];
-    const float* eps[2];
-    float alpha, beta_w, x_logvar, loss_scale;
-    float* sums_partials;
-    float* d_mean[2];
-    float* d_logvar[2];
-    const float* d_xhat[2];
-    float* d_z[2];
-    float* gp;
-};
 
 template <int TM>
 __global__ void __launch_bounds__(NT, 1) k_dec(const DecArgs a) {
@@ -746,6 +728,8 @@ __global__ void k_ffma_probe(float* out, int iters) {
 // ========================================================================================
 using namespace pcvae;
 
+static int g_train_tc = 1;
+
 static size_t enc_fwd_smem(const Layout& L) {
     const int P = TM_TRAIN + 4, K4 = round4(L.K);
     const int in1 = L.fam == PCVAE_FAMILY_MLP ? L.D : L.K;
@@ -900,7 +884,34 @@ int pcvae_dec(const pcvae_dec_params* p, void* stream) {
     }
     a.alpha = p->alpha; a.beta_w = p->beta_w; a.x_logvar = p->x_logvar; a.loss_scale = p->loss_scale;
     a.sums_partials = p->sums_partials; a.gp = p->grad_partials;
+    if (p->mode == PCVAE_DEC_TRAIN && g_train_tc && dec_tc_supported(L) && p->tc_workspace && p->rows > 0) {
+        const long need = tcw_floats(p->rows, p->n_branch), R2P = tcw_r2p(p->rows, p->n_branch);
+        if (p->tc_workspace_floats < need)
+            return fail(PCVAE_EINVAL, "dec: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
+        float* w = p->tc_workspace;
+        a.R2P = R2P;
+        a.ws_zT = w;   w += R2P * TCW_Z;
+        a.ws_h4T = w;  w += R2P * TCW_H4;
+        a.ws_h5T = w;  w += R2P * TCW_H5;
+        a.ws_dp6T = w; w += R2P * TCW_H5;
+        a.ws_dp5T = w; w += R2P * TCW_H5;
+        a.ws_dp4T = w; w += R2P * TCW_H4;
+        a.ws_relu = reinterpret_cast<unsigned*>(w);
+        return dec_tc_launch(a, grid, (cudaStream_t)stream);
+    }
     return launch(k_dec<TM_TRAIN>, dec_smem(L, bwd), grid, (cudaStream_t)stream, "dec", a);
+}
+
+long pcvae_dec_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch) {
+    Layout L;
+    if (!m || !make_layout(m, &L) || !dec_tc_supported(L) || rows < 0 || n_branch < 1) return 0;
+    return tcw_floats(rows, n_branch);
+}
+
+int pcvae_set_train_tensor_cores(int enable) {
+    const int prev = g_train_tc;
+    g_train_tc = enable ? 1 : 0;
+    return prev;
 }
 
 int pcvae_loss_terms(const pcvae_loss_params* p, void* stream) {

@@ -174,6 +174,11 @@ class Engine:
         d_z = mk(LATENT) if mode == L.DEC_BWD else [None] * nb
         pad = lambda ts: list(ts) + [None] * (2 - len(ts))
         conv = lambda ts: pad([None if t is None else _f32(t) for t in ts])
+        tcw = None
+        if mode == L.DEC_TRAIN:      # scratch for the tcgen05 decoder (0 floats when this shape has none)
+            n = self.lib.pcvae_dec_tc_workspace_floats(C.byref(self.model), B, nb)
+            if n > 0:
+                tcw = torch.empty(n, device=dev, dtype=torch.float32)
         # converted inputs are held in locals until the launch is enqueued
         xc = None if x is None else _f32(x)
         masks_c, mean_c, logvar_c, eps_c, dxh_c = pad(masks), conv(mean), conv(logvar), conv(eps), conv(d_xhat)
@@ -183,9 +188,11 @@ class Engine:
                         alpha=alpha, beta_w=beta_w, x_logvar=x_logvar, loss_scale=loss_scale,
                         sums_partials=_p(self.sums_partials()), d_mean=_pair(d_mean), d_logvar=_pair(d_logvar),
                         d_xhat=_pair(dxh_c), d_z=_pair(d_z),
-                        grad_partials=_p(self.grad_partials() if mode in (L.DEC_TRAIN, L.DEC_BWD) else None))
+                        grad_partials=_p(self.grad_partials() if mode in (L.DEC_TRAIN, L.DEC_BWD) else None),
+                        tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel())
         with torch.cuda.device(dev):
             L.check(self.lib.pcvae_dec(C.byref(p), _stream()), "pcvae_dec")
+        self._last_tcw = tcw      # kept alive until the next call (also lets tests inspect the scratch)
         del xc, masks_c, mean_c, logvar_c, eps_c, dxh_c
         return dict(xhat=xhat, d_mean=d_mean, d_logvar=d_logvar, d_z=d_z)
 

@@ -27,6 +27,7 @@ SYMBOLS = [
     "pcvae_reward_workspace_bytes", "pcvae_reward_chain", "pcvae_ffma_probe", "pcvae_gather_rows",
     "pcvae_draw_submask", "pcvae_draw_normal", "pcvae_dense_fwd", "pcvae_dense_bwd", "pcvae_mnar_sample_z",
     "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss", "pcvae_set_reward_tensor_cores",
+    "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores",
 ]
 
 
@@ -60,7 +61,7 @@ class DecParams(C.Structure):
                 ("mask", _P2), ("mean", _P2), ("logvar", _P2), ("eps", _P2),
                 ("alpha", C.c_float), ("beta_w", C.c_float), ("x_logvar", C.c_float), ("loss_scale", C.c_float),
                 ("sums_partials", C.c_void_p), ("d_mean", _P2), ("d_logvar", _P2), ("d_xhat", _P2),
-                ("d_z", _P2), ("grad_partials", C.c_void_p)]
+                ("d_z", _P2), ("grad_partials", C.c_void_p), ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long)]
 
 
 class LossParams(C.Structure):
@@ -128,6 +129,9 @@ def load():
     lib.pcvae_enc_fwd.argtypes = [C.POINTER(EncFwdParams), C.c_void_p]
     lib.pcvae_enc_bwd.argtypes = [C.POINTER(EncBwdParams), C.c_void_p]
     lib.pcvae_dec.argtypes = [C.POINTER(DecParams), C.c_void_p]
+    lib.pcvae_dec_tc_workspace_floats.restype = C.c_long
+    lib.pcvae_dec_tc_workspace_floats.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
+    lib.pcvae_set_train_tensor_cores.argtypes = [C.c_int]
     lib.pcvae_loss_terms.argtypes = [C.POINTER(LossParams), C.c_void_p]
     lib.pcvae_reduce_sums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.pcvae_reduce_grads.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_int,
