@@ -107,9 +107,17 @@ typedef struct {
     float* act_ws;          /* optional: saved hidden activations for pcvae_enc_bwd,
                                pcvae_enc_act_ws_floats() floats; NULL = do not save */
     float* pnp_ac;          /* PNP only: workspace 2*D*K floats for the collapsed A,C tables */
+    /* optional: scratch of pcvae_enc_tc_workspace_floats() floats.  When given (and tensor cores are enabled and
+     * the shape is supported) the dense products run on tcgen05 in 3xTF32 -- same results to fp32 rounding --
+     * and everything pcvae_enc_bwd needs is saved there instead of act_ws (which may then be NULL). */
+    float* tc_workspace;
+    long tc_workspace_floats;
 } pcvae_enc_fwd_params;
 
 size_t pcvae_enc_act_ws_floats(const pcvae_model* m, int rows, int n_branch);
+/* floats of the encoder tc_workspace for `rows` x `n_branch`; 0 when this (family, obs_dim) has no tensor-core
+ * encoder (PNP family, obs_dim not a multiple of 4 or > 100, or pcvae_set_train_tensor_cores(0)) */
+long pcvae_enc_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch);
 int pcvae_enc_fwd(const pcvae_enc_fwd_params* p, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -136,6 +144,9 @@ typedef struct {
     const float* d_z[2];        /* [B][L] or NULL */
     const float* eps[2];        /* [B][L] or NULL */
     const float* logvar[2];     /* [B][L], required when d_z[b] and eps[b] are given */
+    /* the tc_workspace pcvae_enc_fwd filled for these rows (then act_ws is not read), or NULL */
+    float* tc_workspace;
+    long tc_workspace_floats;
 } pcvae_enc_bwd_params;
 int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream);
 

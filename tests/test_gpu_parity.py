@@ -49,8 +49,9 @@ def engine_for(p):
 
 @pytest.fixture(params=[0, 1], ids=["ffma", "tcgen05"])
 def train_tc(request):
-    """Run the fused-step tests with both decoder kernels: FP32 FFMA and tcgen05 3xTF32 (used when obs_dim % 4 == 0
-    and obs_dim <= 104; other shapes take the FFMA kernel under either setting)."""
+    """Run the fused-step tests with both sets of training kernels: FP32 FFMA and tcgen05 3xTF32 (decoder: obs_dim % 4 == 0
+    and obs_dim <= 104; encoder: MLP family, obs_dim % 4 == 0 and obs_dim <= 100; other shapes take the FFMA kernels
+    under either setting)."""
     KR, L = _mods()
     prev = L.load().pcvae_set_train_tensor_cores(request.param)
     yield request.param
@@ -208,11 +209,37 @@ def test_modular_ops_vs_oracle(family, B, D, K):
         torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-7, msg=lambda m: f"{nm}: {m}")
 
 
-@pytest.mark.parametrize("B,D", [(1, 4), (127, 12), (129, 20), (1000, 100), (513, 104)])
+@pytest.mark.parametrize("D", [20, 13])
+def test_enc_bwd_folds_reparameterisation(D, train_tc):
+    """pcvae_enc_bwd with d_z / eps / logvar given == the caller chaining z = mean + eps * exp(logvar / 2) by hand
+    (VAE.py:390-392); D = 20 takes the tcgen05 encoder when enabled, D = 13 the FFMA one."""
+    KR, L = _mods()
+    B = 150
+    p, x, mask, mask_p, eq, ep = rand_case("mlp", B, D, 0, seed=77)
+    eng, theta, fam = engine_for(p)
+    g = torch.Generator().manual_seed(4)
+    d_z, w_mu, w_lv = (torch.randn(B, 10, generator=g).cuda() for _ in range(3))
+    xc, mc, eqc = x.cuda(), mask.cuda(), eq.cuda()
+    grads = []
+    for folded in (True, False):
+        mean, logvar, z, ws = eng.enc_fwd(theta, xc, [mc], [eqc], save=True)
+        if folded:
+            eng.enc_bwd(theta, xc, [mc], ws, [w_mu], [w_lv], d_z=[d_z], eps=[eqc], logvar=logvar)
+        else:
+            eng.enc_bwd(theta, xc, [mc], ws, [w_mu + d_z], [w_lv + d_z * 0.5 * torch.exp(0.5 * logvar[0]) * eqc])
+        grad = torch.zeros_like(theta)
+        eng.reduce_grads(grad, 0, eng.dec_off)
+        grads.append(grad.cpu())
+    torch.testing.assert_close(grads[0], grads[1], rtol=1e-5, atol=1e-6 * float(grads[1].abs().max()))
+    assert float(grads[1].abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,D", [(1, 4), (127, 12), (129, 20), (300, 8), (65, 96), (1000, 100), (513, 104), (4100, 100)])
 @pytest.mark.parametrize("regularised,mask_float", [(True, False), (False, True), (True, True)])
 def test_tcgen05_decoder_matches_ffma_decoder(B, D, regularised, mask_float):
-    """Same fused step through k_dec (FFMA) and k_dec_tc + k_wgrad_tc (3xTF32): loss sums, every gradient and the
-    Adam update must agree to fp32 rounding; covers one-branch (vanilla) training and float masks."""
+    """Same fused step through the FFMA kernels and through k_enc_*_tc + k_dec_*_tc + k_wgrad_tc (3xTF32): loss sums and
+    every gradient must agree to fp32 rounding; covers one-branch (vanilla) training, float masks, ragged tiles and
+    more rows than one wave of CTAs."""
     KR, L = _mods()
     p, x, mask, mask_p, eq, ep = rand_case("mlp", B, D, 0, seed=3 * B + D, mask_float=mask_float)
     lib = L.load()

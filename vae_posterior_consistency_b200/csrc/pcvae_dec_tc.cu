@@ -12,7 +12,8 @@
 //                  F6: [128 x 104] h5|1 x W6aug^T -> round16(D);  sigmoid, masked NLL sums, dL/d(pre-sigmoid)
 //   k_dec_bwd_tc   X6: [128 x 104] dpre6 x W6 -> 112   X5: [128 x 104] dpre5 x W5 -> 64   X4: [128 x 56] dpre4 x W4 -> 16
 //                  KL sums, d_mean / d_logvar (reparameterisation folded in)
-//   k_wgrad_tc     dWaug[m][n] = sum_rows dpre[row][m] * (act|1)[row][n]  for layers 6, 5, 4 (bias = the 1 column)
+//   k_wgrad_tc     dWaug[m][n] = sum_rows dpre[row][m] * (act|1)[row][n]  for layers 6, 5, 4 (bias = the 1 column;
+//                  pcvae_wgrad_tc.cu, one launch for the three layers)
 //
 // Biases ride along as an extra K column (the augmented weights hold b at column `in`, and one extra output
 // row generates the constant-1 column of the next layer).  In the first two kernels the activation operand
@@ -29,15 +30,12 @@
 //                                                 ACC1 [336,448)                 ACC2 [448,512)
 #include <cuda_pipeline.h>
 
-#include "pcvae_tc.cuh"
+#include "pcvae_tc_tile.cuh"
 #include "pcvae_train.cuh"
 
 namespace pcvae {
 namespace tc {
 
-constexpr int ROWS = 128;
-constexpr int RA_HI = 0, RA_LO = 112, RB_HI = 224, RB_LO = 280, ACC1 = 336, ACC2 = 448;
-constexpr int DEC_ISSUER_WARP = 4;
 // forward images  [K/4 chunks][N rows][4]
 constexpr int F4_C = 4, F4_N = 64;        // K = 16 (z|1), 50 outputs + the constant-1 generator
 constexpr int F5_C = 14, F5_N = 112;      // K = 56 (h4|1), 100 outputs + the constant-1 generator
@@ -47,120 +45,6 @@ constexpr int X6_C = 26, X6_N = 112;      // K = 104 (d), 100 inputs k
 constexpr int X5_C = 26, X5_N = 64;       // K = 104 (n), 50 inputs k
 constexpr int X4_C = 14, X4_N = 16;       // K = 56 (n), 10 inputs k
 
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
-                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 3xTF32 product: activation operand in TMEM (hi at a_hi, lo at a_lo), weight image (K-major) in shared memory;
-// a k-step (8 tf32) is two 16-byte chunks of the image
-__device__ __forceinline__ void issue_3x(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint64_t b_step,
-                                         int ksteps, uint32_t idesc) {
-    for (int ks = 0; ks < ksteps; ++ks) {
-        mma_tf32_ts(acc, a_lo + 8 * ks, b_hi + ks * b_step, idesc, ks > 0);
-        mma_tf32_ts(acc, a_hi + 8 * ks, b_lo + ks * b_step, idesc, 1);
-        mma_tf32_ts(acc, a_hi + 8 * ks, b_hi + ks * b_step, idesc, 1);
-    }
-}
-
-__device__ __forceinline__ void load_mask4(const void* m, long gi, int kind, float* o) {
-    if (kind == PCVAE_MASK_U8) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(static_cast<const unsigned char*>(m) + gi);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = ((w >> (8 * j)) & 0xFFu) ? 1.f : 0.f;
-    } else {
-        const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(m) + gi);
-        o[0] = v.x != 0.f ? 1.f : 0.f; o[1] = v.y != 0.f ? 1.f : 0.f; o[2] = v.z != 0.f ? 1.f : 0.f; o[3] = v.w != 0.f ? 1.f : 0.f;
-    }
-}
-
-// hi / lo image of an augmented weight matrix; w(n, k) supplies element (row n, column k)
-template <typename F>
-__device__ __forceinline__ void build_image(float* hi, float* lo, int chunks, int nrows, int tid, F w) {
-    for (int i = tid; i < chunks * nrows * 4; i += NT) {
-        const int c = i / (nrows * 4), n = (i >> 2) % nrows, k = 4 * c + (i & 3);
-        const float v = w(n, k);
-        hi[i] = v;
-        lo[i] = tf32_lo(v);
-    }
-}
-
-struct TileCtx {
-    uint32_t tmem, lane_addr, ph;
-    int q, cg, row, c28, c16;
-};
-
-// barrier + (one elected lane) MMA issue + commit; every thread then waits for the batch
-template <typename Issue>
-__device__ __forceinline__ void run_mma(TileCtx& cx, uint64_t* bar, int warp, Issue&& issue) {
-    tmem_st_wait();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == DEC_ISSUER_WARP) {
-        tc_fence_after();
-        if (elect_one()) {
-            issue();
-            mma_commit(bar);
-        }
-        __syncwarp();
-    }
-    mbar_wait(bar, cx.ph);
-    cx.ph ^= 1;
-    tc_fence_after();
-}
-
-__device__ __forceinline__ void tc_setup(TileCtx& cx, uint64_t* bar, uint32_t* slot, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    cx.tmem = *slot;
-    cx.ph = 0;
-    cx.q = warp & 3;
-    cx.cg = warp >> 2;
-    cx.row = 32 * cx.q + lane;
-    cx.lane_addr = cx.tmem + ((uint32_t)(32 * cx.q) << 16);
-    cx.c28 = 28 * cx.cg;
-    cx.c16 = 16 * cx.cg;
-}
-
-__device__ __forceinline__ void tc_teardown(const TileCtx& cx, int tid) {
-    tc_fence_before();
-    __syncthreads();
-    if ((tid >> 5) == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"(512));
-    }
-}
-
-// 28 accumulator columns of this thread, in parts of 16 / 8 / 4
-__device__ __forceinline__ void ld_part(uint32_t addr, int part, float* v) {
-    if (part == 0) tmem_ld16(addr, v);
-    else if (part == 1) tmem_ld8(addr + 16, v);
-    else tmem_ld4(addr + 24, v);
-}
-__device__ __forceinline__ void st_part(uint32_t addr, int part, const float* v) {
-    if (part == 0) tmem_st16(addr, v);
-    else if (part == 1) tmem_st8(addr + 16, v);
-    else tmem_st4(addr + 24, v);
-}
 
 // ------------------------------------------------------------------------------------------------
 // forward + loss
@@ -539,146 +423,6 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     tc_teardown(cx, tid);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Weight gradient  dWaug[m][n] = sum_r AT[m][r] * BT[n][r]  over all rows of both branches, 3xTF32, both operands
-// K-major from shared memory (K = rows).  32-row slabs are streamed with cp.async through a 3-stage ring; the
-// accumulator lives in TMEM for the whole launch and is written once, as this CTA's partial, into
-// gp[cta][W_off + m*Kin + n] (n < Kin) and gp[cta][b_off + m] (n == Kin: the constant-1 row of BT).
-// ------------------------------------------------------------------------------------------------
-struct WgradArgs {
-    const float* AT; int Ma;              // [>= Ma][R2P]: pre-activation gradients, feature-major
-    const float* BT; int Kin;             // [>= Kin + 1][R2P]: layer input | 1, feature-major
-    int Nb;                               // MMA N: round16(Kin + 1)
-    long R2P;                             // row pitch (multiple of 32; columns >= the real row count are zero)
-    float* gp; long P; int W_off, b_off;
-};
-
-constexpr int SLAB = 32, WG_STAGES = 3, WG_CH = SLAB / 4;
-constexpr int WG_ACS = (128 + 1) * 4, WG_BCS = (112 + 1) * 4;       // chunk strides in floats (+1 row: conflict-free cp.async writes)
-constexpr int WG_A_FLOATS = WG_CH * WG_ACS, WG_B_FLOATS = WG_CH * WG_BCS;
-constexpr int WG_STAGE_FLOATS = 2 * WG_A_FLOATS + 2 * WG_B_FLOATS;
-
-__global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
-    extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t free_bar[WG_STAGES];
-    __shared__ __align__(8) uint64_t done_bar;
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* gp = a.gp + (long)blockIdx.x * a.P;
-    const long nslab = a.R2P / SLAB;
-    const long mine = blockIdx.x < nslab ? (nslab - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    if (mine == 0) {                                    // no rows for this CTA: its partial is zero
-        for (int i = tid; i < a.Ma * (a.Kin + 1); i += NT) {
-            const int m = i / (a.Kin + 1), n = i - m * (a.Kin + 1);
-            if (n < a.Kin) gp[a.W_off + m * a.Kin + n] = 0.f; else gp[a.b_off + m] = 0.f;
-        }
-        return;
-    }
-    for (int i = tid; i < WG_STAGES * WG_STAGE_FLOATS; i += NT) smem[i] = 0.f;   // rows the copies never touch stay zero
-    if (tid == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&free_bar[s])), "r"(1));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&done_bar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = make_idesc(128, a.Nb);
-    const int nb1 = a.Kin + 1;                          // real rows of BT
-    const int items = WG_CH * (a.Ma + nb1);             // 16-byte copies per slab
-
-    auto stage_ptr = [&](int s) { return smem + s * WG_STAGE_FLOATS; };   // Ahi | Alo | Bhi | Blo
-    auto load_slab = [&](long i) {                        // cp.async this CTA's i-th slab into stage i % 3
-        if (i < mine) {
-            float* st = stage_ptr((int)(i % WG_STAGES));
-            const long r0 = (blockIdx.x + i * gridDim.x) * SLAB;
-            for (int idx = tid; idx < items; idx += NT) {
-                const int f = idx / WG_CH, c = idx - f * WG_CH;          // feature row, 4-row chunk
-                if (f < a.Ma) __pipeline_memcpy_async(st + c * WG_ACS + f * 4, a.AT + (long)f * a.R2P + r0 + 4 * c, 16);
-                else __pipeline_memcpy_async(st + 2 * WG_A_FLOATS + c * WG_BCS + (f - a.Ma) * 4, a.BT + (long)(f - a.Ma) * a.R2P + r0 + 4 * c, 16);
-            }
-        }
-        __pipeline_commit();
-    };
-    uint32_t free_ph[WG_STAGES] = {0, 0, 0};
-    load_slab(0);
-    load_slab(1);
-    for (long i = 0; i < mine; ++i) {
-        const int s = (int)(i % WG_STAGES);
-        if (i >= 1) {                                     // stage (i+2)%3 was read by the MMAs of slab i-1
-            const int sp = (int)((i + 2) % WG_STAGES);
-            mbar_wait(&free_bar[sp], free_ph[sp]);
-            free_ph[sp] ^= 1;
-        }
-        load_slab(i + 2);
-        __pipeline_wait_prior(2);                         // slab i landed (this thread's copies)
-        __syncthreads();
-        float* st = stage_ptr(s);
-        for (int idx = tid; idx < items; idx += NT) {     // lo images
-            const int c = idx / (a.Ma + nb1), f = idx - c * (a.Ma + nb1);
-            float* hi = f < a.Ma ? st + c * WG_ACS + f * 4 : st + 2 * WG_A_FLOATS + c * WG_BCS + (f - a.Ma) * 4;
-            float* lo = hi + (f < a.Ma ? WG_A_FLOATS : WG_B_FLOATS);
-            const float4 v = *reinterpret_cast<const float4*>(hi);
-            *reinterpret_cast<float4*>(lo) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == DEC_ISSUER_WARP) {
-            tc_fence_after();
-            if (elect_one()) {
-                const uint64_t dAh = make_desc(smem_u32(st), WG_ACS * 4, 128), dAl = make_desc(smem_u32(st + WG_A_FLOATS), WG_ACS * 4, 128);
-                const uint64_t dBh = make_desc(smem_u32(st + 2 * WG_A_FLOATS), WG_BCS * 4, 128),
-                               dBl = make_desc(smem_u32(st + 2 * WG_A_FLOATS + WG_B_FLOATS), WG_BCS * 4, 128);
-                constexpr uint64_t sa = (2 * WG_ACS * 4) >> 4, sb = (2 * WG_BCS * 4) >> 4;
-#pragma unroll
-                for (int ks = 0; ks < SLAB / 8; ++ks) {
-                    mma_tf32_ss(tmem, dAl + ks * sa, dBh + ks * sb, idesc, (i > 0 || ks > 0) ? 1u : 0u);
-                    mma_tf32_ss(tmem, dAh + ks * sa, dBl + ks * sb, idesc, 1);
-                    mma_tf32_ss(tmem, dAh + ks * sa, dBh + ks * sb, idesc, 1);
-                }
-                mma_commit(&free_bar[s]);
-                if (i == mine - 1) mma_commit(&done_bar);
-            }
-            __syncwarp();
-        }
-    }
-    __pipeline_wait_prior(0);
-    mbar_wait(&done_bar, 0);
-    tc_fence_after();
-    {   // accumulator row m = TMEM lane; this thread's quarter of the columns
-        const int q = warp & 3, cgp = warp >> 2;
-        const int m = 32 * q + lane;
-        const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-        const int nbc = a.Nb / 4;
-        const int per = (nbc + 3) / 4 * 4;                // columns per group, multiple of 4
-        for (int c = cgp * per; c < min(a.Nb, (cgp + 1) * per); c += 4) {
-            float v[4];
-            tmem_ld4(lane_addr + c, v);
-            if (m < a.Ma) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = c + j;
-                    if (n < a.Kin) gp[a.W_off + m * a.Kin + n] = v[j];
-                    else if (n == a.Kin) gp[a.b_off + m] = v[j];
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
-    }
-}
-
 static size_t dec_fwd_tc_smem(int D) {
     const int N6 = (D + 15) & ~15;
     return (size_t)2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * N6 * 4) * sizeof(float) + 128;
@@ -710,13 +454,10 @@ int dec_tc_launch(const DecArgs& a, int grid, cudaStream_t st) {
     }
     if (int rc = tc_launch(tc::k_dec_fwd_tc, a, tc::dec_fwd_tc_smem(a.L.D), grid, st, "dec_fwd_tc")) return rc;
     if (int rc = tc_launch(tc::k_dec_bwd_tc, a, tc::dec_bwd_tc_smem(), grid, st, "dec_bwd_tc")) return rc;
-    const size_t wsm = (size_t)tc::WG_STAGES * tc::WG_STAGE_FLOATS * sizeof(float) + 128;
-    tc::WgradArgs w6{a.ws_dp6T, a.L.D, a.ws_h5T, G2, 112, a.R2P, a.gp, a.L.total, a.L.W6, a.L.b6};
-    tc::WgradArgs w5{a.ws_dp5T, G2, a.ws_h4T, G1, 64, a.R2P, a.gp, a.L.total, a.L.W5, a.L.b5};
-    tc::WgradArgs w4{a.ws_dp4T, G1, a.ws_zT, LAT, 16, a.R2P, a.gp, a.L.total, a.L.W4, a.L.b4};
-    if (int rc = tc_launch(tc::k_wgrad_tc, w6, wsm, grid, st, "wgrad6")) return rc;
-    if (int rc = tc_launch(tc::k_wgrad_tc, w5, wsm, grid, st, "wgrad5")) return rc;
-    return tc_launch(tc::k_wgrad_tc, w4, wsm, grid, st, "wgrad4");
+    const WgradJob jobs[3] = {{a.ws_dp6T, a.L.D, a.ws_h5T, G2, 112, a.L.W6, a.L.b6},
+                              {a.ws_dp5T, G2, a.ws_h4T, G1, 64, a.L.W5, a.L.b5},
+                              {a.ws_dp4T, G1, a.ws_zT, LAT, 16, a.L.W4, a.L.b4}};
+    return wgrad_tc_launch(jobs, 3, a.R2P, a.gp, a.L.total, grid, st);
 }
 
 }  // namespace pcvae

@@ -1,0 +1,375 @@
+// tcgen05 (5th-gen tensor core) version of the zero-impute MLP encoder and its backward (k_enc_fwd / k_enc_bwd in
+// pcvae_train.cu, family MLP): same mathematics (Reg_VAE.encoder / vanilla_VAE.encoder, src/models/VAE.py:387-395,
+// 1155-1163, and the autograd of train.py:115), 128-row tiles, every dense product on the tensor cores in
+// fp32-accurate 3xTF32 (see pcvae_dec_tc.cu for the scheme; the scaffolding is shared through pcvae_tc_tile.cuh).
+//
+//   k_enc_fwd_tc   E1: [128 x round8(D+1)] x*mask|1 x W1aug^T -> 112     E2: [128 x 104] h1|1 x W2aug^T -> 64
+//                  E3: [128 x 56] h2|1 x W3aug^T -> 32 (mean | logvar);   z = mean + eps * exp(logvar / 2)
+//   k_enc_bwd_tc   X3: [128 x 24] (d_mean|d_logvar) x W3 -> 64    X2: [128 x 56] dpre2 x W2 -> 112
+//                  (no data gradient for the first layer: x is an input)
+//   k_wgrad_tc     dWaug for layers 1, 2, 3 from the feature-major scratch (pcvae_wgrad_tc.cu, one launch)
+//
+// The backward kernel needs 240 TMEM columns and 62 KB of shared memory, so two of its CTAs share an SM.
+#include "pcvae_tc_tile.cuh"
+#include "pcvae_train.cuh"
+
+namespace pcvae {
+namespace tc {
+
+// forward images  [K/4 chunks][N rows][4]
+constexpr int E1_N = 112;                  // 100 outputs + the constant-1 generator; K = round8(D + 1)
+constexpr int E2_C = 26, E2_N = 64;        // K = 104 (h1|1), 50 outputs + the constant-1 generator
+constexpr int E3_C = 14, E3_N = 32;        // K = 56 (h2|1), mean | logvar
+// data-gradient images (transposed weights)
+constexpr int Y3_C = 6, Y3_N = 64;         // K = 24 (n over 2L), 50 inputs k
+constexpr int Y2_C = 14, Y2_N = 112;       // K = 56 (n over 50), 100 inputs k
+// TMEM map of the backward kernel (256 columns): d3 hi [0,24) lo [32,56); acc of X3 [64,128); dpre2 hi [128,184)
+// lo [184,240); acc of X2 [0,112) -- it aliases d3 and the X3 accumulator, both dead by then
+constexpr int B_D3H = 0, B_D3L = 32, B_AC2 = 64, B_RBH = 128, B_RBL = 184, B_AC1 = 0, B_COLS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar_s;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int D = a.L.D, K1 = (D + 8) & ~7, C1 = K1 / 4;
+    float* W1h = smem;
+    float* W1l = W1h + C1 * E1_N * 4;
+    float* W2h = W1l + C1 * E1_N * 4;
+    float* W2l = W2h + E2_C * E2_N * 4;
+    float* W3h = W2l + E2_C * E2_N * 4;
+    float* W3l = W3h + E3_C * E3_N * 4;
+    const float* th = a.theta;
+    const Layout L = a.L;
+    build_image(W1h, W1l, C1, E1_N, tid, [&](int n, int k) {
+        if (n < H1 && k < D) return th[L.W1 + n * D + k];
+        if (n < H1 && k == D) return th[L.b1 + n];
+        return (n == H1 && k == D) ? 1.0f : 0.0f;             // constant-1 output -> bias column of layer 2
+    });
+    build_image(W2h, W2l, E2_C, E2_N, tid, [&](int n, int k) {
+        if (n < H2 && k < H1) return th[L.W2 + n * H1 + k];
+        if (n < H2 && k == H1) return th[L.b2 + n];
+        return (n == H2 && k == H1) ? 1.0f : 0.0f;            // constant-1 output -> bias column of layer 3
+    });
+    build_image(W3h, W3l, E3_C, E3_N, tid, [&](int n, int k) {
+        if (n < LAT2 && k < H2) return th[L.W3 + n * H2 + k];
+        if (n < LAT2 && k == H2) return th[L.b3 + n];
+        return 0.0f;
+    });
+    TileCtx cx;
+    tc_setup(cx, &bar_s, &tmem_slot, tid);
+    const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
+    const int cg = cx.cg, row = cx.row, c28 = cx.c28, c16 = cx.c16;
+
+    const uint32_t cs1 = E1_N * 16, cs2 = E2_N * 16, cs3 = E3_N * 16;   // chunk strides (LBO); 8-row groups are 128 B apart (SBO)
+    const uint64_t e1h = make_desc(smem_u32(W1h), cs1, 128), e1l = make_desc(smem_u32(W1l), cs1, 128);
+    const uint64_t e2h = make_desc(smem_u32(W2h), cs2, 128), e2l = make_desc(smem_u32(W2l), cs2, 128);
+    const uint64_t e3h = make_desc(smem_u32(W3h), cs3, 128), e3l = make_desc(smem_u32(W3l), cs3, 128);
+    const uint64_t es1 = (2 * cs1) >> 4, es2 = (2 * cs2) >> 4, es3 = (2 * cs3) >> 4;
+    const uint32_t idE1 = make_idesc(ROWS, E1_N), idE2 = make_idesc(ROWS, E2_N), idE3 = make_idesc(ROWS, E3_N);
+    const EncTcWs tw = a.tw;
+    const long R2P = tw.R2P;
+    const bool save = tw.inT != nullptr;
+
+    const int ntiles = (a.B + ROWS - 1) / ROWS;
+    const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int grow = t * ROWS + row;
+        const bool ok = grow < a.B;
+        {   // pull the next tile of this CTA towards L2 while this one is processed
+            const int tn = t + gridDim.x;
+            if (tn < ntiles) {
+                const long r0 = (long)tn * ROWS, nrows = min((long)ROWS, (long)a.B - r0);
+                prefetch_l2(a.x + r0 * D, nrows * D * 4, tid);
+                for (int b = 0; b < a.nbr; ++b) prefetch_l2((const char*)a.mask[b] + r0 * D * msz, nrows * D * msz, tid);
+            }
+        }
+        for (int br = 0; br < a.nbr; ++br) {
+            const long wrow = (long)br * a.B + grow;          // column in the feature-major scratch
+            // ---- x * mask | 1 -> RA, HBM ----
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                float v[16], lo[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (4 * g >= cnt) continue;
+                    const int c = c28 + j0 + 4 * g;
+                    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (c < D) {
+                        if (ok) {
+                            const long gi = (long)grow * D + c;
+                            const float4 x4 = *reinterpret_cast<const float4*>(a.x + gi);
+                            float m[4];
+                            load_mask4<true>(a.mask[br], gi, a.mask_kind, m);
+                            xv[0] = x4.x * m[0]; xv[1] = x4.y * m[1]; xv[2] = x4.z * m[2]; xv[3] = x4.w * m[3];
+                        }
+                    } else if (c == D) {
+                        xv[0] = 1.0f;                          // bias column
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { v[4 * g + j] = xv[j]; lo[4 * g + j] = tf32_lo(xv[j]); }
+                }
+                st_part(lane_addr + RA_HI + c28, part, v);
+                st_part(lane_addr + RA_LO + c28, part, lo);
+                if (ok && save) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < cnt && c28 + j0 + j <= D) tw.inT[(c28 + j0 + j) * R2P + wrow] = v[j];
+                }
+            }
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
+
+            // ---- h1 = relu(acc1) | 1 -> RA, HBM ----
+            uint32_t m1 = 0;                                  // relu mask of this thread's 28 h1 columns
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                float v[16], lo[16];
+                ld_part(lane_addr + ACC1 + c28, part, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt) {
+                        if (v[j] > 0.f) m1 |= 1u << (j0 + j); else v[j] = 0.f;
+                        lo[j] = tf32_lo(v[j]);
+                    }
+                st_part(lane_addr + RA_HI + c28, part, v);
+                st_part(lane_addr + RA_LO + c28, part, lo);
+                if (ok && save) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < cnt && c28 + j0 + j < ETW_H1) tw.h1T[(c28 + j0 + j) * R2P + wrow] = v[j];
+                }
+            }
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, e2h, e2l, es2, E2_C / 2, idE2); });
+
+            // ---- h2 = relu(acc2) | 1 -> RB, HBM ----
+            uint32_t m2 = 0;                                  // relu mask of this thread's 16 h2 columns
+            {
+                float v[16], lo[16];
+                tmem_ld16(lane_addr + ACC2 + c16, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (v[j] > 0.f) m2 |= 1u << j; else v[j] = 0.f;
+                    lo[j] = tf32_lo(v[j]);
+                }
+                if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
+                else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
+                if (ok && save) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c16 + j < ETW_H2) tw.h2T[(c16 + j) * R2P + wrow] = v[j];
+                    tw.relu[wrow * 8 + cg] = m1;
+                    tw.relu[wrow * 8 + 4 + cg] = m2;
+                }
+            }
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, e3h, e3l, es3, E3_C / 2, idE3); });
+
+            // ---- mean | logvar, reparameterisation (one row per thread of column group 0) ----
+            if (cg == 0) {
+                float o[LAT2];
+                tmem_ld16(lane_addr + ACC1, o);
+                tmem_ld4(lane_addr + ACC1 + 16, o + 16);
+                if (ok) {
+                    const long gi = (long)grow * LAT;
+                    float2* mo = reinterpret_cast<float2*>(a.mean[br] + gi);
+                    float2* lo_ = reinterpret_cast<float2*>(a.logvar[br] + gi);
+#pragma unroll
+                    for (int l = 0; l < LAT / 2; ++l) {
+                        mo[l] = make_float2(o[2 * l], o[2 * l + 1]);
+                        lo_[l] = make_float2(o[LAT + 2 * l], o[LAT + 2 * l + 1]);
+                    }
+                    if (a.z[br]) {
+                        float2* zo = reinterpret_cast<float2*>(a.z[br] + gi);
+                        const float2* ep = a.eps[br] ? reinterpret_cast<const float2*>(a.eps[br] + gi) : nullptr;
+#pragma unroll
+                        for (int l = 0; l < LAT / 2; ++l) {
+                            float2 zz = make_float2(o[2 * l], o[2 * l + 1]);
+                            if (ep) {
+                                const float2 e = ep[l];
+                                zz.x = fmaf(e.x, expf(o[LAT + 2 * l] * 0.5f), zz.x);
+                                zz.y = fmaf(e.y, expf(o[LAT + 2 * l + 1] * 0.5f), zz.y);
+                            }
+                            zo[l] = zz;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();      // the next branch overwrites RA / ACC2 only after its own barrier
+        }
+    }
+    tc_teardown(cx, tid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: data gradients down to the first layer's pre-activation
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar_s;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float* T3h = smem;
+    float* T3l = T3h + Y3_C * Y3_N * 4;
+    float* T2h = T3l + Y3_C * Y3_N * 4;
+    float* T2l = T2h + Y2_C * Y2_N * 4;
+    const float* th = a.theta;
+    const Layout L = a.L;
+    // transposed weights: image row = layer INPUT index, image column (reduction) = layer OUTPUT index
+    build_image(T3h, T3l, Y3_C, Y3_N, tid, [&](int k, int n) { return (k < H2 && n < LAT2) ? th[L.W3 + n * H2 + k] : 0.0f; });
+    build_image(T2h, T2l, Y2_C, Y2_N, tid, [&](int k, int n) { return (k < H1 && n < H2) ? th[L.W2 + n * H1 + k] : 0.0f; });
+    TileCtx cx;
+    tc_setup(cx, &bar_s, &tmem_slot, tid, B_COLS);
+    const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
+    const int cg = cx.cg, row = cx.row, c28 = cx.c28, c16 = cx.c16;
+
+    const uint32_t cs3 = Y3_N * 16, cs2 = Y2_N * 16;
+    const uint64_t y3h = make_desc(smem_u32(T3h), cs3, 128), y3l = make_desc(smem_u32(T3l), cs3, 128);
+    const uint64_t y2h = make_desc(smem_u32(T2h), cs2, 128), y2l = make_desc(smem_u32(T2l), cs2, 128);
+    const uint64_t ys3 = (2 * cs3) >> 4, ys2 = (2 * cs2) >> 4;
+    const uint32_t idY3 = make_idesc(ROWS, Y3_N), idY2 = make_idesc(ROWS, Y2_N);
+    const EncTcWs tw = a.tw;
+    const long R2P = tw.R2P;
+
+    const int nvt = ((a.B + ROWS - 1) / ROWS) * a.nbr;
+    const int ntiles = (a.B + ROWS - 1) / ROWS;
+    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x) {
+        const int br = vt / ntiles, t = vt - br * ntiles;
+        const int grow = t * ROWS + row;
+        const bool ok = grow < a.B;
+        const long wrow = (long)br * a.B + grow;
+        uint32_t m1 = 0, m2 = 0;
+        if (ok) { m1 = tw.relu[wrow * 8 + cg]; m2 = tw.relu[wrow * 8 + 4 + cg]; }
+        // ---- dpre3 = (d_mean | d_logvar) -> TMEM, HBM ----
+        if (cg == 0) {
+            float v[24], lo[24];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) v[j] = 0.f;
+            if (ok) {
+                const long gi = (long)grow * LAT;
+                const float2* dm = reinterpret_cast<const float2*>(a.d_mean[br] + gi);
+                const float2* dv = reinterpret_cast<const float2*>(a.d_logvar[br] + gi);
+#pragma unroll
+                for (int l = 0; l < LAT / 2; ++l) {
+                    const float2 p = dm[l], q2 = dv[l];
+                    v[2 * l] = p.x; v[2 * l + 1] = p.y; v[LAT + 2 * l] = q2.x; v[LAT + 2 * l + 1] = q2.y;
+                }
+                if (a.d_z[br]) {          // reparameterisation backward folded in (z = mean + eps * exp(logvar / 2))
+#pragma unroll
+                    for (int l = 0; l < LAT; ++l) {
+                        const float dz = a.d_z[br][gi + l];
+                        v[l] += dz;
+                        if (a.eps[br]) v[LAT + l] = fmaf(dz * 0.5f * expf(a.logvar[br][gi + l] * 0.5f), a.eps[br][gi + l], v[LAT + l]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 24; ++j) lo[j] = tf32_lo(v[j]);
+            tmem_st16(lane_addr + B_D3H, v);
+            tmem_st8(lane_addr + B_D3H + 16, v + 16);
+            tmem_st16(lane_addr + B_D3L, lo);
+            tmem_st8(lane_addr + B_D3L + 16, lo + 16);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < LAT2; ++j) tw.dp3T[j * R2P + wrow] = v[j];
+            }
+        }
+        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC2, tmem + B_D3H, tmem + B_D3L, y3h, y3l, ys3, Y3_C / 2, idY3); });
+
+        // ---- dpre2 = dh2 * relu'(h2) -> TMEM, HBM ----
+        {
+            float v[16], lo[16];
+            tmem_ld16(lane_addr + B_AC2 + c16, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (!((m2 >> j) & 1u) || c16 + j >= H2) v[j] = 0.f;     // column H2 is the bias column
+                lo[j] = tf32_lo(v[j]);
+            }
+            if (cg < 3) { tmem_st16(lane_addr + B_RBH + c16, v); tmem_st16(lane_addr + B_RBL + c16, lo); }
+            else { tmem_st8(lane_addr + B_RBH + c16, v); tmem_st8(lane_addr + B_RBL + c16, lo); }
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c16 + j < ETW_H2) tw.dp2T[(c16 + j) * R2P + wrow] = v[j];
+            }
+        }
+        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, y2h, y2l, ys2, Y2_C / 2, idY2); });
+
+        // ---- dpre1 = dh1 * relu'(h1) -> HBM ----
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {
+            const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+            float v[16];
+            ld_part(lane_addr + B_AC1 + c28, part, v);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt && c28 + j0 + j < ETW_H1)
+                        tw.dp1T[(c28 + j0 + j) * R2P + wrow] = (((m1 >> (j0 + j)) & 1u) && c28 + j0 + j < H1) ? v[j] : 0.f;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();            // the X2 accumulator aliases the columns the next tile writes first
+        tc_fence_after();
+    }
+    tc_teardown(cx, tid, B_COLS);
+}
+
+static size_t enc_fwd_tc_smem(int D) {
+    const int C1 = ((D + 8) & ~7) / 4;
+    return (size_t)2 * (C1 * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4) * sizeof(float) + 128;
+}
+static size_t enc_bwd_tc_smem() { return (size_t)2 * (Y3_C * Y3_N * 4 + Y2_C * Y2_N * 4) * sizeof(float) + 128; }
+
+}  // namespace tc
+
+bool enc_tc_supported(const Layout& L) { return L.fam == PCVAE_FAMILY_MLP && L.D % 4 == 0 && L.D >= 4 && L.D <= 100; }
+
+void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw) {
+    const long R2P = tcw_r2p(rows, nbr);
+    tw->R2P = R2P;
+    tw->inT = w;  w += R2P * ETW_IN;
+    tw->h1T = w;  w += R2P * ETW_H1;
+    tw->h2T = w;  w += R2P * ETW_H2;
+    tw->dp1T = w; w += R2P * ETW_H1;
+    tw->dp2T = w; w += R2P * ETW_H2;
+    tw->dp3T = w; w += R2P * ETW_DP3;
+    tw->relu = reinterpret_cast<unsigned*>(w);
+}
+
+template <typename Kern, typename Args>
+static int enc_tc_go(Kern kern, const Args& args, size_t sm, int grid, cudaStream_t st, const char* name) {
+    if (sm > MAX_SMEM) return fail(PCVAE_EINVAL, "%s: shared memory %zu B exceeds %d", name, sm, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    kern<<<grid, NT, sm, st>>>(args);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: launch: %s", name, cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st) {
+    if (a.tw.inT) {
+        const long R2 = (long)a.nbr * a.B, R2P = a.tw.R2P;
+        if (R2P > R2) {   // zero the padding columns [R2, R2P) of every feature row (read by the weight-gradient slabs)
+            cudaError_t e = cudaMemset2DAsync(a.tw.inT + R2, R2P * sizeof(float), 0, (R2P - R2) * sizeof(float), ETW_FEATS, st);
+            if (e != cudaSuccess) return fail(PCVAE_ECUDA, "enc_fwd_tc: cudaMemset2DAsync: %s", cudaGetErrorString(e));
+        }
+    }
+    return enc_tc_go(tc::k_enc_fwd_tc, a, tc::enc_fwd_tc_smem(a.L.D), grid, st, "enc_fwd_tc");
+}
+
+int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st) {
+    if (a.B > 0)
+        if (int rc = enc_tc_go(tc::k_enc_bwd_tc, a, tc::enc_bwd_tc_smem(), 2 * grid, st, "enc_bwd_tc")) return rc;
+    const int D = a.L.D;
+    const WgradJob jobs[3] = {{a.tw.dp1T, H1, a.tw.inT, D, (D + 16) & ~15, a.L.W1, a.L.b1},
+                              {a.tw.dp2T, H2, a.tw.h1T, H1, 112, a.L.W2, a.L.b2},
+                              {a.tw.dp3T, LAT2, a.tw.h2T, H2, 64, a.L.W3, a.L.b3}};
+    return wgrad_tc_launch(jobs, 3, a.tw.R2P, a.gp, a.L.total, grid, st);
+}
+
+}  // namespace pcvae

@@ -1,0 +1,137 @@
+// Row-tile scaffolding shared by the tcgen05 training kernels (decoder: pcvae_dec_tc.cu, encoder: pcvae_enc_tc.cu):
+// 128-row tiles, 512 threads = 4 TMEM lane quarters x 4 column groups, activation operands in TENSOR MEMORY as
+// hi / lo tf32 images, accumulators in TMEM, weights in shared memory as K-major no-swizzle core-matrix images.
+//
+// TMEM columns (all 512):  RA [0,224): 112 hi + 112 lo    RB [224,336): 56 hi + 56 lo
+//                          ACC1 [336,448)                 ACC2 [448,512)
+#pragma once
+#include "pcvae_tc.cuh"
+
+namespace pcvae {
+namespace tc {
+
+constexpr int ROWS = 128;
+constexpr int RA_HI = 0, RA_LO = 112, RB_HI = 224, RB_LO = 280, ACC1 = 336, ACC2 = 448;
+constexpr int DEC_ISSUER_WARP = 4;
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 3xTF32 product: activation operand in TMEM (hi at a_hi, lo at a_lo), weight image (K-major) in shared memory;
+// a k-step (8 tf32) is two 16-byte chunks of the image
+__device__ __forceinline__ void issue_3x(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint64_t b_step,
+                                         int ksteps, uint32_t idesc) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+        mma_tf32_ts(acc, a_lo + 8 * ks, b_hi + ks * b_step, idesc, ks > 0);
+        mma_tf32_ts(acc, a_hi + 8 * ks, b_lo + ks * b_step, idesc, 1);
+        mma_tf32_ts(acc, a_hi + 8 * ks, b_hi + ks * b_step, idesc, 1);
+    }
+}
+
+// four mask entries: uint8 -> 0/1; float32 -> 0/1 (RAW = false) or the stored values (RAW = true: the encoders multiply
+// x by the mask as it is, VAE.py:388)
+template <bool RAW = false>
+__device__ __forceinline__ void load_mask4(const void* m, long gi, int kind, float* o) {
+    if (kind == PCVAE_MASK_U8) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(static_cast<const unsigned char*>(m) + gi);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = ((w >> (8 * j)) & 0xFFu) ? 1.f : 0.f;
+    } else {
+        const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(m) + gi);
+        if (RAW) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+        else { o[0] = v.x != 0.f ? 1.f : 0.f; o[1] = v.y != 0.f ? 1.f : 0.f; o[2] = v.z != 0.f ? 1.f : 0.f; o[3] = v.w != 0.f ? 1.f : 0.f; }
+    }
+}
+
+// hi / lo image of an augmented weight matrix; w(n, k) supplies element (row n, column k)
+template <typename F>
+__device__ __forceinline__ void build_image(float* hi, float* lo, int chunks, int nrows, int tid, F w) {
+    for (int i = tid; i < chunks * nrows * 4; i += NT) {
+        const int c = i / (nrows * 4), n = (i >> 2) % nrows, k = 4 * c + (i & 3);
+        const float v = w(n, k);
+        hi[i] = v;
+        lo[i] = tf32_lo(v);
+    }
+}
+
+struct TileCtx {
+    uint32_t tmem, lane_addr, ph;
+    int q, cg, row, c28, c16;
+};
+
+// barrier + (one elected lane) MMA issue + commit; every thread then waits for the batch
+template <typename Issue>
+__device__ __forceinline__ void run_mma(TileCtx& cx, uint64_t* bar, int warp, Issue&& issue) {
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == DEC_ISSUER_WARP) {
+        tc_fence_after();
+        if (elect_one()) {
+            issue();
+            mma_commit(bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(bar, cx.ph);
+    cx.ph ^= 1;
+    tc_fence_after();
+}
+
+__device__ __forceinline__ void tc_setup(TileCtx& cx, uint64_t* bar, uint32_t* slot, int tid, uint32_t ncols = 512) {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cx.tmem = *slot;
+    cx.ph = 0;
+    cx.q = warp & 3;
+    cx.cg = warp >> 2;
+    cx.row = 32 * cx.q + lane;
+    cx.lane_addr = cx.tmem + ((uint32_t)(32 * cx.q) << 16);
+    cx.c28 = 28 * cx.cg;
+    cx.c16 = 16 * cx.cg;
+}
+
+__device__ __forceinline__ void tc_teardown(const TileCtx& cx, int tid, uint32_t ncols = 512) {
+    tc_fence_before();
+    __syncthreads();
+    if ((tid >> 5) == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"(ncols));
+    }
+}
+
+// 28 accumulator columns of this thread, in parts of 16 / 8 / 4
+__device__ __forceinline__ void ld_part(uint32_t addr, int part, float* v) {
+    if (part == 0) tmem_ld16(addr, v);
+    else if (part == 1) tmem_ld8(addr + 16, v);
+    else tmem_ld4(addr + 24, v);
+}
+__device__ __forceinline__ void st_part(uint32_t addr, int part, const float* v) {
+    if (part == 0) tmem_st16(addr, v);
+    else if (part == 1) tmem_st8(addr + 16, v);
+    else tmem_st4(addr + 24, v);
+}
+
+}  // namespace tc
+}  // namespace pcvae

@@ -74,20 +74,6 @@ void pnp_tables_launch(const Layout& L, const float* theta, float* ac, cudaStrea
 // ====================================================================================
 // Encoder forward
 // ====================================================================================
-struct EncFwdArgs {
-    Layout L;
-    int B, nbr, mask_kind;
-    const float* theta;
-    const float* x;
-    const void* mask[2];
-    const float* eps[2];
-    float* mean[2];
-    float* logvar[2];
-    float* z[2];
-    float* act_ws;
-    const float* ac;
-};
-
 template <int FAM, int TM>
 __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -196,22 +182,6 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
 // ====================================================================================
 // Encoder backward
 // ====================================================================================
-struct EncBwdArgs {
-    Layout L;
-    int B, nbr, mask_kind;
-    const float* theta;
-    const float* x;
-    const void* mask[2];
-    const float* act_ws;
-    const float* d_mean[2];
-    const float* d_logvar[2];
-    const float* ac;
-    float* gp;   // [grid][P]
-    const float* d_z[2];
-    const float* eps[2];
-    const float* logvar[2];
-};
-
 template <int FAM, int TM>
 __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -818,6 +788,13 @@ int pcvae_enc_fwd(const pcvae_enc_fwd_params* p, void* stream) {
     a.L = L; a.B = p->rows; a.nbr = p->n_branch; a.mask_kind = p->mask_kind; a.theta = p->theta; a.x = p->x;
     for (int b = 0; b < 2; ++b) { a.mask[b] = p->mask[b]; a.eps[b] = p->eps[b]; a.mean[b] = p->mean[b]; a.logvar[b] = p->logvar[b]; a.z[b] = p->z[b]; }
     a.act_ws = p->act_ws; a.ac = p->pnp_ac;
+    if (g_train_tc && p->tc_workspace && enc_tc_supported(L)) {
+        const long need = etw_floats(p->rows, p->n_branch);
+        if (p->tc_workspace_floats < need)
+            return fail(PCVAE_EINVAL, "enc_fwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
+        enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        return enc_fwd_tc_launch(a, grid, st);
+    }
     if (L.fam == PCVAE_FAMILY_PNP) {
         if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_fwd: PNP family needs pnp_ac workspace");
         pnp_tables_launch(L, p->theta, p->pnp_ac, st);
@@ -834,7 +811,8 @@ int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
     if (int rc = device_ok(&grid)) return rc;
     if (p->rows < 0 || p->n_branch < 1 || p->n_branch > 2) return fail(PCVAE_EINVAL, "enc_bwd: bad rows/n_branch");
     if (!p->theta || !p->grad_partials) return fail(PCVAE_EINVAL, "enc_bwd: null theta/grad_partials");
-    if (p->rows > 0 && (!p->x || !p->act_ws)) return fail(PCVAE_EINVAL, "enc_bwd: null x/act_ws");
+    const bool use_tc = g_train_tc && p->tc_workspace && p->rows > 0 && enc_tc_supported(L);
+    if (p->rows > 0 && (!p->x || (!p->act_ws && !use_tc))) return fail(PCVAE_EINVAL, "enc_bwd: null x/act_ws");
     for (int b = 0; b < p->n_branch && p->rows > 0; ++b)
         if (!p->mask[b] || !p->d_mean[b] || !p->d_logvar[b]) return fail(PCVAE_EINVAL, "enc_bwd: null mask/d_mean/d_logvar for branch %d", b);
     cudaStream_t st = (cudaStream_t)stream;
@@ -846,6 +824,13 @@ int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
         if (p->d_z[b] && p->eps[b] && !p->logvar[b]) return fail(PCVAE_EINVAL, "enc_bwd: d_z and eps given without logvar for branch %d", b);
     }
     a.act_ws = p->act_ws; a.ac = p->pnp_ac; a.gp = p->grad_partials;
+    if (use_tc) {
+        const long need = etw_floats(p->rows, p->n_branch);
+        if (p->tc_workspace_floats < need)
+            return fail(PCVAE_EINVAL, "enc_bwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
+        enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        return enc_bwd_tc_launch(a, grid, st);
+    }
     if (L.fam == PCVAE_FAMILY_PNP) {
         if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_bwd: PNP family needs pnp_ac tables");
         return launch(k_enc_bwd<PCVAE_FAMILY_PNP, TM_TRAIN>, enc_bwd_smem(L), grid, st, "enc_bwd", a);
@@ -906,6 +891,12 @@ long pcvae_dec_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch)
     Layout L;
     if (!m || !make_layout(m, &L) || !dec_tc_supported(L) || rows < 0 || n_branch < 1) return 0;
     return tcw_floats(rows, n_branch);
+}
+
+long pcvae_enc_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch) {
+    Layout L;
+    if (!g_train_tc || !m || !make_layout(m, &L) || !enc_tc_supported(L) || rows < 1 || n_branch < 1) return 0;
+    return etw_floats(rows, n_branch);
 }
 
 int pcvae_set_train_tensor_cores(int enable) {

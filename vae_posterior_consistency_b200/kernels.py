@@ -133,13 +133,24 @@ class Engine:
         mean, logvar = mk(), mk()
         z = mk() if want_z else [None] * nb
         eps = [None] * nb if eps is None else [None if e is None else _f32(e) for e in eps]
-        ws = self.act_ws(B, nb) if save else None
+        # what the backward needs: the tcgen05 encoder's scratch when this shape has one, else the FFMA kernel's
+        # saved activations; `ws` is an opaque (act_ws, tc_workspace) handle for enc_bwd
+        act, tcw = None, None
+        if save and B > 0:
+            n = self.lib.pcvae_enc_tc_workspace_floats(C.byref(self.model), B, nb)   # 0: no tensor-core encoder here
+            if n > 0:
+                tcw = torch.empty(n, device=x.device, dtype=torch.float32)
+            else:
+                act = self.act_ws(B, nb)
+        elif save:
+            act = self.act_ws(B, nb)
         p = L.EncFwdParams(model=self.model, rows=B, n_branch=nb, mask_kind=kind, theta=_p(theta), x=_p(x),
                            mask=_pair(masks), eps=_pair(eps), mean=_pair(mean), logvar=_pair(logvar), z=_pair(z),
-                           act_ws=_p(ws), pnp_ac=_p(self.pnp_ac()))
+                           act_ws=_p(act), pnp_ac=_p(self.pnp_ac()),
+                           tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel())
         with torch.cuda.device(x.device):
             L.check(self.lib.pcvae_enc_fwd(C.byref(p), _stream()), "pcvae_enc_fwd")
-        return mean, logvar, z, ws
+        return mean, logvar, z, ((act, tcw) if save else None)
 
     def enc_bwd(self, theta, x, masks, ws, d_mean, d_logvar, d_z=None, eps=None, logvar=None):
         x = _f32(x)
@@ -150,10 +161,12 @@ class Engine:
         d_logvar = [_f32(t) for t in d_logvar]
         opt = lambda ts: [None] * nb if ts is None else [None if t is None else _f32(t) for t in ts]
         d_z, eps, logvar = opt(d_z), opt(eps), opt(logvar)
+        act, tcw = ws
         p = L.EncBwdParams(model=self.model, rows=x.shape[0], n_branch=nb, mask_kind=kind, theta=_p(theta),
-                           x=_p(x), mask=_pair(masks), act_ws=_p(ws), d_mean=_pair(d_mean),
+                           x=_p(x), mask=_pair(masks), act_ws=_p(act), d_mean=_pair(d_mean),
                            d_logvar=_pair(d_logvar), pnp_ac=_p(self.pnp_ac()), grad_partials=_p(gp),
-                           d_z=_pair(d_z), eps=_pair(eps), logvar=_pair(logvar))
+                           d_z=_pair(d_z), eps=_pair(eps), logvar=_pair(logvar),
+                           tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel())
         with torch.cuda.device(x.device):
             L.check(self.lib.pcvae_enc_bwd(C.byref(p), _stream()), "pcvae_enc_bwd")
         return gp

@@ -27,7 +27,7 @@ SYMBOLS = [
     "pcvae_reward_workspace_bytes", "pcvae_reward_chain", "pcvae_ffma_probe", "pcvae_gather_rows",
     "pcvae_draw_submask", "pcvae_draw_normal", "pcvae_dense_fwd", "pcvae_dense_bwd", "pcvae_mnar_sample_z",
     "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss", "pcvae_set_reward_tensor_cores",
-    "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores",
+    "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores", "pcvae_enc_tc_workspace_floats",
 ]
 
 
@@ -45,14 +45,16 @@ _P2 = C.c_void_p * 2
 class EncFwdParams(C.Structure):
     _fields_ = [("model", Model), ("rows", C.c_int), ("n_branch", C.c_int), ("mask_kind", C.c_int),
                 ("theta", C.c_void_p), ("x", C.c_void_p), ("mask", _P2), ("eps", _P2), ("mean", _P2),
-                ("logvar", _P2), ("z", _P2), ("act_ws", C.c_void_p), ("pnp_ac", C.c_void_p)]
+                ("logvar", _P2), ("z", _P2), ("act_ws", C.c_void_p), ("pnp_ac", C.c_void_p),
+                ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long)]
 
 
 class EncBwdParams(C.Structure):
     _fields_ = [("model", Model), ("rows", C.c_int), ("n_branch", C.c_int), ("mask_kind", C.c_int),
                 ("theta", C.c_void_p), ("x", C.c_void_p), ("mask", _P2), ("act_ws", C.c_void_p),
                 ("d_mean", _P2), ("d_logvar", _P2), ("pnp_ac", C.c_void_p), ("grad_partials", C.c_void_p),
-                ("d_z", _P2), ("eps", _P2), ("logvar", _P2)]
+                ("d_z", _P2), ("eps", _P2), ("logvar", _P2),
+                ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long)]
 
 
 class DecParams(C.Structure):
@@ -126,6 +128,8 @@ def load():
     lib.pcvae_decoder_offset.argtypes = [C.POINTER(Model)]
     lib.pcvae_enc_act_ws_floats.restype = C.c_size_t
     lib.pcvae_enc_act_ws_floats.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
+    lib.pcvae_enc_tc_workspace_floats.restype = C.c_long
+    lib.pcvae_enc_tc_workspace_floats.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
     lib.pcvae_enc_fwd.argtypes = [C.POINTER(EncFwdParams), C.c_void_p]
     lib.pcvae_enc_bwd.argtypes = [C.POINTER(EncBwdParams), C.c_void_p]
     lib.pcvae_dec.argtypes = [C.POINTER(DecParams), C.c_void_p]
