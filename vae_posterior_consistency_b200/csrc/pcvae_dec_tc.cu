@@ -64,21 +64,11 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
     float* W6l = W6h + F6_C * N6 * 4;
     const float* th = a.theta;
     const Layout L = a.L;
-    build_image(W4h, W4l, F4_C, F4_N, tid, [&](int n, int k) {
-        if (n < G1 && k < LAT) return th[L.W4 + n * LAT + k];
-        if (n < G1 && k == LAT) return th[L.b4 + n];
-        return (n == G1 && k == LAT) ? 1.0f : 0.0f;            // constant-1 output -> bias column of layer 5
-    });
-    build_image(W5h, W5l, F5_C, F5_N, tid, [&](int n, int k) {
-        if (n < G2 && k < G1) return th[L.W5 + n * G1 + k];
-        if (n < G2 && k == G1) return th[L.b5 + n];
-        return (n == G2 && k == G1) ? 1.0f : 0.0f;            // constant-1 output -> bias column of layer 6
-    });
-    build_image(W6h, W6l, F6_C, N6, tid, [&](int n, int k) {
-        if (n < D && k < G2) return th[L.W6 + n * G2 + k];
-        if (n < D && k == G2) return th[L.b6 + n];
-        return 0.0f;
-    });
+    zero_images(smem, 2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * N6 * 4), tid);
+    __syncthreads();
+    image_linear(W4h, W4l, F4_N, th + L.W4, th + L.b4, G1, LAT, true, tid);      // constant-1 output -> bias column of layer 5
+    image_linear(W5h, W5l, F5_N, th + L.W5, th + L.b5, G2, G1, true, tid);       // constant-1 output -> bias column of layer 6
+    image_linear(W6h, W6l, N6, th + L.W6, th + L.b6, D, G2, false, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
@@ -99,7 +89,6 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
     const float log_scale = logf(scale);
     const float alpha = a.alpha, ls = a.loss_scale;
     float s_req = 0.f, s_rep = 0.f, s_red = 0.f, s_imp = 0.f, s_sse = 0.f;
-    const long R2P = a.R2P;
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
     const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
@@ -116,7 +105,12 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
             }
         }
         for (int br = 0; br < a.nbr; ++br) {
-            const long wrow = (long)br * a.B + grow;          // column in the feature-major scratch
+            const long vt = (long)br * ntiles + t;            // tile of the feature-major scratch: [vt][feature][128 rows]
+            float* zT = a.ws_zT + vt * (TCW_Z * ROWS) + row;
+            float* h4T = a.ws_h4T + vt * (TCW_H4 * ROWS) + row;
+            float* h5T = a.ws_h5T + vt * (TCW_H5 * ROWS) + row;
+            float* dp6T = a.ws_dp6T + vt * (TCW_H5 * ROWS) + row;
+            unsigned* reluT = a.ws_relu + (vt * ROWS + row) * 8;
             // ---- z | 1 -> RA, HBM ----
             if (cg == 0) {
                 float v[16], lo[16];
@@ -132,10 +126,8 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                 for (int j = 0; j < 16; ++j) lo[j] = tf32_lo(v[j]);
                 tmem_st16(lane_addr + RA_HI, v);
                 tmem_st16(lane_addr + RA_HI + 16, lo);
-                if (ok) {
 #pragma unroll
-                    for (int j = 0; j < TCW_Z; ++j) a.ws_zT[j * R2P + wrow] = v[j];
-                }
+                for (int j = 0; j < TCW_Z; ++j) zT[j * ROWS] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_HI + 16, f4h, f4l, fs4, F4_C / 2, idF4); });
 
@@ -151,11 +143,9 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                 }
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
-                if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c16 + j < TCW_H4) a.ws_h4T[(c16 + j) * R2P + wrow] = v[j];
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (c16 + j < TCW_H4) h4T[(c16 + j) * ROWS] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, f5h, f5l, fs5, F5_C / 2, idF5); });
 
@@ -174,17 +164,36 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j < TCW_H5) a.ws_h5T[(c28 + j0 + j) * R2P + wrow] = v[j];
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt && c28 + j0 + j < TCW_H5) h5T[(c28 + j0 + j) * ROWS] = v[j];
+            }
+            reluT[cg] = m5;
+            reluT[4 + cg] = m4;
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, f6h, f6l, fs6, F6_C / 2, idF6); });
+            // while the tensor pipe runs F6: this thread's 28 entries of x and of the two masks (as bits)
+            float xr[28];
+            uint32_t mb = 0, mpb = 0;
+#pragma unroll
+            for (int g = 0; g < 7; ++g) {
+                const int c = c28 + 4 * g;
+                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok && c < D) {
+                    const long gi = (long)grow * D + c;
+                    x4 = *reinterpret_cast<const float4*>(a.x + gi);
+                    float m[4];
+                    load_mask4(a.mask[0], gi, a.mask_kind, m);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mb |= (m[j] != 0.f ? 1u : 0u) << (4 * g + j);
+                    if (a.nbr > 1) {
+                        load_mask4(a.mask[1], gi, a.mask_kind, m);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mpb |= (m[j] != 0.f ? 1u : 0u) << (4 * g + j);
+                    }
                 }
+                xr[4 * g] = x4.x; xr[4 * g + 1] = x4.y; xr[4 * g + 2] = x4.z; xr[4 * g + 3] = x4.w;
             }
-            if (ok) {
-                a.ws_relu[wrow * 8 + cg] = m5;
-                a.ws_relu[wrow * 8 + 4 + cg] = m4;
-            }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, f6h, f6l, fs6, F6_C / 2, idF6); });
+            mma_wait(cx, &bar_s);
 
             // ---- x_hat = sigmoid(acc6): loss terms, dL/d(pre-sigmoid) -> HBM ----
             {
@@ -200,35 +209,32 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                         const int c = c28 + j0 + 4 * g;
                         float dpre[4] = {0.f, 0.f, 0.f, 0.f};
                         if (ok && c < D) {
-                            const long gi = (long)grow * D + c;
-                            const float4 xv4 = *reinterpret_cast<const float4*>(a.x + gi);
-                            const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
-                            float m[4], mp[4] = {0.f, 0.f, 0.f, 0.f}, xh[4];
-                            load_mask4(a.mask[0], gi, a.mask_kind, m);
-                            if (a.nbr > 1) load_mask4(a.mask[1], gi, a.mask_kind, mp);
+                            float xh[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
+                                const int e = j0 + 4 * g + j;
+                                const float xv = xr[e], m = (float)((mb >> e) & 1u), mp = (float)((mpb >> e) & 1u);
                                 xh[j] = 1.0f / (1.0f + expf(-v[4 * g + j]));
-                                const float diff = xv[j] - xh[j];
+                                const float diff = xv - xh[j];
                                 const float nll = fmaf(diff * diff, inv2var, log_scale);
                                 float coef;
                                 if (br == 0) {
-                                    s_req += m[j] * nll;
-                                    s_red += m[j] * (1.f - mp[j]) * nll;
-                                    s_imp += (1.f - m[j]) * nll;
-                                    s_sse += (1.f - m[j]) * diff * diff;
-                                    coef = (1.f - alpha) * m[j] + alpha * m[j] * (1.f - mp[j]);
+                                    s_req += m * nll;
+                                    s_red += m * (1.f - mp) * nll;
+                                    s_imp += (1.f - m) * nll;
+                                    s_sse += (1.f - m) * diff * diff;
+                                    coef = (1.f - alpha) * m + alpha * m * (1.f - mp);
                                 } else {
-                                    s_rep += mp[j] * nll;
-                                    coef = alpha * mp[j];
+                                    s_rep += mp * nll;
+                                    coef = alpha * mp;
                                 }
-                                dpre[j] = coef * (xh[j] - xv[j]) * inv_var * ls * xh[j] * (1.f - xh[j]);
+                                dpre[j] = coef * (xh[j] - xv) * inv_var * ls * xh[j] * (1.f - xh[j]);
                             }
-                            if (xo) *reinterpret_cast<float4*>(xo + gi) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+                            if (xo) *reinterpret_cast<float4*>(xo + (long)grow * D + c) = make_float4(xh[0], xh[1], xh[2], xh[3]);
                         }
-                        if (ok && c < TCW_H5) {
+                        if (c < TCW_H5) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) a.ws_dp6T[(c + j) * R2P + wrow] = dpre[j];
+                            for (int j = 0; j < 4; ++j) dp6T[(c + j) * ROWS] = dpre[j];
                         }
                     }
                 }
@@ -272,10 +278,11 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     float* T4l = T4h + X4_C * X4_N * 4;
     const float* th = a.theta;
     const Layout L = a.L;
-    // transposed weights: image row = layer INPUT index, image column (reduction) = layer OUTPUT index
-    build_image(T6h, T6l, X6_C, X6_N, tid, [&](int k, int d) { return (k < G2 && d < D) ? th[L.W6 + d * G2 + k] : 0.0f; });
-    build_image(T5h, T5l, X5_C, X5_N, tid, [&](int k, int n) { return (k < G1 && n < G2) ? th[L.W5 + n * G1 + k] : 0.0f; });
-    build_image(T4h, T4l, X4_C, X4_N, tid, [&](int k, int n) { return (k < LAT && n < G1) ? th[L.W4 + n * LAT + k] : 0.0f; });
+    zero_images(smem, 2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4), tid);
+    __syncthreads();
+    image_linear_T(T6h, T6l, X6_N, th + L.W6, D, G2, tid);
+    image_linear_T(T5h, T5l, X5_N, th + L.W5, G2, G1, tid);
+    image_linear_T(T4h, T4l, X4_N, th + L.W4, G1, LAT, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
@@ -290,7 +297,6 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
 
     const float alpha = a.alpha, ls = a.loss_scale;
     float s_klq = 0.f, s_klp = 0.f, s_klr = 0.f;
-    const long R2P = a.R2P;
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -298,9 +304,13 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
         const int grow = row0 + row;
         const bool ok = grow < a.B;
         for (int br = 0; br < a.nbr; ++br) {
-            const long wrow = (long)br * a.B + grow;
+            const long vt = (long)br * ntiles + t;
+            const float* dp6T = a.ws_dp6T + vt * (TCW_H5 * ROWS) + row;
+            float* dp5T = a.ws_dp5T + vt * (TCW_H5 * ROWS) + row;
+            float* dp4T = a.ws_dp4T + vt * (TCW_H4 * ROWS) + row;
+            const unsigned* reluT = a.ws_relu + (vt * ROWS + row) * 8;
             uint32_t m5 = 0, m4 = 0;
-            if (ok) { m5 = a.ws_relu[wrow * 8 + cg]; m4 = a.ws_relu[wrow * 8 + 4 + cg]; }
+            if (ok) { m5 = reluT[cg]; m4 = reluT[4 + cg]; }
             // ---- dpre6 (HBM) -> RA ----
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
                         const int c = c28 + j0 + j;
-                        v[j] = (ok && c < TCW_H5) ? a.ws_dp6T[c * R2P + wrow] : 0.f;
+                        v[j] = (ok && c < TCW_H5) ? dp6T[c * ROWS] : 0.f;
                         lo[j] = tf32_lo(v[j]);
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
@@ -332,11 +342,9 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j < TCW_H5) a.ws_dp5T[(c28 + j0 + j) * R2P + wrow] = v[j];
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt && c28 + j0 + j < TCW_H5) dp5T[(c28 + j0 + j) * ROWS] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, x5h, x5l, xs5, X5_C / 2, idX5); });
 
@@ -351,11 +359,9 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 }
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
-                if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c16 + j < TCW_H4) a.ws_dp4T[(c16 + j) * R2P + wrow] = v[j];
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (c16 + j < TCW_H4) dp4T[(c16 + j) * ROWS] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, x4h, x4l, xs4, X4_C / 2, idX4); });
 
@@ -447,17 +453,12 @@ static int tc_launch(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
 }
 
 int dec_tc_launch(const DecArgs& a, int grid, cudaStream_t st) {
-    const long R2 = (long)a.nbr * a.B;
-    if (a.R2P > R2) {   // zero the padding columns [R2, R2P) of every feature row (read by the weight-gradient slabs)
-        cudaError_t e = cudaMemset2DAsync(a.ws_zT + R2, a.R2P * sizeof(float), 0, (a.R2P - R2) * sizeof(float), TCW_FEATS, st);
-        if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dec_tc: cudaMemset2DAsync: %s", cudaGetErrorString(e));
-    }
     if (int rc = tc_launch(tc::k_dec_fwd_tc, a, tc::dec_fwd_tc_smem(a.L.D), grid, st, "dec_fwd_tc")) return rc;
     if (int rc = tc_launch(tc::k_dec_bwd_tc, a, tc::dec_bwd_tc_smem(), grid, st, "dec_bwd_tc")) return rc;
-    const WgradJob jobs[3] = {{a.ws_dp6T, a.L.D, a.ws_h5T, G2, 112, a.L.W6, a.L.b6},
-                              {a.ws_dp5T, G2, a.ws_h4T, G1, 64, a.L.W5, a.L.b5},
-                              {a.ws_dp4T, G1, a.ws_zT, LAT, 16, a.L.W4, a.L.b4}};
-    return wgrad_tc_launch(jobs, 3, a.R2P, a.gp, a.L.total, grid, st);
+    const WgradJob jobs[3] = {{a.ws_dp6T, TCW_H5, a.L.D, a.ws_h5T, TCW_H5, G2, 112, a.L.W6, a.L.b6},
+                              {a.ws_dp5T, TCW_H5, G2, a.ws_h4T, TCW_H4, G1, 64, a.L.W5, a.L.b5},
+                              {a.ws_dp4T, TCW_H4, G1, a.ws_zT, TCW_Z, LAT, 16, a.L.W4, a.L.b4}};
+    return wgrad_tc_launch(jobs, 3, a.nvt, a.gp, a.L.total, grid, st);
 }
 
 }  // namespace pcvae

@@ -44,21 +44,11 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
     float* W3l = W3h + E3_C * E3_N * 4;
     const float* th = a.theta;
     const Layout L = a.L;
-    build_image(W1h, W1l, C1, E1_N, tid, [&](int n, int k) {
-        if (n < H1 && k < D) return th[L.W1 + n * D + k];
-        if (n < H1 && k == D) return th[L.b1 + n];
-        return (n == H1 && k == D) ? 1.0f : 0.0f;             // constant-1 output -> bias column of layer 2
-    });
-    build_image(W2h, W2l, E2_C, E2_N, tid, [&](int n, int k) {
-        if (n < H2 && k < H1) return th[L.W2 + n * H1 + k];
-        if (n < H2 && k == H1) return th[L.b2 + n];
-        return (n == H2 && k == H1) ? 1.0f : 0.0f;            // constant-1 output -> bias column of layer 3
-    });
-    build_image(W3h, W3l, E3_C, E3_N, tid, [&](int n, int k) {
-        if (n < LAT2 && k < H2) return th[L.W3 + n * H2 + k];
-        if (n < LAT2 && k == H2) return th[L.b3 + n];
-        return 0.0f;
-    });
+    zero_images(smem, 2 * (C1 * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4), tid);
+    __syncthreads();
+    image_linear(W1h, W1l, E1_N, th + L.W1, th + L.b1, H1, D, true, tid);        // constant-1 output -> bias column of layer 2
+    image_linear(W2h, W2l, E2_N, th + L.W2, th + L.b2, H2, H1, true, tid);       // constant-1 output -> bias column of layer 3
+    image_linear(W3h, W3l, E3_N, th + L.W3, th + L.b3, LAT2, H2, false, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
@@ -71,7 +61,6 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
     const uint64_t es1 = (2 * cs1) >> 4, es2 = (2 * cs2) >> 4, es3 = (2 * cs3) >> 4;
     const uint32_t idE1 = make_idesc(ROWS, E1_N), idE2 = make_idesc(ROWS, E2_N), idE3 = make_idesc(ROWS, E3_N);
     const EncTcWs tw = a.tw;
-    const long R2P = tw.R2P;
     const bool save = tw.inT != nullptr;
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
@@ -88,7 +77,11 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
             }
         }
         for (int br = 0; br < a.nbr; ++br) {
-            const long wrow = (long)br * a.B + grow;          // column in the feature-major scratch
+            const long vt = (long)br * ntiles + t;            // tile of the feature-major scratch: [vt][feature][128 rows]
+            float* inT = tw.inT + vt * (ETW_IN * ROWS) + row;
+            float* h1T = tw.h1T + vt * (ETW_H1 * ROWS) + row;
+            float* h2T = tw.h2T + vt * (ETW_H2 * ROWS) + row;
+            unsigned* reluT = tw.relu + (vt * ROWS + row) * 8;
             // ---- x * mask | 1 -> RA, HBM ----
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
@@ -115,10 +108,10 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                 }
                 st_part(lane_addr + RA_HI + c28, part, v);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                if (ok && save) {
+                if (save) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j <= D) tw.inT[(c28 + j0 + j) * R2P + wrow] = v[j];
+                        if (j < cnt && c28 + j0 + j <= D) inT[(c28 + j0 + j) * ROWS] = v[j];
                 }
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
@@ -138,10 +131,10 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                if (ok && save) {
+                if (save) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j < ETW_H1) tw.h1T[(c28 + j0 + j) * R2P + wrow] = v[j];
+                        if (j < cnt && c28 + j0 + j < ETW_H1) h1T[(c28 + j0 + j) * ROWS] = v[j];
                 }
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, e2h, e2l, es2, E2_C / 2, idE2); });
@@ -158,12 +151,12 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                 }
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
-                if (ok && save) {
+                if (save) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c16 + j < ETW_H2) tw.h2T[(c16 + j) * R2P + wrow] = v[j];
-                    tw.relu[wrow * 8 + cg] = m1;
-                    tw.relu[wrow * 8 + 4 + cg] = m2;
+                        if (c16 + j < ETW_H2) h2T[(c16 + j) * ROWS] = v[j];
+                    reluT[cg] = m1;
+                    reluT[4 + cg] = m2;
                 }
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, e3h, e3l, es3, E3_C / 2, idE3); });
@@ -218,9 +211,10 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
     float* T2l = T2h + Y2_C * Y2_N * 4;
     const float* th = a.theta;
     const Layout L = a.L;
-    // transposed weights: image row = layer INPUT index, image column (reduction) = layer OUTPUT index
-    build_image(T3h, T3l, Y3_C, Y3_N, tid, [&](int k, int n) { return (k < H2 && n < LAT2) ? th[L.W3 + n * H2 + k] : 0.0f; });
-    build_image(T2h, T2l, Y2_C, Y2_N, tid, [&](int k, int n) { return (k < H1 && n < H2) ? th[L.W2 + n * H1 + k] : 0.0f; });
+    zero_images(smem, 2 * (Y3_C * Y3_N * 4 + Y2_C * Y2_N * 4), tid);
+    __syncthreads();
+    image_linear_T(T3h, T3l, Y3_N, th + L.W3, LAT2, H2, tid);
+    image_linear_T(T2h, T2l, Y2_N, th + L.W2, H2, H1, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid, B_COLS);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
@@ -232,7 +226,6 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
     const uint64_t ys3 = (2 * cs3) >> 4, ys2 = (2 * cs2) >> 4;
     const uint32_t idY3 = make_idesc(ROWS, Y3_N), idY2 = make_idesc(ROWS, Y2_N);
     const EncTcWs tw = a.tw;
-    const long R2P = tw.R2P;
 
     const int nvt = ((a.B + ROWS - 1) / ROWS) * a.nbr;
     const int ntiles = (a.B + ROWS - 1) / ROWS;
@@ -240,9 +233,12 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
         const int br = vt / ntiles, t = vt - br * ntiles;
         const int grow = t * ROWS + row;
         const bool ok = grow < a.B;
-        const long wrow = (long)br * a.B + grow;
+        float* dp1T = tw.dp1T + (long)vt * (ETW_H1 * ROWS) + row;      // scratch tile vt: [feature][128 rows]
+        float* dp2T = tw.dp2T + (long)vt * (ETW_H2 * ROWS) + row;
+        float* dp3T = tw.dp3T + (long)vt * (ETW_DP3 * ROWS) + row;
+        const unsigned* reluT = tw.relu + ((long)vt * ROWS + row) * 8;
         uint32_t m1 = 0, m2 = 0;
-        if (ok) { m1 = tw.relu[wrow * 8 + cg]; m2 = tw.relu[wrow * 8 + 4 + cg]; }
+        if (ok) { m1 = reluT[cg]; m2 = reluT[4 + cg]; }
         // ---- dpre3 = (d_mean | d_logvar) -> TMEM, HBM ----
         if (cg == 0) {
             float v[24], lo[24];
@@ -272,10 +268,8 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
             tmem_st8(lane_addr + B_D3H + 16, v + 16);
             tmem_st16(lane_addr + B_D3L, lo);
             tmem_st8(lane_addr + B_D3L + 16, lo + 16);
-            if (ok) {
 #pragma unroll
-                for (int j = 0; j < LAT2; ++j) tw.dp3T[j * R2P + wrow] = v[j];
-            }
+            for (int j = 0; j < LAT2; ++j) dp3T[j * ROWS] = v[j];
         }
         run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC2, tmem + B_D3H, tmem + B_D3L, y3h, y3l, ys3, Y3_C / 2, idY3); });
 
@@ -290,11 +284,9 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
             }
             if (cg < 3) { tmem_st16(lane_addr + B_RBH + c16, v); tmem_st16(lane_addr + B_RBL + c16, lo); }
             else { tmem_st8(lane_addr + B_RBH + c16, v); tmem_st8(lane_addr + B_RBL + c16, lo); }
-            if (ok) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c16 + j < ETW_H2) tw.dp2T[(c16 + j) * R2P + wrow] = v[j];
-            }
+            for (int j = 0; j < 16; ++j)
+                if (c16 + j < ETW_H2) dp2T[(c16 + j) * ROWS] = v[j];
         }
         run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, y2h, y2l, ys2, Y2_C / 2, idY2); });
 
@@ -304,12 +296,10 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
             const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
             float v[16];
             ld_part(lane_addr + B_AC1 + c28, part, v);
-            if (ok) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < cnt && c28 + j0 + j < ETW_H1)
-                        tw.dp1T[(c28 + j0 + j) * R2P + wrow] = (((m1 >> (j0 + j)) & 1u) && c28 + j0 + j < H1) ? v[j] : 0.f;
-            }
+            for (int j = 0; j < 16; ++j)
+                if (j < cnt && c28 + j0 + j < ETW_H1)
+                    dp1T[(c28 + j0 + j) * ROWS] = (((m1 >> (j0 + j)) & 1u) && c28 + j0 + j < H1) ? v[j] : 0.f;
         }
         tc_fence_before();
         __syncthreads();            // the X2 accumulator aliases the columns the next tile writes first
@@ -329,14 +319,14 @@ static size_t enc_bwd_tc_smem() { return (size_t)2 * (Y3_C * Y3_N * 4 + Y2_C * Y
 bool enc_tc_supported(const Layout& L) { return L.fam == PCVAE_FAMILY_MLP && L.D % 4 == 0 && L.D >= 4 && L.D <= 100; }
 
 void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw) {
-    const long R2P = tcw_r2p(rows, nbr);
-    tw->R2P = R2P;
-    tw->inT = w;  w += R2P * ETW_IN;
-    tw->h1T = w;  w += R2P * ETW_H1;
-    tw->h2T = w;  w += R2P * ETW_H2;
-    tw->dp1T = w; w += R2P * ETW_H1;
-    tw->dp2T = w; w += R2P * ETW_H2;
-    tw->dp3T = w; w += R2P * ETW_DP3;
+    const long nvt = tc_nvt(rows, nbr), n = nvt * 128;
+    tw->nvt = nvt;
+    tw->inT = w;  w += n * ETW_IN;
+    tw->h1T = w;  w += n * ETW_H1;
+    tw->h2T = w;  w += n * ETW_H2;
+    tw->dp1T = w; w += n * ETW_H1;
+    tw->dp2T = w; w += n * ETW_H2;
+    tw->dp3T = w; w += n * ETW_DP3;
     tw->relu = reinterpret_cast<unsigned*>(w);
 }
 
@@ -352,13 +342,6 @@ static int enc_tc_go(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
 }
 
 int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st) {
-    if (a.tw.inT) {
-        const long R2 = (long)a.nbr * a.B, R2P = a.tw.R2P;
-        if (R2P > R2) {   // zero the padding columns [R2, R2P) of every feature row (read by the weight-gradient slabs)
-            cudaError_t e = cudaMemset2DAsync(a.tw.inT + R2, R2P * sizeof(float), 0, (R2P - R2) * sizeof(float), ETW_FEATS, st);
-            if (e != cudaSuccess) return fail(PCVAE_ECUDA, "enc_fwd_tc: cudaMemset2DAsync: %s", cudaGetErrorString(e));
-        }
-    }
     return enc_tc_go(tc::k_enc_fwd_tc, a, tc::enc_fwd_tc_smem(a.L.D), grid, st, "enc_fwd_tc");
 }
 
@@ -366,10 +349,10 @@ int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st) {
     if (a.B > 0)
         if (int rc = enc_tc_go(tc::k_enc_bwd_tc, a, tc::enc_bwd_tc_smem(), 2 * grid, st, "enc_bwd_tc")) return rc;
     const int D = a.L.D;
-    const WgradJob jobs[3] = {{a.tw.dp1T, H1, a.tw.inT, D, (D + 16) & ~15, a.L.W1, a.L.b1},
-                              {a.tw.dp2T, H2, a.tw.h1T, H1, 112, a.L.W2, a.L.b2},
-                              {a.tw.dp3T, LAT2, a.tw.h2T, H2, 64, a.L.W3, a.L.b3}};
-    return wgrad_tc_launch(jobs, 3, a.tw.R2P, a.gp, a.L.total, grid, st);
+    const WgradJob jobs[3] = {{a.tw.dp1T, ETW_H1, H1, a.tw.inT, ETW_IN, D, (D + 16) & ~15, a.L.W1, a.L.b1},
+                              {a.tw.dp2T, ETW_H2, H2, a.tw.h1T, ETW_H1, H1, 112, a.L.W2, a.L.b2},
+                              {a.tw.dp3T, ETW_DP3, LAT2, a.tw.h2T, ETW_H2, H2, 64, a.L.W3, a.L.b3}};
+    return wgrad_tc_launch(jobs, 3, a.tw.nvt, a.gp, a.L.total, grid, st);
 }
 
 }  // namespace pcvae

@@ -53,14 +53,34 @@ __device__ __forceinline__ void load_mask4(const void* m, long gi, int kind, flo
     }
 }
 
-// hi / lo image of an augmented weight matrix; w(n, k) supplies element (row n, column k)
-template <typename F>
-__device__ __forceinline__ void build_image(float* hi, float* lo, int chunks, int nrows, int tid, F w) {
-    for (int i = tid; i < chunks * nrows * 4; i += NT) {
-        const int c = i / (nrows * 4), n = (i >> 2) % nrows, k = 4 * c + (i & 3);
-        const float v = w(n, k);
-        hi[i] = v;
-        lo[i] = tf32_lo(v);
+// hi / lo image of a weight matrix in the K-major no-swizzle core-matrix layout [k/4][row][4].  The caller zeroes the
+// images first (zero_images), then scatters the real entries: global reads run along the nn.Linear rows (coalesced),
+// the shared-memory writes take whatever banks they hit (a few dozen elements per thread, once per launch).
+__device__ __forceinline__ void zero_images(float* base, int floats, int tid) {
+    float4* p = reinterpret_cast<float4*>(base);
+    for (int i = tid; i < floats / 4; i += NT) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void image_put(float* hi, float* lo, int nrows, int row, int col, float v) {
+    const int dst = ((col >> 2) * nrows + row) * 4 + (col & 3);
+    hi[dst] = v;
+    lo[dst] = tf32_lo(v);
+}
+// forward image of y = W x + b with W [N][K] row-major: image row n, column k; the bias sits at column K and, when
+// `one` is set, image row N holds a 1 at column K (it regenerates the constant-1 column for the next layer)
+__device__ __forceinline__ void image_linear(float* hi, float* lo, int nrows, const float* __restrict__ W,
+                                             const float* __restrict__ b, int N, int K, bool one, int tid) {
+    for (int i = tid; i < N * K; i += NT) {
+        const int n = i / K, k = i - n * K;
+        image_put(hi, lo, nrows, n, k, __ldg(W + i));
+    }
+    for (int n = tid; n < N; n += NT) image_put(hi, lo, nrows, n, K, __ldg(b + n));
+    if (one && tid == 0) image_put(hi, lo, nrows, N, K, 1.0f);
+}
+// data-gradient image (transposed weights): image row = layer INPUT index k, image column (reduction) = OUTPUT index n
+__device__ __forceinline__ void image_linear_T(float* hi, float* lo, int nrows, const float* __restrict__ W, int N, int K, int tid) {
+    for (int i = tid; i < N * K; i += NT) {
+        const int n = i / K, k = i - n * K;
+        image_put(hi, lo, nrows, k, n, __ldg(W + i));
     }
 }
 
@@ -69,9 +89,10 @@ struct TileCtx {
     int q, cg, row, c28, c16;
 };
 
-// barrier + (one elected lane) MMA issue + commit; every thread then waits for the batch
+// barrier + (one elected lane) MMA issue + commit; every thread then waits for the batch.  mma_kick / mma_wait are the
+// two halves: independent work (global loads for the next epilogue) placed between them overlaps the tensor pipe.
 template <typename Issue>
-__device__ __forceinline__ void run_mma(TileCtx& cx, uint64_t* bar, int warp, Issue&& issue) {
+__device__ __forceinline__ void mma_kick(uint64_t* bar, int warp, Issue&& issue) {
     tmem_st_wait();
     tc_fence_before();
     __syncthreads();
@@ -83,9 +104,16 @@ __device__ __forceinline__ void run_mma(TileCtx& cx, uint64_t* bar, int warp, Is
         }
         __syncwarp();
     }
+}
+__device__ __forceinline__ void mma_wait(TileCtx& cx, uint64_t* bar) {
     mbar_wait(bar, cx.ph);
     cx.ph ^= 1;
     tc_fence_after();
+}
+template <typename Issue>
+__device__ __forceinline__ void run_mma(TileCtx& cx, uint64_t* bar, int warp, Issue&& issue) {
+    mma_kick(bar, warp, issue);
+    mma_wait(cx, bar);
 }
 
 __device__ __forceinline__ void tc_setup(TileCtx& cx, uint64_t* bar, uint32_t* slot, int tid, uint32_t ncols = 512) {

@@ -870,11 +870,11 @@ int pcvae_dec(const pcvae_dec_params* p, void* stream) {
     a.alpha = p->alpha; a.beta_w = p->beta_w; a.x_logvar = p->x_logvar; a.loss_scale = p->loss_scale;
     a.sums_partials = p->sums_partials; a.gp = p->grad_partials;
     if (p->mode == PCVAE_DEC_TRAIN && g_train_tc && dec_tc_supported(L) && p->tc_workspace && p->rows > 0) {
-        const long need = tcw_floats(p->rows, p->n_branch), R2P = tcw_r2p(p->rows, p->n_branch);
+        const long need = tcw_floats(p->rows, p->n_branch), nvt = tc_nvt(p->rows, p->n_branch), R2P = nvt * 128;
         if (p->tc_workspace_floats < need)
             return fail(PCVAE_EINVAL, "dec: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
         float* w = p->tc_workspace;
-        a.R2P = R2P;
+        a.nvt = nvt;
         a.ws_zT = w;   w += R2P * TCW_Z;
         a.ws_h4T = w;  w += R2P * TCW_H4;
         a.ws_h5T = w;  w += R2P * TCW_H5;

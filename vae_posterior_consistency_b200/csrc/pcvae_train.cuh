@@ -22,28 +22,29 @@ struct DecArgs {
     const float* d_xhat[2];
     float* d_z[2];
     float* gp;
-    // tensor-core path only: feature-major ("transposed") activation / pre-activation-gradient buffers [feature][R2P]
-    // (R2P = nbr*B rounded up to 32, padding columns zero) for the weight-gradient GEMMs, and the ReLU masks
-    float* ws_zT;     // [16][R2P]   (z, 1, 0...)
-    float* ws_h4T;    // [56][R2P]   (relu h4, 1, 0...)
-    float* ws_h5T;    // [104][R2P]  (relu h5, 1, 0...)
-    float* ws_dp6T;   // [104][R2P]  dL/d(pre-sigmoid)
-    float* ws_dp5T;   // [104][R2P]
-    float* ws_dp4T;   // [56][R2P]
-    unsigned* ws_relu; // [nbr*B][8]: bit masks of h5 > 0 (4 column groups x 28) and h4 > 0 (4 x 16)
-    long R2P;
+    // tensor-core path only: activation / pre-activation-gradient buffers for the weight-gradient GEMMs, tile-blocked
+    // feature-major [vt][feature][128 rows] (vt = branch * ntiles + tile; one 128-row tile of a kernel is one contiguous
+    // block, rows past the batch hold zero gradients), and the ReLU masks
+    float* ws_zT;     // [nvt][16][128]   (z, 1, 0...)
+    float* ws_h4T;    // [nvt][56][128]   (relu h4, 1, 0...)
+    float* ws_h5T;    // [nvt][104][128]  (relu h5, 1, 0...)
+    float* ws_dp6T;   // [nvt][104][128]  dL/d(pre-sigmoid)
+    float* ws_dp5T;   // [nvt][104][128]
+    float* ws_dp4T;   // [nvt][56][128]
+    unsigned* ws_relu; // [nvt*128][8]: bit masks of h5 > 0 (4 column groups x 28) and h4 > 0 (4 x 16)
+    long nvt;
 };
 
-// tensor-core encoder scratch (pcvae_enc_tc.cu): feature-major [feature][R2P] like the decoder's
+// tensor-core encoder scratch (pcvae_enc_tc.cu): tile-blocked feature-major [vt][feature][128 rows] like the decoder's
 struct EncTcWs {
-    float* inT;       // [104][R2P]  (x*mask, 1 at feature D, 0...)
-    float* h1T;       // [104][R2P]  (relu h1, 1, 0...)
-    float* h2T;       // [56][R2P]   (relu h2, 1, 0...)
-    float* dp1T;      // [104][R2P]  dL/d(pre1)
-    float* dp2T;      // [56][R2P]
-    float* dp3T;      // [24][R2P]   (d_mean | d_logvar)
-    unsigned* relu;   // [nbr*B][8]: bit masks of h1 > 0 (4 column groups x 28) and h2 > 0 (4 x 16)
-    long R2P;
+    float* inT;       // [nvt][104][128]  (x*mask, 1 at feature D, 0...)
+    float* h1T;       // [nvt][104][128]  (relu h1, 1, 0...)
+    float* h2T;       // [nvt][56][128]   (relu h2, 1, 0...)
+    float* dp1T;      // [nvt][104][128]  dL/d(pre1)
+    float* dp2T;      // [nvt][56][128]
+    float* dp3T;      // [nvt][24][128]   (d_mean | d_logvar)
+    unsigned* relu;   // [nvt*128][8]: bit masks of h1 > 0 (4 column groups x 28) and h2 > 0 (4 x 16)
+    long nvt;
 };
 
 struct EncFwdArgs {
@@ -81,15 +82,15 @@ struct EncBwdArgs {
 // pcvae_dec_tc.cu
 constexpr int TCW_Z = 16, TCW_H4 = 56, TCW_H5 = 104;            // pitches of the buffers above
 constexpr int TCW_FEATS = TCW_Z + 2 * TCW_H4 + 3 * TCW_H5;      // feature rows of the scratch
-inline long tcw_r2p(long rows, int nbr) { return (rows * nbr + 31) / 32 * 32; }
-inline long tcw_floats(long rows, int nbr) { return TCW_FEATS * tcw_r2p(rows, nbr) + 8 * rows * nbr; }
+inline long tc_nvt(long rows, int nbr) { return nbr * ((rows + 127) / 128); }      // 128-row tiles over all branches
+inline long tcw_floats(long rows, int nbr) { return (TCW_FEATS + 8) * 128 * tc_nvt(rows, nbr); }
 bool dec_tc_supported(const Layout& L);
 int dec_tc_launch(const DecArgs& a, int grid, cudaStream_t st);
 
 // pcvae_enc_tc.cu
 constexpr int ETW_IN = 104, ETW_H1 = 104, ETW_H2 = 56, ETW_DP3 = 24;          // pitches (feature rows) of EncTcWs
 constexpr int ETW_FEATS = ETW_IN + 2 * ETW_H1 + 2 * ETW_H2 + ETW_DP3;
-inline long etw_floats(long rows, int nbr) { return ETW_FEATS * tcw_r2p(rows, nbr) + 8 * rows * nbr; }
+inline long etw_floats(long rows, int nbr) { return (ETW_FEATS + 8) * 128 * tc_nvt(rows, nbr); }
 bool enc_tc_supported(const Layout& L);
 void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw);
 int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st);
@@ -97,11 +98,11 @@ int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st);
 
 // pcvae_wgrad_tc.cu: dWaug[m][n] = sum_rows AT[m][row] * BT[n][row] for up to three layers in one launch
 struct WgradJob {
-    const float* AT; int Ma;              // [>= Ma][R2P]: pre-activation gradients, feature-major
-    const float* BT; int Kin;             // [>= Kin + 1][R2P]: layer input | 1, feature-major
+    const float* AT; int Fa, Ma;          // [nvt][Fa][128]: pre-activation gradients (Ma <= Fa real features)
+    const float* BT; int Fb, Kin;         // [nvt][Fb][128]: layer input | 1 (Kin + 1 <= Fb real features)
     int Nb;                               // MMA N: round16(Kin + 1)
     int W_off, b_off;                     // where dW [Ma][Kin] and db [Ma] go in the flat layout
 };
-int wgrad_tc_launch(const WgradJob* jobs, int njobs, long R2P, float* gp, long P, int grid, cudaStream_t st);
+int wgrad_tc_launch(const WgradJob* jobs, int njobs, long nvt, float* gp, long P, int grid, cudaStream_t st);
 
 }  // namespace pcvae
