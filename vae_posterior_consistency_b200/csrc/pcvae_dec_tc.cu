@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
             }
         }
         for (int br = 0; br < a.nbr; ++br) {
-            const long vt = (long)br * ntiles + t;            // tile of the feature-major scratch: [vt][feature][128 rows]
-            float* zT = a.ws_zT + vt * (TCW_Z * ROWS) + row;
-            float* h4T = a.ws_h4T + vt * (TCW_H4 * ROWS) + row;
-            float* h5T = a.ws_h5T + vt * (TCW_H5 * ROWS) + row;
-            float* dp6T = a.ws_dp6T + vt * (TCW_H5 * ROWS) + row;
+            const long vt = (long)br * ntiles + t;            // tile of the scratch: [vt][row / 32][feature][row % 32]
+            float* zT = a.ws_zT + (long)vt * (TCW_Z * ROWS) + (row >> 5) * (32 * TCW_Z) + (row & 31);
+            float* h4T = a.ws_h4T + (long)vt * (TCW_H4 * ROWS) + (row >> 5) * (32 * TCW_H4) + (row & 31);
+            float* h5T = a.ws_h5T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
+            float* dp6T = a.ws_dp6T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
             unsigned* reluT = a.ws_relu + (vt * ROWS + row) * 8;
             // ---- z | 1 -> RA, HBM ----
             if (cg == 0) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                 tmem_st16(lane_addr + RA_HI, v);
                 tmem_st16(lane_addr + RA_HI + 16, lo);
 #pragma unroll
-                for (int j = 0; j < TCW_Z; ++j) zT[j * ROWS] = v[j];
+                for (int j = 0; j < TCW_Z; ++j) zT[j * 32] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_HI + 16, f4h, f4l, fs4, F4_C / 2, idF4); });
 
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c16 + j < TCW_H4) h4T[(c16 + j) * ROWS] = v[j];
+                    if (c16 + j < TCW_H4) h4T[(c16 + j) * 32] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, f5h, f5l, fs5, F5_C / 2, idF5); });
 
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                 st_part(lane_addr + RA_LO + c28, part, lo);
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (j < cnt && c28 + j0 + j < TCW_H5) h5T[(c28 + j0 + j) * ROWS] = v[j];
+                    if (j < cnt && c28 + j0 + j < TCW_H5) h5T[(c28 + j0 + j) * 32] = v[j];
             }
             reluT[cg] = m5;
             reluT[4 + cg] = m4;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                         }
                         if (c < TCW_H5) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dp6T[(c + j) * ROWS] = dpre[j];
+                            for (int j = 0; j < 4; ++j) dp6T[(c + j) * 32] = dpre[j];
                         }
                     }
                 }
@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
         const bool ok = grow < a.B;
         for (int br = 0; br < a.nbr; ++br) {
             const long vt = (long)br * ntiles + t;
-            const float* dp6T = a.ws_dp6T + vt * (TCW_H5 * ROWS) + row;
-            float* dp5T = a.ws_dp5T + vt * (TCW_H5 * ROWS) + row;
-            float* dp4T = a.ws_dp4T + vt * (TCW_H4 * ROWS) + row;
+            const float* dp6T = a.ws_dp6T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
+            float* dp5T = a.ws_dp5T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
+            float* dp4T = a.ws_dp4T + (long)vt * (TCW_H4 * ROWS) + (row >> 5) * (32 * TCW_H4) + (row & 31);
             const unsigned* reluT = a.ws_relu + (vt * ROWS + row) * 8;
             uint32_t m5 = 0, m4 = 0;
             if (ok) { m5 = reluT[cg]; m4 = reluT[4 + cg]; }
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
                         const int c = c28 + j0 + j;
-                        v[j] = (ok && c < TCW_H5) ? dp6T[c * ROWS] : 0.f;
+                        v[j] = (ok && c < TCW_H5) ? dp6T[c * 32] : 0.f;
                         lo[j] = tf32_lo(v[j]);
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 st_part(lane_addr + RA_LO + c28, part, lo);
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (j < cnt && c28 + j0 + j < TCW_H5) dp5T[(c28 + j0 + j) * ROWS] = v[j];
+                    if (j < cnt && c28 + j0 + j < TCW_H5) dp5T[(c28 + j0 + j) * 32] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, x5h, x5l, xs5, X5_C / 2, idX5); });
 
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c16 + j < TCW_H4) dp4T[(c16 + j) * ROWS] = v[j];
+                    if (c16 + j < TCW_H4) dp4T[(c16 + j) * 32] = v[j];
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, x4h, x4l, xs4, X4_C / 2, idX4); });
 

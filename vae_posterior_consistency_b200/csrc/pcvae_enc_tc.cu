@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
             }
         }
         for (int br = 0; br < a.nbr; ++br) {
-            const long vt = (long)br * ntiles + t;            // tile of the feature-major scratch: [vt][feature][128 rows]
-            float* inT = tw.inT + vt * (ETW_IN * ROWS) + row;
-            float* h1T = tw.h1T + vt * (ETW_H1 * ROWS) + row;
-            float* h2T = tw.h2T + vt * (ETW_H2 * ROWS) + row;
+            const long vt = (long)br * ntiles + t;            // tile of the scratch: [vt][row / 32][feature][row % 32]
+            float* inT = tw.inT + (long)vt * (ETW_IN * ROWS) + (row >> 5) * (32 * ETW_IN) + (row & 31);
+            float* h1T = tw.h1T + (long)vt * (ETW_H1 * ROWS) + (row >> 5) * (32 * ETW_H1) + (row & 31);
+            float* h2T = tw.h2T + (long)vt * (ETW_H2 * ROWS) + (row >> 5) * (32 * ETW_H2) + (row & 31);
             unsigned* reluT = tw.relu + (vt * ROWS + row) * 8;
             // ---- x * mask | 1 -> RA, HBM ----
 #pragma unroll
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                 if (save) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j <= D) inT[(c28 + j0 + j) * ROWS] = v[j];
+                        if (j < cnt && c28 + j0 + j <= D) inT[(c28 + j0 + j) * 32] = v[j];
                 }
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                 if (save) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j < ETW_H1) h1T[(c28 + j0 + j) * ROWS] = v[j];
+                        if (j < cnt && c28 + j0 + j < ETW_H1) h1T[(c28 + j0 + j) * 32] = v[j];
                 }
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, e2h, e2l, es2, E2_C / 2, idE2); });
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                 if (save) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c16 + j < ETW_H2) h2T[(c16 + j) * ROWS] = v[j];
+                        if (c16 + j < ETW_H2) h2T[(c16 + j) * 32] = v[j];
                     reluT[cg] = m1;
                     reluT[4 + cg] = m2;
                 }
@@ -233,9 +233,9 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
         const int br = vt / ntiles, t = vt - br * ntiles;
         const int grow = t * ROWS + row;
         const bool ok = grow < a.B;
-        float* dp1T = tw.dp1T + (long)vt * (ETW_H1 * ROWS) + row;      // scratch tile vt: [feature][128 rows]
-        float* dp2T = tw.dp2T + (long)vt * (ETW_H2 * ROWS) + row;
-        float* dp3T = tw.dp3T + (long)vt * (ETW_DP3 * ROWS) + row;
+        float* dp1T = tw.dp1T + (long)vt * (ETW_H1 * ROWS) + (row >> 5) * (32 * ETW_H1) + (row & 31);      // scratch tile vt: [row / 32][feature][row % 32]
+        float* dp2T = tw.dp2T + (long)vt * (ETW_H2 * ROWS) + (row >> 5) * (32 * ETW_H2) + (row & 31);
+        float* dp3T = tw.dp3T + (long)vt * (ETW_DP3 * ROWS) + (row >> 5) * (32 * ETW_DP3) + (row & 31);
         const unsigned* reluT = tw.relu + ((long)vt * ROWS + row) * 8;
         uint32_t m1 = 0, m2 = 0;
         if (ok) { m1 = reluT[cg]; m2 = reluT[4 + cg]; }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
             tmem_st16(lane_addr + B_D3L, lo);
             tmem_st8(lane_addr + B_D3L + 16, lo + 16);
 #pragma unroll
-            for (int j = 0; j < LAT2; ++j) dp3T[j * ROWS] = v[j];
+            for (int j = 0; j < LAT2; ++j) dp3T[j * 32] = v[j];
         }
         run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC2, tmem + B_D3H, tmem + B_D3L, y3h, y3l, ys3, Y3_C / 2, idY3); });
 
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
             else { tmem_st8(lane_addr + B_RBH + c16, v); tmem_st8(lane_addr + B_RBL + c16, lo); }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (c16 + j < ETW_H2) dp2T[(c16 + j) * ROWS] = v[j];
+                if (c16 + j < ETW_H2) dp2T[(c16 + j) * 32] = v[j];
         }
         run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, y2h, y2l, ys2, Y2_C / 2, idY2); });
 
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
                 if (j < cnt && c28 + j0 + j < ETW_H1)
-                    dp1T[(c28 + j0 + j) * ROWS] = (((m1 >> (j0 + j)) & 1u) && c28 + j0 + j < H1) ? v[j] : 0.f;
+                    dp1T[(c28 + j0 + j) * 32] = (((m1 >> (j0 + j)) & 1u) && c28 + j0 + j < H1) ? v[j] : 0.f;
         }
         tc_fence_before();
         __syncthreads();            // the X2 accumulator aliases the columns the next tile writes first

@@ -134,7 +134,7 @@ class Engine:
         z = mk() if want_z else [None] * nb
         eps = [None] * nb if eps is None else [None if e is None else _f32(e) for e in eps]
         # what the backward needs: the tcgen05 encoder's scratch when this shape has one, else the FFMA kernel's
-        # saved activations; `ws` is an opaque (act_ws, tc_workspace) handle for enc_bwd
+        # saved activations; `ws` is that one tensor (enc_bwd tells the two apart by their sizes, which never coincide)
         act, tcw = None, None
         if save and B > 0:
             n = self.lib.pcvae_enc_tc_workspace_floats(C.byref(self.model), B, nb)   # 0: no tensor-core encoder here
@@ -150,7 +150,7 @@ class Engine:
                            tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel())
         with torch.cuda.device(x.device):
             L.check(self.lib.pcvae_enc_fwd(C.byref(p), _stream()), "pcvae_enc_fwd")
-        return mean, logvar, z, ((act, tcw) if save else None)
+        return mean, logvar, z, (tcw if tcw is not None else act)
 
     def enc_bwd(self, theta, x, masks, ws, d_mean, d_logvar, d_z=None, eps=None, logvar=None):
         x = _f32(x)
@@ -161,7 +161,8 @@ class Engine:
         d_logvar = [_f32(t) for t in d_logvar]
         opt = lambda ts: [None] * nb if ts is None else [None if t is None else _f32(t) for t in ts]
         d_z, eps, logvar = opt(d_z), opt(eps), opt(logvar)
-        act, tcw = ws
+        n_tc = self.lib.pcvae_enc_tc_workspace_floats(C.byref(self.model), x.shape[0], nb) if x.shape[0] > 0 else 0
+        act, tcw = (None, ws) if (n_tc > 0 and ws.numel() == n_tc) else (ws, None)
         p = L.EncBwdParams(model=self.model, rows=x.shape[0], n_branch=nb, mask_kind=kind, theta=_p(theta),
                            x=_p(x), mask=_pair(masks), act_ws=_p(act), d_mean=_pair(d_mean),
                            d_logvar=_pair(d_logvar), pnp_ac=_p(self.pnp_ac()), grad_partials=_p(gp),
