@@ -27,9 +27,32 @@ D_TRAIN = 100
 D_REWARD = 101
 # algorithmic FLOP per unit (FLOP = 2*MAC, transcendental work excluded)
 FLOP_TRAIN_ROW = 338_000          # Reg_VAE D=100 fwd+bwd, both branches
-MAC_DEC_BRANCH_ROW = 46_500       # decoder fwd 15 500 + dX 15 500 + dW 15 500 (one branch)
+# per-kernel algorithmic FLOP per branch-row at D=100 (they add up to FLOP_TRAIN_ROW / 2 = 169 000)
+KERNEL_FLOP_BRANCH_ROW = {
+    "k_enc_fwd_tc": 32_000,        # 2 x (100x100 + 100x50 + 50x20)
+    "k_dec_fwd_tc": 31_000,        # 2 x (10x50 + 50x100 + 100x100)
+    "k_dec_bwd_tc": 31_000,        # data gradients of the three decoder layers
+    "k_wgrad_tc[dec]": 31_000,     # weight gradients of the three decoder layers
+    "k_enc_bwd_tc": 12_000,        # data gradients of encoder layers 3 and 2
+    "k_wgrad_tc[enc]": 32_000,     # weight gradients of the three encoder layers
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 65 536 from the ncu --set full captures summarised
+# in profiles/r01_ncu_summary.md
+KERNEL_DRAM_BYTES = {"k_enc_fwd_tc": 185e6, "k_dec_fwd_tc": 219e6, "k_dec_bwd_tc": 187e6, "k_wgrad_tc[dec]": 226e6,
+                     "k_enc_bwd_tc": 105e6, "k_wgrad_tc[enc]": 231e6}
 FLOP_REWARD_TRIPLE = 24_460       # Reg_VAE incremental form
 MAC_REWARD_MAIN_TRIPLE = 12_000   # 2 tail evaluations x (100x50 + 50x20)
+
+
+def tensor_peak_3xtf32():
+    """Tensor-core roofline of an fp32-accurate product issued as three kind::tf32 MMAs: the measured dense bf16
+    rate / 2 (tf32 runs at half the bf16 rate) / 3."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]) / 6.0, "MEASURED_PEAKS.json bf16_tflops (burst) / 2 (tf32) / 3 (3xTF32)"
+    except Exception:
+        return 1590.0 / 6.0, "fallback 1.59 PFLOP/s bf16 / 2 (tf32) / 3 (3xTF32)"
 
 
 def peaks():
@@ -366,57 +389,74 @@ def run_ours(args):
     mask = torch.empty(B, D, device=dev, dtype=torch.bool)
     mask_p = torch.empty(B, D, device=dev, dtype=torch.bool)
     eps = torch.empty(2, B, 10, device=dev)
-    dec_ev = []
     launches = [0]
+    # per-kernel CUDA events recorded by the library itself (pcvae_profile_events): 9 marks per step
+    # enc_fwd: [0] k [1]   dec: [2] k_fwd [3] k_bwd [4] k_wgrad [5]   enc_bwd: [6] k_bwd [7] k_wgrad [8]
+    KERNELS = [("k_enc_fwd_tc", 0, 1), ("k_dec_fwd_tc", 2, 3), ("k_dec_bwd_tc", 3, 4), ("k_wgrad_tc[dec]", 4, 5),
+               ("k_enc_bwd_tc", 6, 7), ("k_wgrad_tc[enc]", 7, 8)]
+    ev_sets = []
+
+    def new_events():
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
+        for e in evs:
+            e.record()                                   # creates the underlying cudaEvent_t
+        return evs, (C.c_void_p * 9)(*[e.cuda_event for e in evs])
 
     def prep_step(s, xs, ms):
-        """device-side batch preparation: gather by the sampler permutation, draw sub-mask and noise"""
+        """device-side batch preparation in one launch: gather by the sampler permutation, draw sub-mask and noise"""
         idx = perm[s * B:(s + 1) * B]
-        L.check(lib.pcvae_gather_rows(table.data_ptr(), mtable.data_ptr(), idx.data_ptr(), xs.data_ptr(),
-                                      ms.data_ptr(), B, D, L.MASK_U8, stream()), "gather_rows")
+        L.check(lib.pcvae_prep_batch(table.data_ptr(), mtable.data_ptr(), idx.data_ptr(), xs.data_ptr(), ms.data_ptr(),
+                                     mask_p.data_ptr(), eps.data_ptr(), B, D, 2, 0.7, 99, s * 4, stream()), "prep_batch")
         launches[0] += 1
 
     def draw_step(s, ms):
+        """e2e path (x and mask arrive from the host): sub-mask and noise only"""
         L.check(lib.pcvae_draw_submask(ms.data_ptr(), mask_p.data_ptr(), B * D, 0.7, 99, s * 4, stream()), "draw_submask")
         L.check(lib.pcvae_draw_normal(eps.data_ptr(), 2 * B * 10, 77, s * 4, stream()), "draw_normal")
         launches[0] += 2
 
     def train_step(xs, ms, timed):
         masks, e = [ms, mask_p], [eps[0], eps[1]]
-        mean, logvar, z, ws = eng.enc_fwd(theta, xs, masks, e, save=True)
         if timed:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
+            evs, arr = new_events()
+            lib.pcvae_profile_events(arr, 9)
+        mean, logvar, z, ws = eng.enc_fwd(theta, xs, masks, e, save=True)
         out = eng.dec(L.DEC_TRAIN, theta, z, x=xs, masks=masks, mean=mean, logvar=logvar, eps=e, alpha=1.0,
                       beta_w=1.0, loss_scale=1.0 / (B * world))
-        if timed:
-            b.record()
-            dec_ev.append((a, b))
         eng.enc_bwd(theta, xs, masks, ws, out["d_mean"], out["d_logvar"])
-        eng.reduce_grads(tr.grad)
-        sums = eng.reduce_sums(B)
-        if world > 1:
-            torch.distributed.all_reduce(tr.grad, group=dist_group)
+        if timed:
+            if lib.pcvae_profile_events(None, 0) == 9:   # all nine marks were recorded (tensor-core path taken)
+                ev_sets.append(evs)
         tr.step_count += 1
-        eng.adam_step(theta, tr.grad, tr.exp_avg, tr.exp_avg_sq, tr.step_count)
-        launches[0] += 6
+        if world > 1:
+            eng.reduce_grads(tr.grad)
+            sums = eng.reduce_sums(B)
+            torch.distributed.all_reduce(tr.grad, group=dist_group)
+            eng.adam_step(theta, tr.grad, tr.exp_avg, tr.exp_avg_sq, tr.step_count)
+            launches[0] += 6 + 3
+        else:
+            sums = eng.reduce_adam(tr.grad, theta, tr.exp_avg, tr.exp_avg_sq, tr.step_count, B)
+            launches[0] += 6 + 1
         return sums
 
     for s in range(args.warmup):
-        prep_step(s, x, mask); draw_step(s, mask); train_step(x, mask, False)
+        prep_step(s, x, mask); train_step(x, mask, False)
     barrier(world)
     launches[0] = 0
     w0 = time.time()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for s in range(args.warmup, n_total):
-        prep_step(s, x, mask); draw_step(s, mask); sums = train_step(x, mask, True)
+        prep_step(s, x, mask); sums = train_step(x, mask, (s - args.warmup) % 4 == 0)
     t1.record()
     barrier(world)
     clocks.window(w0, time.time())
     train_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
     train_launches = launches[0]
-    dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / len(dec_ev)
+    kernel_us = {}
+    for name, i0, i1 in KERNELS:
+        if ev_sets:
+            kernel_us[name] = 1e3 * sum(evs[i0].elapsed_time(evs[i1]) for evs in ev_sets) / len(ev_sets)
     loss = float(KR.loss_from_sums(sums, B * world, 1.0, 1.0, True))
     rows_s = B * world / (train_ms * 1e-3)
 
@@ -520,8 +560,15 @@ def run_ours(args):
 
     clk = clocks.stop()
     if rank == 0:
-        dec_flops = 2 * MAC_DEC_BRANCH_ROW * 2 * B
-        achieved = dec_flops / (dec_ms * 1e-3) / 1e12
+        # dominant kernel of the step = the longest of the six tensor-core kernels, timed with the library's own events
+        tensor_peak, tensor_src = tensor_peak_3xtf32()
+        if kernel_us:
+            dom = max(kernel_us, key=kernel_us.get)
+            dom_flops = KERNEL_FLOP_BRANCH_ROW[dom] * 2 * B
+            achieved = dom_flops / (kernel_us[dom] * 1e-6) / 1e12
+        else:
+            dom, achieved = "unavailable (tensor-core path not taken)", 0.0
+        step_tflops = FLOP_TRAIN_ROW * B / (train_ms * 1e-3) / 1e12
         line = {
             "metric": "train rows/s (fwd+bwd+Adam), consistency-regularised partial VAE",
             "value": rows_s, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -537,16 +584,21 @@ def run_ours(args):
                     "ms_per_step": e2e_ms},
             "gpu_launches": train_launches,
             "clocks": clk,
-            "roofline": {"bound": "fp32_ffma", "kernel": "k_dec<64> (decoder fwd + loss + decoder bwd, both branches)",
-                         "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_dec launch at this shape, from the
-                         # ncu --set full capture summarised in profiles/r01_ncu_summary.md (algorithmic: 65536 rows x
-                         # (400 B x + 200 B masks + 480 B latent stats in/out) = 71 MB)
-                         "traffic": 65.4e6 if B == 65536 else None, "peak_source": "pcvae_ffma_probe on this GPU (MEASURED_PEAKS.json has no FP32 entry)",
-                         "step_achieved": FLOP_TRAIN_ROW * B / (train_ms * 1e-3) / 1e12,
-                         "step_frac": FLOP_TRAIN_ROW * B / (train_ms * 1e-3) / 1e12 / ffma_tflops,
-                         "hbm": {"achieved": (B * D * 10 + B * 2 * 152 * 8) / (train_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                                 "unit": "GB/s", "peak_source": peak_src}},
+            "roofline": {"bound": "tensor", "kernel": dom + " (tcgen05.mma kind::tf32, fp32-accurate 3xTF32 split; longest of the "
+                                                           "six kernels of the step)",
+                         "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                         "traffic": KERNEL_DRAM_BYTES.get(dom) if B == 65536 else None,
+                         "peak_source": tensor_src,
+                         "kernel_us": kernel_us,
+                         "step_achieved": step_tflops, "step_frac": step_tflops / tensor_peak,
+                         # the same algorithmic fp32 FLOP against the FP32 FFMA peak measured on this GPU (the roofline
+                         # of an implementation that keeps the products on the CUDA cores, as rounds before did)
+                         "vs_fp32_ffma": {"peak": ffma_tflops, "kernel_frac": achieved / ffma_tflops,
+                                          "step_frac": step_tflops / ffma_tflops,
+                                          "peak_source": "pcvae_ffma_probe on this GPU"},
+                         "hbm": {"achieved": sum(KERNEL_DRAM_BYTES.values()) / (train_ms * 1e-3) / 1e9 if B == 65536 else None,
+                                 "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                                 "note": "ncu DRAM bytes of the six kernels / step time"}},
             "secondary": sec,
         }
         if world == 1 and args.mnar_steps > 0:

@@ -196,6 +196,11 @@ int pcvae_dec(const pcvae_dec_params* p, void* stream);
 long pcvae_dec_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch);
 /* process-wide switch for the tcgen05 training kernels (default 1); returns the previous value */
 int pcvae_set_train_tensor_cores(int enable);
+/* Per-kernel timing hooks for benchmarks: arm `n` caller-created CUDA events (cudaEvent_t[n], timing enabled) on the
+ * calling thread.  Each tensor-core launcher (pcvae_enc_fwd, pcvae_dec TRAIN, pcvae_enc_bwd) then records the next
+ * event on its stream before its first kernel and after every kernel, until the events run out.  Pass NULL to
+ * disarm.  Returns how many events of the previous arming were recorded.  No effect on results. */
+int pcvae_profile_events(void** events, int n);
 
 /* ------------------------------------------------------------------------
  * Stand-alone loss terms for the module API (`model.loss(...)` called on tensors the
@@ -235,6 +240,12 @@ int pcvae_reduce_grads(const float* grad_partials, int grid, long param_count, l
 int pcvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq,
                     long n, int step, float lr, float beta1, float beta2, float eps,
                     void* stream);
+/* Single-GPU training: pcvae_reduce_grads over all parameters, pcvae_adam_step and (when sums_partials / sums are
+ * non-NULL) pcvae_reduce_sums in ONE launch.  `grad` receives the reduced gradient.  The partials of a parameter
+ * are summed in a fixed order (four interleaved chains, then combined), so results are deterministic. */
+int pcvae_reduce_adam(const float* grad_partials, int grid, long param_count, float* grad, float* theta,
+                      float* exp_avg, float* exp_avg_sq, int step, float lr, float beta1, float beta2, float eps,
+                      const float* sums_partials, int rows, int obs_dim, double* sums, void* stream);
 
 /* ------------------------------------------------------------------------
  * Active-selection information reward for ONE acquisition step, all (row, candidate,
@@ -283,6 +294,11 @@ int pcvae_gather_rows(const float* table, const void* mask_table, const long* id
 int pcvae_draw_submask(const uint8_t* mask, uint8_t* mask_p, long n, float keep_prob,
                        unsigned long long seed, unsigned long long offset, void* stream);
 int pcvae_draw_normal(float* out, long n, unsigned long long seed, unsigned long long offset, void* stream);
+/* The three steps above in ONE launch (uint8 masks, obs_dim % 4 == 0, obs_dim <= 128): x, mask gathered by idx,
+ * mask_p drawn, and eps[n_eps][rows][10] standard normals (n_eps = 2 for the regularised families, 1 for vanilla). */
+int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* idx, float* x, uint8_t* mask,
+                     uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
+                     unsigned long long seed, unsigned long long offset, void* stream);
 
 /* ------------------------------------------------------------------------
  * Generic dense layer y = act(x W^T + b) on row tiles (weights resident in shared memory), forward

@@ -50,6 +50,15 @@ bool make_layout(const pcvae_model* m, Layout* L) {
     return true;
 }
 
+// Optional per-kernel timing hooks (pcvae_profile_events): the tensor-core launchers call prof_mark() before their
+// first kernel and after every kernel; while armed, mark k records the caller's k-th CUDA event on the stream.
+static thread_local cudaEvent_t* g_prof_ev = nullptr;
+static thread_local int g_prof_n = 0, g_prof_i = 0;
+
+void prof_mark(cudaStream_t st) {
+    if (g_prof_ev && g_prof_i < g_prof_n) cudaEventRecord(g_prof_ev[g_prof_i++], st);
+}
+
 int device_ok(int* n_sm) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -67,3 +76,11 @@ int device_ok(int* n_sm) {
 }
 
 }  // namespace pcvae
+
+extern "C" int pcvae_profile_events(void** events, int n) {
+    pcvae::g_prof_ev = reinterpret_cast<cudaEvent_t*>(events);
+    pcvae::g_prof_n = events ? n : 0;
+    const int used = pcvae::g_prof_i;
+    pcvae::g_prof_i = 0;
+    return used;
+}

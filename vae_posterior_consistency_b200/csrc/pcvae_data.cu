@@ -53,6 +53,49 @@ __global__ void k_draw_normal(float* __restrict__ out, long n, unsigned long lon
     }
 }
 
+// Fused batch preparation (one launch instead of three): a warp per table row copies the row of x and of the
+// mask with 16-byte / 4-byte vector accesses, draws the sub-mask for its entries and (lanes 0..4) the 2 x 10
+// standard-normal draws of the row.  Requires D % 4 == 0 and D <= 128, uint8 masks.
+__global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ table, const uint8_t* __restrict__ mtable,
+                                                    const long* __restrict__ idx, float* __restrict__ x,
+                                                    uint8_t* __restrict__ mask, uint8_t* __restrict__ mask_p,
+                                                    float* __restrict__ eps, int B, int D, int n_eps, float keep,
+                                                    unsigned long long seed, unsigned long long offset) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int D4 = D >> 2;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        const long src = idx[b];
+        if (lane < D4) {
+            const float4 v = reinterpret_cast<const float4*>(table + src * D)[lane];
+            const uint32_t m = reinterpret_cast<const uint32_t*>(mtable + src * D)[lane];
+            reinterpret_cast<float4*>(x + (long)b * D)[lane] = v;
+            reinterpret_cast<uint32_t*>(mask + (long)b * D)[lane] = m;
+            curandStatePhilox4_32_10_t st;
+            curand_init(seed, (unsigned long long)b * 64 + lane, offset, &st);
+            const float4 u = curand_uniform4(&st);      // (0,1]
+            const float uv[4] = {u.x, u.y, u.z, u.w};
+            uint32_t mp = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (((m >> (8 * j)) & 0xFFu) && (1.0f - uv[j]) < keep) mp |= 1u << (8 * j);   // rand() in [0,1) < keep
+            reinterpret_cast<uint32_t*>(mask_p + (long)b * D)[lane] = mp;
+        }
+        if (lane < (10 * n_eps + 3) / 4) {               // n_eps * 10 normals per row, four per lane
+            curandStatePhilox4_32_10_t st;
+            curand_init(seed ^ 0x9E3779B97F4A7C15ull, (unsigned long long)b * 64 + 32 + lane, offset, &st);
+            const float4 g = curand_normal4(&st);
+            const int e0 = 4 * lane;                     // entry in the row's [n_eps][10] block
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = e0 + j, br = e / 10, l = e - br * 10;
+                if (br < n_eps) eps[((long)br * B + b) * 10 + l] = gv[j];
+            }
+        }
+    }
+}
+
 }  // namespace pcvae
 
 using namespace pcvae;
@@ -69,6 +112,22 @@ int pcvae_gather_rows(const float* table, const void* mask_table, const long* id
     k_gather_rows<<<grid * 8, 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx, x, mask, rows, obs_dim, mask_kind);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "gather_rows: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* idx, float* x, uint8_t* mask,
+                     uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
+                     unsigned long long seed, unsigned long long offset, void* stream) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (rows < 0 || obs_dim < 4 || obs_dim > 128 || obs_dim % 4 || n_eps < 0 || n_eps > 2 || !(keep_prob >= 0.f && keep_prob <= 1.f))
+        return fail(PCVAE_EINVAL, "prep_batch: bad arguments (obs_dim must be a multiple of 4, <= 128; n_eps 0..2)");
+    if (rows == 0) return PCVAE_OK;
+    if (!table || !mask_table || !idx || !x || !mask || !mask_p || (n_eps > 0 && !eps)) return fail(PCVAE_EINVAL, "prep_batch: null pointer");
+    k_prep_batch<<<grid * 8, 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx, x, mask, mask_p, eps, rows, obs_dim, n_eps,
+                                                              keep_prob, seed, offset);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "prep_batch: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }
 

@@ -453,12 +453,17 @@ static int tc_launch(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
 }
 
 int dec_tc_launch(const DecArgs& a, int grid, cudaStream_t st) {
+    prof_mark(st);
     if (int rc = tc_launch(tc::k_dec_fwd_tc, a, tc::dec_fwd_tc_smem(a.L.D), grid, st, "dec_fwd_tc")) return rc;
+    prof_mark(st);
     if (int rc = tc_launch(tc::k_dec_bwd_tc, a, tc::dec_bwd_tc_smem(), grid, st, "dec_bwd_tc")) return rc;
+    prof_mark(st);
     const WgradJob jobs[3] = {{a.ws_dp6T, TCW_H5, a.L.D, a.ws_h5T, TCW_H5, G2, 112, a.L.W6, a.L.b6},
                               {a.ws_dp5T, TCW_H5, G2, a.ws_h4T, TCW_H4, G1, 64, a.L.W5, a.L.b5},
                               {a.ws_dp4T, TCW_H4, G1, a.ws_zT, TCW_Z, LAT, 16, a.L.W4, a.L.b4}};
-    return wgrad_tc_launch(jobs, 3, a.nvt, a.gp, a.L.total, grid, st);
+    const int rc = wgrad_tc_launch(jobs, 3, a.nvt, a.gp, a.L.total, grid, st);
+    prof_mark(st);
+    return rc;
 }
 
 }  // namespace pcvae

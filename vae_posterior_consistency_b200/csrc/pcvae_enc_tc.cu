@@ -342,17 +342,24 @@ static int enc_tc_go(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
 }
 
 int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st) {
-    return enc_tc_go(tc::k_enc_fwd_tc, a, tc::enc_fwd_tc_smem(a.L.D), grid, st, "enc_fwd_tc");
+    prof_mark(st);
+    const int rc = enc_tc_go(tc::k_enc_fwd_tc, a, tc::enc_fwd_tc_smem(a.L.D), grid, st, "enc_fwd_tc");
+    prof_mark(st);
+    return rc;
 }
 
 int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st) {
+    prof_mark(st);
     if (a.B > 0)
         if (int rc = enc_tc_go(tc::k_enc_bwd_tc, a, tc::enc_bwd_tc_smem(), 2 * grid, st, "enc_bwd_tc")) return rc;
+    prof_mark(st);
     const int D = a.L.D;
     const WgradJob jobs[3] = {{a.tw.dp1T, ETW_H1, H1, a.tw.inT, ETW_IN, D, (D + 16) & ~15, a.L.W1, a.L.b1},
                               {a.tw.dp2T, ETW_H2, H2, a.tw.h1T, ETW_H1, H1, 112, a.L.W2, a.L.b2},
                               {a.tw.dp3T, ETW_DP3, LAT2, a.tw.h2T, ETW_H2, H2, 64, a.L.W3, a.L.b3}};
-    return wgrad_tc_launch(jobs, 3, a.tw.nvt, a.gp, a.L.total, grid, st);
+    const int rc = wgrad_tc_launch(jobs, 3, a.tw.nvt, a.gp, a.L.total, grid, st);
+    prof_mark(st);
+    return rc;
 }
 
 }  // namespace pcvae

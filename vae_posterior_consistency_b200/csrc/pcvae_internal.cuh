@@ -37,6 +37,8 @@ int fail(int code, const char* fmt, ...);
 bool make_layout(const pcvae_model* m, Layout* L);
 // PCVAE_OK and the SM count when the current device is a compute-capability-10.x part
 int device_ok(int* n_sm);
+// records the next armed profiling event (pcvae_profile_events) on `st`, if any
+void prof_mark(cudaStream_t st);
 // fills the PNP collapsed tables A,C (2*D*round4(K) floats) from theta
 void pnp_tables_launch(const Layout& L, const float* theta, float* ac, cudaStream_t st);
 

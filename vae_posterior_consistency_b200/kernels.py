@@ -252,6 +252,16 @@ class Engine:
             L.check(self.lib.pcvae_adam_step(_p(theta), _p(grad), _p(exp_avg), _p(exp_avg_sq), theta.numel(), step,
                                              lr, b1, b2, eps, _stream()), "pcvae_adam_step")
 
+    def reduce_adam(self, grad, theta, exp_avg, exp_avg_sq, step, rows, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+        """reduce_grads over all parameters + adam_step + reduce_sums in one launch (single-GPU training)."""
+        sums = torch.empty(L.NSUMS, device=self.device, dtype=torch.float64)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pcvae_reduce_adam(_p(self.grad_partials()), self.grid, self.P, _p(grad), _p(theta),
+                                               _p(exp_avg), _p(exp_avg_sq), step, lr, b1, b2, eps,
+                                               _p(self.sums_partials()), rows, self.D, _p(sums), _stream()),
+                    "pcvae_reduce_adam")
+        return sums
+
     # ---- reward -----------------------------------------------------------------------
     def reward(self, theta, x, mask, im, workspace=None):
         """R[N, D-1] for one acquisition step (evaluate.py:416-425)."""
@@ -411,7 +421,7 @@ class FusedTrainer:
         self.regularised, self.alpha, self.beta_w, self.lr = regularised, alpha, beta_w, lr
         self.dist_group, self.world_size = dist_group, world_size
 
-    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None):
+    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True):
         e = self.eng
         B = x.shape[0]
         rows = B if global_rows is None else global_rows
@@ -422,15 +432,21 @@ class FusedTrainer:
         out = e.dec(L.DEC_TRAIN, self.theta, z, x=x, masks=masks, mean=mean, logvar=logvar, eps=eps, alpha=alpha,
                     beta_w=self.beta_w, loss_scale=1.0 / rows)
         e.enc_bwd(self.theta, x, masks, ws, out["d_mean"], out["d_logvar"])
+        if not reduce:
+            return None
         e.reduce_grads(self.grad)
         sums = e.reduce_sums(B)
         return sums
 
     def step(self, x, mask, mask_p, eps_q, eps_p, global_rows=None):
-        sums = self.forward_backward(x, mask, mask_p, eps_q, eps_p, global_rows)
-        if self.dist_group is not None and self.world_size > 1:
-            torch.distributed.all_reduce(self.grad, group=self.dist_group)
         self.step_count += 1
-        self.eng.adam_step(self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)
+        if self.dist_group is not None and self.world_size > 1:
+            sums = self.forward_backward(x, mask, mask_p, eps_q, eps_p, global_rows)
+            torch.distributed.all_reduce(self.grad, group=self.dist_group)
+            self.eng.adam_step(self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)
+        else:       # single GPU: partial reduce, Adam and the loss sums in one launch
+            self.forward_backward(x, mask, mask_p, eps_q, eps_p, global_rows, reduce=False)
+            sums = self.eng.reduce_adam(self.grad, self.theta, self.exp_avg, self.exp_avg_sq, self.step_count,
+                                        x.shape[0], lr=self.lr)
         rows = x.shape[0] if global_rows is None else global_rows
         return loss_from_sums(sums, rows, self.alpha, self.beta_w, self.regularised)

@@ -28,6 +28,7 @@ SYMBOLS = [
     "pcvae_draw_submask", "pcvae_draw_normal", "pcvae_dense_fwd", "pcvae_dense_bwd", "pcvae_mnar_sample_z",
     "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss", "pcvae_set_reward_tensor_cores",
     "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores", "pcvae_enc_tc_workspace_floats",
+    "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events",
 ]
 
 
@@ -136,6 +137,7 @@ def load():
     lib.pcvae_dec_tc_workspace_floats.restype = C.c_long
     lib.pcvae_dec_tc_workspace_floats.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
     lib.pcvae_set_train_tensor_cores.argtypes = [C.c_int]
+    lib.pcvae_profile_events.argtypes = [C.c_void_p, C.c_int]
     lib.pcvae_loss_terms.argtypes = [C.POINTER(LossParams), C.c_void_p]
     lib.pcvae_reduce_sums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.pcvae_reduce_grads.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_int,
@@ -150,6 +152,11 @@ def load():
     lib.pcvae_draw_submask.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_ulonglong, C.c_ulonglong,
                                        C.c_void_p]
     lib.pcvae_draw_normal.argtypes = [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
+    lib.pcvae_prep_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
+    lib.pcvae_reduce_adam.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p]
     lib.pcvae_dense_fwd.argtypes = [C.POINTER(DenseFwdParams), C.c_void_p]
     lib.pcvae_dense_bwd.argtypes = [C.POINTER(DenseBwdParams), C.c_void_p]
     lib.pcvae_mnar_sample_z.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -42,8 +42,10 @@ def _save(model, experiment_type, data_type, vae_type, missing_rate, alpha, p_mi
     return path
 
 
-def _epoch_batches(loader, device, throughput):
-    """Yield (x, mask) batches on `device` in the order the reference's DataLoader would."""
+def _epoch_batches(loader, device, throughput, prep=None):
+    """Yield (x, mask) batches on `device` in the order the reference's DataLoader would.  In throughput mode with
+    `prep` = dict(keep=..., n_eps=..., step=...) and a shape pcvae_prep_batch takes, the sub-mask and the noise of the
+    step are drawn by the same launch and left in prep['mask_p'] / prep['eps']."""
     table = getattr(loader, 'pcvae_table', None)
     if not throughput or table is None or not table[0].is_cuda:
         for data_sample, mask in loader:
@@ -61,6 +63,18 @@ def _epoch_batches(loader, device, throughput):
         B = idx.numel()
         x = torch.empty(B, D, device=device)
         m = torch.empty(B, D, device=device, dtype=mask_src.dtype)
+        if prep is not None and kind == L.MASK_U8 and D % 4 == 0 and D <= 128:
+            prep['step'] += 1
+            mp = torch.empty_like(m)
+            eps = torch.empty(prep['n_eps'], B, 10, device=device)
+            with torch.cuda.device(device):
+                L.check(lib.pcvae_prep_batch(data.data_ptr(), mask_src.data_ptr(), idx.data_ptr(), x.data_ptr(),
+                                             m.data_ptr(), mp.data_ptr(), eps.data_ptr(), B, D, prep['n_eps'],
+                                             prep['keep'], 0xC0FFEE, prep['step'] * 8,
+                                             torch.cuda.current_stream().cuda_stream), "pcvae_prep_batch")
+            prep['mask_p'], prep['eps'] = mp, eps
+            yield x, m
+            continue
         with torch.cuda.device(device):
             L.check(lib.pcvae_gather_rows(data.data_ptr(), mask_src.data_ptr(), idx.data_ptr(), x.data_ptr(),
                                           m.data_ptr(), B, D, kind, torch.cuda.current_stream().cuda_stream),
@@ -122,12 +136,22 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
             graph_trainer = GraphedTrainer(model, make_fn, optimizer, fill_normal_)
     keep = 1 - p_missingness / 100
     step = 0
+    # throughput mode, fused regularised step: gather + sub-mask + noise in one launch (pcvae_prep_batch)
+    prep = dict(keep=keep, n_eps=2, step=0) if (throughput and fused and regularised and latent_dim == 10
+                                                and 'with_drop' not in vae_type) else None
     for i in tqdm(range(max_epochs)):
         total = torch.zeros((), device=device, dtype=torch.float64)
-        for data_sample, mask in _epoch_batches(data_loader_train, device, throughput):
+        for data_sample, mask in _epoch_batches(data_loader_train, device, throughput, prep):
             step += 1
             B = data_sample.shape[0]
             mask_p = None
+            prepped = prep.pop('mask_p', None) if prep is not None else None
+            if prepped is not None:
+                mask_p, eps_pair = prepped, prep.pop('eps')
+                lo, hi = row_block(B, world_size, rank)
+                sl = slice(lo, hi)
+                total += trainer.step(data_sample[sl], mask[sl], mask_p[sl], eps_pair[0][sl], eps_pair[1][sl], global_rows=B)
+                continue
             if 'with_drop' in vae_type:
                 mask_drop = create_missing_uci_drop_eddi(data_sample.shape).to(device)
             else:
