@@ -259,6 +259,45 @@ def test_tcgen05_decoder_matches_ffma_decoder(B, D, regularised, mask_float):
     torch.testing.assert_close(g1, g0, rtol=2e-4, atol=2e-6 * float(g0.abs().max()))
 
 
+def test_throughput_prep_then_step_tcgen05_matches_ffma():
+    """Throughput-mode sequence at the bench shape: pcvae_prep_batch (gather + Philox sub-mask + noise in one launch)
+    followed by the fused step, through the tcgen05 kernels and through the FFMA kernels on the same prepared batch.
+    (Running other kernels right before the tensor-core ones also guards against state they might depend on.)"""
+    KR, L = _mods()
+    lib = L.load()
+    B, D, T = 65536, 100, 200_000
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(11)
+    table = torch.rand(T, D, device=dev, generator=g)
+    mtable = torch.rand(T, D, device=dev, generator=g) < 0.7
+    idx = torch.randint(0, T, (B,), device=dev, generator=g)
+    p = O.init_params("mlp", D, 0, seed=5)
+    out = []
+    for tc in (0, 1):
+        prev = lib.pcvae_set_train_tensor_cores(tc)
+        try:
+            x = torch.empty(B, D, device=dev); mask = torch.empty(B, D, device=dev, dtype=torch.bool)
+            mask_p = torch.empty(B, D, device=dev, dtype=torch.bool); eps = torch.empty(2, B, 10, device=dev)
+            L.check(lib.pcvae_prep_batch(table.data_ptr(), mtable.data_ptr(), idx.data_ptr(), x.data_ptr(), mask.data_ptr(),
+                                         mask_p.data_ptr(), eps.data_ptr(), B, D, 2, 0.7, 99, 8,
+                                         torch.cuda.current_stream().cuda_stream), "pcvae_prep_batch")
+            theta = KR.flatten_params(p, L.FAMILY_MLP, "cuda")
+            tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, theta, regularised=True, alpha=1.0)
+            loss = tr.step(x, mask, mask_p, eps[0], eps[1])
+            torch.cuda.synchronize()
+            out.append((float(loss), tr.grad.cpu().clone(), tr.theta.cpu().clone(), x.cpu(), mask.cpu(), mask_p.cpu(), eps.cpu()))
+        finally:
+            lib.pcvae_set_train_tensor_cores(prev)
+    (l0, g0, t0, x0, m0, mp0, e0), (l1, g1, t1, x1, m1, mp1, e1) = out
+    assert torch.equal(x0, x1) and torch.equal(m0, m1) and torch.equal(mp0, mp1) and torch.equal(e0, e1)   # Philox: same counters
+    assert torch.equal(x0, table[idx].cpu()) and torch.equal(m0, mtable[idx].cpu())                          # the gather itself
+    assert bool((mp0 <= m0).all()) and 0.66 < float(mp0.float().sum() / m0.float().sum()) < 0.74
+    assert abs(float(e0.mean())) < 5e-3 and abs(float(e0.std()) - 1.0) < 5e-3
+    assert abs(l1 - l0) <= 1e-5 * abs(l0)
+    torch.testing.assert_close(g1, g0, rtol=2e-3, atol=2e-5 * float(g0.abs().max()))
+    torch.testing.assert_close(t1, t0, rtol=0, atol=2.1e-3)      # one Adam step moves every weight by at most lr = 1e-3
+
+
 def test_empty_batch_is_a_no_op():
     KR, L = _mods()
     p = O.init_params("mlp", 13)

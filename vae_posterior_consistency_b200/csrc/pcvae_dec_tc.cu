@@ -92,19 +92,22 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
     const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // work items = (tile, branch) pairs, tile-major, strided over the CTAs: the two branches of a tile run on
+    // neighbouring CTAs at about the same time (x and the masks are shared through L2) and the load is balanced
+    for (int w = blockIdx.x; w < ntiles * a.nbr; w += gridDim.x) {
+        const int t = a.nbr == 2 ? (w >> 1) : w, br = a.nbr == 2 ? (w & 1) : 0;
         const int row0 = t * ROWS;
         const int grow = row0 + row;
         const bool ok = grow < a.B;
-        {   // pull the next tile of this CTA towards L2 while this one is processed
-            const int tn = t + gridDim.x;
-            if (tn < ntiles) {
-                const long r0 = (long)tn * ROWS, nrows = min((long)ROWS, (long)a.B - r0);
+        {   // pull the next item of this CTA towards L2 while this one is processed
+            const int wn = w + gridDim.x;
+            if (wn < ntiles * a.nbr) {
+                const long r0 = (long)(a.nbr == 2 ? (wn >> 1) : wn) * ROWS, nrows = min((long)ROWS, (long)a.B - r0);
                 prefetch_l2(a.x + r0 * D, nrows * D * 4, tid);
                 for (int b = 0; b < a.nbr; ++b) prefetch_l2((const char*)a.mask[b] + r0 * D * msz, nrows * D * msz, tid);
             }
         }
-        for (int br = 0; br < a.nbr; ++br) {
+        {
             const long vt = (long)br * ntiles + t;            // tile of the scratch: [vt][row / 32][feature][row % 32]
             float* zT = a.ws_zT + (long)vt * (TCW_Z * ROWS) + (row >> 5) * (32 * TCW_Z) + (row & 31);
             float* h4T = a.ws_h4T + (long)vt * (TCW_H4 * ROWS) + (row >> 5) * (32 * TCW_H4) + (row & 31);
@@ -299,11 +302,12 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     float s_klq = 0.f, s_klp = 0.f, s_klr = 0.f;
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < ntiles * a.nbr; w += gridDim.x) {      // (tile, branch) items as in k_dec_fwd_tc
+        const int t = a.nbr == 2 ? (w >> 1) : w, br = a.nbr == 2 ? (w & 1) : 0;
         const int row0 = t * ROWS;
         const int grow = row0 + row;
         const bool ok = grow < a.B;
-        for (int br = 0; br < a.nbr; ++br) {
+        {
             const long vt = (long)br * ntiles + t;
             const float* dp6T = a.ws_dp6T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
             float* dp5T = a.ws_dp5T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
@@ -311,20 +315,29 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
             const unsigned* reluT = a.ws_relu + (vt * ROWS + row) * 8;
             uint32_t m5 = 0, m4 = 0;
             if (ok) { m5 = reluT[cg]; m4 = reluT[4 + cg]; }
-            // ---- dpre6 (HBM) -> RA ----
+            {   // pull the next item's dpre6 block (contiguous, written by k_dec_fwd_tc) towards L2
+                const int wn = w + gridDim.x;
+                if (wn < ntiles * a.nbr) {
+                    const int tn = a.nbr == 2 ? (wn >> 1) : wn, bn = a.nbr == 2 ? (wn & 1) : 0;
+                    const char* nb = reinterpret_cast<const char*>(a.ws_dp6T + ((long)bn * ntiles + tn) * (TCW_H5 * ROWS));
+                    if (tid < TCW_H5 * ROWS * 4 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (long)tid * 128));
+                }
+            }
+            // ---- dpre6 (HBM) -> RA: all 28 loads of the thread in flight before the first TMEM store ----
+            {
+                float d6[28];
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
-                float v[16], lo[16];
+                for (int j = 0; j < 28; ++j) d6[j] = (ok && c28 + j < TCW_H5) ? dp6T[(c28 + j) * 32] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < cnt) {
-                        const int c = c28 + j0 + j;
-                        v[j] = (ok && c < TCW_H5) ? dp6T[c * 32] : 0.f;
-                        lo[j] = tf32_lo(v[j]);
-                    }
-                st_part(lane_addr + RA_HI + c28, part, v);
-                st_part(lane_addr + RA_LO + c28, part, lo);
+                for (int part = 0; part < 3; ++part) {
+                    const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                    float v[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < cnt) { v[j] = d6[j0 + j]; lo[j] = tf32_lo(v[j]); }
+                    st_part(lane_addr + RA_HI + c28, part, v);
+                    st_part(lane_addr + RA_LO + c28, part, lo);
+                }
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, x6h, x6l, xs6, X6_C / 2, idX6); });
 

@@ -82,15 +82,12 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
             float* h1T = tw.h1T + (long)vt * (ETW_H1 * ROWS) + (row >> 5) * (32 * ETW_H1) + (row & 31);
             float* h2T = tw.h2T + (long)vt * (ETW_H2 * ROWS) + (row >> 5) * (32 * ETW_H2) + (row & 31);
             unsigned* reluT = tw.relu + (vt * ROWS + row) * 8;
-            // ---- x * mask | 1 -> RA, HBM ----
+            // ---- x * mask | 1 -> RA, HBM: all loads of the thread in flight before the first TMEM store ----
+            {
+                float xm[28];
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
-                float v[16], lo[16];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (4 * g >= cnt) continue;
-                    const int c = c28 + j0 + 4 * g;
+                for (int g = 0; g < 7; ++g) {
+                    const int c = c28 + 4 * g;
                     float xv[4] = {0.f, 0.f, 0.f, 0.f};
                     if (c < D) {
                         if (ok) {
@@ -104,14 +101,22 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                         xv[0] = 1.0f;                          // bias column
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { v[4 * g + j] = xv[j]; lo[4 * g + j] = tf32_lo(xv[j]); }
+                    for (int j = 0; j < 4; ++j) xm[4 * g + j] = xv[j];
                 }
-                st_part(lane_addr + RA_HI + c28, part, v);
-                st_part(lane_addr + RA_LO + c28, part, lo);
-                if (save) {
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                    float v[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j <= D) inT[(c28 + j0 + j) * 32] = v[j];
+                        if (j < cnt) { v[j] = xm[j0 + j]; lo[j] = tf32_lo(v[j]); }
+                    st_part(lane_addr + RA_HI + c28, part, v);
+                    st_part(lane_addr + RA_LO + c28, part, lo);
+                    if (save) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < cnt && c28 + j0 + j <= D) inT[(c28 + j0 + j) * 32] = v[j];
+                    }
                 }
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
