@@ -242,7 +242,7 @@ int pcvae_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_
                     void* stream);
 /* Single-GPU training: pcvae_reduce_grads over all parameters, pcvae_adam_step and (when sums_partials / sums are
  * non-NULL) pcvae_reduce_sums in ONE launch.  `grad` receives the reduced gradient.  The partials of a parameter
- * are summed in a fixed order (four interleaved chains, then combined), so results are deterministic. */
+ * are summed in a fixed order (eight interleaved chains, then combined), so results are deterministic. */
 int pcvae_reduce_adam(const float* grad_partials, int grid, long param_count, float* grad, float* theta,
                       float* exp_avg, float* exp_avg_sq, int step, float lr, float beta1, float beta2, float eps,
                       const float* sums_partials, int rows, int obs_dim, double* sums, void* stream);

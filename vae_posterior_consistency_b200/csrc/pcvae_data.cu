@@ -53,9 +53,25 @@ __global__ void k_draw_normal(float* __restrict__ out, long n, unsigned long lon
     }
 }
 
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): counter-based, no state to initialise.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }          // [0, 1)
+__device__ __forceinline__ float u01_open(uint32_t r) { return ((float)(r >> 8) + 1.0f) * 5.9604644775390625e-08f; }   // (0, 1]
+
 // Fused batch preparation (one launch instead of three): a warp per table row copies the row of x and of the
 // mask with 16-byte / 4-byte vector accesses, draws the sub-mask for its entries and (lanes 0..4) the 2 x 10
-// standard-normal draws of the row.  Requires D % 4 == 0 and D <= 128, uint8 masks.
+// standard-normal draws of the row (Box-Muller).  Philox counter = (row, lane | stream, offset), key = seed.
+// Requires D % 4 == 0 and D <= 128, uint8 masks.
 __global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ table, const uint8_t* __restrict__ mtable,
                                                     const long* __restrict__ idx, float* __restrict__ x,
                                                     uint8_t* __restrict__ mask, uint8_t* __restrict__ mask_p,
@@ -64,6 +80,7 @@ __global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ ta
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int D4 = D >> 2;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
         const long src = idx[b];
         if (lane < D4) {
@@ -71,22 +88,23 @@ __global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ ta
             const uint32_t m = reinterpret_cast<const uint32_t*>(mtable + src * D)[lane];
             reinterpret_cast<float4*>(x + (long)b * D)[lane] = v;
             reinterpret_cast<uint32_t*>(mask + (long)b * D)[lane] = m;
-            curandStatePhilox4_32_10_t st;
-            curand_init(seed, (unsigned long long)b * 64 + lane, offset, &st);
-            const float4 u = curand_uniform4(&st);      // (0,1]
-            const float uv[4] = {u.x, u.y, u.z, u.w};
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)lane, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+            const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
             uint32_t mp = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (((m >> (8 * j)) & 0xFFu) && (1.0f - uv[j]) < keep) mp |= 1u << (8 * j);   // rand() in [0,1) < keep
+                if (((m >> (8 * j)) & 0xFFu) && u01(rv[j]) < keep) mp |= 1u << (8 * j);       // rand() in [0,1) < keep
             reinterpret_cast<uint32_t*>(mask_p + (long)b * D)[lane] = mp;
         }
         if (lane < (10 * n_eps + 3) / 4) {               // n_eps * 10 normals per row, four per lane
-            curandStatePhilox4_32_10_t st;
-            curand_init(seed ^ 0x9E3779B97F4A7C15ull, (unsigned long long)b * 64 + 32 + lane, offset, &st);
-            const float4 g = curand_normal4(&st);
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(64 + lane), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+            float gv[4];
+            const float r0 = sqrtf(-2.0f * logf(u01_open(r.x))), r1 = sqrtf(-2.0f * logf(u01_open(r.z)));
+            float s0, c0, s1, c1;
+            sincospif(2.0f * u01(r.y), &s0, &c0);
+            sincospif(2.0f * u01(r.w), &s1, &c1);
+            gv[0] = r0 * c0; gv[1] = r0 * s0; gv[2] = r1 * c1; gv[3] = r1 * s1;
             const int e0 = 4 * lane;                     // entry in the row's [n_eps][10] block
-            const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int e = e0 + j, br = e / 10, l = e - br * 10;

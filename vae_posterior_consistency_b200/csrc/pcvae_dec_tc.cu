@@ -92,6 +92,20 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
     const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
+    // z of the item in hand (column group 0 only): loaded one item ahead, under the F6 MMAs of the previous item
+    float2 zreg[LAT / 2];
+    auto load_z = [&](int wi) {
+        const int ti = a.nbr == 2 ? (wi >> 1) : wi, bi = a.nbr == 2 ? (wi & 1) : 0;
+        const int gr = ti * ROWS + row;
+#pragma unroll
+        for (int j = 0; j < LAT / 2; ++j) zreg[j] = make_float2(0.f, 0.f);
+        if (cg == 0 && wi < ntiles * a.nbr && gr < a.B) {
+            const float2* zp = reinterpret_cast<const float2*>((bi ? a.z[1] : a.z[0]) + (long)gr * LAT);
+#pragma unroll
+            for (int j = 0; j < LAT / 2; ++j) zreg[j] = zp[j];
+        }
+    };
+    load_z(blockIdx.x);
     // work items = (tile, branch) pairs, tile-major, strided over the CTAs: the two branches of a tile run on
     // neighbouring CTAs at about the same time (x and the masks are shared through L2) and the load is balanced
     for (int w = blockIdx.x; w < ntiles * a.nbr; w += gridDim.x) {
@@ -119,11 +133,8 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                 float v[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                if (ok) {
-                    const float2* zp = reinterpret_cast<const float2*>(a.z[br] + (long)grow * LAT);
 #pragma unroll
-                    for (int j = 0; j < LAT / 2; ++j) { const float2 p2 = zp[j]; v[2 * j] = p2.x; v[2 * j + 1] = p2.y; }
-                }
+                for (int j = 0; j < LAT / 2; ++j) { v[2 * j] = zreg[j].x; v[2 * j + 1] = zreg[j].y; }     // zero for rows past the batch
                 v[LAT] = 1.0f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) lo[j] = tf32_lo(v[j]);
@@ -196,6 +207,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
                 }
                 xr[4 * g] = x4.x; xr[4 * g + 1] = x4.y; xr[4 * g + 2] = x4.z; xr[4 * g + 3] = x4.w;
             }
+            load_z(w + gridDim.x);                            // the next item's z, also under the F6 MMAs
             mma_wait(cx, &bar_s);
 
             // ---- x_hat = sigmoid(acc6): loss terms, dL/d(pre-sigmoid) -> HBM ----
@@ -378,13 +390,16 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, x4h, x4l, xs4, X4_C / 2, idX4); });
 
-            // ---- latent-space terms: KL sums, d_mean / d_logvar (one row per thread of column group 0) ----
-            if (cg == 0) {
-                float dzv[16];
-                tmem_ld16(lane_addr + ACC2, dzv);
+            // ---- latent-space terms: KL sums, d_mean / d_logvar; the row's 10 latents are split over its column
+            //      groups (4 + 4 + 2 + 0) so that no warp waits for a single group doing all of them ----
+            if (cg < 3) {
+                float dzv[4];
+                tmem_ld4(lane_addr + ACC2 + 4 * cg, dzv);
                 if (ok) {
 #pragma unroll
-                    for (int l = 0; l < LAT; ++l) {
+                    for (int li = 0; li < 4; ++li) {
+                        const int l = 4 * cg + li;
+                        if (l >= LAT) continue;
                         const long gi = (long)grow * LAT + l;
                         const float mq = a.mean[0][gi], lq = a.logvar[0][gi];
                         const float eq = expf(lq);
@@ -398,7 +413,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                                 s_klr += 0.5f * (expf(lq - lp) + dmu * dmu / ep - 1.f - (lq - lp));
                             }
                         }
-                        const float dz = dzv[l];
+                        const float dz = dzv[li];
                         float gm, gv;
                         if (br == 0) {
                             gm = (1.f - alpha) * a.beta_w * mq;

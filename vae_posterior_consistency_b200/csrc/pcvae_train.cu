@@ -677,29 +677,32 @@ __global__ void k_adam(float* __restrict__ theta, const float* __restrict__ grad
     }
 }
 
-// reduce + Adam (+ loss sums) in one launch: four lanes per parameter sum interleaved quarters of the per-CTA partials
-// (always in the same order), lane 0 of the group applies torch.optim.Adam; block 0 also reduces the loss sums.
+// reduce + Adam (+ loss sums) in one launch: a block owns 32 consecutive parameters; its eight warps sum interleaved
+// eighths of the per-CTA partials (128-byte coalesced loads, always in the same order), warp 0 combines the eight
+// sums in a fixed order and applies torch.optim.Adam; block 0 also reduces the loss sums.
 __global__ void __launch_bounds__(256) k_reduce_adam(const float* __restrict__ gp, int grid, long P, float* __restrict__ grad,
                                                      float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                                                      float lr_bc1, float inv_sqrt_bc2, float b1, float b2, float eps,
                                                      const float* __restrict__ sp, double nll_const, double* __restrict__ sums) {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long i = t >> 2;
-    const int part = (int)(t & 3);
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const long i = (long)blockIdx.x * 32 + lane;
     float s = 0.f;
     if (i < P) {
         int c = part;
-        for (; c + 12 < grid; c += 16) {                // four loads in flight per lane, summed in CTA order
-            const float v0 = gp[(long)c * P + i], v1 = gp[(long)(c + 4) * P + i], v2 = gp[(long)(c + 8) * P + i],
-                        v3 = gp[(long)(c + 12) * P + i];
+        for (; c + 24 < grid; c += 32) {                // four loads in flight per thread, summed in CTA order
+            const float v0 = gp[(long)c * P + i], v1 = gp[(long)(c + 8) * P + i], v2 = gp[(long)(c + 16) * P + i],
+                        v3 = gp[(long)(c + 24) * P + i];
             s += v0; s += v1; s += v2; s += v3;
         }
-        for (; c < grid; c += 4) s += gp[(long)c * P + i];
+        for (; c < grid; c += 8) s += gp[(long)c * P + i];
     }
-    const float s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
-                s3 = __shfl_down_sync(0xffffffffu, s, 3);
-    if (i < P && part == 0) {
-        const float g = ((s + s1) + s2) + s3;
+    red[part][lane] = s;
+    __syncthreads();
+    if (part == 0 && i < P) {
+        float g = red[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) g += red[q][lane];
         grad[i] = g;
         const float mi = m[i] + (g - m[i]) * (1.f - b1);          // exp_avg.lerp_(grad, 1-beta1)
         const float vi = fmaf(b2, v[i], (1.f - b2) * g * g);      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
@@ -707,8 +710,8 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const float* __restrict__ g
         v[i] = vi;
         theta[i] -= lr_bc1 * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
     }
-    if (sp && blockIdx.x == 0 && threadIdx.x < PCVAE_NSUMS) {
-        const int j = threadIdx.x;
+    if (sp && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + PCVAE_NSUMS) {
+        const int j = threadIdx.x - 32;
         double a = 0.0;
         for (int c = 0; c < grid; ++c) a += (double)sp[c * PCVAE_NSUMS + j];
         if (j == PCVAE_S_RE_Q || j == PCVAE_S_RE_P || j == PCVAE_S_RE_D || j == PCVAE_S_RE_IMP) a += nll_const;
@@ -1012,7 +1015,7 @@ int pcvae_reduce_adam(const float* grad_partials, int grid, long param_count, fl
     if ((sums_partials == nullptr) != (sums == nullptr)) return fail(PCVAE_EINVAL, "reduce_adam: sums_partials and sums go together");
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     const double c = 0.5 * 1.8378770664093453 * (double)rows * (double)obs_dim;   // 0.5*log(2*pi) per entry
-    const int blocks = (int)((4 * param_count + 255) / 256);
+    const int blocks = (int)((param_count + 31) / 32);
     k_reduce_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_partials, grid, param_count, grad, theta, exp_avg, exp_avg_sq,
                                                             (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps,
                                                             sums_partials, c, sums);
