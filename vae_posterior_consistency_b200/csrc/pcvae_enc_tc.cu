@@ -30,9 +30,10 @@ constexpr int B_D3H = 0, B_D3L = 32, B_AC2 = 64, B_RBH = 128, B_RBL = 184, B_AC1
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
+__global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const int stage_inputs) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar_s;
+    __shared__ __align__(8) uint64_t in_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int D = a.L.D, K1 = (D + 8) & ~7, C1 = K1 / 4;
@@ -42,8 +43,13 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
     float* W2l = W2h + E2_C * E2_N * 4;
     float* W3h = W2l + E2_C * E2_N * 4;
     float* W3l = W3h + E3_C * E3_N * 4;
+    // input staging (uint8 masks): the 128 x D tile of x and of the item's mask, fetched one item ahead with two bulk
+    // async copies, so that stage 0 reads shared memory instead of issuing 14 uncoalesced global loads per thread
+    float* xin = W3l + E3_C * E3_N * 4;
+    const uint8_t* min_ = reinterpret_cast<const uint8_t*>(xin + ROWS * D);
     const float* th = a.theta;
     const Layout L = a.L;
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&in_bar)), "r"(1));
     zero_images(smem, 2 * (C1 * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4), tid);
     __syncthreads();
     image_linear(W1h, W1l, E1_N, th + L.W1, th + L.b1, H1, D, true, tid);        // constant-1 output -> bias column of layer 2
@@ -65,6 +71,20 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
     const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
+    uint32_t in_ph = 0;
+    // request the inputs of item (ti, bi); full tiles only (a ragged last tile takes the direct global loads)
+    auto issue_in = [&](int ti, int bi) -> bool {
+        if (!stage_inputs || ti >= ntiles || (ti + 1) * ROWS > a.B) return false;
+        if (tid == 0) {
+            const uint32_t xb = (uint32_t)(ROWS * D * 4), mb = (uint32_t)(ROWS * D);
+            mbar_expect_tx(&in_bar, xb + mb);
+            bulk_g2s(xin, a.x + (long)ti * ROWS * D, xb, &in_bar);
+            bulk_g2s(reinterpret_cast<float*>(const_cast<uint8_t*>(min_)),
+                     reinterpret_cast<const float*>(static_cast<const uint8_t*>(bi ? a.mask[1] : a.mask[0]) + (long)ti * ROWS * D), mb, &in_bar);
+        }
+        return true;
+    };
+    bool staged = issue_in(blockIdx.x, 0);
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int grow = t * ROWS + row;
         const bool ok = grow < a.B;
@@ -83,6 +103,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
             float* h2T = tw.h2T + (long)vt * (ETW_H2 * ROWS) + (row >> 5) * (32 * ETW_H2) + (row & 31);
             unsigned* reluT = tw.relu + (vt * ROWS + row) * 8;
             // ---- x * mask | 1 -> RA, HBM: all loads of the thread in flight before the first TMEM store ----
+            if (staged) { mbar_wait(&in_bar, in_ph); in_ph ^= 1u; }
             {
                 float xm[28];
 #pragma unroll
@@ -90,7 +111,12 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                     const int c = c28 + 4 * g;
                     float xv[4] = {0.f, 0.f, 0.f, 0.f};
                     if (c < D) {
-                        if (ok) {
+                        if (staged) {                          // full tile, inputs in shared memory
+                            const float4 x4 = *reinterpret_cast<const float4*>(xin + row * D + c);
+                            const uint32_t mw = *reinterpret_cast<const uint32_t*>(min_ + row * D + c);
+                            xv[0] = x4.x * ((mw & 0xFFu) ? 1.f : 0.f); xv[1] = x4.y * ((mw & 0xFF00u) ? 1.f : 0.f);
+                            xv[2] = x4.z * ((mw & 0xFF0000u) ? 1.f : 0.f); xv[3] = x4.w * ((mw & 0xFF000000u) ? 1.f : 0.f);
+                        } else if (ok) {
                             const long gi = (long)grow * D + c;
                             const float4 x4 = *reinterpret_cast<const float4*>(a.x + gi);
                             float m[4];
@@ -119,7 +145,10 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a) {
                     }
                 }
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
+            // every thread has read its inputs (barrier inside mma_kick): the staging buffer is free for the next item
+            staged = (br + 1 < a.nbr) ? issue_in(t, br + 1) : issue_in(t + gridDim.x, 0);
+            mma_wait(cx, &bar_s);
 
             // ---- h1 = relu(acc1) | 1 -> RA, HBM ----
             uint32_t m1 = 0;                                  // relu mask of this thread's 28 h1 columns
@@ -313,9 +342,10 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
     tc_teardown(cx, tid, B_COLS);
 }
 
-static size_t enc_fwd_tc_smem(int D) {
+static size_t enc_fwd_tc_smem(int D, bool stage_inputs) {
     const int C1 = ((D + 8) & ~7) / 4;
-    return (size_t)2 * (C1 * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4) * sizeof(float) + 128;
+    return (size_t)2 * (C1 * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4) * sizeof(float) + 128 +
+           (stage_inputs ? (size_t)ROWS * D * 5 : 0);
 }
 static size_t enc_bwd_tc_smem() { return (size_t)2 * (Y3_C * Y3_N * 4 + Y2_C * Y2_N * 4) * sizeof(float) + 128; }
 
@@ -347,10 +377,18 @@ static int enc_tc_go(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
 }
 
 int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st) {
+    // inputs are staged through shared memory when the masks are bytes and the tile fits beside the weight images
+    const bool stage_inputs = a.mask_kind == PCVAE_MASK_U8 && tc::enc_fwd_tc_smem(a.L.D, true) <= (size_t)MAX_SMEM;
+    const size_t sm = tc::enc_fwd_tc_smem(a.L.D, stage_inputs);
+    if (sm > MAX_SMEM) return fail(PCVAE_EINVAL, "enc_fwd_tc: shared memory %zu B exceeds %d", sm, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc::k_enc_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "enc_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     prof_mark(st);
-    const int rc = enc_tc_go(tc::k_enc_fwd_tc, a, tc::enc_fwd_tc_smem(a.L.D), grid, st, "enc_fwd_tc");
+    tc::k_enc_fwd_tc<<<grid, NT, sm, st>>>(a, stage_inputs ? 1 : 0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "enc_fwd_tc: launch: %s", cudaGetErrorString(e));
     prof_mark(st);
-    return rc;
+    return PCVAE_OK;
 }
 
 int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st) {
