@@ -49,10 +49,11 @@ constexpr int X4_C = 14, X4_N = 16;       // K = 56 (n), 10 inputs k
 // ------------------------------------------------------------------------------------------------
 // forward + loss
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
+__global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int stage_inputs) {
     extern __shared__ __align__(128) float smem[];
     __shared__ float red_s[NWARP][PCVAE_NSUMS];
     __shared__ __align__(8) uint64_t bar_s;
+    __shared__ __align__(8) uint64_t in_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = a.L.D, N6 = (D + 15) & ~15;
@@ -62,8 +63,14 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
     float* W5l = W5h + F5_C * F5_N * 4;
     float* W6h = W5l + F5_C * F5_N * 4;
     float* W6l = W6h + F6_C * N6 * 4;
+    // loss-input staging (uint8 masks): the item's 128 x D tile of x and of both masks, requested with bulk async copies
+    // at the start of the item and read from shared memory by the loss epilogue
+    float* xin = W6l + F6_C * N6 * 4;
+    const uint8_t* m0s = reinterpret_cast<const uint8_t*>(xin + ROWS * D);
+    const uint8_t* m1s = m0s + ROWS * D;
     const float* th = a.theta;
     const Layout L = a.L;
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&in_bar)), "r"(1));
     zero_images(smem, 2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * N6 * 4), tid);
     __syncthreads();
     image_linear(W4h, W4l, F4_N, th + L.W4, th + L.b4, G1, LAT, true, tid);      // constant-1 output -> bias column of layer 5
@@ -106,6 +113,21 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
         }
     };
     load_z(blockIdx.x);
+    uint32_t in_ph = 0;
+    auto issue_in = [&](int ti) -> bool {                // full tiles only (a ragged last tile takes the direct global loads)
+        if (!stage_inputs || (ti + 1) * ROWS > a.B) return false;
+        if (tid == 0) {
+            const uint32_t xb = (uint32_t)(ROWS * D * 4), mb_ = (uint32_t)(ROWS * D);
+            mbar_expect_tx(&in_bar, xb + a.nbr * mb_);
+            bulk_g2s(xin, a.x + (long)ti * ROWS * D, xb, &in_bar);
+            bulk_g2s(reinterpret_cast<float*>(const_cast<uint8_t*>(m0s)),
+                     reinterpret_cast<const float*>(static_cast<const uint8_t*>(a.mask[0]) + (long)ti * ROWS * D), mb_, &in_bar);
+            if (a.nbr > 1)
+                bulk_g2s(reinterpret_cast<float*>(const_cast<uint8_t*>(m1s)),
+                         reinterpret_cast<const float*>(static_cast<const uint8_t*>(a.mask[1]) + (long)ti * ROWS * D), mb_, &in_bar);
+        }
+        return true;
+    };
     // work items = (tile, branch) pairs, tile-major, strided over the CTAs: the two branches of a tile run on
     // neighbouring CTAs at about the same time (x and the masks are shared through L2) and the load is balanced
     for (int w = blockIdx.x; w < ntiles * a.nbr; w += gridDim.x) {
@@ -143,7 +165,10 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
 #pragma unroll
                 for (int j = 0; j < TCW_Z; ++j) zT[j * 32] = v[j];
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_HI + 16, f4h, f4l, fs4, F4_C / 2, idF4); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_HI + 16, f4h, f4l, fs4, F4_C / 2, idF4); });
+            // the barrier inside mma_kick ends the previous item's loss epilogue: the staging buffer is free
+            const bool staged = issue_in(t);
+            mma_wait(cx, &bar_s);
 
             // ---- h4 = relu(acc4) | 1 -> RB, HBM ----
             uint32_t m4 = 0;                                  // relu mask of this thread's 16 h4 columns
@@ -186,13 +211,23 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a) {
             reluT[4 + cg] = m4;
             mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, f6h, f6l, fs6, F6_C / 2, idF6); });
             // while the tensor pipe runs F6: this thread's 28 entries of x and of the two masks (as bits)
+            if (staged) { mbar_wait(&in_bar, in_ph); in_ph ^= 1u; }
             float xr[28];
             uint32_t mb = 0, mpb = 0;
 #pragma unroll
             for (int g = 0; g < 7; ++g) {
                 const int c = c28 + 4 * g;
                 float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok && c < D) {
+                if (staged && c < D) {                         // full tile, inputs in shared memory
+                    x4 = *reinterpret_cast<const float4*>(xin + row * D + c);
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(m0s + row * D + c);
+                    const uint32_t w1 = a.nbr > 1 ? *reinterpret_cast<const uint32_t*>(m1s + row * D + c) : 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mb |= (((w0 >> (8 * j)) & 0xFFu) ? 1u : 0u) << (4 * g + j);
+                        mpb |= (((w1 >> (8 * j)) & 0xFFu) ? 1u : 0u) << (4 * g + j);
+                    }
+                } else if (ok && c < D) {
                     const long gi = (long)grow * D + c;
                     x4 = *reinterpret_cast<const float4*>(a.x + gi);
                     float m[4];
@@ -457,9 +492,10 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     tc_teardown(cx, tid);
 }
 
-static size_t dec_fwd_tc_smem(int D) {
+static size_t dec_fwd_tc_smem(int D, int nbr, bool stage_inputs) {
     const int N6 = (D + 15) & ~15;
-    return (size_t)2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * N6 * 4) * sizeof(float) + 128;
+    return (size_t)2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * N6 * 4) * sizeof(float) + 128 +
+           (stage_inputs ? (size_t)ROWS * D * (4 + nbr) : 0);
 }
 static size_t dec_bwd_tc_smem() {
     return (size_t)2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4) * sizeof(float) + 128;
@@ -482,7 +518,16 @@ static int tc_launch(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
 
 int dec_tc_launch(const DecArgs& a, int grid, cudaStream_t st) {
     prof_mark(st);
-    if (int rc = tc_launch(tc::k_dec_fwd_tc, a, tc::dec_fwd_tc_smem(a.L.D), grid, st, "dec_fwd_tc")) return rc;
+    {   // loss inputs are staged through shared memory when the masks are bytes and the tile fits beside the weight images
+        const bool stage_inputs = a.mask_kind == PCVAE_MASK_U8 && tc::dec_fwd_tc_smem(a.L.D, a.nbr, true) + 1024 <= (size_t)MAX_SMEM;
+        const size_t sm = tc::dec_fwd_tc_smem(a.L.D, a.nbr, stage_inputs);
+        if (sm > MAX_SMEM) return fail(PCVAE_EINVAL, "dec_fwd_tc: shared memory %zu B exceeds %d", sm, MAX_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(tc::k_dec_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dec_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        tc::k_dec_fwd_tc<<<grid, NT, sm, st>>>(a, stage_inputs ? 1 : 0);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dec_fwd_tc: launch: %s", cudaGetErrorString(e));
+    }
     prof_mark(st);
     if (int rc = tc_launch(tc::k_dec_bwd_tc, a, tc::dec_bwd_tc_smem(), grid, st, "dec_bwd_tc")) return rc;
     prof_mark(st);
