@@ -85,6 +85,12 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
         return true;
     };
     bool staged = issue_in(blockIdx.x, 0);
+    // NOTE: tiles are strided over the CTAs and both branches of a tile run back to back on one CTA.  Flattening this
+    // into (tile, branch) work items as k_dec_fwd_tc / k_dec_bwd_tc do balances the load better (7 vs 8 items per CTA
+    // at 1024 items), but that version of THIS kernel computed wrong layer-1 products (h1 off by O(1), constant-1
+    // column not 1) although its inputs in TMEM / scratch were right, and faulted when run after certain other
+    // kernels, with nvcc 12.9.86; the cause was not found (see tests/test_gpu_parity.py::
+    // test_throughput_prep_then_step_tcgen05_matches_ffma, which pins the symptom), so the nested form stays.
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int grow = t * ROWS + row;
         const bool ok = grow < a.B;
