@@ -27,6 +27,8 @@
  *   family MLP (Reg_VAE, vanilla_VAE; src/models/VAE.py:366-376):
  *     seq_encoder.0.{weight[100,D],bias[100]} .2.{[50,100],[50]} .4.{[2L,50],[2L]}
  *     seq_decoder.0.{[50,L],[50]} .2.{[100,50],[100]} .4.{[D,100],[D]}
+ *   family MLP_MASK (Reg_VAE_mask, vanilla_VAE_mask; src/models/VAE.py:526-537, 1011-1022): as MLP, but the first
+ *     encoder layer reads [x*mask, mask] (VAE.py:547): seq_encoder.0.weight[100,2D]
  *   family PNP (Reg_EDDI, vanilla_EDDI; src/models/VAE.py:687-709):
  *     type_pars1[D,K], type_bias1[D,1], pnp_encoder1.0.{[K,K+2],[K]},
  *     pnp_encoder2.0.{[100,K],[100]} .2.{[50,100],[50]} .4.{[2L,50],[2L]}, seq_decoder.* as above
@@ -49,7 +51,7 @@ extern "C" {
 #define PCVAE_ABI_VERSION 1
 
 enum { PCVAE_OK = 0, PCVAE_EINVAL = 1, PCVAE_EDEVICE = 2, PCVAE_ECUDA = 3, PCVAE_EWORKSPACE = 4 };
-enum { PCVAE_FAMILY_MLP = 0, PCVAE_FAMILY_PNP = 1 };
+enum { PCVAE_FAMILY_MLP = 0, PCVAE_FAMILY_PNP = 1, PCVAE_FAMILY_MLP_MASK = 2 };
 enum { PCVAE_MASK_U8 = 0, PCVAE_MASK_F32 = 1 };
 
 /* number of loss partial sums produced by pcvae_dec_loss / pcvae_loss_terms */

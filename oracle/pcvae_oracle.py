@@ -78,6 +78,9 @@ def init_params(family: str, obs_dim: int, K: int = 20, latent: int = LATENT,
         enc, first_in = "pnp_encoder2", K
     elif family in ("mlp", "vae"):
         enc, first_in = "seq_encoder", obs_dim
+    elif family in ("mlp_mask", "vae_mask"):
+        # Reg_VAE_mask / vanilla_VAE_mask: first layer reads [x*mask, mask], src/models/VAE.py:526-527, 1011-1012
+        enc, first_in = "seq_encoder", 2 * obs_dim
     else:
         raise ValueError(family)
     p["prior_mean"] = torch.zeros(latent, dtype=dtype)
@@ -94,8 +97,14 @@ def init_params(family: str, obs_dim: int, K: int = 20, latent: int = LATENT,
 # --------------------------------------------------------------------------
 
 def mlp_first_layer_pre(p: Params, x: Tensor, mask: Tensor) -> Tensor:
-    """W1 (x*mask) + b1, the pre-activation the reward's incremental form builds on."""
-    return _lin(x * _as(mask, x), p["seq_encoder.0.weight"], p["seq_encoder.0.bias"])
+    """W1 (x*mask) + b1, the pre-activation the reward's incremental form builds on.  The mask-augmented
+    family (first-layer fan-in 2D) feeds `stack([x*mask, mask], 1).reshape(-1, 2D)` = [x*mask | mask],
+    src/models/VAE.py:547, 1032."""
+    m = _as(mask, x)
+    h = x * m
+    if p["seq_encoder.0.weight"].shape[1] == 2 * x.shape[1]:
+        h = torch.cat([h, m.expand_as(h)], 1)
+    return _lin(h, p["seq_encoder.0.weight"], p["seq_encoder.0.bias"])
 
 
 def mlp_tail(p: Params, h_pre: Tensor, prefix: str = "seq_encoder") -> Tuple[Tensor, Tensor]:

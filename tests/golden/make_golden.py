@@ -206,7 +206,7 @@ def mnar_case(V, cls_name, B, D, S, seed, alpha):
                 xlv_q=xlv_q.detach(), loss=loss.detach(), grads=grads, xm_imp=xm_imp, re=re)
 
 
-def driver_cases(V, E):
+def driver_cases(V, E, cases=None, with_al=True):
     """Run the reference's own train() / eval_vae() / active_learning_func() (the call sequence of
     imputation.py:28-59 and active_learning.py:58-74) on a tiny synthetic Data/ tree with fixed seeds
     and record the artefacts they write."""
@@ -220,7 +220,7 @@ def driver_cases(V, E):
     c = DRIVER_CFG
     out = {}
     cwd = os.getcwd()
-    for name, vae_type, K in DRIVER_CASES:
+    for name, vae_type, K in (cases or DRIVER_CASES):
         with tempfile.TemporaryDirectory() as root:
             make_tree(root, c["data_type"], c["n_rows"], c["obs_dim"], seed=0, missing_rate=c["missing_rate"],
                       experiment_type=c["experiment_type"])
@@ -243,6 +243,11 @@ def driver_cases(V, E):
                            c["epochs"], 5000, 10, device=torch.device("cpu"), alpha=c["alpha"],
                            p_missingness=c["p_missingness"], reg_type=c["reg_type"])
                 # active_learning.py:24-74 call sequence (min-max, split, DataLoader, active_learning_func)
+                if not with_al:
+                    files = {os.path.relpath(f, "experiments"): torch.load(f)
+                             for f in glob.glob(os.path.join("experiments", "**", "*.pt"), recursive=True)}
+                    out[name] = dict(vae_type=vae_type, K=K, epoch_losses=torch.tensor(losses), files=files)
+                    continue
                 data = torch.load(os.path.join("Data", c["data_type"], "data.pt"))
                 test_idx = np.loadtxt(os.path.join("Data", c["data_type"], "test_index1.csv"), delimiter=",")
                 mask = torch.load(os.path.join("Data", c["data_type"], f"mask_{c['missing_rate']}_missing1.pt"))
@@ -312,6 +317,7 @@ def mnar_driver_cases(V, E):
 
 
 def main():
+    sys.path.insert(0, os.path.dirname(HERE))
     V, E = _import_reference()
     torch.set_num_threads(1)
     fx = {}
@@ -328,10 +334,24 @@ def main():
     fx["mnar_reg_v2_b16_d8_s5"] = mnar_case(V, "REG_notMIWAE_v2", 16, 8, 5, 20, 1.0)
     fx["mnar_reg_v2_b9_d50_s20_a06"] = mnar_case(V, "REG_notMIWAE_v2", 9, 50, 20, 21, 0.6)
     fx["mnar_vanilla_b16_d8_s5"] = mnar_case(V, "notMIWAE_myversion", 16, 8, 5, 22, 1.0)
+    # mask-augmented zero-imputation family (VAE.py:510-667, 995-1116): first layer reads [x*mask, mask]
+    fx["reg_vae_mask_b64_d13"] = reg_case(V, "Reg_VAE_mask", 64, 13, 20, 30, 1.0)
+    fx["reg_vae_mask_b37_d20_a05"] = reg_case(V, "Reg_VAE_mask", 37, 20, 20, 31, 0.5)
+    fx["vanilla_vae_mask_b64_d13"] = vanilla_case(V, "vanilla_VAE_mask", 64, 13, 20, 32)
+    fx["traj_reg_vae_mask_b32_d13"] = train_traj_case(V, "Reg_VAE_mask", 32, 13, 20, 33, 4)
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     if "--skip-drivers" not in sys.argv:
-        fx["drivers_synth_150x6"] = driver_cases(V, E)
-        fx["drivers_mnar_40x6"] = mnar_driver_cases(V, E)
+        from synth import MASK_DRIVER_CASES
+        if not only or "drivers_synth_150x6" in only:
+            fx["drivers_synth_150x6"] = driver_cases(V, E)
+        if not only or "drivers_mnar_40x6" in only:
+            fx["drivers_mnar_40x6"] = mnar_driver_cases(V, E)
+        if not only or "drivers_mask_augm_150x6" in only:
+            # imputation.py call sequence only: active_learning.py never selects the mask-augmented family
+            fx["drivers_mask_augm_150x6"] = driver_cases(V, E, MASK_DRIVER_CASES, with_al=False)
     for name, d in fx.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, name + ".pt")
         torch.save(d, path)
         print(f"{name}: {os.path.getsize(path) / 1024:.1f} KB")

@@ -33,6 +33,11 @@ DRIVER_CASES = [
     ("vanilla_vae", "vanilla_vae1", 20),
     ("vanilla_eddi", "vanilla_EDDI1", 20),
 ]
+#: imputation_args.json lines 16-18 / 31-33 ("*_mask_augm"): Reg_VAE_mask / vanilla_VAE_mask (imputation.py path only)
+MASK_DRIVER_CASES = [
+    ("reg_vae_mask", "reg_vae1_mask_augm", 20),
+    ("vanilla_vae_mask", "vanilla_vae1_mask_augm", 20),
+]
 DRIVER_CFG = dict(data_type="synth", n_rows=150, obs_dim=6, batch_size=64, epochs=3, M_eval=2, M_al=3,
                   missing_rate=30, p_missingness=30, alpha=1.0, reg_type="kl_reg",
                   experiment_type="UCI_experiments_consistency_missingness")

@@ -42,6 +42,8 @@ def test_layout_helpers_and_argument_validation_without_gpu():
     assert L.param_count(L.model(L.FAMILY_MLP, 100)) == 31920
     assert L.param_count(L.model(L.FAMILY_PNP, 13, 20)) == 15866
     assert L.param_count(L.model(L.FAMILY_PNP, 100, 20)) == 26480
+    assert L.param_count(L.model(L.FAMILY_MLP_MASK, 13)) == 14433 + 100 * 13     # first layer [100, 2D], VAE.py:526
+    assert L.param_offsets(L.model(L.FAMILY_MLP_MASK, 100))[:3] == [0, 20000, 20100]
     offs = L.param_offsets(L.model(L.FAMILY_PNP, 100, 20))
     assert len(offs) == 17 and offs[0] == 0 and offs[-1] == 26480
     assert L.decoder_offset(m) == 7470

@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from synth import DRIVER_CASES, DRIVER_CFG, make_tree  # noqa: E402
+from synth import DRIVER_CASES, DRIVER_CFG, MASK_DRIVER_CASES, make_tree  # noqa: E402
 
 
 def _pkg():
@@ -42,7 +42,7 @@ class FeedNoise:
 
 
 @pytest.mark.parametrize("name", ["reg_vae_b64_d13", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07",
-                                  "reg_vae_b37_d20_a05"])
+                                  "reg_vae_b37_d20_a05", "reg_vae_mask_b64_d13", "reg_vae_mask_b37_d20_a05"])
 def test_module_api_autograd_matches_reference(golden, name):
     VAE, *_ = _pkg()
     g = golden(name)
@@ -77,7 +77,7 @@ def test_module_api_autograd_matches_reference(golden, name):
         torch.testing.assert_close(got.cpu(), g[key], rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20"])
+@pytest.mark.parametrize("name", ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20", "vanilla_vae_mask_b64_d13"])
 def test_vanilla_module_api(golden, name):
     VAE, *_ = _pkg()
     g = golden(name)
@@ -117,13 +117,14 @@ def test_empty_batch_guard():
     assert z.shape == m.shape == lv.shape == (0, 10)                  # VAE.py:723-724
 
 
-@pytest.mark.parametrize("name,vae_type,K", DRIVER_CASES)
+@pytest.mark.parametrize("name,vae_type,K", DRIVER_CASES + MASK_DRIVER_CASES)
 def test_driver_sequence_matches_reference_artifacts(golden, tmp_path, name, vae_type, K):
     """imputation.py:28-59 and active_learning.py:58-74 call sequences through the mirror on the GPU, same
     seeds, parity (host-noise) mode; every .pt artefact must match what the reference wrote on CPU."""
     VAE, train_mod, evaluate, loaders, inject = _pkg()
     c = DRIVER_CFG
-    g = golden("drivers_synth_150x6")[name]
+    mask_augm = "mask_augm" in vae_type              # imputation.py path only: active_learning.py never selects it
+    g = golden("drivers_mask_augm_150x6" if mask_augm else "drivers_synth_150x6")[name]
     make_tree(str(tmp_path), c["data_type"], c["n_rows"], c["obs_dim"], seed=0, missing_rate=c["missing_rate"],
               experiment_type=c["experiment_type"])
     cwd = os.getcwd()
@@ -151,10 +152,11 @@ def test_driver_sequence_matches_reference_artifacts(golden, tmp_path, name, vae
         test_idx = np.loadtxt(os.path.join("Data", c["data_type"], "test_index1.csv"), delimiter=",")
         mask = torch.load(os.path.join("Data", c["data_type"], f"mask_{c['missing_rate']}_missing1.pt"))
         norm = (data - data.min(axis=0).values) / (data.max(axis=0).values - data.min(axis=0).values)
-        evaluate.active_learning_func(tr[0], norm[test_idx], mask[test_idx], c["missing_rate"], obs_dim, 500, K,
-                                      c["M_al"], 10, c["data_type"], tp, c["experiment_type"], vae_type, c["epochs"],
-                                      5000, 10, device=dev, alpha=c["alpha"], p_missingness=c["p_missingness"],
-                                      reg_type=c["reg_type"], Repeat=1)
+        if not mask_augm:
+            evaluate.active_learning_func(tr[0], norm[test_idx], mask[test_idx], c["missing_rate"], obs_dim, 500, K,
+                                          c["M_al"], 10, c["data_type"], tp, c["experiment_type"], vae_type,
+                                          c["epochs"], 5000, 10, device=dev, alpha=c["alpha"],
+                                          p_missingness=c["p_missingness"], reg_type=c["reg_type"], Repeat=1)
         checked = 0
         for rel, ref in g["files"].items():
             path = os.path.join("experiments", rel)

@@ -19,7 +19,10 @@ def _mods():
 
 
 def fam_of(p, L):
-    return L.FAMILY_PNP if "type_pars1" in p else L.FAMILY_MLP
+    if "type_pars1" in p:
+        return L.FAMILY_PNP
+    w1 = p["seq_encoder.0.weight"]                       # mask-augmented family: fan-in 2D (reference VAE.py:526)
+    return L.FAMILY_MLP_MASK if w1.shape[1] == 2 * p["seq_decoder.4.bias"].numel() else L.FAMILY_MLP
 
 
 def dims(p):
@@ -58,8 +61,9 @@ def train_tc(request):
     L.load().pcvae_set_train_tensor_cores(prev)
 
 
-REG = ["reg_vae_b64_d13", "reg_vae_b37_d20_a05", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07"]
-VAN = ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20"]
+REG = ["reg_vae_b64_d13", "reg_vae_b37_d20_a05", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07",
+       "reg_vae_mask_b64_d13", "reg_vae_mask_b37_d20_a05"]
+VAN = ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20", "vanilla_vae_mask_b64_d13"]
 
 
 @pytest.mark.parametrize("name", REG)
@@ -112,7 +116,7 @@ def test_golden_vanilla_fused_step(golden, name):
         grad_close(grads[k], ref, k)
 
 
-@pytest.mark.parametrize("name", ["traj_reg_vae_b32_d13", "traj_reg_eddi_b32_d13_k10"])
+@pytest.mark.parametrize("name", ["traj_reg_vae_b32_d13", "traj_reg_eddi_b32_d13_k10", "traj_reg_vae_mask_b32_d13"])
 def test_golden_training_trajectory_with_adam(golden, name, train_tc):
     KR, L = _mods()
     g = golden(name)
@@ -143,7 +147,9 @@ def rand_case(family, B, D, K, seed, mask_float=False):
 SHAPES = [("mlp", 1, 4, 0), ("mlp", 129, 8, 0), ("mlp", 300, 100, 0), ("mlp", 257, 104, 0), ("pnp", 131, 12, 10),
           ("mlp", 1, 2, 0), ("mlp", 63, 13, 0), ("mlp", 65, 50, 0), ("mlp", 200, 100, 0), ("mlp", 130, 101, 0),
           ("mlp", 70, 128, 0), ("pnp", 1, 2, 10), ("pnp", 65, 13, 20), ("pnp", 200, 100, 20), ("pnp", 97, 50, 7),
-          ("pnp", 64, 128, 20)]
+          ("pnp", 64, 128, 20),
+          ("mlp_mask", 1, 2, 0), ("mlp_mask", 65, 13, 0), ("mlp_mask", 130, 50, 0), ("mlp_mask", 200, 100, 0),
+          ("mlp_mask", 97, 21, 0)]
 
 
 @pytest.mark.parametrize("family,B,D,K", SHAPES)
@@ -162,7 +168,7 @@ def test_fused_step_vs_oracle_random_shapes(family, B, D, K, alpha, train_tc):
         grad_close(grads[k], ref_grads[k], k)
 
 
-@pytest.mark.parametrize("family,B,D,K", [("mlp", 100, 20, 0), ("pnp", 100, 20, 10)])
+@pytest.mark.parametrize("family,B,D,K", [("mlp", 100, 20, 0), ("pnp", 100, 20, 10), ("mlp_mask", 100, 20, 0)])
 def test_modular_ops_vs_oracle(family, B, D, K):
     """decoder backward from an arbitrary d_xhat, encoder backward from arbitrary d_mean/d_logvar,
     and the stand-alone loss kernel (what the nn.Module API composes)."""

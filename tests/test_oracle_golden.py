@@ -12,8 +12,9 @@ def close(a, b, rtol=RTOL, atol=1e-6):
     torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
 
 
-REG = ["reg_vae_b64_d13", "reg_vae_b37_d20_a05", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07"]
-VAN = ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20"]
+REG = ["reg_vae_b64_d13", "reg_vae_b37_d20_a05", "reg_eddi_b64_d13_k20", "reg_eddi_b33_d7_k10_a07",
+       "reg_vae_mask_b64_d13", "reg_vae_mask_b37_d20_a05"]
+VAN = ["vanilla_vae_b64_d13", "vanilla_eddi_b64_d13_k20", "vanilla_vae_mask_b64_d13"]
 
 
 @pytest.mark.parametrize("name", REG)
@@ -53,7 +54,7 @@ def test_vanilla(golden, name):
     close(ev, g["eval_loss"]); close(negl, g["negl"]); close(negl_imp, g["negl_imp"])
 
 
-@pytest.mark.parametrize("name", ["traj_reg_vae_b32_d13", "traj_reg_eddi_b32_d13_k10"])
+@pytest.mark.parametrize("name", ["traj_reg_vae_b32_d13", "traj_reg_eddi_b32_d13_k10", "traj_reg_vae_mask_b32_d13"])
 def test_training_trajectory(golden, name):
     g = golden(name)
     p = {k: v.clone() for k, v in g["state_dict0"].items()}

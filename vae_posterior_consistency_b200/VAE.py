@@ -218,9 +218,9 @@ class _VanillaMixin:
         return mean_q, logvar_q, x_mean_q, x_logvar_q
 
 
-def _mlp_encoder(obs_dim, latent_dim):
-    return nn.Sequential(nn.Linear(obs_dim, 100), nn.ReLU(), nn.Linear(100, 50), nn.ReLU(),
-                         nn.Linear(50, 2 * latent_dim))
+def _mlp_encoder(obs_dim, latent_dim, mask_augmented=False):
+    return nn.Sequential(nn.Linear(2 * obs_dim if mask_augmented else obs_dim, 100), nn.ReLU(), nn.Linear(100, 50),
+                         nn.ReLU(), nn.Linear(50, 2 * latent_dim))
 
 
 class Reg_VAE(_RegMixin, _PartialVAEBase):
@@ -234,7 +234,7 @@ class Reg_VAE(_RegMixin, _PartialVAEBase):
                           num_estimates)
         self.K = K
         self.reg_type = reg_type
-        self.seq_encoder = _mlp_encoder(obs_dim, latent_dim)
+        self.seq_encoder = _mlp_encoder(obs_dim, latent_dim, self.FAMILY == L.FAMILY_MLP_MASK)
         self._init_decoder_and_prior()
         self._init_prior()
 
@@ -258,7 +258,7 @@ class vanilla_VAE(_VanillaMixin, _PartialVAEBase):
         self._init_common(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, num_samples,
                           num_estimates)
         self.K = K
-        self.seq_encoder = _mlp_encoder(obs_dim, latent_dim)
+        self.seq_encoder = _mlp_encoder(obs_dim, latent_dim, self.FAMILY == L.FAMILY_MLP_MASK)
         self._init_decoder_and_prior()
         self._init_prior()
 
@@ -267,6 +267,26 @@ class vanilla_VAE(_VanillaMixin, _PartialVAEBase):
              beta=1.0, alpha=0.8, alpha_annealing=True, stage='train'):
         return self._vanilla_loss(x, x_recon_q, x_logvar_q, mean_q, logvar_q, epoch, mask, vae_elbo, llh_eval, MI,
                                   beta_annealing, beta, stage)
+
+
+class Reg_VAE_mask(Reg_VAE):
+    """Mask-augmented regularised VAE, reference VAE.py:510-667: the first encoder layer reads
+    `stack([x*mask, mask], 1).reshape(-1, 2D)` = [x*mask | mask] (:547); decoder, loss body and forward are
+    Reg_VAE's.  Only the keyword order of `loss` differs (alpha_annealing before stage, :560-563)."""
+    FAMILY = L.FAMILY_MLP_MASK          # Reg_VAE.__init__ builds the 2D-wide first layer from this (same RNG order)
+
+    def loss(self, x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q, mask, mask_p,
+             epoch,
+             vae_elbo=False, llh_eval=False, MI=False, beta_annealing=False,
+             beta=1.0, alpha=0.8, alpha_annealing=True, stage='train'):
+        return self._reg_loss(x, x_recon_p, x_logvar_p, mean_p, logvar_p, x_recon_q, x_logvar_q, mean_q, logvar_q,
+                              mask, mask_p, epoch, vae_elbo, llh_eval, MI, beta_annealing, beta, alpha, stage,
+                              alpha_annealing)
+
+
+class vanilla_VAE_mask(vanilla_VAE):
+    """Mask-augmented vanilla VAE, reference VAE.py:995-1116 (encoder :1031-1033, loss as vanilla_VAE)."""
+    FAMILY = L.FAMILY_MLP_MASK
 
 
 def _init_pnp(self, K, training_parameters, xavier):
@@ -478,7 +498,8 @@ class notMIWAE_myversion(_NotMIWAEBase):
 
 
 IN_SCOPE = {"REG_notMIWAE_v2": REG_notMIWAE_v2, "notMIWAE_myversion": notMIWAE_myversion,
-            "Reg_VAE": Reg_VAE, "vanilla_VAE": vanilla_VAE, "Reg_EDDI": Reg_EDDI, "vanilla_EDDI": vanilla_EDDI}
+            "Reg_VAE": Reg_VAE, "vanilla_VAE": vanilla_VAE, "Reg_EDDI": Reg_EDDI, "vanilla_EDDI": vanilla_EDDI,
+            "Reg_VAE_mask": Reg_VAE_mask, "vanilla_VAE_mask": vanilla_VAE_mask}
 
 
 def _out_of_scope(name):
@@ -492,6 +513,6 @@ def _out_of_scope(name):
 
 
 # names src/utils/loaders.py:2-5 imports; the out-of-scope ones fail loudly when instantiated
-for _n in ("Flow", "MIWAE", "Reg_MIWAE", "vanilla_VAE_mask", "Reg_VAE_mask", "notMIWAE", "REG_notMIWAE",
+for _n in ("Flow", "MIWAE", "Reg_MIWAE", "notMIWAE", "REG_notMIWAE",
            "REG_notMIWAE_new_version", "REG_VAEFlow", "VAEFlow", "vanilla_EDDI_mnist", "Reg_EDDI_mnist"):
     globals()[_n] = _out_of_scope(_n)

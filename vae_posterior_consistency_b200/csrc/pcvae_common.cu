@@ -17,12 +17,13 @@ int fail(int code, const char* fmt, ...) {
 
 bool make_layout(const pcvae_model* m, Layout* L) {
     if (!m) { fail(PCVAE_EINVAL, "null model"); return false; }
-    if (m->family != PCVAE_FAMILY_MLP && m->family != PCVAE_FAMILY_PNP) { fail(PCVAE_EINVAL, "unknown family %d", m->family); return false; }
+    if (m->family != PCVAE_FAMILY_MLP && m->family != PCVAE_FAMILY_PNP && m->family != PCVAE_FAMILY_MLP_MASK) { fail(PCVAE_EINVAL, "unknown family %d", m->family); return false; }
     if (m->obs_dim < 1 || m->obs_dim > MAX_D) { fail(PCVAE_EINVAL, "obs_dim %d outside [1,%d]", m->obs_dim, MAX_D); return false; }
     if (m->latent_dim != LAT) { fail(PCVAE_EINVAL, "latent_dim must be %d (got %d)", LAT, m->latent_dim); return false; }
     const int D = m->obs_dim;
     int K = 0, o = 0;
-    L->fam = m->family; L->D = D;
+    L->aug = m->family == PCVAE_FAMILY_MLP_MASK ? 1 : 0;
+    L->fam = L->aug ? PCVAE_FAMILY_MLP : m->family; L->D = D;
     L->E = L->bE = L->We = L->be = 0;
     if (m->family == PCVAE_FAMILY_PNP) {
         K = m->emb_dim;
@@ -33,7 +34,7 @@ bool make_layout(const pcvae_model* m, Layout* L) {
         L->be = o; o += K;
     }
     L->K = K;
-    const int in1 = (m->family == PCVAE_FAMILY_PNP) ? K : D;
+    const int in1 = (m->family == PCVAE_FAMILY_PNP) ? K : (L->aug ? 2 * D : D);
     L->W1 = o; o += H1 * in1;
     L->b1 = o; o += H1;
     L->W2 = o; o += H2 * H1;

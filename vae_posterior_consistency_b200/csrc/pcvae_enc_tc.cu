@@ -357,7 +357,7 @@ static size_t enc_bwd_tc_smem() { return (size_t)2 * (Y3_C * Y3_N * 4 + Y2_C * Y
 
 }  // namespace tc
 
-bool enc_tc_supported(const Layout& L) { return L.fam == PCVAE_FAMILY_MLP && L.D % 4 == 0 && L.D >= 4 && L.D <= 100; }
+bool enc_tc_supported(const Layout& L) { return L.fam == PCVAE_FAMILY_MLP && !L.aug && L.D % 4 == 0 && L.D >= 4 && L.D <= 100; }
 
 void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw) {
     const long nvt = tc_nvt(rows, nbr), n = nvt * 128;

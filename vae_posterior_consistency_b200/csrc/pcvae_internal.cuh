@@ -21,7 +21,8 @@ constexpr int MAX_D = 128, MAX_K = 32;
 
 // offsets (floats) of every parameter tensor in the flat vector, see pcvae_b200.h
 struct Layout {
-    int fam, D, K;
+    int fam, D, K;                     // fam: PCVAE_FAMILY_MLP or _PNP (MLP_MASK is MLP with aug = 1)
+    int aug;                           // 1: first encoder layer reads [x*mask, mask] (2D inputs), VAE.py:547
     int E, bE, We, be;                 // PNP only
     int W1, b1, W2, b2, W3, b3;        // encoder MLP (first layer input = D or K)
     int W4, b4, W5, b5, W6, b6;        // decoder

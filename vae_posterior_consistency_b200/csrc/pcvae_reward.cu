@@ -403,6 +403,7 @@ int pcvae_reward_chain(const pcvae_reward_params* p, void* stream) {
     if (!p->theta || !p->x || !p->mask || !p->im || !p->R || !p->workspace) return fail(PCVAE_EINVAL, "reward_chain: null pointer");
     const WsPlan w = plan_ws(L, p->rows, p->samples);
     if (p->workspace_bytes < w.total) return fail(PCVAE_EWORKSPACE, "reward_chain: workspace %zu < %zu bytes", p->workspace_bytes, w.total);
+    if (L.aug) return fail(PCVAE_EINVAL, "reward_chain: the mask-augmented family has no reward kernel (active_learning.py never selects it)");
     if (L.fam == PCVAE_FAMILY_PNP && !p->pnp_ac) return fail(PCVAE_EINVAL, "reward_chain: PNP family needs pnp_ac workspace");
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)p->workspace;

@@ -81,15 +81,16 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
     constexpr int P = TM + 4;
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
-    const int IN1 = (FAM == PCVAE_FAMILY_MLP) ? D : K;
+    const int IN1 = (FAM == PCVAE_FAMILY_MLP) ? (a.L.aug ? 2 * D : D) : K;
+    const int INR = (FAM == PCVAE_FAMILY_MLP) ? IN1 : D;          // feature rows of in_s
     float* W1_s = smem;
     float* b1_s = W1_s + IN1 * H1;
     float* W2_s = b1_s + H1;
     float* b2_s = W2_s + H1 * H2P;
     float* W3_s = b2_s + H2P;
     float* b3_s = W3_s + H2 * LAT2;
-    float* in_s = b3_s + LAT2;            // [D][P]  MLP: x*mask   PNP: x
-    float* h1_s = in_s + D * P;           // [100][P]
+    float* in_s = b3_s + LAT2;            // [INR][P]  MLP: x*mask (, mask)   PNP: x
+    float* h1_s = in_s + INR * P;         // [100][P]
     float* h2_s = h1_s + H1 * P;          // [52][P]
     float* o_s = h2_s + H2P * P;          // [20][P]
     float* ms_s = o_s + LAT2 * P;         // PNP [D][P]
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
                 return v;
             },
             [&](int d, int r, bool, XM v) {
-                if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = v.x * v.m;
+                if (FAM == PCVAE_FAMILY_MLP) { in_s[d * P + r] = v.x * v.m; if (a.L.aug) in_s[(D + d) * P + r] = v.m; }
                 else { in_s[d * P + r] = v.x; ms_s[d * P + r] = v.m; }
             });
         __syncthreads();
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd(const EncFwdArgs a) {
             __syncthreads();
             gemm_fwd<TM, RB, ACT_RELU>(agg_s, W1_s, b1_s, h1_s, K, H1, tid);
         } else {
-            gemm_fwd<TM, RB, ACT_RELU>(in_s, W1_s, b1_s, h1_s, D, H1, tid);
+            gemm_fwd<TM, RB, ACT_RELU>(in_s, W1_s, b1_s, h1_s, IN1, H1, tid);
         }
         __syncthreads();
         gemm_fwd<TM, RB, ACT_RELU, 2>(h1_s, W2_s, b2_s, h2_s, H1, H2P, tid);
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
     constexpr int P = TM + 4;
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
-    const int IN1 = (FAM == PCVAE_FAMILY_MLP) ? D : K;
+    const int IN1 = (FAM == PCVAE_FAMILY_MLP) ? (a.L.aug ? 2 * D : D) : K;
+    const int INR = (FAM == PCVAE_FAMILY_MLP) ? IN1 : D;               // feature rows of in_s
     float* W2_s = smem;                        // [100][52]
     float* W3_s = W2_s + H1 * H2P;             // [50][20]
     float* dW1_s = W3_s + H2 * LAT2;           // [IN1][100]
@@ -198,8 +200,8 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
     float* db2_s = dW2_s + H1 * H2P;
     float* dW3_s = db2_s + H2P;                // [50][20]
     float* db3_s = dW3_s + H2 * LAT2;
-    float* in_s = db3_s + LAT2;                // [D][P]
-    float* h1_s = in_s + D * P;                // [100][P]
+    float* in_s = db3_s + LAT2;                // [INR][P]
+    float* h1_s = in_s + INR * P;              // [100][P]
     float* h2_s = h1_s + H1 * P;               // [52][P]
     float* d3_s = h2_s + H2P * P;              // [20][P]
     float* ms_s = d3_s + LAT2 * P;             // PNP [D][P]
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
                 return v;
             },
             [&](int d, int r, bool, XM v) {
-                if (FAM == PCVAE_FAMILY_MLP) in_s[d * P + r] = v.x * v.m;
+                if (FAM == PCVAE_FAMILY_MLP) { in_s[d * P + r] = v.x * v.m; if (a.L.aug) in_s[(D + d) * P + r] = v.m; }
                 else { in_s[d * P + r] = v.x; ms_s[d * P + r] = v.m; }
             });
         {
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_bwd(const EncBwdArgs a) {
         gemm_dx<TM, RB, true>(h2_s, W2_s, h1_s, H1, H2P, tid);      // h1_s <- dL/d(pre1)
         __syncthreads();
         if (FAM == PCVAE_FAMILY_MLP) {
-            gemm_dw<TM>(in_s, h1_s, dW1_s, D, H1, H1, tid);
+            gemm_dw<TM>(in_s, h1_s, dW1_s, IN1, H1, H1, tid);
             bias_dw<TM>(h1_s, db1_s, H1, tid);
         } else {
             gemm_dw<TM, 2>(agg_s, h1_s, dW1_s, K, H1, H1, tid);
@@ -744,17 +746,19 @@ static int g_train_tc = 1;
 
 static size_t enc_fwd_smem(const Layout& L) {
     const int P = TM_TRAIN + 4, K4 = round4(L.K);
-    const int in1 = L.fam == PCVAE_FAMILY_MLP ? L.D : L.K;
-    size_t f = (size_t)in1 * H1 + H1 + H1 * H2P + H2P + H2 * LAT2 + LAT2 + (size_t)(L.D + H1 + H2P + LAT2) * P;
+    const int in1 = L.fam == PCVAE_FAMILY_MLP ? (L.aug ? 2 * L.D : L.D) : L.K;
+    const int inr = L.fam == PCVAE_FAMILY_MLP ? in1 : L.D;
+    size_t f = (size_t)in1 * H1 + H1 + H1 * H2P + H2P + H2 * LAT2 + LAT2 + (size_t)(inr + H1 + H2P + LAT2) * P;
     if (L.fam == PCVAE_FAMILY_PNP) f += (size_t)L.D * P + 2 * L.D * K4 + K4 * P;
     return f * sizeof(float);
 }
 
 static size_t enc_bwd_smem(const Layout& L) {
     const int P = TM_TRAIN + 4, K4 = round4(L.K);
-    const int in1 = L.fam == PCVAE_FAMILY_MLP ? L.D : L.K;
+    const int in1 = L.fam == PCVAE_FAMILY_MLP ? (L.aug ? 2 * L.D : L.D) : L.K;
+    const int inr = L.fam == PCVAE_FAMILY_MLP ? in1 : L.D;
     size_t f = (size_t)H1 * H2P + H2 * LAT2 + ((size_t)in1 * H1 + H1 + H1 * H2P + H2P + H2 * LAT2 + LAT2) +
-               (size_t)(L.D + H1 + H2P + LAT2) * P;
+               (size_t)(inr + H1 + H2P + LAT2) * P;
     if (L.fam == PCVAE_FAMILY_PNP) f += (size_t)L.D * P + K4 * P + L.K * H1 + 4 * L.D * K4;
     return f * sizeof(float);
 }
@@ -791,7 +795,7 @@ int pcvae_param_offsets(const pcvae_model* m, long* offsets) {
     Layout L;
     if (!make_layout(m, &L)) return -1;
     int n = 0;
-    if (m->family == PCVAE_FAMILY_PNP) { offsets[n++] = L.E; offsets[n++] = L.bE; offsets[n++] = L.We; offsets[n++] = L.be; }
+    if (L.fam == PCVAE_FAMILY_PNP) { offsets[n++] = L.E; offsets[n++] = L.bE; offsets[n++] = L.We; offsets[n++] = L.be; }
     const int rest[12] = {L.W1, L.b1, L.W2, L.b2, L.W3, L.b3, L.W4, L.b4, L.W5, L.b5, L.W6, L.b6};
     for (int i = 0; i < 12; ++i) offsets[n++] = rest[i];
     offsets[n] = L.total;

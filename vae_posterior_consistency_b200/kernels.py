@@ -41,7 +41,8 @@ def unflatten_params(theta: torch.Tensor, family: int, obs_dim: int, emb_dim: in
     m = L.model(family, obs_dim, emb_dim)
     offs = L.param_offsets(m)
     D, K = obs_dim, emb_dim
-    shapes = ([(D, K), (D, 1), (K, K + 2), (K,), (100, K), (100,)] if family == L.FAMILY_PNP else [(100, D), (100,)])
+    in1 = 2 * D if family == L.FAMILY_MLP_MASK else D        # Reg_VAE_mask / vanilla_VAE_mask, reference VAE.py:526
+    shapes = ([(D, K), (D, 1), (K, K + 2), (K,), (100, K), (100,)] if family == L.FAMILY_PNP else [(100, in1), (100,)])
     shapes += [(50, 100), (50,), (20, 50), (20,), (50, 10), (50,), (100, 50), (100,), (D, 100), (D,)]
     keys = param_keys(family)
     return {k: theta[offs[i]:offs[i + 1]].view(*shapes[i]) for i, k in enumerate(keys)}

@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcvae_b200.so")
 
-FAMILY_MLP, FAMILY_PNP = 0, 1
+FAMILY_MLP, FAMILY_PNP, FAMILY_MLP_MASK = 0, 1, 2     # MLP_MASK: first encoder layer reads [x*mask, mask]
 MASK_U8, MASK_F32 = 0, 1
 DEC_FWD, DEC_BWD, DEC_TRAIN, DEC_EVAL = 0, 1, 2, 3
 NSUMS = 8

@@ -6,9 +6,10 @@ import torch
 from numpy import loadtxt
 from torch.utils.data import DataLoader
 
-from .VAE import REG_notMIWAE_v2, Reg_EDDI, Reg_VAE, notMIWAE_myversion, vanilla_EDDI, vanilla_VAE
+from .VAE import (REG_notMIWAE_v2, Reg_EDDI, Reg_VAE, Reg_VAE_mask, notMIWAE_myversion, vanilla_EDDI, vanilla_VAE,
+                  vanilla_VAE_mask)
 
-_OUT_OF_SCOPE = ("flow", "mask_augm", "reg_MIWAE")
+_OUT_OF_SCOPE = ("flow", "reg_MIWAE")
 
 
 def _strip_digits(s):
@@ -34,9 +35,11 @@ def model_loader(stage, obs_dim, hid_dim, K, latent_dim, missing_rate, data_type
             raise NotImplementedError(f"vae_type {vae_type!r} selects a family outside the B200 hot path "
                                       "(SURVEY.md section 8f); use the reference's eager implementation")
     if 'reg_vae' in vae_type:
-        model = Reg_VAE(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, reg_type, num_samples,
-                        num_estimates)
-        load_dir = _strip_digits(vae_type)
+        # loaders.py:51-89: '*_mask_augm' selects the mask-augmented class and always loads from .../reg_vae/
+        cls = Reg_VAE_mask if 'mask_augm' in vae_type else Reg_VAE
+        model = cls(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, reg_type, num_samples,
+                    num_estimates)
+        load_dir = 'reg_vae' if 'mask_augm' in vae_type else _strip_digits(vae_type)
     elif 'reg_notMIWAE' in vae_type:
         model = REG_notMIWAE_v2(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
         load_dir = _strip_digits(vae_type)
@@ -47,8 +50,9 @@ def model_loader(stage, obs_dim, hid_dim, K, latent_dim, missing_rate, data_type
                          num_estimates)
         load_dir = _strip_digits(vae_type)
     elif 'vanilla_vae' in vae_type:
-        model = vanilla_VAE(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, num_samples,
-                            num_estimates)
+        cls = vanilla_VAE_mask if 'mask_augm' in vae_type else vanilla_VAE          # loaders.py:149-184
+        model = cls(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, num_samples,
+                    num_estimates)
         load_dir = 'vanilla_vae'
     elif 'vanilla_EDDI' in vae_type:
         if data_type == 'mnist':
