@@ -182,19 +182,21 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
                 }
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c16 + j < TCW_H4) h4T[(c16 + j) * 32] = v[j];
+                scratch_store(h4T, c16, TCW_H4, v, 16);
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, f5h, f5l, fs5, F5_C / 2, idF5); });
 
             // ---- h5 = relu(acc5) | 1 -> RA, HBM ----
             uint32_t m5 = 0;                                  // relu mask of this thread's 28 h5 columns
+            float acc[28];
+            tmem_ld28(lane_addr + ACC1 + c28, acc);
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
                 float v[16], lo[16];
-                ld_part(lane_addr + ACC1 + c28, part, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt) v[j] = acc[j0 + j];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
@@ -203,9 +205,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < cnt && c28 + j0 + j < TCW_H5) h5T[(c28 + j0 + j) * 32] = v[j];
+                scratch_store(h5T, c28 + j0, TCW_H5, v, cnt);
             }
             reluT[cg] = m5;
             reluT[4 + cg] = m4;
@@ -373,8 +373,17 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
             // ---- dpre6 (HBM) -> RA: all 28 loads of the thread in flight before the first TMEM store ----
             {
                 float d6[28];
+                {   // one base pointer, immediate offsets; the all-valid case (warp-uniform in c28) has no per-element test
+                    const float* __restrict__ p6 = dp6T + (size_t)c28 * 32;
+                    const int nv = ok ? min(28, TCW_H5 - c28) : 0;
+                    if (__all_sync(0xffffffffu, nv == 28)) {
 #pragma unroll
-                for (int j = 0; j < 28; ++j) d6[j] = (ok && c28 + j < TCW_H5) ? dp6T[(c28 + j) * 32] : 0.f;
+                        for (int j = 0; j < 28; ++j) d6[j] = p6[j * 32];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 28; ++j) d6[j] = j < nv ? p6[j * 32] : 0.f;
+                    }
+                }
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {
                     const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
@@ -386,25 +395,44 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                     st_part(lane_addr + RA_LO + c28, part, lo);
                 }
             }
+            // latent-space inputs of this thread's (up to four) latents, see the last epilogue of the item: requested here
+            // so that their latency hides under the three MMA stages instead of being exposed after the last one
+            float lat_mq[4] = {0.f, 0.f, 0.f, 0.f}, lat_lq[4] = {0.f, 0.f, 0.f, 0.f}, lat_mp[4] = {0.f, 0.f, 0.f, 0.f},
+                  lat_lp[4] = {0.f, 0.f, 0.f, 0.f}, lat_e[4] = {0.f, 0.f, 0.f, 0.f};
+            if (cg < 3 && ok) {
+                const long g0 = (long)grow * LAT + 4 * cg;
+                auto ld4 = [&](const float* p, float* o) {
+                    const float2 u = *reinterpret_cast<const float2*>(p + g0);
+                    o[0] = u.x; o[1] = u.y;
+                    if (cg < 2) { const float2 w2 = *reinterpret_cast<const float2*>(p + g0 + 2); o[2] = w2.x; o[3] = w2.y; }
+                };
+                ld4(a.mean[0], lat_mq);
+                ld4(a.logvar[0], lat_lq);
+                if (a.nbr > 1) { ld4(a.mean[1], lat_mp); ld4(a.logvar[1], lat_lp); }
+                if (a.eps[br]) ld4(a.eps[br], lat_e);
+            }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, x6h, x6l, xs6, X6_C / 2, idX6); });
 
             // ---- dpre5 = dh5 * relu'(h5) -> RA, HBM ----
+            const uint32_t k5 = m5 & col_bits(c28, G2);                  // column G2 is the bias column
+            float acc[28];
+            tmem_ld28(lane_addr + ACC1 + c28, acc);
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
                 float v[16], lo[16];
-                ld_part(lane_addr + ACC1 + c28, part, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt) v[j] = acc[j0 + j];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
-                        if (!((m5 >> (j0 + j)) & 1u) || c28 + j0 + j >= G2) v[j] = 0.f;     // column G2 is the bias column
+                        if (!(k5 & (1u << (j0 + j)))) v[j] = 0.f;
                         lo[j] = tf32_lo(v[j]);
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < cnt && c28 + j0 + j < TCW_H5) dp5T[(c28 + j0 + j) * 32] = v[j];
+                scratch_store(dp5T, c28 + j0, TCW_H5, v, cnt);
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, x5h, x5l, xs5, X5_C / 2, idX5); });
 
@@ -412,16 +440,15 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
             {
                 float v[16], lo[16];
                 tmem_ld16(lane_addr + ACC2 + c16, v);
+                const uint32_t k4 = m4 & col_bits(c16, G1);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    if (!((m4 >> j) & 1u) || c16 + j >= G1) v[j] = 0.f;
+                    if (!(k4 & (1u << j))) v[j] = 0.f;
                     lo[j] = tf32_lo(v[j]);
                 }
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c16 + j < TCW_H4) dp4T[(c16 + j) * 32] = v[j];
+                scratch_store(dp4T, c16, TCW_H4, v, 16);
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, x4h, x4l, xs4, X4_C / 2, idX4); });
 
@@ -436,10 +463,10 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                         const int l = 4 * cg + li;
                         if (l >= LAT) continue;
                         const long gi = (long)grow * LAT + l;
-                        const float mq = a.mean[0][gi], lq = a.logvar[0][gi];
+                        const float mq = lat_mq[li], lq = lat_lq[li];
                         const float eq = expf(lq);
                         float mp_ = 0.f, lp = 0.f, ep = 1.f;
-                        if (a.nbr > 1) { mp_ = a.mean[1][gi]; lp = a.logvar[1][gi]; ep = expf(lp); }
+                        if (a.nbr > 1) { mp_ = lat_mp[li]; lp = lat_lp[li]; ep = expf(lp); }
                         const float dmu = mq - mp_;
                         if (br == 0) {
                             s_klq += 0.5f * (eq + mq * mq - 1.f - lq);
@@ -458,12 +485,12 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                                 gv += alpha * 0.5f * (expf(lq - lp) - 1.f);
                             }
                             gm = fmaf(gm, ls, dz);
-                            gv = fmaf(gv, ls, dz * 0.5f * expf(lq * 0.5f) * (a.eps[0] ? a.eps[0][gi] : 0.f));
+                            gv = fmaf(gv, ls, dz * 0.5f * expf(lq * 0.5f) * lat_e[li]);
                         } else {
                             gm = alpha * a.beta_w * mp_ - alpha * dmu / ep;
                             gv = alpha * a.beta_w * 0.5f * (ep - 1.f) + alpha * 0.5f * (1.f - (eq + dmu * dmu) / ep);
                             gm = fmaf(gm, ls, dz);
-                            gv = fmaf(gv, ls, dz * 0.5f * expf(lp * 0.5f) * (a.eps[1] ? a.eps[1][gi] : 0.f));
+                            gv = fmaf(gv, ls, dz * 0.5f * expf(lp * 0.5f) * lat_e[li]);
                         }
                         a.d_mean[br][gi] = gm;
                         a.d_logvar[br][gi] = gv;

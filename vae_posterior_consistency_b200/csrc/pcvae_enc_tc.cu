@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
     __syncthreads();
     image_linear(W1h, W1l, E1_N, th + L.W1, th + L.b1, H1, D, true, tid);        // constant-1 output -> bias column of layer 2
     image_linear(W2h, W2l, E2_N, th + L.W2, th + L.b2, H2, H1, true, tid);       // constant-1 output -> bias column of layer 3
-    image_linear(W3h, W3l, E3_N, th + L.W3, th + L.b3, LAT2, H2, false, tid);
+    // mean rows -> accumulator columns [0, 10), logvar rows -> [16, 26): both start on a 4-column boundary, so the latent
+    // epilogue can be split over the column groups with aligned 4-column TMEM loads
+    image_linear(W3h, W3l, E3_N, th + L.W3, th + L.b3, LAT, H2, false, tid);
+    image_linear(W3h + 16 * 4, W3l + 16 * 4, E3_N, th + L.W3 + LAT * H2, th + L.b3 + LAT, LAT, H2, false, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
@@ -144,11 +147,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                         if (j < cnt) { v[j] = xm[j0 + j]; lo[j] = tf32_lo(v[j]); }
                     st_part(lane_addr + RA_HI + c28, part, v);
                     st_part(lane_addr + RA_LO + c28, part, lo);
-                    if (save) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < cnt && c28 + j0 + j <= D) inT[(c28 + j0 + j) * 32] = v[j];
-                    }
+                    if (save) scratch_store(inT, c28 + j0, D + 1, v, cnt);
                 }
             }
             mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
@@ -158,11 +157,15 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
 
             // ---- h1 = relu(acc1) | 1 -> RA, HBM ----
             uint32_t m1 = 0;                                  // relu mask of this thread's 28 h1 columns
+            float acc[28];
+            tmem_ld28(lane_addr + ACC1 + c28, acc);
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
                 float v[16], lo[16];
-                ld_part(lane_addr + ACC1 + c28, part, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt) v[j] = acc[j0 + j];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
@@ -171,11 +174,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                     }
                 st_part(lane_addr + RA_HI + c28, part, v);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                if (save) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < cnt && c28 + j0 + j < ETW_H1) h1T[(c28 + j0 + j) * 32] = v[j];
-                }
+                if (save) scratch_store(h1T, c28 + j0, ETW_H1, v, cnt);
             }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, e2h, e2l, es2, E2_C / 2, idE2); });
 
@@ -192,42 +191,46 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
                 if (save) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c16 + j < ETW_H2) h2T[(c16 + j) * 32] = v[j];
+                    scratch_store(h2T, c16, ETW_H2, v, 16);
                     reluT[cg] = m1;
                     reluT[4 + cg] = m2;
                 }
             }
+            // the row's 10 latents are split over its column groups (4 + 4 + 2 + 0) so that no warp waits for one group
+            // doing all of them; the noise of the thread's latents is requested before the E3 MMAs are waited for
+            const int l0 = 4 * cg;
+            const long gl = (long)grow * LAT + l0;
+            float2 e01 = make_float2(0.f, 0.f), e23 = make_float2(0.f, 0.f);
+            if (cg < 3 && ok && a.z[br] && a.eps[br]) {
+                e01 = *reinterpret_cast<const float2*>(a.eps[br] + gl);
+                if (cg < 2) e23 = *reinterpret_cast<const float2*>(a.eps[br] + gl + 2);
+            }
             run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, e3h, e3l, es3, E3_C / 2, idE3); });
 
-            // ---- mean | logvar, reparameterisation (one row per thread of column group 0) ----
-            if (cg == 0) {
-                float o[LAT2];
-                tmem_ld16(lane_addr + ACC1, o);
-                tmem_ld4(lane_addr + ACC1 + 16, o + 16);
+            // ---- mean | logvar, reparameterisation ----
+            if (cg < 3) {
+                float mv[4], lv[4];
+                tmem_ld4(lane_addr + ACC1 + l0, mv);
+                tmem_ld4(lane_addr + ACC1 + 16 + l0, lv);
                 if (ok) {
-                    const long gi = (long)grow * LAT;
-                    float2* mo = reinterpret_cast<float2*>(a.mean[br] + gi);
-                    float2* lo_ = reinterpret_cast<float2*>(a.logvar[br] + gi);
-#pragma unroll
-                    for (int l = 0; l < LAT / 2; ++l) {
-                        mo[l] = make_float2(o[2 * l], o[2 * l + 1]);
-                        lo_[l] = make_float2(o[LAT + 2 * l], o[LAT + 2 * l + 1]);
+                    *reinterpret_cast<float2*>(a.mean[br] + gl) = make_float2(mv[0], mv[1]);
+                    *reinterpret_cast<float2*>(a.logvar[br] + gl) = make_float2(lv[0], lv[1]);
+                    if (cg < 2) {
+                        *reinterpret_cast<float2*>(a.mean[br] + gl + 2) = make_float2(mv[2], mv[3]);
+                        *reinterpret_cast<float2*>(a.logvar[br] + gl + 2) = make_float2(lv[2], lv[3]);
                     }
                     if (a.z[br]) {
-                        float2* zo = reinterpret_cast<float2*>(a.z[br] + gi);
-                        const float2* ep = a.eps[br] ? reinterpret_cast<const float2*>(a.eps[br] + gi) : nullptr;
-#pragma unroll
-                        for (int l = 0; l < LAT / 2; ++l) {
-                            float2 zz = make_float2(o[2 * l], o[2 * l + 1]);
-                            if (ep) {
-                                const float2 e = ep[l];
-                                zz.x = fmaf(e.x, expf(o[LAT + 2 * l] * 0.5f), zz.x);
-                                zz.y = fmaf(e.y, expf(o[LAT + 2 * l + 1] * 0.5f), zz.y);
+                        float zz[4] = {mv[0], mv[1], mv[2], mv[3]};
+                        if (a.eps[br]) {
+                            zz[0] = fmaf(e01.x, expf(lv[0] * 0.5f), zz[0]);
+                            zz[1] = fmaf(e01.y, expf(lv[1] * 0.5f), zz[1]);
+                            if (cg < 2) {
+                                zz[2] = fmaf(e23.x, expf(lv[2] * 0.5f), zz[2]);
+                                zz[3] = fmaf(e23.y, expf(lv[3] * 0.5f), zz[3]);
                             }
-                            zo[l] = zz;
                         }
+                        *reinterpret_cast<float2*>(a.z[br] + gl) = make_float2(zz[0], zz[1]);
+                        if (cg < 2) *reinterpret_cast<float2*>(a.z[br] + gl + 2) = make_float2(zz[2], zz[3]);
                     }
                 }
             }
@@ -317,29 +320,33 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
         {
             float v[16], lo[16];
             tmem_ld16(lane_addr + B_AC2 + c16, v);
+            const uint32_t k2 = m2 & col_bits(c16, H2);                  // column H2 is the bias column
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (!((m2 >> j) & 1u) || c16 + j >= H2) v[j] = 0.f;     // column H2 is the bias column
+                if (!(k2 & (1u << j))) v[j] = 0.f;
                 lo[j] = tf32_lo(v[j]);
             }
             if (cg < 3) { tmem_st16(lane_addr + B_RBH + c16, v); tmem_st16(lane_addr + B_RBL + c16, lo); }
             else { tmem_st8(lane_addr + B_RBH + c16, v); tmem_st8(lane_addr + B_RBL + c16, lo); }
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (c16 + j < ETW_H2) dp2T[(c16 + j) * 32] = v[j];
+            scratch_store(dp2T, c16, ETW_H2, v, 16);
         }
         run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, y2h, y2l, ys2, Y2_C / 2, idY2); });
 
         // ---- dpre1 = dh1 * relu'(h1) -> HBM ----
+        const uint32_t k1 = m1 & col_bits(c28, H1);                      // column H1 is the bias column
+        float acc[28];
+        tmem_ld28(lane_addr + B_AC1 + c28, acc);
 #pragma unroll
         for (int part = 0; part < 3; ++part) {
             const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
             float v[16];
-            ld_part(lane_addr + B_AC1 + c28, part, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (j < cnt && c28 + j0 + j < ETW_H1)
-                    dp1T[(c28 + j0 + j) * 32] = (((m1 >> (j0 + j)) & 1u) && c28 + j0 + j < H1) ? v[j] : 0.f;
+                if (j < cnt) v[j] = acc[j0 + j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < cnt && !(k1 & (1u << (j0 + j)))) v[j] = 0.f;
+            scratch_store(dp1T, c28 + j0, ETW_H1, v, cnt);
         }
         tc_fence_before();
         __syncthreads();            // the X2 accumulator aliases the columns the next tile writes first

@@ -65,23 +65,40 @@ __device__ __forceinline__ void image_put(float* hi, float* lo, int nrows, int r
     hi[dst] = v;
     lo[dst] = tf32_lo(v);
 }
+// scatter of one nn.Linear weight matrix W [N][K] (row-major, read coalesced) into an image; eight loads of a thread are
+// in flight before the first shared-memory store, so a matrix costs N*K / (8*NT) L2 round trips instead of N*K / NT
+template <bool TRANSPOSED>
+__device__ __forceinline__ void image_scatter(float* hi, float* lo, int nrows, const float* __restrict__ W, int N, int K, int tid) {
+    const int n_el = N * K;
+    for (int base = tid; base < n_el; base += 8 * NT) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * NT;
+            v[u] = i < n_el ? __ldg(W + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * NT;
+            if (i < n_el) {
+                const int n = i / K, k = i - n * K;
+                if (TRANSPOSED) image_put(hi, lo, nrows, k, n, v[u]);
+                else image_put(hi, lo, nrows, n, k, v[u]);
+            }
+        }
+    }
+}
 // forward image of y = W x + b with W [N][K] row-major: image row n, column k; the bias sits at column K and, when
 // `one` is set, image row N holds a 1 at column K (it regenerates the constant-1 column for the next layer)
 __device__ __forceinline__ void image_linear(float* hi, float* lo, int nrows, const float* __restrict__ W,
                                              const float* __restrict__ b, int N, int K, bool one, int tid) {
-    for (int i = tid; i < N * K; i += NT) {
-        const int n = i / K, k = i - n * K;
-        image_put(hi, lo, nrows, n, k, __ldg(W + i));
-    }
+    image_scatter<false>(hi, lo, nrows, W, N, K, tid);
     for (int n = tid; n < N; n += NT) image_put(hi, lo, nrows, n, K, __ldg(b + n));
     if (one && tid == 0) image_put(hi, lo, nrows, N, K, 1.0f);
 }
 // data-gradient image (transposed weights): image row = layer INPUT index k, image column (reduction) = OUTPUT index n
 __device__ __forceinline__ void image_linear_T(float* hi, float* lo, int nrows, const float* __restrict__ W, int N, int K, int tid) {
-    for (int i = tid; i < N * K; i += NT) {
-        const int n = i / K, k = i - n * K;
-        image_put(hi, lo, nrows, k, n, __ldg(W + i));
-    }
+    image_scatter<true>(hi, lo, nrows, W, N, K, tid);
 }
 
 struct TileCtx {
@@ -149,6 +166,23 @@ __device__ __forceinline__ void tc_teardown(const TileCtx& cx, int tid, uint32_t
     }
 }
 
+// all 28 accumulator columns of this thread with the three loads in flight together (one TMEM round trip instead of three)
+__device__ __forceinline__ void tmem_ld28(uint32_t taddr, float* v) {
+    uint32_t r[28];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+                 : "r"(taddr + 16));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]) : "r"(taddr + 24));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 28; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // 28 accumulator columns of this thread, in parts of 16 / 8 / 4
 __device__ __forceinline__ void ld_part(uint32_t addr, int part, float* v) {
     if (part == 0) tmem_ld16(addr, v);
@@ -159,6 +193,29 @@ __device__ __forceinline__ void st_part(uint32_t addr, int part, const float* v)
     if (part == 0) tmem_st16(addr, v);
     else if (part == 1) tmem_st8(addr + 16, v);
     else tmem_st4(addr + 24, v);
+}
+
+// bits j < 32 with first + j < limit (the columns of a thread's run that are real features)
+__device__ __forceinline__ uint32_t col_bits(int first, int limit) {
+    const int n = limit - first;
+    return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u));
+}
+
+// `cnt` consecutive features (first, first + 1, ...) of this thread's row into the feature-major scratch; `col0` points
+// at the row's slot of feature 0, features >= limit are skipped.  One 64-bit base and immediate offsets (feature f + 1
+// lives 32 floats after feature f); `first` is warp-uniform, so the all-valid test is a uniform branch and the common
+// case carries no per-element predicate or address arithmetic.
+__device__ __forceinline__ void scratch_store(float* __restrict__ col0, int first, int limit, const float* v, int cnt) {
+    float* __restrict__ p = col0 + (size_t)first * 32;
+    if (first + cnt <= limit) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < cnt) p[j * 32] = v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < cnt && j < limit - first) p[j * 32] = v[j];
+    }
 }
 
 }  // namespace tc
