@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ float red_s[NWARP][3];
     __shared__ __align__(8) uint64_t bar_s;
+    __shared__ __align__(8) uint64_t in_bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = a.L.D;
@@ -326,8 +327,28 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     float* T5l = T5h + X5_C * X5_N * 4;
     float* T4h = T5l + X5_C * X5_N * 4;
     float* T4l = T4h + X4_C * X4_N * 4;
+    // dpre6 staging: the item's [4 slabs][104 features][32 rows] block of the scratch (contiguous, written by
+    // k_dec_fwd_tc) arrives by one bulk async copy requested an item ahead, so stage 0 reads shared memory instead of
+    // waiting for 28 global loads per thread
+    float* d6s = T4l + X4_C * X4_N * 4;
     const float* th = a.theta;
     const Layout L = a.L;
+    const int ntiles = (a.B + ROWS - 1) / ROWS;
+    uint32_t in_ph = 0;
+    auto issue_in = [&](int wi) {
+        if (wi < ntiles * a.nbr && tid == 0) {
+            const int ti = a.nbr == 2 ? (wi >> 1) : wi, bi = a.nbr == 2 ? (wi & 1) : 0;
+            const uint32_t bytes = (uint32_t)(TCW_H5 * ROWS * 4);
+            mbar_expect_tx(&in_bar, bytes);
+            bulk_g2s(d6s, a.ws_dp6T + ((long)bi * ntiles + ti) * (TCW_H5 * ROWS), bytes, &in_bar);
+        }
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&in_bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    issue_in(blockIdx.x);                                   // overlaps the weight-image build
     zero_images(smem, 2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4), tid);
     __syncthreads();
     image_linear_T(T6h, T6l, X6_N, th + L.W6, D, G2, tid);
@@ -348,7 +369,6 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     const float alpha = a.alpha, ls = a.loss_scale;
     float s_klq = 0.f, s_klp = 0.f, s_klr = 0.f;
 
-    const int ntiles = (a.B + ROWS - 1) / ROWS;
     for (int w = blockIdx.x; w < ntiles * a.nbr; w += gridDim.x) {      // (tile, branch) items as in k_dec_fwd_tc
         const int t = a.nbr == 2 ? (w >> 1) : w, br = a.nbr == 2 ? (w & 1) : 0;
         const int row0 = t * ROWS;
@@ -356,33 +376,21 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
         const bool ok = grow < a.B;
         {
             const long vt = (long)br * ntiles + t;
-            const float* dp6T = a.ws_dp6T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
             float* dp5T = a.ws_dp5T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
             float* dp4T = a.ws_dp4T + (long)vt * (TCW_H4 * ROWS) + (row >> 5) * (32 * TCW_H4) + (row & 31);
             const unsigned* reluT = a.ws_relu + (vt * ROWS + row) * 8;
             uint32_t m5 = 0, m4 = 0;
             if (ok) { m5 = reluT[cg]; m4 = reluT[4 + cg]; }
-            {   // pull the next item's dpre6 block (contiguous, written by k_dec_fwd_tc) towards L2
-                const int wn = w + gridDim.x;
-                if (wn < ntiles * a.nbr) {
-                    const int tn = a.nbr == 2 ? (wn >> 1) : wn, bn = a.nbr == 2 ? (wn & 1) : 0;
-                    const char* nb = reinterpret_cast<const char*>(a.ws_dp6T + ((long)bn * ntiles + tn) * (TCW_H5 * ROWS));
-                    if (tid < TCW_H5 * ROWS * 4 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (long)tid * 128));
-                }
-            }
-            // ---- dpre6 (HBM) -> RA: all 28 loads of the thread in flight before the first TMEM store ----
+            // ---- dpre6 (staged in shared memory) -> RA ----
+            mbar_wait(&in_bar, in_ph);
+            in_ph ^= 1u;
             {
                 float d6[28];
-                {   // one base pointer, immediate offsets; the all-valid case (warp-uniform in c28) has no per-element test
-                    const float* __restrict__ p6 = dp6T + (size_t)c28 * 32;
+                {
+                    const float* __restrict__ p6 = d6s + (row >> 5) * (32 * TCW_H5) + (row & 31) + c28 * 32;
                     const int nv = ok ? min(28, TCW_H5 - c28) : 0;
-                    if (__all_sync(0xffffffffu, nv == 28)) {
 #pragma unroll
-                        for (int j = 0; j < 28; ++j) d6[j] = p6[j * 32];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 28; ++j) d6[j] = j < nv ? p6[j * 32] : 0.f;
-                    }
+                    for (int j = 0; j < 28; ++j) d6[j] = j < nv ? p6[j * 32] : 0.f;
                 }
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {
@@ -411,7 +419,9 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 if (a.nbr > 1) { ld4(a.mean[1], lat_mp); ld4(a.logvar[1], lat_lp); }
                 if (a.eps[br]) ld4(a.eps[br], lat_e);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, x6h, x6l, xs6, X6_C / 2, idX6); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, x6h, x6l, xs6, X6_C / 2, idX6); });
+            issue_in(w + gridDim.x);        // every thread has read the staging buffer (barrier inside mma_kick)
+            mma_wait(cx, &bar_s);
 
             // ---- dpre5 = dh5 * relu'(h5) -> RA, HBM ----
             const uint32_t k5 = m5 & col_bits(c28, G2);                  // column G2 is the bias column
@@ -525,7 +535,8 @@ static size_t dec_fwd_tc_smem(int D, int nbr, bool stage_inputs) {
            (stage_inputs ? (size_t)ROWS * D * (4 + nbr) : 0);
 }
 static size_t dec_bwd_tc_smem() {
-    return (size_t)2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4) * sizeof(float) + 128;
+    return (size_t)2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4) * sizeof(float) + 128 +
+           (size_t)TCW_H5 * ROWS * sizeof(float);
 }
 
 }  // namespace tc

@@ -65,25 +65,52 @@ __device__ __forceinline__ void image_put(float* hi, float* lo, int nrows, int r
     hi[dst] = v;
     lo[dst] = tf32_lo(v);
 }
-// scatter of one nn.Linear weight matrix W [N][K] (row-major, read coalesced) into an image; eight loads of a thread are
-// in flight before the first shared-memory store, so a matrix costs N*K / (8*NT) L2 round trips instead of N*K / NT
+// One nn.Linear weight matrix W [N][K] (row-major) into an image.  A warp takes one 16-byte chunk column of the image
+// at a time and its lanes run along the image rows, so every shared-memory store is a conflict-free STS.128 (a
+// scalar scatter along K puts the eight chunks of a warp into the same banks: image rows are 16 B apart, chunks
+// nrows * 16 B); all loads of a thread are requested before its first store.
+//   forward   : image row n, chunk c = W[n][4c .. 4c+3]   (one 16-byte load when W + n*K is 16-byte aligned)
+//   transposed: image row k, chunk c = W[4c .. 4c+3][k]   (four loads that are coalesced along k)
 template <bool TRANSPOSED>
 __device__ __forceinline__ void image_scatter(float* hi, float* lo, int nrows, const float* __restrict__ W, int N, int K, int tid) {
-    const int n_el = N * K;
-    for (int base = tid; base < n_el; base += 8 * NT) {
-        float v[8];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int R = TRANSPOSED ? K : N;                     // image rows
+    const int Cn = TRANSPOSED ? N : K;                    // image columns (reduction index)
+    const int nch = (Cn + 3) >> 2, rg = (R + 31) >> 5;    // chunks, row groups of 32
+    const bool vec = !TRANSPOSED && ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    for (int base = warp; base < nch * rg; base += 4 * NWARP) {
+        float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = base + u * NT;
-            v[u] = i < n_el ? __ldg(W + i) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+            const int it = base + u * NWARP;
+            const int c = it / rg, r = (it - c * rg) * 32 + lane;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < nch * rg && r < R) {
+                if (vec) {
+                    v[u] = __ldg(reinterpret_cast<const float4*>(W + (long)r * K + 4 * c));
+                } else if (!TRANSPOSED) {
+                    const float* w = W + (long)r * K + 4 * c;
+                    v[u].x = __ldg(w);
+                    if (4 * c + 1 < K) v[u].y = __ldg(w + 1);
+                    if (4 * c + 2 < K) v[u].z = __ldg(w + 2);
+                    if (4 * c + 3 < K) v[u].w = __ldg(w + 3);
+                } else {
+                    const float* w = W + (long)(4 * c) * K + r;
+                    v[u].x = __ldg(w);
+                    if (4 * c + 1 < N) v[u].y = __ldg(w + K);
+                    if (4 * c + 2 < N) v[u].z = __ldg(w + 2 * K);
+                    if (4 * c + 3 < N) v[u].w = __ldg(w + 3 * K);
+                }
+            }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = base + u * NT;
-            if (i < n_el) {
-                const int n = i / K, k = i - n * K;
-                if (TRANSPOSED) image_put(hi, lo, nrows, k, n, v[u]);
-                else image_put(hi, lo, nrows, n, k, v[u]);
+        for (int u = 0; u < 4; ++u) {
+            const int it = base + u * NWARP;
+            const int c = it / rg, r = (it - c * rg) * 32 + lane;
+            if (it < nch * rg && r < R) {
+                const int dst = (c * nrows + r) * 4;
+                *reinterpret_cast<float4*>(hi + dst) = v[u];
+                *reinterpret_cast<float4*>(lo + dst) = make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
             }
         }
     }
@@ -93,6 +120,7 @@ __device__ __forceinline__ void image_scatter(float* hi, float* lo, int nrows, c
 __device__ __forceinline__ void image_linear(float* hi, float* lo, int nrows, const float* __restrict__ W,
                                              const float* __restrict__ b, int N, int K, bool one, int tid) {
     image_scatter<false>(hi, lo, nrows, W, N, K, tid);
+    __syncthreads();            // when K % 4 != 0 the bias column shares its 16-byte chunk with the last weight columns
     for (int n = tid; n < N; n += NT) image_put(hi, lo, nrows, n, K, __ldg(b + n));
     if (one && tid == 0) image_put(hi, lo, nrows, N, K, 1.0f);
 }
