@@ -46,6 +46,15 @@ constexpr int X5_C = 26, X5_N = 64;       // K = 104 (n), 50 inputs k
 constexpr int X4_C = 14, X4_N = 16;       // K = 56 (n), 10 inputs k
 
 
+// sigmoid with the two special-function instructions only: ex2.approx(-v log2 e) and rcp.approx(1 + t).  1 + t lies in
+// [1, inf], so no denormal handling is needed; relative error ~2^-21 (the loss tolerance is 1e-4 relative)
+__device__ __forceinline__ float sigmoid_fast(float v) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward + loss
 // ------------------------------------------------------------------------------------------------
@@ -95,6 +104,10 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
     const float inv_var = 1.0f / var;
     const float log_scale = logf(scale);
     const float alpha = a.alpha, ls = a.loss_scale;
+    // dL/dx_hat = coef * (x_hat - x) / var * loss_scale with coef = (1 - alpha) m + alpha m (1 - m_p) on the q branch and
+    // alpha m_p on the p branch (VAE.py:432-445): three constants, selected by the mask bits
+    const float coef_q_both = (1.f - alpha) * inv_var * ls, coef_q_only = ((1.f - alpha) + alpha) * inv_var * ls,
+                coef_p = alpha * inv_var * ls;
     float s_req = 0.f, s_rep = 0.f, s_red = 0.f, s_imp = 0.f, s_sse = 0.f;
 
     const int ntiles = (a.B + ROWS - 1) / ROWS;
@@ -246,8 +259,16 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
             mma_wait(cx, &bar_s);
 
             // ---- x_hat = sigmoid(acc6): loss terms, dL/d(pre-sigmoid) -> HBM ----
+            // Branch-free per element: the item fixes a primary mask P (q branch: mask, p branch: mask_p), a secondary
+            // mask S (q: mask_p, p: all ones) and two gradient weights; NLL sums are taken per item and folded into the
+            // running sums of the item's branch afterwards.
+            //   q: RE_q over P, RE_d over P & ~S, RE_q_imputed / SSE over ~P; dL/dx_hat weight (1 - alpha) on P & S, 1 on P & ~S
+            //   p: RE_p over P;                                              dL/dx_hat weight alpha on P       (VAE.py:432-445)
             {
                 float* xo = a.xhat[br];
+                const uint32_t Pm = br == 0 ? mb : mpb, Sm = br == 0 ? mpb : 0xFFFFFFFFu;
+                const float wA = br == 0 ? coef_q_both : coef_p, wB = br == 0 ? coef_q_only : coef_p;
+                float n_p = 0.f, n_pns = 0.f, n_np = 0.f, q_np = 0.f;
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {
                     const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
@@ -263,31 +284,28 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int e = j0 + 4 * g + j;
-                                const float xv = xr[e], m = (float)((mb >> e) & 1u), mp = (float)((mpb >> e) & 1u);
-                                xh[j] = 1.0f / (1.0f + expf(-v[4 * g + j]));
-                                const float diff = xv - xh[j];
-                                const float nll = fmaf(diff * diff, inv2var, log_scale);
-                                float coef;
-                                if (br == 0) {
-                                    s_req += m * nll;
-                                    s_red += m * (1.f - mp) * nll;
-                                    s_imp += (1.f - m) * nll;
-                                    s_sse += (1.f - m) * diff * diff;
-                                    coef = (1.f - alpha) * m + alpha * m * (1.f - mp);
-                                } else {
-                                    s_rep += mp * nll;
-                                    coef = alpha * mp;
-                                }
-                                dpre[j] = coef * (xh[j] - xv) * inv_var * ls * xh[j] * (1.f - xh[j]);
+                                const bool pb = (Pm >> e) & 1u, sb = (Sm >> e) & 1u;
+                                xh[j] = sigmoid_fast(v[4 * g + j]);
+                                const float diff = xr[e] - xh[j];
+                                const float d2 = diff * diff;
+                                const float nll = fmaf(d2, inv2var, log_scale);
+                                if (pb) n_p += nll;
+                                if (pb && !sb) n_pns += nll;
+                                if (!pb) { n_np += nll; q_np += d2; }
+                                const float coef = pb ? (sb ? wA : wB) : 0.f;
+                                dpre[j] = (coef * -diff) * (xh[j] * (1.f - xh[j]));
                             }
                             if (xo) *reinterpret_cast<float4*>(xo + (long)grow * D + c) = make_float4(xh[0], xh[1], xh[2], xh[3]);
                         }
                         if (c < TCW_H5) {
+                            float* __restrict__ p6 = dp6T + (size_t)c * 32;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dp6T[(c + j) * 32] = dpre[j];
+                            for (int j = 0; j < 4; ++j) p6[j * 32] = dpre[j];
                         }
                     }
                 }
+                if (br == 0) { s_req += n_p; s_red += n_pns; s_imp += n_np; s_sse += q_np; }
+                else s_rep += n_p;
             }
             tc_fence_before();      // the next branch overwrites RA / ACC2 only after its own barrier
         }
