@@ -302,6 +302,19 @@ int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* 
                      uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
                      unsigned long long seed, unsigned long long offset, void* stream);
 
+/* Host-streamed batches (a table kept in host memory; the e2e path of bench.py).  What DataLoader + collate hand to
+ * train.py:36-58 as (data_sample, mask) arrives here in a compact form built once by the loader:
+ *   mask_bits[rows][ceil(obs_dim / 32)]  bit j of word w = mask[row][32 w + j]           (always)
+ *   vals[nnz], row_off[rows]             x's OBSERVED entries only, row-major; row r starts at vals[row_off[r]]
+ *                                        (optional pair: entries under a zero mask bit never reach the training
+ *                                        loss, VAE.py:388, 411-445; pass NULL, NULL when x was copied dense)
+ * One launch writes the dense uint8 mask, x (zeros at unobserved entries; only with vals), mask_p (may be NULL) and
+ * eps[n_eps][rows][10], drawing exactly what pcvae_prep_batch draws for the same (row, seed, offset).
+ * obs_dim % 4 == 0, obs_dim <= 128. */
+int pcvae_prep_packed(const uint32_t* mask_bits, const float* vals, const uint32_t* row_off, float* x, uint8_t* mask,
+                      uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
+                      unsigned long long seed, unsigned long long offset, void* stream);
+
 /* ------------------------------------------------------------------------
  * Generic dense layer y = act(x W^T + b) on row tiles (weights resident in shared memory), forward
  * and backward.  Building block of the 128-wide not-MIWAE MNAR networks (REG_notMIWAE_v2 /

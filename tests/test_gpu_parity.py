@@ -304,6 +304,52 @@ def test_throughput_prep_then_step_tcgen05_matches_ffma():
     torch.testing.assert_close(t1, t0, rtol=0, atol=2.1e-3)      # one Adam step moves every weight by at most lr = 1e-3
 
 
+@pytest.mark.parametrize("B,D", [(1, 4), (777, 100), (4096, 128), (300, 36)])
+def test_prep_packed_equals_prep_batch_on_the_same_rows(B, D):
+    """Host-streamed batch format (bit-packed mask + observed-entry stream of x): pcvae_prep_packed must rebuild
+    the dense mask bit for bit, x * mask exactly, and draw the SAME sub-mask and noise as pcvae_prep_batch does
+    for those rows (same Philox counters); a fused step on either batch then gives identical results."""
+    KR, L = _mods()
+    lib = L.load()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(B + D)
+    xh = torch.rand(B, D, generator=g)
+    mh = torch.rand(B, D, generator=g) < 0.7
+    if B > 2:
+        mh[1] = False                                     # a row with nothing observed
+        mh[2] = True                                      # and a fully observed one
+    vals, row_off, bits = KR.compact_rows(xh, mh)
+    assert vals.numel() == int(mh.sum()) and bits.shape == (B, (D + 31) // 32)
+    eng = KR.Engine(L.FAMILY_MLP, D, 0, dev)
+    st = torch.cuda.current_stream().cuda_stream
+    # reference: the resident-table path with the identity permutation
+    table, mtable = xh.to(dev), mh.to(dev)
+    idx = torch.arange(B, device=dev)
+    x0 = torch.empty(B, D, device=dev); m0 = torch.empty(B, D, device=dev, dtype=torch.bool)
+    mp0 = torch.empty_like(m0); e0 = torch.empty(2, B, 10, device=dev)
+    L.check(lib.pcvae_prep_batch(table.data_ptr(), mtable.data_ptr(), idx.data_ptr(), x0.data_ptr(), m0.data_ptr(),
+                                 mp0.data_ptr(), e0.data_ptr(), B, D, 2, 0.7, 99, 24, st), "pcvae_prep_batch")
+    # compact form: observed entries only
+    x1 = torch.full((B, D), float("nan"), device=dev); m1 = torch.empty(B, D, device=dev, dtype=torch.bool)
+    mp1 = torch.empty_like(m1); e1 = torch.empty(2, B, 10, device=dev)
+    eng.prep_packed(bits.to(dev), m1, mp1, e1, vals=vals.to(dev) if vals.numel() else torch.zeros(1, device=dev),
+                    row_off=row_off.to(dev), x=x1, keep=0.7, seed=99, offset=24)
+    assert torch.equal(m1, m0) and torch.equal(mp1, mp0) and torch.equal(e1, e0)
+    assert torch.equal(x1, x0 * m0)                       # unobserved entries are zero, observed ones exact
+    # dense x copied separately, mask bit-packed only
+    m2 = torch.empty(B, D, device=dev, dtype=torch.bool); mp2 = torch.empty_like(m2); e2 = torch.empty(2, B, 10, device=dev)
+    eng.prep_packed(bits.to(dev), m2, mp2, e2, keep=0.7, seed=99, offset=24)
+    assert torch.equal(m2, m0) and torch.equal(mp2, mp0) and torch.equal(e2, e0)
+    if D % 4 == 0 and D <= 100:
+        p = O.init_params("mlp", D, 0, seed=3)
+        res = []
+        for xs, ms, mps, es in ((x0, m0, mp0, e0), (x1, m1, mp1, e1)):
+            tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, KR.flatten_params(p, L.FAMILY_MLP, "cuda"), regularised=True)
+            res.append((tr.forward_backward(xs, ms, mps, es[0], es[1]).clone(), tr.grad.clone()))
+        assert torch.equal(res[0][0][:6], res[1][0][:6])  # every training sum (the imputed / SSE slots read unobserved x)
+        assert torch.equal(res[0][1], res[1][1])          # and every gradient, bit for bit
+
+
 def test_empty_batch_is_a_no_op():
     KR, L = _mods()
     p = O.init_params("mlp", 13)

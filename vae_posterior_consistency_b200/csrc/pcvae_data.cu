@@ -114,6 +114,69 @@ __global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ ta
     }
 }
 
+// Host-streamed batches: the mask arrives bit-packed (W = ceil(D / 32) words per row, bit j of word w is
+// mask[row][32 w + j]) and, optionally, x as the stream of its OBSERVED entries only (row-major, row r starting at
+// vals[row_off[r]]; entries under a zero mask bit never reach the training loss, VAE.py:388, 411-445).  A warp per
+// row expands both into the dense layouts the row-tile kernels read, and draws the sub-mask and the noise exactly
+// as k_prep_batch does (same Philox counters), so a step fed this way equals a step fed by k_prep_batch on the
+// same rows.  Requires D % 4 == 0 and D <= 128.
+__global__ void __launch_bounds__(256) k_prep_packed(const uint32_t* __restrict__ bits, const float* __restrict__ vals,
+                                                     const uint32_t* __restrict__ row_off, float* __restrict__ x,
+                                                     uint8_t* __restrict__ mask, uint8_t* __restrict__ mask_p,
+                                                     float* __restrict__ eps, int B, int D, int n_eps, float keep,
+                                                     unsigned long long seed, unsigned long long offset) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int D4 = D >> 2, W = (D + 31) >> 5;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        if (lane < D4) {
+            const uint32_t* rb = bits + (long)b * W;
+            const int wi = lane >> 3, sh = (lane & 7) * 4;
+            const uint32_t word = rb[wi];
+            const uint32_t nib = (word >> sh) & 0xFu;
+            const uint32_t m = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);   // four 0/1 bytes
+            reinterpret_cast<uint32_t*>(mask + (long)b * D)[lane] = m;
+            if (vals) {
+                int before = __popc(word & ((1u << sh) - 1u));
+                for (int w = 0; w < wi; ++w) before += __popc(rb[w]);
+                const float* v = vals + row_off[b] + before;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                int k = 0;
+                if (nib & 1u) o.x = v[k++];
+                if (nib & 2u) o.y = v[k++];
+                if (nib & 4u) o.z = v[k++];
+                if (nib & 8u) o.w = v[k++];
+                reinterpret_cast<float4*>(x + (long)b * D)[lane] = o;
+            }
+            if (mask_p) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)lane, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+                const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+                uint32_t mp = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((nib >> j) & 1u) && u01(rv[j]) < keep) mp |= 1u << (8 * j);
+                reinterpret_cast<uint32_t*>(mask_p + (long)b * D)[lane] = mp;
+            }
+        }
+        if (lane < (10 * n_eps + 3) / 4) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(64 + lane), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+            float gv[4];
+            const float r0 = sqrtf(-2.0f * logf(u01_open(r.x))), r1 = sqrtf(-2.0f * logf(u01_open(r.z)));
+            float s0, c0, s1, c1;
+            sincospif(2.0f * u01(r.y), &s0, &c0);
+            sincospif(2.0f * u01(r.w), &s1, &c1);
+            gv[0] = r0 * c0; gv[1] = r0 * s0; gv[2] = r1 * c1; gv[3] = r1 * s1;
+            const int e0 = 4 * lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = e0 + j, br = e / 10, l = e - br * 10;
+                if (br < n_eps) eps[((long)br * B + b) * 10 + l] = gv[j];
+            }
+        }
+    }
+}
+
 }  // namespace pcvae
 
 using namespace pcvae;
@@ -146,6 +209,24 @@ int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* 
                                                               keep_prob, seed, offset);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "prep_batch: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_prep_packed(const uint32_t* mask_bits, const float* vals, const uint32_t* row_off, float* x, uint8_t* mask,
+                      uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
+                      unsigned long long seed, unsigned long long offset, void* stream) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (rows < 0 || obs_dim < 4 || obs_dim > 128 || obs_dim % 4 || n_eps < 0 || n_eps > 2 || !(keep_prob >= 0.f && keep_prob <= 1.f))
+        return fail(PCVAE_EINVAL, "prep_packed: bad arguments (obs_dim must be a multiple of 4, <= 128; n_eps 0..2)");
+    if (rows == 0) return PCVAE_OK;
+    if (!mask_bits || !mask || (n_eps > 0 && !eps)) return fail(PCVAE_EINVAL, "prep_packed: null pointer");
+    if ((vals != nullptr) != (row_off != nullptr) || (vals && !x))
+        return fail(PCVAE_EINVAL, "prep_packed: vals, row_off and x go together (all three or none)");
+    k_prep_packed<<<grid * 8, 256, 0, (cudaStream_t)stream>>>(mask_bits, vals, row_off, x, mask, mask_p, eps, rows, obs_dim, n_eps,
+                                                               keep_prob, seed, offset);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "prep_packed: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }
 

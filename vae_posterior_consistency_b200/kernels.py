@@ -76,6 +76,30 @@ def prep_masks(masks: Sequence[torch.Tensor]):
     return L.MASK_F32, [_f32(m) for m in masks]
 
 
+def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    """Host side of pcvae_prep_packed: a [rows, D] boolean mask -> [rows, ceil(D / 32)] int32 words, bit j of word w =
+    mask[row][32 w + j].  Done once per table by the loader (like its min-max pass), not per step."""
+    import numpy as np
+    m = mask.detach().cpu().numpy().astype(bool)
+    rows, D = m.shape
+    W = (D + 31) // 32
+    by = np.packbits(m, axis=1, bitorder="little")                       # [rows, ceil(D / 8)] bytes
+    out = np.zeros((rows, W * 4), dtype=np.uint8)
+    out[:, :by.shape[1]] = by
+    return torch.from_numpy(out.view("<i4").reshape(rows, W).copy())       # the bit pattern of the uint32 words
+
+
+def compact_rows(x: torch.Tensor, mask: torch.Tensor):
+    """Observed-entry form of a host table: (vals [nnz] fp32 in row-major order, row_off [rows] int32 (as uint32 on the
+    device), mask_bits).  Entries under mask == 0 are dropped: they never reach the training loss (reference VAE.py:388,
+    411-445), so a training step fed from this form equals one fed from the dense table."""
+    m = mask.detach().cpu().bool()
+    vals = x.detach().cpu().float()[m].contiguous()
+    cnt = m.sum(1, dtype=torch.int64)
+    row_off = (torch.cumsum(cnt, 0) - cnt).to(torch.int32)
+    return vals, row_off, pack_mask_bits(m)
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -122,6 +146,18 @@ class Engine:
     def act_ws(self, rows, n_branch):
         n = self.lib.pcvae_enc_act_ws_floats(C.byref(self.model), rows, n_branch)
         return torch.empty(max(n, 1), device=self.device, dtype=torch.float32)
+
+    # ---- host-streamed batches ----------------------------------------------------
+    def prep_packed(self, bits, mask, mask_p=None, eps=None, vals=None, row_off=None, x=None, keep=0.7, seed=0xC0FFEE,
+                    offset=0):
+        """pcvae_prep_packed: bit-packed mask (+ optionally the observed-entry stream of x) -> dense uint8 mask, x,
+        sub-mask and noise in one launch.  All tensors on the device; `mask`, `mask_p` uint8/bool [rows, D]."""
+        _need_cuda(bits, mask, mask_p, eps, vals, row_off, x)
+        rows = mask.shape[0]
+        n_eps = 0 if eps is None else eps.shape[0]
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pcvae_prep_packed(_p(bits), _p(vals), _p(row_off), _p(x), _p(mask), _p(mask_p), _p(eps), rows,
+                                               self.D, n_eps, float(keep), seed, offset, _stream()), "pcvae_prep_packed")
 
     # ---- encoder ----------------------------------------------------------------
     def enc_fwd(self, theta, x, masks, eps=None, save=False, want_z=True):

@@ -28,7 +28,7 @@ SYMBOLS = [
     "pcvae_draw_submask", "pcvae_draw_normal", "pcvae_dense_fwd", "pcvae_dense_bwd", "pcvae_mnar_sample_z",
     "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss", "pcvae_set_reward_tensor_cores",
     "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores", "pcvae_enc_tc_workspace_floats",
-    "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events",
+    "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events", "pcvae_prep_packed",
 ]
 
 
@@ -154,6 +154,8 @@ def load():
     lib.pcvae_draw_normal.argtypes = [C.c_void_p, C.c_long, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
     lib.pcvae_prep_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
+    lib.pcvae_prep_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
     lib.pcvae_reduce_adam.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]
