@@ -86,6 +86,22 @@ __device__ __forceinline__ void bulk_g2s(float* dst, const float* src, uint32_t 
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// the same copy with an L2 eviction-priority hint (createpolicy.fractional): evict_first for streams that are read once
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(float* dst, const float* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 // one lane of a converged warp (the predicate ptxas recognises for single-thread tcgen05 issue)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

@@ -110,10 +110,15 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
             int r = 0;
             uint32_t pr = 0;                             // parity of the current pass over the raw ring
             bool wrapped = false;
+            // The gradient operand A was written (and B's producer ran) just before this launch, last tiles last: tiles
+            // are taken in DESCENDING order so that the first reads find what is still in L2, and the activation
+            // operand B (written a few kernels ago, read exactly once here) is marked evict-first so that it does not
+            // push the not-yet-read gradient tiles out.
+            const uint64_t pol_b = l2_policy_evict_first();
             for (int j = 0; j < a.njobs; ++j) {
                 const WgradJob J = a.job[j];
                 const uint32_t abytes = (uint32_t)(J.Fa * SLAB * 4), bbytes = (uint32_t)(min(J.Fb, J.Nb) * SLAB * 4);
-                for (int t = 0; t < mine_t; ++t) {
+                for (int t = mine_t - 1; t >= 0; --t) {
                     const long vt = blockIdx.x + (long)t * gridDim.x;
                     const float* At = J.AT + vt * (long)(J.Fa * WG_TROWS);
                     const float* Bt = J.BT + vt * (long)(J.Fb * WG_TROWS);
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
                         float* st = raw0 + r * WG_RSTAGE_FLOATS;
                         mbar_expect_tx(&land_bar[r], abytes + bbytes);
                         bulk_g2s(st, At + sl * (SLAB * J.Fa), abytes, &land_bar[r]);
-                        bulk_g2s(st + WG_RAW_FLOATS, Bt + sl * (SLAB * J.Fb), bbytes, &land_bar[r]);
+                        bulk_g2s_hint(st + WG_RAW_FLOATS, Bt + sl * (SLAB * J.Fb), bbytes, &land_bar[r], pol_b);
                         if (++r == WG_RSTAGES) { r = 0; pr ^= 1u; wrapped = true; }
                     }
                 }
