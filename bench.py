@@ -422,7 +422,10 @@ def run_ours(args):
             if lib.pcvae_profile_events(None, 0) == 9:   # all nine marks were recorded (tensor-core path taken)
                 ev_sets.append(evs)
         tr.step_count += 1
-        if world > 1:
+        if world > 1 and tr.xch is not None:             # reduce + NVLink peer exchange + Adam in one launch
+            sums = eng.dp_reduce_adam(tr.xch, tr.grad, theta, tr.exp_avg, tr.exp_avg_sq, tr.step_count, B)
+            launches[0] += 6 + 1
+        elif world > 1:                                  # PCVAE_DP=nccl: reduce, NCCL all-reduce, Adam
             eng.reduce_grads(tr.grad)
             sums = eng.reduce_sums(B)
             torch.distributed.all_reduce(tr.grad, group=dist_group)
@@ -606,7 +609,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"Reg_VAE D={D}, synthetic {T} x {D} table resident in HBM, batch {B} rows per GPU "
                                    f"per step (cfg4), device-side gather + Philox sub-mask/noise, "
-                                   f"{'NCCL grad all-reduce, ' if world > 1 else ''}Adam",
+                                   f"{('gradient exchange over NVLink peer memory fused with the reduce and ' if tr.xch is not None else 'NCCL grad all-reduce, ') if world > 1 else ''}Adam",
                        "batch_per_gpu": B, "global_batch": B * world, "table_rows": T,
                        "l2": "inputs larger than L2 (500 MB table, a fresh 33 MB batch gathered every step)",
                        "final_loss": loss},

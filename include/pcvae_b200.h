@@ -250,6 +250,34 @@ int pcvae_reduce_adam(const float* grad_partials, int grid, long param_count, fl
                       const float* sums_partials, int rows, int obs_dim, double* sums, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Data-parallel training (optional): the tail of a step in ONE launch on every rank --
+ * deterministic reduce of the rank's partials, exchange of the reduced gradient with the other GPUs of the node over
+ * NVLink peer memory, sum over the ranks in rank order (bit-identical on all ranks) and Adam.  It stands where
+ * `train_loss.backward(); optimizer.step()` stand in train.py:114-116 once the batch is split over GPUs, and replaces
+ * pcvae_reduce_grads + an NCCL all-reduce + pcvae_adam_step.  Each rank (one process per GPU) allocates an exchange
+ * buffer, publishes its 64-byte CUDA IPC handle (any host channel, e.g. torch.distributed.all_gather_object), opens the
+ * handles of the others, and passes all `world` base pointers (its own at index `rank`) with every call.  `seq` is the
+ * 1-based number of the call on this buffer and must advance by one per call on every rank in lockstep.  A rank that
+ * does not arrive within ~4 s makes the waiting ranks set *status = 1 and continue (no hang); check it on the host.
+ * --------------------------------------------------------------------- */
+#define PCVAE_DP_MAX_WORLD 16
+size_t pcvae_dp_exchange_bytes(long param_count, int world);
+int pcvae_dp_exchange_alloc(long param_count, int world, void** buffer, unsigned char* ipc_handle_64);
+int pcvae_dp_exchange_open(const unsigned char* ipc_handle_64, void** peer_buffer);
+int pcvae_dp_exchange_close(void* peer_buffer);
+int pcvae_dp_exchange_free(void* buffer);
+typedef struct {
+    const float* grad_partials; int grid; long param_count;     /* as pcvae_reduce_adam */
+    float* grad; float* theta; float* exp_avg; float* exp_avg_sq;
+    int step; float lr, beta1, beta2, eps;
+    const float* sums_partials; int rows, obs_dim; double* sums; /* this rank's loss sums (optional pair) */
+    int world, rank; unsigned seq;
+    void* peer_buffers[PCVAE_DP_MAX_WORLD];
+    int* status;                                                  /* device int, zero-initialised by the caller */
+} pcvae_dp_params;
+int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
  * Active-selection information reward for ONE acquisition step, all (row, candidate,
  * sample) triples in one launch.  Replaces the candidate loop around R_lindley_chain and
  * chaini_I / chaini_II (src/experiment_main/evaluate.py:416-425, 514-634) using the

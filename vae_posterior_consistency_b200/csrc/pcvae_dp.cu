@@ -1,0 +1,193 @@
+// Data-parallel training step tail in ONE launch: deterministic reduce of this GPU's per-CTA gradient partials, exchange
+// of the reduced gradient with the other GPUs of the node over NVLink peer memory, fixed-order sum over the ranks and
+// torch.optim.Adam -- what `loss.backward(); all_reduce(grad); optimizer.step()` would be for the reference's train.py:
+// 114-116 under data parallelism.  Replaces pcvae_reduce_grads + NCCL all-reduce + pcvae_adam_step.
+//
+// Every rank owns an EXCHANGE BUFFER (cudaMalloc'ed by pcvae_dp_exchange_alloc, opened on the peers through CUDA IPC):
+//     float    data [2][world][P32]     slot [seq & 1][r] holds rank r's reduced gradient of call number seq
+//     unsigned flag [world][nblocks]    flag [r][b] = seq once block b of rank r has delivered its 32 parameters
+// Block b owns 32 consecutive parameters on every rank.  After its local reduce it PUSHES the 32 values into slot
+// [rank] of every rank's buffer (peer stores over NVLink), fences (system scope) and raises flag [rank][b] on every
+// rank; it then polls only its OWN copy of the flags (local memory) until all ranks have delivered block b, sums the
+// slots in rank order -- the same order on every rank, so all ranks compute bit-identical gradients and weights -- and
+// applies Adam.  No block ever waits for another block of its own grid, so the launch cannot deadlock on residency; a
+// rank that never arrives is detected by a bounded wait (status word, no hang).  The two data slots alternate by call
+// number: a rank can overwrite slot s only in call seq + 2, which it reaches only after every rank has delivered call
+// seq + 1, i.e. after every rank has finished reading call seq.
+#include <cstring>
+
+#include "pcvae_internal.cuh"
+
+namespace pcvae {
+
+constexpr int DP_MAX_WORLD = PCVAE_DP_MAX_WORLD;
+
+struct DpArgs {
+    const float* gp; int grid; long P;
+    float* grad; float* theta; float* m; float* v;
+    float lr_bc1, inv_sqrt_bc2, b1, b2, eps;
+    const float* sp; double nll_const; double* sums;
+    int world, rank; unsigned seq;
+    long P32; int nblocks;
+    char* peer[DP_MAX_WORLD];
+    int* status;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_dp_reduce_adam(const DpArgs a) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const long i = (long)blockIdx.x * 32 + lane;
+    const long P = a.P;
+    float s = 0.f;
+    if (i < P) {                                         // same summation order as k_reduce_adam
+        int c = part;
+        for (; c + 24 < a.grid; c += 32) {
+            const float v0 = a.gp[(long)c * P + i], v1 = a.gp[(long)(c + 8) * P + i], v2 = a.gp[(long)(c + 16) * P + i],
+                        v3 = a.gp[(long)(c + 24) * P + i];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; c < a.grid; c += 8) s += a.gp[(long)c * P + i];
+    }
+    red[part][lane] = s;
+    __syncthreads();
+    if (part == 0) {
+        float g = red[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) g += red[q][lane];
+        const long slot_floats = a.P32;
+        const long data_floats = 2 * (long)a.world * slot_floats;
+        const long my_slot = ((long)(a.seq & 1u) * a.world + a.rank) * slot_floats + (long)blockIdx.x * 32 + lane;
+        // push this block's 32 values into slot [rank] of every rank (one 128-byte store per rank)
+        for (int r = 0; r < a.world; ++r) reinterpret_cast<float*>(a.peer[r])[my_slot] = g;
+        __threadfence_system();
+        __syncwarp();
+        if (lane < a.world) {                            // lane r raises the flag on rank r ...
+            volatile unsigned* f = reinterpret_cast<volatile unsigned*>(reinterpret_cast<float*>(a.peer[lane]) + data_floats) +
+                                   (long)a.rank * a.nblocks + blockIdx.x;
+            *f = a.seq;
+            // ... and then waits for rank r's flag in the local buffer
+            volatile unsigned* w = reinterpret_cast<volatile unsigned*>(reinterpret_cast<float*>(a.peer[a.rank]) + data_floats) +
+                                   (long)lane * a.nblocks + blockIdx.x;
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned spins = 0;
+            while ((int)(*w - a.seq) < 0) {              // flags only grow (wrap-safe comparison)
+                if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) { atomicExch(a.status, 1); break; }
+            }
+        }
+        __syncwarp();
+        __threadfence_system();
+        // sum the slots in rank order: identical on every rank
+        const volatile float* mine = reinterpret_cast<const volatile float*>(a.peer[a.rank]) + (long)(a.seq & 1u) * a.world * slot_floats +
+                                     (long)blockIdx.x * 32 + lane;
+        float tot = 0.f;
+        for (int r = 0; r < a.world; ++r) tot += mine[(long)r * slot_floats];
+        if (i < P) {
+            a.grad[i] = tot;
+            const float mi = a.m[i] + (tot - a.m[i]) * (1.f - a.b1);
+            const float vi = fmaf(a.b2, a.v[i], (1.f - a.b2) * tot * tot);
+            a.m[i] = mi;
+            a.v[i] = vi;
+            a.theta[i] -= a.lr_bc1 * (mi / (sqrtf(vi) * a.inv_sqrt_bc2 + a.eps));
+        }
+    }
+    if (a.sp && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + PCVAE_NSUMS) {   // this rank's loss sums
+        const int j = threadIdx.x - 32;
+        double acc = 0.0;
+        for (int c = 0; c < a.grid; ++c) acc += (double)a.sp[c * PCVAE_NSUMS + j];
+        if (j == PCVAE_S_RE_Q || j == PCVAE_S_RE_P || j == PCVAE_S_RE_D || j == PCVAE_S_RE_IMP) acc += a.nll_const;
+        a.sums[j] = acc;
+    }
+}
+
+static long dp_p32(long P) { return (P + 31) / 32 * 32; }
+
+}  // namespace pcvae
+
+using namespace pcvae;
+
+extern "C" {
+
+size_t pcvae_dp_exchange_bytes(long param_count, int world) {
+    if (param_count < 1 || world < 1 || world > DP_MAX_WORLD) return 0;
+    const long P32 = dp_p32(param_count);
+    return (size_t)2 * world * P32 * sizeof(float) + (size_t)world * (P32 / 32) * sizeof(unsigned);
+}
+
+int pcvae_dp_exchange_alloc(long param_count, int world, void** buffer, unsigned char* ipc_handle_64) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    const size_t bytes = pcvae_dp_exchange_bytes(param_count, world);
+    if (!bytes || !buffer || !ipc_handle_64) return fail(PCVAE_EINVAL, "dp_exchange_alloc: bad arguments (world 1..%d)", DP_MAX_WORLD);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dp_exchange_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(PCVAE_ECUDA, "dp_exchange_alloc: %s", cudaGetErrorString(e)); }
+    memcpy(ipc_handle_64, &h, 64);
+    *buffer = p;
+    return PCVAE_OK;
+}
+
+int pcvae_dp_exchange_open(const unsigned char* ipc_handle_64, void** peer_buffer) {
+    if (!ipc_handle_64 || !peer_buffer) return fail(PCVAE_EINVAL, "dp_exchange_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle_64, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dp_exchange_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    *peer_buffer = p;
+    return PCVAE_OK;
+}
+
+int pcvae_dp_exchange_close(void* peer_buffer) {
+    if (!peer_buffer) return PCVAE_OK;
+    const cudaError_t e = cudaIpcCloseMemHandle(peer_buffer);
+    return e == cudaSuccess ? PCVAE_OK : fail(PCVAE_ECUDA, "dp_exchange_close: %s", cudaGetErrorString(e));
+}
+
+int pcvae_dp_exchange_free(void* buffer) {
+    if (!buffer) return PCVAE_OK;
+    const cudaError_t e = cudaFree(buffer);
+    return e == cudaSuccess ? PCVAE_OK : fail(PCVAE_ECUDA, "dp_exchange_free: %s", cudaGetErrorString(e));
+}
+
+int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (!p || !p->grad_partials || !p->grad || !p->theta || !p->exp_avg || !p->exp_avg_sq || p->grid < 1 || p->param_count < 1 ||
+        p->step < 1 || !p->status)
+        return fail(PCVAE_EINVAL, "dp_reduce_adam: bad arguments");
+    if (p->world < 1 || p->world > DP_MAX_WORLD || p->rank < 0 || p->rank >= p->world || p->seq == 0)
+        return fail(PCVAE_EINVAL, "dp_reduce_adam: world %d (1..%d), rank %d, seq %u (>= 1)", p->world, DP_MAX_WORLD, p->rank, p->seq);
+    if ((p->sums_partials == nullptr) != (p->sums == nullptr)) return fail(PCVAE_EINVAL, "dp_reduce_adam: sums_partials and sums go together");
+    DpArgs a{};
+    for (int r = 0; r < p->world; ++r) {
+        if (!p->peer_buffers[r]) return fail(PCVAE_EINVAL, "dp_reduce_adam: peer buffer %d is null", r);
+        a.peer[r] = static_cast<char*>(p->peer_buffers[r]);
+    }
+    const double bc1 = 1.0 - pow((double)p->beta1, p->step), bc2 = 1.0 - pow((double)p->beta2, p->step);
+    a.gp = p->grad_partials; a.grid = p->grid; a.P = p->param_count;
+    a.grad = p->grad; a.theta = p->theta; a.m = p->exp_avg; a.v = p->exp_avg_sq;
+    a.lr_bc1 = (float)(p->lr / bc1); a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.b1 = p->beta1; a.b2 = p->beta2; a.eps = p->eps;
+    a.sp = p->sums_partials; a.sums = p->sums;
+    a.nll_const = 0.5 * 1.8378770664093453 * (double)p->rows * (double)p->obs_dim;
+    a.world = p->world; a.rank = p->rank; a.seq = p->seq;
+    a.P32 = dp_p32(p->param_count); a.nblocks = (int)(a.P32 / 32);
+    a.status = p->status;
+    k_dp_reduce_adam<<<a.nblocks, 256, 0, (cudaStream_t)stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dp_reduce_adam: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+}  // extern "C"

@@ -34,3 +34,58 @@ def allreduce_grads(flat_grad: torch.Tensor, group):
     import torch.distributed as dist
     dist.all_reduce(flat_grad, group=group)
     return flat_grad
+
+
+class PeerExchange:
+    """Exchange buffers of pcvae_dp_reduce_adam (include/pcvae_b200.h): one cudaMalloc'ed buffer per rank, opened on
+    every other rank of the node through CUDA IPC; the 64-byte handles travel over torch.distributed.  Collective:
+    every rank of `group` must construct it (and later call `FusedTrainer.step`) in lockstep."""
+
+    def __init__(self, param_count: int, group, device):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import lib as L
+        self.lib = L.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > L.DP_MAX_WORLD:
+            raise L.PcvaeError(f"PeerExchange: world size {self.world} > {L.DP_MAX_WORLD}")
+        self.device = torch.device(device)
+        self.P = param_count
+        self.seq = 0
+        self.own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pcvae_dp_exchange_alloc(param_count, self.world, C.byref(self.own), handle), "pcvae_dp_exchange_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs = [None] * self.world
+        self.opened = []
+        with torch.cuda.device(self.device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs[r] = self.own.value
+                else:
+                    q = C.c_void_p()
+                    L.check(self.lib.pcvae_dp_exchange_open(h, C.byref(q)), "pcvae_dp_exchange_open")
+                    self.ptrs[r] = q.value
+                    self.opened.append(q)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group=group)                       # every buffer is zeroed and mapped before the first push
+
+    def next_seq(self) -> int:
+        self.seq += 1
+        return self.seq
+
+    def check(self):
+        """Host-side check of the bounded wait (synchronises)."""
+        from . import lib as L
+        if int(self.status.item()) != 0:
+            raise L.PcvaeError("pcvae_dp_reduce_adam: a rank did not deliver its gradient within the wait bound")
+
+    def close(self):
+        for q in self.opened:
+            self.lib.pcvae_dp_exchange_close(q)
+        self.opened = []
+        if self.own:
+            self.lib.pcvae_dp_exchange_free(self.own)
+            self.own = None

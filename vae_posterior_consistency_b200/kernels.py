@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -299,6 +300,23 @@ class Engine:
                     "pcvae_reduce_adam")
         return sums
 
+    def dp_reduce_adam(self, xch, grad, theta, exp_avg, exp_avg_sq, step, rows, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+        """Data-parallel tail of a step in one launch (pcvae_dp_reduce_adam): reduce, exchange the reduced gradient with
+        the other ranks over NVLink peer memory (`xch`: dist.PeerExchange), rank-ordered sum, Adam, this rank's sums."""
+        sums = torch.empty(L.NSUMS, device=self.device, dtype=torch.float64)
+        p = L.DpParams()
+        p.grad_partials, p.grid, p.param_count = _p(self.grad_partials()), self.grid, self.P
+        p.grad, p.theta, p.exp_avg, p.exp_avg_sq = _p(grad), _p(theta), _p(exp_avg), _p(exp_avg_sq)
+        p.step, p.lr, p.beta1, p.beta2, p.eps = step, lr, b1, b2, eps
+        p.sums_partials, p.rows, p.obs_dim, p.sums = _p(self.sums_partials()), rows, self.D, _p(sums)
+        p.world, p.rank, p.seq = xch.world, xch.rank, xch.next_seq()
+        for r in range(xch.world):
+            p.peer_buffers[r] = xch.ptrs[r]
+        p.status = _p(xch.status)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pcvae_dp_reduce_adam(C.byref(p), _stream()), "pcvae_dp_reduce_adam")
+        return sums
+
     # ---- reward -----------------------------------------------------------------------
     def reward(self, theta, x, mask, im, workspace=None):
         """R[N, D-1] for one acquisition step (evaluate.py:416-425)."""
@@ -457,6 +475,12 @@ class FusedTrainer:
         self.step_count = 0
         self.regularised, self.alpha, self.beta_w, self.lr = regularised, alpha, beta_w, lr
         self.dist_group, self.world_size = dist_group, world_size
+        # data parallel: the fused reduce + NVLink exchange + Adam kernel unless PCVAE_DP=nccl asks for the plain
+        # reduce -> NCCL all-reduce -> Adam sequence (kept as the cross-check of the fused kernel)
+        self.xch = None
+        if dist_group is not None and world_size > 1 and os.environ.get("PCVAE_DP", "peer") != "nccl":
+            from .dist import PeerExchange
+            self.xch = PeerExchange(self.eng.P, dist_group, theta.device)
 
     def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True):
         e = self.eng
@@ -477,7 +501,11 @@ class FusedTrainer:
 
     def step(self, x, mask, mask_p, eps_q, eps_p, global_rows=None):
         self.step_count += 1
-        if self.dist_group is not None and self.world_size > 1:
+        if self.xch is not None:
+            self.forward_backward(x, mask, mask_p, eps_q, eps_p, global_rows, reduce=False)
+            sums = self.eng.dp_reduce_adam(self.xch, self.grad, self.theta, self.exp_avg, self.exp_avg_sq, self.step_count,
+                                           x.shape[0], lr=self.lr)
+        elif self.dist_group is not None and self.world_size > 1:
             sums = self.forward_backward(x, mask, mask_p, eps_q, eps_p, global_rows)
             torch.distributed.all_reduce(self.grad, group=self.dist_group)
             self.eng.adam_step(self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)

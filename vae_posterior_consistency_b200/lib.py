@@ -29,11 +29,26 @@ SYMBOLS = [
     "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss", "pcvae_set_reward_tensor_cores",
     "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores", "pcvae_enc_tc_workspace_floats",
     "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events", "pcvae_prep_packed",
+    "pcvae_dp_exchange_bytes", "pcvae_dp_exchange_alloc", "pcvae_dp_exchange_open", "pcvae_dp_exchange_close",
+    "pcvae_dp_exchange_free", "pcvae_dp_reduce_adam",
 ]
 
 
 class PcvaeError(RuntimeError):
     pass
+
+
+DP_MAX_WORLD = 16
+
+
+class DpParams(C.Structure):
+    """pcvae_dp_params (include/pcvae_b200.h)."""
+    _fields_ = [("grad_partials", C.c_void_p), ("grid", C.c_int), ("param_count", C.c_long),
+                ("grad", C.c_void_p), ("theta", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("step", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("sums_partials", C.c_void_p), ("rows", C.c_int), ("obs_dim", C.c_int), ("sums", C.c_void_p),
+                ("world", C.c_int), ("rank", C.c_int), ("seq", C.c_uint),
+                ("peer_buffers", C.c_void_p * DP_MAX_WORLD), ("status", C.c_void_p)]
 
 
 class Model(C.Structure):
@@ -156,6 +171,13 @@ def load():
                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
     lib.pcvae_prep_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
+    lib.pcvae_dp_exchange_bytes.restype = C.c_size_t
+    lib.pcvae_dp_exchange_bytes.argtypes = [C.c_long, C.c_int]
+    lib.pcvae_dp_exchange_alloc.argtypes = [C.c_long, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.pcvae_dp_exchange_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.pcvae_dp_exchange_close.argtypes = [C.c_void_p]
+    lib.pcvae_dp_exchange_free.argtypes = [C.c_void_p]
+    lib.pcvae_dp_reduce_adam.argtypes = [C.POINTER(DpParams), C.c_void_p]
     lib.pcvae_reduce_adam.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]
