@@ -41,7 +41,7 @@ class PeerExchange:
     every other rank of the node through CUDA IPC; the 64-byte handles travel over torch.distributed.  Collective:
     every rank of `group` must construct it (and later call `FusedTrainer.step`) in lockstep."""
 
-    def __init__(self, param_count: int, group, device):
+    def __init__(self, param_count: int, group, device, _barrier=True):
         import ctypes as C
         import torch.distributed as dist
         from . import lib as L
@@ -70,7 +70,30 @@ class PeerExchange:
                     self.ptrs[r] = q.value
                     self.opened.append(q)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        dist.barrier(group=group)                       # every buffer is zeroed and mapped before the first push
+        if _barrier:                                    # every buffer is zeroed and mapped before the first push
+            dist.barrier(group=group)                   # (create_or_none: its all-reduce is that barrier)
+
+    @classmethod
+    def create_or_none(cls, param_count: int, group, device):
+        """Collective constructor: the exchange is used only if EVERY rank could set it up (peer access / CUDA IPC can be
+        unavailable, e.g. GPUs of different nodes); otherwise all ranks agree on None and the caller keeps the NCCL
+        all-reduce.  Both are GPU paths; this is a choice of collective, not a fallback of the arithmetic."""
+        import sys
+        import torch.distributed as dist
+        xch, err = None, None
+        try:
+            xch = cls(param_count, group, device, _barrier=False)
+        except Exception as e:                      # noqa: BLE001 -- any set-up failure must reach the vote below
+            err = e
+        ok = torch.tensor([1 if xch is not None else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            return xch
+        if xch is not None:
+            xch.close()
+        if dist.get_rank(group) == 0:
+            print(f"pcvae: NVLink peer exchange unavailable ({err}); using the NCCL all-reduce", file=sys.stderr)
+        return None
 
     def next_seq(self) -> int:
         self.seq += 1

@@ -480,7 +480,7 @@ class FusedTrainer:
         self.xch = None
         if dist_group is not None and world_size > 1 and os.environ.get("PCVAE_DP", "peer") != "nccl":
             from .dist import PeerExchange
-            self.xch = PeerExchange(self.eng.P, dist_group, theta.device)
+            self.xch = PeerExchange.create_or_none(self.eng.P, dist_group, theta.device)
 
     def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True):
         e = self.eng
