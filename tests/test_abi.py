@@ -67,3 +67,41 @@ def test_product_package_does_not_import_the_oracle():
         if fn.endswith(".py"):
             txt = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in re.sub(r'""".*?"""', "", txt, flags=re.S).replace("the oracle", ""), fn
+
+
+def test_sass_every_mma_descriptor_register_is_written_before_its_first_use():
+    """Guard against a ptxas 12.9 miscompilation seen in k_enc_fwd_tc: the high word of a tcgen05 shared-memory
+    descriptor pair (stride-byte-offset + version bits) was materialised by a UMOV placed BEHIND the first UTCHMMA that
+    reads it, inside the work-item loop, so the first item of every CTA ran with SBO = 0.  For every UTCHMMA in the
+    library, both uniform registers of its gdesc[URn] pair must have a write earlier in the function's linear order."""
+    from vae_posterior_consistency_b200 import build
+    out = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+        if name and m:
+            funcs[name].append(m.group(1).strip())
+    n_mma, bad = 0, []
+    for fn, ins in funcs.items():
+        first_write = {}
+        for i, s_ in enumerate(ins):
+            m = re.match(r"(?:@!?U?P\d+\s+)?(\S+)\s+(UR\d+)", s_)
+            if not m or m.group(1).startswith(("UTCHMMA", "UTCBAR", "UBLKCP")):
+                continue
+            dst = int(m.group(2)[2:])
+            for r in ([dst, dst + 1] if (".64" in m.group(1) or ".WIDE" in m.group(1)) else [dst]):
+                first_write.setdefault(r, i)
+        for i, s_ in enumerate(ins):
+            if "UTCHMMA" in s_:
+                n_mma += 1
+                for m in re.finditer(r"gdesc\[UR(\d+)\]", s_):
+                    for r in (int(m.group(1)), int(m.group(1)) + 1):
+                        if first_write.get(r, 1 << 30) > i:
+                            bad.append((fn, i, f"UR{r}", first_write.get(r)))
+    assert n_mma > 100, "no tcgen05 MMAs found in the library: the check did not look at anything"
+    assert not bad, bad[:5]

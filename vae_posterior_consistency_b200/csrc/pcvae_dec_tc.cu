@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
     __shared__ float red_s[NWARP][PCVAE_NSUMS];
     __shared__ __align__(8) uint64_t bar_s;
     __shared__ __align__(8) uint64_t in_bar;
+    __shared__ __align__(8) uint64_t desc_s[6];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = a.L.D, N6 = (D + 15) & ~15;
@@ -94,6 +95,15 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
     const uint64_t f4h = make_desc(smem_u32(W4h), cs4, 128), f4l = make_desc(smem_u32(W4l), cs4, 128);
     const uint64_t f5h = make_desc(smem_u32(W5h), cs5, 128), f5l = make_desc(smem_u32(W5l), cs5, 128);
     const uint64_t f6h = make_desc(smem_u32(W6h), cs6, 128), f6l = make_desc(smem_u32(W6l), cs6, 128);
+    if (tid == 0) { st_desc(&desc_s[0], f4h); st_desc(&desc_s[1], f4l); st_desc(&desc_s[2], f5h); st_desc(&desc_s[3], f5l); st_desc(&desc_s[4], f6h); st_desc(&desc_s[5], f6l); }
+    __syncthreads();
+    // opaque run-time copies (loaded back with volatile loads): nothing for ptxas to fold or hoist
+    const uint64_t r_f4h = ld_desc(&desc_s[0]);
+    const uint64_t r_f4l = ld_desc(&desc_s[1]);
+    const uint64_t r_f5h = ld_desc(&desc_s[2]);
+    const uint64_t r_f5l = ld_desc(&desc_s[3]);
+    const uint64_t r_f6h = ld_desc(&desc_s[4]);
+    const uint64_t r_f6l = ld_desc(&desc_s[5]);
     const uint64_t fs4 = (2 * cs4) >> 4, fs5 = (2 * cs5) >> 4, fs6 = (2 * cs6) >> 4;
     const uint32_t idF4 = make_idesc(ROWS, F4_N), idF5 = make_idesc(ROWS, F5_N), idF6 = make_idesc(ROWS, N6);
 
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
 #pragma unroll
                 for (int j = 0; j < TCW_Z; ++j) zT[j * 32] = v[j];
             }
-            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_HI + 16, f4h, f4l, fs4, F4_C / 2, idF4); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_HI + 16, r_f4h, r_f4l, fs4, F4_C / 2, idF4); });
             // the barrier inside mma_kick ends the previous item's loss epilogue: the staging buffer is free
             const bool staged = issue_in(t);
             mma_wait(cx, &bar_s);
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
                 scratch_store(h4T, c16, TCW_H4, v, 16);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, f5h, f5l, fs5, F5_C / 2, idF5); });
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, r_f5h, r_f5l, fs5, F5_C / 2, idF5); });
 
             // ---- h5 = relu(acc5) | 1 -> RA, HBM ----
             uint32_t m5 = 0;                                  // relu mask of this thread's 28 h5 columns
@@ -222,7 +232,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
             }
             reluT[cg] = m5;
             reluT[4 + cg] = m4;
-            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, f6h, f6l, fs6, F6_C / 2, idF6); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_f6h, r_f6l, fs6, F6_C / 2, idF6); });
             // while the tensor pipe runs F6: this thread's 28 entries of x and of the two masks (as bits)
             if (staged) { mbar_wait(&in_bar, in_ph); in_ph ^= 1u; }
             float xr[28];
@@ -336,6 +346,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     __shared__ float red_s[NWARP][3];
     __shared__ __align__(8) uint64_t bar_s;
     __shared__ __align__(8) uint64_t in_bar;
+    __shared__ __align__(8) uint64_t desc_s[6];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = a.L.D;
@@ -381,6 +392,15 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     const uint64_t x6h = make_desc(smem_u32(T6h), cs6, 128), x6l = make_desc(smem_u32(T6l), cs6, 128);
     const uint64_t x5h = make_desc(smem_u32(T5h), cs5, 128), x5l = make_desc(smem_u32(T5l), cs5, 128);
     const uint64_t x4h = make_desc(smem_u32(T4h), cs4, 128), x4l = make_desc(smem_u32(T4l), cs4, 128);
+    if (tid == 0) { st_desc(&desc_s[0], x6h); st_desc(&desc_s[1], x6l); st_desc(&desc_s[2], x5h); st_desc(&desc_s[3], x5l); st_desc(&desc_s[4], x4h); st_desc(&desc_s[5], x4l); }
+    __syncthreads();
+    // opaque run-time copies (loaded back with volatile loads): nothing for ptxas to fold or hoist
+    const uint64_t r_x6h = ld_desc(&desc_s[0]);
+    const uint64_t r_x6l = ld_desc(&desc_s[1]);
+    const uint64_t r_x5h = ld_desc(&desc_s[2]);
+    const uint64_t r_x5l = ld_desc(&desc_s[3]);
+    const uint64_t r_x4h = ld_desc(&desc_s[4]);
+    const uint64_t r_x4l = ld_desc(&desc_s[5]);
     const uint64_t xs6 = (2 * cs6) >> 4, xs5 = (2 * cs5) >> 4, xs4 = (2 * cs4) >> 4;
     const uint32_t idX6 = make_idesc(ROWS, X6_N), idX5 = make_idesc(ROWS, X5_N), idX4 = make_idesc(ROWS, X4_N);
 
@@ -437,7 +457,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 if (a.nbr > 1) { ld4(a.mean[1], lat_mp); ld4(a.logvar[1], lat_lp); }
                 if (a.eps[br]) ld4(a.eps[br], lat_e);
             }
-            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, x6h, x6l, xs6, X6_C / 2, idX6); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_x6h, r_x6l, xs6, X6_C / 2, idX6); });
             issue_in(w + gridDim.x);        // every thread has read the staging buffer (barrier inside mma_kick)
             mma_wait(cx, &bar_s);
 
@@ -462,7 +482,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 st_part(lane_addr + RA_LO + c28, part, lo);
                 scratch_store(dp5T, c28 + j0, TCW_H5, v, cnt);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, x5h, x5l, xs5, X5_C / 2, idX5); });
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, r_x5h, r_x5l, xs5, X5_C / 2, idX5); });
 
             // ---- dpre4 = dh4 * relu'(h4) -> RB, HBM ----
             {
@@ -478,7 +498,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
                 scratch_store(dp4T, c16, TCW_H4, v, 16);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, x4h, x4l, xs4, X4_C / 2, idX4); });
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, r_x4h, r_x4l, xs4, X4_C / 2, idX4); });
 
             // ---- latent-space terms: KL sums, d_mean / d_logvar; the row's 10 latents are split over its column
             //      groups (4 + 4 + 2 + 0) so that no warp waits for a single group doing all of them ----

@@ -10,6 +10,8 @@
 //   k_wgrad_tc     dWaug for layers 1, 2, 3 from the feature-major scratch (pcvae_wgrad_tc.cu, one launch)
 //
 // The backward kernel needs 240 TMEM columns and 62 KB of shared memory, so two of its CTAs share an SM.
+#include <cstdlib>
+
 #include "pcvae_tc_tile.cuh"
 #include "pcvae_train.cuh"
 
@@ -30,10 +32,12 @@ constexpr int B_D3H = 0, B_D3L = 32, B_AC2 = 64, B_RBH = 128, B_RBL = 184, B_AC1
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const int stage_inputs) {
+__global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const int stage_inputs_mode) {
+    const int stage_inputs = stage_inputs_mode & 1;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar_s;
     __shared__ __align__(8) uint64_t in_bar;
+    __shared__ __align__(8) uint64_t desc_s[6];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int D = a.L.D, K1 = (D + 8) & ~7, C1 = K1 / 4;
@@ -67,6 +71,15 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
     const uint64_t e1h = make_desc(smem_u32(W1h), cs1, 128), e1l = make_desc(smem_u32(W1l), cs1, 128);
     const uint64_t e2h = make_desc(smem_u32(W2h), cs2, 128), e2l = make_desc(smem_u32(W2l), cs2, 128);
     const uint64_t e3h = make_desc(smem_u32(W3h), cs3, 128), e3l = make_desc(smem_u32(W3l), cs3, 128);
+    if (tid == 0) { st_desc(&desc_s[0], e1h); st_desc(&desc_s[1], e1l); st_desc(&desc_s[2], e2h); st_desc(&desc_s[3], e2l); st_desc(&desc_s[4], e3h); st_desc(&desc_s[5], e3l); }
+    __syncthreads();
+    // opaque run-time copies (loaded back with volatile loads): nothing for ptxas to fold or hoist
+    const uint64_t r_e1h = ld_desc(&desc_s[0]);
+    const uint64_t r_e1l = ld_desc(&desc_s[1]);
+    const uint64_t r_e2h = ld_desc(&desc_s[2]);
+    const uint64_t r_e2l = ld_desc(&desc_s[3]);
+    const uint64_t r_e3h = ld_desc(&desc_s[4]);
+    const uint64_t r_e3l = ld_desc(&desc_s[5]);
     const uint64_t es1 = (2 * cs1) >> 4, es2 = (2 * cs2) >> 4, es3 = (2 * cs3) >> 4;
     const uint32_t idE1 = make_idesc(ROWS, E1_N), idE2 = make_idesc(ROWS, E2_N), idE3 = make_idesc(ROWS, E3_N);
     const EncTcWs tw = a.tw;
@@ -87,25 +100,42 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
         }
         return true;
     };
-    bool staged = issue_in(blockIdx.x, 0);
-    // NOTE: tiles are strided over the CTAs and both branches of a tile run back to back on one CTA.  Flattening this
-    // into (tile, branch) work items as k_dec_fwd_tc / k_dec_bwd_tc do balances the load better (7 vs 8 items per CTA
-    // at 1024 items), but that version of THIS kernel computed wrong layer-1 products (h1 off by O(1), constant-1
-    // column not 1) although its inputs in TMEM / scratch were right, and faulted when run after certain other
-    // kernels, with nvcc 12.9.86; the cause was not found (see tests/test_gpu_parity.py::
-    // test_throughput_prep_then_step_tcgen05_matches_ffma, which pins the symptom), so the nested form stays.
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // The j-th work item of this CTA.  Flat order (default, bit 1 of `mode`): (tile, branch) pairs, tile-major, strided
+    // over the CTAs as in k_dec_fwd_tc (7 instead of 8 items on the busiest CTA at 1024 items).  Nested order
+    // (PCVAE_ENC_FLAT=0, kept as a cross-check): tiles strided over the CTAs, both branches of a tile back to back.
+    const bool flat = (stage_inputs_mode & 2) != 0;
+    const int nitems = ntiles * a.nbr;
+    auto item_of = [&](int j, int& t_, int& br_) -> bool {
+        if (flat) {
+            const int w = blockIdx.x + j * gridDim.x;
+            if (w >= nitems) return false;
+            t_ = a.nbr == 2 ? (w >> 1) : w;
+            br_ = a.nbr == 2 ? (w & 1) : 0;
+            return true;
+        }
+        const int tj = j / a.nbr;
+        br_ = j - tj * a.nbr;
+        t_ = blockIdx.x + tj * gridDim.x;
+        return t_ < ntiles;
+    };
+    bool staged = false;
+    {
+        int t0, b0;
+        if (item_of(0, t0, b0)) staged = issue_in(t0, b0);
+    }
+    for (int j = 0;; ++j) {
+        int t, br, tn = 0, bn = 0;
+        if (!item_of(j, t, br)) break;
+        const bool has_next = item_of(j + 1, tn, bn);
         const int grow = t * ROWS + row;
         const bool ok = grow < a.B;
-        {   // pull the next tile of this CTA towards L2 while this one is processed
-            const int tn = t + gridDim.x;
-            if (tn < ntiles) {
-                const long r0 = (long)tn * ROWS, nrows = min((long)ROWS, (long)a.B - r0);
-                prefetch_l2(a.x + r0 * D, nrows * D * 4, tid);
-                for (int b = 0; b < a.nbr; ++b) prefetch_l2((const char*)a.mask[b] + r0 * D * msz, nrows * D * msz, tid);
-            }
+        if (has_next && (flat || bn == 0)) {   // pull the next tile of this CTA towards L2 while this one is processed
+            const long r0 = (long)tn * ROWS, nrows = min((long)ROWS, (long)a.B - r0);
+            prefetch_l2(a.x + r0 * D, nrows * D * 4, tid);
+            for (int b = 0; b < a.nbr; ++b)
+                if (!flat || b == bn) prefetch_l2((const char*)(b ? a.mask[1] : a.mask[0]) + r0 * D * msz, nrows * D * msz, tid);
         }
-        for (int br = 0; br < a.nbr; ++br) {
+        {
             const long vt = (long)br * ntiles + t;            // tile of the scratch: [vt][row / 32][feature][row % 32]
             float* inT = tw.inT + (long)vt * (ETW_IN * ROWS) + (row >> 5) * (32 * ETW_IN) + (row & 31);
             float* h1T = tw.h1T + (long)vt * (ETW_H1 * ROWS) + (row >> 5) * (32 * ETW_H1) + (row & 31);
@@ -129,7 +159,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                             const long gi = (long)grow * D + c;
                             const float4 x4 = *reinterpret_cast<const float4*>(a.x + gi);
                             float m[4];
-                            load_mask4<true>(a.mask[br], gi, a.mask_kind, m);
+                            load_mask4<true>(br ? a.mask[1] : a.mask[0], gi, a.mask_kind, m);
                             xv[0] = x4.x * m[0]; xv[1] = x4.y * m[1]; xv[2] = x4.z * m[2]; xv[3] = x4.w * m[3];
                         }
                     } else if (c == D) {
@@ -150,9 +180,9 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                     if (save) scratch_store(inT, c28 + j0, D + 1, v, cnt);
                 }
             }
-            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, e1h, e1l, es1, K1 / 8, idE1); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_e1h, r_e1l, es1, K1 / 8, idE1); });
             // every thread has read its inputs (barrier inside mma_kick): the staging buffer is free for the next item
-            staged = (br + 1 < a.nbr) ? issue_in(t, br + 1) : issue_in(t + gridDim.x, 0);
+            staged = has_next ? issue_in(tn, bn) : false;
             mma_wait(cx, &bar_s);
 
             // ---- h1 = relu(acc1) | 1 -> RA, HBM ----
@@ -176,7 +206,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                 st_part(lane_addr + RA_LO + c28, part, lo);
                 if (save) scratch_store(h1T, c28 + j0, ETW_H1, v, cnt);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, e2h, e2l, es2, E2_C / 2, idE2); });
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, r_e2h, r_e2l, es2, E2_C / 2, idE2); });
 
             // ---- h2 = relu(acc2) | 1 -> RB, HBM ----
             uint32_t m2 = 0;                                  // relu mask of this thread's 16 h2 columns
@@ -205,7 +235,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                 e01 = *reinterpret_cast<const float2*>(a.eps[br] + gl);
                 if (cg < 2) e23 = *reinterpret_cast<const float2*>(a.eps[br] + gl + 2);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, e3h, e3l, es3, E3_C / 2, idE3); });
+            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, r_e3h, r_e3l, es3, E3_C / 2, idE3); });
 
             // ---- mean | logvar, reparameterisation ----
             if (cg < 3) {
@@ -246,6 +276,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
 __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar_s;
+    __shared__ __align__(8) uint64_t desc_s[6];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     float* T3h = smem;
@@ -266,6 +297,13 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
     const uint32_t cs3 = Y3_N * 16, cs2 = Y2_N * 16;
     const uint64_t y3h = make_desc(smem_u32(T3h), cs3, 128), y3l = make_desc(smem_u32(T3l), cs3, 128);
     const uint64_t y2h = make_desc(smem_u32(T2h), cs2, 128), y2l = make_desc(smem_u32(T2l), cs2, 128);
+    if (tid == 0) { st_desc(&desc_s[0], y3h); st_desc(&desc_s[1], y3l); st_desc(&desc_s[2], y2h); st_desc(&desc_s[3], y2l); }
+    __syncthreads();
+    // opaque run-time copies (loaded back with volatile loads): nothing for ptxas to fold or hoist
+    const uint64_t r_y3h = ld_desc(&desc_s[0]);
+    const uint64_t r_y3l = ld_desc(&desc_s[1]);
+    const uint64_t r_y2h = ld_desc(&desc_s[2]);
+    const uint64_t r_y2l = ld_desc(&desc_s[3]);
     const uint64_t ys3 = (2 * cs3) >> 4, ys2 = (2 * cs2) >> 4;
     const uint32_t idY3 = make_idesc(ROWS, Y3_N), idY2 = make_idesc(ROWS, Y2_N);
     const EncTcWs tw = a.tw;
@@ -314,7 +352,7 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
 #pragma unroll
             for (int j = 0; j < LAT2; ++j) dp3T[j * 32] = v[j];
         }
-        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC2, tmem + B_D3H, tmem + B_D3L, y3h, y3l, ys3, Y3_C / 2, idY3); });
+        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC2, tmem + B_D3H, tmem + B_D3L, r_y3h, r_y3l, ys3, Y3_C / 2, idY3); });
 
         // ---- dpre2 = dh2 * relu'(h2) -> TMEM, HBM ----
         {
@@ -330,7 +368,7 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
             else { tmem_st8(lane_addr + B_RBH + c16, v); tmem_st8(lane_addr + B_RBL + c16, lo); }
             scratch_store(dp2T, c16, ETW_H2, v, 16);
         }
-        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, y2h, y2l, ys2, Y2_C / 2, idY2); });
+        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, r_y2h, r_y2l, ys2, Y2_C / 2, idY2); });
 
         // ---- dpre1 = dh1 * relu'(h1) -> HBM ----
         const uint32_t k1 = m1 & col_bits(c28, H1);                      // column H1 is the bias column
@@ -397,7 +435,8 @@ int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(tc::k_enc_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "enc_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     prof_mark(st);
-    tc::k_enc_fwd_tc<<<grid, NT, sm, st>>>(a, stage_inputs ? 1 : 0);
+    static const int flat_items = [] { const char* e = getenv("PCVAE_ENC_FLAT"); return e && e[0] == '0' ? 0 : 2; }();
+    tc::k_enc_fwd_tc<<<grid, NT, sm, st>>>(a, (stage_inputs ? 1 : 0) | flat_items);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "enc_fwd_tc: launch: %s", cudaGetErrorString(e));
     prof_mark(st);

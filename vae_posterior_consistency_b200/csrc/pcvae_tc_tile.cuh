@@ -129,6 +129,19 @@ __device__ __forceinline__ void image_linear_T(float* hi, float* lo, int nrows, 
     image_scatter<true>(hi, lo, nrows, W, N, K, tid);
 }
 
+// The shared-memory matrix descriptors of a kernel live in SHARED MEMORY and the issuing lane reads the two it needs
+// with volatile loads right before each MMA batch.  Descriptors built from immediates in registers are miscompiled
+// by ptxas 12.9.86 in some code shapes: the constant high word (stride-byte-offset and version bits) of descriptor
+// pairs of different layers is merged into one uniform register whose UMOV is placed behind a later use inside the
+// work-item loop, so the FIRST item of a CTA issues its first MMA batch with SBO = 0 (image rows >= 8 alias rows
+// 0..7; found with profiles/r01_ncu_summary.md "descriptor high word", guarded by tests/test_abi.py's SASS check).
+__device__ __forceinline__ void st_desc(uint64_t* slot, uint64_t d) { *reinterpret_cast<volatile uint64_t*>(slot) = d; }
+__device__ __forceinline__ uint64_t ld_desc(const uint64_t* slot) {
+    uint64_t v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(slot)) : "memory");
+    return v;
+}
+
 struct TileCtx {
     uint32_t tmem, lane_addr, ph;
     int q, cg, row, c28, c16;
