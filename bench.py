@@ -380,11 +380,19 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist_group = dist.group.WORLD
-    tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, theta, regularised=True, alpha=1.0, dist_group=dist_group,
-                         world_size=world)
-    eng = tr.eng
     n_total = args.warmup + args.steps
     perm = torch.cat([torch.randperm(T, device=dev, generator=g) for _ in range((n_total * B + T - 1) // T + 1)])
+    graphed = world == 1 and os.environ.get("PCVAE_GRAPH", "1") != "0"
+    if graphed:
+        # one GPU: the whole step (gather + sub-mask + noise, six training kernels, reduce + Adam) is replayed from a CUDA
+        # graph; the per-step scalars live in a device counter (KR.GraphedFusedTrainer)
+        tr = KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, theta, table, mtable, B, n_total, keep=0.7, seed=99, regularised=True,
+                                    alpha=1.0)
+        tr.set_batches(perm[:n_total * B].view(n_total, B))
+    else:
+        tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, theta, regularised=True, alpha=1.0, dist_group=dist_group,
+                             world_size=world)
+    eng = tr.eng
     x = torch.empty(B, D, device=dev)
     mask = torch.empty(B, D, device=dev, dtype=torch.bool)
     mask_p = torch.empty(B, D, device=dev, dtype=torch.bool)
@@ -436,20 +444,42 @@ def run_ours(args):
             launches[0] += 6 + 1
         return sums
 
-    for s in range(args.warmup):
-        prep_step(s, x, mask); train_step(x, mask, False)
-    barrier(world)
-    launches[0] = 0
-    w0 = time.time()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for s in range(args.warmup, n_total):
-        prep_step(s, x, mask); sums = train_step(x, mask, (s - args.warmup) % 4 == 0)
-    t1.record()
-    barrier(world)
-    clocks.window(w0, time.time())
-    train_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
-    train_launches = launches[0]
+    if graphed:
+        w_graph = min(3, args.warmup)
+        tr.capture(warmup=w_graph)                       # `w_graph` eager warm-up steps, then the capture
+        for s in range(args.warmup - w_graph):
+            tr.step_graph()
+        barrier(world)
+        w0 = time.time()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for s in range(args.steps):
+            sums = tr.step_graph()
+        t1.record()
+        barrier(world)
+        clocks.window(w0, time.time())
+        train_ms = t0.elapsed_time(t1) / args.steps
+        train_launches = 8 * args.steps                  # the eight kernels of the captured step, per replay
+        sums = sums.clone()
+        # per-kernel times: the same step launched kernel by kernel, the library's own events between its launches
+        for s in range(24):
+            prep_step(s, x, mask); train_step(x, mask, s % 4 == 0)
+        torch.cuda.synchronize()
+    else:
+        for s in range(args.warmup):
+            prep_step(s, x, mask); train_step(x, mask, False)
+        barrier(world)
+        launches[0] = 0
+        w0 = time.time()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for s in range(args.warmup, n_total):
+            prep_step(s, x, mask); sums = train_step(x, mask, (s - args.warmup) % 4 == 0)
+        t1.record()
+        barrier(world)
+        clocks.window(w0, time.time())
+        train_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
+        train_launches = launches[0]
     kernel_us = {}
     for name, i0, i1 in KERNELS:
         if ev_sets:
@@ -608,7 +638,7 @@ def run_ours(args):
             "ms_per_step": train_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"Reg_VAE D={D}, synthetic {T} x {D} table resident in HBM, batch {B} rows per GPU "
-                                   f"per step (cfg4), device-side gather + Philox sub-mask/noise, "
+                                   f"per step (cfg4), device-side gather + Philox sub-mask/noise, {'step replayed from a CUDA graph, ' if graphed else ''}"
                                    f"{('gradient exchange over NVLink peer memory fused with the reduce and ' if tr.xch is not None else 'NCCL grad all-reduce, ') if world > 1 else ''}Adam",
                        "batch_per_gpu": B, "global_batch": B * world, "table_rows": T,
                        "l2": "inputs larger than L2 (500 MB table, a fresh 33 MB batch gathered every step)",

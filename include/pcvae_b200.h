@@ -330,6 +330,20 @@ int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* 
                      uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
                      unsigned long long seed, unsigned long long offset, void* stream);
 
+/* Replayable variants for a CUDA graph of the whole training step (launch-bound small batches, train.py's default batch
+ * of 64; also removes the launch gaps at large batches): the per-step scalars come from a device counter
+ * step_state[0] = number of completed steps (step_state[1] is a ticket word; both zero-initialised by the caller).
+ *   pcvae_prep_batch_dev : rows of batch (step % n_batches) of idx_batches[n_batches][rows], Philox offset
+ *                          offset0 + 8 * step                          (pcvae_prep_batch with idx + ..., offset0 + 8 step)
+ *   pcvae_reduce_adam_dev: Adam step number step + 1 (bias corrections computed on the device); the last block of the
+ *                          launch then advances step_state[0]          (pcvae_reduce_adam with step + 1) */
+int pcvae_prep_batch_dev(const float* table, const uint8_t* mask_table, const long* idx_batches, long n_batches, float* x,
+                         uint8_t* mask, uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
+                         unsigned long long seed, unsigned long long offset0, const unsigned long long* step_state, void* stream);
+int pcvae_reduce_adam_dev(const float* grad_partials, int grid, long param_count, float* grad, float* theta, float* exp_avg,
+                          float* exp_avg_sq, unsigned long long* step_state, float lr, float beta1, float beta2, float eps,
+                          const float* sums_partials, int rows, int obs_dim, double* sums, void* stream);
+
 /* Host-streamed batches (a table kept in host memory; the e2e path of bench.py).  What DataLoader + collate hand to
  * train.py:36-58 as (data_sample, mask) arrives here in a compact form built once by the loader:
  *   mask_bits[rows][ceil(obs_dim / 32)]  bit j of word w = mask[row][32 w + j]           (always)

@@ -350,6 +350,46 @@ def test_prep_packed_equals_prep_batch_on_the_same_rows(B, D):
         assert torch.equal(res[0][1], res[1][1])          # and every gradient, bit for bit
 
 
+@pytest.mark.parametrize("B,D,T", [(64, 20, 455), (4096, 100, 20000)])
+def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D, T):
+    """GraphedFusedTrainer: the whole step (prep_batch_dev + six kernels + reduce_adam_dev, per-step scalars from a device
+    counter) replayed from a CUDA graph == the same launches issued eagerly, bit for bit; and == the host-counted
+    sequence pcvae_prep_batch(offset = 8 step) -> FusedTrainer.step up to the rounding of Adam's bias correction."""
+    KR, L = _mods()
+    lib = L.load()
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    table = torch.rand(T, D, device=dev, generator=g)
+    mtable = torch.rand(T, D, device=dev, generator=g) < 0.7
+    nb, steps = T // B, 9
+    idx = torch.stack([torch.randperm(T, device=dev, generator=g)[:B] for _ in range(nb)])
+    p = O.init_params("mlp", D, 0, seed=7)
+    mk = lambda: KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, KR.flatten_params(p, L.FAMILY_MLP, dev), table, mtable, B, nb,
+                                        keep=0.7, seed=99)
+    a, b = mk(), mk()
+    a.set_batches(idx); b.set_batches(idx)
+    a.capture()                                            # three eager warm-up steps, then the capture
+    for _ in range(steps):
+        a.step_graph()
+    for _ in range(3 + steps):
+        b.step_eager_dev()
+    torch.cuda.synchronize()
+    assert a.step_count == b.step_count == 3 + steps and int(a.state[0]) == int(b.state[0]) == 3 + steps
+    assert torch.equal(a.theta, b.theta) and torch.equal(a.exp_avg_sq, b.exp_avg_sq) and torch.equal(a.total, b.total)
+    # host-counted reference sequence
+    tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, KR.flatten_params(p, L.FAMILY_MLP, dev), regularised=True)
+    x = torch.empty(B, D, device=dev); m = torch.empty(B, D, device=dev, dtype=torch.bool); mp = torch.empty_like(m)
+    eps = torch.empty(2, B, 10, device=dev)
+    total = 0.0
+    for s_ in range(3 + steps):
+        L.check(lib.pcvae_prep_batch(table.data_ptr(), mtable.data_ptr(), idx[s_ % nb].data_ptr(), x.data_ptr(), m.data_ptr(),
+                                     mp.data_ptr(), eps.data_ptr(), B, D, 2, 0.7, 99, 8 * s_,
+                                     torch.cuda.current_stream().cuda_stream), "pcvae_prep_batch")
+        total += float(tr.step(x, m, mp, eps[0], eps[1]))
+    torch.testing.assert_close(a.theta, tr.theta, rtol=0, atol=1e-6)
+    assert abs(float(a.total) - total) <= 1e-6 * abs(total)
+
+
 def test_empty_batch_is_a_no_op():
     KR, L = _mods()
     p = O.init_params("mlp", 13)

@@ -76,11 +76,17 @@ __global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ ta
                                                     const long* __restrict__ idx, float* __restrict__ x,
                                                     uint8_t* __restrict__ mask, uint8_t* __restrict__ mask_p,
                                                     float* __restrict__ eps, int B, int D, int n_eps, float keep,
-                                                    unsigned long long seed, unsigned long long offset) {
+                                                    unsigned long long seed, unsigned long long offset,
+                                                    const unsigned long long* __restrict__ step_state, long n_batches) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int D4 = D >> 2;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    if (step_state) {        // replayable launch: batch number and Philox offset come from the device step counter
+        const unsigned long long st = *step_state;
+        idx += (long)(st % (unsigned long long)n_batches) * B;
+        offset += st * 8ull;
+    }
     for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
         const long src = idx[b];
         if (lane < D4) {
@@ -206,9 +212,26 @@ int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* 
     if (rows == 0) return PCVAE_OK;
     if (!table || !mask_table || !idx || !x || !mask || !mask_p || (n_eps > 0 && !eps)) return fail(PCVAE_EINVAL, "prep_batch: null pointer");
     k_prep_batch<<<grid * 8, 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx, x, mask, mask_p, eps, rows, obs_dim, n_eps,
-                                                              keep_prob, seed, offset);
+                                                              keep_prob, seed, offset, nullptr, 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "prep_batch: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_prep_batch_dev(const float* table, const uint8_t* mask_table, const long* idx_batches, long n_batches, float* x,
+                         uint8_t* mask, uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
+                         unsigned long long seed, unsigned long long offset0, const unsigned long long* step_state, void* stream) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (rows < 1 || obs_dim < 4 || obs_dim > 128 || obs_dim % 4 || n_eps < 0 || n_eps > 2 || !(keep_prob >= 0.f && keep_prob <= 1.f) ||
+        n_batches < 1)
+        return fail(PCVAE_EINVAL, "prep_batch_dev: bad arguments (obs_dim must be a multiple of 4, <= 128; n_eps 0..2; n_batches >= 1)");
+    if (!table || !mask_table || !idx_batches || !x || !mask || !mask_p || (n_eps > 0 && !eps) || !step_state)
+        return fail(PCVAE_EINVAL, "prep_batch_dev: null pointer");
+    k_prep_batch<<<grid * 8, 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx_batches, x, mask, mask_p, eps, rows, obs_dim, n_eps,
+                                                              keep_prob, seed, offset0, step_state, n_batches);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "prep_batch_dev: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }
 

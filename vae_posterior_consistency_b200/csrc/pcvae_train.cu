@@ -682,12 +682,26 @@ __global__ void k_adam(float* __restrict__ theta, const float* __restrict__ grad
 // reduce + Adam (+ loss sums) in one launch: a block owns 32 consecutive parameters; its eight warps sum interleaved
 // eighths of the per-CTA partials (128-byte coalesced loads, always in the same order), warp 0 combines the eight
 // sums in a fixed order and applies torch.optim.Adam; block 0 also reduces the loss sums.
+// DEV: the 1-based Adam step is *state + 1 (device counter of completed steps, so that a CUDA graph can replay the
+// launch); lr_bc1 then carries the plain learning rate and the bias corrections are computed here.  The last block to
+// finish (ticket state[1]) advances the counter: every block has read it by then.
+template <bool DEV>
 __global__ void __launch_bounds__(256) k_reduce_adam(const float* __restrict__ gp, int grid, long P, float* __restrict__ grad,
                                                      float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                                                      float lr_bc1, float inv_sqrt_bc2, float b1, float b2, float eps,
-                                                     const float* __restrict__ sp, double nll_const, double* __restrict__ sums) {
+                                                     const float* __restrict__ sp, double nll_const, double* __restrict__ sums,
+                                                     unsigned long long* __restrict__ state) {
     __shared__ float red[8][32];
+    __shared__ float bc_s[2];
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    if (DEV) {
+        if (threadIdx.x == 0) {
+            const double step = (double)(*reinterpret_cast<volatile unsigned long long*>(state) + 1ull);
+            const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+            bc_s[0] = (float)((double)lr_bc1 / bc1);
+            bc_s[1] = (float)(1.0 / sqrt(bc2));
+        }
+    }
     const long i = (long)blockIdx.x * 32 + lane;
     float s = 0.f;
     if (i < P) {
@@ -701,6 +715,7 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const float* __restrict__ g
     }
     red[part][lane] = s;
     __syncthreads();
+    if (DEV) { lr_bc1 = bc_s[0]; inv_sqrt_bc2 = bc_s[1]; }
     if (part == 0 && i < P) {
         float g = red[0][lane];
 #pragma unroll
@@ -711,6 +726,17 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const float* __restrict__ g
         m[i] = mi;
         v[i] = vi;
         theta[i] -= lr_bc1 * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+    }
+    if (DEV) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned* ticket = reinterpret_cast<unsigned*>(state + 1);
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1) {         // last block: every block has read the counter
+                *ticket = 0u;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long*>(state) = *reinterpret_cast<volatile unsigned long long*>(state) + 1ull;
+            }
+        }
     }
     if (sp && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + PCVAE_NSUMS) {
         const int j = threadIdx.x - 32;
@@ -1020,11 +1046,26 @@ int pcvae_reduce_adam(const float* grad_partials, int grid, long param_count, fl
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     const double c = 0.5 * 1.8378770664093453 * (double)rows * (double)obs_dim;   // 0.5*log(2*pi) per entry
     const int blocks = (int)((param_count + 31) / 32);
-    k_reduce_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_partials, grid, param_count, grad, theta, exp_avg, exp_avg_sq,
-                                                            (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps,
-                                                            sums_partials, c, sums);
+    k_reduce_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_partials, grid, param_count, grad, theta, exp_avg, exp_avg_sq,
+                                                                   (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps,
+                                                                   sums_partials, c, sums, nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reduce_adam: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_reduce_adam_dev(const float* grad_partials, int grid, long param_count, float* grad, float* theta, float* exp_avg,
+                          float* exp_avg_sq, unsigned long long* step_state, float lr, float beta1, float beta2, float eps,
+                          const float* sums_partials, int rows, int obs_dim, double* sums, void* stream) {
+    if (!grad_partials || !grad || !theta || !exp_avg || !exp_avg_sq || grid < 1 || param_count < 1 || !step_state)
+        return fail(PCVAE_EINVAL, "reduce_adam_dev: bad arguments");
+    if ((sums_partials == nullptr) != (sums == nullptr)) return fail(PCVAE_EINVAL, "reduce_adam_dev: sums_partials and sums go together");
+    const double c = 0.5 * 1.8378770664093453 * (double)rows * (double)obs_dim;
+    const int blocks = (int)((param_count + 31) / 32);
+    k_reduce_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_partials, grid, param_count, grad, theta, exp_avg, exp_avg_sq,
+                                                                  lr, 1.0f, beta1, beta2, eps, sums_partials, c, sums, step_state);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reduce_adam_dev: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }
 

@@ -515,3 +515,93 @@ class FusedTrainer:
                                         x.shape[0], lr=self.lr)
         rows = x.shape[0] if global_rows is None else global_rows
         return loss_from_sums(sums, rows, self.alpha, self.beta_w, self.regularised)
+
+
+class GraphedFusedTrainer(FusedTrainer):
+    """FusedTrainer with the whole step -- batch gather + sub-mask + noise (pcvae_prep_batch_dev), the six training
+    kernels, reduce + Adam (pcvae_reduce_adam_dev) and the running loss total -- captured once in a CUDA graph and
+    replayed (throughput mode, single GPU, uint8 masks, obs_dim % 4 == 0).  The per-step scalars (batch number, Philox
+    offset, Adam step) come from a device counter, so a replay is an exact repetition of the launch sequence an eager
+    `prep_batch -> step` would issue for that step number (tests/test_gpu_parity.py checks bit-identity).  At the
+    reference's default batch of 64 the step is launch-bound: 210 -> 96 us; at 65 536 rows the launch gaps go: 416 -> 377 us.
+
+    `idx_batches` holds n_batches index lists of `batch_rows` rows; step number s uses list s % n_batches, so the caller
+    writes the lists of an epoch rotated by the step number the epoch starts at (`set_batches`)."""
+
+    def __init__(self, family, obs_dim, emb_dim, theta, table, mask_table, batch_rows, n_batches, keep=0.7, seed=0xC0FFEE,
+                 regularised=True, alpha=1.0, beta_w=1.0, lr=1e-3):
+        super().__init__(family, obs_dim, emb_dim, theta, regularised=regularised, alpha=alpha, beta_w=beta_w, lr=lr)
+        if mask_table.dtype not in (torch.bool, torch.uint8) or obs_dim % 4 or obs_dim > 128:
+            raise L.PcvaeError("GraphedFusedTrainer: needs uint8 / bool masks and obs_dim % 4 == 0, obs_dim <= 128")
+        dev = theta.device
+        self.table, self.mtable = _f32(table), mask_table.contiguous()
+        self.B, self.n_batches, self.keep, self.seed = int(batch_rows), int(n_batches), float(keep), int(seed)
+        self.idx = torch.zeros(self.n_batches, self.B, dtype=torch.int64, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)          # [completed steps, ticket]
+        self.x = torch.empty(self.B, obs_dim, device=dev)
+        self.mask = torch.empty(self.B, obs_dim, device=dev, dtype=mask_table.dtype)
+        self.mask_p = torch.empty_like(self.mask)
+        self.n_eps = 2 if regularised else 1
+        self.eps = torch.empty(self.n_eps, self.B, LATENT, device=dev)
+        self.total = torch.zeros((), dtype=torch.float64, device=dev)       # sum of the step losses since reset_total()
+        self.sums = None
+        self.graph = None
+
+    def set_batches(self, idx_batches: torch.Tensor):
+        """Index lists of the coming n_batches steps, in order; rotated here so that list j is used at step number
+        step_count + j."""
+        assert idx_batches.shape == (self.n_batches, self.B)
+        rot = self.step_count % self.n_batches
+        self.idx.copy_(torch.roll(idx_batches.to(self.idx.device), rot, 0))
+
+    def reset_total(self):
+        self.total.zero_()
+
+    def _launch_step(self):
+        with torch.cuda.device(self.theta.device):
+            L.check(self.eng.lib.pcvae_prep_batch_dev(_p(self.table), _p(self.mtable), _p(self.idx), self.n_batches, _p(self.x),
+                                                      _p(self.mask), _p(self.mask_p), _p(self.eps), self.B, self.eng.D, self.n_eps,
+                                                      self.keep, self.seed, 0, _p(self.state), _stream()), "pcvae_prep_batch_dev")
+        self.forward_backward(self.x, self.mask, self.mask_p if self.regularised else None, self.eps[0],
+                              self.eps[1] if self.regularised else None, reduce=False)
+        e = self.eng
+        sums = torch.empty(L.NSUMS, device=e.device, dtype=torch.float64)
+        with torch.cuda.device(e.device):
+            L.check(e.lib.pcvae_reduce_adam_dev(_p(e.grad_partials()), e.grid, e.P, _p(self.grad), _p(self.theta), _p(self.exp_avg),
+                                                _p(self.exp_avg_sq), _p(self.state), self.lr, 0.9, 0.999, 1e-8,
+                                                _p(e.sums_partials()), self.B, e.D, _p(sums), _stream()), "pcvae_reduce_adam_dev")
+        self.total += loss_from_sums(sums, self.B, self.alpha, self.beta_w, self.regularised)
+        return sums
+
+    def capture(self, warmup=3):
+        """Warm up on a side stream (`warmup` real steps, they count), then capture one step."""
+        side = torch.cuda.Stream(device=self.theta.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._launch_step()
+                self.step_count += 1
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.theta.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.sums = self._launch_step()               # recorded, not executed: neither counter moves
+        return self
+
+    def step_graph(self):
+        """One training step (replay).  Returns the step's loss sums (a static buffer: read or clone before the next step)."""
+        if self.graph is None:
+            raise L.PcvaeError("GraphedFusedTrainer: capture() first")
+        self.graph.replay()
+        self.step_count += 1
+        return self.sums
+
+    def step_eager_dev(self):
+        """The same step launched kernel by kernel (cross-check of the replay)."""
+        sums = self._launch_step()
+        self.step_count += 1
+        return sums
+
+    def sync_counter(self):
+        """After steps taken through the inherited host-counted `step` (a ragged last batch): publish the host step count."""
+        self.state[0] = self.step_count

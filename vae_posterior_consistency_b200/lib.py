@@ -30,7 +30,7 @@ SYMBOLS = [
     "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores", "pcvae_enc_tc_workspace_floats",
     "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events", "pcvae_prep_packed",
     "pcvae_dp_exchange_bytes", "pcvae_dp_exchange_alloc", "pcvae_dp_exchange_open", "pcvae_dp_exchange_close",
-    "pcvae_dp_exchange_free", "pcvae_dp_reduce_adam",
+    "pcvae_dp_exchange_free", "pcvae_dp_reduce_adam", "pcvae_prep_batch_dev", "pcvae_reduce_adam_dev",
 ]
 
 
@@ -171,6 +171,11 @@ def load():
                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
     lib.pcvae_prep_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p]
+    lib.pcvae_prep_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p]
+    lib.pcvae_reduce_adam_dev.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]
     lib.pcvae_dp_exchange_bytes.restype = C.c_size_t
     lib.pcvae_dp_exchange_bytes.argtypes = [C.c_long, C.c_int]
     lib.pcvae_dp_exchange_alloc.argtypes = [C.c_long, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]

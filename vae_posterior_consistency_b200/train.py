@@ -82,6 +82,43 @@ def _epoch_batches(loader, device, throughput, prep=None):
         yield x, m
 
 
+def _graph_epoch(trainer, loader, device, regularised, latent_dim):
+    """One epoch through GraphedFusedTrainer: the sampler's full batches are uploaded as one index table and replayed
+    from the CUDA graph, a ragged last batch is gathered and stepped eagerly.  Same RNG consumption on the host as
+    iter(DataLoader) (base seed, then the sampler's permutation)."""
+    torch.empty((), dtype=torch.int64).random_()
+    batches = list(loader.batch_sampler)
+    B = trainer.B
+    full = [b for b in batches if len(b) == B]
+    ragged = [b for b in batches if len(b) != B]
+    trainer.reset_total()
+    trainer.set_batches(torch.as_tensor(full, dtype=torch.int64))
+    done = 0
+    if trainer.graph is None:
+        done = max(1, min(3, len(full)))
+        trainer.capture(warmup=done)
+    for _ in range(len(full) - done):
+        trainer.step_graph()
+    total = trainer.total.clone()
+    lib = L.load()
+    data, mask = trainer.table, trainer.mtable
+    for b in ragged:                                     # at most one
+        idx = torch.as_tensor(b, dtype=torch.int64).to(device)
+        n = idx.numel()
+        x = torch.empty(n, data.shape[1], device=device)
+        m = torch.empty(n, data.shape[1], device=device, dtype=mask.dtype)
+        mp = torch.empty_like(m)
+        eps = torch.empty(2 if regularised else 1, n, latent_dim, device=device)
+        with torch.cuda.device(device):
+            L.check(lib.pcvae_prep_batch(data.data_ptr(), mask.data_ptr(), idx.data_ptr(), x.data_ptr(), m.data_ptr(),
+                                         mp.data_ptr(), eps.data_ptr(), n, data.shape[1], eps.shape[0], trainer.keep,
+                                         trainer.seed, 8 * trainer.step_count, torch.cuda.current_stream().cuda_stream),
+                    "pcvae_prep_batch")
+        total += trainer.step(x, m, mp if regularised else None, eps[0], eps[1] if regularised else None)
+        trainer.sync_counter()
+    return total
+
+
 def _device_submask(mask, keep, step):
     out = torch.empty_like(mask)
     lib = L.load()
@@ -111,10 +148,25 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
     fused = ('notMIWAE' not in vae_type) and (not beta_annealing) and (not regularised or reg_type == 'kl_reg')
     world_size, rank, group = world()
 
+    keep = 1 - p_missingness / 100
+    use_graph = False
     if fused:
         theta = model.flat_theta().detach().clone()
-        trainer = KR.FusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, regularised=regularised,
-                                  alpha=float(alpha), beta_w=float(beta), lr=0.001, dist_group=group, world_size=world_size)
+        table = getattr(data_loader_train, 'pcvae_table', None)
+        bs = getattr(data_loader_train, 'batch_size', None)
+        # throughput mode on one GPU: the whole step is replayed from a CUDA graph (GraphedFusedTrainer); the ragged last
+        # batch of an epoch takes the eager launches.  At the reference's batch of 64 the step is launch-bound.
+        use_graph = (throughput and world_size == 1 and table is not None and table[0].is_cuda and bs is not None
+                     and table[1].dtype in (torch.bool, torch.uint8) and obs_dim % 4 == 0 and obs_dim <= 128
+                     and model.FAMILY == L.FAMILY_MLP and 'with_drop' not in vae_type and table[0].shape[0] >= bs
+                     and os.environ.get('PCVAE_GRAPH', '1') != '0')
+        if use_graph:
+            trainer = KR.GraphedFusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, table[0], table[1], bs,
+                                             table[0].shape[0] // bs, keep=keep, seed=0xC0FFEE, regularised=regularised,
+                                             alpha=float(alpha), beta_w=float(beta), lr=0.001)
+        else:
+            trainer = KR.FusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, regularised=regularised,
+                                      alpha=float(alpha), beta_w=float(beta), lr=0.001, dist_group=group, world_size=world_size)
     else:
         # throughput mode: the launch-bound MNAR step is replayed from a CUDA graph (graphed.py)
         graphed = throughput and 'notMIWAE' in vae_type and not beta_annealing
@@ -134,12 +186,15 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
                                           stage=stage)[1]
                 return fn
             graph_trainer = GraphedTrainer(model, make_fn, optimizer, fill_normal_)
-    keep = 1 - p_missingness / 100
     step = 0
     # throughput mode, fused regularised step: gather + sub-mask + noise in one launch (pcvae_prep_batch)
     prep = dict(keep=keep, n_eps=2, step=0) if (throughput and fused and regularised and latent_dim == 10
                                                 and 'with_drop' not in vae_type) else None
     for i in tqdm(range(max_epochs)):
+        if use_graph:
+            total = _graph_epoch(trainer, data_loader_train, device, regularised, latent_dim)
+            tqdm.write('Epoch: [{}/{}], Total Loss: {}'.format(i, max_epochs, float(total)))
+            continue
         total = torch.zeros((), device=device, dtype=torch.float64)
         for data_sample, mask in _epoch_batches(data_loader_train, device, throughput, prep):
             step += 1
