@@ -382,12 +382,12 @@ def run_ours(args):
         dist_group = dist.group.WORLD
     n_total = args.warmup + args.steps
     perm = torch.cat([torch.randperm(T, device=dev, generator=g) for _ in range((n_total * B + T - 1) // T + 1)])
-    graphed = world == 1 and os.environ.get("PCVAE_GRAPH", "1") != "0"
+    graphed = os.environ.get("PCVAE_GRAPH", "1") != "0" and (world == 1 or os.environ.get("PCVAE_DP", "peer") != "nccl")
     if graphed:
-        # one GPU: the whole step (gather + sub-mask + noise, six training kernels, reduce + Adam) is replayed from a CUDA
-        # graph; the per-step scalars live in a device counter (KR.GraphedFusedTrainer)
+        # the whole step (gather + sub-mask + noise, six training kernels, reduce [+ NVLink gradient exchange] + Adam) is
+        # replayed from a CUDA graph; the per-step scalars live in a device counter (KR.GraphedFusedTrainer)
         tr = KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, theta, table, mtable, B, n_total, keep=0.7, seed=99, regularised=True,
-                                    alpha=1.0)
+                                    alpha=1.0, dist_group=dist_group, world_size=world, global_rows=B * world)
         tr.set_batches(perm[:n_total * B].view(n_total, B))
     else:
         tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, theta, regularised=True, alpha=1.0, dist_group=dist_group,
@@ -458,7 +458,7 @@ def run_ours(args):
         t1.record()
         barrier(world)
         clocks.window(w0, time.time())
-        train_ms = t0.elapsed_time(t1) / args.steps
+        train_ms = max_over_ranks(t0.elapsed_time(t1), world) / args.steps
         train_launches = 8 * args.steps                  # the eight kernels of the captured step, per replay
         sums = sums.clone()
         # per-kernel times: the same step launched kernel by kernel, the library's own events between its launches

@@ -274,6 +274,9 @@ typedef struct {
     int world, rank; unsigned seq;
     void* peer_buffers[PCVAE_DP_MAX_WORLD];
     int* status;                                                  /* device int, zero-initialised by the caller */
+    unsigned long long* step_state;                               /* optional (CUDA-graph replay): seq and the Adam step are
+                                                                     step_state[0] + 1 and the launch advances it, as in
+                                                                     pcvae_reduce_adam_dev; `step` and `seq` are then ignored */
 } pcvae_dp_params;
 int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream);
 
@@ -336,7 +339,10 @@ int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* 
  *   pcvae_prep_batch_dev : rows of batch (step % n_batches) of idx_batches[n_batches][rows], Philox offset
  *                          offset0 + 8 * step                          (pcvae_prep_batch with idx + ..., offset0 + 8 step)
  *   pcvae_reduce_adam_dev: Adam step number step + 1 (bias corrections computed on the device); the last block of the
- *                          launch then advances step_state[0]          (pcvae_reduce_adam with step + 1) */
+ *                          launch then advances step_state[0]          (pcvae_reduce_adam with step + 1).  `sums` holds
+ *                          2 * PCVAE_NSUMS doubles here: the step's sums, then running totals (+= every launch; the
+ *                          caller zeroes them), so that an epoch's loss needs no per-step host work.  The same holds
+ *                          for pcvae_dp_reduce_adam when its step_state is set. */
 int pcvae_prep_batch_dev(const float* table, const uint8_t* mask_table, const long* idx_batches, long n_batches, float* x,
                          uint8_t* mask, uint8_t* mask_p, float* eps, int rows, int obs_dim, int n_eps, float keep_prob,
                          unsigned long long seed, unsigned long long offset0, const unsigned long long* step_state, void* stream);

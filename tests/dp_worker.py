@@ -72,6 +72,37 @@ def main():
     # a second trainer on fresh buffers starts its own sequence (no stale flags)
     th2, _, _ = run("peer")
     assert torch.equal(th2, th_peer)
+    # the same tail inside a CUDA graph of the whole step (device-counted seq / Adam step): replay == eager launches
+    os.environ["PCVAE_DP"] = "peer"
+    T, Bl, nb = 5000, 512, 6
+    gt = torch.Generator(device=dev).manual_seed(11)
+    table = torch.rand(T, D, device=dev, generator=gt)
+    mtable = torch.rand(T, D, device=dev, generator=gt) < 0.7
+    gi = torch.Generator(device=dev).manual_seed(100 + rank)                # every rank gathers its own rows
+    idx = torch.stack([torch.randperm(T, device=dev, generator=gi)[:Bl] for _ in range(nb)])
+    res = []
+    for graph in (True, False):
+        tr = KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, KR.flatten_params(p, L.FAMILY_MLP, dev), table, mtable, Bl, nb,
+                                    keep=0.7, seed=5, dist_group=dist.group.WORLD, world_size=world, global_rows=Bl * world)
+        tr.set_batches(idx)
+        if graph:
+            tr.capture(warmup=2)
+            for _ in range(7):
+                tr.step_graph()
+        else:
+            for _ in range(9):
+                tr.step_eager_dev()
+        torch.cuda.synchronize()
+        tr.xch.check()
+        res.append((tr.theta.clone(), float(tr.total), int(tr.state[0])))
+        tr.xch.close()
+    assert res[0][2] == res[1][2] == 9
+    assert torch.equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+    gathered = [torch.empty_like(res[0][0]) for _ in range(world)]
+    dist.all_gather(gathered, res[0][0])
+    for r in range(world):
+        assert torch.equal(gathered[r], gathered[0]), f"graph replay: rank {r} diverged from rank 0"
+    assert not torch.equal(res[0][0], KR.flatten_params(p, L.FAMILY_MLP, dev))          # it did train
     dist.barrier()
     if rank == 0:
         print(f"dp_worker ok: world {world}, losses {l_peer}")

@@ -31,6 +31,7 @@ struct DpArgs {
     long P32; int nblocks;
     char* peer[DP_MAX_WORLD];
     int* status;
+    unsigned long long* state;      // optional device step counter (CUDA-graph replay): seq = Adam step = state[0] + 1
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -39,9 +40,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-__global__ void __launch_bounds__(256) k_dp_reduce_adam(const DpArgs a) {
+__global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     __shared__ float red[8][32];
+    __shared__ float bc_s[2];
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    if (a.state) {                                        // replayable launch: call number and Adam step from the device
+        const unsigned long long st = *reinterpret_cast<volatile unsigned long long*>(a.state) + 1ull;
+        a.seq = (unsigned)st;
+        if (threadIdx.x == 0) {
+            const double bc1 = 1.0 - pow((double)a.b1, (double)st), bc2 = 1.0 - pow((double)a.b2, (double)st);
+            bc_s[0] = (float)((double)a.lr_bc1 / bc1);
+            bc_s[1] = (float)(1.0 / sqrt(bc2));
+        }
+    }
     const long i = (long)blockIdx.x * 32 + lane;
     const long P = a.P;
     float s = 0.f;
@@ -56,6 +67,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(const DpArgs a) {
     }
     red[part][lane] = s;
     __syncthreads();
+    if (a.state) { a.lr_bc1 = bc_s[0]; a.inv_sqrt_bc2 = bc_s[1]; }
     if (part == 0) {
         float g = red[0][lane];
 #pragma unroll
@@ -96,12 +108,24 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(const DpArgs a) {
             a.theta[i] -= a.lr_bc1 * (mi / (sqrtf(vi) * a.inv_sqrt_bc2 + a.eps));
         }
     }
+    if (a.state) {                                        // the last block advances the step counter (every block has read it)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned* ticket = reinterpret_cast<unsigned*>(a.state + 1);
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+                *ticket = 0u;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long*>(a.state) = *reinterpret_cast<volatile unsigned long long*>(a.state) + 1ull;
+            }
+        }
+    }
     if (a.sp && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + PCVAE_NSUMS) {   // this rank's loss sums
         const int j = threadIdx.x - 32;
         double acc = 0.0;
         for (int c = 0; c < a.grid; ++c) acc += (double)a.sp[c * PCVAE_NSUMS + j];
         if (j == PCVAE_S_RE_Q || j == PCVAE_S_RE_P || j == PCVAE_S_RE_D || j == PCVAE_S_RE_IMP) acc += a.nll_const;
         a.sums[j] = acc;
+        if (a.state) a.sums[PCVAE_NSUMS + j] += acc;      // running totals since the caller last zeroed them
     }
 }
 
@@ -165,9 +189,9 @@ int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
     int grid;
     if (int rc = device_ok(&grid)) return rc;
     if (!p || !p->grad_partials || !p->grad || !p->theta || !p->exp_avg || !p->exp_avg_sq || p->grid < 1 || p->param_count < 1 ||
-        p->step < 1 || !p->status)
+        (p->step < 1 && !p->step_state) || !p->status)
         return fail(PCVAE_EINVAL, "dp_reduce_adam: bad arguments");
-    if (p->world < 1 || p->world > DP_MAX_WORLD || p->rank < 0 || p->rank >= p->world || p->seq == 0)
+    if (p->world < 1 || p->world > DP_MAX_WORLD || p->rank < 0 || p->rank >= p->world || (p->seq == 0 && !p->step_state))
         return fail(PCVAE_EINVAL, "dp_reduce_adam: world %d (1..%d), rank %d, seq %u (>= 1)", p->world, DP_MAX_WORLD, p->rank, p->seq);
     if ((p->sums_partials == nullptr) != (p->sums == nullptr)) return fail(PCVAE_EINVAL, "dp_reduce_adam: sums_partials and sums go together");
     DpArgs a{};
@@ -175,7 +199,10 @@ int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
         if (!p->peer_buffers[r]) return fail(PCVAE_EINVAL, "dp_reduce_adam: peer buffer %d is null", r);
         a.peer[r] = static_cast<char*>(p->peer_buffers[r]);
     }
-    const double bc1 = 1.0 - pow((double)p->beta1, p->step), bc2 = 1.0 - pow((double)p->beta2, p->step);
+    const int host_step = p->step_state ? 1 : p->step;
+    const double bc1 = p->step_state ? 1.0 : 1.0 - pow((double)p->beta1, host_step);       // device: corrections in the kernel
+    const double bc2 = p->step_state ? 1.0 : 1.0 - pow((double)p->beta2, host_step);
+    a.state = p->step_state;
     a.gp = p->grad_partials; a.grid = p->grid; a.P = p->param_count;
     a.grad = p->grad; a.theta = p->theta; a.m = p->exp_avg; a.v = p->exp_avg_sq;
     a.lr_bc1 = (float)(p->lr / bc1); a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.b1 = p->beta1; a.b2 = p->beta2; a.eps = p->eps;

@@ -744,6 +744,7 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const float* __restrict__ g
         for (int c = 0; c < grid; ++c) a += (double)sp[c * PCVAE_NSUMS + j];
         if (j == PCVAE_S_RE_Q || j == PCVAE_S_RE_P || j == PCVAE_S_RE_D || j == PCVAE_S_RE_IMP) a += nll_const;
         sums[j] = a;
+        if (DEV) sums[PCVAE_NSUMS + j] += a;              // running totals since the caller last zeroed them
     }
 }
 

@@ -300,16 +300,19 @@ class Engine:
                     "pcvae_reduce_adam")
         return sums
 
-    def dp_reduce_adam(self, xch, grad, theta, exp_avg, exp_avg_sq, step, rows, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    def dp_reduce_adam(self, xch, grad, theta, exp_avg, exp_avg_sq, step, rows, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8,
+                       step_state=None, sums=None):
         """Data-parallel tail of a step in one launch (pcvae_dp_reduce_adam): reduce, exchange the reduced gradient with
         the other ranks over NVLink peer memory (`xch`: dist.PeerExchange), rank-ordered sum, Adam, this rank's sums."""
-        sums = torch.empty(L.NSUMS, device=self.device, dtype=torch.float64)
+        if sums is None:
+            sums = torch.empty(L.NSUMS, device=self.device, dtype=torch.float64)
         p = L.DpParams()
         p.grad_partials, p.grid, p.param_count = _p(self.grad_partials()), self.grid, self.P
         p.grad, p.theta, p.exp_avg, p.exp_avg_sq = _p(grad), _p(theta), _p(exp_avg), _p(exp_avg_sq)
         p.step, p.lr, p.beta1, p.beta2, p.eps = step, lr, b1, b2, eps
         p.sums_partials, p.rows, p.obs_dim, p.sums = _p(self.sums_partials()), rows, self.D, _p(sums)
         p.world, p.rank, p.seq = xch.world, xch.rank, xch.next_seq()
+        p.step_state = _p(step_state)                     # device counter (graph replay): seq / step come from it
         for r in range(xch.world):
             p.peer_buffers[r] = xch.ptrs[r]
         p.status = _p(xch.status)
@@ -529,8 +532,13 @@ class GraphedFusedTrainer(FusedTrainer):
     writes the lists of an epoch rotated by the step number the epoch starts at (`set_batches`)."""
 
     def __init__(self, family, obs_dim, emb_dim, theta, table, mask_table, batch_rows, n_batches, keep=0.7, seed=0xC0FFEE,
-                 regularised=True, alpha=1.0, beta_w=1.0, lr=1e-3):
-        super().__init__(family, obs_dim, emb_dim, theta, regularised=regularised, alpha=alpha, beta_w=beta_w, lr=lr)
+                 regularised=True, alpha=1.0, beta_w=1.0, lr=1e-3, dist_group=None, world_size=1, global_rows=None):
+        super().__init__(family, obs_dim, emb_dim, theta, regularised=regularised, alpha=alpha, beta_w=beta_w, lr=lr,
+                         dist_group=dist_group, world_size=world_size)
+        if world_size > 1 and self.xch is None:
+            raise L.PcvaeError("GraphedFusedTrainer: data parallelism needs the NVLink peer exchange (an NCCL all-reduce "
+                               "inside the captured step is not supported)")
+        self.global_rows = global_rows
         if mask_table.dtype not in (torch.bool, torch.uint8) or obs_dim % 4 or obs_dim > 128:
             raise L.PcvaeError("GraphedFusedTrainer: needs uint8 / bool masks and obs_dim % 4 == 0, obs_dim <= 128")
         dev = theta.device
@@ -543,8 +551,8 @@ class GraphedFusedTrainer(FusedTrainer):
         self.mask_p = torch.empty_like(self.mask)
         self.n_eps = 2 if regularised else 1
         self.eps = torch.empty(self.n_eps, self.B, LATENT, device=dev)
-        self.total = torch.zeros((), dtype=torch.float64, device=dev)       # sum of the step losses since reset_total()
-        self.sums = None
+        self.sums2 = torch.zeros(2 * L.NSUMS, dtype=torch.float64, device=dev)  # [step sums | totals since reset_total()]
+        self.sums = self.sums2[:L.NSUMS]
         self.graph = None
 
     def set_batches(self, idx_batches: torch.Tensor):
@@ -555,7 +563,12 @@ class GraphedFusedTrainer(FusedTrainer):
         self.idx.copy_(torch.roll(idx_batches.to(self.idx.device), rot, 0))
 
     def reset_total(self):
-        self.total.zero_()
+        self.sums2[L.NSUMS:].zero_()
+
+    @property
+    def total(self):
+        """Sum of the step losses since reset_total() (every step of the sum had B rows: the loss is linear in the sums)."""
+        return loss_from_sums(self.sums2[L.NSUMS:], self.global_rows or self.B, self.alpha, self.beta_w, self.regularised)
 
     def _launch_step(self):
         with torch.cuda.device(self.theta.device):
@@ -563,15 +576,18 @@ class GraphedFusedTrainer(FusedTrainer):
                                                       _p(self.mask), _p(self.mask_p), _p(self.eps), self.B, self.eng.D, self.n_eps,
                                                       self.keep, self.seed, 0, _p(self.state), _stream()), "pcvae_prep_batch_dev")
         self.forward_backward(self.x, self.mask, self.mask_p if self.regularised else None, self.eps[0],
-                              self.eps[1] if self.regularised else None, reduce=False)
+                              self.eps[1] if self.regularised else None, global_rows=self.global_rows, reduce=False)
         e = self.eng
-        sums = torch.empty(L.NSUMS, device=e.device, dtype=torch.float64)
+        sums = self.sums2
+        if self.xch is not None:                          # data parallel: reduce + NVLink exchange + Adam, device-counted
+            e.dp_reduce_adam(self.xch, self.grad, self.theta, self.exp_avg, self.exp_avg_sq, 1, self.B, lr=self.lr,
+                             step_state=self.state, sums=sums)
+            return self.sums
         with torch.cuda.device(e.device):
             L.check(e.lib.pcvae_reduce_adam_dev(_p(e.grad_partials()), e.grid, e.P, _p(self.grad), _p(self.theta), _p(self.exp_avg),
                                                 _p(self.exp_avg_sq), _p(self.state), self.lr, 0.9, 0.999, 1e-8,
                                                 _p(e.sums_partials()), self.B, e.D, _p(sums), _stream()), "pcvae_reduce_adam_dev")
-        self.total += loss_from_sums(sums, self.B, self.alpha, self.beta_w, self.regularised)
-        return sums
+        return self.sums
 
     def capture(self, warmup=3):
         """Warm up on a side stream (`warmup` real steps, they count), then capture one step."""
@@ -581,11 +597,15 @@ class GraphedFusedTrainer(FusedTrainer):
             for _ in range(max(1, warmup)):
                 self._launch_step()
                 self.step_count += 1
+                if self.xch is not None:
+                    self.xch.seq = self.step_count
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.theta.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):
-            self.sums = self._launch_step()               # recorded, not executed: neither counter moves
+            self._launch_step()                           # recorded, not executed: neither counter moves
+        if self.xch is not None:
+            self.xch.seq = self.step_count
         return self
 
     def step_graph(self):
@@ -594,12 +614,16 @@ class GraphedFusedTrainer(FusedTrainer):
             raise L.PcvaeError("GraphedFusedTrainer: capture() first")
         self.graph.replay()
         self.step_count += 1
+        if self.xch is not None:
+            self.xch.seq = self.step_count                # host mirror of the device-counted call number
         return self.sums
 
     def step_eager_dev(self):
         """The same step launched kernel by kernel (cross-check of the replay)."""
         sums = self._launch_step()
         self.step_count += 1
+        if self.xch is not None:
+            self.xch.seq = self.step_count
         return sums
 
     def sync_counter(self):

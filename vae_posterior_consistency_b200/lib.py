@@ -48,7 +48,7 @@ class DpParams(C.Structure):
                 ("step", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("sums_partials", C.c_void_p), ("rows", C.c_int), ("obs_dim", C.c_int), ("sums", C.c_void_p),
                 ("world", C.c_int), ("rank", C.c_int), ("seq", C.c_uint),
-                ("peer_buffers", C.c_void_p * DP_MAX_WORLD), ("status", C.c_void_p)]
+                ("peer_buffers", C.c_void_p * DP_MAX_WORLD), ("status", C.c_void_p), ("step_state", C.c_void_p)]
 
 
 class Model(C.Structure):
