@@ -77,23 +77,25 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
         const long my_slot = ((long)(a.seq & 1u) * a.world + a.rank) * slot_floats + (long)blockIdx.x * 32 + lane;
         // push this block's 32 values into slot [rank] of every rank (one 128-byte store per rank)
         for (int r = 0; r < a.world; ++r) reinterpret_cast<float*>(a.peer[r])[my_slot] = g;
-        __threadfence_system();
-        __syncwarp();
-        if (lane < a.world) {                            // lane r raises the flag on rank r ...
-            volatile unsigned* f = reinterpret_cast<volatile unsigned*>(reinterpret_cast<float*>(a.peer[lane]) + data_floats) +
-                                   (long)a.rank * a.nblocks + blockIdx.x;
-            *f = a.seq;
-            // ... and then waits for rank r's flag in the local buffer
-            volatile unsigned* w = reinterpret_cast<volatile unsigned*>(reinterpret_cast<float*>(a.peer[a.rank]) + data_floats) +
-                                   (long)lane * a.nblocks + blockIdx.x;
+        __syncwarp();                                    // orders the 32 lanes' stores before the releasing lanes below
+        if (lane < a.world) {                            // lane r raises the flag on rank r (release: the warp's pushes first) ...
+            unsigned* f = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(a.peer[lane]) + data_floats) +
+                          (long)a.rank * a.nblocks + blockIdx.x;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.seq) : "memory");
+            // ... and then waits for rank r's flag in the local buffer (acquire), backing off so that the pollers of the
+            // ~1000 resident blocks do not crowd the L2 the reducing blocks and the incoming peer writes need
+            const unsigned* w = reinterpret_cast<const unsigned*>(reinterpret_cast<const float*>(a.peer[a.rank]) + data_floats) +
+                                (long)lane * a.nblocks + blockIdx.x;
             const unsigned long long t0 = globaltimer_ns();
-            unsigned spins = 0;
-            while ((int)(*w - a.seq) < 0) {              // flags only grow (wrap-safe comparison)
-                if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) { atomicExch(a.status, 1); break; }
+            unsigned spins = 0, seen;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
+                if ((int)(seen - a.seq) >= 0) break;     // flags only grow (wrap-safe comparison)
+                __nanosleep(200);
+                if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) { atomicExch(a.status, 1); break; }
             }
         }
         __syncwarp();
-        __threadfence_system();
         // sum the slots in rank order: identical on every rank
         const volatile float* mine = reinterpret_cast<const volatile float*>(a.peer[a.rank]) + (long)(a.seq & 1u) * a.world * slot_floats +
                                      (long)blockIdx.x * 32 + lane;
