@@ -37,9 +37,9 @@ KERNEL_FLOP_BRANCH_ROW = {
     "k_wgrad_tc[enc]": 32_000,     # weight gradients of the three encoder layers
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 65 536 from the ncu --set full captures summarised
-# in profiles/r01_ncu_summary.md (capture 5)
-KERNEL_DRAM_BYTES = {"k_enc_fwd_tc": 143.0e6, "k_dec_fwd_tc": 137.1e6, "k_dec_bwd_tc": 116.0e6, "k_wgrad_tc[dec]": 238.5e6,
-                     "k_enc_bwd_tc": 49.9e6, "k_wgrad_tc[enc]": 239.0e6}
+# in profiles/r01_ncu_summary.md (capture 6)
+KERNEL_DRAM_BYTES = {"k_enc_fwd_tc": 142.1e6, "k_dec_fwd_tc": 136.6e6, "k_dec_bwd_tc": 118.7e6, "k_wgrad_tc[dec]": 235.4e6,
+                     "k_enc_bwd_tc": 49.5e6, "k_wgrad_tc[enc]": 238.9e6}
 FLOP_REWARD_TRIPLE = 24_460       # Reg_VAE incremental form
 MAC_REWARD_MAIN_TRIPLE = 12_000   # 2 tail evaluations x (100x50 + 50x20)
 
