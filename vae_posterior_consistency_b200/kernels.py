@@ -526,7 +526,7 @@ class GraphedFusedTrainer(FusedTrainer):
     replayed (throughput mode, single GPU, uint8 masks, obs_dim % 4 == 0).  The per-step scalars (batch number, Philox
     offset, Adam step) come from a device counter, so a replay is an exact repetition of the launch sequence an eager
     `prep_batch -> step` would issue for that step number (tests/test_gpu_parity.py checks bit-identity).  At the
-    reference's default batch of 64 the step is launch-bound: 210 -> 96 us; at 65 536 rows the launch gaps go: 416 -> 377 us.
+    reference's default batch of 64 the step is launch-bound: 210 -> 96 us; at 65 536 rows the launch gaps go: 386 -> 358 us.
 
     `idx_batches` holds n_batches index lists of `batch_rows` rows; step number s uses list s % n_batches, so the caller
     writes the lists of an epoch rotated by the step number the epoch starts at (`set_batches`)."""
