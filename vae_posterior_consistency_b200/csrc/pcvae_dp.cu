@@ -6,12 +6,14 @@
 // Every rank owns an EXCHANGE BUFFER (cudaMalloc'ed by pcvae_dp_exchange_alloc, opened on the peers through CUDA IPC):
 //     float    data [2][world][P32]     slot [seq & 1][r] holds rank r's reduced gradient of call number seq
 //     unsigned flag [world][nblocks]    flag [r][b] = seq once block b of rank r has delivered its 32 parameters
-// Block b owns 32 consecutive parameters on every rank.  After its local reduce it PUSHES the 32 values into slot
-// [rank] of every rank's buffer (peer stores over NVLink), fences (system scope) and raises flag [rank][b] on every
-// rank; it then polls only its OWN copy of the flags (local memory) until all ranks have delivered block b, sums the
-// slots in rank order -- the same order on every rank, so all ranks compute bit-identical gradients and weights -- and
-// applies Adam.  No block ever waits for another block of its own grid, so the launch cannot deadlock on residency; a
-// rank that never arrives is detected by a bounded wait (status word, no hang).  The two data slots alternate by call
+// Block b owns the chunks of 32 consecutive parameters b, b + gridDim, ... on every rank (same grid on all ranks).  After
+// its local reduce of a chunk it PUSHES the 32 values into slot [rank] of every rank's buffer (peer stores over NVLink);
+// after its last chunk it raises flag [rank][b] on every rank with release semantics; it then polls only its OWN copy
+// of the flags (local memory, acquire) until all ranks have delivered block b, sums the slots in rank order -- the same
+// order on every rank, so all ranks compute bit-identical gradients and weights -- and applies Adam.  The grid is sized
+// so that all blocks are resident at once (no second wave queues behind blocks that wait for other ranks) and no block
+// waits for another block of its own grid, so the launch cannot deadlock on residency; a rank that never arrives is
+// detected by a bounded wait (status word, no hang).  The two data slots alternate by call
 // number: a rank can overwrite slot s only in call seq + 2, which it reaches only after every rank has delivered call
 // seq + 1, i.e. after every rank has finished reading call seq.
 #include <cstring>
@@ -53,37 +55,44 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
             bc_s[1] = (float)(1.0 / sqrt(bc2));
         }
     }
-    const long i = (long)blockIdx.x * 32 + lane;
     const long P = a.P;
-    float s = 0.f;
-    if (i < P) {                                         // same summation order as k_reduce_adam
-        int c = part;
-        for (; c + 24 < a.grid; c += 32) {
-            const float v0 = a.gp[(long)c * P + i], v1 = a.gp[(long)(c + 8) * P + i], v2 = a.gp[(long)(c + 16) * P + i],
-                        v3 = a.gp[(long)(c + 24) * P + i];
-            s += v0; s += v1; s += v2; s += v3;
+    const long slot_floats = a.P32;
+    const long data_floats = 2 * (long)a.world * slot_floats;
+    const long slot0 = (long)(a.seq & 1u) * a.world * slot_floats;
+    // ---- phase 1: this block's chunks of 32 parameters (chunk c = blockIdx.x, + gridDim.x, ...): reduce the rank's
+    //      partials in the order of k_reduce_adam and push the 32 values into slot [rank] of every rank ----
+    for (int c = blockIdx.x; c < a.nblocks; c += gridDim.x) {
+        const long i = (long)c * 32 + lane;
+        float s = 0.f;
+        if (i < P) {
+            int q = part;
+            for (; q + 24 < a.grid; q += 32) {
+                const float v0 = a.gp[(long)q * P + i], v1 = a.gp[(long)(q + 8) * P + i], v2 = a.gp[(long)(q + 16) * P + i],
+                            v3 = a.gp[(long)(q + 24) * P + i];
+                s += v0; s += v1; s += v2; s += v3;
+            }
+            for (; q < a.grid; q += 8) s += a.gp[(long)q * P + i];
         }
-        for (; c < a.grid; c += 8) s += a.gp[(long)c * P + i];
-    }
-    red[part][lane] = s;
-    __syncthreads();
-    if (a.state) { a.lr_bc1 = bc_s[0]; a.inv_sqrt_bc2 = bc_s[1]; }
-    if (part == 0) {
-        float g = red[0][lane];
+        red[part][lane] = s;
+        __syncthreads();
+        if (part == 0) {
+            float g = red[0][lane];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) g += red[q][lane];
-        const long slot_floats = a.P32;
-        const long data_floats = 2 * (long)a.world * slot_floats;
-        const long my_slot = ((long)(a.seq & 1u) * a.world + a.rank) * slot_floats + (long)blockIdx.x * 32 + lane;
-        // push this block's 32 values into slot [rank] of every rank (one 128-byte store per rank)
-        for (int r = 0; r < a.world; ++r) reinterpret_cast<float*>(a.peer[r])[my_slot] = g;
-        __syncwarp();                                    // orders the 32 lanes' stores before the releasing lanes below
-        if (lane < a.world) {                            // lane r raises the flag on rank r (release: the warp's pushes first) ...
+            for (int q = 1; q < 8; ++q) g += red[q][lane];
+            const long my = slot0 + (long)a.rank * slot_floats + (long)c * 32 + lane;
+            for (int r = 0; r < a.world; ++r) reinterpret_cast<float*>(a.peer[r])[my] = g;      // one 128-byte store per rank
+        }
+        __syncthreads();
+    }
+    // ---- phase 2: ONE flag per (rank, block): lane r of warp 0 raises it on rank r with release semantics (the warp's
+    //      pushes of all chunks come first), then waits (acquire) for rank r's flag in the local buffer.  All blocks of
+    //      the grid are resident at once (the launcher sizes the grid for that), so no block waits for a second wave ----
+    if (part == 0) {
+        __syncwarp();
+        if (lane < a.world) {
             unsigned* f = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(a.peer[lane]) + data_floats) +
                           (long)a.rank * a.nblocks + blockIdx.x;
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.seq) : "memory");
-            // ... and then waits for rank r's flag in the local buffer (acquire), backing off so that the pollers of the
-            // ~1000 resident blocks do not crowd the L2 the reducing blocks and the incoming peer writes need
             const unsigned* w = reinterpret_cast<const unsigned*>(reinterpret_cast<const float*>(a.peer[a.rank]) + data_floats) +
                                 (long)lane * a.nblocks + blockIdx.x;
             const unsigned long long t0 = globaltimer_ns();
@@ -91,23 +100,32 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
             for (;;) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
                 if ((int)(seen - a.seq) >= 0) break;     // flags only grow (wrap-safe comparison)
-                __nanosleep(200);
+                __nanosleep(100);
                 if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) { atomicExch(a.status, 1); break; }
             }
         }
         __syncwarp();
-        // sum the slots in rank order: identical on every rank
-        const volatile float* mine = reinterpret_cast<const volatile float*>(a.peer[a.rank]) + (long)(a.seq & 1u) * a.world * slot_floats +
-                                     (long)blockIdx.x * 32 + lane;
-        float tot = 0.f;
-        for (int r = 0; r < a.world; ++r) tot += mine[(long)r * slot_floats];
-        if (i < P) {
-            a.grad[i] = tot;
-            const float mi = a.m[i] + (tot - a.m[i]) * (1.f - a.b1);
-            const float vi = fmaf(a.b2, a.v[i], (1.f - a.b2) * tot * tot);
-            a.m[i] = mi;
-            a.v[i] = vi;
-            a.theta[i] -= a.lr_bc1 * (mi / (sqrtf(vi) * a.inv_sqrt_bc2 + a.eps));
+    }
+    __syncthreads();
+    if (a.state) { a.lr_bc1 = bc_s[0]; a.inv_sqrt_bc2 = bc_s[1]; }
+    // ---- phase 3: sum the slots in rank order (identical on every rank) and apply Adam; the block's chunks are dealt
+    //      over its eight warps ----
+    {
+        int j = 0;
+        for (int c = blockIdx.x; c < a.nblocks; c += gridDim.x, ++j) {
+            if ((j & 7) != part) continue;
+            const long i = (long)c * 32 + lane;
+            const volatile float* mine = reinterpret_cast<const volatile float*>(a.peer[a.rank]) + slot0 + (long)c * 32 + lane;
+            float tot = 0.f;
+            for (int r = 0; r < a.world; ++r) tot += mine[(long)r * slot_floats];
+            if (i < P) {
+                a.grad[i] = tot;
+                const float mi = a.m[i] + (tot - a.m[i]) * (1.f - a.b1);
+                const float vi = fmaf(a.b2, a.v[i], (1.f - a.b2) * tot * tot);
+                a.m[i] = mi;
+                a.v[i] = vi;
+                a.theta[i] -= a.lr_bc1 * (mi / (sqrtf(vi) * a.inv_sqrt_bc2 + a.eps));
+            }
         }
     }
     if (a.state) {                                        // the last block advances the step counter (every block has read it)
@@ -213,7 +231,10 @@ int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
     a.world = p->world; a.rank = p->rank; a.seq = p->seq;
     a.P32 = dp_p32(p->param_count); a.nblocks = (int)(a.P32 / 32);
     a.status = p->status;
-    k_dp_reduce_adam<<<a.nblocks, 256, 0, (cudaStream_t)stream>>>(a);
+    // every block must be resident at once (a block waits for the other ranks before it ends): at most two per SM.  All
+    // ranks must launch the same grid, i.e. be the same GPU model.
+    const int blocks = a.nblocks < 2 * grid ? a.nblocks : 2 * grid;
+    k_dp_reduce_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dp_reduce_adam: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
