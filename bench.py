@@ -386,10 +386,13 @@ def run_ours(args):
     if graphed:
         # the whole step (gather + sub-mask + noise, six training kernels, reduce [+ NVLink gradient exchange] + Adam) is
         # replayed from a CUDA graph; the per-step scalars live in a device counter (KR.GraphedFusedTrainer)
-        tr = KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, theta, table, mtable, B, n_total, keep=0.7, seed=99, regularised=True,
-                                    alpha=1.0, dist_group=dist_group, world_size=world, global_rows=B * world)
-        tr.set_batches(perm[:n_total * B].view(n_total, B))
-    else:
+        try:
+            tr = KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, theta, table, mtable, B, n_total, keep=0.7, seed=99, regularised=True,
+                                        alpha=1.0, dist_group=dist_group, world_size=world, global_rows=B * world)
+            tr.set_batches(perm[:n_total * B].view(n_total, B))
+        except L.PcvaeError:                             # no peer access between the GPUs (every rank agrees, see
+            graphed = False                              # PeerExchange.create_or_none): eager launches + NCCL all-reduce
+    if not graphed:
         tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, theta, regularised=True, alpha=1.0, dist_group=dist_group,
                              world_size=world)
     eng = tr.eng

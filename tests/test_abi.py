@@ -105,3 +105,30 @@ def test_sass_every_mma_descriptor_register_is_written_before_its_first_use():
                             bad.append((fn, i, f"UR{r}", first_write.get(r)))
     assert n_mma > 100, "no tcgen05 MMAs found in the library: the check did not look at anything"
     assert not bad, bad[:5]
+
+
+def test_host_side_packing_of_the_streamed_batch_format():
+    """kernels.pack_mask_bits / compact_rows (the host side of pcvae_prep_packed): bit j of word w is mask[row][32 w + j];
+    vals are the observed entries in row-major order, row_off their exclusive prefix sums."""
+    import numpy as np
+    import torch
+    from vae_posterior_consistency_b200 import kernels as KR
+    g = torch.Generator().manual_seed(0)
+    for rows, D in ((1, 4), (7, 100), (33, 128), (5, 36)):
+        x = torch.rand(rows, D, generator=g)
+        m = torch.rand(rows, D, generator=g) < 0.6
+        if rows > 2:
+            m[0] = False
+            m[1] = True
+        bits = KR.pack_mask_bits(m)
+        assert bits.dtype == torch.int32 and bits.shape == (rows, (D + 31) // 32)
+        u = bits.numpy().view(np.uint32)
+        back = np.array([[(u[r, d // 32] >> (d % 32)) & 1 for d in range(D)] for r in range(rows)], dtype=bool)
+        assert (back == m.numpy()).all()
+        assert all(int(u[r, -1]) >> (D - 32 * (u.shape[1] - 1)) == 0 for r in range(rows)) or D % 32 == 0   # padding bits are zero
+        vals, row_off, bits2 = KR.compact_rows(x, m)
+        assert torch.equal(bits2, bits) and vals.numel() == int(m.sum())
+        cnt = m.sum(1)
+        assert torch.equal(row_off.long(), torch.cumsum(cnt, 0) - cnt)
+        for r in range(rows):
+            assert torch.equal(vals[row_off[r]:row_off[r] + cnt[r]], x[r][m[r]])

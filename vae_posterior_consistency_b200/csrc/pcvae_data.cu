@@ -87,21 +87,40 @@ __global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ ta
         idx += (long)(st % (unsigned long long)n_batches) * B;
         offset += st * 8ull;
     }
-    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
-        const long src = idx[b];
+    const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // gather: two rows of the warp in flight per trip (index -> row is a dependent pair of HBM round trips)
+    for (int b0 = w0; b0 < B; b0 += 2 * warps) {
+        const int b1 = b0 + warps;
+        const bool two = b1 < B;
+        const long s0 = idx[b0], s1 = two ? idx[b1] : 0;
         if (lane < D4) {
-            const float4 v = reinterpret_cast<const float4*>(table + src * D)[lane];
-            const uint32_t m = reinterpret_cast<const uint32_t*>(mtable + src * D)[lane];
-            reinterpret_cast<float4*>(x + (long)b * D)[lane] = v;
-            reinterpret_cast<uint32_t*>(mask + (long)b * D)[lane] = m;
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)lane, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
-            const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
-            uint32_t mp = 0;
+            const float4 v0 = reinterpret_cast<const float4*>(table + s0 * D)[lane];
+            const uint32_t m0 = reinterpret_cast<const uint32_t*>(mtable + s0 * D)[lane];
+            float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t m1 = 0;
+            if (two) {
+                v1 = reinterpret_cast<const float4*>(table + s1 * D)[lane];
+                m1 = reinterpret_cast<const uint32_t*>(mtable + s1 * D)[lane];
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (((m >> (8 * j)) & 0xFFu) && u01(rv[j]) < keep) mp |= 1u << (8 * j);       // rand() in [0,1) < keep
-            reinterpret_cast<uint32_t*>(mask_p + (long)b * D)[lane] = mp;
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
+                const int b = h ? b1 : b0;
+                const float4 v = h ? v1 : v0;
+                const uint32_t m = h ? m1 : m0;
+                reinterpret_cast<float4*>(x + (long)b * D)[lane] = v;
+                reinterpret_cast<uint32_t*>(mask + (long)b * D)[lane] = m;
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)lane, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+                const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+                uint32_t mp = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((m >> (8 * j)) & 0xFFu) && u01(rv[j]) < keep) mp |= 1u << (8 * j);       // rand() in [0,1) < keep
+                reinterpret_cast<uint32_t*>(mask_p + (long)b * D)[lane] = mp;
+            }
         }
+    }
+    for (int b = w0; b < B; b += warps) {
         if (lane < (10 * n_eps + 3) / 4) {               // n_eps * 10 normals per row, four per lane
             const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(64 + lane), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
             float gv[4];
