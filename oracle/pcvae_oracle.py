@@ -488,3 +488,115 @@ def init_mnar_params(obs_dim: int, latent: int = LATENT, seed: int = 0, with_log
         w, b = linear(obs_dim, obs_dim)
         p["logits.0.weight"], p["logits.0.bias"] = w.double(), b.double()
     return p
+
+
+# --------------------------------------------------------------------------
+# MIWAE (Student-t decoder + importance-weighted bound): MIWAE / Reg_MIWAE, src/models/VAE.py:3011-3301
+# (SURVEY.md section 8f item 4).  Restated here so that the family's oracle is pinned to the reference before its
+# kernels exist; the product package does not build this family yet.
+# --------------------------------------------------------------------------
+
+HALF_LOG_PI = 0.5 * math.log(math.pi)
+
+
+def miwae_encoder_stats(p: Params, x: Tensor, mask: Tensor) -> Tuple[Tensor, Tensor]:
+    """mean [B, L], scale = softplus(raw) [B, L]  (VAE.py:3047-3049, 3178-3180); nets :3026-3032."""
+    h = torch.relu(_lin(x * _as(mask, x), p["seq_encoder.0.weight"], p["seq_encoder.0.bias"]))
+    h = torch.relu(_lin(h, p["seq_encoder.2.weight"], p["seq_encoder.2.bias"]))
+    o = _lin(h, p["seq_encoder.4.weight"], p["seq_encoder.4.bias"])
+    L = o.shape[1] // 2
+    return o[:, :L], torch.nn.functional.softplus(o[:, L:])
+
+
+def miwae_decoder(p: Params, z: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """z [B, S, L] -> (mean = sigmoid, scale = softplus + 0.001, df = softplus + 3), each [B, S, D]  (VAE.py:3061-3066)."""
+    h = torch.relu(_lin(z, p["seq_decoder.0.weight"], p["seq_decoder.0.bias"]))
+    h = torch.relu(_lin(h, p["seq_decoder.2.weight"], p["seq_decoder.2.bias"]))
+    o = _lin(h, p["seq_decoder.4.weight"], p["seq_decoder.4.bias"])
+    D = o.shape[-1] // 3
+    sp = torch.nn.functional.softplus
+    return torch.sigmoid(o[..., :D]), sp(o[..., D:2 * D]) + 0.001, sp(o[..., 2 * D:]) + 3.0
+
+
+def student_t_log_prob(x: Tensor, loc: Tensor, scale: Tensor, df: Tensor) -> Tensor:
+    """torch.distributions.StudentT(df, loc, scale).log_prob(x)."""
+    y = (x - loc) / scale
+    Z = torch.log(scale) + 0.5 * torch.log(df) + HALF_LOG_PI + torch.lgamma(0.5 * df) - torch.lgamma(0.5 * (df + 1.0))
+    return -0.5 * (df + 1.0) * torch.log1p(y * y / df) - Z
+
+
+def _miwae_bound_terms(x, m, xm, xs, df, mean, scale, eps2):
+    """Per-branch pieces of the bound as the reference writes them.  NOTE the reference's indexing quirk
+    (VAE.py:3080-3081): the [B*S] vector of per-(row, sample) log-likelihoods, laid out row-major in (b, s), is
+    reshaped to [S, B] WITHOUT a transpose, so entry (i, j) of the "[samples, rows]" matrix is the likelihood of
+    (row, sample) = divmod(i * B + j, S); log p(z) - log q(z|x) IS transposed properly.  Kept for parity."""
+    B, S, D = xm.shape
+    logp = student_t_log_prob(x.unsqueeze(1), xm, xs, df)                   # [B, S, D]
+    mf = _as(m, x).unsqueeze(1)
+    lpx = (logp * mf).sum(2).reshape(S, B)                                  # the mis-indexed view
+    z = mean.unsqueeze(1) + scale.unsqueeze(1) * eps2                       # fresh draw inside loss(), VAE.py:3086-3088
+    logpz = (-0.5 * z * z - HALF_LOG_2PI).sum(2).t()                        # [S, B]
+    sc = scale.unsqueeze(1)
+    logq = (-((z - mean.unsqueeze(1)) ** 2) / (2 * sc * sc) - torch.log(sc) - HALF_LOG_2PI).sum(2).t()
+    lw = lpx + logpz - logq
+    return logp, lw
+
+
+def miwae_loss(x, mask, xm, xs, df, mean, scale, eps2):
+    """MIWAE.loss (VAE.py:3068-3110): returns (neg_bound, xm_imputed [B, D], imputed-likelihood scalar of llh_eval)."""
+    B, S, D = xm.shape
+    logp, lw = _miwae_bound_terms(x, mask, xm, xs, df, mean, scale, eps2)
+    neg_bound = -torch.mean(torch.logsumexp(lw, 0))
+    w = torch.softmax(lw, 0)                                                # [S, B]
+    xm_imp = torch.einsum('ki,kij->ij', w, xm.permute(1, 0, 2))
+    imp = (logp * (1.0 - _as(mask, x)).unsqueeze(1)).sum() / (B * 5000)
+    return neg_bound, xm_imp, imp
+
+
+def reg_miwae_loss(x, mask, mask_p, q, pbr, eps2_q, eps2_p, alpha=1.0):
+    """Reg_MIWAE.loss (VAE.py:3197-3263).  q / pbr = (xm, xs, df, mean, scale) of the two branches."""
+    xm_q, xs_q, df_q, mean_q, scale_q = q
+    xm_p, xs_p, df_p, mean_p, scale_p = pbr
+    B, S, D = xm_q.shape
+    logp_q, lw_q = _miwae_bound_terms(x, mask, xm_q, xs_q, df_q, mean_q, scale_q, eps2_q)
+    nb_q = -torch.mean(torch.logsumexp(lw_q, 0))
+    _, lw_p = _miwae_bound_terms(x, mask_p, xm_p, xs_p, df_p, mean_p, scale_p, eps2_p)
+    nb_p = -torch.mean(torch.logsumexp(lw_p, 0))
+    only_q = (_as(mask, x) * (1.0 - _as(mask_p, x))).unsqueeze(1)
+    reg_like = (logp_q * only_q).sum(2).mean()                              # mean over all (row, sample) pairs
+    # KL(N(mean_q, scale_q) || N(mean_p, scale_p)) per latent, mean over [B, S, L] == mean over [B, L]
+    var_ratio = (scale_q / scale_p) ** 2
+    t1 = ((mean_q - mean_p) / scale_p) ** 2
+    kl_reg = (0.5 * (var_ratio + t1 - 1.0 - torch.log(var_ratio))).mean()
+    loss = nb_q + alpha * (kl_reg - nb_q + nb_p - reg_like)
+    w = torch.softmax(lw_q, 0)
+    xm_imp = torch.einsum('ki,kij->ij', w, xm_q.permute(1, 0, 2))
+    return loss, xm_imp
+
+
+def miwae_trainable_names(p: Params) -> Sequence[str]:
+    return [k for k in p if k.startswith("seq_encoder") or k.startswith("seq_decoder")]
+
+
+def miwae_train_step(p: Params, x, mask, mask_p, draws, alpha=1.0, regularised=True):
+    """forward + loss + backward.  `draws` in the reference's order (SURVEY.md A.6 style): regularised
+    [eps_q, eps_p, eps2_q, eps2_p], vanilla [eps, eps2]; each [B, S, L]."""
+    names = miwae_trainable_names(p)
+    w = {k: (v.detach().clone().requires_grad_(True) if k in names else v) for k, v in p.items()}
+    mean_q, scale_q = miwae_encoder_stats(w, x, mask)
+    z_q = mean_q.unsqueeze(1) + scale_q.unsqueeze(1) * draws[0]
+    xm_q, xs_q, df_q = miwae_decoder(w, z_q)
+    if regularised:
+        mean_p, scale_p = miwae_encoder_stats(w, x, mask_p)
+        z_p = mean_p.unsqueeze(1) + scale_p.unsqueeze(1) * draws[1]
+        xm_p, xs_p, df_p = miwae_decoder(w, z_p)
+        loss, xm_imp = reg_miwae_loss(x, mask, mask_p, (xm_q, xs_q, df_q, mean_q, scale_q),
+                                      (xm_p, xs_p, df_p, mean_p, scale_p), draws[2], draws[3], alpha)
+        imp = None
+    else:
+        loss, xm_imp, imp = miwae_loss(x, mask, xm_q, xs_q, df_q, mean_q, scale_q, draws[1])
+    grads = torch.autograd.grad(loss, [w[k] for k in names], allow_unused=True)
+    gd = {k: (g if g is not None else torch.zeros_like(w[k])) for k, g in zip(names, grads)}
+    return loss.detach(), gd, dict(xm_q=xm_q.detach(), xs_q=xs_q.detach(), df_q=df_q.detach(), mean_q=mean_q.detach(),
+                                   scale_q=scale_q.detach(), xm_imp=xm_imp.detach(),
+                                   imp=None if imp is None else imp.detach())

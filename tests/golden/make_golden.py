@@ -206,6 +206,43 @@ def mnar_case(V, cls_name, B, D, S, seed, alpha):
                 xlv_q=xlv_q.detach(), loss=loss.detach(), grads=grads, xm_imp=xm_imp, re=re)
 
 
+def miwae_case(V, cls_name, B, D, S, seed, alpha):
+    """MIWAE / Reg_MIWAE (VAE.py:3011-3301): forward, loss, backward and the llh_eval imputation with recorded noise."""
+    torch.manual_seed(seed)
+    cls = getattr(V, cls_name)
+    model = cls(D, 500, 20, 10, {"batch_size": B, "patience": 100}, S, 10)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(B, D, generator=g)
+    mask = torch.rand(B, D, generator=g) < 0.7                       # bool: the losses use ~mask
+    mask_p = mask & (torch.rand(B, D, generator=g) < 0.6)
+    reg = cls_name == "Reg_MIWAE"
+    with NoiseTape() as tape:
+        if reg:
+            mean_p, scale_p, xm_p, xs_p, df_p, mean_q, scale_q, xm_q, xs_q, df_q = model.forward(x, mask, mask_p)
+            _, loss = model.loss(x, xm_p, xs_p, df_p, mean_p, scale_p, xm_q, xs_q, df_q, mean_q, scale_q, mask, mask_p, 1,
+                                 beta_annealing=False, beta=1.0, alpha=alpha)
+        else:
+            mean_q, scale_q, xm_q, xs_q, df_q = model.forward(x, mask)
+            _, loss = model.loss(x, xm_q, xs_q, df_q, mean_q, scale_q, mask, 1)
+    draws = [d.clone() for d in tape.draws]
+    model.zero_grad()
+    loss.backward()
+    grads = {k: prm.grad.detach().clone() for k, prm in model.named_parameters() if prm.grad is not None}
+    # llh_eval redraws the loss-internal noise: record it and the imputation it produces
+    with torch.no_grad():
+        with NoiseTape() as tape2:
+            if reg:
+                xm_imp, ev_loss, _ = model.loss(x, xm_p, xs_p, df_p, mean_p, scale_p, xm_q, xs_q, df_q, mean_q, scale_q, mask,
+                                                mask_p, 1, llh_eval=True, alpha=alpha)
+                imp = None
+            else:
+                xm_imp, ev_loss, imp = model.loss(x, xm_q, xs_q, df_q, mean_q, scale_q, mask, 1, llh_eval=True)
+    return dict(cls=cls_name, D=D, S=S, alpha=alpha, state_dict=sd_clone(model), x=x, mask=mask, mask_p=mask_p, draws=draws,
+                eval_draws=[d.clone() for d in tape2.draws], mean_q=mean_q.detach(), scale_q=scale_q.detach(),
+                xm_q=xm_q.detach(), xs_q=xs_q.detach(), df_q=df_q.detach(), loss=loss.detach(), grads=grads,
+                xm_imp=xm_imp, eval_loss=ev_loss, imp=imp)
+
+
 def driver_cases(V, E, cases=None, with_al=True):
     """Run the reference's own train() / eval_vae() / active_learning_func() (the call sequence of
     imputation.py:28-59 and active_learning.py:58-74) on a tiny synthetic Data/ tree with fixed seeds
@@ -339,6 +376,11 @@ def main():
     fx["reg_vae_mask_b37_d20_a05"] = reg_case(V, "Reg_VAE_mask", 37, 20, 20, 31, 0.5)
     fx["vanilla_vae_mask_b64_d13"] = vanilla_case(V, "vanilla_VAE_mask", 64, 13, 20, 32)
     fx["traj_reg_vae_mask_b32_d13"] = train_traj_case(V, "Reg_VAE_mask", 32, 13, 20, 33, 4)
+    # MIWAE family (Student-t decoder, importance-weighted bound), VAE.py:3011-3301: oracle pinned ahead of its kernels
+    fx["miwae_b12_d6_s4"] = miwae_case(V, "MIWAE", 12, 6, 4, 40, 1.0)
+    fx["miwae_b7_d9_s5"] = miwae_case(V, "MIWAE", 7, 9, 5, 41, 1.0)
+    fx["reg_miwae_b12_d6_s4"] = miwae_case(V, "Reg_MIWAE", 12, 6, 4, 42, 1.0)
+    fx["reg_miwae_b7_d9_s5_a06"] = miwae_case(V, "Reg_MIWAE", 7, 9, 5, 43, 0.6)
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     if "--skip-drivers" not in sys.argv:
         from synth import MASK_DRIVER_CASES

@@ -124,3 +124,53 @@ def test_mnar_families(golden, name):
         # llh_eval draws a fresh z' for the MC KL: recompute with the recorded third draw
         _, xm_imp, re = O.mnar_vanilla_loss(p, g["x"], g["mask"], aux["mu_q"], aux["lv_q"], aux["xm_q"], aux["xlv_q"], d[2])
         close(xm_imp, g["xm_imp"]); close(re, g["re"])
+
+
+MIWAE = ["miwae_b12_d6_s4", "miwae_b7_d9_s5", "reg_miwae_b12_d6_s4", "reg_miwae_b7_d9_s5_a06"]
+
+
+@pytest.mark.parametrize("name", MIWAE)
+def test_miwae_families(golden, name):
+    """MIWAE / Reg_MIWAE (Student-t decoder, importance-weighted bound; reference VAE.py:3011-3301):
+    the oracle's restatement -- including the reference's un-transposed [B*S] -> [S, B] reshape of the likelihoods --
+    against a recorded run of the reference: forward, loss, every parameter gradient, llh_eval imputation.  The
+    product package does not build this family yet; the oracle is pinned ahead of the kernels."""
+    g = golden(name)
+    p = g["state_dict"]
+    reg = g["cls"] == "Reg_MIWAE"
+    loss, grads, aux = O.miwae_train_step(p, g["x"], g["mask"], g["mask_p"] if reg else None, g["draws"], alpha=g["alpha"],
+                                          regularised=reg)
+    S = g["S"]
+    close(aux["mean_q"].unsqueeze(1).expand(-1, S, -1), g["mean_q"])
+    close(aux["scale_q"].unsqueeze(1).expand(-1, S, -1), g["scale_q"])
+    close(aux["xm_q"], g["xm_q"]); close(aux["xs_q"], g["xs_q"]); close(aux["df_q"], g["df_q"])
+    close(loss, g["loss"])
+    assert set(grads) == set(g["grads"])
+    for k, ref in g["grads"].items():
+        torch.testing.assert_close(grads[k], ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max() + 1e-3))
+    # llh_eval: the loss redraws its internal noise; replay the recorded eval draws
+    mean_q, scale_q = O.miwae_encoder_stats(p, g["x"], g["mask"])
+    xm_q, xs_q, df_q = g["xm_q"], g["xs_q"], g["df_q"]
+    if reg:
+        mean_p, scale_p = O.miwae_encoder_stats(p, g["x"], g["mask_p"])
+        z_p = mean_p.unsqueeze(1) + scale_p.unsqueeze(1) * g["draws"][1]
+        xm_p, xs_p, df_p = O.miwae_decoder(p, z_p)
+        ev, xm_imp = O.reg_miwae_loss(g["x"], g["mask"], g["mask_p"], (xm_q, xs_q, df_q, mean_q, scale_q),
+                                      (xm_p, xs_p, df_p, mean_p, scale_p), g["eval_draws"][0], g["eval_draws"][1], g["alpha"])
+    else:
+        ev, xm_imp, imp = O.miwae_loss(g["x"], g["mask"], xm_q, xs_q, df_q, mean_q, scale_q, g["eval_draws"][0])
+        close(imp, g["imp"])
+    close(ev, g["eval_loss"]); close(xm_imp, g["xm_imp"])
+
+
+def test_miwae_reshape_quirk_matters():
+    """The un-transposed reshape is not a no-op: with it 'fixed' the loss of the recorded case changes."""
+    g = torch.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "miwae_b12_d6_s4.pt"))
+    p = g["state_dict"]
+    mean, scale = O.miwae_encoder_stats(p, g["x"], g["mask"])
+    z = mean.unsqueeze(1) + scale.unsqueeze(1) * g["draws"][0]
+    xm, xs, df = O.miwae_decoder(p, z)
+    logp = O.student_t_log_prob(g["x"].unsqueeze(1), xm, xs, df)
+    lpx_ref = (logp * g["mask"].float().unsqueeze(1)).sum(2).reshape(g["S"], -1)
+    lpx_fixed = (logp * g["mask"].float().unsqueeze(1)).sum(2).t()
+    assert not torch.allclose(lpx_ref, lpx_fixed)
