@@ -22,9 +22,9 @@
 // images in the canonical K-major no-swizzle core-matrix layout [k/4][n][4].  Between the kernels the
 // activations travel through HBM feature-major ([feature][row]: a warp's 32 rows make one 128-byte store), which
 // is exactly the K-major operand layout of the weight-gradient GEMM (its reduction runs over rows); that
-// kernel streams 32-row slabs with cp.async through a 3-stage ring and keeps its accumulator in TMEM for the
-// whole launch.  Its per-CTA partials land in the [grid][param_count] layout k_dec uses, so
-// pcvae_reduce_grads is unchanged.
+// kernel streams 32-row slabs with bulk async copies through a 4-stage ring (pcvae_wgrad_tc.cu) and keeps its
+// accumulator in TMEM for a whole layer.  Its per-CTA partials land in the [grid][param_count] layout k_dec
+// uses, so pcvae_reduce_grads is unchanged.
 //
 // TMEM columns (all 512), both row-tile kernels:  RA [0,224): 112 hi + 112 lo    RB [224,336): 56 hi + 56 lo
 //                                                 ACC1 [336,448)                 ACC2 [448,512)

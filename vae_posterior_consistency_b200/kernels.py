@@ -465,8 +465,9 @@ def loss_from_sums(sums: torch.Tensor, rows: int, alpha: float, beta_w: float, r
 class FusedTrainer:
     """The fused training step of train.py:87-116 on flat device vectors:
     encoder fwd (both branches) -> decoder + loss + decoder bwd -> encoder bwd ->
-    deterministic partial reduce -> Adam.  Optionally a data-parallel gradient all-reduce
-    (torch.distributed, NCCL) between reduce and Adam."""
+    deterministic partial reduce -> Adam.  Data parallel (dist_group, world_size > 1): the tail is one
+    launch, reduce + gradient exchange over NVLink peer memory + Adam (pcvae_dp_reduce_adam, dist.PeerExchange);
+    with PCVAE_DP=nccl, or when peer access cannot be set up, reduce -> NCCL all-reduce -> Adam."""
 
     def __init__(self, family, obs_dim, emb_dim, theta, regularised=True, alpha=1.0, beta_w=1.0, lr=1e-3,
                  dist_group=None, world_size=1):
