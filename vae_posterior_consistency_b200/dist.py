@@ -53,13 +53,23 @@ class PeerExchange:
         self.P = param_count
         self.seq = 0
         self.own = C.c_void_p()
-        handle = C.create_string_buffer(64)
-        with torch.cuda.device(self.device):
-            L.check(self.lib.pcvae_dp_exchange_alloc(param_count, self.world, C.byref(self.own), handle), "pcvae_dp_exchange_alloc")
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.ptrs = [None] * self.world
         self.opened = []
+        handle = C.create_string_buffer(64)
+        mine = None
+        try:
+            with torch.cuda.device(self.device):
+                L.check(self.lib.pcvae_dp_exchange_alloc(param_count, self.world, C.byref(self.own), handle),
+                        "pcvae_dp_exchange_alloc")
+            mine = bytes(handle.raw)
+        except L.PcvaeError:               # still take part in the collective below: every rank must see the failure
+            pass
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        if any(h is None for h in handles):
+            self.close()
+            raise L.PcvaeError("PeerExchange: exchange buffer could not be allocated on rank(s) "
+                               f"{[r for r, h in enumerate(handles) if h is None]}")
+        self.ptrs = [None] * self.world
         with torch.cuda.device(self.device):
             for r, h in enumerate(handles):
                 if r == self.rank:
@@ -109,6 +119,6 @@ class PeerExchange:
         for q in self.opened:
             self.lib.pcvae_dp_exchange_close(q)
         self.opened = []
-        if self.own:
+        if self.own is not None and self.own.value:
             self.lib.pcvae_dp_exchange_free(self.own)
-            self.own = None
+        self.own = None
