@@ -132,3 +132,57 @@ def test_host_side_packing_of_the_streamed_batch_format():
         assert torch.equal(row_off.long(), torch.cumsum(cnt, 0) - cnt)
         for r in range(rows):
             assert torch.equal(vals[row_off[r]:row_off[r] + cnt[r]], x[r][m[r]])
+
+
+def test_ctypes_structures_have_the_size_and_field_offsets_of_the_header(tmp_path):
+    """The ctypes mirrors in lib.py against include/pcvae_b200.h compiled as plain C (gcc): sizeof and the offset of every
+    field, struct by struct -- a field added on one side only (as pcvae_dp_params.step_state was, mid-round) shows here
+    on the CPU instead of as a garbage pointer on the GPU."""
+    import ctypes as C
+    from vae_posterior_consistency_b200 import lib as L
+    pairs = {"pcvae_model": L.Model, "pcvae_enc_fwd_params": L.EncFwdParams, "pcvae_enc_bwd_params": L.EncBwdParams,
+             "pcvae_dec_params": L.DecParams, "pcvae_loss_params": L.LossParams, "pcvae_reward_params": L.RewardParams,
+             "pcvae_dense_fwd_params": L.DenseFwdParams, "pcvae_dense_bwd_params": L.DenseBwdParams,
+             "pcvae_mnar_loss_params": L.MnarLossParams, "pcvae_dp_params": L.DpParams}
+    hdr = open(os.path.join(ROOT, "include", "pcvae_b200.h")).read()
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pcvae_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        assert re.search(r"\}\s*" + cname + r"\s*;", hdr), f"{cname} is not a struct of the header"
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.strip().splitlines():
+        cname, size, *offs = line.split()
+        cls = pairs[cname]
+        assert int(size) == C.sizeof(cls), f"{cname}: sizeof {size} (header) vs {C.sizeof(cls)} (ctypes)"
+        got = [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert [int(o) for o in offs] == got, f"{cname}: field offsets differ: {offs} vs {got}"
+    # and every struct typedef of the header has a ctypes mirror
+    assert set(re.findall(r"\}\s*(pcvae_\w+)\s*;", hdr)) == set(pairs)
+
+
+def test_ctypes_argtypes_have_the_arity_of_the_header_prototypes():
+    """Every prototype of include/pcvae_b200.h against the argtypes lib.py sets: same number of parameters."""
+    from vae_posterior_consistency_b200 import lib as L
+    lib = L.load()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "pcvae_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|long|const char\*)\s+(pcvae_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 35, len(protos)
+    seen = set()
+    for name, args in protos:
+        seen.add(name)
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            assert n == 0, f"{name}: {n} parameters in the header, no argtypes in lib.py"
+        else:
+            assert len(fn.argtypes) == n, f"{name}: {n} parameters in the header, {len(fn.argtypes)} argtypes"
+    assert seen == set(L.SYMBOLS), (seen ^ set(L.SYMBOLS))

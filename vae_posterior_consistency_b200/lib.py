@@ -152,6 +152,7 @@ def load():
     lib.pcvae_dec_tc_workspace_floats.restype = C.c_long
     lib.pcvae_dec_tc_workspace_floats.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
     lib.pcvae_set_train_tensor_cores.argtypes = [C.c_int]
+    lib.pcvae_set_reward_tensor_cores.argtypes = [C.c_int]
     lib.pcvae_profile_events.argtypes = [C.c_void_p, C.c_int]
     lib.pcvae_loss_terms.argtypes = [C.POINTER(LossParams), C.c_void_p]
     lib.pcvae_reduce_sums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
