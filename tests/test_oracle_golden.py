@@ -174,3 +174,16 @@ def test_miwae_reshape_quirk_matters():
     lpx_ref = (logp * g["mask"].float().unsqueeze(1)).sum(2).reshape(g["S"], -1)
     lpx_fixed = (logp * g["mask"].float().unsqueeze(1)).sum(2).t()
     assert not torch.allclose(lpx_ref, lpx_fixed)
+
+
+def test_miwae_oracle_is_dtype_generic():
+    """The MIWAE restatement in fp64 agrees with its fp32 run (and hence with the reference) far inside the tolerance:
+    the kernels of the family will be checked against the fp64 evaluation as the reward kernels are."""
+    g = torch.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "reg_miwae_b12_d6_s4.pt"))
+    p64 = {k: v.double() for k, v in g["state_dict"].items()}
+    loss64, grads64, _ = O.miwae_train_step(p64, g["x"].double(), g["mask"], g["mask_p"], [d.double() for d in g["draws"]],
+                                            alpha=g["alpha"], regularised=True)
+    assert loss64.dtype == torch.float64
+    assert abs(float(loss64) - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
+    for k, ref in g["grads"].items():
+        torch.testing.assert_close(grads64[k].float(), ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max() + 1e-3))
