@@ -600,3 +600,46 @@ def miwae_train_step(p: Params, x, mask, mask_p, draws, alpha=1.0, regularised=T
     return loss.detach(), gd, dict(xm_q=xm_q.detach(), xs_q=xs_q.detach(), df_q=df_q.detach(), mean_q=mean_q.detach(),
                                    scale_q=scale_q.detach(), xm_imp=xm_imp.detach(),
                                    imp=None if imp is None else imp.detach())
+
+
+def miwae_loss_closed_form_grads(x, mask, raw, mean, scale, eps2):
+    """What a fused MIWAE loss kernel has to produce (the kernel of SURVEY.md 8f item 4 is to follow this line by line):
+    the loss and its gradients with respect to the RAW decoder output `raw` [B, S, 3D] (before the sigmoid / softplus
+    heads, VAE.py:3061-3066) and the direct gradients with respect to the encoder statistics mean / scale [B, L] through
+    log p(z) - log q(z|x) of the loss-internal draw z = mean + scale * eps2 (VAE.py:3086-3092).  Closed forms only (no
+    autograd); tests/test_oracle_golden.py checks them against autograd of miwae_loss."""
+    B, S, D3 = raw.shape
+    D = D3 // 3
+    sig = torch.sigmoid
+    xm = sig(raw[..., :D])
+    xs = torch.nn.functional.softplus(raw[..., D:2 * D]) + 0.001
+    df = torch.nn.functional.softplus(raw[..., 2 * D:]) + 3.0
+    xb = x.unsqueeze(1)
+    y = (xb - xm) / xs
+    A = 1.0 + y * y / df
+    logp = -0.5 * (df + 1.0) * torch.log(A) - (torch.log(xs) + 0.5 * torch.log(df) + HALF_LOG_PI + torch.lgamma(0.5 * df)
+                                               - torch.lgamma(0.5 * (df + 1.0)))
+    mf = _as(mask, x).unsqueeze(1)
+    lpx_flat = (logp * mf).sum(2).reshape(-1)                               # index k = b * S + s
+    z = mean.unsqueeze(1) + scale.unsqueeze(1) * eps2
+    logpz = (-0.5 * z * z - HALF_LOG_2PI).sum(2)                            # [B, S]
+    logq = (-0.5 * eps2 * eps2 - torch.log(scale).unsqueeze(1) - HALF_LOG_2PI).sum(2)
+    lw = lpx_flat.reshape(S, B) + (logpz - logq).t()                        # [S, B], the reference's un-transposed reshape
+    loss = -torch.mean(torch.logsumexp(lw, 0))
+    w = torch.softmax(lw, 0)                                                # [S, B]
+    g_lw = -w / B                                                           # dloss / dlw[i, j]
+    # likelihood side: lw[i, j] reads lpx_flat[i * B + j], i.e. (row, sample) = divmod(i * B + j, S)
+    g_lpx = g_lw.reshape(-1).reshape(B, S)                                  # back in (b, s) order
+    dl_loc = (df + 1.0) * y / (xs * df * A)
+    dl_scale = (df + 1.0) * y * y / (xs * df * A) - 1.0 / xs
+    dl_df = (-0.5 * torch.log(A) + 0.5 * (df + 1.0) * y * y / (df * df * A)
+             - (0.5 / df + 0.5 * torch.digamma(0.5 * df) - 0.5 * torch.digamma(0.5 * (df + 1.0))))
+    gm = (g_lpx.unsqueeze(2) * mf)
+    d_raw = torch.cat([gm * dl_loc * xm * (1.0 - xm),
+                       gm * dl_scale * sig(raw[..., D:2 * D]),
+                       gm * dl_df * sig(raw[..., 2 * D:])], 2)
+    # prior / posterior side: lw[i, j] reads (row j, sample i)
+    gt = g_lw.t().unsqueeze(2)                                              # [B, S, 1]
+    d_mean = (gt * (-z)).sum(1)
+    d_scale = (gt * (-z * eps2 + 1.0 / scale.unsqueeze(1))).sum(1)
+    return loss, d_raw, d_mean, d_scale

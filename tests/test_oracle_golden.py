@@ -187,3 +187,31 @@ def test_miwae_oracle_is_dtype_generic():
     assert abs(float(loss64) - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
     for k, ref in g["grads"].items():
         torch.testing.assert_close(grads64[k].float(), ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max() + 1e-3))
+
+
+@pytest.mark.parametrize("name", ["miwae_b12_d6_s4", "miwae_b7_d9_s5"])
+def test_miwae_closed_form_loss_gradients_match_autograd(golden, name):
+    """The closed forms a fused MIWAE loss kernel will implement (Student-t score functions incl. the digamma terms of
+    d/d(df), the softmax weights routed back through the reference's un-transposed reshape) against autograd of the
+    oracle's loss, in fp64."""
+    g = golden(name)
+    p = {k: v.double() for k, v in g["state_dict"].items()}
+    x, mask = g["x"].double(), g["mask"]
+    mean, scale = O.miwae_encoder_stats(p, x, mask)
+    z = mean.unsqueeze(1) + scale.unsqueeze(1) * g["draws"][0].double()
+    h = torch.relu(z @ p["seq_decoder.0.weight"].t() + p["seq_decoder.0.bias"])
+    h = torch.relu(h @ p["seq_decoder.2.weight"].t() + p["seq_decoder.2.bias"])
+    raw = (h @ p["seq_decoder.4.weight"].t() + p["seq_decoder.4.bias"]).detach().requires_grad_(True)
+    mean_l, scale_l = mean.detach().requires_grad_(True), scale.detach().requires_grad_(True)
+    D = x.shape[1]
+    sp = torch.nn.functional.softplus
+    xm, xs, df = torch.sigmoid(raw[..., :D]), sp(raw[..., D:2 * D]) + 0.001, sp(raw[..., 2 * D:]) + 3.0
+    eps2 = g["draws"][1].double()
+    loss_ad, _, _ = O.miwae_loss(x, mask, xm, xs, df, mean_l, scale_l, eps2)
+    g_raw, g_mean, g_scale = torch.autograd.grad(loss_ad, [raw, mean_l, scale_l])
+    loss, d_raw, d_mean, d_scale = O.miwae_loss_closed_form_grads(x, mask, raw.detach(), mean.detach(), scale.detach(), eps2)
+    assert abs(float(loss) - float(loss_ad.detach())) < 1e-12 and abs(float(loss) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    torch.testing.assert_close(d_raw, g_raw, rtol=1e-9, atol=1e-12)
+    torch.testing.assert_close(d_mean, g_mean, rtol=1e-9, atol=1e-12)
+    torch.testing.assert_close(d_scale, g_scale, rtol=1e-9, atol=1e-12)
+    assert float(d_raw[..., 2 * D:].abs().max()) > 0          # the degrees-of-freedom head does receive a gradient
