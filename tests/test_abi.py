@@ -186,3 +186,26 @@ def test_ctypes_argtypes_have_the_arity_of_the_header_prototypes():
         else:
             assert len(fn.argtypes) == n, f"{name}: {n} parameters in the header, {len(fn.argtypes)} argtypes"
     assert seen == set(L.SYMBOLS), (seen ^ set(L.SYMBOLS))
+
+
+def test_digamma_of_the_student_t_score_against_scipy(tmp_path):
+    """csrc/pcvae_special.cuh (host build, g++) against scipy.special.digamma on the range the MIWAE decoder produces
+    (df = softplus + 3 >= 3, so arguments >= 1.5), in double and in float."""
+    import numpy as np
+    from scipy.special import digamma
+    src = tmp_path / "dg.cpp"
+    src.write_text('#include <cstdio>\n#include "pcvae_special.cuh"\n'
+                   'int main() { for (double x = 1.5; x < 400.0; x *= 1.07) '
+                   'printf("%.17g %.17g %.9g %.9g\\n", x, pcvae::digamma_pos<double>(x), (double)pcvae::digamma_pos<float>((float)x), '
+                   '(double)pcvae::digamma_half_step<float>((float)(2.0 * x))); return 0; }\n')
+    exe = tmp_path / "dg"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "vae_posterior_consistency_b200", "csrc"), str(src), "-o", str(exe)])
+    rows = np.array([[float(v) for v in line.split()] for line in
+                     subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()])
+    x = rows[:, 0]
+    assert len(x) > 50
+    ref = digamma(x)
+    assert np.max(np.abs(rows[:, 1] - ref)) < 5e-10                                  # double: series truncation only
+    assert np.max(np.abs(rows[:, 2] - digamma(x.astype(np.float32).astype(np.float64)))) < 2e-6   # float
+    step = digamma(np.float32(2 * x).astype(np.float64) / 2 + 0.5) - digamma(np.float32(2 * x).astype(np.float64) / 2)
+    assert np.max(np.abs(rows[:, 3] - step) / step) < 2e-3 and np.max(np.abs(rows[:, 3] - step)) < 2e-6
