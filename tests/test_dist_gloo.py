@@ -76,3 +76,60 @@ def test_row_blocks_tile_exactly():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_graph_epoch_host_logic_without_a_gpu():
+    """train._graph_epoch (throughput mode, CUDA-graph replay): host side only -- the sampler's full batches go to the
+    trainer as one index table, the first epoch's warm-up steps count as steps, later epochs replay every batch, and the
+    host RNG is consumed as iter(DataLoader) would (base seed, then the sampler's permutation)."""
+    import torch
+    from torch.utils.data import DataLoader, TensorDataset
+    from vae_posterior_consistency_b200 import train as T
+
+    class FakeTrainer:
+        def __init__(self, B):
+            self.B, self.graph, self.step_count, self.calls = B, None, 0, []
+            self.table = self.mtable = None
+            self._total = torch.zeros((), dtype=torch.float64)
+
+        @property
+        def total(self):
+            return self._total
+
+        def reset_total(self):
+            self._total = torch.zeros((), dtype=torch.float64)
+
+        def set_batches(self, idx):
+            self.calls.append(("set", idx.clone(), self.step_count))
+
+        def capture(self, warmup=3):
+            self.graph = object()
+            self.step_count += warmup
+            self._total += warmup
+            self.calls.append(("capture", warmup))
+
+        def step_graph(self):
+            self.step_count += 1
+            self._total += 1
+            self.calls.append(("replay",))
+
+    N, B = 64, 8
+    loader = DataLoader(TensorDataset(torch.arange(N)), batch_size=B, shuffle=True)
+    tr = FakeTrainer(B)
+    torch.manual_seed(5)
+    tot1 = T._graph_epoch(tr, loader, torch.device("cpu"), True, 10)
+    tot2 = T._graph_epoch(tr, loader, torch.device("cpu"), True, 10)
+    state_after = torch.get_rng_state()
+    assert float(tot1) == N // B and float(tot2) == N // B and tr.step_count == 2 * (N // B)
+    kinds = [c[0] for c in tr.calls]
+    assert kinds == ["set", "capture"] + ["replay"] * (N // B - 3) + ["set"] + ["replay"] * (N // B)
+    assert tr.calls[1] == ("capture", 3)
+    # the index tables are the epochs' permutations, batch by batch, and the RNG stream is the DataLoader's
+    torch.manual_seed(5)
+    ref = []
+    for _ in range(2):
+        ref.append(torch.stack([b[0] for b in loader]))
+    assert torch.equal(torch.get_rng_state(), state_after)
+    sets = [c for c in tr.calls if c[0] == "set"]
+    assert torch.equal(sets[0][1], ref[0]) and sets[0][2] == 0
+    assert torch.equal(sets[1][1], ref[1]) and sets[1][2] == N // B
