@@ -643,3 +643,47 @@ def miwae_loss_closed_form_grads(x, mask, raw, mean, scale, eps2):
     d_mean = (gt * (-z)).sum(1)
     d_scale = (gt * (-z * eps2 + 1.0 / scale.unsqueeze(1))).sum(1)
     return loss, d_raw, d_mean, d_scale
+
+
+def reg_miwae_loss_closed_form_grads(x, mask, mask_p, raw_q, mean_q, scale_q, eps2_q, raw_p, mean_p, scale_p, eps2_p, alpha=1.0):
+    """Reg_MIWAE.loss (VAE.py:3197-3263) and its gradients in closed form:
+        loss = nb_q + alpha (KL_reg - nb_q + nb_p - reg_like)
+             = (1 - alpha) nb_q + alpha nb_p + alpha KL_reg - alpha reg_like
+    nb_* as in miwae_loss_closed_form_grads (masks: mask for q, mask_p for p), reg_like the mean over (row, sample) of the
+    q-branch log-likelihood on mask & ~mask_p, KL_reg the mean over [B, L] of KL(N(mean_q, scale_q) || N(mean_p, scale_p)).
+    Returns (loss, d_raw_q, d_mean_q, d_scale_q, d_raw_p, d_mean_p, d_scale_p)."""
+    B, S, D3 = raw_q.shape
+    D = D3 // 3
+    nb_q, dq_raw, dq_mean, dq_scale = miwae_loss_closed_form_grads(x, mask, raw_q, mean_q, scale_q, eps2_q)
+    nb_p, dp_raw, dp_mean, dp_scale = miwae_loss_closed_form_grads(x, mask_p, raw_p, mean_p, scale_p, eps2_p)
+    # reg_like and its gradient with respect to the q branch's raw decoder output
+    sig = torch.sigmoid
+    xm = sig(raw_q[..., :D])
+    xs = torch.nn.functional.softplus(raw_q[..., D:2 * D]) + 0.001
+    df = torch.nn.functional.softplus(raw_q[..., 2 * D:]) + 3.0
+    y = (x.unsqueeze(1) - xm) / xs
+    A = 1.0 + y * y / df
+    logp = -0.5 * (df + 1.0) * torch.log(A) - (torch.log(xs) + 0.5 * torch.log(df) + HALF_LOG_PI + torch.lgamma(0.5 * df)
+                                               - torch.lgamma(0.5 * (df + 1.0)))
+    only_q = (_as(mask, x) * (1.0 - _as(mask_p, x))).unsqueeze(1)
+    reg_like = (logp * only_q).sum(2).mean()
+    gw = only_q / (B * S)
+    dl_loc = (df + 1.0) * y / (xs * df * A)
+    dl_scale = (df + 1.0) * y * y / (xs * df * A) - 1.0 / xs
+    dl_df = (-0.5 * torch.log(A) + 0.5 * (df + 1.0) * y * y / (df * df * A)
+             - (0.5 / df + 0.5 * torch.digamma(0.5 * df) - 0.5 * torch.digamma(0.5 * (df + 1.0))))
+    d_reg_raw = torch.cat([gw * dl_loc * xm * (1.0 - xm), gw * dl_scale * sig(raw_q[..., D:2 * D]),
+                           gw * dl_df * sig(raw_q[..., 2 * D:])], 2)
+    # KL_reg = mean over [B, L] of  log(sp/sq) + (sq^2 + (mq - mp)^2) / (2 sp^2) - 1/2
+    L = mean_q.shape[1]
+    dm = mean_q - mean_p
+    kl = (torch.log(scale_p / scale_q) + (scale_q ** 2 + dm ** 2) / (2 * scale_p ** 2) - 0.5).mean()
+    n = B * L
+    dk_mq = dm / scale_p ** 2 / n
+    dk_mp = -dk_mq
+    dk_sq = (-1.0 / scale_q + scale_q / scale_p ** 2) / n
+    dk_sp = (1.0 / scale_p - (scale_q ** 2 + dm ** 2) / scale_p ** 3) / n
+    loss = (1.0 - alpha) * nb_q + alpha * nb_p + alpha * kl - alpha * reg_like
+    return (loss,
+            (1.0 - alpha) * dq_raw - alpha * d_reg_raw, (1.0 - alpha) * dq_mean + alpha * dk_mq, (1.0 - alpha) * dq_scale + alpha * dk_sq,
+            alpha * dp_raw, alpha * dp_mean + alpha * dk_mp, alpha * dp_scale + alpha * dk_sp)
