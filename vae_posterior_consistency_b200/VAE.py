@@ -19,8 +19,6 @@ There is no CPU execution path: calling these modules with CPU tensors raises Pc
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import torch
 from torch import nn

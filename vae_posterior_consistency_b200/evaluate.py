@@ -14,7 +14,6 @@ import os
 import numpy as np
 import torch
 
-from . import kernels as KR
 from . import lib as L
 from . import ops
 from .dist import merge_row_blocks, row_block, world

@@ -23,7 +23,7 @@ from tqdm import tqdm
 
 from . import kernels as KR
 from . import lib as L
-from .dist import merge_row_blocks, row_block, world
+from .dist import row_block, world
 from .loaders import checkpoint_path, model_loader
 from .utils import create_missing_uci, create_missing_uci_drop_eddi
 from .VAE import draw_noise, fill_normal_
