@@ -258,7 +258,8 @@ int pcvae_reduce_adam(const float* grad_partials, int grid, long param_count, fl
  * buffer, publishes its 64-byte CUDA IPC handle (any host channel, e.g. torch.distributed.all_gather_object), opens the
  * handles of the others, and passes all `world` base pointers (its own at index `rank`) with every call.  `seq` is the
  * 1-based number of the call on this buffer and must advance by one per call on every rank in lockstep.  A rank that
- * does not arrive within ~4 s makes the waiting ranks set *status = 1 and continue (no hang); check it on the host.
+ * does not arrive within ~4 s makes the waiting ranks set *status = 1 and SKIP their Adam update (no hang, no update from
+ * stale slots); check the status word on the host (dist.PeerExchange.check, called by train() at every epoch end).
  * --------------------------------------------------------------------- */
 #define PCVAE_DP_MAX_WORLD 16
 size_t pcvae_dp_exchange_bytes(long param_count, int world);
@@ -279,6 +280,13 @@ typedef struct {
                                                                      pcvae_reduce_adam_dev; `step` and `seq` are then ignored */
 } pcvae_dp_params;
 int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream);
+/* The same kernel body with `world` ranks EMULATED on one GPU (tests on a single-GPU box): ranks[r] describes rank r
+ * (its own partials, weights, moments; peer_buffers = `world` plain cudaMalloc'ed exchange buffers on this GPU, the same
+ * array in every entry).  One cooperative launch plays all ranks -- separate launches that wait for one another on one
+ * GPU are not guaranteed to overlap.  Results are bit-identical to `world` real ranks (the per-chunk arithmetic does
+ * not depend on the grid). */
+#define PCVAE_DP_EMU_MAX_WORLD 4
+int pcvae_dp_reduce_adam_emulated(const pcvae_dp_params* const* ranks, int world, void* stream);
 
 /* ------------------------------------------------------------------------
  * Active-selection information reward for ONE acquisition step, all (row, candidate,

@@ -60,6 +60,31 @@ void prof_mark(cudaStream_t st) {
     if (g_prof_ev && g_prof_i < g_prof_n) cudaEventRecord(g_prof_ev[g_prof_i++], st);
 }
 
+// Per-device status word of the tensor-core kernels: one int in pinned, mapped host memory.  A kernel whose bounded
+// mbarrier wait runs out (tc::mbar_wait) stores a non-zero code there; the NEXT entry into the library on that device
+// (device_ok, the first thing every entry point does) reports it as PCVAE_ECUDA instead of letting a corrupted
+// training run continue with rc = 0.  Reading the word needs no synchronisation.
+constexpr int MAX_DEVICES = 64;
+static int* g_status_host[MAX_DEVICES];
+static int* g_status_dev[MAX_DEVICES];
+
+static void status_init(int dev) {
+    if (dev < 0 || dev >= MAX_DEVICES || g_status_host[dev]) return;
+    int* h = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return; }
+    *h = 0;
+    int* d = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(h); return; }
+    g_status_dev[dev] = d;
+    g_status_host[dev] = h;
+}
+
+int* tc_status_ptr() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    return g_status_dev[dev];
+}
+
 int device_ok(int* n_sm) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -73,6 +98,17 @@ int device_ok(int* n_sm) {
     }
     if (cached_major != 10) return fail(PCVAE_EDEVICE, "device %d is compute capability %d.x; this library is sm_100a only", dev, cached_major);
     if (n_sm) *n_sm = cached_sm;
+    if (dev >= 0 && dev < MAX_DEVICES) {
+        if (!g_status_host[dev]) status_init(dev);
+        if (g_status_host[dev]) {
+            const int code = *reinterpret_cast<volatile int*>(g_status_host[dev]);
+            if (code != 0) {
+                *reinterpret_cast<volatile int*>(g_status_host[dev]) = 0;
+                return fail(PCVAE_ECUDA, "a tensor-core kernel of an earlier call on device %d gave up waiting for an mbarrier "
+                            "(kernel code %d): the results of that call are invalid", dev, code);
+            }
+        }
+    }
     return PCVAE_OK;
 }
 

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
     image_linear(W5h, W5l, F5_N, th + L.W5, th + L.b5, G2, G1, true, tid);       // constant-1 output -> bias column of layer 6
     image_linear(W6h, W6l, N6, th + L.W6, th + L.b6, D, G2, false, tid);
     TileCtx cx;
-    tc_setup(cx, &bar_s, &tmem_slot, tid);
+    tc_setup(cx, &bar_s, &tmem_slot, tid, a.status);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
     const int cg = cx.cg, row = cx.row, c28 = cx.c28, c16 = cx.c16;
 
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
             reluT[4 + cg] = m4;
             mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_f6h, r_f6l, fs6, F6_C / 2, idF6); });
             // while the tensor pipe runs F6: this thread's 28 entries of x and of the two masks (as bits)
-            if (staged) { mbar_wait(&in_bar, in_ph); in_ph ^= 1u; }
+            if (staged) { mbar_wait(&in_bar, in_ph, a.status, 3); in_ph ^= 1u; }
             float xr[28];
             uint32_t mb = 0, mpb = 0;
 #pragma unroll
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     image_linear_T(T5h, T5l, X5_N, th + L.W5, G2, G1, tid);
     image_linear_T(T4h, T4l, X4_N, th + L.W4, G1, LAT, tid);
     TileCtx cx;
-    tc_setup(cx, &bar_s, &tmem_slot, tid);
+    tc_setup(cx, &bar_s, &tmem_slot, tid, a.status);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
     const int cg = cx.cg, row = cx.row, c28 = cx.c28, c16 = cx.c16;
 
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
             uint32_t m5 = 0, m4 = 0;
             if (ok) { m5 = reluT[cg]; m4 = reluT[4 + cg]; }
             // ---- dpre6 (staged in shared memory) -> RA ----
-            mbar_wait(&in_bar, in_ph);
+            mbar_wait(&in_bar, in_ph, a.status, 3);
             in_ph ^= 1u;
             {
                 float d6[28];
@@ -592,7 +592,9 @@ static int tc_launch(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
     return PCVAE_OK;
 }
 
-int dec_tc_launch(const DecArgs& a, int grid, cudaStream_t st) {
+int dec_tc_launch(const DecArgs& a_in, int grid, cudaStream_t st) {
+    DecArgs a = a_in;
+    a.status = tc_status_ptr();
     prof_mark(st);
     {   // loss inputs are staged through shared memory when the masks are bytes and the tile fits beside the weight images
         const bool stage_inputs = a.mask_kind == PCVAE_MASK_U8 && tc::dec_fwd_tc_smem(a.L.D, a.nbr, true) + 1024 <= (size_t)MAX_SMEM;

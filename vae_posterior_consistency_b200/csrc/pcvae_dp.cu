@@ -42,10 +42,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-__global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
+// One block of one rank.  `bid` / `nbid` are the block's index and the block count WITHIN its rank: blockIdx.x / gridDim.x
+// in a real multi-GPU launch (k_dp_reduce_adam), a slice of the grid when several ranks are emulated in one cooperative
+// launch on one GPU (k_dp_reduce_adam_emulated).
+__device__ __forceinline__ void dp_block(DpArgs a, const int bid, const int nbid) {
     __shared__ float red[8][32];
     __shared__ float bc_s[2];
+    __shared__ int late_s;
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    if (threadIdx.x == 0) late_s = 0;
     if (a.state) {                                        // replayable launch: call number and Adam step from the device
         const unsigned long long st = *reinterpret_cast<volatile unsigned long long*>(a.state) + 1ull;
         a.seq = (unsigned)st;
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     const long slot0 = (long)(a.seq & 1u) * a.world * slot_floats;
     // ---- phase 1: this block's chunks of 32 parameters (chunk c = blockIdx.x, + gridDim.x, ...): reduce the rank's
     //      partials in the order of k_reduce_adam and push the 32 values into slot [rank] of every rank ----
-    for (int c = blockIdx.x; c < a.nblocks; c += gridDim.x) {
+    for (int c = bid; c < a.nblocks; c += nbid) {
         const long i = (long)c * 32 + lane;
         float s = 0.f;
         if (i < P) {
@@ -91,28 +96,31 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
         __syncwarp();
         if (lane < a.world) {
             unsigned* f = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(a.peer[lane]) + data_floats) +
-                          (long)a.rank * a.nblocks + blockIdx.x;
+                          (long)a.rank * a.nblocks + bid;
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.seq) : "memory");
             const unsigned* w = reinterpret_cast<const unsigned*>(reinterpret_cast<const float*>(a.peer[a.rank]) + data_floats) +
-                                (long)lane * a.nblocks + blockIdx.x;
+                                (long)lane * a.nblocks + bid;
             const unsigned long long t0 = globaltimer_ns();
             unsigned spins = 0, seen;
             for (;;) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
                 if ((int)(seen - a.seq) >= 0) break;     // flags only grow (wrap-safe comparison)
                 __nanosleep(100);
-                if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) { atomicExch(a.status, 1); break; }
+                if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) { atomicExch(a.status, 1); late_s = 1; break; }
             }
         }
         __syncwarp();
     }
     __syncthreads();
+    // a rank that did not deliver within the bound: the slots hold stale data, so this block applies NO update (the status
+    // word is set; the host raises on it, dist.PeerExchange.check); weights stay what they were
+    const bool late = late_s != 0;
     if (a.state) { a.lr_bc1 = bc_s[0]; a.inv_sqrt_bc2 = bc_s[1]; }
     // ---- phase 3: sum the slots in rank order (identical on every rank) and apply Adam; the block's chunks are dealt
     //      over its eight warps ----
     {
         int j = 0;
-        for (int c = blockIdx.x; c < a.nblocks; c += gridDim.x, ++j) {
+        for (int c = bid; c < a.nblocks && !late; c += nbid, ++j) {
             if ((j & 7) != part) continue;
             const long i = (long)c * 32 + lane;
             const volatile float* mine = reinterpret_cast<const volatile float*>(a.peer[a.rank]) + slot0 + (long)c * 32 + lane;
@@ -132,14 +140,14 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned* ticket = reinterpret_cast<unsigned*>(a.state + 1);
-            if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            if (atomicAdd(ticket, 1u) == (unsigned)nbid - 1) {
                 *ticket = 0u;
                 __threadfence();
                 *reinterpret_cast<volatile unsigned long long*>(a.state) = *reinterpret_cast<volatile unsigned long long*>(a.state) + 1ull;
             }
         }
     }
-    if (a.sp && blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + PCVAE_NSUMS) {   // this rank's loss sums
+    if (a.sp && bid == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + PCVAE_NSUMS) {   // this rank's loss sums
         const int j = threadIdx.x - 32;
         double acc = 0.0;
         for (int c = 0; c < a.grid; ++c) acc += (double)a.sp[c * PCVAE_NSUMS + j];
@@ -147,6 +155,17 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
         a.sums[j] = acc;
         if (a.state) a.sums[PCVAE_NSUMS + j] += acc;      // running totals since the caller last zeroed them
     }
+}
+
+__global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) { dp_block(a, blockIdx.x, gridDim.x); }
+
+// Test vehicle (pcvae_dp_reduce_adam_emulated): `world` ranks whose buffers all live on ONE GPU, run as one cooperative
+// launch -- blocks [r * nbid, (r + 1) * nbid) play rank r.  Separate launches that wait for one another on one GPU are
+// not guaranteed to run concurrently (B200_PROFILING.md); a cooperative launch is.
+struct DpEmuArgs { DpArgs r[PCVAE_DP_EMU_MAX_WORLD]; int nbid; };
+__global__ void __launch_bounds__(256) k_dp_reduce_adam_emulated(DpEmuArgs e) {
+    const int r = blockIdx.x / e.nbid;
+    dp_block(e.r[r], blockIdx.x - r * e.nbid, e.nbid);
 }
 
 static long dp_p32(long P) { return (P + 31) / 32 * 32; }
@@ -205,16 +224,14 @@ int pcvae_dp_exchange_free(void* buffer) {
     return e == cudaSuccess ? PCVAE_OK : fail(PCVAE_ECUDA, "dp_exchange_free: %s", cudaGetErrorString(e));
 }
 
-int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
-    int grid;
-    if (int rc = device_ok(&grid)) return rc;
+static int dp_convert(const pcvae_dp_params* p, DpArgs& a) {
     if (!p || !p->grad_partials || !p->grad || !p->theta || !p->exp_avg || !p->exp_avg_sq || p->grid < 1 || p->param_count < 1 ||
         (p->step < 1 && !p->step_state) || !p->status)
         return fail(PCVAE_EINVAL, "dp_reduce_adam: bad arguments");
     if (p->world < 1 || p->world > DP_MAX_WORLD || p->rank < 0 || p->rank >= p->world || (p->seq == 0 && !p->step_state))
         return fail(PCVAE_EINVAL, "dp_reduce_adam: world %d (1..%d), rank %d, seq %u (>= 1)", p->world, DP_MAX_WORLD, p->rank, p->seq);
     if ((p->sums_partials == nullptr) != (p->sums == nullptr)) return fail(PCVAE_EINVAL, "dp_reduce_adam: sums_partials and sums go together");
-    DpArgs a{};
+    a = DpArgs{};
     for (int r = 0; r < p->world; ++r) {
         if (!p->peer_buffers[r]) return fail(PCVAE_EINVAL, "dp_reduce_adam: peer buffer %d is null", r);
         a.peer[r] = static_cast<char*>(p->peer_buffers[r]);
@@ -231,12 +248,49 @@ int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
     a.world = p->world; a.rank = p->rank; a.seq = p->seq;
     a.P32 = dp_p32(p->param_count); a.nblocks = (int)(a.P32 / 32);
     a.status = p->status;
+    return PCVAE_OK;
+}
+
+int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    DpArgs a;
+    if (int rc = dp_convert(p, a)) return rc;
     // every block must be resident at once (a block waits for the other ranks before it ends): at most two per SM.  All
     // ranks must launch the same grid, i.e. be the same GPU model.
     const int blocks = a.nblocks < 2 * grid ? a.nblocks : 2 * grid;
     k_dp_reduce_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dp_reduce_adam: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+int pcvae_dp_reduce_adam_emulated(const pcvae_dp_params* const* ranks, int world, void* stream) {
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    if (!ranks || world < 1 || world > PCVAE_DP_EMU_MAX_WORLD)
+        return fail(PCVAE_EINVAL, "dp_reduce_adam_emulated: world %d (1..%d)", world, PCVAE_DP_EMU_MAX_WORLD);
+    DpEmuArgs e{};
+    for (int r = 0; r < world; ++r) {
+        if (!ranks[r] || ranks[r]->world != world || ranks[r]->rank != r)
+            return fail(PCVAE_EINVAL, "dp_reduce_adam_emulated: entry %d must describe rank %d of %d", r, r, world);
+        if (int rc = dp_convert(ranks[r], e.r[r])) return rc;
+        if (e.r[r].nblocks != e.r[0].nblocks) return fail(PCVAE_EINVAL, "dp_reduce_adam_emulated: ranks differ in param_count");
+    }
+    // all world * nbid blocks must be co-resident: ask the occupancy calculator, then launch cooperatively (the runtime
+    // refuses a cooperative grid that does not fit instead of letting it deadlock)
+    int per_sm = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_reduce_adam_emulated, 256, 0);
+    if (err != cudaSuccess || per_sm < 1) return fail(PCVAE_ECUDA, "dp_reduce_adam_emulated: occupancy query: %s", cudaGetErrorString(err));
+    int nbid = (per_sm * grid) / world;
+    if (nbid > 2 * grid) nbid = 2 * grid;
+    if (nbid > e.r[0].nblocks) nbid = e.r[0].nblocks;
+    if (nbid < 1) return fail(PCVAE_EINVAL, "dp_reduce_adam_emulated: %d ranks do not fit on this GPU", world);
+    e.nbid = nbid;
+    void* kargs[] = {&e};
+    err = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_dp_reduce_adam_emulated), dim3(world * nbid), dim3(256), kargs, 0,
+                                      (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail(PCVAE_ECUDA, "dp_reduce_adam_emulated: launch: %s", cudaGetErrorString(err));
     return PCVAE_OK;
 }
 

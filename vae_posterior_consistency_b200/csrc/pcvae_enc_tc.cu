@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
     image_linear(W3h, W3l, E3_N, th + L.W3, th + L.b3, LAT, H2, false, tid);
     image_linear(W3h + 16 * 4, W3l + 16 * 4, E3_N, th + L.W3 + LAT * H2, th + L.b3 + LAT, LAT, H2, false, tid);
     TileCtx cx;
-    tc_setup(cx, &bar_s, &tmem_slot, tid);
+    tc_setup(cx, &bar_s, &tmem_slot, tid, a.tw.status);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
     const int cg = cx.cg, row = cx.row, c28 = cx.c28, c16 = cx.c16;
 
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
             float* h2T = tw.h2T + (long)vt * (ETW_H2 * ROWS) + (row >> 5) * (32 * ETW_H2) + (row & 31);
             unsigned* reluT = tw.relu + (vt * ROWS + row) * 8;
             // ---- x * mask | 1 -> RA, HBM: all loads of the thread in flight before the first TMEM store ----
-            if (staged) { mbar_wait(&in_bar, in_ph); in_ph ^= 1u; }
+            if (staged) { mbar_wait(&in_bar, in_ph, a.tw.status, 3); in_ph ^= 1u; }
             {
                 float xm[28];
 #pragma unroll
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
     image_linear_T(T3h, T3l, Y3_N, th + L.W3, LAT2, H2, tid);
     image_linear_T(T2h, T2l, Y2_N, th + L.W2, H2, H1, tid);
     TileCtx cx;
-    tc_setup(cx, &bar_s, &tmem_slot, tid, B_COLS);
+    tc_setup(cx, &bar_s, &tmem_slot, tid, a.tw.status, B_COLS);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
     const int cg = cx.cg, row = cx.row, c28 = cx.c28, c16 = cx.c16;
 
@@ -407,6 +407,7 @@ bool enc_tc_supported(const Layout& L) { return L.fam == PCVAE_FAMILY_MLP && !L.
 void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw) {
     const long nvt = tc_nvt(rows, nbr), n = nvt * 128;
     tw->nvt = nvt;
+    tw->status = tc_status_ptr();
     tw->inT = w;  w += n * ETW_IN;
     tw->h1T = w;  w += n * ETW_H1;
     tw->h2T = w;  w += n * ETW_H2;

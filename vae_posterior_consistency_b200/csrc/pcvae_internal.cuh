@@ -38,6 +38,9 @@ int fail(int code, const char* fmt, ...);
 bool make_layout(const pcvae_model* m, Layout* L);
 // PCVAE_OK and the SM count when the current device is a compute-capability-10.x part
 int device_ok(int* n_sm);
+// device pointer of the current device's tensor-core status word (pinned mapped host memory; nullptr if it could not be
+// set up): kernels store a non-zero code there when a bounded mbarrier wait runs out, device_ok() reports it
+int* tc_status_ptr();
 // records the next armed profiling event (pcvae_profile_events) on `st`, if any
 void prof_mark(cudaStream_t st);
 // fills the PNP collapsed tables A,C (2*D*round4(K) floats) from theta

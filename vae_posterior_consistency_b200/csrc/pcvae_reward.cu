@@ -413,6 +413,7 @@ int pcvae_reward_chain(const pcvae_reward_params* p, void* stream) {
     a.base_in = (float*)(ws + w.base_in); a.base0 = (float*)(ws + w.base0); a.baseT = (float*)(ws + w.baseT);
     a.cnt = (int*)(ws + w.cnt); a.off = (int*)(ws + w.off); a.cand = (uint8_t*)(ws + w.cand); a.pairs = (int*)(ws + w.pairs);
     a.ac = p->pnp_ac;
+    a.status = tc_status_ptr();
     cudaError_t e;
     const size_t s1 = prep_smem(L), s2 = main_smem(L);
     if (s1 > MAX_SMEM || s2 > MAX_SMEM) return fail(PCVAE_EINVAL, "reward_chain: shared memory %zu/%zu B exceeds %d", s1, s2, MAX_SMEM);

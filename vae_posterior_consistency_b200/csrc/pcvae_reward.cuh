@@ -26,6 +26,7 @@ struct RewardArgs {
     uint8_t* cand;    // [N][CANDP]
     int* pairs;       // [N*(D-1)]  n*128+u
     const float* ac;  // PNP tables
+    int* status;      // tensor-core status word (tc_status_ptr), set by the launcher
 };
 
 

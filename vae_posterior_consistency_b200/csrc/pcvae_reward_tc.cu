@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
         // KL of sample m against the base posteriors (warps 0-3, one tile row per thread)
         auto kl_epilogue = [&](int m) {
             const int buf = m % NBUF;
-            mbar_wait(bar3, ph3);
+            mbar_wait(bar3, ph3, a.status, 4);
             tc_fence_after();
             float o[20];
             tmem_ld16(lane_addr + COL_D3, o);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_tc(const RewardArgs a) {
                 if (cg == 0) kl_epilogue(m - 1);
                 ph3 ^= 1;
             }
-            mbar_wait(bar2, ph2);          // MMA2(m) (and everything issued before it) complete
+            mbar_wait(bar2, ph2, a.status, 4);          // MMA2(m) (and everything issued before it) complete
             ph2 ^= 1;
             tc_fence_after();
             // ---- epilogue 2: D2 -> ReLU -> hi / lo operand of layer 3 in shared memory ----

@@ -64,7 +64,10 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: never hangs the GPU.  When the bound runs out the kernel's results are invalid; `status` (the device's
+// tensor-core status word, pcvae_internal.cuh: tc_status_ptr) receives `code` and the next entry into the library on
+// this device fails with PCVAE_ECUDA instead of continuing silently.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* status, int code) {
     const uint32_t addr = smem_u32(bar);
     for (int i = 0; i < (1 << 20); ++i) {
         uint32_t ok;
@@ -72,7 +75,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return true;
     }
-    return false;   // bounded: never hang the GPU; the caller's results will be wrong and tests catch it
+    if (status) { *reinterpret_cast<volatile int*>(status) = code; __threadfence_system(); }
+    return false;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -145,6 +145,7 @@ __device__ __forceinline__ uint64_t ld_desc(const uint64_t* slot) {
 struct TileCtx {
     uint32_t tmem, lane_addr, ph;
     int q, cg, row, c28, c16;
+    int* status;                      // tensor-core status word of the device (bounded waits report here)
 };
 
 // barrier + (one elected lane) MMA issue + commit; every thread then waits for the batch.  mma_kick / mma_wait are the
@@ -164,7 +165,7 @@ __device__ __forceinline__ void mma_kick(uint64_t* bar, int warp, Issue&& issue)
     }
 }
 __device__ __forceinline__ void mma_wait(TileCtx& cx, uint64_t* bar) {
-    mbar_wait(bar, cx.ph);
+    mbar_wait(bar, cx.ph, cx.status, 2);
     cx.ph ^= 1;
     tc_fence_after();
 }
@@ -174,7 +175,7 @@ __device__ __forceinline__ void run_mma(TileCtx& cx, uint64_t* bar, int warp, Is
     mma_wait(cx, bar);
 }
 
-__device__ __forceinline__ void tc_setup(TileCtx& cx, uint64_t* bar, uint32_t* slot, int tid, uint32_t ncols = 512) {
+__device__ __forceinline__ void tc_setup(TileCtx& cx, uint64_t* bar, uint32_t* slot, int tid, int* status, uint32_t ncols = 512) {
     const int warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
@@ -190,6 +191,7 @@ __device__ __forceinline__ void tc_setup(TileCtx& cx, uint64_t* bar, uint32_t* s
     tc_fence_after();
     cx.tmem = *slot;
     cx.ph = 0;
+    cx.status = status;
     cx.q = warp & 3;
     cx.cg = warp >> 2;
     cx.row = 32 * cx.q + lane;

@@ -33,6 +33,7 @@ struct DecArgs {
     float* ws_dp4T;   // [nvt][56][128]
     unsigned* ws_relu; // [nvt*128][8]: bit masks of h5 > 0 (4 column groups x 28) and h4 > 0 (4 x 16)
     long nvt;
+    int* status;      // tensor-core status word (tc_status_ptr), set by the launchers
 };
 
 // tensor-core encoder scratch (pcvae_enc_tc.cu): tile-blocked feature-major [vt][feature][128 rows] like the decoder's
@@ -45,6 +46,7 @@ struct EncTcWs {
     float* dp3T;      // [nvt][24][128]   (d_mean | d_logvar)
     unsigned* relu;   // [nvt*128][8]: bit masks of h1 > 0 (4 column groups x 28) and h2 > 0 (4 x 16)
     long nvt;
+    int* status;      // tensor-core status word (tc_status_ptr), set by the launchers
 };
 
 struct EncFwdArgs {

@@ -49,6 +49,7 @@ struct WgradArgs {
     int njobs;
     long nvt;                             // 128-row tiles in the scratch (rows past the batch carry zero gradients)
     float* gp; long P;
+    int* status;                          // tensor-core status word (tc_status_ptr)
 };
 
 __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
                     const float* At = J.AT + vt * (long)(J.Fa * WG_TROWS);
                     const float* Bt = J.BT + vt * (long)(J.Fb * WG_TROWS);
                     for (int sl = 0; sl < WG_SPT; ++sl) {
-                        if (wrapped) mbar_wait(&rfree_bar[r], pr ^ 1u);      // the converters have read the stage's previous slab
+                        if (wrapped) mbar_wait(&rfree_bar[r], pr ^ 1u, a.status, 5);      // the converters have read the stage's previous slab
                         float* st = raw0 + r * WG_RSTAGE_FLOATS;
                         mbar_expect_tx(&land_bar[r], abytes + bbytes);
                         bulk_g2s(st, At + sl * (SLAB * J.Fa), abytes, &land_bar[r]);
@@ -143,11 +144,11 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
             const uint32_t id2 = make_idesc(128, 2 * Nb), id1 = make_idesc(128, Nb);
             constexpr uint64_t sa = (2 * WG_ACS * 4) >> 4, sb = (2 * WG_BCS * 4) >> 4;
             if (j >= 2) {                                // this accumulator buffer was layer j-2's: wait until it is drained
-                mbar_wait(&drained_bar[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
+                mbar_wait(&drained_bar[j & 1], (uint32_t)(((j >> 1) - 1) & 1), a.status, 5);
                 tc_fence_after();
             }
             for (int i = 0; i < nslab; ++i) {
-                mbar_wait(&full_bar[im], pi);
+                mbar_wait(&full_bar[im], pi, a.status, 5);
                 tc_fence_after();
                 if (elect_one()) {
                     float* st = img0 + im * WG_ISTAGE_FLOATS;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
         // Row m of dWaug = TMEM lane (this warp's quarter); columns [0,Nb) hold A_hi B_hi + A_lo B_hi, [Nb,2Nb) A_hi B_lo.
         for (int j = 0; j < a.njobs; ++j) {
             const WgradJob J = a.job[j];
-            mbar_wait(&done_bar[j & 1], (uint32_t)((j >> 1) & 1));
+            mbar_wait(&done_bar[j & 1], (uint32_t)((j >> 1) & 1), a.status, 5);
             tc_fence_after();
             const int q = warp & 3;
             const int m = 32 * q + lane;
@@ -212,14 +213,14 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
             for (int i = 0; i < nslab; ++i) {
                 const float* raw = raw0 + r * WG_RSTAGE_FLOATS + tid * 4;
                 float* st = img0 + im * WG_ISTAGE_FLOATS;
-                mbar_wait(&land_bar[r], pr);
+                mbar_wait(&land_bar[r], pr, a.status, 5);
                 float4 va[WG_IPT], vb[WG_IPT];
 #pragma unroll
                 for (int k = 0; k < WG_IPT; ++k) {
                     if (imgA[k] >= 0) va[k] = *reinterpret_cast<const float4*>(raw + k * (WG_CONVERTERS * 4));
                     if (imgB[k] >= 0) vb[k] = *reinterpret_cast<const float4*>(raw + WG_RAW_FLOATS + k * (WG_CONVERTERS * 4));
                 }
-                if (iwrapped) mbar_wait(&empty_bar[im], pi ^ 1u);            // the MMAs of the image stage's previous slab are done
+                if (iwrapped) mbar_wait(&empty_bar[im], pi ^ 1u, a.status, 5);            // the MMAs of the image stage's previous slab are done
 #pragma unroll
                 for (int k = 0; k < WG_IPT; ++k) {
                     if (imgA[k] >= 0) {
@@ -261,7 +262,7 @@ int wgrad_tc_launch(const WgradJob* jobs, int njobs, long nvt, float* gp, long P
             J.Ma > J.Fa || J.Kin + 1 > J.Fb || J.Kin + 1 > J.Nb || tc::WG_CH * J.Fa > tc::WG_IPT * tc::WG_CONVERTERS)
             return fail(PCVAE_EINVAL, "wgrad_tc: layer %d shape (%d/%d x %d/%d, N %d) not supported", j, J.Ma, J.Fa, J.Kin, J.Fb, J.Nb);
     }
-    a.njobs = njobs; a.nvt = nvt; a.gp = gp; a.P = P;
+    a.njobs = njobs; a.nvt = nvt; a.gp = gp; a.P = P; a.status = tc_status_ptr();
     const size_t sm = (size_t)tc::WG_SMEM_FLOATS * sizeof(float) + 128;
     cudaError_t e = cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

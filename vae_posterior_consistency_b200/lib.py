@@ -31,6 +31,7 @@ SYMBOLS = [
     "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events", "pcvae_prep_packed",
     "pcvae_dp_exchange_bytes", "pcvae_dp_exchange_alloc", "pcvae_dp_exchange_open", "pcvae_dp_exchange_close",
     "pcvae_dp_exchange_free", "pcvae_dp_reduce_adam", "pcvae_prep_batch_dev", "pcvae_reduce_adam_dev",
+    "pcvae_dp_reduce_adam_emulated",
 ]
 
 
@@ -184,6 +185,7 @@ def load():
     lib.pcvae_dp_exchange_close.argtypes = [C.c_void_p]
     lib.pcvae_dp_exchange_free.argtypes = [C.c_void_p]
     lib.pcvae_dp_reduce_adam.argtypes = [C.POINTER(DpParams), C.c_void_p]
+    lib.pcvae_dp_reduce_adam_emulated.argtypes = [C.POINTER(C.POINTER(DpParams)), C.c_int, C.c_void_p]
     lib.pcvae_reduce_adam.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]
