@@ -446,6 +446,62 @@ typedef struct {
 size_t pcvae_mnar_loss_workspace_bytes(int rows, int samples, int obs_dim);
 int pcvae_mnar_loss(const pcvae_mnar_loss_params* p, void* stream);
 
+/* ------------------------------------------------------------------------
+ * MIWAE / Reg_MIWAE (Student-t decoder + importance-weighted bound), reference src/models/VAE.py:3011-3134, 3137-3301;
+ * dispatched by src/utils/loaders.py:135-147, 234-245, trained at src/experiment_main/train.py:102-113, evaluated by
+ * eval_miwae, src/experiment_main/evaluate.py:72-133.  The 128-wide ReLU layers are
+ * pcvae_dense_fwd / pcvae_dense_bwd calls (PCVAE_ACT_RELU / PCVAE_ACT_NONE); these entries are the rest:
+ *  pcvae_miwae_heads        encoder (VAE.py:3047-3049): raw [rows][2W] -> out0 = raw[:, :W], out1 = softplus(raw[:, W:]);
+ *                           decoder (VAE.py:3061-3066): raw [rows][3W] -> out0 = sigmoid, out1 = softplus + 0.001,
+ *                           out2 = softplus + 3   (nn.Softplus: beta 1, threshold 20)
+ *  pcvae_miwae_heads_bwd    d_raw from the gradients of the outputs (NULL = zero), derivatives taken from raw
+ *  pcvae_miwae_sample_z     z[b][s][l] = mean[b][l] + scale[b][l] eps[b][s][l] (VAE.py:3054-3056; eps NULL: z = mean)
+ *  pcvae_miwae_sample_z_bwd d_mean = sum_s d_z, d_scale = sum_s d_z eps
+ *  pcvae_miwae_loss         MIWAE.loss (regularised = 0, VAE.py:3068-3110) / Reg_MIWAE.loss (regularised = 1,
+ *                           VAE.py:3197-3263): StudentT(df, loc, scale).log_prob(x) per (row, sample, feature), masked sums,
+ *                           the reference's [B*S] -> [S, B] reshape WITHOUT a transpose of the per-(row, sample)
+ *                           likelihoods (VAE.py:3078-3081; rowwise = 1 instead treats every row as its own batch, which is
+ *                           what eval_miwae's per-row calls amount to), log p(z) - log q(z|x) of the loss-internal draw
+ *                           z = mean + scale eps2, -mean(logsumexp over samples); Reg: loss = nb_q + alpha (KL_reg - nb_q +
+ *                           nb_p - reg_like); llh_eval imputation sum_k softmax_k x_mean[., k, :]; every gradient.
+ * out[0] = loss, [1] = neg_bound_q, [2] = neg_bound_p, [3] = KL_reg, [4] = reg_like, [5] = sum of the log-likelihood on the
+ * unobserved entries / (rows * 5000) (third return value of MIWAE.loss with llh_eval, VAE.py:3100); doubles, device.
+ * --------------------------------------------------------------------- */
+enum { PCVAE_MIWAE_HEADS_ENC = 0, PCVAE_MIWAE_HEADS_DEC = 1 };
+int pcvae_miwae_heads(const float* raw, long rows, int width, int mode, float* out0, float* out1, float* out2, void* stream);
+int pcvae_miwae_heads_bwd(const float* raw, long rows, int width, int mode, const float* d0, const float* d1, const float* d2,
+                          float* d_raw, void* stream);
+int pcvae_miwae_sample_z(const float* mean, const float* scale, const float* eps, float* z, int rows, int samples,
+                         int latent_dim, void* stream);
+int pcvae_miwae_sample_z_bwd(const float* d_z, const float* eps, float* d_mean, float* d_scale, int rows, int samples,
+                             int latent_dim, void* stream);
+typedef struct {
+    int rows, samples, obs_dim, latent_dim, regularised;
+    int mask_kind;             /* PCVAE_MASK_U8 (torch.bool bytes; the reference needs bool for `~new_mask`) or _F32 */
+    int rowwise;               /* 0: the reference's reshape (training); 1: every row its own batch (eval_miwae) */
+    const float* x;            /* [B][D] */
+    const void* mask;          /* [B][D] */
+    const void* mask_p;        /* [B][D] (regularised only) */
+    const float* xm[2];        /* [B][S][D] Student-t loc, q and p branch */
+    const float* xs[2];        /* [B][S][D] scale */
+    const float* df[2];        /* [B][S][D] degrees of freedom */
+    const float* mean[2];      /* [B][L] */
+    const float* scale[2];     /* [B][L] */
+    const float* eps2[2];      /* [B][S][L] N(0,1) draws of the loss-internal z (VAE.py:3086-3088, 3218-3220, 3239-3241) */
+    float alpha;
+    void* workspace;           /* pcvae_miwae_loss_workspace_bytes() */
+    size_t workspace_bytes;
+    double* out;               /* [6] */
+    float* xm_imputed;         /* optional [B][D] */
+    float* d_xm[2];            /* optional gradients, NULL = forward only */
+    float* d_xs[2];
+    float* d_df[2];
+    float* d_mean[2];          /* direct terms only (through log p(z) - log q(z|x) and KL_reg) */
+    float* d_scale[2];
+} pcvae_miwae_loss_params;
+size_t pcvae_miwae_loss_workspace_bytes(int rows, int samples);
+int pcvae_miwae_loss(const pcvae_miwae_loss_params* p, void* stream);
+
 /* FP32 FFMA peak probe used by bench.py for the roofline denominator: runs `iters`
  * dependent-chain-free FMA rounds on every SM; returns 0 and the FLOP count in *flops. */
 int pcvae_ffma_probe(float* scratch, int iters, double* flops, void* stream);

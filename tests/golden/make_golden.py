@@ -353,44 +353,150 @@ def mnar_driver_cases(V, E):
     return out
 
 
+def _run_reference_driver(driver, seed=0):
+    """runpy the UNMODIFIED driver file of the reference (CPU), seeds fixed by the harness (the reference sets none),
+    epoch losses captured from its tqdm.write lines."""
+    import runpy
+    import tqdm as tqdm_mod
+    losses = []
+    orig_write, old_argv = tqdm_mod.tqdm.write, sys.argv
+    tqdm_mod.tqdm.write = staticmethod(lambda s, *a, **k: losses.append(float(s.split("Total Loss:")[1])))
+    sys.argv = [driver]
+    try:
+        torch.manual_seed(seed); np.random.seed(seed)
+        runpy.run_path(os.path.join(REF, "src", "experiment_main", driver), run_name="__main__")
+    finally:
+        tqdm_mod.tqdm.write, sys.argv = orig_write, old_argv
+    return torch.tensor(losses)
+
+
+def _template_line():
+    import json
+    return json.loads(open(os.path.join(REF, "Data", "imputation_args.json")).readline())
+
+
+def full_size_driver_cases():
+    """BASELINE.json configs 1 and 3 through the reference's own, unmodified driver FILES on CPU:
+    cfg1  imputation.py on a 506 x 13 table (four model lines in one Data/imputation_args.json, so the RNG stream runs
+          across experiments exactly as in the reference), every scalar artefact recorded;
+    cfg3  imputation.py (training) then active_learning.py on a 2 000 x 20 test set with M = 50: action_CHAI (uint8),
+          the information curve, R_hist_CHAI for the first three acquisition steps on all rows and for every step on
+          every 8th row.  im_CHAI (152 MB) is not stored."""
+    import glob
+    import tempfile
+    sys.path.insert(0, os.path.dirname(HERE))
+    from synth import CFG1, CFG1_MIWAE, CFG3, family_dirs, make_tree, write_args_json
+    out = {}
+    cwd = os.getcwd()
+    fams = ("reg_vae", "vanilla_vae", "reg_EDDI", "vanilla_EDDI", "reg_MIWAE", "vanilla_MIWAE")
+    with tempfile.TemporaryDirectory() as root:                              # MIWAE lines: train() + eval_miwae()
+        c = CFG1_MIWAE
+        make_tree(root, c["data_type"], c["n_rows"], c["obs_dim"], seed=0, missing_rate=c["missing_rate"], test_frac=c["test_frac"])
+        family_dirs(root, c["data_type"], fams)
+        write_args_json(root, _template_line(), c, train_k=c["train_k"], valid_k=c["valid_k"])
+        os.chdir(root)
+        try:
+            losses = _run_reference_driver("imputation.py")
+            files = {os.path.relpath(f, "experiments"): torch.load(f)
+                     for f in glob.glob(os.path.join("experiments", "**", "*.pt"), recursive=True) if "checkpoint" not in f}
+            out["cfg1_miwae"] = dict(epoch_losses=losses, files=files)
+        finally:
+            os.chdir(cwd)
+    with tempfile.TemporaryDirectory() as root:
+        c = CFG1
+        make_tree(root, c["data_type"], c["n_rows"], c["obs_dim"], seed=0, missing_rate=c["missing_rate"], test_frac=c["test_frac"])
+        family_dirs(root, c["data_type"], fams)
+        write_args_json(root, _template_line(), c)
+        os.chdir(root)
+        try:
+            losses = _run_reference_driver("imputation.py")
+            files = {}
+            for f in glob.glob(os.path.join("experiments", "**", "*.pt"), recursive=True):
+                if "checkpoint" in f:
+                    continue
+                files[os.path.relpath(f, "experiments")] = torch.load(f)
+            out["cfg1"] = dict(epoch_losses=losses, files=files)
+        finally:
+            os.chdir(cwd)
+    with tempfile.TemporaryDirectory() as root:
+        c = CFG3
+        make_tree(root, c["data_type"], c["n_rows"], c["obs_dim"], seed=1, missing_rate=c["missing_rate"], test_frac=c["test_frac"],
+                  factors=c["factors"])
+        family_dirs(root, c["data_type"], fams)
+        write_args_json(root, _template_line(), c, M=1)                    # imputation.py: M = eval repeats
+        os.chdir(root)
+        try:
+            losses = _run_reference_driver("imputation.py")
+            write_args_json(root, _template_line(), c)                       # active_learning.py: M = 50 reward samples
+            _run_reference_driver("active_learning.py", seed=1)
+            files = {}
+            for f in glob.glob(os.path.join("experiments", "**", "*.pt"), recursive=True):
+                rel = os.path.relpath(f, "experiments")
+                if "im_CHAI" in f or "checkpoint" in f:
+                    continue
+                t = torch.load(f)
+                if "action_CHAI" in f:
+                    t = t.to(torch.uint8)
+                elif "R_hist_CHAI" in f:                                     # [1, step, row, candidate]
+                    top2 = t[0].topk(2, dim=2).values                        # reference's best-minus-second reward per
+                    files[rel + "#gap"] = (top2[..., 0] - top2[..., 1]).clone()   # (step, row): which selections are decided
+                    files[rel + "#first3"] = t[:, :3].clone()
+                    t = t[:, :, ::8].clone()
+                    rel = rel + "#rows8"
+                elif "information_curve" in f:                               # broadcast over rows: keep row 0
+                    t = t[:, :1].clone()
+                files[rel] = t
+            out["cfg3"] = dict(epoch_losses=losses, files=files)
+        finally:
+            os.chdir(cwd)
+    return out
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     V, E = _import_reference()
     torch.set_num_threads(1)
-    fx = {}
-    fx["reg_vae_b64_d13"] = reg_case(V, "Reg_VAE", 64, 13, 20, 0, 1.0)
-    fx["reg_vae_b37_d20_a05"] = reg_case(V, "Reg_VAE", 37, 20, 20, 1, 0.5)
-    fx["reg_eddi_b64_d13_k20"] = reg_case(V, "Reg_EDDI", 64, 13, 20, 2, 1.0)
-    fx["reg_eddi_b33_d7_k10_a07"] = reg_case(V, "Reg_EDDI", 33, 7, 10, 3, 0.7)
-    fx["vanilla_vae_b64_d13"] = vanilla_case(V, "vanilla_VAE", 64, 13, 20, 4)
-    fx["vanilla_eddi_b64_d13_k20"] = vanilla_case(V, "vanilla_EDDI", 64, 13, 20, 5)
-    fx["traj_reg_vae_b32_d13"] = train_traj_case(V, "Reg_VAE", 32, 13, 20, 6, 4)
-    fx["traj_reg_eddi_b32_d13_k10"] = train_traj_case(V, "Reg_EDDI", 32, 13, 10, 7, 4)
-    fx["reward_reg_vae_n24_d8_m5"] = reward_case(V, E, "Reg_VAE", 24, 8, 20, 5, 8, 3)
-    fx["reward_reg_eddi_n24_d8_k10_m5"] = reward_case(V, E, "Reg_EDDI", 24, 8, 10, 5, 9, 3)
-    fx["mnar_reg_v2_b16_d8_s5"] = mnar_case(V, "REG_notMIWAE_v2", 16, 8, 5, 20, 1.0)
-    fx["mnar_reg_v2_b9_d50_s20_a06"] = mnar_case(V, "REG_notMIWAE_v2", 9, 50, 20, 21, 0.6)
-    fx["mnar_vanilla_b16_d8_s5"] = mnar_case(V, "notMIWAE_myversion", 16, 8, 5, 22, 1.0)
-    # mask-augmented zero-imputation family (VAE.py:510-667, 995-1116): first layer reads [x*mask, mask]
-    fx["reg_vae_mask_b64_d13"] = reg_case(V, "Reg_VAE_mask", 64, 13, 20, 30, 1.0)
-    fx["reg_vae_mask_b37_d20_a05"] = reg_case(V, "Reg_VAE_mask", 37, 20, 20, 31, 0.5)
-    fx["vanilla_vae_mask_b64_d13"] = vanilla_case(V, "vanilla_VAE_mask", 64, 13, 20, 32)
-    fx["traj_reg_vae_mask_b32_d13"] = train_traj_case(V, "Reg_VAE_mask", 32, 13, 20, 33, 4)
-    # MIWAE family (Student-t decoder, importance-weighted bound), VAE.py:3011-3301: oracle pinned ahead of its kernels
-    fx["miwae_b12_d6_s4"] = miwae_case(V, "MIWAE", 12, 6, 4, 40, 1.0)
-    fx["miwae_b7_d9_s5"] = miwae_case(V, "MIWAE", 7, 9, 5, 41, 1.0)
-    fx["reg_miwae_b12_d6_s4"] = miwae_case(V, "Reg_MIWAE", 12, 6, 4, 42, 1.0)
-    fx["reg_miwae_b7_d9_s5_a06"] = miwae_case(V, "Reg_MIWAE", 7, 9, 5, 43, 0.6)
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+
+    class Lazy(dict):                       # name -> fixture; with --only=... the other cases are not even run
+        def __setitem__(self, k, thunk):
+            if not only or k in only:
+                dict.__setitem__(self, k, thunk())
+    fx = Lazy()
+    fx["reg_vae_b64_d13"] = lambda: reg_case(V, "Reg_VAE", 64, 13, 20, 0, 1.0)
+    fx["reg_vae_b37_d20_a05"] = lambda: reg_case(V, "Reg_VAE", 37, 20, 20, 1, 0.5)
+    fx["reg_eddi_b64_d13_k20"] = lambda: reg_case(V, "Reg_EDDI", 64, 13, 20, 2, 1.0)
+    fx["reg_eddi_b33_d7_k10_a07"] = lambda: reg_case(V, "Reg_EDDI", 33, 7, 10, 3, 0.7)
+    fx["vanilla_vae_b64_d13"] = lambda: vanilla_case(V, "vanilla_VAE", 64, 13, 20, 4)
+    fx["vanilla_eddi_b64_d13_k20"] = lambda: vanilla_case(V, "vanilla_EDDI", 64, 13, 20, 5)
+    fx["traj_reg_vae_b32_d13"] = lambda: train_traj_case(V, "Reg_VAE", 32, 13, 20, 6, 4)
+    fx["traj_reg_eddi_b32_d13_k10"] = lambda: train_traj_case(V, "Reg_EDDI", 32, 13, 10, 7, 4)
+    fx["reward_reg_vae_n24_d8_m5"] = lambda: reward_case(V, E, "Reg_VAE", 24, 8, 20, 5, 8, 3)
+    fx["reward_reg_eddi_n24_d8_k10_m5"] = lambda: reward_case(V, E, "Reg_EDDI", 24, 8, 10, 5, 9, 3)
+    fx["mnar_reg_v2_b16_d8_s5"] = lambda: mnar_case(V, "REG_notMIWAE_v2", 16, 8, 5, 20, 1.0)
+    fx["mnar_reg_v2_b9_d50_s20_a06"] = lambda: mnar_case(V, "REG_notMIWAE_v2", 9, 50, 20, 21, 0.6)
+    fx["mnar_vanilla_b16_d8_s5"] = lambda: mnar_case(V, "notMIWAE_myversion", 16, 8, 5, 22, 1.0)
+    # mask-augmented zero-imputation family (VAE.py:510-667, 995-1116): first layer reads [x*mask, mask]
+    fx["reg_vae_mask_b64_d13"] = lambda: reg_case(V, "Reg_VAE_mask", 64, 13, 20, 30, 1.0)
+    fx["reg_vae_mask_b37_d20_a05"] = lambda: reg_case(V, "Reg_VAE_mask", 37, 20, 20, 31, 0.5)
+    fx["vanilla_vae_mask_b64_d13"] = lambda: vanilla_case(V, "vanilla_VAE_mask", 64, 13, 20, 32)
+    fx["traj_reg_vae_mask_b32_d13"] = lambda: train_traj_case(V, "Reg_VAE_mask", 32, 13, 20, 33, 4)
+    # MIWAE family (Student-t decoder, importance-weighted bound), VAE.py:3011-3301: oracle pinned ahead of its kernels
+    fx["miwae_b12_d6_s4"] = lambda: miwae_case(V, "MIWAE", 12, 6, 4, 40, 1.0)
+    fx["miwae_b7_d9_s5"] = lambda: miwae_case(V, "MIWAE", 7, 9, 5, 41, 1.0)
+    fx["reg_miwae_b12_d6_s4"] = lambda: miwae_case(V, "Reg_MIWAE", 12, 6, 4, 42, 1.0)
+    fx["reg_miwae_b7_d9_s5_a06"] = lambda: miwae_case(V, "Reg_MIWAE", 7, 9, 5, 43, 0.6)
     if "--skip-drivers" not in sys.argv:
         from synth import MASK_DRIVER_CASES
         if not only or "drivers_synth_150x6" in only:
-            fx["drivers_synth_150x6"] = driver_cases(V, E)
+            fx["drivers_synth_150x6"] = lambda: driver_cases(V, E)
         if not only or "drivers_mnar_40x6" in only:
-            fx["drivers_mnar_40x6"] = mnar_driver_cases(V, E)
+            fx["drivers_mnar_40x6"] = lambda: mnar_driver_cases(V, E)
         if not only or "drivers_mask_augm_150x6" in only:
             # imputation.py call sequence only: active_learning.py never selects the mask-augmented family
-            fx["drivers_mask_augm_150x6"] = driver_cases(V, E, MASK_DRIVER_CASES, with_al=False)
+            fx["drivers_mask_augm_150x6"] = lambda: driver_cases(V, E, MASK_DRIVER_CASES, with_al=False)
+    if "--skip-drivers" not in sys.argv and (not only or "drivers_full_size" in only):
+        fx["drivers_full_size"] = lambda: full_size_driver_cases()
     for name, d in fx.items():
         if only and name not in only:
             continue

@@ -495,7 +495,139 @@ class notMIWAE_myversion(_NotMIWAEBase):
         return mean, logvar, x_mean, x_logvar
 
 
-IN_SCOPE = {"REG_notMIWAE_v2": REG_notMIWAE_v2, "notMIWAE_myversion": notMIWAE_myversion,
+class _MIWAEBase(nn.Module):
+    """Shared parts of MIWAE / Reg_MIWAE (reference VAE.py:3011-3066, 3137-3195): encoder D -> 128 -> 128 -> 2L (ReLU),
+    mean | softplus scale, S importance samples per row; decoder L -> 128 -> 128 -> 3D (ReLU) with the Student-t heads
+    sigmoid | softplus + 0.001 | softplus + 3.  The dense layers are pcvae::dense ops, heads / sampling / loss the
+    pcvae::miwae_* ops (csrc/pcvae_miwae.cu)."""
+
+    noise = "host"
+
+    def _build(self, obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates):
+        self.obs_dim = obs_dim
+        self.hid_dim = hid_dim
+        self.emb_dim = 10
+        self.num_samples = num_samples
+        self.num_estimates = num_estimates
+        self.latent_dim = latent_dim
+        self.batch_size = training_parameters['batch_size']
+        self.K = K
+        self.obs_std = 0.1
+        self.number_components = 500
+        self.training_paramters = training_parameters
+        self.seq_encoder = nn.Sequential(nn.Linear(obs_dim, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(),
+                                         nn.Linear(128, 2 * latent_dim))
+        self.seq_decoder = nn.Sequential(nn.Linear(latent_dim, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(),
+                                         nn.Linear(128, 3 * obs_dim))
+        self.max_epoch = 2800
+
+    @staticmethod
+    def _dense(layer, h, act, mask=None):
+        """nn.Linear (+ activation) through pcvae::dense; layers wider than the kernel's 128 outputs (the 3D-wide decoder
+        head for D > 42) go in row slices of the weight matrix, concatenated."""
+        W, b = layer.weight, layer.bias
+        if W.shape[0] <= 128:
+            return ops.dense_op(h, W, b, mask, act)
+        parts = [ops.dense_op(h, W[o:o + 128], b[o:o + 128], mask, act) for o in range(0, W.shape[0], 128)]
+        return torch.cat(parts, 1)
+
+    def _stats(self, x, mask):
+        dev = x.device
+        if dev.type != "cuda":
+            raise L.PcvaeError("pcvae modules need CUDA tensors: there is no CPU fallback for this path")
+        h = self._dense(self.seq_encoder[0], x.float().contiguous(), L.ACT_RELU, mask.to(dev).float().contiguous())
+        h = self._dense(self.seq_encoder[2], h, L.ACT_RELU)
+        return ops.miwae_enc_heads_op(self._dense(self.seq_encoder[4], h, L.ACT_NONE))
+
+    def encoder(self, x, mask, sample=True):
+        """VAE.py:3045-3059: (z, mean, scale), each [B, S, L]."""
+        mean, scale = self._stats(x, mask)
+        B, S, Lt = x.shape[0], self.num_samples, self.latent_dim
+        eps = draw_noise_bsl(B, S, Lt, x.device, self.noise) if sample else None
+        z = ops.miwae_sample_z_op(mean, scale, eps, S)
+        return z, mean.unsqueeze(1).expand(B, S, Lt), scale.unsqueeze(1).expand(B, S, Lt)
+
+    def decoder(self, z_int):
+        """VAE.py:3061-3066: (mean, scale, deg_free), each [B, S, D]."""
+        shp = z_int.shape
+        h = self._dense(self.seq_decoder[0], z_int.reshape(-1, shp[-1]).contiguous(), L.ACT_RELU)
+        h = self._dense(self.seq_decoder[2], h, L.ACT_RELU)
+        xm, xs, df = ops.miwae_dec_heads_op(self._dense(self.seq_decoder[4], h, L.ACT_NONE))
+        v = lambda t: t.view(*shp[:-1], self.obs_dim)
+        return v(xm), v(xs), v(df)
+
+    @staticmethod
+    def _row_stats(t):
+        return t[:, 0, :].contiguous() if t.dim() == 3 else t
+
+    def _miwae_loss(self, x, mask, mask_p, q, p, alpha, llh_eval, MI, rowwise=False):
+        if MI:
+            raise NotImplementedError("the MI branch of the MIWAE losses references undefined names in the reference "
+                                      "(VAE.py:3101-3107) and cannot run there either")
+        xm_q, xs_q, df_q, mean_q, scale_q = q
+        dev = xm_q.device
+        B, S = xm_q.shape[0], xm_q.shape[1]
+        reg = mask_p is not None
+        # the loss draws its own z ~ q(z|x) for log p(z) - log q(z|x) (VAE.py:3086-3088; Reg: q first, then p, :3218-3241)
+        eps2_q = draw_noise_bsl(B, S, self.latent_dim, dev, self.noise)
+        eps2_p = draw_noise_bsl(B, S, self.latent_dim, dev, self.noise) if reg else None
+        want = torch.is_grad_enabled() and (xm_q.requires_grad or mean_q.requires_grad)
+        c = lambda t: None if t is None else t.contiguous()
+        rs = lambda t: None if t is None else self._row_stats(t)
+        xm_p, xs_p, df_p, mean_p, scale_p = p if reg else (None,) * 5
+        out = ops.miwae_loss_op(x.to(dev).float().contiguous(), mask.to(dev).contiguous(),
+                                None if mask_p is None else mask_p.to(dev).contiguous(), c(xm_q), c(xs_q), c(df_q),
+                                rs(mean_q), rs(scale_q), eps2_q, c(xm_p), c(xs_p), c(df_p), rs(mean_p), rs(scale_p), eps2_p,
+                                float(alpha), bool(rowwise), want, bool(llh_eval))
+        loss, stats, xm_imp = out[0], out[1], out[2]
+        if llh_eval:
+            return xm_imp, loss, (loss if reg else stats[5].float())
+        return loss, loss
+
+
+class MIWAE(_MIWAEBase):
+    """Reference VAE.py:3011-3134."""
+
+    def __init__(self, obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates):
+        super().__init__()
+        self._build(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
+
+    def loss(self, x, x_mean, x_scale, deg_free, mean, scale, mask, epoch, vae_elbo=False, llh_eval=False,
+             MI=False,
+             beta_annealing=True, beta=1.0, stage='train', rowwise=False):
+        return self._miwae_loss(x, mask, None, (x_mean, x_scale, deg_free, mean, scale), None, 1.0, llh_eval, MI, rowwise)
+
+    def forward(self, data, mask):
+        z, mean, scale = self.encoder(data, mask)
+        x_mean, x_scale, deg_free = self.decoder(z)
+        return mean, scale, x_mean, x_scale, deg_free
+
+
+class Reg_MIWAE(_MIWAEBase):
+    """Reference VAE.py:3137-3301."""
+
+    def __init__(self, obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates):
+        super().__init__()
+        self._build(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
+
+    def loss(self, x, x_mean_p, x_scale_p, deg_free_p, mean_p, scale_p, x_mean_q, x_scale_q, deg_free_q, mean_q,
+             scale_q, mask, mask_p, epoch, vae_elbo=False, llh_eval=False,
+             MI=False,
+             beta_annealing=True, beta=1.0, alpha=1.0, stage='train', rowwise=False):
+        return self._miwae_loss(x, mask, mask_p, (x_mean_q, x_scale_q, deg_free_q, mean_q, scale_q),
+                                (x_mean_p, x_scale_p, deg_free_p, mean_p, scale_p), alpha, llh_eval, MI, rowwise)
+
+    def forward(self, data, mask, mask_p, stage='train'):
+        """VAE.py:3296-3301: q branch first (its noise is drawn first), 10-tuple p-first."""
+        z_q, mean_q, scale_q = self.encoder(data, mask)
+        x_mean_q, x_scale_q, deg_free_q = self.decoder(z_q)
+        z_p, mean_p, scale_p = self.encoder(data, mask_p)
+        x_mean_p, x_scale_p, deg_free_p = self.decoder(z_p)
+        return mean_p, scale_p, x_mean_p, x_scale_p, deg_free_p, mean_q, scale_q, x_mean_q, x_scale_q, deg_free_q
+
+
+IN_SCOPE = {"REG_notMIWAE_v2": REG_notMIWAE_v2, "notMIWAE_myversion": notMIWAE_myversion, "MIWAE": MIWAE,
+            "Reg_MIWAE": Reg_MIWAE,
             "Reg_VAE": Reg_VAE, "vanilla_VAE": vanilla_VAE, "Reg_EDDI": Reg_EDDI, "vanilla_EDDI": vanilla_EDDI,
             "Reg_VAE_mask": Reg_VAE_mask, "vanilla_VAE_mask": vanilla_VAE_mask}
 
@@ -511,6 +643,6 @@ def _out_of_scope(name):
 
 
 # names src/utils/loaders.py:2-5 imports; the out-of-scope ones fail loudly when instantiated
-for _n in ("Flow", "MIWAE", "Reg_MIWAE", "notMIWAE", "REG_notMIWAE",
+for _n in ("Flow", "notMIWAE", "REG_notMIWAE",
            "REG_notMIWAE_new_version", "REG_VAEFlow", "VAEFlow", "vanilla_EDDI_mnist", "Reg_EDDI_mnist"):
     globals()[_n] = _out_of_scope(_n)

@@ -20,13 +20,28 @@ def row_block(n_rows: int, world_size: int, rank: int):
     return (rank * n_rows) // world_size, ((rank + 1) * n_rows) // world_size
 
 
+def all_reduce_sum(t: torch.Tensor, group):
+    """In-place sum over the ranks.  NCCL reduces device tensors directly; a gloo group (CPU tests, or several ranks
+    sharing one GPU) takes the tensor through host memory."""
+    import torch.distributed as dist
+    if t.is_cuda and dist.get_backend(group) == "gloo":
+        h = t.cpu()
+        dist.all_reduce(h, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, group=group)
+    return t
+
+
 def merge_row_blocks(t: torch.Tensor, group, device=None):
     """Every rank holds `t` with only its own row block filled (zeros elsewhere): all-reduce(sum) is a gather."""
     import torch.distributed as dist
-    buf = t.to(device) if device is not None else t
+    if dist.get_backend(group) == "gloo" or device is None:
+        dist.all_reduce(t, group=group)
+        return t
+    buf = t.to(device)
     dist.all_reduce(buf, group=group)
-    if buf is not t:
-        t.copy_(buf.cpu())
+    t.copy_(buf.cpu())
     return t
 
 

@@ -16,7 +16,7 @@ import torch
 
 from . import lib as L
 from . import ops
-from .dist import merge_row_blocks, row_block, world
+from .dist import all_reduce_sum, merge_row_blocks, row_block, world
 from .loaders import model_loader
 from .utils import create_missing_uci
 from .VAE import draw_noise
@@ -47,6 +47,11 @@ def eval_vae(list_loaders, missing_rate, obs_dim, hid_dim, K, M, latent_dim, dat
                              max_epochs, valid_k, num_estimates, experiment_type, reg_type, vae_type, alpha=alpha,
                              p_missingness=p_missingness)
         model.to(device)
+        if not hasattr(model, 'flat_theta'):
+            # the reference's else-branch (evaluate.py:218-231) would also take importance-sampling models here; its
+            # drivers never do (imputation.py:40-59 sends MIWAE types to eval_miwae, imputation_mnar.py to eval_vae_mnar)
+            raise NotImplementedError(f"eval_vae: vae_type {vae_type!r} is an importance-sampling model; use eval_miwae "
+                                      "(MIWAE / Reg_MIWAE) or eval_vae_mnar (not-MIWAE)")
         regularised = 'reg' in vae_type
         theta = model.flat_theta()
         eng = ops.engine(model.FAMILY, obs_dim, model._emb(), device)
@@ -88,6 +93,94 @@ def eval_vae(list_loaders, missing_rate, obs_dim, hid_dim, K, M, latent_dim, dat
                 torch.save(out[key], _result_path(kind, experiment_type, data_type, vae_type,
                                                   f'{loader_stage}_{vae_type}{suffix}', missing_rate, alpha,
                                                   p_missingness, reg_type))
+        return results
+
+
+class _NoiseQueue:
+    """Stand-in for a model's `noise` mode that hands out pre-drawn [rows, S, L] tensors in call order."""
+
+    def __init__(self, tensors):
+        self.tensors, self.i = list(tensors), 0
+
+    def __call__(self, rows, samples, latent, device):
+        t = self.tensors[self.i]
+        self.i += 1
+        assert t.shape == (rows, samples, latent), (t.shape, rows, samples, latent)
+        return t.to(device, non_blocking=True)
+
+
+def eval_miwae(list_loaders, missing_rate, obs_dim, hid_dim, K, M, latent_dim, data_type, training_parameters,
+               experiment_type, vae_type, max_epochs, valid_k, num_estimates, device=torch.device('cpu'), alpha=0.5,
+               stage='evaluate', p_missingness=30, reg_type='ml_reg', beta=1.0, beta_annealing=False,
+               alpha_annealing=True):
+    """Importance-weighted imputation RMSE of MIWAE / Reg_MIWAE (reference evaluate.py:72-133).  The reference calls
+    forward + loss(llh_eval=True) once per ROW with S = valid_k samples; here the rows of a batch go through the
+    kernels in blocks with `rowwise` semantics (every row its own batch, which is what the per-row calls amount to:
+    the [B*S] -> [S, B] reshape of VAE.py:3078-3081 is the identity for B = 1).  In parity mode the host noise is
+    drawn row by row in the reference's order (Reg: eps_q, eps_p of forward, then the two loss-internal draws;
+    vanilla: eps, then the loss-internal draw), so a seeded run consumes the RNG exactly like the reference."""
+    device = torch.device(device)
+    with torch.no_grad():
+        model = model_loader('test', obs_dim, hid_dim, K, latent_dim, missing_rate, data_type, training_parameters,
+                             max_epochs, valid_k, num_estimates, experiment_type, reg_type, vae_type, alpha=alpha,
+                             p_missingness=p_missingness)
+        model.to(device)
+        reg = 'reg_MIWAE' in vae_type
+        S, Lt = model.num_samples, latent_dim
+        n_draws = 4 if reg else 2
+        results = {}
+        throughput = os.environ.get('PCVAE_MODE', 'parity') == 'throughput'
+        for loader, loader_stage in list_loaders:
+            recon = []
+            for _ in range(M):
+                XM = []
+                for data_sample, mask in loader:
+                    data_sample, mask = data_sample.to(device), mask.to(device)
+                    B = data_sample.shape[0]
+                    temp_mask = create_missing_uci(data_sample.shape, p_missingness)      # evaluate.py:94, per batch
+                    mask_p = mask * temp_mask.to(device)
+                    temp_XM = torch.zeros(B, obs_dim, device=device)
+                    block = max(1, (1 << 18) // max(S, 1))                                # ~256k decoder rows per block
+                    for lo in range(0, B, block):
+                        hi = min(B, lo + block)
+                        if throughput:
+                            model.noise = 'device'
+                        else:
+                            draws = [[] for _ in range(n_draws)]
+                            for _i in range(lo, hi):
+                                for d in draws:
+                                    d.append(torch.empty(1, S, Lt).normal_())
+                            model.noise = _NoiseQueue([torch.cat(d) for d in draws])
+                        try:
+                            xb, mb = data_sample[lo:hi], mask[lo:hi]
+                            if reg:
+                                out = model.forward(xb, mb, mask_p[lo:hi])
+                                (mean_p, scale_p, x_mean_p, x_scale_p, deg_free_p, mean_q, scale_q, x_mean_q, x_scale_q,
+                                 deg_free_q) = out
+                                xm, _, _ = model.loss(xb, x_mean_p, x_scale_p, deg_free_p, mean_p, scale_p, x_mean_q,
+                                                      x_scale_q, deg_free_q, mean_q, scale_q, mb, mask_p[lo:hi], 1,
+                                                      llh_eval=True, beta_annealing=beta_annealing, beta=beta, alpha=alpha,
+                                                      rowwise=True)
+                            else:
+                                mean, scale, x_mean, x_scale, deg_free = model.forward(xb, mb)
+                                xm, _, _ = model.loss(xb, x_mean, x_scale, deg_free, mean, scale, mb, max_epochs,
+                                                      llh_eval=True, beta_annealing=beta_annealing, beta=beta, rowwise=True)
+                        finally:
+                            model.noise = 'host'
+                        temp_XM[lo:hi] = xm
+                    miss = ~mask.bool()
+                    XM.append(torch.sqrt(torch.sum(torch.square(temp_XM * miss - data_sample.view(-1, obs_dim) * miss))
+                                         / torch.sum(miss)))
+                recon.append(torch.stack(XM).mean())
+            recon = torch.stack(recon).mean().cpu()
+            results[loader_stage] = recon
+            base = os.path.join('experiments', experiment_type, data_type, 'rest', _family_dir(vae_type))
+            os.makedirs(base, exist_ok=True)
+            if 'vanilla' in vae_type:
+                fname = f'{loader_stage}_{vae_type}_rmse_50_missing_rate_test.pt'
+            else:
+                fname = f'{loader_stage}_{vae_type}_rmse_{alpha}_{p_missingness}_{reg_type}_full_reg_50_missing_rate_test.pt'
+            torch.save(recon, os.path.join(base, fname))
         return results
 
 
@@ -201,10 +294,12 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                 return torch.stack(outs, 0)
 
             def target_mse(im):
-                se = ((im[:, :, -1] - target.unsqueeze(0)) ** 2).sum(1)          # [M] local sums
+                # [M] sums of squared errors over this rank's rows, accumulated in float64 so that the total does not
+                # depend on how the rows are split over the ranks (fp32 squares add exactly enough in fp64)
+                se = ((im[:, :, -1] - target.unsqueeze(0)) ** 2).double().sum(1)
                 if world_size > 1:
-                    torch.distributed.all_reduce(se, group=group)
-                return (se / n_test).mean()                                       # mean over rows, then over M
+                    all_reduce_sum(se, group)
+                return (se / n_test).float().mean()                               # mean over rows, then over M
 
             info[r, :, 0] = target_mse(sample_means()).cpu()
             for t in range(C):
@@ -219,7 +314,7 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                     # draws per candidate (evaluate.py:562-626); burn them so the next `im` sees the same RNG state
                     unsel = (mask[:, :C] == 0).sum(0)
                     if world_size > 1:
-                        torch.distributed.all_reduce(unsel, group=group)
+                        all_reduce_sum(unsel, group)
                     for cnt in unsel.cpu().tolist():
                         for _ in range(4 * M):
                             torch.empty(int(cnt), latent_dim).normal_()

@@ -62,9 +62,6 @@ def install():
     for missing in ("data_loader_mnist",):
         if not hasattr(loaders, missing):
             setattr(loaders, missing, _ais_unavailable)
-    for missing in ("eval_miwae",):
-        if not hasattr(evaluate, missing):
-            setattr(evaluate, missing, _ais_unavailable)
     return mods
 
 

@@ -453,6 +453,94 @@ def mnar_loss(x, mask, mask_p, xm, xlv, mean, logvar, W, b, alpha, regularised, 
     return dict(out=out, xm_imputed=xm_imp, d_xm=d_xm, d_xlv=d_xlv, d_mean=d_mean, d_logvar=d_logvar, d_W=d_W, d_b=d_b)
 
 
+# ------------------------------------------------------------------------------------------------
+# MIWAE / Reg_MIWAE pieces (Student-t decoder + importance-weighted bound), reference VAE.py:3011-3301
+# ------------------------------------------------------------------------------------------------
+
+def miwae_heads(raw, mode):
+    """Encoder heads (mode ENC): raw [R, 2W] -> (mean, softplus); decoder heads (mode DEC): raw [R, 3W] ->
+    (sigmoid, softplus + 0.001, softplus + 3).  VAE.py:3047-3049, 3061-3066."""
+    _need_cuda(raw)
+    raw = _f32(raw)
+    C_ = 2 if mode == L.MIWAE_HEADS_ENC else 3
+    R, W = raw.shape[0], raw.shape[1] // C_
+    outs = [torch.empty(R, W, device=raw.device, dtype=torch.float32) for _ in range(C_)]
+    with torch.cuda.device(raw.device):
+        L.check(L.load().pcvae_miwae_heads(_p(raw), R, W, mode, _p(outs[0]), _p(outs[1]), _p(outs[2]) if C_ == 3 else None,
+                                           _stream()), "pcvae_miwae_heads")
+    return outs
+
+
+def miwae_heads_bwd(raw, mode, grads):
+    raw = _f32(raw)
+    C_ = 2 if mode == L.MIWAE_HEADS_ENC else 3
+    R, W = raw.shape[0], raw.shape[1] // C_
+    g = [None if t is None else _f32(t) for t in grads] + [None] * (3 - len(grads))
+    d_raw = torch.empty_like(raw)
+    with torch.cuda.device(raw.device):
+        L.check(L.load().pcvae_miwae_heads_bwd(_p(raw), R, W, mode, _p(g[0]), _p(g[1]), _p(g[2]), _p(d_raw), _stream()),
+                "pcvae_miwae_heads_bwd")
+    return d_raw
+
+
+def miwae_sample_z(mean, scale, eps, samples):
+    """z[b,s,:] = mean[b] + scale[b] * eps[b,s]; eps None -> z = mean (sample=False).  VAE.py:3050-3058."""
+    _need_cuda(mean, scale)
+    mean, scale = _f32(mean), _f32(scale)
+    eps = None if eps is None else _f32(eps)
+    B, Lt = mean.shape
+    z = torch.empty(B, samples, Lt, device=mean.device, dtype=torch.float32)
+    with torch.cuda.device(mean.device):
+        L.check(L.load().pcvae_miwae_sample_z(_p(mean), _p(scale), _p(eps), _p(z), B, samples, Lt, _stream()),
+                "pcvae_miwae_sample_z")
+    return z
+
+
+def miwae_sample_z_bwd(d_z, eps):
+    d_z = _f32(d_z)
+    eps = None if eps is None else _f32(eps)
+    B, S, Lt = d_z.shape
+    d_mean = torch.empty(B, Lt, device=d_z.device, dtype=torch.float32)
+    d_scale = torch.empty_like(d_mean)
+    with torch.cuda.device(d_z.device):
+        L.check(L.load().pcvae_miwae_sample_z_bwd(_p(d_z), _p(eps), _p(d_mean), _p(d_scale), B, S, Lt, _stream()),
+                "pcvae_miwae_sample_z_bwd")
+    return d_mean, d_scale
+
+
+def miwae_loss(x, mask, mask_p, xm, xs, df, mean, scale, eps2, alpha, regularised, rowwise=False, want_grads=False,
+               want_imputed=False):
+    """MIWAE.loss / Reg_MIWAE.loss (VAE.py:3068-3110, 3197-3263).  xm / xs / df / mean / scale / eps2 are lists over the
+    branches (q[, p]).  Returns dict(out=[loss, nb_q, nb_p, kl_reg, reg_like, imp] float64, xm_imputed, gradients)."""
+    _need_cuda(x, *xm)
+    x = _f32(x)
+    nb = 2 if regularised else 1
+    kind, masks = prep_masks([mask, mask_p] if regularised else [mask])
+    xm, xs, df = [_f32(t) for t in xm[:nb]], [_f32(t) for t in xs[:nb]], [_f32(t) for t in df[:nb]]
+    mean, scale, eps2 = [_f32(t) for t in mean[:nb]], [_f32(t) for t in scale[:nb]], [_f32(t) for t in eps2[:nb]]
+    B, S, D = xm[0].shape
+    Lt = mean[0].shape[1]
+    dev = x.device
+    lib = L.load()
+    nbytes = lib.pcvae_miwae_loss_workspace_bytes(B, S)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    out = torch.empty(6, device=dev, dtype=torch.float64)
+    xm_imp = torch.empty(B, D, device=dev) if want_imputed else None
+    g = lambda like: [torch.empty_like(t) for t in like] if want_grads else [None] * nb
+    d_xm, d_xs, d_df, d_mean, d_scale = g(xm), g(xs), g(df), g(mean), g(scale)
+    pad = lambda ts: list(ts) + [None] * (2 - len(ts))
+    p = L.MiwaeLossParams(rows=B, samples=S, obs_dim=D, latent_dim=Lt, regularised=int(regularised), mask_kind=kind,
+                          rowwise=int(rowwise), x=_p(x), mask=_p(masks[0]), mask_p=_p(masks[1]) if regularised else None,
+                          xm=_pair(pad(xm)), xs=_pair(pad(xs)), df=_pair(pad(df)), mean=_pair(pad(mean)),
+                          scale=_pair(pad(scale)), eps2=_pair(pad(eps2)), alpha=float(alpha), workspace=_p(ws),
+                          workspace_bytes=nbytes, out=_p(out), xm_imputed=_p(xm_imp), d_xm=_pair(pad(d_xm)),
+                          d_xs=_pair(pad(d_xs)), d_df=_pair(pad(d_df)), d_mean=_pair(pad(d_mean)),
+                          d_scale=_pair(pad(d_scale)))
+    with torch.cuda.device(dev):
+        L.check(lib.pcvae_miwae_loss(C.byref(p), _stream()), "pcvae_miwae_loss")
+    return dict(out=out, xm_imputed=xm_imp, d_xm=d_xm, d_xs=d_xs, d_df=d_df, d_mean=d_mean, d_scale=d_scale)
+
+
 def loss_from_sums(sums: torch.Tensor, rows: int, alpha: float, beta_w: float, regularised: bool):
     """train_loss = L / B with L as in VAE.py:441-452 (device tensor, float64)."""
     loss_q = sums[L.S_RE_Q] + beta_w * sums[L.S_KL_Q]

@@ -31,7 +31,8 @@ SYMBOLS = [
     "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events", "pcvae_prep_packed",
     "pcvae_dp_exchange_bytes", "pcvae_dp_exchange_alloc", "pcvae_dp_exchange_open", "pcvae_dp_exchange_close",
     "pcvae_dp_exchange_free", "pcvae_dp_reduce_adam", "pcvae_prep_batch_dev", "pcvae_reduce_adam_dev",
-    "pcvae_dp_reduce_adam_emulated",
+    "pcvae_dp_reduce_adam_emulated", "pcvae_miwae_heads", "pcvae_miwae_heads_bwd", "pcvae_miwae_sample_z",
+    "pcvae_miwae_sample_z_bwd", "pcvae_miwae_loss_workspace_bytes", "pcvae_miwae_loss",
 ]
 
 
@@ -121,6 +122,18 @@ class MnarLossParams(C.Structure):
                 ("d_logvar", _P2), ("d_W", C.c_void_p), ("d_b", C.c_void_p)]
 
 
+class MiwaeLossParams(C.Structure):
+    """pcvae_miwae_loss_params (include/pcvae_b200.h)."""
+    _fields_ = [("rows", C.c_int), ("samples", C.c_int), ("obs_dim", C.c_int), ("latent_dim", C.c_int),
+                ("regularised", C.c_int), ("mask_kind", C.c_int), ("rowwise", C.c_int), ("x", C.c_void_p),
+                ("mask", C.c_void_p), ("mask_p", C.c_void_p), ("xm", _P2), ("xs", _P2), ("df", _P2), ("mean", _P2),
+                ("scale", _P2), ("eps2", _P2), ("alpha", C.c_float), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t), ("out", C.c_void_p), ("xm_imputed", C.c_void_p), ("d_xm", _P2),
+                ("d_xs", _P2), ("d_df", _P2), ("d_mean", _P2), ("d_scale", _P2)]
+
+
+MIWAE_HEADS_ENC, MIWAE_HEADS_DEC = 0, 1
+
 _lib = None
 
 
@@ -198,6 +211,16 @@ def load():
     lib.pcvae_mnar_loss_workspace_bytes.restype = C.c_size_t
     lib.pcvae_mnar_loss_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.pcvae_mnar_loss.argtypes = [C.POINTER(MnarLossParams), C.c_void_p]
+    lib.pcvae_miwae_heads.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pcvae_miwae_heads_bwd.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+    lib.pcvae_miwae_sample_z.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p]
+    lib.pcvae_miwae_sample_z_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p]
+    lib.pcvae_miwae_loss_workspace_bytes.restype = C.c_size_t
+    lib.pcvae_miwae_loss_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    lib.pcvae_miwae_loss.argtypes = [C.POINTER(MiwaeLossParams), C.c_void_p]
     lib.pcvae_ffma_probe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     _lib = lib
     return lib

@@ -6,10 +6,10 @@ import torch
 from numpy import loadtxt
 from torch.utils.data import DataLoader
 
-from .VAE import (REG_notMIWAE_v2, Reg_EDDI, Reg_VAE, Reg_VAE_mask, notMIWAE_myversion, vanilla_EDDI, vanilla_VAE,
-                  vanilla_VAE_mask)
+from .VAE import (MIWAE, REG_notMIWAE_v2, Reg_EDDI, Reg_MIWAE, Reg_VAE, Reg_VAE_mask, notMIWAE_myversion, vanilla_EDDI,
+                  vanilla_VAE, vanilla_VAE_mask)
 
-_OUT_OF_SCOPE = ("flow", "reg_MIWAE")
+_OUT_OF_SCOPE = ("flow",)
 
 
 def _strip_digits(s):
@@ -49,6 +49,9 @@ def model_loader(stage, obs_dim, hid_dim, K, latent_dim, missing_rate, data_type
         model = Reg_EDDI(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, reg_type, num_samples,
                          num_estimates)
         load_dir = _strip_digits(vae_type)
+    elif 'reg_MIWAE' in vae_type:                                                    # loaders.py:135-147
+        model = Reg_MIWAE(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
+        load_dir = _strip_digits(vae_type)
     elif 'vanilla_vae' in vae_type:
         cls = vanilla_VAE_mask if 'mask_augm' in vae_type else vanilla_VAE          # loaders.py:149-184
         model = cls(obs_dim, hid_dim, K, latent_dim, training_parameters, experiment_type, num_samples,
@@ -63,8 +66,9 @@ def model_loader(stage, obs_dim, hid_dim, K, latent_dim, missing_rate, data_type
     elif 'vanilla_notMIWAE' in vae_type:
         model = notMIWAE_myversion(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
         load_dir = _strip_digits(vae_type)
-    else:
-        raise NotImplementedError(f"vae_type {vae_type!r}: MIWAE (Student-t) is outside the B200 hot path")
+    else:                                                                            # loaders.py:234-245: everything else is MIWAE
+        model = MIWAE(obs_dim, hid_dim, K, latent_dim, training_parameters, num_samples, num_estimates)
+        load_dir = _strip_digits(vae_type)
     if stage == 'train':
         print("Initializing fresh model")
     else:

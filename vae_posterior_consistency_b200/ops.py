@@ -349,3 +349,153 @@ def _mnar_backward(ctx, d_loss, *unused):
 
 
 torch.library.register_autograd("pcvae::mnar_loss", _mnar_backward, setup_context=_mnar_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# MIWAE / Reg_MIWAE pieces (reference VAE.py:3011-3301)
+# ------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("pcvae::miwae_enc_heads", mutates_args=())
+def miwae_enc_heads_op(raw: Tensor) -> Tuple[Tensor, Tensor]:
+    """(mean, scale = softplus) from the encoder's raw [B, 2L] output, VAE.py:3047-3049."""
+    o = KR.miwae_heads(raw, L.MIWAE_HEADS_ENC)
+    return o[0], o[1]
+
+
+@miwae_enc_heads_op.register_fake
+def _(raw):
+    W = raw.shape[1] // 2
+    return raw.new_empty(raw.shape[0], W), raw.new_empty(raw.shape[0], W)
+
+
+@torch.library.custom_op("pcvae::miwae_dec_heads", mutates_args=())
+def miwae_dec_heads_op(raw: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """(sigmoid, softplus + 0.001, softplus + 3) from the decoder's raw [R, 3D] output, VAE.py:3061-3066."""
+    o = KR.miwae_heads(raw, L.MIWAE_HEADS_DEC)
+    return o[0], o[1], o[2]
+
+
+@miwae_dec_heads_op.register_fake
+def _(raw):
+    W = raw.shape[1] // 3
+    return tuple(raw.new_empty(raw.shape[0], W) for _ in range(3))
+
+
+@torch.library.custom_op("pcvae::miwae_heads_bwd", mutates_args=())
+def miwae_heads_bwd_op(raw: Tensor, mode: int, d0: Optional[Tensor], d1: Optional[Tensor], d2: Optional[Tensor]) -> Tensor:
+    return KR.miwae_heads_bwd(raw, mode, [d0, d1, d2])
+
+
+@miwae_heads_bwd_op.register_fake
+def _(raw, mode, d0, d1, d2):
+    return torch.empty_like(raw)
+
+
+def _heads_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+def _enc_heads_backward(ctx, d0, d1):
+    (raw,) = ctx.saved_tensors
+    return miwae_heads_bwd_op(raw, L.MIWAE_HEADS_ENC, _c(d0), _c(d1), None)
+
+
+def _dec_heads_backward(ctx, d0, d1, d2):
+    (raw,) = ctx.saved_tensors
+    return miwae_heads_bwd_op(raw, L.MIWAE_HEADS_DEC, _c(d0), _c(d1), _c(d2))
+
+
+torch.library.register_autograd("pcvae::miwae_enc_heads", _enc_heads_backward, setup_context=_heads_setup)
+torch.library.register_autograd("pcvae::miwae_dec_heads", _dec_heads_backward, setup_context=_heads_setup)
+
+
+@torch.library.custom_op("pcvae::miwae_sample_z", mutates_args=())
+def miwae_sample_z_op(mean: Tensor, scale: Tensor, eps: Optional[Tensor], samples: int) -> Tensor:
+    """z [B,S,L] = mean + scale * eps (Normal(mean, scale).rsample()), VAE.py:3050-3058."""
+    return KR.miwae_sample_z(mean, scale, eps, samples)
+
+
+@miwae_sample_z_op.register_fake
+def _(mean, scale, eps, samples):
+    return mean.new_empty(mean.shape[0], samples, mean.shape[1])
+
+
+@torch.library.custom_op("pcvae::miwae_sample_z_bwd", mutates_args=())
+def miwae_sample_z_bwd_op(d_z: Tensor, eps: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    return KR.miwae_sample_z_bwd(d_z, eps)
+
+
+@miwae_sample_z_bwd_op.register_fake
+def _(d_z, eps):
+    return d_z.new_empty(d_z.shape[0], d_z.shape[2]), d_z.new_empty(d_z.shape[0], d_z.shape[2])
+
+
+def _msz_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[2])
+    ctx.has_eps = inputs[2] is not None
+
+
+def _msz_backward(ctx, d_z):
+    (eps,) = ctx.saved_tensors if ctx.has_eps else (None,)
+    dm, ds = miwae_sample_z_bwd_op(d_z.contiguous(), eps)
+    return dm, (ds if ctx.has_eps else None), None, None
+
+
+torch.library.register_autograd("pcvae::miwae_sample_z", _msz_backward, setup_context=_msz_setup)
+
+
+@torch.library.custom_op("pcvae::miwae_loss", mutates_args=())
+def miwae_loss_op(x: Tensor, mask: Tensor, mask_p: Optional[Tensor], xm_q: Tensor, xs_q: Tensor, df_q: Tensor,
+                  mean_q: Tensor, scale_q: Tensor, eps2_q: Tensor, xm_p: Optional[Tensor], xs_p: Optional[Tensor],
+                  df_p: Optional[Tensor], mean_p: Optional[Tensor], scale_p: Optional[Tensor], eps2_p: Optional[Tensor],
+                  alpha: float, rowwise: bool, want_grads: bool, want_imputed: bool
+                  ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor,
+                             Tensor]:
+    """(loss fp32, out[6] f64, xm_imputed, then the gradients of the loss w.r.t. xm_q, xs_q, df_q, mean_q, scale_q, xm_p,
+    xs_p, df_p, mean_p, scale_p).  MIWAE.loss / Reg_MIWAE.loss, VAE.py:3068-3110 / 3197-3263."""
+    reg = mask_p is not None
+    br = lambda q, p_: [q, p_] if reg else [q]
+    r = KR.miwae_loss(x, mask, mask_p, br(xm_q, xm_p), br(xs_q, xs_p), br(df_q, df_p), br(mean_q, mean_p),
+                      br(scale_q, scale_p), br(eps2_q, eps2_p), alpha, reg, rowwise=rowwise, want_grads=want_grads,
+                      want_imputed=want_imputed)
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    loss = r["out"][0].to(torch.float32)
+    g = [e() for _ in range(10)]
+    if want_grads:
+        g[:5] = [r["d_xm"][0], r["d_xs"][0], r["d_df"][0], r["d_mean"][0], r["d_scale"][0]]
+        if reg:
+            g[5:] = [r["d_xm"][1], r["d_xs"][1], r["d_df"][1], r["d_mean"][1], r["d_scale"][1]]
+    return (loss, r["out"], e() if r["xm_imputed"] is None else r["xm_imputed"], *g)
+
+
+@miwae_loss_op.register_fake
+def _(x, mask, mask_p, xm_q, xs_q, df_q, mean_q, scale_q, eps2_q, xm_p, xs_p, df_p, mean_p, scale_p, eps2_p, alpha, rowwise,
+      want_grads, want_imputed):
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    return (x.new_empty((), dtype=torch.float32), x.new_empty(6, dtype=torch.float64),
+            torch.empty_like(x) if want_imputed else e(), *[e() for _ in range(10)])
+
+
+def _miwae_setup(ctx, inputs, output):
+    ctx.reg = inputs[2] is not None
+    ctx.has_grads = inputs[17]
+    ctx.save_for_backward(*output[3:])
+
+
+def _miwae_backward(ctx, d_loss, *unused):
+    if not ctx.has_grads:
+        raise RuntimeError("pcvae::miwae_loss was run with want_grads=False")
+    g = ctx.saved_tensors
+    sc = lambda t: t * d_loss
+    out = [None] * 19
+    out[3], out[4], out[5], out[6], out[7] = sc(g[0]), sc(g[1]), sc(g[2]), sc(g[3]), sc(g[4])
+    if ctx.reg:
+        out[9], out[10], out[11], out[12], out[13] = sc(g[5]), sc(g[6]), sc(g[7]), sc(g[8]), sc(g[9])
+    return tuple(out)
+
+
+torch.library.register_autograd("pcvae::miwae_loss", _miwae_backward, setup_context=_miwae_setup)

@@ -42,14 +42,18 @@ def _save(model, experiment_type, data_type, vae_type, missing_rate, alpha, p_mi
     return path
 
 
-def _epoch_batches(loader, device, throughput, prep=None):
-    """Yield (x, mask) batches on `device` in the order the reference's DataLoader would.  In throughput mode with
+def _epoch_batches(loader, device, throughput, prep=None, world_size=1, rank=0):
+    """Yield (x, mask, global_rows) batches on `device` in the order the reference's DataLoader would; under data
+    parallelism every rank gets ITS row block of each global batch (dist.row_block) and `global_rows` is the size of the
+    whole batch.  In throughput mode the rank slices the sampler's index list first and gathers only its own rows; with
     `prep` = dict(keep=..., n_eps=..., step=...) and a shape pcvae_prep_batch takes, the sub-mask and the noise of the
     step are drawn by the same launch and left in prep['mask_p'] / prep['eps']."""
     table = getattr(loader, 'pcvae_table', None)
     if not throughput or table is None or not table[0].is_cuda:
         for data_sample, mask in loader:
-            yield data_sample.to(device), mask.to(device)
+            n = data_sample.shape[0]
+            lo, hi = row_block(n, world_size, rank)
+            yield data_sample[lo:hi].to(device), mask[lo:hi].to(device), n
         return
     # same RNG consumption as iter(DataLoader): base seed first (dataloader.py), then the sampler's own seed
     torch.empty((), dtype=torch.int64).random_()
@@ -59,7 +63,9 @@ def _epoch_batches(loader, device, throughput, prep=None):
     mask_src = mask if kind == L.MASK_U8 else mask.float()
     D = data.shape[1]
     for idx in loader.batch_sampler:
-        idx = torch.as_tensor(idx, dtype=torch.int64).to(device, non_blocking=True)
+        n = len(idx)
+        lo, hi = row_block(n, world_size, rank)
+        idx = torch.as_tensor(idx[lo:hi], dtype=torch.int64).to(device, non_blocking=True)
         B = idx.numel()
         x = torch.empty(B, D, device=device)
         m = torch.empty(B, D, device=device, dtype=mask_src.dtype)
@@ -70,27 +76,29 @@ def _epoch_batches(loader, device, throughput, prep=None):
             with torch.cuda.device(device):
                 L.check(lib.pcvae_prep_batch(data.data_ptr(), mask_src.data_ptr(), idx.data_ptr(), x.data_ptr(),
                                              m.data_ptr(), mp.data_ptr(), eps.data_ptr(), B, D, prep['n_eps'],
-                                             prep['keep'], 0xC0FFEE, prep['step'] * 8,
+                                             prep['keep'], 0xC0FFEE + rank, prep['step'] * 8,
                                              torch.cuda.current_stream().cuda_stream), "pcvae_prep_batch")
             prep['mask_p'], prep['eps'] = mp, eps
-            yield x, m
+            yield x, m, n
             continue
         with torch.cuda.device(device):
             L.check(lib.pcvae_gather_rows(data.data_ptr(), mask_src.data_ptr(), idx.data_ptr(), x.data_ptr(),
                                           m.data_ptr(), B, D, kind, torch.cuda.current_stream().cuda_stream),
                     "pcvae_gather_rows")
-        yield x, m
+        yield x, m, n
 
 
-def _graph_epoch(trainer, loader, device, regularised, latent_dim):
+def _graph_epoch(trainer, loader, device, regularised, latent_dim, world_size=1, rank=0):
     """One epoch through GraphedFusedTrainer: the sampler's full batches are uploaded as one index table and replayed
     from the CUDA graph, a ragged last batch is gathered and stepped eagerly.  Same RNG consumption on the host as
-    iter(DataLoader) (base seed, then the sampler's permutation)."""
+    iter(DataLoader) (base seed, then the sampler's permutation).  Data parallel: every rank holds the same
+    permutation (train() checks the ranks' RNG states) and takes its row block of every batch."""
     torch.empty((), dtype=torch.int64).random_()
     batches = list(loader.batch_sampler)
-    B = trainer.B
-    full = [b for b in batches if len(b) == B]
-    ragged = [b for b in batches if len(b) != B]
+    Bg = trainer.B * world_size                              # rows of a full GLOBAL batch
+    lo, hi = row_block(Bg, world_size, rank)
+    full = [b[lo:hi] for b in batches if len(b) == Bg]
+    ragged = [b for b in batches if len(b) != Bg]
     trainer.reset_total()
     trainer.set_batches(torch.as_tensor(full, dtype=torch.int64))
     done = 0
@@ -103,7 +111,10 @@ def _graph_epoch(trainer, loader, device, regularised, latent_dim):
     lib = L.load()
     data, mask = trainer.table, trainer.mtable
     for b in ragged:                                     # at most one
-        idx = torch.as_tensor(b, dtype=torch.int64).to(device)
+        rlo, rhi = row_block(len(b), world_size, rank)
+        if rhi == rlo:
+            raise L.PcvaeError(f"train(): the last batch of the epoch has {len(b)} rows for {world_size} ranks")
+        idx = torch.as_tensor(b[rlo:rhi], dtype=torch.int64).to(device)
         n = idx.numel()
         x = torch.empty(n, data.shape[1], device=device)
         m = torch.empty(n, data.shape[1], device=device, dtype=mask.dtype)
@@ -114,7 +125,8 @@ def _graph_epoch(trainer, loader, device, regularised, latent_dim):
                                          mp.data_ptr(), eps.data_ptr(), n, data.shape[1], eps.shape[0], trainer.keep,
                                          trainer.seed, 8 * trainer.step_count, torch.cuda.current_stream().cuda_stream),
                     "pcvae_prep_batch")
-        total += trainer.step(x, m, mp if regularised else None, eps[0], eps[1] if regularised else None)
+        total += trainer.step(x, m, mp if regularised else None, eps[0], eps[1] if regularised else None,
+                              global_rows=len(b))
         trainer.sync_counter()
     return total
 
@@ -145,26 +157,46 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
     throughput = os.environ.get('PCVAE_MODE', 'parity') == 'throughput'
     model.noise = 'device' if throughput else 'host'
     regularised = 'reg' in vae_type
-    fused = ('notMIWAE' not in vae_type) and (not beta_annealing) and (not regularised or reg_type == 'kl_reg')
+    # the Student-t family: everything model_loader's last two branches build (loaders.py:135-147, 234-245)
+    miwae = 'MIWAE' in vae_type and 'notMIWAE' not in vae_type
+    fused = ('MIWAE' not in vae_type) and (not beta_annealing) and (not regularised or reg_type == 'kl_reg')
     world_size, rank, group = world()
+    if world_size > 1:
+        if not fused:
+            # the module / autograd paths (not-MIWAE, MIWAE, ml_reg, beta annealing) have no gradient exchange: running
+            # them on several ranks would be N-fold redundant work on replicas that only agree if seeded identically
+            raise L.PcvaeError(f"train(): data parallelism is built for the fused partial-VAE step (kl_reg / vanilla); "
+                               f"run vae_type {vae_type!r} on one GPU")
+        _sync_replicas(model, group, device)
 
     keep = 1 - p_missingness / 100
     use_graph = False
+    trainer = None
     if fused:
         theta = model.flat_theta().detach().clone()
         table = getattr(data_loader_train, 'pcvae_table', None)
         bs = getattr(data_loader_train, 'batch_size', None)
-        # throughput mode on one GPU: the whole step is replayed from a CUDA graph (GraphedFusedTrainer); the ragged last
-        # batch of an epoch takes the eager launches.  At the reference's batch of 64 the step is launch-bound.
-        use_graph = (throughput and world_size == 1 and table is not None and table[0].is_cuda and bs is not None
+        # throughput mode: the whole step is replayed from a CUDA graph (GraphedFusedTrainer); the ragged last batch of an
+        # epoch takes the eager launches.  At the reference's batch of 64 the step is launch-bound.  Data parallel: each
+        # rank replays its own graph over its row block of every global batch, the tail of the step is the fused
+        # reduce + NVLink exchange + Adam kernel (needs peer access; otherwise eager launches + NCCL all-reduce).
+        use_graph = (throughput and table is not None and table[0].is_cuda and bs is not None and bs % world_size == 0
                      and table[1].dtype in (torch.bool, torch.uint8) and obs_dim % 4 == 0 and obs_dim <= 128
                      and model.FAMILY == L.FAMILY_MLP and 'with_drop' not in vae_type and table[0].shape[0] >= bs
-                     and os.environ.get('PCVAE_GRAPH', '1') != '0')
+                     and os.environ.get('PCVAE_GRAPH', '1') != '0'
+                     and (world_size == 1 or os.environ.get('PCVAE_DP', 'peer') != 'nccl'))
         if use_graph:
-            trainer = KR.GraphedFusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, table[0], table[1], bs,
-                                             table[0].shape[0] // bs, keep=keep, seed=0xC0FFEE, regularised=regularised,
-                                             alpha=float(alpha), beta_w=float(beta), lr=0.001)
-        else:
+            try:
+                trainer = KR.GraphedFusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, table[0], table[1],
+                                                 bs // world_size, table[0].shape[0] // bs, keep=keep, seed=0xC0FFEE + rank,
+                                                 regularised=regularised, alpha=float(alpha), beta_w=float(beta), lr=0.001,
+                                                 dist_group=group if world_size > 1 else None, world_size=world_size,
+                                                 global_rows=bs if world_size > 1 else None)
+            except L.PcvaeError:
+                if world_size == 1:
+                    raise
+                use_graph = False                            # no peer access (every rank agrees, PeerExchange.create_or_none)
+        if not use_graph:
             trainer = KR.FusedTrainer(model.FAMILY, obs_dim, model._emb(), theta, regularised=regularised,
                                       alpha=float(alpha), beta_w=float(beta), lr=0.001, dist_group=group, world_size=world_size)
     else:
@@ -186,76 +218,11 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
                                           stage=stage)[1]
                 return fn
             graph_trainer = GraphedTrainer(model, make_fn, optimizer, fill_normal_)
-    step = 0
-    # throughput mode, fused regularised step: gather + sub-mask + noise in one launch (pcvae_prep_batch)
-    prep = dict(keep=keep, n_eps=2, step=0) if (throughput and fused and regularised and latent_dim == 10
-                                                and 'with_drop' not in vae_type) else None
-    for i in tqdm(range(max_epochs)):
-        if use_graph:
-            total = _graph_epoch(trainer, data_loader_train, device, regularised, latent_dim)
-            tqdm.write('Epoch: [{}/{}], Total Loss: {}'.format(i, max_epochs, float(total)))
-            continue
-        total = torch.zeros((), device=device, dtype=torch.float64)
-        for data_sample, mask in _epoch_batches(data_loader_train, device, throughput, prep):
-            step += 1
-            B = data_sample.shape[0]
-            mask_p = None
-            prepped = prep.pop('mask_p', None) if prep is not None else None
-            if prepped is not None:
-                mask_p, eps_pair = prepped, prep.pop('eps')
-                lo, hi = row_block(B, world_size, rank)
-                sl = slice(lo, hi)
-                total += trainer.step(data_sample[sl], mask[sl], mask_p[sl], eps_pair[0][sl], eps_pair[1][sl], global_rows=B)
-                continue
-            if 'with_drop' in vae_type:
-                mask_drop = create_missing_uci_drop_eddi(data_sample.shape).to(device)
-            else:
-                if regularised:
-                    if throughput and mask.dtype in (torch.bool, torch.uint8):
-                        mask_p = _device_submask(mask, keep, step)
-                    elif throughput:
-                        mask_p = (torch.rand(data_sample.shape, device=device) < keep).to(mask.dtype) * mask
-                    else:
-                        temp_mask = create_missing_uci(data_sample.shape, p_missingness)     # host, NumPy RNG
-                        mask_p = temp_mask.to(device) * mask
-                mask_drop = torch.ones(data_sample.shape, device=device)
-            if fused:
-                lo, hi = row_block(B, world_size, rank)
-                sl = slice(lo, hi)
-                if regularised:
-                    eps_q = draw_noise(B, latent_dim, device, model.noise)
-                    eps_p = draw_noise(B, latent_dim, device, model.noise)
-                    loss = trainer.step(data_sample[sl], mask[sl], mask_p[sl], eps_q[sl], eps_p[sl], global_rows=B)
-                else:
-                    eps_q = draw_noise(B, latent_dim, device, model.noise)
-                    mk = (mask * mask_drop)                                                   # float32, train.py:97
-                    loss = trainer.step(data_sample[sl], mk[sl], None, eps_q[sl], None, global_rows=B)
-                total += loss
-            elif graphed:
-                if regularised:
-                    total += graph_trainer.step(data_sample, mask, mask_p)
-                else:
-                    total += graph_trainer.step(data_sample, mask * mask_drop)
-            else:
-                if regularised:
-                    out = model.forward(data_sample, mask, mask_p, stage=stage)
-                    mean_p, logvar_p, x_mean_p, x_logvar_p, mean_q, logvar_q, x_mean_q, x_logvar_q = out
-                    print_loss, train_loss = model.loss(
-                        data_sample, x_mean_p, x_logvar_p, mean_p, logvar_p, x_mean_q, x_logvar_q, mean_q, logvar_q,
-                        mask, mask_p, i + 1, beta_annealing=beta_annealing, beta=beta, alpha=alpha,
-                        alpha_annealing=alpha_annealing, stage=stage)
-                else:
-                    mean_q, logvar_q, x_mean_q, x_logvar_q = model.forward(data_sample, mask * mask_drop)
-                    print_loss, train_loss = model.loss(data_sample, x_mean_q, x_logvar_q, mean_q, logvar_q, i + 1,
-                                                        mask * mask_drop, beta_annealing=beta_annealing, beta=beta,
-                                                        stage=stage)
-                optimizer.zero_grad()
-                train_loss.backward()
-                optimizer.step()
-                total += train_loss.detach()
-        if world_size > 1 and fused:
-            torch.distributed.all_reduce(total, group=group)
-        tqdm.write('Epoch: [{}/{}], Total Loss: {}'.format(i, max_epochs, float(total)))
+    try:
+        _train_epochs(locals())
+    finally:
+        if trainer is not None and getattr(trainer, 'xch', None) is not None:
+            trainer.xch.close()                              # CUDA IPC handles and the exchange buffer of this rank
 
     if fused:
         with torch.no_grad():
@@ -267,3 +234,130 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
         _save(model, experiment_type, data_type, vae_type, missing_rate, alpha, p_missingness, reg_type)
     print('Training is over!')
     return model
+
+
+def _sync_replicas(model, group, device):
+    """Data parallel start-up: every replica takes rank 0's freshly initialised parameters, and the ranks' host RNG
+    states (torch CPU generator: DataLoader permutation and parity-mode noise; NumPy: sub-masks) must be identical --
+    every rank slices the SAME global batch, which only holds when the launcher seeded all ranks alike.  The states are
+    compared (not overwritten: rank 0's stream stays what a single-GPU run would see) and a mismatch raises."""
+    import hashlib
+    import numpy as np
+    import torch.distributed as dist
+    with torch.no_grad():
+        for p_ in model.parameters():
+            dist.broadcast(p_.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    h = hashlib.sha256(torch.get_rng_state().numpy().tobytes())
+    st = np.random.get_state()
+    h.update(np.asarray(st[1]).tobytes() + str(st[2:]).encode())
+    mine = torch.tensor(list(h.digest()[:8]), dtype=torch.int64, device=device)
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if not torch.equal(lo, hi):
+        raise L.PcvaeError("train(): the ranks' host RNG states differ.  Data-parallel training slices ONE global batch "
+                           "over the ranks, so every rank must be seeded identically (torch.manual_seed, np.random.seed) "
+                           "before train() is called")
+
+
+def _train_epochs(v):
+    """The epoch loop of train() (reference train.py:23-117); `v` is train()'s local namespace."""
+    model, trainer, device, vae_type = v['model'], v['trainer'], v['device'], v['vae_type']
+    loader, throughput, fused, regularised, miwae = v['data_loader_train'], v['throughput'], v['fused'], v['regularised'], v['miwae']
+    world_size, rank, group, use_graph = v['world_size'], v['rank'], v['group'], v['use_graph']
+    keep, latent_dim, max_epochs, p_missingness = v['keep'], v['latent_dim'], v['max_epochs'], v['p_missingness']
+    beta, beta_annealing, alpha, alpha_annealing, stage = v['beta'], v['beta_annealing'], v['alpha'], v['alpha_annealing'], v['stage']
+    graphed = v.get('graphed', False)
+    optimizer, graph_trainer = v.get('optimizer'), v.get('graph_trainer')
+    step = 0
+    # throughput mode, fused regularised step: gather + sub-mask + noise in one launch (pcvae_prep_batch)
+    prep = dict(keep=keep, n_eps=2, step=0) if (throughput and fused and regularised and latent_dim == 10
+                                                and 'with_drop' not in vae_type) else None
+    for i in tqdm(range(max_epochs)):
+        if use_graph:
+            total = _graph_epoch(trainer, loader, device, regularised, latent_dim, world_size, rank)
+        else:
+            total = torch.zeros((), device=device, dtype=torch.float64)
+            for data_sample, mask, n in _epoch_batches(loader, device, throughput, prep, world_size, rank):
+                step += 1
+                lo, hi = row_block(n, world_size, rank)              # this rank's rows of the global batch of n rows
+                sl = slice(lo, hi)
+                shape = (n, data_sample.shape[1])
+                mask_p = None
+                prepped = prep.pop('mask_p', None) if prep is not None else None
+                if prepped is not None:
+                    mask_p, eps_pair = prepped, prep.pop('eps')
+                    total += trainer.step(data_sample, mask, mask_p, eps_pair[0], eps_pair[1], global_rows=n)
+                    continue
+                # host draws are made for the WHOLE global batch on every rank (the same RNG consumption as one GPU), then
+                # sliced; device draws are made for the local rows only
+                if 'with_drop' in vae_type:
+                    mask_drop = create_missing_uci_drop_eddi(shape)[sl].to(device)
+                else:
+                    if regularised:
+                        if throughput and mask.dtype in (torch.bool, torch.uint8):
+                            mask_p = _device_submask(mask, keep, step)
+                        elif throughput:
+                            mask_p = (torch.rand(data_sample.shape, device=device) < keep).to(mask.dtype) * mask
+                        else:
+                            temp_mask = create_missing_uci(shape, p_missingness)              # host, NumPy RNG
+                            mask_p = temp_mask[sl].to(device) * mask
+                    mask_drop = torch.ones(data_sample.shape, device=device)
+                if fused:
+                    def noise():
+                        if model.noise == 'host':
+                            return draw_noise(n, latent_dim, device, 'host')[sl]
+                        return draw_noise(hi - lo, latent_dim, device, model.noise)
+                    if regularised:
+                        eps_q = noise()
+                        eps_p = noise()
+                        loss = trainer.step(data_sample, mask, mask_p, eps_q, eps_p, global_rows=n)
+                    else:
+                        eps_q = noise()
+                        mk = (mask * mask_drop)                                                   # float32, train.py:97
+                        loss = trainer.step(data_sample, mk, None, eps_q, None, global_rows=n)
+                    total += loss
+                elif graphed:
+                    if regularised:
+                        total += graph_trainer.step(data_sample, mask, mask_p)
+                    else:
+                        total += graph_trainer.step(data_sample, mask * mask_drop)
+                elif miwae:
+                    if regularised:                                           # train.py:102-108
+                        (mean_p, scale_p, x_mean_p, x_scale_p, deg_free_p, mean_q, scale_q, x_mean_q, x_scale_q,
+                         deg_free_q) = model.forward(data_sample, mask, mask_p)
+                        print_loss, train_loss = model.loss(data_sample, x_mean_p, x_scale_p, deg_free_p, mean_p, scale_p,
+                                                            x_mean_q, x_scale_q, deg_free_q, mean_q, scale_q, mask, mask_p,
+                                                            i + 1, beta_annealing=beta_annealing, beta=beta, alpha=alpha)
+                    else:                                                     # train.py:109-113
+                        mean, scale, x_mean, x_scale, deg_free = model.forward(data_sample, mask)
+                        print_loss, train_loss = model.loss(data_sample, x_mean, x_scale, deg_free, mean, scale, mask, i + 1)
+                    optimizer.zero_grad()
+                    train_loss.backward()
+                    optimizer.step()
+                    total += train_loss.detach()
+                else:
+                    if regularised:
+                        out = model.forward(data_sample, mask, mask_p, stage=stage)
+                        mean_p, logvar_p, x_mean_p, x_logvar_p, mean_q, logvar_q, x_mean_q, x_logvar_q = out
+                        print_loss, train_loss = model.loss(
+                            data_sample, x_mean_p, x_logvar_p, mean_p, logvar_p, x_mean_q, x_logvar_q, mean_q, logvar_q,
+                            mask, mask_p, i + 1, beta_annealing=beta_annealing, beta=beta, alpha=alpha,
+                            alpha_annealing=alpha_annealing, stage=stage)
+                    else:
+                        mean_q, logvar_q, x_mean_q, x_logvar_q = model.forward(data_sample, mask * mask_drop)
+                        print_loss, train_loss = model.loss(data_sample, x_mean_q, x_logvar_q, mean_q, logvar_q, i + 1,
+                                                            mask * mask_drop, beta_annealing=beta_annealing, beta=beta,
+                                                            stage=stage)
+                    optimizer.zero_grad()
+                    train_loss.backward()
+                    optimizer.step()
+                    total += train_loss.detach()
+        if world_size > 1 and fused:
+            torch.distributed.all_reduce(total, group=group)
+        # float(total) synchronises the stream; the data-parallel exchange's bounded wait reports here (a late rank: no
+        # Adam update was applied on the waiting ranks, pcvae_dp.cu) instead of letting the replicas drift apart
+        epoch_total = float(total)
+        if trainer is not None and getattr(trainer, 'xch', None) is not None:
+            trainer.xch.check()
+        tqdm.write('Epoch: [{}/{}], Total Loss: {}'.format(i, max_epochs, epoch_total))
