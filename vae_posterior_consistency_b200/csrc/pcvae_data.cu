@@ -8,6 +8,7 @@
 #include <curand_kernel.h>
 
 #include "pcvae_internal.cuh"
+#include "pcvae_philox.cuh"
 
 namespace pcvae {
 
@@ -52,21 +53,6 @@ __global__ void k_draw_normal(float* __restrict__ out, long n, unsigned long lon
             if (i + j < n) out[i + j] = gv[j];
     }
 }
-
-// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): counter-based, no state to initialise.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }          // [0, 1)
-__device__ __forceinline__ float u01_open(uint32_t r) { return ((float)(r >> 8) + 1.0f) * 5.9604644775390625e-08f; }   // (0, 1]
 
 // Fused batch preparation (one launch instead of three): a warp per table row copies the row of x and of the
 // mask with 16-byte / 4-byte vector accesses, draws the sub-mask for its entries and (lanes 0..4) the 2 x 10
