@@ -447,6 +447,33 @@ size_t pcvae_mnar_loss_workspace_bytes(int rows, int samples, int obs_dim);
 int pcvae_mnar_loss(const pcvae_mnar_loss_params* p, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Importance-weighted MNAR imputation in one pass over the [rows, samples] grid: replaces
+ * eval_vae_mnar's row-by-row model.forward + model.loss(llh_eval=True) calls (src/experiment_main/evaluate.py:27-49) for
+ * REG_notMIWAE_v2 (regularised = 1, src/models/VAE.py:2377-2396, 2398-2461) and notMIWAE_myversion (regularised = 0,
+ * VAE.py:2748-2770, 2772-2823):  x_imputed[n] = sum_s softmax_s(-l_w[n][s]) x_mean[n][s][:],  l_w = RE + KL - log p(mask | x~).
+ * The [samples, obs_dim] decoder outputs of a row never reach memory (online softmax per chunk of samples, chunks merged
+ * in order).  mean / logvar [rows][L] are the encoder statistics (pcvae_dense_fwd x 4).  Noise: eps (and, for
+ * regularised = 0, eps_kl: the second draw of the Monte-Carlo KL, VAE.py:2791-2798) as [rows][samples][L] arrays drawn by
+ * the caller, or both NULL: drawn in the kernel with Philox from (seed, offset).  obs_dim <= 64, latent_dim <= 16.
+ * --------------------------------------------------------------------- */
+typedef struct {
+    int rows, samples, obs_dim, latent_dim, regularised;
+    const float* dec0_W; const float* dec0_b;         /* seq_decoder.0  [128][L], [128] */
+    const float* dec2_W; const float* dec2_b;         /* seq_decoder.2  [128][128], [128] */
+    const float* xmean_W; const float* xmean_b;       /* x_mean.0       [D][128], [D] */
+    const float* xlogvar_W; const float* xlogvar_b;   /* x_logvar.0     [D][128], [D] */
+    const float* W; const float* b;                   /* self-masking slope (before softplus) and offset, [D] */
+    const float* x; const float* mask;                /* [rows][D] fp32 */
+    const float* mean; const float* logvar;           /* [rows][L] */
+    const float* eps; const float* eps_kl;            /* [rows][samples][L] or NULL */
+    unsigned long long seed, offset;                  /* Philox key / counter base when eps is NULL */
+    void* workspace; size_t workspace_bytes;          /* pcvae_mnar_impute_workspace_bytes() */
+    float* xm_imputed;                                /* out [rows][D] */
+} pcvae_mnar_impute_params;
+size_t pcvae_mnar_impute_workspace_bytes(int rows, int samples, int obs_dim);
+int pcvae_mnar_impute(const pcvae_mnar_impute_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
  * MIWAE / Reg_MIWAE (Student-t decoder + importance-weighted bound), reference src/models/VAE.py:3011-3134, 3137-3301;
  * dispatched by src/utils/loaders.py:135-147, 234-245, trained at src/experiment_main/train.py:102-113, evaluated by
  * eval_miwae, src/experiment_main/evaluate.py:72-133.  The 128-wide ReLU layers are

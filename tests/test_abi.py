@@ -144,7 +144,7 @@ def test_ctypes_structures_have_the_size_and_field_offsets_of_the_header(tmp_pat
              "pcvae_dec_params": L.DecParams, "pcvae_loss_params": L.LossParams, "pcvae_reward_params": L.RewardParams,
              "pcvae_dense_fwd_params": L.DenseFwdParams, "pcvae_dense_bwd_params": L.DenseBwdParams,
              "pcvae_mnar_loss_params": L.MnarLossParams, "pcvae_dp_params": L.DpParams,
-             "pcvae_miwae_loss_params": L.MiwaeLossParams}
+             "pcvae_miwae_loss_params": L.MiwaeLossParams, "pcvae_mnar_impute_params": L.MnarImputeParams}
     hdr = open(os.path.join(ROOT, "include", "pcvae_b200.h")).read()
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pcvae_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():

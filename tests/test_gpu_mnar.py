@@ -221,3 +221,80 @@ def test_graph_replayed_step_equals_eager_step(cls):
     np.testing.assert_allclose(l_graph, l_eager, rtol=1e-6)
     for (k, a), (_, b) in zip(m_eager.state_dict().items(), m_graph.state_dict().items()):
         torch.testing.assert_close(b, a, rtol=1e-6, atol=1e-7, msg=k)
+
+
+@pytest.mark.parametrize("cls,N,D,S", [("REG_notMIWAE_v2", 130, 50, 10000), ("notMIWAE_myversion", 100, 50, 10000),
+                                       ("REG_notMIWAE_v2", 7, 6, 5), ("notMIWAE_myversion", 300, 13, 77),
+                                       ("REG_notMIWAE_v2", 3, 64, 1000)])
+def test_one_pass_imputation_at_full_valid_k(cls, N, D, S):
+    """pcvae_mnar_impute (one pass over [rows, samples], online softmax) at the reference's
+    valid_k = 10 000 on >= 100 rows: against the row-blocked path through the generic dense / loss kernels with the
+    same noise, and against the oracle in float64 on a few rows."""
+    from vae_posterior_consistency_b200 import VAE, kernels as KR, ops
+    torch.manual_seed(5)
+    dev = torch.device("cuda")
+    model = getattr(VAE, cls)(D, 500, 20, 10, {"batch_size": 64, "patience": 100}, S, 10).to(dev)
+    with torch.no_grad():                                     # spread the importance weights: sharper decoder, real slopes
+        for prm in model.parameters():
+            prm.mul_(1.7)
+    reg = cls == "REG_notMIWAE_v2"
+    g = torch.Generator().manual_seed(N + D + S)
+    x = torch.rand(N, D, generator=g).to(dev)
+    mask = (torch.rand(N, D, generator=g) < 0.6).float().to(dev)
+    eps = torch.randn(N, S, 10, generator=g).to(dev)
+    eps_kl = torch.randn(N, S, 10, generator=g).to(dev)
+    with torch.no_grad():
+        mean, logvar = model._stats(x, mask)
+        got = KR.mnar_impute(model, x, mask, mean, logvar, S, reg, eps=eps, eps_kl=None if reg else eps_kl)
+        # row-blocked cross-check (materialises [block, S, D])
+        ref = torch.empty_like(got)
+        block = max(1, (1 << 22) // (S * D))
+        for lo in range(0, N, block):
+            hi = min(N, lo + block)
+            z = ops.mnar_sample_z_op(mean[lo:hi], logvar[lo:hi], eps[lo:hi].contiguous(), S)
+            xm, xlv = model.decoder(z)
+            if reg:
+                out = ops.mnar_loss_op(x[lo:hi], mask[lo:hi], mask[lo:hi], xm, xlv, xm, xlv, mean[lo:hi], logvar[lo:hi],
+                                       mean[lo:hi], logvar[lo:hi], model.W, model.b, None, 1.0, False, True)
+            else:
+                out = ops.mnar_loss_op(x[lo:hi], mask[lo:hi], None, xm, xlv, None, None, mean[lo:hi], logvar[lo:hi], None,
+                                       None, model.W, model.b, eps_kl[lo:hi].contiguous(), 1.0, False, True)
+            ref[lo:hi] = out[2]
+    err = float((got - ref).abs().max())
+    print(f"{cls} N={N} D={D} S={S}: max |one-pass - blocked| = {err:.3e}")
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-6)
+    # oracle in float64 on the first rows (the reference formulas, oracle/pcvae_oracle.py)
+    k = min(N, 4)
+    sd = {kk: v.detach().cpu().double() for kk, v in model.state_dict().items() if v.dtype.is_floating_point}
+    xs, ms = x[:k].cpu().double(), mask[:k].cpu().double()
+    mu, lv = O.mnar_encoder_stats(sd, xs, ms)
+    zz = mu.unsqueeze(1) + torch.exp(lv / 2).unsqueeze(1) * eps[:k].cpu().double()
+    xm64, xlv64 = O.mnar_decoder(sd, zz)
+    if reg:
+        _, imp64, _ = O.mnar_reg_loss(sd, xs, ms, ms, mu, lv, mu, lv, xm64, xlv64, xm64, xlv64, alpha=1.0)
+    else:
+        _, imp64, _ = O.mnar_vanilla_loss(sd, xs, ms, mu, lv, xm64, xlv64, eps_kl[:k].cpu().double())
+    torch.testing.assert_close(got[:k].cpu().double(), imp64, rtol=2e-4, atol=1e-5)
+
+
+def test_one_pass_imputation_with_device_noise_is_statistically_the_same():
+    """Throughput mode: the kernel draws its own noise (Philox); with S = 10 000 samples the importance-weighted means of
+    two independent noise streams agree to Monte-Carlo accuracy, and the call is deterministic."""
+    from vae_posterior_consistency_b200 import VAE, kernels as KR
+    torch.manual_seed(6)
+    dev = torch.device("cuda")
+    N, D, S = 64, 20, 10000
+    model = VAE.notMIWAE_myversion(D, 500, 20, 10, {"batch_size": 64, "patience": 100}, S, 10).to(dev)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(N, D, generator=g).to(dev)
+    mask = (torch.rand(N, D, generator=g) < 0.6).float().to(dev)
+    with torch.no_grad():
+        mean, logvar = model._stats(x, mask)
+        a = KR.mnar_impute(model, x, mask, mean, logvar, S, False, seed=11)
+        a2 = KR.mnar_impute(model, x, mask, mean, logvar, S, False, seed=11)
+        b = KR.mnar_impute(model, x, mask, mean, logvar, S, False, seed=12)
+        h = KR.mnar_impute(model, x, mask, mean, logvar, S, False, eps=torch.randn(N, S, 10, device=dev),
+                           eps_kl=torch.randn(N, S, 10, device=dev))
+    assert torch.equal(a, a2) and not torch.equal(a, b)
+    assert float((a - b).abs().max()) < 0.02 and float((a - h).abs().max()) < 0.02
+    assert float((a - h).abs().mean()) < 0.004

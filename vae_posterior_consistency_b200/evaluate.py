@@ -19,7 +19,8 @@ from . import ops
 from .dist import all_reduce_sum, merge_row_blocks, row_block, world
 from .loaders import model_loader
 from .utils import create_missing_uci
-from .VAE import draw_noise
+from . import kernels as KR
+from .VAE import draw_noise, draw_noise_bsl
 
 
 def _family_dir(vae_type):
@@ -189,9 +190,10 @@ def eval_vae_mnar(data_test, mask_test, missing_rate, obs_dim, hid_dim, K, M, la
                   device=torch.device('cpu'), alpha=0.5, stage='evaluate', p_missingness=30, reg_type='ml_reg',
                   beta=1.0, beta_annealing=False, alpha_annealing=True, not_miwae_type='changed'):
     """Importance-weighted MNAR imputation RMSE (evaluate.py:13-69).  The reference loops row by row with
-    S = valid_k samples; here rows are processed in blocks while the host noise is
-    still drawn row by row in the reference's order (sub-mask, eps_q, eps_p / eps, eps_kl) so that parity-mode
-    results match bit for bit in their inputs."""
+    S = valid_k samples; here all rows go through ONE kernel over the [rows, samples] grid with an online softmax
+    (pcvae_mnar_impute).  Parity mode: the host noise is still drawn row by row in the
+    reference's order (sub-mask, eps_q, eps_p / eps, eps_kl) so that the inputs match bit for bit; PCVAE_MODE=throughput:
+    the noise is drawn inside the kernel (Philox), no per-row host work at all."""
     device = torch.device(device)
     with torch.no_grad():
         model = model_loader('test', obs_dim, hid_dim, K, latent_dim, missing_rate, data_type, training_parameters,
@@ -202,20 +204,40 @@ def eval_vae_mnar(data_test, mask_test, missing_rate, obs_dim, hid_dim, K, M, la
         S, Lt = model.num_samples, latent_dim
         N = data_test.shape[0]
         x_all, m_all = data_test.float().to(device), mask_test.float().to(device)
-        block = max(1, min(N, (1 << 22) // max(S * obs_dim, 1)))          # ~4M decoder outputs per block
+        throughput = os.environ.get('PCVAE_MODE', 'parity') == 'throughput'
+        # one pass over the [rows, samples] grid with an online softmax (pcvae_mnar_impute): nothing of size [rows, S, D]
+        # is materialised.  Shapes the kernel does not take (obs_dim > 64) and PCVAE_IMPUTE=blocked (the cross-check) go
+        # through the generic dense / loss kernels in row blocks.
+        fused = (obs_dim <= KR.IMPUTE_MAX_D and Lt <= 16 and os.environ.get('PCVAE_IMPUTE', 'fused') != 'blocked')
+        if fused:
+            block = N if throughput else max(1, min(N, (1 << 24) // max(S * Lt, 1)))   # parity: <= 64 MB of host noise per draw
+        else:
+            block = max(1, min(N, (1 << 22) // max(S * obs_dim, 1)))                    # ~4M decoder outputs per block
         recons = []
-        for _ in range(M):
+        for rep in range(M):
             XM = torch.zeros(N, obs_dim, device=device)
             for lo in range(0, N, block):
                 hi = min(N, lo + block)
-                eps_q, eps_kl = [], []
-                for i in range(lo, hi):
-                    create_missing_uci(data_test.shape, p_missingness)          # evaluate.py:31, per row
-                    eps_q.append(torch.empty(1, S, Lt).normal_())
-                    eps_kl.append(torch.empty(1, S, Lt).normal_())              # reg: the p-branch draw; vanilla: z'
-                eps_q = torch.cat(eps_q).to(device)
+                eps_q = eps_kl = None
+                if not throughput:
+                    # the reference's per-row order: sub-mask (evaluate.py:31, a full-table draw per row), then the two
+                    # [1, S, L] normal draws of the row (reg: q and p encoder; vanilla: encoder, then the loss' z')
+                    eq, ek = [], []
+                    for i in range(lo, hi):
+                        create_missing_uci(data_test.shape, p_missingness)
+                        eq.append(torch.empty(1, S, Lt).normal_())
+                        ek.append(torch.empty(1, S, Lt).normal_())
+                    eps_q, eps_kl = torch.cat(eq).to(device), torch.cat(ek).to(device)
                 xb, mb = x_all[lo:hi], m_all[lo:hi]
                 mean, log_var = model._stats(xb, mb)
+                if fused:
+                    XM[lo:hi] = KR.mnar_impute(model, xb, mb, mean, log_var, S, reg, eps=eps_q,
+                                               eps_kl=None if (reg or throughput) else eps_kl, seed=0x1A9E + rep,
+                                               offset=0)
+                    continue
+                if throughput:
+                    eps_q = draw_noise_bsl(hi - lo, S, Lt, device, 'device')
+                    eps_kl = draw_noise_bsl(hi - lo, S, Lt, device, 'device')
                 z = ops.mnar_sample_z_op(mean, log_var, eps_q, S)
                 xm, xlv = model.decoder(z)
                 if reg:
@@ -224,7 +246,7 @@ def eval_vae_mnar(data_test, mask_test, missing_rate, obs_dim, hid_dim, K, M, la
                                            model.b, None, float(alpha), False, True)
                 else:
                     out = ops.mnar_loss_op(xb, mb, None, xm, xlv, None, None, mean, log_var, None, None, model.W,
-                                           model.b, torch.cat(eps_kl).to(device), 1.0, False, True)
+                                           model.b, eps_kl, 1.0, False, True)
                 XM[lo:hi] = out[2]
             miss = 1 - m_all
             recons.append(torch.sqrt(torch.sum((XM * miss - x_all * miss) ** 2) / torch.sum(miss)))

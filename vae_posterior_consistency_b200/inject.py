@@ -66,13 +66,19 @@ def install():
 
 
 def run_driver(path, argv=()):
+    """Execute the driver file as __main__.  The drivers switch autograd's anomaly mode on at import time
+    (imputation.py:19, active_learning.py:21) and never off; the caller's setting is restored afterwards (anomaly mode
+    synchronises after every backward node, which among other things forbids CUDA-graph capture)."""
+    import torch
     install()
     old = sys.argv
+    anomaly = torch.is_anomaly_enabled()
     sys.argv = [path, *argv]
     try:
         return runpy.run_path(path, run_name="__main__")
     finally:
         sys.argv = old
+        torch.autograd.set_detect_anomaly(anomaly)
 
 
 if __name__ == "__main__":

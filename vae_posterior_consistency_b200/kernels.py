@@ -453,6 +453,38 @@ def mnar_loss(x, mask, mask_p, xm, xlv, mean, logvar, W, b, alpha, regularised, 
     return dict(out=out, xm_imputed=xm_imp, d_xm=d_xm, d_xlv=d_xlv, d_mean=d_mean, d_logvar=d_logvar, d_W=d_W, d_b=d_b)
 
 
+IMPUTE_MAX_D = 64
+
+
+def mnar_impute(model, x, mask, mean, logvar, samples, regularised, eps=None, eps_kl=None, seed=0x1A9E, offset=0):
+    """x_imputed [N, D] of a not-MIWAE model for N rows with `samples` importance samples each, in one pass
+    (pcvae_mnar_impute).  `model` supplies the decoder / self-masking parameters (nn.Linear layouts); mean / logvar are
+    its encoder statistics for (x, mask).  eps / eps_kl [N, S, L] (parity mode) or None (Philox in the kernel)."""
+    _need_cuda(x, mask, mean, logvar)
+    x, mask, mean, logvar = _f32(x), _f32(mask), _f32(mean), _f32(logvar)
+    N, D = x.shape
+    Lt = mean.shape[1]
+    lib = L.load()
+    prm = lambda t: _f32(t.detach())
+    w = [prm(model.seq_decoder[0].weight), prm(model.seq_decoder[0].bias), prm(model.seq_decoder[2].weight),
+         prm(model.seq_decoder[2].bias), prm(model.x_mean[0].weight), prm(model.x_mean[0].bias),
+         prm(model.x_logvar[0].weight), prm(model.x_logvar[0].bias), prm(model.W).reshape(-1), prm(model.b).reshape(-1)]
+    eps = None if eps is None else _f32(eps)
+    eps_kl = None if eps_kl is None else _f32(eps_kl)
+    with torch.cuda.device(x.device):
+        nbytes = lib.pcvae_mnar_impute_workspace_bytes(N, samples, D)
+    ws = torch.empty(max(nbytes, 4), device=x.device, dtype=torch.uint8)
+    out = torch.empty(N, D, device=x.device, dtype=torch.float32)
+    p = L.MnarImputeParams(rows=N, samples=samples, obs_dim=D, latent_dim=Lt, regularised=int(regularised),
+                           dec0_W=_p(w[0]), dec0_b=_p(w[1]), dec2_W=_p(w[2]), dec2_b=_p(w[3]), xmean_W=_p(w[4]),
+                           xmean_b=_p(w[5]), xlogvar_W=_p(w[6]), xlogvar_b=_p(w[7]), W=_p(w[8]), b=_p(w[9]), x=_p(x),
+                           mask=_p(mask), mean=_p(mean), logvar=_p(logvar), eps=_p(eps), eps_kl=_p(eps_kl), seed=seed,
+                           offset=offset, workspace=_p(ws), workspace_bytes=ws.numel(), xm_imputed=_p(out))
+    with torch.cuda.device(x.device):
+        L.check(lib.pcvae_mnar_impute(C.byref(p), _stream()), "pcvae_mnar_impute")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # MIWAE / Reg_MIWAE pieces (Student-t decoder + importance-weighted bound), reference VAE.py:3011-3301
 # ------------------------------------------------------------------------------------------------

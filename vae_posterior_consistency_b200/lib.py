@@ -33,6 +33,7 @@ SYMBOLS = [
     "pcvae_dp_exchange_free", "pcvae_dp_reduce_adam", "pcvae_prep_batch_dev", "pcvae_reduce_adam_dev",
     "pcvae_dp_reduce_adam_emulated", "pcvae_miwae_heads", "pcvae_miwae_heads_bwd", "pcvae_miwae_sample_z",
     "pcvae_miwae_sample_z_bwd", "pcvae_miwae_loss_workspace_bytes", "pcvae_miwae_loss",
+    "pcvae_mnar_impute_workspace_bytes", "pcvae_mnar_impute",
 ]
 
 
@@ -132,6 +133,17 @@ class MiwaeLossParams(C.Structure):
                 ("d_xs", _P2), ("d_df", _P2), ("d_mean", _P2), ("d_scale", _P2)]
 
 
+class MnarImputeParams(C.Structure):
+    """pcvae_mnar_impute_params (include/pcvae_b200.h)."""
+    _fields_ = [("rows", C.c_int), ("samples", C.c_int), ("obs_dim", C.c_int), ("latent_dim", C.c_int),
+                ("regularised", C.c_int), ("dec0_W", C.c_void_p), ("dec0_b", C.c_void_p), ("dec2_W", C.c_void_p),
+                ("dec2_b", C.c_void_p), ("xmean_W", C.c_void_p), ("xmean_b", C.c_void_p), ("xlogvar_W", C.c_void_p),
+                ("xlogvar_b", C.c_void_p), ("W", C.c_void_p), ("b", C.c_void_p), ("x", C.c_void_p), ("mask", C.c_void_p),
+                ("mean", C.c_void_p), ("logvar", C.c_void_p), ("eps", C.c_void_p), ("eps_kl", C.c_void_p),
+                ("seed", C.c_ulonglong), ("offset", C.c_ulonglong), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t), ("xm_imputed", C.c_void_p)]
+
+
 MIWAE_HEADS_ENC, MIWAE_HEADS_DEC = 0, 1
 
 _lib = None
@@ -221,6 +233,9 @@ def load():
     lib.pcvae_miwae_loss_workspace_bytes.restype = C.c_size_t
     lib.pcvae_miwae_loss_workspace_bytes.argtypes = [C.c_int, C.c_int]
     lib.pcvae_miwae_loss.argtypes = [C.POINTER(MiwaeLossParams), C.c_void_p]
+    lib.pcvae_mnar_impute_workspace_bytes.restype = C.c_size_t
+    lib.pcvae_mnar_impute_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.pcvae_mnar_impute.argtypes = [C.POINTER(MnarImputeParams), C.c_void_p]
     lib.pcvae_ffma_probe.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     _lib = lib
     return lib
