@@ -432,9 +432,12 @@ def full_size_driver_cases():
             files = {}
             for f in glob.glob(os.path.join("experiments", "**", "*.pt"), recursive=True):
                 rel = os.path.relpath(f, "experiments")
-                if "im_CHAI" in f or "checkpoint" in f:
+                if "im_CHAI" in f:
                     continue
                 t = torch.load(f)
+                if "checkpoint" in f:        # the weights active_learning.py loaded: the GPU run of the acquisition loop starts
+                    files[rel] = t           # from the same ones (the 600-step training trajectory is compared separately)
+                    continue
                 if "action_CHAI" in f:
                     t = t.to(torch.uint8)
                 elif "R_hist_CHAI" in f:                                     # [1, step, row, candidate]
