@@ -429,9 +429,6 @@ static int enc_tc_go(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
 }
 
 int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st) {
-    // default: two work items in flight per SM (pcvae_enc_tc2.cu); PCVAE_ENC_FWD_V2=0 selects round 1's one-item kernel
-    static const int v2 = [] { const char* e = getenv("PCVAE_ENC_FWD_V2"); return e && e[0] == '0' ? 0 : 1; }();
-    if (v2) return enc_fwd_tc2_launch(a, grid, st);
     // inputs are staged through shared memory when the masks are bytes and the tile fits beside the weight images
     const bool stage_inputs = a.mask_kind == PCVAE_MASK_U8 && tc::enc_fwd_tc_smem(a.L.D, true) <= (size_t)MAX_SMEM;
     const size_t sm = tc::enc_fwd_tc_smem(a.L.D, stage_inputs);

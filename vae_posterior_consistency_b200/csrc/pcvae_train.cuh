@@ -96,7 +96,6 @@ inline long etw_floats(long rows, int nbr) { return (ETW_FEATS + 8) * 128 * tc_n
 bool enc_tc_supported(const Layout& L);
 void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw);
 int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st);
-int enc_fwd_tc2_launch(const EncFwdArgs& a, int grid, cudaStream_t st);      // pcvae_enc_tc2.cu
 int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st);
 
 // pcvae_wgrad_tc.cu: dWaug[m][n] = sum_rows AT[m][row] * BT[n][row] for up to three layers in one launch

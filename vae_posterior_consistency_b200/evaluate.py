@@ -23,6 +23,10 @@ from . import kernels as KR
 from .VAE import draw_noise, draw_noise_bsl
 
 
+#: device time and (row, candidate, sample) count of the reward calls of the last active_learning_func run on this rank
+LAST_TIMING = {}
+
+
 def _family_dir(vae_type):
     return ''.join(c for c in '_'.join(vae_type.split('_')[:2]) if not c.isdigit())
 
@@ -284,6 +288,7 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
     lo, hi = row_block(n_test, world_size, rank)                           # this rank's row block
     n_loc = hi - lo
     C = obs_dim - 1
+    reward_events = []                                                   # (start, stop, triples) of every reward call
     info = torch.zeros(Repeat, n_test, obs_dim)
     action = torch.zeros(Repeat, n_test, C)
     R_hist = torch.zeros(Repeat, C, n_test, C)
@@ -294,6 +299,8 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                                  training_parameters, max_epochs, valid_k, num_estimates, experiment_type, reg_type,
                                  vae_type, alpha=alpha, p_missingness=p_missingness, alpha_annealing=alpha_annealing)
             model.to(device)
+            # PCVAE_MODE=throughput: Philox noise on the device, no host draws (statistically, not bitwise, the same loop)
+            model.noise = 'device' if os.environ.get('PCVAE_MODE', 'parity') == 'throughput' else 'host'
             regularised = 'reg' in vae_type
             theta = model.flat_theta()
             eng = ops.engine(model.FAMILY, obs_dim, model._emb(), device)
@@ -330,7 +337,11 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                 print("Step = {:.1f}".format(t))
                 im = sample_means()
                 im_hist[r, t, :, lo:hi] = im.cpu()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
                 R, ws = eng.reward(theta, x, mask, im, ws)
+                ev1.record()
+                reward_events.append((ev0, ev1, int((mask[:, :C] == 0).sum()) * M))
                 if model.noise == 'host':
                     # the reference's chaini_I / chaini_II call encoder(sample=True): 4*M discarded [|loc|, L]
                     # draws per candidate (evaluate.py:562-626); burn them so the next `im` sees the same RNG state
@@ -345,6 +356,9 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                 action[r, lo:hi, t] = i_opt.float().cpu()
                 mask = mask + torch.eye(obs_dim, device=device)[i_opt]
                 info[r, :, t + 1] = target_mse(sample_means()).cpu()
+    torch.cuda.synchronize(device)
+    LAST_TIMING.update(reward_ms=sum(a.elapsed_time(b) for a, b, _ in reward_events),
+                       triples=sum(n for _, _, n in reward_events), reward_calls=len(reward_events))
     if world_size > 1:
         for tns in (action, R_hist, im_hist):
             merge_row_blocks(tns, group, device)                       # row blocks are disjoint: sum == gather

@@ -341,6 +341,58 @@ class Engine:
         return R, workspace
 
 
+    def reward_streamed(self, theta, hx, hmask, him, hR, chunks=8, copy_stream=None):
+        """The reward of one acquisition step with x / mask / im in PINNED HOST memory and R returned to pinned host
+        memory: rows are independent, so they are taken in `chunks` row blocks whose host-to-device
+        copies (copy stream, double-buffered; im [M, N, D] is copied sample by sample, each a contiguous block) run
+        under the reward kernel of the previous block.  Returns the number of bytes copied in each direction."""
+        M, N, D = him.shape
+        dev = theta.device
+        main = torch.cuda.current_stream(dev)
+        cs = copy_stream if copy_stream is not None else torch.cuda.Stream(device=dev)
+        nmax = (N + chunks - 1) // chunks
+        bufs = getattr(self, "_rs_bufs", None)
+        if bufs is None or bufs[0][0].shape[0] < nmax or bufs[0][2].shape[0] != M:
+            bufs = [(torch.empty(nmax, D, device=dev), torch.empty(nmax, D, device=dev, dtype=hmask.dtype),
+                     torch.empty(M, nmax, D, device=dev), torch.empty(nmax, D - 1, device=dev)) for _ in range(2)]
+            self._rs_bufs = bufs
+            self._rs_ws = None
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        cs.wait_stream(main)
+        h2d = d2h = 0
+        for c in range(chunks):
+            lo, hi = (c * N) // chunks, ((c + 1) * N) // chunks
+            n, b = hi - lo, c % 2
+            if n == 0:
+                continue
+            dx, dm, dim, dR = bufs[b]
+            with torch.cuda.stream(cs):
+                if c >= 2:
+                    cs.wait_event(freed[b])
+                dx[:n].copy_(hx[lo:hi], non_blocking=True)
+                dm[:n].copy_(hmask[lo:hi], non_blocking=True)
+                for m in range(M):
+                    dim[m, :n].copy_(him[m, lo:hi], non_blocking=True)
+                ready[b].record(cs)
+            h2d += 2 * n * D * 4 + M * n * D * 4
+            main.wait_event(ready[b])
+            # the kernel reads im[m][row] at im + m * stride: the chunk buffer keeps the full-chunk sample stride
+            kind, (mk,) = prep_masks([dm[:n]])
+            nbytes = self.lib.pcvae_reward_workspace_bytes(C.byref(self.model), n, M)
+            if self._rs_ws is None or self._rs_ws.numel() < nbytes:
+                self._rs_ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
+            p = L.RewardParams(model=self.model, rows=n, samples=M, mask_kind=kind, theta=_p(theta), x=_p(dx), mask=_p(mk),
+                               im=_p(dim), im_sample_stride=nmax * D, R=_p(dR), workspace=_p(self._rs_ws),
+                               workspace_bytes=self._rs_ws.numel(), pnp_ac=_p(self.pnp_ac()))
+            with torch.cuda.device(dev):
+                L.check(self.lib.pcvae_reward_chain(C.byref(p), _stream()), "pcvae_reward_chain")
+            hR[lo:hi].copy_(dR[:n], non_blocking=True)
+            freed[b].record(main)
+            d2h += n * (D - 1) * 4
+        return h2d, d2h
+
+
 # ------------------------------------------------------------------------------------------------
 # generic dense layers and the not-MIWAE MNAR pieces
 # ------------------------------------------------------------------------------------------------
