@@ -46,7 +46,7 @@ KERNEL_DRAM_BYTES = {"k_enc_fwd_tc": 142.1e6, "k_dec_fwd_tc": 136.6e6, "k_dec_bw
                      "k_enc_bwd_tc": 49.5e6, "k_wgrad_tc[enc]": 238.9e6}
 FLOP_REWARD_TRIPLE = 24_460       # Reg_VAE incremental form: 2 tail evaluations + amortised bases
 # dram bytes of k_reward_main_tc at cfg5 (100k rows x 100 candidates x 50 samples), profiles/r02_ncu_summary.md
-REWARD_DRAM_BYTES = None
+REWARD_DRAM_BYTES = 2.983e9       # read 2.935 GB (imputations 2.02 GB + per-(row, sample) base posteriors) + write 0.048 GB
 
 #: the workload both arms are run on (identical `config` in the two JSON lines)
 def config_dict(args):
@@ -514,11 +514,13 @@ def gpu_al_loop(args, dev, world, rank):
         test = torch.rand(N, D, generator=g)
         tmask = torch.rand(N, D, generator=g) < 0.7
         out = {}
+        import contextlib
         for rep in range(2):                                              # first pass warms up (lazy module load, allocator)
             barrier(world)
             t0 = time.perf_counter()
-            evaluate.active_learning_func(None, test, tmask, 30, D, 500, 10, M, 10, data_type, tp, exp, vae_type, 1, 5000, 10,
-                                          device=dev, alpha=1.0, p_missingness=30, reg_type="kl_reg", Repeat=1)
+            with contextlib.redirect_stdout(sys.stderr):                  # the loop prints its progress like the reference's
+                evaluate.active_learning_func(None, test, tmask, 30, D, 500, 10, M, 10, data_type, tp, exp, vae_type, 1, 5000,
+                                              10, device=dev, alpha=1.0, p_missingness=30, reg_type="kl_reg", Repeat=1)
             barrier(world)
             wall = time.perf_counter() - t0
             tm = dict(evaluate.LAST_TIMING)

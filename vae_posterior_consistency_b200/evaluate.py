@@ -311,16 +311,23 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
             ws = None
 
             def sample_means():
-                """M x model.forward(x, mask, mask_p)[x_mean_q] (evaluate.py:365-386, 394-415): full-size host
-                noise sliced to this rank's rows; the p-branch draw is made and discarded."""
-                outs = []
+                """M x model.forward(x, mask, mask_p)[x_mean_q] (evaluate.py:365-386, 394-415).  The noise is drawn as the
+                reference draws it -- per sample a full-size host draw, sliced to this rank's rows, the p-branch draw made
+                and discarded -- but the M encoder / decoder passes go to the GPU as ONE launch each over the M stacked
+                copies of the rows (rows are independent, so the results are the same bit for bit)."""
+                eps = []
                 for _ in range(M):
-                    eps_q = draw_noise(n_test, latent_dim, device, model.noise)[lo:hi]
+                    eps.append(draw_noise(n_test, latent_dim, device, model.noise)[lo:hi])
                     if regularised:
                         draw_noise(n_test, latent_dim, device, model.noise)
-                    _, _, z, _ = eng.enc_fwd(theta, x, [mask], [eps_q.contiguous()])
-                    outs.append(eng.dec(L.DEC_FWD, theta, z)["xhat"][0])
-                return torch.stack(outs, 0)
+                outs = []
+                group = max(1, min(M, (1 << 20) // max(n_loc, 1)))                 # <= ~1M stacked rows per launch
+                for m0 in range(0, M, group):
+                    k = min(group, M - m0)
+                    e = torch.cat(eps[m0:m0 + k]).contiguous()
+                    _, _, z, _ = eng.enc_fwd(theta, x.repeat(k, 1), [mask.repeat(k, 1)], [e])
+                    outs.append(eng.dec(L.DEC_FWD, theta, z)["xhat"][0].view(k, n_loc, obs_dim))
+                return torch.cat(outs, 0)
 
             def target_mse(im):
                 # [M] sums of squared errors over this rank's rows, accumulated in float64 so that the total does not
