@@ -314,9 +314,11 @@ typedef struct {
 } pcvae_reward_params;
 size_t pcvae_reward_workspace_bytes(const pcvae_model* m, int rows, int samples);
 int pcvae_reward_chain(const pcvae_reward_params* p, void* stream);
-/* Select the main reward kernel of the MLP family: 1 = tcgen05 tensor cores with the fp32-accurate
- * 3xTF32 operand split (csrc/pcvae_reward_tc.cu), 0 = FP32 FFMA (csrc/pcvae_reward.cu).  Both compute the
- * same function to fp32 accuracy; the PNP family always uses the FFMA kernel.  Returns the previous value. */
+/* Select the main reward kernel of the MLP family: 1 (default) = tcgen05 tensor cores with the fp32-accurate
+ * 3xTF32 operand split, warp-specialised (csrc/pcvae_reward_ws.cu: constructor / epilogue / KL warpgroups
+ * pipelined through mbarriers); 2 = the same arithmetic in lock-step phases (csrc/pcvae_reward_tc.cu, kept as
+ * the cross-check: R is bit-identical to 1); 0 = FP32 FFMA (csrc/pcvae_reward.cu).  All compute the same
+ * function to fp32 accuracy; the PNP family always uses the FFMA kernel.  Returns the previous value. */
 int pcvae_set_reward_tensor_cores(int enable);
 
 /* ------------------------------------------------------------------------

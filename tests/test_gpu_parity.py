@@ -399,9 +399,10 @@ def test_empty_batch_is_a_no_op():
     assert mean[0].shape == (0, 10) and z[0].shape == (0, 10)        # VAE.py:723-724 empty guard
 
 
-@pytest.fixture(params=[0, 1], ids=["ffma", "tcgen05"])
+@pytest.fixture(params=[0, 1, 2], ids=["ffma", "tcgen05", "tcgen05-lockstep"])
 def reward_tc(request):
-    """Run the reward tests with both main kernels: FP32 FFMA and tcgen05 3xTF32 (MLP family)."""
+    """Run the reward tests with all three main kernels: FP32 FFMA, tcgen05 3xTF32 warp-specialised (the default) and
+    tcgen05 3xTF32 in lock-step phases (MLP family)."""
     KR, L = _mods()
     prev = L.load().pcvae_set_reward_tensor_cores(request.param)
     yield request.param
@@ -467,6 +468,35 @@ def test_reward_is_row_shardable_bit_exact(reward_tc):
     Ra, _ = eng.reward(theta, x[:cut], mask[:cut], im[:, :cut].contiguous())
     Rb, _ = eng.reward(theta, x[cut:], mask[cut:], im[:, cut:].contiguous())
     assert torch.equal(R, torch.cat([Ra, Rb]))
+
+
+@pytest.mark.parametrize("N,D,M", [(333, 20, 6), (70, 101, 3), (5, 2, 1), (1500, 100, 50), (9, 8, 2)])
+def test_warp_specialised_reward_kernel_equals_lockstep_kernel_bit_for_bit(N, D, M):
+    """pcvae_reward_ws.cu issues the same MMAs and the same scalar arithmetic in the same order as pcvae_reward_tc.cu;
+    only the scheduling differs (warpgroup roles pipelined through mbarriers, sample counter running across tiles)."""
+    KR, L = _mods()
+    p = O.init_params("mlp", D, seed=N)
+    g = torch.Generator().manual_seed(N + M)
+    x = torch.rand(N, D, generator=g).cuda()
+    mask = (torch.rand(N, D, generator=g) < 0.3).float()
+    mask[:, -1] = 0
+    mask = mask.cuda()
+    im = torch.rand(M, N, D, generator=g).cuda()
+    eng, theta, fam = engine_for(p)
+    lib = L.load()
+    prev = lib.pcvae_set_reward_tensor_cores(2)
+    try:
+        R_lock, _ = eng.reward(theta, x, mask, im)
+        R_lock = R_lock.clone()
+        lib.pcvae_set_reward_tensor_cores(1)
+        R_ws, _ = eng.reward(theta, x, mask, im)
+        torch.cuda.synchronize()
+    finally:
+        lib.pcvae_set_reward_tensor_cores(prev)
+    assert torch.equal(R_ws, R_lock)
+    # and a second call reproduces it (no state left in the barriers' phases, no race between the roles)
+    R_again, _ = eng.reward(theta, x, mask, im)
+    assert torch.equal(R_again, R_ws)
 
 
 def test_large_batch_properties(train_tc):

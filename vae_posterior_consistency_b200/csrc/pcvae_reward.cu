@@ -374,13 +374,13 @@ static WsPlan plan_ws(const Layout& L, int N, int M) {
 
 using namespace pcvae;
 
-static int g_reward_tc = 1;   // tcgen05 path is the default for the MLP family
+static int g_reward_tc = 1;   // MLP family: 1 = warp-specialised tcgen05 kernel (default), 2 = lock-step tcgen05 kernel, 0 = FFMA
 
 extern "C" {
 
 int pcvae_set_reward_tensor_cores(int enable) {
     const int prev = g_reward_tc;
-    g_reward_tc = enable ? 1 : 0;
+    g_reward_tc = enable == 2 ? 2 : (enable ? 1 : 0);
     return prev;
 }
 
@@ -431,7 +431,8 @@ int pcvae_reward_chain(const pcvae_reward_params* p, void* stream) {
     k_scan<<<1, 1024, 0, st>>>(a.cnt, a.off, a.N);
     k_pairs<<<(a.N + 255) / 256, 256, 0, st>>>(a.cnt, a.off, a.cand, a.pairs, a.N);
     if (L.fam == PCVAE_FAMILY_PNP) k_reward_main<PCVAE_FAMILY_PNP><<<grid, NT, s2, st>>>(a);
-    else if (g_reward_tc) { if (int rc = reward_main_tc_launch(a, grid, st)) return rc; }
+    else if (g_reward_tc == 1) { if (int rc = reward_main_ws_launch(a, grid, st)) return rc; }
+    else if (g_reward_tc == 2) { if (int rc = reward_main_tc_launch(a, grid, st)) return rc; }
     else k_reward_main<PCVAE_FAMILY_MLP><<<grid, NT, s2, st>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(PCVAE_ECUDA, "reward_chain: main launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;

@@ -32,5 +32,8 @@ struct RewardArgs {
 
 // tcgen05 version of k_reward_main for the MLP family; returns a PCVAE_* code.
 int reward_main_tc_launch(const RewardArgs& a, int grid, cudaStream_t st);
+// warp-specialised tcgen05 version (pcvae_reward_ws.cu): same arithmetic in the same order, phases of consecutive
+// samples overlapped through mbarriers; bit-identical R
+int reward_main_ws_launch(const RewardArgs& a, int grid, cudaStream_t st);
 
 }  // namespace pcvae

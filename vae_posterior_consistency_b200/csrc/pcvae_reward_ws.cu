@@ -1,0 +1,476 @@
+// Warp-specialised tcgen05 reward main kernel for the MLP family (the default; pcvae_reward_tc.cu keeps the
+// lock-step version as the in-process cross-check, pcvae_reward.cu the FP32 FFMA one).
+//
+// Mathematics, tile shape (64 (row,candidate) pairs x {without, with target} = 128 tail evaluations), MMA
+// shapes, 3xTF32 operand split and the order of every floating-point operation are those of
+// k_reward_main_tc, so R is bit-identical to it.  What changes is who does what and when.  The lock-step kernel
+// runs construct -> MMA2 -> epilogue 2 -> MMA3 -> KL with all 16 warps doing each phase together between CTA
+// barriers; its tensor pipe was 43 % active because every phase boundary exposed a TMEM / shared-memory round
+// trip.  Here each warpgroup owns one phase for the whole launch and the phases of consecutive samples overlap
+// through mbarriers; there is no CTA-wide barrier after the prologue:
+//
+//   warpgroups 0,1  constructors   A2(g) = relu(h0 + v w_u [+ t w_T]) | 1 -> TMEM buffer g&1 (52 features each)
+//   warpgroup 2     epilogue 2     D2(g) -> ReLU -> hi / lo layer-3 operand in shared memory, then
+//                   + KL           D3(g-1) -> KL against the base posteriors -> per-pair accumulator -> R
+//   warpgroup 3     issuer         one elected lane of warp 12 issues every tcgen05.mma and tcgen05.commit and does
+//                                  nothing else (warps 13-15 only give their registers away):
+//                                  a tcgen05.mma does not retire from the issuing warp until the tensor pipe accepts it
+//                                  (measured: issuing MMA2 holds the warp for about as long as MMA2 runs), so an
+//                                  issuer that shares its warp with other work serialises that work with the MMAs
+//
+//   tensor pipe:  MMA2(g+1) | MMA3(g) | MMA2(g+2) | MMA3(g+1) | ...   (epilogue 2 reads D2(g+1) under MMA3(g)
+//                                                                      and writes A3(g+1) under MMA2(g+2))
+//
+// g counts the samples of all tiles of this CTA (tile-major), so the pipeline does not drain at tile ends.  The
+// constructors keep h0 and w_u of their row in registers (104 per thread): setmaxnreg moves registers from
+// warpgroup 3 to warpgroups 0,1.  Each role prefetches its own per-sample inputs (v, t; base posteriors of the
+// with-target rows) with cp.async into a private ring: no cross-thread hand-over, no barrier.
+//
+// Handshakes (producer -> consumer, arrivals per phase):
+//   full_A2[b]  constructors (256 threads)      -> issuer          empty_A2[b]  tcgen05.commit after MMA2 -> constructors
+//   full_D2     tcgen05.commit after MMA2       -> epilogue 2      empty_D2     epilogue 2 (128)          -> issuer
+//   full_A3     epilogue 2 (128)                -> issuer          empty_A3     tcgen05.commit after MMA3 -> epilogue 2
+//   full_D3     tcgen05.commit after MMA3       -> KL              empty_D3     KL (128)                  -> issuer
+// Every wait is bounded (status word + a CTA-wide abort flag: after one time-out all waits fall through).
+#include <cuda_pipeline.h>
+
+#include "pcvae_reward.cuh"
+#include "pcvae_tc.cuh"
+
+namespace pcvae {
+namespace rws {
+
+using namespace tc;
+
+constexpr int ROWS = 128;                 // UMMA M
+constexpr int K2 = 104, C2 = K2 / 4;      // layer-2 reduction (100 + bias + pad), 16-byte K chunks of B2
+constexpr int N2 = 64;                    // layer-2 outputs (50 + ones column + pad)
+constexpr int K3 = 56, C3 = K3 / 4;       // layer-3 reduction (50 + bias + pad)
+constexpr int N3 = 32;                    // layer-3 outputs (20 + pad)
+constexpr int TMEM_COLS = 512;
+constexpr int A2_COLS = 2 * K2;           // hi + lo of one A2 buffer
+constexpr int COL_D2 = 2 * A2_COLS, COL_D3 = COL_D2 + N2;
+constexpr int A_CHUNK = ROWS * 4;         // floats per 16-byte K chunk of the layer-3 operand in shared memory
+constexpr int KC = K2 / 2;                // features per constructor thread (52)
+constexpr int VT_NB = 4, VT_AHEAD = 3;    // ring of (v, t) per constructor thread
+constexpr int BT_NB = 3, BT_AHEAD = 2;    // ring of base posteriors per with-target row
+constexpr int BPITCH = BASEW + 4;         // 44 floats: 16-byte reads of consecutive rows hit distinct bank groups
+constexpr int NCON = 256;                 // constructor threads
+// setmaxnreg: the kernel launches with 128 registers per thread (512 threads; the launcher checks it); warpgroup 3
+// keeps 56 (it frees 128 * 72 = 9 216), warpgroups 0 and 1 grow to 160 (they take 256 * 32 = 8 192)
+constexpr int REG_LAUNCH = 128, REG_CON = 160, REG_ISSUE = 56;
+
+enum { FULL_A2 = 0, EMPTY_A2 = 2, FULL_D2 = 4, EMPTY_D2, FULL_A3, EMPTY_A3, FULL_D3, EMPTY_D3, NBAR };
+
+struct Ctl {
+    int* status;
+    volatile int* abort_s;
+};
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded in TIME (2 s), not in polls: try_wait is given a suspend-time hint, so how long one poll takes is up to the
+// hardware; a warp parked in try_wait leaves the issue slots of its scheduler to the warps that have work
+__device__ __forceinline__ void wait_on(uint64_t* bar, uint32_t parity, const Ctl& c) {
+    const uint32_t addr = smem_u32(bar);
+    uint64_t t0 = 0;
+    for (int i = 0;; ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
+        if (ok) return;
+        if ((i & 15) == 15) {
+            if (*c.abort_s) return;
+            const uint64_t t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) break;
+        }
+    }
+    *c.abort_s = 1;
+    if (c.status) { *reinterpret_cast<volatile int*>(c.status) = 5; __threadfence_system(); }
+}
+
+__device__ __forceinline__ void st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])) : "memory");
+}
+// 16 / 8 accumulator columns without the wait (the caller waits once for all its loads)
+__device__ __forceinline__ void ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void ld8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void ld4_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int R>
+__device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+__global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = a.L.D;
+    float* B2_hi = smem;                             // [C2][64][4]
+    float* B2_lo = B2_hi + C2 * N2 * 4;
+    float* B3_hi = B2_lo + C2 * N2 * 4;              // [C3][32][4]
+    float* B3_lo = B3_hi + C3 * N3 * 4;
+    float* A3_hi = B3_lo + C3 * N3 * 4;              // [C3][128][4]
+    float* A3_lo = A3_hi + C3 * A_CHUNK;
+    float* wT_s = A3_lo + C3 * A_CHUNK;              // [K2]
+    float* b0_s = wT_s + K2;                         // [64][44]   base posterior of the pair's row (without target)
+    float* bT_s = b0_s + NPAIR * BPITCH;             // [BT_NB][64][44]   base posteriors with the sampled target
+    float* vt_s = bT_s + BT_NB * NPAIR * BPITCH;     // [VT_NB][2][256]
+    float* kl_s = vt_s + VT_NB * 2 * NCON;           // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(kl_s + 2 * ROWS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    int* abort_s = reinterpret_cast<int*>(tmem_slot + 1);
+
+    // ---- one-time setup: weights (hi / lo, K-major core-matrix layout), barriers, TMEM ----
+    const float* th = a.theta;
+    for (int i = tid; i < C2 * N2 * 4; i += NT) {
+        const int c = i / (N2 * 4), n = (i >> 2) % N2, k = 4 * c + (i & 3);
+        float w = 0.f;
+        if (n < H2 && k < H1) w = th[a.L.W2 + n * H1 + k];
+        else if (n < H2 && k == H1) w = th[a.L.b2 + n];
+        else if (n == H2 && k == H1) w = 1.0f;           // ones column -> bias column of layer 3
+        B2_hi[i] = w;
+        B2_lo[i] = tf32_lo(w);
+    }
+    for (int i = tid; i < C3 * N3 * 4; i += NT) {
+        const int c = i / (N3 * 4), n = (i >> 2) % N3, k = 4 * c + (i & 3);
+        float w = 0.f;
+        if (n < LAT2 && k < H2) w = th[a.L.W3 + n * H2 + k];
+        else if (n < LAT2 && k == H2) w = th[a.L.b3 + n];
+        B3_hi[i] = w;
+        B3_lo[i] = tf32_lo(w);
+    }
+    for (int k = tid; k < K2; k += NT) wT_s[k] = (k < H1) ? th[a.L.W1 + (long)k * D + (D - 1)] : 0.f;
+    if (tid == 0) {
+        auto init = [&](int b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(count)); };
+        init(FULL_A2, NCON); init(FULL_A2 + 1, NCON); init(EMPTY_A2, 1); init(EMPTY_A2 + 1, 1);
+        init(FULL_D2, 1); init(EMPTY_D2, 128); init(FULL_A3, 128); init(EMPTY_A3, 1); init(FULL_D3, 1); init(EMPTY_D3, 128);
+        *abort_s = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const Ctl ctl{a.status, abort_s};
+
+    const int wg = warp >> 2, q = warp & 3;
+    const int row = 32 * q + lane, pi = row & (NPAIR - 1);
+    const bool withT = row >= NPAIR;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+
+    const int ptot = a.off[a.N];
+    const int ntiles = (ptot + NPAIR - 1) / NPAIR;
+    const int nt_cta = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int M = a.M;
+    const int G = nt_cta * M;                         // samples this CTA walks through, tile-major
+    // (row n, candidate u) of this thread's pair in the it-th tile of this CTA; pairs past the end evaluate pair (0, 0)
+    auto pair_of = [&](int it, int& n, int& u) -> bool {
+        const int p = (blockIdx.x + it * gridDim.x) * NPAIR + pi;
+        n = 0; u = 0;
+        if (p >= ptot) return false;
+        const int pr = a.pairs[p];
+        n = pr / CANDP;
+        u = pr - n * CANDP;
+        return true;
+    };
+
+    if (wg < 2) {
+        // ------------------------------------------------------------------------------------------
+        // constructors: features [52 * wg, 52 * wg + 52) of this thread's row
+        // ------------------------------------------------------------------------------------------
+        regs_inc<REG_CON>();
+        const int k0 = KC * wg;
+        float* vt_mine = vt_s + tid;                 // slot s: v at [s][0][tid], t at [s][1][tid]
+        int pf_it = 0, pf_m = 0, pf_n = 0, pf_u = 0, pf_slot = 0;
+        if (nt_cta > 0) pair_of(0, pf_n, pf_u);
+        auto prefetch = [&]() {
+            if (pf_it < nt_cta) {
+                const float* r = a.im + (long)pf_m * a.im_ss + (long)pf_n * D;
+                __pipeline_memcpy_async(vt_mine + (pf_slot * 2) * NCON, r + pf_u, 4);
+                if (withT) __pipeline_memcpy_async(vt_mine + (pf_slot * 2 + 1) * NCON, r + (D - 1), 4);
+                pf_slot = pf_slot + 1 == VT_NB ? 0 : pf_slot + 1;
+                if (++pf_m == M) {
+                    pf_m = 0;
+                    if (++pf_it < nt_cta) pair_of(pf_it, pf_n, pf_u);
+                }
+            }
+            __pipeline_commit();       // one group per call (possibly empty) keeps wait_prior counts uniform
+        };
+#pragma unroll
+        for (int i = 0; i < VT_AHEAD; ++i) prefetch();
+        uint32_t g = 0;
+        int slot = 0;
+        for (int it = 0; it < nt_cta; ++it) {
+            int n, u;
+            pair_of(it, n, u);
+            float H0r[KC], Ur[KC];
+            {
+                const float* h0 = a.base_in + (long)n * H1;
+#pragma unroll
+                for (int j = 0; j < KC; ++j) {
+                    const int k = k0 + j;
+                    float hv = 0.f, uv = 0.f;
+                    if (k < H1) { hv = h0[k]; uv = __ldg(th + a.L.W1 + (long)k * D + u); }
+                    else if (k == H1) hv = 1.0f;          // bias column
+                    H0r[j] = hv;
+                    Ur[j] = uv;
+                }
+            }
+            for (int m = 0; m < M; ++m, ++g) {
+                prefetch();
+                __pipeline_wait_prior(VT_AHEAD);          // the copies of sample g landed
+                const float v = vt_mine[(slot * 2) * NCON];
+                const float t = withT ? vt_mine[(slot * 2 + 1) * NCON] : 0.f;
+                slot = slot + 1 == VT_NB ? 0 : slot + 1;
+                const uint32_t b = g & 1u;
+                if (g >= 2) {                             // MMA2(g - 2) has read this buffer
+                    wait_on(bars + EMPTY_A2 + b, ((g >> 1) & 1u) ^ 1u, ctl);
+                    tc_fence_after();
+                }
+                const uint32_t ah0 = lane_addr + A2_COLS * b + k0, al0 = ah0 + K2;
+#pragma unroll
+                for (int part = 0; part < 4; ++part) {
+                    const int j0 = 16 * part, cnt = part < 3 ? 16 : 4;
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < cnt) {
+                            float pre = fmaf(v, Ur[j0 + j], H0r[j0 + j]);
+                            // rows without the target have t = 0: fmaf(0, w, pre) == pre, the product is skipped
+                            if (withT) pre = fmaf(t, wT_s[k0 + j0 + j], pre);
+                            const float h = fmaxf(pre, 0.f);
+                            hi[j] = h;
+                            lo[j] = tf32_lo(h);
+                        }
+                    if (part < 3) { tmem_st16(ah0 + j0, hi); tmem_st16(al0 + j0, lo); }
+                    else { st4(ah0 + j0, hi); st4(al0 + j0, lo); }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bars + FULL_A2 + b);
+            }
+        }
+        __pipeline_wait_prior(0);
+    } else if (wg == 2) {
+        // ------------------------------------------------------------------------------------------
+        // epilogue 2 of sample g, then the KL of sample g - 1 (off the tensor pipe's critical path: MMA3(g) needs only
+        // the operand written by epilogue 2).  Keeps the launch allocation of 128 registers.
+        // ------------------------------------------------------------------------------------------
+        float* a3h = A3_hi + row * 4;
+        float* a3l = A3_lo + row * 4;
+        float* b0_mine = b0_s + pi * BPITCH;
+        float* bT_mine = bT_s + pi * BPITCH;            // slot s at + s * NPAIR * BPITCH
+        int pf_it = 0, pf_m = 0, pf_n = 0, pf_u = 0, pf_slot = 0;
+        if (nt_cta > 0) pair_of(0, pf_n, pf_u);
+        auto prefetch = [&]() {                          // base posteriors of a with-target row, BT_AHEAD samples ahead
+            if (withT && pf_it < nt_cta) {
+                const float* src = a.baseT + ((long)pf_n * M + pf_m) * BASEW;
+                float* dst = bT_mine + pf_slot * NPAIR * BPITCH;
+#pragma unroll
+                for (int c = 0; c < BASEW / 4; ++c) __pipeline_memcpy_async(dst + 4 * c, src + 4 * c, 16);
+                pf_slot = pf_slot + 1 == BT_NB ? 0 : pf_slot + 1;
+                if (++pf_m == M) {
+                    pf_m = 0;
+                    if (++pf_it < nt_cta) pair_of(pf_it, pf_n, pf_u);
+                }
+            }
+            __pipeline_commit();
+        };
+#pragma unroll
+        for (int i = 0; i < BT_AHEAD; ++i) prefetch();
+        // KL state: walks the same (tile, sample) sequence one sample behind epilogue 2
+        uint32_t kg = 0;
+        int k_it = 0, k_m = 0, k_n = 0, k_u = 0, slot = 0;
+        bool k_valid = false;
+        float acc = 0.f;
+        auto kl_step = [&]() {
+            if (k_m == 0) {
+                k_valid = pair_of(k_it, k_n, k_u);
+                if (!withT) {                              // this thread is the only reader of its b0 row: no barrier
+                    const float4* src = reinterpret_cast<const float4*>(a.base0 + (long)k_n * BASEW);
+#pragma unroll
+                    for (int c = 0; c < BASEW / 4; ++c) *reinterpret_cast<float4*>(b0_mine + 4 * c) = src[c];
+                }
+                acc = 0.f;
+            }
+            prefetch();
+            __pipeline_wait_prior(BT_AHEAD);
+            const float* bt = withT ? bT_mine + slot * NPAIR * BPITCH : b0_mine;
+            slot = slot + 1 == BT_NB ? 0 : slot + 1;
+            float bv[BASEW];
+#pragma unroll
+            for (int c = 0; c < BASEW / 4; ++c) {
+                const float4 x4 = *reinterpret_cast<const float4*>(bt + 4 * c);
+                bv[4 * c] = x4.x; bv[4 * c + 1] = x4.y; bv[4 * c + 2] = x4.z; bv[4 * c + 3] = x4.w;
+            }
+            wait_on(bars + FULL_D3, kg & 1u, ctl);
+            tc_fence_after();
+            uint32_t o[LAT2];
+            ld16_nowait(lane_addr + COL_D3, o);
+            ld4_nowait(lane_addr + COL_D3 + 16, o + 16);
+            ld_wait();
+            tc_fence_before();
+            mbar_arrive(bars + EMPTY_D3);
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < LAT; ++l) {
+                const float mu = __uint_as_float(o[l]), lv = __uint_as_float(o[LAT + l]);
+                const float dm = mu - bv[l];
+                sum += (((dm * dm) * bv[2 * LAT + l] + expf(lv) * bv[3 * LAT + l] - 1.0f) - lv) + bv[LAT + l];
+            }
+            float* kb = kl_s + (kg & 1u) * ROWS;
+            kb[row] = 0.5f * sum;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!withT) {              // approx_KL += KL_I; approx_KL -= KL_II   (evaluate.py:537-538)
+                acc += kb[pi];
+                acc -= kb[NPAIR + pi];
+            }
+            ++kg;
+            if (++k_m == M) {
+                if (!withT && k_valid) a.R[(long)k_n * (D - 1) + k_u] = acc / (float)M;   // evaluate.py:540
+                k_m = 0;
+                ++k_it;
+            }
+        };
+        for (uint32_t g = 0; g < (uint32_t)G; ++g) {
+            wait_on(bars + FULL_D2, g & 1u, ctl);
+            tc_fence_after();
+            uint32_t d[K3];
+            ld16_nowait(lane_addr + COL_D2, d);
+            ld16_nowait(lane_addr + COL_D2 + 16, d + 16);
+            ld16_nowait(lane_addr + COL_D2 + 32, d + 32);
+            ld8_nowait(lane_addr + COL_D2 + 48, d + 48);
+            ld_wait();
+            tc_fence_before();
+            mbar_arrive(bars + EMPTY_D2);             // D2 is in registers: MMA2(g + 1) may overwrite it
+            if (g >= 1) wait_on(bars + EMPTY_A3, (g - 1) & 1u, ctl);     // MMA3(g - 1) has read the operand
+#pragma unroll
+            for (int c = 0; c < C3; ++c) {
+                float4 hi, lo;
+                hi.x = fmaxf(__uint_as_float(d[4 * c + 0]), 0.f); hi.y = fmaxf(__uint_as_float(d[4 * c + 1]), 0.f);
+                hi.z = fmaxf(__uint_as_float(d[4 * c + 2]), 0.f); hi.w = fmaxf(__uint_as_float(d[4 * c + 3]), 0.f);
+                lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
+                *reinterpret_cast<float4*>(a3h + c * A_CHUNK) = hi;
+                *reinterpret_cast<float4*>(a3l + c * A_CHUNK) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(bars + FULL_A3);
+            if (g >= 1) kl_step();                    // KL of sample g - 1, under MMA2(g + 1)
+        }
+        if (G > 0) kl_step();
+        __pipeline_wait_prior(0);
+    } else {
+        // ------------------------------------------------------------------------------------------
+        // warpgroup 3: its registers go to the constructors; one elected lane of warp 12 is the issuer
+        // ------------------------------------------------------------------------------------------
+        regs_dec<REG_ISSUE>();
+        if (warp == 12) {
+            constexpr uint32_t IDESC2 = make_idesc(ROWS, N2), IDESC3 = make_idesc(ROWS, N3);
+            constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16, A3_LBO = A_CHUNK * 4;
+            // descriptors of k-step 0; a k-step (8 tf32 = two 16-byte chunks) advances the 16-byte-unit address field
+            const uint64_t dB2h = make_desc(smem_u32(B2_hi), B2_LBO, SBO), dB2l = make_desc(smem_u32(B2_lo), B2_LBO, SBO);
+            const uint64_t dB3h = make_desc(smem_u32(B3_hi), B3_LBO, SBO), dB3l = make_desc(smem_u32(B3_lo), B3_LBO, SBO);
+            const uint64_t dA3h = make_desc(smem_u32(A3_hi), A3_LBO, SBO), dA3l = make_desc(smem_u32(A3_lo), A3_LBO, SBO);
+            constexpr uint64_t B2_STEP = (2 * B2_LBO) >> 4, B3_STEP = (2 * B3_LBO) >> 4, A3_STEP = (2 * A3_LBO) >> 4;
+            auto issue_mma2 = [&](uint32_t buf) {     // D2 = A2[buf] * B2^T, 3xTF32 (single thread)
+                const uint32_t ah = tmem + A2_COLS * buf, al = ah + K2;
+#pragma unroll
+                for (int ks = 0; ks < K2 / 8; ++ks) {
+                    mma_tf32_ts(tmem + COL_D2, al + 8 * ks, dB2h + ks * B2_STEP, IDESC2, ks > 0);
+                    mma_tf32_ts(tmem + COL_D2, ah + 8 * ks, dB2l + ks * B2_STEP, IDESC2, 1);
+                    mma_tf32_ts(tmem + COL_D2, ah + 8 * ks, dB2h + ks * B2_STEP, IDESC2, 1);
+                }
+                mma_commit(bars + FULL_D2);
+                mma_commit(bars + EMPTY_A2 + buf);
+            };
+            auto issue_mma3 = [&]() {                 // D3 = A3 * B3^T, 3xTF32 (single thread)
+#pragma unroll
+                for (int ks = 0; ks < K3 / 8; ++ks) {
+                    mma_tf32_ss(tmem + COL_D3, dA3l + ks * A3_STEP, dB3h + ks * B3_STEP, IDESC3, ks > 0);
+                    mma_tf32_ss(tmem + COL_D3, dA3h + ks * A3_STEP, dB3l + ks * B3_STEP, IDESC3, 1);
+                    mma_tf32_ss(tmem + COL_D3, dA3h + ks * A3_STEP, dB3h + ks * B3_STEP, IDESC3, 1);
+                }
+                mma_commit(bars + FULL_D3);
+                mma_commit(bars + EMPTY_A3);
+            };
+            if (elect_one()) {
+                if (G > 0) {
+                    wait_on(bars + FULL_A2, 0, ctl);
+                    tc_fence_after();
+                    issue_mma2(0);
+                }
+                for (uint32_t g = 0; g < (uint32_t)G; ++g) {
+                    if (g + 1 < (uint32_t)G) {
+                        wait_on(bars + EMPTY_D2, g & 1u, ctl);                                   // epilogue 2 holds D2(g) in registers
+                        wait_on(bars + FULL_A2 + ((g + 1) & 1u), ((g + 1) >> 1) & 1u, ctl);      // A2(g + 1) is written
+                        tc_fence_after();
+                        issue_mma2((g + 1) & 1u);
+                    }
+                    wait_on(bars + FULL_A3, g & 1u, ctl);                                        // A3(g) is written
+                    if (g >= 1) wait_on(bars + EMPTY_D3, (g - 1) & 1u, ctl);                     // the KL holds D3(g - 1) in registers
+                    tc_fence_after();
+                    issue_mma3();
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+static size_t smem_bytes() {
+    size_t f = 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + 2 * (size_t)C3 * A_CHUNK + K2 + (size_t)NPAIR * BPITCH +
+               (size_t)BT_NB * NPAIR * BPITCH + (size_t)VT_NB * 2 * NCON + 2 * ROWS;
+    return f * sizeof(float) + NBAR * sizeof(uint64_t) + 16 + 128;
+}
+
+}  // namespace rws
+
+int reward_main_ws_launch(const RewardArgs& a, int grid, cudaStream_t st) {
+    const size_t sm = rws::smem_bytes();
+    if (sm > MAX_SMEM) return fail(PCVAE_EINVAL, "reward_main_ws: shared memory %zu B exceeds %d", sm, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(rws::k_reward_main_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reward_main_ws: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    // setmaxnreg.inc waits for registers that only exist if the launch allocation is what the budget assumes
+    static int regs = -1;
+    if (regs < 0) {
+        cudaFuncAttributes fa;
+        if ((e = cudaFuncGetAttributes(&fa, rws::k_reward_main_ws)) != cudaSuccess) return fail(PCVAE_ECUDA, "reward_main_ws: cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+        regs = fa.numRegs;
+    }
+    if (regs != rws::REG_LAUNCH) return fail(PCVAE_EINVAL, "reward_main_ws: built with %d registers per thread, the register budget needs %d", regs, rws::REG_LAUNCH);
+    rws::k_reward_main_ws<<<grid, NT, sm, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reward_main_ws: launch: %s", cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+}  // namespace pcvae
