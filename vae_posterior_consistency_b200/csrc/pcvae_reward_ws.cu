@@ -3,36 +3,45 @@
 //
 // Mathematics, tile shape (64 (row,candidate) pairs x {without, with target} = 128 tail evaluations), MMA
 // shapes, 3xTF32 operand split and the order of every floating-point operation are those of
-// k_reward_main_tc, so R is bit-identical to it.  What changes is who does what and when.  The lock-step kernel
-// runs construct -> MMA2 -> epilogue 2 -> MMA3 -> KL with all 16 warps doing each phase together between CTA
-// barriers; its tensor pipe was 43 % active because every phase boundary exposed a TMEM / shared-memory round
-// trip.  Here each warpgroup owns one phase for the whole launch and the phases of consecutive samples overlap
-// through mbarriers; there is no CTA-wide barrier after the prologue:
+// k_reward_main_tc, so R is bit-identical to it.  What changes is who does what and when, and where the layer-3
+// operand lives.  The lock-step kernel runs construct -> MMA2 -> epilogue 2 -> MMA3 -> KL with all 16 warps doing
+// each phase together between CTA barriers (tensor pipe 43 % active).  Here each warpgroup owns one phase for the
+// whole launch and the phases of consecutive samples overlap through mbarriers; no CTA-wide barrier after the prologue:
 //
-//   warpgroups 0,1  constructors   A2(g) = relu(h0 + v w_u [+ t w_T]) | 1 -> TMEM buffer g&1 (52 features each)
-//   warpgroup 2     epilogue 2     D2(g) -> ReLU -> hi / lo layer-3 operand in shared memory, then
+//   warpgroup 0     constructor    features [0, 48)   of A2(g) = relu(h0 + v w_u [+ t w_T]) | 1  -> TMEM (K-steps 0-5)
+//   warpgroup 1     constructor    features [48, 104) of A2(g)                                   -> TMEM (K-steps 6-12)
+//   warpgroup 2     epilogue 2     D2(g) -> ReLU -> hi written over D2 in place, lo next to it (TMEM), then
 //                   + KL           D3(g-1) -> KL against the base posteriors -> per-pair accumulator -> R
 //   warpgroup 3     issuer         one elected lane of warp 12 issues every tcgen05.mma and tcgen05.commit and does
-//                                  nothing else (warps 13-15 only give their registers away):
-//                                  a tcgen05.mma does not retire from the issuing warp until the tensor pipe accepts it
-//                                  (measured: issuing MMA2 holds the warp for about as long as MMA2 runs), so an
-//                                  issuer that shares its warp with other work serialises that work with the MMAs
+//                                  nothing else (warps 13-15 only give their registers away): a tcgen05.mma does not
+//                                  retire from the issuing warp until the tensor pipe accepts it (measured: issuing
+//                                  MMA2 holds the warp for about as long as MMA2 runs), so an issuer that shares its
+//                                  warp with other work serialises that work with the MMAs
 //
-//   tensor pipe:  MMA2(g+1) | MMA3(g) | MMA2(g+2) | MMA3(g+1) | ...   (epilogue 2 reads D2(g+1) under MMA3(g)
-//                                                                      and writes A3(g+1) under MMA2(g+2))
+//   tensor pipe:  MMA2(g+1) K-steps 0-5 | K-steps 6-12 | MMA3(g) | MMA2(g+2) ...
+//
+// Both layers take their A operand from tensor memory.  (A first version kept the layer-3 operand in shared memory as
+// the lock-step kernel does: MMA3 then ran at ~70 cycles per instruction instead of 16 -- the tensor core fetches
+// shared-memory operands at ~64 B/cycle and an M = 128 A tile is 4 KB per K-step -- and took as long as MMA2.)
+// TMEM (512 columns): A2 hi [0,104) lo [104,208), ONE buffer: the constructors of the first K-half refill it for sample
+// g+1 as soon as the first six K-steps of MMA2(g) have completed (tcgen05.commit between the halves), while the other
+// half is still being read; X[b] = D2 accumulator / layer-3 operand hi [.., +64) and lo [+64, +120), two buffers at 208
+// and 328; D3[b] at 448 + 32 b.  X and D3 alternate by sample, and the in-order tensor pipe orders MMA3(g) before
+// MMA2(g+2), so epilogue 2 needs no "empty" handshake.
 //
 // g counts the samples of all tiles of this CTA (tile-major), so the pipeline does not drain at tile ends.  The
-// constructors keep h0 and w_u of their row in registers (104 per thread): setmaxnreg moves registers from
+// constructors keep h0 and w_u of their row in registers (96 / 104 per thread): setmaxnreg moves registers from
 // warpgroup 3 to warpgroups 0,1.  Each role prefetches its own per-sample inputs (v, t; base posteriors of the
 // with-target rows) with cp.async into a private ring: no cross-thread hand-over, no barrier.
 //
 // Handshakes (producer -> consumer, arrivals per phase):
-//   full_A2[b]  constructors (256 threads)      -> issuer          empty_A2[b]  tcgen05.commit after MMA2 -> constructors
-//   full_D2     tcgen05.commit after MMA2       -> epilogue 2      empty_D2     epilogue 2 (128)          -> issuer
-//   full_A3     epilogue 2 (128)                -> issuer          empty_A3     tcgen05.commit after MMA3 -> epilogue 2
-//   full_D3     tcgen05.commit after MMA3       -> KL              empty_D3     KL (128)                  -> issuer
-// Every wait is bounded (status word + a CTA-wide abort flag: after one time-out all waits fall through).
+//   full_H[h]   constructors of half h (128)    -> issuer          empty_H[h]   tcgen05.commit after the half's K-steps -> constructors
+//   full_D2[b]  tcgen05.commit after MMA2       -> epilogue 2      full_A3[b]   epilogue 2 (128)          -> issuer
+//   full_D3[b]  tcgen05.commit after MMA3       -> KL              empty_D3[b]  KL (128)                  -> issuer
+// Every wait is bounded in time (status word + a CTA-wide abort flag: after one time-out all waits fall through).
 #include <cuda_pipeline.h>
+
+#include <type_traits>
 
 #include "pcvae_reward.cuh"
 #include "pcvae_tc.cuh"
@@ -48,10 +57,10 @@ constexpr int N2 = 64;                    // layer-2 outputs (50 + ones column +
 constexpr int K3 = 56, C3 = K3 / 4;       // layer-3 reduction (50 + bias + pad)
 constexpr int N3 = 32;                    // layer-3 outputs (20 + pad)
 constexpr int TMEM_COLS = 512;
-constexpr int A2_COLS = 2 * K2;           // hi + lo of one A2 buffer
-constexpr int COL_D2 = 2 * A2_COLS, COL_D3 = COL_D2 + N2;
-constexpr int A_CHUNK = ROWS * 4;         // floats per 16-byte K chunk of the layer-3 operand in shared memory
-constexpr int KC = K2 / 2;                // features per constructor thread (52)
+constexpr int COL_X = 2 * K2, X_COLS = N2 + K3;   // X[b] at COL_X + b * X_COLS: accumulator / hi [0,64), lo [64,120)
+constexpr int COL_D3 = COL_X + 2 * X_COLS;        // D3[b] at COL_D3 + b * N3
+static_assert(COL_D3 + 2 * N3 == TMEM_COLS, "TMEM map");
+constexpr int KH0 = 48, KH1 = K2 - KH0;   // features of the two constructor warpgroups (K-steps 0-5 and 6-12)
 constexpr int VT_NB = 4, VT_AHEAD = 3;    // ring of (v, t) per constructor thread
 constexpr int BT_NB = 3, BT_AHEAD = 2;    // ring of base posteriors per with-target row
 constexpr int BPITCH = BASEW + 4;         // 44 floats: 16-byte reads of consecutive rows hit distinct bank groups
@@ -60,7 +69,7 @@ constexpr int NCON = 256;                 // constructor threads
 // keeps 56 (it frees 128 * 72 = 9 216), warpgroups 0 and 1 grow to 160 (they take 256 * 32 = 8 192)
 constexpr int REG_LAUNCH = 128, REG_CON = 160, REG_ISSUE = 56;
 
-enum { FULL_A2 = 0, EMPTY_A2 = 2, FULL_D2 = 4, EMPTY_D2, FULL_A3, EMPTY_A3, FULL_D3, EMPTY_D3, NBAR };
+enum { FULL_H = 0, EMPTY_H = 2, FULL_D2 = 4, FULL_A3 = 6, FULL_D3 = 8, EMPTY_D3 = 10, NBAR = 12 };
 
 struct Ctl {
     int* status;
@@ -127,9 +136,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
     float* B2_lo = B2_hi + C2 * N2 * 4;
     float* B3_hi = B2_lo + C2 * N2 * 4;              // [C3][32][4]
     float* B3_lo = B3_hi + C3 * N3 * 4;
-    float* A3_hi = B3_lo + C3 * N3 * 4;              // [C3][128][4]
-    float* A3_lo = A3_hi + C3 * A_CHUNK;
-    float* wT_s = A3_lo + C3 * A_CHUNK;              // [K2]
+    float* wT_s = B3_lo + C3 * N3 * 4;               // [K2]
     float* b0_s = wT_s + K2;                         // [64][44]   base posterior of the pair's row (without target)
     float* bT_s = b0_s + NPAIR * BPITCH;             // [BT_NB][64][44]   base posteriors with the sampled target
     float* vt_s = bT_s + BT_NB * NPAIR * BPITCH;     // [VT_NB][2][256]
@@ -160,8 +167,10 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
     for (int k = tid; k < K2; k += NT) wT_s[k] = (k < H1) ? th[a.L.W1 + (long)k * D + (D - 1)] : 0.f;
     if (tid == 0) {
         auto init = [&](int b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(count)); };
-        init(FULL_A2, NCON); init(FULL_A2 + 1, NCON); init(EMPTY_A2, 1); init(EMPTY_A2 + 1, 1);
-        init(FULL_D2, 1); init(EMPTY_D2, 128); init(FULL_A3, 128); init(EMPTY_A3, 1); init(FULL_D3, 1); init(EMPTY_D3, 128);
+        for (int b = 0; b < 2; ++b) {
+            init(FULL_H + b, 128); init(EMPTY_H + b, 1); init(FULL_D2 + b, 1); init(FULL_A3 + b, 128);
+            init(FULL_D3 + b, 1); init(EMPTY_D3 + b, 128);
+        }
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -199,88 +208,90 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
 
     if (wg < 2) {
         // ------------------------------------------------------------------------------------------
-        // constructors: features [52 * wg, 52 * wg + 52) of this thread's row
+        // constructors: warpgroup 0 features [0, 48), warpgroup 1 features [48, 104) of this thread's row
         // ------------------------------------------------------------------------------------------
         regs_inc<REG_CON>();
-        const int k0 = KC * wg;
-        float* vt_mine = vt_s + tid;                 // slot s: v at [s][0][tid], t at [s][1][tid]
-        int pf_it = 0, pf_m = 0, pf_n = 0, pf_u = 0, pf_slot = 0;
-        if (nt_cta > 0) pair_of(0, pf_n, pf_u);
-        auto prefetch = [&]() {
-            if (pf_it < nt_cta) {
-                const float* r = a.im + (long)pf_m * a.im_ss + (long)pf_n * D;
-                __pipeline_memcpy_async(vt_mine + (pf_slot * 2) * NCON, r + pf_u, 4);
-                if (withT) __pipeline_memcpy_async(vt_mine + (pf_slot * 2 + 1) * NCON, r + (D - 1), 4);
-                pf_slot = pf_slot + 1 == VT_NB ? 0 : pf_slot + 1;
-                if (++pf_m == M) {
-                    pf_m = 0;
-                    if (++pf_it < nt_cta) pair_of(pf_it, pf_n, pf_u);
+        auto role = [&](auto k0c, auto knc) {
+            constexpr int K0 = decltype(k0c)::value, KN = decltype(knc)::value;
+            const int h = K0 == 0 ? 0 : 1;
+            float* vt_mine = vt_s + tid;                 // slot s: v at [s][0][tid], t at [s][1][tid]
+            int pf_it = 0, pf_m = 0, pf_n = 0, pf_u = 0, pf_slot = 0;
+            if (nt_cta > 0) pair_of(0, pf_n, pf_u);
+            auto prefetch = [&]() {
+                if (pf_it < nt_cta) {
+                    const float* r = a.im + (long)pf_m * a.im_ss + (long)pf_n * D;
+                    __pipeline_memcpy_async(vt_mine + (pf_slot * 2) * NCON, r + pf_u, 4);
+                    if (withT) __pipeline_memcpy_async(vt_mine + (pf_slot * 2 + 1) * NCON, r + (D - 1), 4);
+                    pf_slot = pf_slot + 1 == VT_NB ? 0 : pf_slot + 1;
+                    if (++pf_m == M) {
+                        pf_m = 0;
+                        if (++pf_it < nt_cta) pair_of(pf_it, pf_n, pf_u);
+                    }
+                }
+                __pipeline_commit();       // one group per call (possibly empty) keeps wait_prior counts uniform
+            };
+#pragma unroll
+            for (int i = 0; i < VT_AHEAD; ++i) prefetch();
+            uint32_t g = 0;
+            int slot = 0;
+            const uint32_t ah0 = lane_addr + K0, al0 = ah0 + K2;
+            for (int it = 0; it < nt_cta; ++it) {
+                int n, u;
+                pair_of(it, n, u);
+                float H0r[KN], Ur[KN];
+                {
+                    const float* h0 = a.base_in + (long)n * H1;
+#pragma unroll
+                    for (int j = 0; j < KN; ++j) {
+                        const int k = K0 + j;            // compile-time: the bias and pad columns cost no registers
+                        float hv = 0.f, uv = 0.f;
+                        if (k < H1) { hv = h0[k]; uv = __ldg(th + a.L.W1 + (long)k * D + u); }
+                        else if (k == H1) hv = 1.0f;          // bias column
+                        H0r[j] = hv;
+                        Ur[j] = uv;
+                    }
+                }
+                for (int m = 0; m < M; ++m, ++g) {
+                    prefetch();
+                    __pipeline_wait_prior(VT_AHEAD);          // the copies of sample g landed
+                    const float v = vt_mine[(slot * 2) * NCON];
+                    const float t = withT ? vt_mine[(slot * 2 + 1) * NCON] : 0.f;
+                    slot = slot + 1 == VT_NB ? 0 : slot + 1;
+                    if (g >= 1) {                             // the K-steps of MMA2(g - 1) that read this half have completed
+                        wait_on(bars + EMPTY_H + h, (g - 1) & 1u, ctl);
+                        tc_fence_after();
+                    }
+#pragma unroll
+                    for (int j0 = 0; j0 < KN; j0 += 16) {
+                        const int cnt = KN - j0 >= 16 ? 16 : 8;
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < cnt) {
+                                float pre = fmaf(v, Ur[j0 + j], H0r[j0 + j]);
+                                // rows without the target have t = 0: fmaf(0, w, pre) == pre, the product is skipped
+                                if (withT) pre = fmaf(t, wT_s[K0 + j0 + j], pre);
+                                const float hh = fmaxf(pre, 0.f);
+                                hi[j] = hh;
+                                lo[j] = tf32_lo(hh);
+                            }
+                        if (cnt == 16) { tmem_st16(ah0 + j0, hi); tmem_st16(al0 + j0, lo); }
+                        else { tmem_st8(ah0 + j0, hi); tmem_st8(al0 + j0, lo); }
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bars + FULL_H + h);
                 }
             }
-            __pipeline_commit();       // one group per call (possibly empty) keeps wait_prior counts uniform
+            __pipeline_wait_prior(0);
         };
-#pragma unroll
-        for (int i = 0; i < VT_AHEAD; ++i) prefetch();
-        uint32_t g = 0;
-        int slot = 0;
-        for (int it = 0; it < nt_cta; ++it) {
-            int n, u;
-            pair_of(it, n, u);
-            float H0r[KC], Ur[KC];
-            {
-                const float* h0 = a.base_in + (long)n * H1;
-#pragma unroll
-                for (int j = 0; j < KC; ++j) {
-                    const int k = k0 + j;
-                    float hv = 0.f, uv = 0.f;
-                    if (k < H1) { hv = h0[k]; uv = __ldg(th + a.L.W1 + (long)k * D + u); }
-                    else if (k == H1) hv = 1.0f;          // bias column
-                    H0r[j] = hv;
-                    Ur[j] = uv;
-                }
-            }
-            for (int m = 0; m < M; ++m, ++g) {
-                prefetch();
-                __pipeline_wait_prior(VT_AHEAD);          // the copies of sample g landed
-                const float v = vt_mine[(slot * 2) * NCON];
-                const float t = withT ? vt_mine[(slot * 2 + 1) * NCON] : 0.f;
-                slot = slot + 1 == VT_NB ? 0 : slot + 1;
-                const uint32_t b = g & 1u;
-                if (g >= 2) {                             // MMA2(g - 2) has read this buffer
-                    wait_on(bars + EMPTY_A2 + b, ((g >> 1) & 1u) ^ 1u, ctl);
-                    tc_fence_after();
-                }
-                const uint32_t ah0 = lane_addr + A2_COLS * b + k0, al0 = ah0 + K2;
-#pragma unroll
-                for (int part = 0; part < 4; ++part) {
-                    const int j0 = 16 * part, cnt = part < 3 ? 16 : 4;
-                    float hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < cnt) {
-                            float pre = fmaf(v, Ur[j0 + j], H0r[j0 + j]);
-                            // rows without the target have t = 0: fmaf(0, w, pre) == pre, the product is skipped
-                            if (withT) pre = fmaf(t, wT_s[k0 + j0 + j], pre);
-                            const float h = fmaxf(pre, 0.f);
-                            hi[j] = h;
-                            lo[j] = tf32_lo(h);
-                        }
-                    if (part < 3) { tmem_st16(ah0 + j0, hi); tmem_st16(al0 + j0, lo); }
-                    else { st4(ah0 + j0, hi); st4(al0 + j0, lo); }
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(bars + FULL_A2 + b);
-            }
-        }
-        __pipeline_wait_prior(0);
+        if (wg == 0) role(std::integral_constant<int, 0>{}, std::integral_constant<int, KH0>{});
+        else role(std::integral_constant<int, KH0>{}, std::integral_constant<int, KH1>{});
     } else if (wg == 2) {
         // ------------------------------------------------------------------------------------------
         // epilogue 2 of sample g, then the KL of sample g - 1 (off the tensor pipe's critical path: MMA3(g) needs only
         // the operand written by epilogue 2).  Keeps the launch allocation of 128 registers.
         // ------------------------------------------------------------------------------------------
-        float* a3h = A3_hi + row * 4;
-        float* a3l = A3_lo + row * 4;
         float* b0_mine = b0_s + pi * BPITCH;
         float* bT_mine = bT_s + pi * BPITCH;            // slot s at + s * NPAIR * BPITCH
         int pf_it = 0, pf_m = 0, pf_n = 0, pf_u = 0, pf_slot = 0;
@@ -326,14 +337,15 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                 const float4 x4 = *reinterpret_cast<const float4*>(bt + 4 * c);
                 bv[4 * c] = x4.x; bv[4 * c + 1] = x4.y; bv[4 * c + 2] = x4.z; bv[4 * c + 3] = x4.w;
             }
-            wait_on(bars + FULL_D3, kg & 1u, ctl);
+            const uint32_t kb_ = kg & 1u;
+            wait_on(bars + FULL_D3 + kb_, (kg >> 1) & 1u, ctl);
             tc_fence_after();
             uint32_t o[LAT2];
-            ld16_nowait(lane_addr + COL_D3, o);
-            ld4_nowait(lane_addr + COL_D3 + 16, o + 16);
+            ld16_nowait(lane_addr + COL_D3 + N3 * kb_, o);
+            ld4_nowait(lane_addr + COL_D3 + N3 * kb_ + 16, o + 16);
             ld_wait();
             tc_fence_before();
-            mbar_arrive(bars + EMPTY_D3);
+            mbar_arrive(bars + EMPTY_D3 + kb_);
             float sum = 0.f;
 #pragma unroll
             for (int l = 0; l < LAT; ++l) {
@@ -356,28 +368,33 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
             }
         };
         for (uint32_t g = 0; g < (uint32_t)G; ++g) {
-            wait_on(bars + FULL_D2, g & 1u, ctl);
+            const uint32_t b = g & 1u;
+            const uint32_t xa = lane_addr + COL_X + X_COLS * b;
+            wait_on(bars + FULL_D2 + b, (g >> 1) & 1u, ctl);
             tc_fence_after();
             uint32_t d[K3];
-            ld16_nowait(lane_addr + COL_D2, d);
-            ld16_nowait(lane_addr + COL_D2 + 16, d + 16);
-            ld16_nowait(lane_addr + COL_D2 + 32, d + 32);
-            ld8_nowait(lane_addr + COL_D2 + 48, d + 48);
+            ld16_nowait(xa, d);
+            ld16_nowait(xa + 16, d + 16);
+            ld16_nowait(xa + 32, d + 32);
+            ld8_nowait(xa + 48, d + 48);
             ld_wait();
-            tc_fence_before();
-            mbar_arrive(bars + EMPTY_D2);             // D2 is in registers: MMA2(g + 1) may overwrite it
-            if (g >= 1) wait_on(bars + EMPTY_A3, (g - 1) & 1u, ctl);     // MMA3(g - 1) has read the operand
+            // ReLU; hi goes back over the accumulator columns it came from (this thread's lane, its own 56 columns), lo next to it
 #pragma unroll
-            for (int c = 0; c < C3; ++c) {
-                float4 hi, lo;
-                hi.x = fmaxf(__uint_as_float(d[4 * c + 0]), 0.f); hi.y = fmaxf(__uint_as_float(d[4 * c + 1]), 0.f);
-                hi.z = fmaxf(__uint_as_float(d[4 * c + 2]), 0.f); hi.w = fmaxf(__uint_as_float(d[4 * c + 3]), 0.f);
-                lo.x = tf32_lo(hi.x); lo.y = tf32_lo(hi.y); lo.z = tf32_lo(hi.z); lo.w = tf32_lo(hi.w);
-                *reinterpret_cast<float4*>(a3h + c * A_CHUNK) = hi;
-                *reinterpret_cast<float4*>(a3l + c * A_CHUNK) = lo;
+            for (int j0 = 0; j0 < K3; j0 += 16) {
+                const int cnt = K3 - j0 >= 16 ? 16 : 8;
+                float hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < cnt) {
+                        hi[j] = fmaxf(__uint_as_float(d[j0 + j]), 0.f);
+                        lo[j] = tf32_lo(hi[j]);
+                    }
+                if (cnt == 16) { tmem_st16(xa + j0, hi); tmem_st16(xa + N2 + j0, lo); }
+                else { tmem_st8(xa + j0, hi); tmem_st8(xa + N2 + j0, lo); }
             }
-            fence_async_smem();
-            mbar_arrive(bars + FULL_A3);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bars + FULL_A3 + b);
             if (g >= 1) kl_step();                    // KL of sample g - 1, under MMA2(g + 1)
         }
         if (G > 0) kl_step();
@@ -389,50 +406,60 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
         regs_dec<REG_ISSUE>();
         if (warp == 12) {
             constexpr uint32_t IDESC2 = make_idesc(ROWS, N2), IDESC3 = make_idesc(ROWS, N3);
-            constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16, A3_LBO = A_CHUNK * 4;
+            constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16;
             // descriptors of k-step 0; a k-step (8 tf32 = two 16-byte chunks) advances the 16-byte-unit address field
             const uint64_t dB2h = make_desc(smem_u32(B2_hi), B2_LBO, SBO), dB2l = make_desc(smem_u32(B2_lo), B2_LBO, SBO);
             const uint64_t dB3h = make_desc(smem_u32(B3_hi), B3_LBO, SBO), dB3l = make_desc(smem_u32(B3_lo), B3_LBO, SBO);
-            const uint64_t dA3h = make_desc(smem_u32(A3_hi), A3_LBO, SBO), dA3l = make_desc(smem_u32(A3_lo), A3_LBO, SBO);
-            constexpr uint64_t B2_STEP = (2 * B2_LBO) >> 4, B3_STEP = (2 * B3_LBO) >> 4, A3_STEP = (2 * A3_LBO) >> 4;
-            auto issue_mma2 = [&](uint32_t buf) {     // D2 = A2[buf] * B2^T, 3xTF32 (single thread)
-                const uint32_t ah = tmem + A2_COLS * buf, al = ah + K2;
+            constexpr uint64_t B2_STEP = (2 * B2_LBO) >> 4, B3_STEP = (2 * B3_LBO) >> 4;
+            const uint32_t ah = tmem, al = tmem + K2;
+            // D2 = A2 * B2^T into X[b], 3xTF32, K-steps [KS0, KS1) (single thread)
+            auto issue_mma2 = [&](uint32_t b, auto ks0c, auto ks1c) {
+                constexpr int KS0 = decltype(ks0c)::value, KS1 = decltype(ks1c)::value;
+                const uint32_t dcol = tmem + COL_X + X_COLS * b;
 #pragma unroll
-                for (int ks = 0; ks < K2 / 8; ++ks) {
-                    mma_tf32_ts(tmem + COL_D2, al + 8 * ks, dB2h + ks * B2_STEP, IDESC2, ks > 0);
-                    mma_tf32_ts(tmem + COL_D2, ah + 8 * ks, dB2l + ks * B2_STEP, IDESC2, 1);
-                    mma_tf32_ts(tmem + COL_D2, ah + 8 * ks, dB2h + ks * B2_STEP, IDESC2, 1);
+                for (int ks = KS0; ks < KS1; ++ks) {
+                    mma_tf32_ts(dcol, al + 8 * ks, dB2h + ks * B2_STEP, IDESC2, ks > 0);
+                    mma_tf32_ts(dcol, ah + 8 * ks, dB2l + ks * B2_STEP, IDESC2, 1);
+                    mma_tf32_ts(dcol, ah + 8 * ks, dB2h + ks * B2_STEP, IDESC2, 1);
                 }
-                mma_commit(bars + FULL_D2);
-                mma_commit(bars + EMPTY_A2 + buf);
             };
-            auto issue_mma3 = [&]() {                 // D3 = A3 * B3^T, 3xTF32 (single thread)
+            using IC0 = std::integral_constant<int, 0>;
+            using ICH = std::integral_constant<int, KH0 / 8>;
+            using ICE = std::integral_constant<int, K2 / 8>;
+            // sample g: first half as soon as its features are written, then the second; the commit between them
+            // hands the first half of the A2 buffer back to its constructors while the second is still being read
+            auto mma2_of = [&](uint32_t g) {
+                const uint32_t b = g & 1u;
+                wait_on(bars + FULL_H, g & 1u, ctl);
+                tc_fence_after();
+                issue_mma2(b, IC0{}, ICH{});
+                mma_commit(bars + EMPTY_H);
+                wait_on(bars + FULL_H + 1, g & 1u, ctl);
+                tc_fence_after();
+                issue_mma2(b, ICH{}, ICE{});
+                mma_commit(bars + EMPTY_H + 1);
+                mma_commit(bars + FULL_D2 + b);
+            };
+            // D3[b] = relu(D2)[b] * B3^T, 3xTF32, A operand from tensor memory (single thread)
+            auto mma3_of = [&](uint32_t g) {
+                const uint32_t b = g & 1u;
+                const uint32_t xh = tmem + COL_X + X_COLS * b, xl = xh + N2, dcol = tmem + COL_D3 + N3 * b;
+                wait_on(bars + FULL_A3 + b, (g >> 1) & 1u, ctl);                               // epilogue 2 wrote the operand
+                if (g >= 2) wait_on(bars + EMPTY_D3 + b, ((g >> 1) & 1u) ^ 1u, ctl);           // the KL holds D3(g - 2) in registers
+                tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < K3 / 8; ++ks) {
-                    mma_tf32_ss(tmem + COL_D3, dA3l + ks * A3_STEP, dB3h + ks * B3_STEP, IDESC3, ks > 0);
-                    mma_tf32_ss(tmem + COL_D3, dA3h + ks * A3_STEP, dB3l + ks * B3_STEP, IDESC3, 1);
-                    mma_tf32_ss(tmem + COL_D3, dA3h + ks * A3_STEP, dB3h + ks * B3_STEP, IDESC3, 1);
+                    mma_tf32_ts(dcol, xl + 8 * ks, dB3h + ks * B3_STEP, IDESC3, ks > 0);
+                    mma_tf32_ts(dcol, xh + 8 * ks, dB3l + ks * B3_STEP, IDESC3, 1);
+                    mma_tf32_ts(dcol, xh + 8 * ks, dB3h + ks * B3_STEP, IDESC3, 1);
                 }
-                mma_commit(bars + FULL_D3);
-                mma_commit(bars + EMPTY_A3);
+                mma_commit(bars + FULL_D3 + b);
             };
             if (elect_one()) {
-                if (G > 0) {
-                    wait_on(bars + FULL_A2, 0, ctl);
-                    tc_fence_after();
-                    issue_mma2(0);
-                }
+                if (G > 0) mma2_of(0);
                 for (uint32_t g = 0; g < (uint32_t)G; ++g) {
-                    if (g + 1 < (uint32_t)G) {
-                        wait_on(bars + EMPTY_D2, g & 1u, ctl);                                   // epilogue 2 holds D2(g) in registers
-                        wait_on(bars + FULL_A2 + ((g + 1) & 1u), ((g + 1) >> 1) & 1u, ctl);      // A2(g + 1) is written
-                        tc_fence_after();
-                        issue_mma2((g + 1) & 1u);
-                    }
-                    wait_on(bars + FULL_A3, g & 1u, ctl);                                        // A3(g) is written
-                    if (g >= 1) wait_on(bars + EMPTY_D3, (g - 1) & 1u, ctl);                     // the KL holds D3(g - 1) in registers
-                    tc_fence_after();
-                    issue_mma3();
+                    if (g + 1 < (uint32_t)G) mma2_of(g + 1);
+                    mma3_of(g);
                 }
             }
             __syncwarp();
@@ -447,7 +474,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
 }
 
 static size_t smem_bytes() {
-    size_t f = 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + 2 * (size_t)C3 * A_CHUNK + K2 + (size_t)NPAIR * BPITCH +
+    size_t f = 2 * (size_t)C2 * N2 * 4 + 2 * (size_t)C3 * N3 * 4 + K2 + (size_t)NPAIR * BPITCH +
                (size_t)BT_NB * NPAIR * BPITCH + (size_t)VT_NB * 2 * NCON + 2 * ROWS;
     return f * sizeof(float) + NBAR * sizeof(uint64_t) + 16 + 128;
 }
