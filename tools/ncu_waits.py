@@ -20,6 +20,8 @@ for r in rows[2:]:
     if "SYNCS.PHASECHK" in src:
         nm = (region, "WAIT " + name_of(src))
         if cur is None or cur[0] != nm: cur = [nm, 0, 0, 0]; segs.append(cur)
+    elif "NANOSLEEP" in src and cur is not None and cur[0][1].startswith("WAIT"):
+        pass
     elif cur is None or cur[0][1].startswith("WAIT") and not any(k in src for k in ("BRA", "BREAK", "BSYNC", "BSSY", "NOP", "LDS", "ISETP", "VIADD", "IADD3", "LOP3", "CS2R", "S2UR", "UMOV", "ULEA", "IMAD", "R2UR", "MOV", "PLOP3", "SEL")):
         cur = [(region, "code@" + src[:28]), 0, 0, 0]; segs.append(cur)
     cur[1] += s; cur[2] += 1; cur[3] += "UTCHMMA" in src

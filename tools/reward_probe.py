@@ -2,7 +2,11 @@
 import sys, time
 import torch
 sys.path.insert(0, ".")
-from vae_posterior_consistency_b200 import kernels as KR, lib as L
+import os
+from vae_posterior_consistency_b200 import lib as L
+if os.environ.get("PCVAE_LIB"):
+    L.LIB_PATH = os.path.abspath(os.environ["PCVAE_LIB"])
+from vae_posterior_consistency_b200 import kernels as KR
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2, 1]

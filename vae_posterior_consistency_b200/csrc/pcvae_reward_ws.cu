@@ -37,7 +37,8 @@
 // Handshakes (producer -> consumer, arrivals per phase):
 //   full_H[h]   constructors of half h (128)    -> issuer          empty_H[h]   tcgen05.commit after the half's K-steps -> constructors
 //   full_D2[b]  tcgen05.commit after MMA2       -> epilogue 2      full_A3[b]   epilogue 2 (128)          -> issuer
-//   full_D3[b]  tcgen05.commit after MMA3       -> KL              empty_D3[b]  KL (128)                  -> issuer
+//   full_D3[b]  tcgen05.commit after MMA3       -> KL              (no empty_D3: the KL of sample g-2 precedes epilogue 2 of
+//                                                                   sample g in the same threads, so full_A3(g) implies D3[b] was read)
 // Every wait is bounded in time (status word + a CTA-wide abort flag: after one time-out all waits fall through).
 #include <cuda_pipeline.h>
 
@@ -69,7 +70,7 @@ constexpr int NCON = 256;                 // constructor threads
 // keeps 56 (it frees 128 * 72 = 9 216), warpgroups 0 and 1 grow to 160 (they take 256 * 32 = 8 192)
 constexpr int REG_LAUNCH = 128, REG_CON = 160, REG_ISSUE = 56;
 
-enum { FULL_H = 0, EMPTY_H = 2, FULL_D2 = 4, FULL_A3 = 6, FULL_D3 = 8, EMPTY_D3 = 10, NBAR = 12 };
+enum { FULL_H = 0, EMPTY_H = 2, FULL_D2 = 4, FULL_A3 = 6, FULL_D3 = 8, NBAR = 10 };
 
 struct Ctl {
     int* status;
@@ -86,7 +87,8 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __device__ __forceinline__ void wait_on(uint64_t* bar, uint32_t parity, const Ctl& c) {
     const uint32_t addr = smem_u32(bar);
     uint64_t t0 = 0;
-    for (int i = 0;; ++i) {
+#pragma unroll 1
+    for (int i = 0;; ++i) {            // not unrolled: the hot loops of all roles have to stay in the instruction cache
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
@@ -120,6 +122,9 @@ __device__ __forceinline__ void ld8_nowait(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void ld4_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void ld2_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
 }
 __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
         auto init = [&](int b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(count)); };
         for (int b = 0; b < 2; ++b) {
             init(FULL_H + b, 128); init(EMPTY_H + b, 1); init(FULL_D2 + b, 1); init(FULL_A3 + b, 128);
-            init(FULL_D3 + b, 1); init(EMPTY_D3 + b, 128);
+            init(FULL_D3 + b, 1);
         }
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -267,13 +272,23 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                         float hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
+                            if (j < cnt) hi[j] = fmaf(v, Ur[j0 + j], H0r[j0 + j]);
+                        // rows without the target (TMEM lane quarters 0, 1) have t = 0: fmaf(0, w, pre) == pre, and the
+                        // warp-uniform branch skips the products and the loads of w_T
+                        if (withT) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                if (j < cnt) {
+                                    const float4 w4 = *reinterpret_cast<const float4*>(wT_s + K0 + j0 + j);
+                                    hi[j] = fmaf(t, w4.x, hi[j]); hi[j + 1] = fmaf(t, w4.y, hi[j + 1]);
+                                    hi[j + 2] = fmaf(t, w4.z, hi[j + 2]); hi[j + 3] = fmaf(t, w4.w, hi[j + 3]);
+                                }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
                             if (j < cnt) {
-                                float pre = fmaf(v, Ur[j0 + j], H0r[j0 + j]);
-                                // rows without the target have t = 0: fmaf(0, w, pre) == pre, the product is skipped
-                                if (withT) pre = fmaf(t, wT_s[K0 + j0 + j], pre);
-                                const float hh = fmaxf(pre, 0.f);
-                                hi[j] = hh;
-                                lo[j] = tf32_lo(hh);
+                                hi[j] = fmaxf(hi[j], 0.f);
+                                lo[j] = tf32_lo(hi[j]);
                             }
                         if (cnt == 16) { tmem_st16(ah0 + j0, hi); tmem_st16(al0 + j0, lo); }
                         else { tmem_st8(ah0 + j0, hi); tmem_st8(al0 + j0, lo); }
@@ -285,8 +300,11 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
             }
             __pipeline_wait_prior(0);
         };
-        if (wg == 0) role(std::integral_constant<int, 0>{}, std::integral_constant<int, KH0>{});
-        else role(std::integral_constant<int, KH0>{}, std::integral_constant<int, KH1>{});
+        using IC0 = std::integral_constant<int, 0>;
+        using ICA = std::integral_constant<int, KH0>;
+        using ICB = std::integral_constant<int, KH1>;
+        if (wg == 0) role(IC0{}, ICA{});
+        else role(ICA{}, ICB{});
     } else if (wg == 2) {
         // ------------------------------------------------------------------------------------------
         // epilogue 2 of sample g, then the KL of sample g - 1 (off the tensor pipe's critical path: MMA3(g) needs only
@@ -345,7 +363,6 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
             ld4_nowait(lane_addr + COL_D3 + N3 * kb_ + 16, o + 16);
             ld_wait();
             tc_fence_before();
-            mbar_arrive(bars + EMPTY_D3 + kb_);
             float sum = 0.f;
 #pragma unroll
             for (int l = 0; l < LAT; ++l) {
@@ -367,21 +384,29 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                 ++k_it;
             }
         };
+        {       // lo columns [48, 56) of both layer-3 operand buffers: 48, 49 are rewritten per sample, 50-55 stay zero
+            const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            tmem_st8(lane_addr + COL_X + N2 + 48, z);
+            tmem_st8(lane_addr + COL_X + X_COLS + N2 + 48, z);
+            tmem_st_wait();
+        }
         for (uint32_t g = 0; g < (uint32_t)G; ++g) {
             const uint32_t b = g & 1u;
             const uint32_t xa = lane_addr + COL_X + X_COLS * b;
             wait_on(bars + FULL_D2 + b, (g >> 1) & 1u, ctl);
             tc_fence_after();
-            uint32_t d[K3];
+            // columns [0, 50) only: column 50 is the constant 1 the MMA itself produced (its hi is already in place, its
+            // lo is 0) and columns 51-55 are exact zeros (zero weight rows); their lo columns were zeroed once above
+            uint32_t d[H2 + 2];
             ld16_nowait(xa, d);
             ld16_nowait(xa + 16, d + 16);
             ld16_nowait(xa + 32, d + 32);
-            ld8_nowait(xa + 48, d + 48);
+            ld2_nowait(xa + 48, d + 48);
             ld_wait();
-            // ReLU; hi goes back over the accumulator columns it came from (this thread's lane, its own 56 columns), lo next to it
+            // ReLU; hi goes back over the accumulator columns it came from (this thread's lane, its own columns), lo next to it
 #pragma unroll
-            for (int j0 = 0; j0 < K3; j0 += 16) {
-                const int cnt = K3 - j0 >= 16 ? 16 : 8;
+            for (int j0 = 0; j0 < H2; j0 += 16) {
+                const int cnt = H2 - j0 >= 16 ? 16 : 2;
                 float hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -390,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                         lo[j] = tf32_lo(hi[j]);
                     }
                 if (cnt == 16) { tmem_st16(xa + j0, hi); tmem_st16(xa + N2 + j0, lo); }
-                else { tmem_st8(xa + j0, hi); tmem_st8(xa + N2 + j0, lo); }
+                else { tmem_st2(xa + j0, hi); tmem_st2(xa + N2 + j0, lo); }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -445,7 +470,6 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                 const uint32_t b = g & 1u;
                 const uint32_t xh = tmem + COL_X + X_COLS * b, xl = xh + N2, dcol = tmem + COL_D3 + N3 * b;
                 wait_on(bars + FULL_A3 + b, (g >> 1) & 1u, ctl);                               // epilogue 2 wrote the operand
-                if (g >= 2) wait_on(bars + EMPTY_D3 + b, ((g >> 1) & 1u) ^ 1u, ctl);           // the KL holds D3(g - 2) in registers
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < K3 / 8; ++ks) {
@@ -456,10 +480,10 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                 mma_commit(bars + FULL_D3 + b);
             };
             if (elect_one()) {
-                if (G > 0) mma2_of(0);
-                for (uint32_t g = 0; g < (uint32_t)G; ++g) {
-                    if (g + 1 < (uint32_t)G) mma2_of(g + 1);
-                    mma3_of(g);
+                // MMA2(0), then per sample MMA2(g + 1) | MMA3(g); one loop so that the issue code exists once
+                for (uint32_t g = 0; g <= (uint32_t)G; ++g) {
+                    if (g < (uint32_t)G) mma2_of(g);
+                    if (g >= 1) mma3_of(g - 1);
                 }
             }
             __syncwarp();
