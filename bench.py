@@ -45,7 +45,8 @@ KERNEL_FLOP_BRANCH_ROW = {
 KERNEL_DRAM_BYTES = {"k_enc_fwd_tc": 142.1e6, "k_dec_fwd_tc": 136.6e6, "k_dec_bwd_tc": 118.7e6, "k_wgrad_tc[dec]": 235.4e6,
                      "k_enc_bwd_tc": 49.5e6, "k_wgrad_tc[enc]": 238.9e6}
 FLOP_REWARD_TRIPLE = 24_460       # Reg_VAE incremental form: 2 tail evaluations + amortised bases
-# dram bytes of k_reward_main_tc at cfg5 (100k rows x 100 candidates x 50 samples), profiles/r02_ncu_summary.md
+# dram bytes of the reward main kernel at cfg5 (100k rows x 100 candidates x 50 samples), profiles/r02_ncu_summary.md
+# (same reads in the lock-step and the warp-specialised kernel: imputations and base posteriors, once each)
 REWARD_DRAM_BYTES = 2.983e9       # read 2.935 GB (imputations 2.02 GB + per-(row, sample) base posteriors) + write 0.048 GB
 
 #: the workload both arms are run on (identical `config` in the two JSON lines)
@@ -844,8 +845,10 @@ def run_ours(args):
                     "note": f"rows streamed in {args.reward_chunks} blocks, copies overlapped with the kernel of the previous block; "
                             "R bit-identical to the resident call"},
             "roofline": {"bound": "tensor",
-                         "kernel": "k_reward_main_tc (tcgen05.mma kind::tf32, fp32-accurate 3xTF32 split; the two dense layers of the "
-                                   "tail MLP) + k_reward_prep: whole pcvae_reward_chain call",
+                         "kernel": "k_reward_main_ws (warp-specialised: constructor / epilogue+KL / issuer warpgroups pipelined "
+                                   "through mbarriers; tcgen05.mma kind::tf32, fp32-accurate 3xTF32 split, both dense layers "
+                                   "of the tail MLP with the A operand in tensor memory) + k_reward_prep: whole "
+                                   "pcvae_reward_chain call",
                          "achieved": r_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": r_tflops / tensor_peak,
                          "peak_source": tensor_src, "traffic": REWARD_DRAM_BYTES,
                          "vs_fp32_ffma": {"peak": ffma_tflops, "frac": r_tflops / ffma_tflops,

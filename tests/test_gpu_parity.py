@@ -471,9 +471,11 @@ def test_reward_is_row_shardable_bit_exact(reward_tc):
 
 
 @pytest.mark.parametrize("N,D,M", [(333, 20, 6), (70, 101, 3), (5, 2, 1), (1500, 100, 50), (9, 8, 2)])
-def test_warp_specialised_reward_kernel_equals_lockstep_kernel_bit_for_bit(N, D, M):
-    """pcvae_reward_ws.cu issues the same MMAs and the same scalar arithmetic in the same order as pcvae_reward_tc.cu;
-    only the scheduling differs (warpgroup roles pipelined through mbarriers, sample counter running across tiles)."""
+def test_warp_specialised_reward_kernel_against_lockstep_kernel(N, D, M):
+    """pcvae_reward_ws.cu computes what pcvae_reward_tc.cu computes with the same operand split and scalar arithmetic;
+    the scheduling differs (warpgroup roles pipelined through mbarriers, sample counter running across tiles) and layer 3
+    keeps hi*lo in a second accumulator, so the two agree to rounding of the layer-3 outputs (observed difference
+    printed), and the warp-specialised kernel reproduces itself bit for bit."""
     KR, L = _mods()
     p = O.init_params("mlp", D, seed=N)
     g = torch.Generator().manual_seed(N + M)
@@ -493,7 +495,12 @@ def test_warp_specialised_reward_kernel_equals_lockstep_kernel_bit_for_bit(N, D,
         torch.cuda.synchronize()
     finally:
         lib.pcvae_set_reward_tensor_cores(prev)
-    assert torch.equal(R_ws, R_lock)
+    sel = mask[:, :-1] != 0
+    assert torch.equal(R_ws[sel], R_lock[sel]) and torch.all(R_ws[sel] == -1e4)
+    diff = float((R_ws - R_lock)[~sel].abs().max()) if (~sel).any() else 0.0
+    scale = float(R_lock[~sel].abs().max()) if (~sel).any() else 0.0
+    print(f"reward ws vs lock-step N={N} D={D} M={M}: max |diff| {diff:.3e} at scale {scale:.3e}")
+    assert diff <= 2e-5 * scale + 1e-6
     # and a second call reproduces it (no state left in the barriers' phases, no race between the roles)
     R_again, _ = eng.reward(theta, x, mask, im)
     assert torch.equal(R_again, R_ws)

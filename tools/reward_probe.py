@@ -36,4 +36,4 @@ for mode in modes:
     print(f"mode {mode}: {ms:.2f} ms  {rows * 100 * M / ms / 1e6:.2f} G triples/s", flush=True)
 if len(out) == 2:
     a, b = list(out.values())
-    print("bit-identical:", torch.equal(a, b), float((a - b).abs().max()))
+    print("bit-identical:", torch.equal(a, b), "max |diff|", float((a - b).abs().max()), "scale", float(a.abs().max()))

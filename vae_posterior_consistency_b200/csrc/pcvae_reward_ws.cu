@@ -1,9 +1,10 @@
 // Warp-specialised tcgen05 reward main kernel for the MLP family (the default; pcvae_reward_tc.cu keeps the
 // lock-step version as the in-process cross-check, pcvae_reward.cu the FP32 FFMA one).
 //
-// Mathematics, tile shape (64 (row,candidate) pairs x {without, with target} = 128 tail evaluations), MMA
-// shapes, 3xTF32 operand split and the order of every floating-point operation are those of
-// k_reward_main_tc, so R is bit-identical to it.  What changes is who does what and when, and where the layer-3
+// Mathematics, tile shape (64 (row,candidate) pairs x {without, with target} = 128 tail evaluations), the 3xTF32
+// operand split and the order of the scalar arithmetic are those of k_reward_main_tc; layer 3 sums its three partial
+// products in two accumulators instead of one, so R agrees with that kernel to the last few ulps of the layer-3
+// outputs, not bit for bit (tests/test_gpu_parity.py).  What changes is who does what and when, and where the layer-3
 // operand lives.  The lock-step kernel runs construct -> MMA2 -> epilogue 2 -> MMA3 -> KL with all 16 warps doing
 // each phase together between CTA barriers (tensor pipe 43 % active).  Here each warpgroup owns one phase for the
 // whole launch and the phases of consecutive samples overlap through mbarriers; no CTA-wide barrier after the prologue:
@@ -26,7 +27,9 @@
 // TMEM (512 columns): A2 hi [0,104) lo [104,208), ONE buffer: the constructors of the first K-half refill it for sample
 // g+1 as soon as the first six K-steps of MMA2(g) have completed (tcgen05.commit between the halves), while the other
 // half is still being read; X[b] = D2 accumulator / layer-3 operand hi [.., +64) and lo [+64, +120), two buffers at 208
-// and 328; D3[b] at 448 + 32 b.  X and D3 alternate by sample, and the in-order tensor pipe orders MMA3(g) before
+// and 328; D3 at 448 (64 columns: layer 3 issues a_hi * [b_hi; b_lo] as ONE N = 64 instruction and a_lo * b_hi as an
+// N = 32 one -- 14 instead of 21 instructions per sample, an M = 128 tf32 MMA costs ~40 cycles for any N <= 64 -- and the
+// KL adds the two column halves).  X alternates by sample and the in-order tensor pipe orders MMA3(g) before
 // MMA2(g+2), so epilogue 2 needs no "empty" handshake.
 //
 // g counts the samples of all tiles of this CTA (tile-major), so the pipeline does not drain at tile ends.  The
@@ -37,8 +40,8 @@
 // Handshakes (producer -> consumer, arrivals per phase):
 //   full_H[h]   constructors of half h (128)    -> issuer          empty_H[h]   tcgen05.commit after the half's K-steps -> constructors
 //   full_D2[b]  tcgen05.commit after MMA2       -> epilogue 2      full_A3[b]   epilogue 2 (128)          -> issuer
-//   full_D3[b]  tcgen05.commit after MMA3       -> KL              (no empty_D3: the KL of sample g-2 precedes epilogue 2 of
-//                                                                   sample g in the same threads, so full_A3(g) implies D3[b] was read)
+//   full_D3     tcgen05.commit after MMA3       -> KL              (no empty_D3: the KL of sample g-1 precedes the full_A3(g)
+//                                                                   arrival in the same threads, so full_A3(g) implies D3 was read)
 // Every wait is bounded in time (status word + a CTA-wide abort flag: after one time-out all waits fall through).
 #include <cuda_pipeline.h>
 
@@ -59,7 +62,7 @@ constexpr int K3 = 56, C3 = K3 / 4;       // layer-3 reduction (50 + bias + pad)
 constexpr int N3 = 32;                    // layer-3 outputs (20 + pad)
 constexpr int TMEM_COLS = 512;
 constexpr int COL_X = 2 * K2, X_COLS = N2 + K3;   // X[b] at COL_X + b * X_COLS: accumulator / hi [0,64), lo [64,120)
-constexpr int COL_D3 = COL_X + 2 * X_COLS;        // D3[b] at COL_D3 + b * N3
+constexpr int COL_D3 = COL_X + 2 * X_COLS;        // D3: [0,32) = hi*hi + lo*hi, [32,64) = hi*lo (one buffer)
 static_assert(COL_D3 + 2 * N3 == TMEM_COLS, "TMEM map");
 constexpr int KH0 = 48, KH1 = K2 - KH0;   // features of the two constructor warpgroups (K-steps 0-5 and 6-12)
 constexpr int VT_NB = 4, VT_AHEAD = 3;    // ring of (v, t) per constructor thread
@@ -70,7 +73,7 @@ constexpr int NCON = 256;                 // constructor threads
 // keeps 56 (it frees 128 * 72 = 9 216), warpgroups 0 and 1 grow to 160 (they take 256 * 32 = 8 192)
 constexpr int REG_LAUNCH = 128, REG_CON = 160, REG_ISSUE = 56;
 
-enum { FULL_H = 0, EMPTY_H = 2, FULL_D2 = 4, FULL_A3 = 6, FULL_D3 = 8, NBAR = 10 };
+enum { FULL_H = 0, EMPTY_H = 2, FULL_D2 = 4, FULL_A3 = 6, FULL_D3 = 8, NBAR = 9 };
 
 struct Ctl {
     int* status;
@@ -139,9 +142,8 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
     const int D = a.L.D;
     float* B2_hi = smem;                             // [C2][64][4]
     float* B2_lo = B2_hi + C2 * N2 * 4;
-    float* B3_hi = B2_lo + C2 * N2 * 4;              // [C3][32][4]
-    float* B3_lo = B3_hi + C3 * N3 * 4;
-    float* wT_s = B3_lo + C3 * N3 * 4;               // [K2]
+    float* B3_s = B2_lo + C2 * N2 * 4;               // [C3][64][4]
+    float* wT_s = B3_s + 2 * C3 * N3 * 4;            // [K2]
     float* b0_s = wT_s + K2;                         // [64][44]   base posterior of the pair's row (without target)
     float* bT_s = b0_s + NPAIR * BPITCH;             // [BT_NB][64][44]   base posteriors with the sampled target
     float* vt_s = bT_s + BT_NB * NPAIR * BPITCH;     // [VT_NB][2][256]
@@ -161,21 +163,23 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
         B2_hi[i] = w;
         B2_lo[i] = tf32_lo(w);
     }
+    // layer 3: hi and lo images stacked along N ([C3][64][4]: rows 0-31 hi, rows 32-63 lo), so that a_hi * [b_hi; b_lo]
+    // is ONE N = 64 instruction (an M = 128 tf32 MMA costs ~40 cycles for any N <= 64: the A read from tensor memory)
     for (int i = tid; i < C3 * N3 * 4; i += NT) {
         const int c = i / (N3 * 4), n = (i >> 2) % N3, k = 4 * c + (i & 3);
         float w = 0.f;
         if (n < LAT2 && k < H2) w = th[a.L.W3 + n * H2 + k];
         else if (n < LAT2 && k == H2) w = th[a.L.b3 + n];
-        B3_hi[i] = w;
-        B3_lo[i] = tf32_lo(w);
+        B3_s[(c * 2 * N3 + n) * 4 + (i & 3)] = w;
+        B3_s[(c * 2 * N3 + N3 + n) * 4 + (i & 3)] = tf32_lo(w);
     }
     for (int k = tid; k < K2; k += NT) wT_s[k] = (k < H1) ? th[a.L.W1 + (long)k * D + (D - 1)] : 0.f;
     if (tid == 0) {
         auto init = [&](int b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(count)); };
         for (int b = 0; b < 2; ++b) {
             init(FULL_H + b, 128); init(EMPTY_H + b, 1); init(FULL_D2 + b, 1); init(FULL_A3 + b, 128);
-            init(FULL_D3 + b, 1);
         }
+        init(FULL_D3, 1);
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -355,14 +359,17 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                 const float4 x4 = *reinterpret_cast<const float4*>(bt + 4 * c);
                 bv[4 * c] = x4.x; bv[4 * c + 1] = x4.y; bv[4 * c + 2] = x4.z; bv[4 * c + 3] = x4.w;
             }
-            const uint32_t kb_ = kg & 1u;
-            wait_on(bars + FULL_D3 + kb_, (kg >> 1) & 1u, ctl);
+            wait_on(bars + FULL_D3, kg & 1u, ctl);
             tc_fence_after();
-            uint32_t o[LAT2];
-            ld16_nowait(lane_addr + COL_D3 + N3 * kb_, o);
-            ld4_nowait(lane_addr + COL_D3 + N3 * kb_ + 16, o + 16);
+            uint32_t o[LAT2], o2[LAT2];
+            ld16_nowait(lane_addr + COL_D3, o);
+            ld4_nowait(lane_addr + COL_D3 + 16, o + 16);
+            ld16_nowait(lane_addr + COL_D3 + N3, o2);
+            ld4_nowait(lane_addr + COL_D3 + N3 + 16, o2 + 16);
             ld_wait();
             tc_fence_before();
+#pragma unroll
+            for (int l = 0; l < LAT2; ++l) o[l] = __float_as_uint(__uint_as_float(o[l]) + __uint_as_float(o2[l]));
             float sum = 0.f;
 #pragma unroll
             for (int l = 0; l < LAT; ++l) {
@@ -418,9 +425,11 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                 else { tmem_st2(xa + j0, hi); tmem_st2(xa + N2 + j0, lo); }
             }
             tmem_st_wait();
+            // KL of sample g - 1 BEFORE the arrival: MMA3(g) overwrites the D3 this reads, and MMA3(g) waits for full_A3(g).
+            // The issuer is busy with MMA2(g + 1) for longer than both take.
+            if (g >= 1) kl_step();
             tc_fence_before();
             mbar_arrive(bars + FULL_A3 + b);
-            if (g >= 1) kl_step();                    // KL of sample g - 1, under MMA2(g + 1)
         }
         if (G > 0) kl_step();
         __pipeline_wait_prior(0);
@@ -430,11 +439,11 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
         // ------------------------------------------------------------------------------------------
         regs_dec<REG_ISSUE>();
         if (warp == 12) {
-            constexpr uint32_t IDESC2 = make_idesc(ROWS, N2), IDESC3 = make_idesc(ROWS, N3);
-            constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = N3 * 16;
+            constexpr uint32_t IDESC2 = make_idesc(ROWS, N2), IDESC3 = make_idesc(ROWS, N3), IDESC3S = make_idesc(ROWS, 2 * N3);
+            constexpr uint32_t SBO = 128, B2_LBO = N2 * 16, B3_LBO = 2 * N3 * 16;
             // descriptors of k-step 0; a k-step (8 tf32 = two 16-byte chunks) advances the 16-byte-unit address field
             const uint64_t dB2h = make_desc(smem_u32(B2_hi), B2_LBO, SBO), dB2l = make_desc(smem_u32(B2_lo), B2_LBO, SBO);
-            const uint64_t dB3h = make_desc(smem_u32(B3_hi), B3_LBO, SBO), dB3l = make_desc(smem_u32(B3_lo), B3_LBO, SBO);
+            const uint64_t dB3 = make_desc(smem_u32(B3_s), B3_LBO, SBO);
             constexpr uint64_t B2_STEP = (2 * B2_LBO) >> 4, B3_STEP = (2 * B3_LBO) >> 4;
             const uint32_t ah = tmem, al = tmem + K2;
             // D2 = A2 * B2^T into X[b], 3xTF32, K-steps [KS0, KS1) (single thread)
@@ -465,19 +474,18 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
                 mma_commit(bars + EMPTY_H + 1);
                 mma_commit(bars + FULL_D2 + b);
             };
-            // D3[b] = relu(D2)[b] * B3^T, 3xTF32, A operand from tensor memory (single thread)
+            // D3 = relu(D2)[b] * B3^T, 3xTF32 as a_hi * [b_hi; b_lo] (N = 64) + a_lo * b_hi (N = 32), A from tensor memory
             auto mma3_of = [&](uint32_t g) {
                 const uint32_t b = g & 1u;
-                const uint32_t xh = tmem + COL_X + X_COLS * b, xl = xh + N2, dcol = tmem + COL_D3 + N3 * b;
-                wait_on(bars + FULL_A3 + b, (g >> 1) & 1u, ctl);                               // epilogue 2 wrote the operand
+                const uint32_t xh = tmem + COL_X + X_COLS * b, xl = xh + N2, dcol = tmem + COL_D3;
+                wait_on(bars + FULL_A3 + b, (g >> 1) & 1u, ctl);      // epilogue 2 wrote the operand (and the KL read D3(g - 1))
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < K3 / 8; ++ks) {
-                    mma_tf32_ts(dcol, xl + 8 * ks, dB3h + ks * B3_STEP, IDESC3, ks > 0);
-                    mma_tf32_ts(dcol, xh + 8 * ks, dB3l + ks * B3_STEP, IDESC3, 1);
-                    mma_tf32_ts(dcol, xh + 8 * ks, dB3h + ks * B3_STEP, IDESC3, 1);
+                    mma_tf32_ts(dcol, xh + 8 * ks, dB3 + ks * B3_STEP, IDESC3S, ks > 0);
+                    mma_tf32_ts(dcol, xl + 8 * ks, dB3 + ks * B3_STEP, IDESC3, 1);
                 }
-                mma_commit(bars + FULL_D3 + b);
+                mma_commit(bars + FULL_D3);
             };
             if (elect_one()) {
                 // MMA2(0), then per sample MMA2(g + 1) | MMA3(g); one loop so that the issue code exists once
