@@ -9,8 +9,10 @@
 // each phase together between CTA barriers (tensor pipe 43 % active).  Here each warpgroup owns one phase for the
 // whole launch and the phases of consecutive samples overlap through mbarriers; no CTA-wide barrier after the prologue:
 //
-//   warpgroup 0     constructor    features [0, 48)   of A2(g) = relu(h0 + v w_u [+ t w_T]) | 1  -> TMEM (K-steps 0-5)
-//   warpgroup 1     constructor    features [48, 104) of A2(g)                                   -> TMEM (K-steps 6-12)
+//   warpgroup 0     constructor    features [0, 56)   of A2(g) = relu(h0 + v w_u [+ t w_T]) | 1  -> TMEM (K-steps 0-6)
+//   warpgroup 1     constructor    features [56, 104) of A2(g)                                   -> TMEM (K-steps 7-12)
+//                                  (the second half has the shorter deadline -- MMA3 + the first half of the next MMA2 --
+//                                  and gets the smaller share: 44 real features + the bias column)
 //   warpgroup 2     epilogue 2     D2(g) -> ReLU -> hi written over D2 in place, lo next to it (TMEM), then
 //                   + KL           D3(g-1) -> KL against the base posteriors -> per-pair accumulator -> R
 //   warpgroup 3     issuer         one elected lane of warp 12 issues every tcgen05.mma and tcgen05.commit and does
@@ -19,13 +21,13 @@
 //                                  MMA2 holds the warp for about as long as MMA2 runs), so an issuer that shares its
 //                                  warp with other work serialises that work with the MMAs
 //
-//   tensor pipe:  MMA2(g+1) K-steps 0-5 | K-steps 6-12 | MMA3(g) | MMA2(g+2) ...
+//   tensor pipe:  MMA2(g+1) K-steps 0-6 | K-steps 7-12 | MMA3(g) | MMA2(g+2) ...
 //
 // Both layers take their A operand from tensor memory.  (A first version kept the layer-3 operand in shared memory as
 // the lock-step kernel does: MMA3 then ran at ~70 cycles per instruction instead of 16 -- the tensor core fetches
 // shared-memory operands at ~64 B/cycle and an M = 128 A tile is 4 KB per K-step -- and took as long as MMA2.)
 // TMEM (512 columns): A2 hi [0,104) lo [104,208), ONE buffer: the constructors of the first K-half refill it for sample
-// g+1 as soon as the first six K-steps of MMA2(g) have completed (tcgen05.commit between the halves), while the other
+// g+1 as soon as the first seven K-steps of MMA2(g) have completed (tcgen05.commit between the halves), while the other
 // half is still being read; X[b] = D2 accumulator / layer-3 operand hi [.., +64) and lo [+64, +120), two buffers at 208
 // and 328; D3 at 448 (64 columns: layer 3 issues a_hi * [b_hi; b_lo] as ONE N = 64 instruction and a_lo * b_hi as an
 // N = 32 one -- 14 instead of 21 instructions per sample, an M = 128 tf32 MMA costs ~40 cycles for any N <= 64 -- and the
@@ -33,7 +35,7 @@
 // MMA2(g+2), so epilogue 2 needs no "empty" handshake.
 //
 // g counts the samples of all tiles of this CTA (tile-major), so the pipeline does not drain at tile ends.  The
-// constructors keep h0 and w_u of their row in registers (96 / 104 per thread): setmaxnreg moves registers from
+// constructors keep h0 and w_u of their row in registers (112 / 88 per thread): setmaxnreg moves registers from
 // warpgroup 3 to warpgroups 0,1.  Each role prefetches its own per-sample inputs (v, t; base posteriors of the
 // with-target rows) with cp.async into a private ring: no cross-thread hand-over, no barrier.
 //
@@ -64,7 +66,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int COL_X = 2 * K2, X_COLS = N2 + K3;   // X[b] at COL_X + b * X_COLS: accumulator / hi [0,64), lo [64,120)
 constexpr int COL_D3 = COL_X + 2 * X_COLS;        // D3: [0,32) = hi*hi + lo*hi, [32,64) = hi*lo (one buffer)
 static_assert(COL_D3 + 2 * N3 == TMEM_COLS, "TMEM map");
-constexpr int KH0 = 48, KH1 = K2 - KH0;   // features of the two constructor warpgroups (K-steps 0-5 and 6-12)
+constexpr int KH0 = 56, KH1 = K2 - KH0;   // features of the two constructor warpgroups (K-steps 0-6 and 7-12)
 constexpr int VT_NB = 4, VT_AHEAD = 3;    // ring of (v, t) per constructor thread
 constexpr int BT_NB = 3, BT_AHEAD = 2;    // ring of base posteriors per with-target row
 constexpr int BPITCH = BASEW + 4;         // 44 floats: 16-byte reads of consecutive rows hit distinct bank groups
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(NT, 1) k_reward_main_ws(const RewardArgs a) {
 
     if (wg < 2) {
         // ------------------------------------------------------------------------------------------
-        // constructors: warpgroup 0 features [0, 48), warpgroup 1 features [48, 104) of this thread's row
+        // constructors: warpgroup 0 features [0, 56), warpgroup 1 features [56, 104) of this thread's row
         // ------------------------------------------------------------------------------------------
         regs_inc<REG_CON>();
         auto role = [&](auto k0c, auto knc) {
