@@ -47,7 +47,7 @@ KERNEL_DRAM_BYTES = {"k_enc_fwd_tc": 142.1e6, "k_dec_fwd_tc": 136.6e6, "k_dec_bw
 FLOP_REWARD_TRIPLE = 24_460       # Reg_VAE incremental form: 2 tail evaluations + amortised bases
 # dram bytes of the reward main kernel at cfg5 (100k rows x 100 candidates x 50 samples), profiles/r02_ncu_summary.md
 # (same reads in the lock-step and the warp-specialised kernel: imputations and base posteriors, once each)
-REWARD_DRAM_BYTES = 2.983e9       # read 2.935 GB (imputations 2.02 GB + per-(row, sample) base posteriors) + write 0.048 GB
+REWARD_DRAM_BYTES = 2.993e9       # read 2.945 GB (imputations 2.02 GB + per-(row, sample) base posteriors) + write 0.048 GB
 
 #: the workload both arms are run on (identical `config` in the two JSON lines)
 def config_dict(args):
