@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
         if (tid == 0) {
             const uint32_t xb = (uint32_t)(ROWS * D * 4), mb = (uint32_t)(ROWS * D);
             mbar_expect_tx(&in_bar, xb + mb);
-            bulk_g2s(xin, a.x + (long)ti * ROWS * D, xb, &in_bar);
+            bulk_g2s(xin, a.x + bi * a.x_bs + (long)ti * ROWS * D, xb, &in_bar);
             bulk_g2s(reinterpret_cast<float*>(const_cast<uint8_t*>(min_)),
                      reinterpret_cast<const float*>(static_cast<const uint8_t*>(bi ? a.mask[1] : a.mask[0]) + (long)ti * ROWS * D), mb, &in_bar);
         }
@@ -131,9 +131,12 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
         const bool ok = grow < a.B;
         if (has_next && (flat || bn == 0)) {   // pull the next tile of this CTA towards L2 while this one is processed
             const long r0 = (long)tn * ROWS, nrows = min((long)ROWS, (long)a.B - r0);
-            prefetch_l2(a.x + r0 * D, nrows * D * 4, tid);
+            if (a.x_bs == 0) prefetch_l2(a.x + r0 * D, nrows * D * 4, tid);
             for (int b = 0; b < a.nbr; ++b)
-                if (!flat || b == bn) prefetch_l2((const char*)(b ? a.mask[1] : a.mask[0]) + r0 * D * msz, nrows * D * msz, tid);
+                if (!flat || b == bn) {
+                    if (a.x_bs != 0) prefetch_l2(a.x + b * a.x_bs + r0 * D, nrows * D * 4, tid);
+                    prefetch_l2((const char*)(b ? a.mask[1] : a.mask[0]) + r0 * D * msz, nrows * D * msz, tid);
+                }
         }
         {
             const long vt = (long)br * ntiles + t;            // tile of the scratch: [vt][row / 32][feature][row % 32]
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                             xv[2] = x4.z * ((mw & 0xFF0000u) ? 1.f : 0.f); xv[3] = x4.w * ((mw & 0xFF000000u) ? 1.f : 0.f);
                         } else if (ok) {
                             const long gi = (long)grow * D + c;
-                            const float4 x4 = *reinterpret_cast<const float4*>(a.x + gi);
+                            const float4 x4 = *reinterpret_cast<const float4*>(a.x + br * a.x_bs + gi);
                             float m[4];
                             load_mask4<true>(br ? a.mask[1] : a.mask[0], gi, a.mask_kind, m);
                             xv[0] = x4.x * m[0]; xv[1] = x4.y * m[1]; xv[2] = x4.z * m[2]; xv[3] = x4.w * m[3];

@@ -1,0 +1,246 @@
+// PNP (EDDI) set encoder with its MLP tail on the tensor cores (Reg_EDDI / vanilla_EDDI.encoder and its backward,
+// src/models/VAE.py:719-741, 903-925; emb_dim a multiple of 4).
+//
+// The encoder is  agg = sum_d m_d * relu(x_d * A_d + C_d)  (collapsed per-feature embedding + masked sum-pool,
+// element-wise work with a ReLU inside the sum, CUDA cores)  followed by the MLP K -> 100 -> 50 -> 2L
+// (dense, tensor cores).  The FFMA kernels k_enc_fwd<PNP> / k_enc_bwd<PNP> do both on the CUDA cores in one launch each
+// (220 + 369 us at batch 65 536 x 2 branches, K = 20).  Here the two halves are separate launches:
+//
+//   forward    k_pnp_embed_fwd : agg[branch][row][K] (row-major) + a mask of ones          (pcvae_tile.cuh: pnp_embed)
+//              k_enc_fwd_tc    : the zero-impute MLP encoder kernel run with obs_dim = K, x = agg of the branch
+//                                (EncFwdArgs::x_bs), mask = ones; its scratch keeps agg | 1, h1, h2 for the backward
+//   backward   k_enc_bwd_tc + k_wgrad_tc : dpre3, dpre2, dpre1 and dW1..dW3, db1..db3 exactly as for the MLP family
+//              k_pnp_embed_bwd : d_agg = dpre1 * W1 (K x 100, FFMA), dA / dC accumulated per CTA (pnp_embed_bwd), then the
+//                                chain rule through the collapsed tables to type_pars1, type_bias1, pnp_encoder1
+//
+// Parameter offsets are those of the PNP layout, so every gradient lands where the FFMA path puts it.
+#include <cuda_pipeline.h>
+
+#include "pcvae_train.cuh"
+
+namespace pcvae {
+
+constexpr int TMP = 64;           // rows per tile of the two element-wise kernels
+constexpr int PP = TMP + 4;       // feature-major pitch in shared memory
+constexpr int EMB_SEG = 8;        // feature segments pnp_embed may split D into (partial sums in shared memory)
+
+struct PnpEmbArgs {
+    Layout L;
+    int B, nbr, mask_kind;
+    const float* theta;
+    const float* x;
+    const void* mask[2];
+    const float* ac;          // collapsed tables A | C
+    float* agg;               // [nbr][B][K]
+    unsigned char* ones;      // [B][K]
+    const float* dp1T;        // backward: [nvt][row / 32][ETW_H1][row % 32]
+    float* gp;                // backward: [grid][P]
+};
+
+__global__ void __launch_bounds__(NT, 1) k_pnp_embed_fwd(const PnpEmbArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int D = a.L.D, K = a.L.K, K4 = round4(K);
+    float* in_s = smem;                      // [D][PP]  x
+    float* ms_s = in_s + D * PP;             // [D][PP]  mask
+    float* A_s = ms_s + D * PP;              // [D][K4]
+    float* C_s = A_s + D * K4;               // [D][K4]
+    float* agg_s = C_s + D * K4;             // [K4][PP]
+    float* part_s = agg_s + K4 * PP;         // [EMB_SEG][K4][PP]
+    for (int i = tid; i < 2 * D * K4; i += NT) A_s[i] = a.ac[i];
+    // the mask of ones the tensor-core kernel multiplies the pooled embedding with (it is the MLP family's kernel)
+    for (long i = (long)blockIdx.x * NT + tid; i < ((long)a.B * K + 3) / 4; i += (long)gridDim.x * NT)
+        reinterpret_cast<unsigned*>(a.ones)[i] = 0x01010101u;
+    __syncthreads();
+    const int ntiles = (a.B + TMP - 1) / TMP;
+    for (int vt = blockIdx.x; vt < ntiles * a.nbr; vt += gridDim.x) {
+        const int br = vt / ntiles, row0 = (vt - br * ntiles) * TMP;
+        const float* __restrict__ x = a.x;
+        const void* __restrict__ mk = a.mask[br];
+        {   // L2 prefetch of this CTA's next tile while the current one is being processed
+            const int nvt = vt + gridDim.x;
+            if (nvt < ntiles * a.nbr) {
+                const int nbr_ = nvt / ntiles, nrow0 = (nvt - nbr_ * ntiles) * TMP;
+                const long nrows = min(TMP, a.B - nrow0);
+                prefetch_l2(x + (long)nrow0 * D, nrows * D * 4, tid);
+                const int msz = a.mask_kind == PCVAE_MASK_U8 ? 1 : 4;
+                prefetch_l2((const char*)a.mask[nbr_] + (long)nrow0 * D * msz, nrows * D * msz, tid);
+            }
+        }
+        tile_elems<TMP, 16, XM>(D, row0, a.B, tid,
+            [&](int d, int r, bool ok) {
+                XM v{0.f, 0.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * D + d;
+                    v.x = x[gi];
+                    v.m = load_mask(mk, gi, a.mask_kind);
+                }
+                return v;
+            },
+            [&](int d, int r, bool, XM v) { in_s[d * PP + r] = v.x; ms_s[d * PP + r] = v.m; });
+        __syncthreads();
+        pnp_embed<TMP>(in_s, ms_s, A_s, C_s, agg_s, part_s, EMB_SEG * K4 * PP, D, K4, tid);
+        __syncthreads();
+        float* out = a.agg + ((long)br * a.B + row0) * K;
+        for (int i = tid; i < TMP * K; i += NT) {
+            const int r = i / K, k = i - r * K;
+            if (row0 + r < a.B) out[i] = agg_s[k * PP + r];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) k_pnp_embed_bwd(const PnpEmbArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int RB = 1;
+    const int tid = threadIdx.x;
+    const int D = a.L.D, K = a.L.K, K4 = round4(K);
+    float* in_s = smem;                      // [D][PP]  x
+    float* ms_s = in_s + D * PP;             // [D][PP]  mask
+    float* dp1_s = ms_s + D * PP;            // [100][PP]  dL/d(pre1)
+    float* agg_s = dp1_s + H1 * PP;          // [K4][PP]   dL/d(agg)
+    float* W1_s = agg_s + K4 * PP;           // [K][100]
+    float* A_s = W1_s + K * H1;              // [D][K4] (A then C)
+    float* C_s = A_s + D * K4;
+    float* dA_s = C_s + D * K4;              // [D][K4] (dA then dC)
+    float* dC_s = dA_s + D * K4;
+    stage_linear(W1_s, nullptr, a.theta + a.L.W1, nullptr, K, H1, H1, tid);
+    for (int i = tid; i < 2 * D * K4; i += NT) { A_s[i] = a.ac[i]; dA_s[i] = 0.f; }
+    zero_floats(agg_s, K4 * PP, tid);
+    __syncthreads();
+    const int ntiles = (a.B + TMP - 1) / TMP, nt128 = (a.B + 127) / 128;
+    for (int vt = blockIdx.x; vt < ntiles * a.nbr; vt += gridDim.x) {
+        const int br = vt / ntiles, t64 = vt - br * ntiles, row0 = t64 * TMP;
+        const float* __restrict__ x = a.x;
+        const void* __restrict__ mk = a.mask[br];
+        {   // the dpre1 rows of this tile: half of a 128-row tile of the tensor-core scratch, 32-row slabs feature-major
+            const float* src = a.dp1T + ((long)br * nt128 + (t64 >> 1)) * (ETW_H1 * 128) + (long)((t64 & 1) * 2) * (32 * ETW_H1);
+            for (int i = tid; i < H1 * (TMP / 4); i += NT) {
+                const int f = i / (TMP / 4), c = i - f * (TMP / 4), r = 4 * c;
+                __pipeline_memcpy_async(dp1_s + f * PP + r, src + (long)(r >> 5) * (32 * ETW_H1) + f * 32 + (r & 31), 16);
+            }
+            __pipeline_commit();
+        }
+        tile_elems<TMP, 16, XM>(D, row0, a.B, tid,
+            [&](int d, int r, bool ok) {
+                XM v{0.f, 0.f};
+                if (ok) {
+                    const long gi = (long)(row0 + r) * D + d;
+                    v.x = x[gi];
+                    v.m = load_mask(mk, gi, a.mask_kind);
+                }
+                return v;
+            },
+            [&](int d, int r, bool, XM v) { in_s[d * PP + r] = v.x; ms_s[d * PP + r] = v.m; });
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        gemm_dx<TMP, RB, false, 2>(dp1_s, W1_s, agg_s, K, H1, tid);      // agg_s <- dL/d(agg)
+        __syncthreads();
+        pnp_embed_bwd<TMP>(in_s, ms_s, agg_s, A_s, C_s, dA_s, dC_s, D, K, K4, tid);
+        __syncthreads();
+    }
+    // chain rule through the collapsed tables back to type_pars1, type_bias1, pnp_encoder1 (as k_enc_bwd<PNP>)
+    float* gp = a.gp + (long)blockIdx.x * a.L.total;
+    const float* th = a.theta;
+    for (int i = tid; i < D * K; i += NT) {           // dE[d][q] = sum_j dA[d][j] We[j][1+q]
+        const int d = i / K, q = i - d * K;
+        float s = 0.f;
+        for (int j = 0; j < K; ++j) s = fmaf(dA_s[d * K4 + j], th[a.L.We + j * (K + 2) + 1 + q], s);
+        gp[a.L.E + i] = s;
+    }
+    for (int d = tid; d < D; d += NT) {               // dbE[d] = sum_j dC[d][j] We[j][K+1]
+        float s = 0.f;
+        for (int j = 0; j < K; ++j) s = fmaf(dC_s[d * K4 + j], th[a.L.We + j * (K + 2) + K + 1], s);
+        gp[a.L.bE + d] = s;
+    }
+    for (int i = tid; i < K * (K + 2); i += NT) {     // dWe[j][c]
+        const int j = i / (K + 2), c = i - j * (K + 2);
+        float s = 0.f;
+        if (c == 0) for (int d = 0; d < D; ++d) s += dA_s[d * K4 + j];
+        else if (c <= K) for (int d = 0; d < D; ++d) s = fmaf(dA_s[d * K4 + j], th[a.L.E + d * K + (c - 1)], s);
+        else for (int d = 0; d < D; ++d) s = fmaf(dC_s[d * K4 + j], th[a.L.bE + d], s);
+        gp[a.L.We + i] = s;
+    }
+    for (int j = tid; j < K; j += NT) {               // dbe[j] = sum_d dC[d][j]
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s += dC_s[d * K4 + j];
+        gp[a.L.be + j] = s;
+    }
+}
+
+static size_t emb_fwd_smem(const Layout& L) {
+    const int K4 = round4(L.K);
+    return ((size_t)2 * L.D * PP + 2 * L.D * K4 + (size_t)(1 + EMB_SEG) * K4 * PP) * sizeof(float);
+}
+static size_t emb_bwd_smem(const Layout& L) {
+    const int K4 = round4(L.K);
+    return ((size_t)2 * L.D * PP + (size_t)H1 * PP + K4 * PP + (size_t)L.K * H1 + 4 * L.D * K4) * sizeof(float);
+}
+
+// the MLP tail as the tensor-core kernels see it: obs_dim = emb_dim, weights where the PNP layout keeps them
+static Layout tail_layout(const Layout& L) {
+    Layout T = L;
+    T.fam = PCVAE_FAMILY_MLP;
+    T.D = L.K;
+    T.K = 0;
+    T.aug = 0;
+    return T;
+}
+
+bool pnp_tc_supported(const Layout& L) {
+    return L.fam == PCVAE_FAMILY_PNP && L.K % 4 == 0 && L.K >= 4 && L.K <= MAX_K && enc_tc_supported(tail_layout(L)) &&
+           emb_fwd_smem(L) <= (size_t)MAX_SMEM && emb_bwd_smem(L) <= (size_t)MAX_SMEM;
+}
+
+// agg [nbr][rows][K] floats, then the ones mask [rows][K] bytes (both rounded up to 16 bytes)
+long pnp_tc_extra_floats(const Layout& L, long rows, int nbr) {
+    return ((long)nbr * rows * L.K + 3) / 4 * 4 + ((long)rows * L.K + 15) / 16 * 4;
+}
+
+template <typename Kern>
+static int emb_go(Kern kern, const PnpEmbArgs& args, size_t sm, int grid, cudaStream_t st, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    kern<<<grid, NT, sm, st>>>(args);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: launch: %s", name, cudaGetErrorString(e));
+    return PCVAE_OK;
+}
+
+static void emb_args(PnpEmbArgs* e, const Layout& L, int B, int nbr, int mask_kind, const float* theta, const float* x,
+                     const void* const* mask, const float* ac, float* extra) {
+    e->L = L; e->B = B; e->nbr = nbr; e->mask_kind = mask_kind; e->theta = theta; e->x = x;
+    e->mask[0] = mask[0]; e->mask[1] = mask[1]; e->ac = ac;
+    e->agg = extra;
+    e->ones = reinterpret_cast<unsigned char*>(extra + ((long)nbr * B * L.K + 3) / 4 * 4);
+}
+
+int pnp_enc_fwd_tc_launch(const EncFwdArgs& a, float* extra, int grid, cudaStream_t st) {
+    PnpEmbArgs e{};
+    emb_args(&e, a.L, a.B, a.nbr, a.mask_kind, a.theta, a.x, a.mask, a.ac, extra);
+    prof_mark(st);
+    if (int rc = emb_go(k_pnp_embed_fwd, e, emb_fwd_smem(a.L), grid, st, "pnp_embed_fwd")) return rc;
+    EncFwdArgs t = a;
+    t.L = tail_layout(a.L);
+    t.x = e.agg;
+    t.x_bs = (long)a.B * a.L.K;
+    t.mask[0] = t.mask[1] = e.ones;
+    t.mask_kind = PCVAE_MASK_U8;
+    t.act_ws = nullptr;
+    return enc_fwd_tc_launch(t, grid, st);
+}
+
+int pnp_enc_bwd_tc_launch(const EncBwdArgs& a, float* extra, int grid, cudaStream_t st) {
+    EncBwdArgs t = a;
+    t.L = tail_layout(a.L);
+    if (int rc = enc_bwd_tc_launch(t, grid, st)) return rc;
+    PnpEmbArgs e{};
+    emb_args(&e, a.L, a.B, a.nbr, a.mask_kind, a.theta, a.x, a.mask, a.ac, extra);
+    e.dp1T = a.tw.dp1T;
+    e.gp = a.gp;
+    const int rc = emb_go(k_pnp_embed_bwd, e, emb_bwd_smem(a.L), grid, st, "pnp_embed_bwd");
+    prof_mark(st);
+    return rc;
+}
+
+}  // namespace pcvae

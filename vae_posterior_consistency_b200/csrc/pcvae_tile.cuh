@@ -385,6 +385,44 @@ __device__ __forceinline__ void pnp_embed(const float* __restrict__ xs, const fl
     }
 }
 
+// dC[d][j] += sum_r t,  dA[d][j] += sum_r t * x   with  t = m * [x A + C > 0] * dagg[j][r].
+// One thread per (feature d, group of 4 embedding columns): consecutive lanes take consecutive
+// features (conflict-free with the +4 pitch), the dagg loads are warp broadcasts; each (d,j) has
+// exactly one owner, so the shared-memory accumulate is race-free and deterministic.
+template <int TM>
+__device__ __forceinline__ void pnp_embed_bwd(const float* __restrict__ xs, const float* __restrict__ ms,
+                                              const float* __restrict__ dagg_s, const float* __restrict__ A_s,
+                                              const float* __restrict__ C_s, float* __restrict__ dA_s,
+                                              float* __restrict__ dC_s, int D, int K, int K4, int tid) {
+    constexpr int P = TM + 4;
+    const int ngs = K4 / 4;
+    for (int item = tid; item < D * ngs; item += NT) {
+        const int jg = item / D, d = item - jg * D, j0 = 4 * jg;
+        const float4 a4 = lds4(A_s + d * K4 + j0), c4 = lds4(C_s + d * K4 + j0);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+        float accA[4] = {0.f, 0.f, 0.f, 0.f}, accC[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int r = 0; r < TM; r += 4) {
+            const float4 x4 = lds4(xs + d * P + r), m4 = lds4(ms + d * P + r);
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 g4 = lds4(dagg_s + (j0 + jj) * P + r);
+                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float tval = (fmaf(xv[i], av[jj], cv[jj]) > 0.f) ? mv[i] * gv[i] : 0.f;
+                    accC[jj] += tval;
+                    accA[jj] = fmaf(tval, xv[i], accA[jj]);
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+            if (j0 + jj < K) { dA_s[d * K4 + j0 + jj] += accA[jj]; dC_s[d * K4 + j0 + jj] += accC[jj]; }
+    }
+}
+
 __device__ __forceinline__ float load_mask(const void* __restrict__ m, long idx, int kind) {
     if (kind == 0) return reinterpret_cast<const uint8_t*>(m)[idx] ? 1.0f : 0.0f;
     return reinterpret_cast<const float*>(m)[idx];

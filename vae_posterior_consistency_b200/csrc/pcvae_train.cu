@@ -29,44 +29,6 @@ __global__ void k_pnp_tables(Layout L, const float* __restrict__ theta, float* _
     }
 }
 
-// dC[d][j] += sum_r t,  dA[d][j] += sum_r t * x   with  t = m * [x A + C > 0] * dagg[j][r].
-// One thread per (feature d, group of 4 embedding columns): consecutive lanes take consecutive
-// features (conflict-free with the +4 pitch), the dagg loads are warp broadcasts; each (d,j) has
-// exactly one owner, so the shared-memory accumulate is race-free and deterministic.
-template <int TM>
-__device__ __forceinline__ void pnp_embed_bwd(const float* __restrict__ xs, const float* __restrict__ ms,
-                                              const float* __restrict__ dagg_s, const float* __restrict__ A_s,
-                                              const float* __restrict__ C_s, float* __restrict__ dA_s,
-                                              float* __restrict__ dC_s, int D, int K, int K4, int tid) {
-    constexpr int P = TM + 4;
-    const int ngs = K4 / 4;
-    for (int item = tid; item < D * ngs; item += NT) {
-        const int jg = item / D, d = item - jg * D, j0 = 4 * jg;
-        const float4 a4 = lds4(A_s + d * K4 + j0), c4 = lds4(C_s + d * K4 + j0);
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
-        float accA[4] = {0.f, 0.f, 0.f, 0.f}, accC[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-        for (int r = 0; r < TM; r += 4) {
-            const float4 x4 = lds4(xs + d * P + r), m4 = lds4(ms + d * P + r);
-            const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const float4 g4 = lds4(dagg_s + (j0 + jj) * P + r);
-                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float tval = (fmaf(xv[i], av[jj], cv[jj]) > 0.f) ? mv[i] * gv[i] : 0.f;
-                    accC[jj] += tval;
-                    accA[jj] = fmaf(tval, xv[i], accA[jj]);
-                }
-            }
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-            if (j0 + jj < K) { dA_s[d * K4 + j0 + jj] += accA[jj]; dC_s[d * K4 + j0 + jj] += accC[jj]; }
-    }
-}
-
 void pnp_tables_launch(const Layout& L, const float* theta, float* ac, cudaStream_t st) {
     k_pnp_tables<<<8, 256, 0, st>>>(L, theta, ac);
 }
@@ -861,6 +823,16 @@ int pcvae_enc_fwd(const pcvae_enc_fwd_params* p, void* stream) {
     a.L = L; a.B = p->rows; a.nbr = p->n_branch; a.mask_kind = p->mask_kind; a.theta = p->theta; a.x = p->x;
     for (int b = 0; b < 2; ++b) { a.mask[b] = p->mask[b]; a.eps[b] = p->eps[b]; a.mean[b] = p->mean[b]; a.logvar[b] = p->logvar[b]; a.z[b] = p->z[b]; }
     a.act_ws = p->act_ws; a.ac = p->pnp_ac;
+    if (g_train_tc && p->tc_workspace && pnp_tc_supported(L)) {
+        // pooled embedding on the CUDA cores, MLP tail on the tensor cores (pcvae_pnp_tc.cu)
+        const long base = etw_floats(p->rows, p->n_branch), need = base + pnp_tc_extra_floats(L, p->rows, p->n_branch);
+        if (p->tc_workspace_floats < need)
+            return fail(PCVAE_EINVAL, "enc_fwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
+        if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_fwd: PNP family needs pnp_ac workspace");
+        enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        pnp_tables_launch(L, p->theta, p->pnp_ac, st);
+        return pnp_enc_fwd_tc_launch(a, p->tc_workspace + base, grid, st);
+    }
     if (g_train_tc && p->tc_workspace && enc_tc_supported(L)) {
         const long need = etw_floats(p->rows, p->n_branch);
         if (p->tc_workspace_floats < need)
@@ -884,7 +856,8 @@ int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
     if (int rc = device_ok(&grid)) return rc;
     if (p->rows < 0 || p->n_branch < 1 || p->n_branch > 2) return fail(PCVAE_EINVAL, "enc_bwd: bad rows/n_branch");
     if (!p->theta || !p->grad_partials) return fail(PCVAE_EINVAL, "enc_bwd: null theta/grad_partials");
-    const bool use_tc = g_train_tc && p->tc_workspace && p->rows > 0 && enc_tc_supported(L);
+    const bool use_pnp_tc = g_train_tc && p->tc_workspace && p->rows > 0 && pnp_tc_supported(L);
+    const bool use_tc = use_pnp_tc || (g_train_tc && p->tc_workspace && p->rows > 0 && enc_tc_supported(L));
     if (p->rows > 0 && (!p->x || (!p->act_ws && !use_tc))) return fail(PCVAE_EINVAL, "enc_bwd: null x/act_ws");
     for (int b = 0; b < p->n_branch && p->rows > 0; ++b)
         if (!p->mask[b] || !p->d_mean[b] || !p->d_logvar[b]) return fail(PCVAE_EINVAL, "enc_bwd: null mask/d_mean/d_logvar for branch %d", b);
@@ -897,6 +870,14 @@ int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
         if (p->d_z[b] && p->eps[b] && !p->logvar[b]) return fail(PCVAE_EINVAL, "enc_bwd: d_z and eps given without logvar for branch %d", b);
     }
     a.act_ws = p->act_ws; a.ac = p->pnp_ac; a.gp = p->grad_partials;
+    if (use_pnp_tc) {
+        const long base = etw_floats(p->rows, p->n_branch), need = base + pnp_tc_extra_floats(L, p->rows, p->n_branch);
+        if (p->tc_workspace_floats < need)
+            return fail(PCVAE_EINVAL, "enc_bwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
+        if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_bwd: PNP family needs pnp_ac tables");
+        enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        return pnp_enc_bwd_tc_launch(a, p->tc_workspace + base, grid, st);
+    }
     if (use_tc) {
         const long need = etw_floats(p->rows, p->n_branch);
         if (p->tc_workspace_floats < need)
@@ -968,7 +949,9 @@ long pcvae_dec_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch)
 
 long pcvae_enc_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch) {
     Layout L;
-    if (!g_train_tc || !m || !make_layout(m, &L) || !enc_tc_supported(L) || rows < 1 || n_branch < 1) return 0;
+    if (!g_train_tc || !m || !make_layout(m, &L) || rows < 1 || n_branch < 1) return 0;
+    if (pnp_tc_supported(L)) return etw_floats(rows, n_branch) + pnp_tc_extra_floats(L, rows, n_branch);
+    if (!enc_tc_supported(L)) return 0;
     return etw_floats(rows, n_branch);
 }
 

@@ -62,6 +62,8 @@ struct EncFwdArgs {
     float* act_ws;
     const float* ac;
     EncTcWs tw;       // tensor-core path only
+    long x_bs;        // tensor-core path only: floats between the x of branch 0 and of branch 1 (0: both branches read
+                      // the same x; PNP family: the pooled embeddings differ per branch, pcvae_pnp_tc.cu)
 };
 
 struct EncBwdArgs {
@@ -97,6 +99,13 @@ bool enc_tc_supported(const Layout& L);
 void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw);
 int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st);
 int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st);
+
+// pcvae_pnp_tc.cu: PNP (EDDI) set encoder = masked pooled embedding on the CUDA cores + the MLP tail on the tensor-core
+// encoder kernels (the tail sees obs_dim = emb_dim, x = pooled embedding per branch, mask = ones)
+bool pnp_tc_supported(const Layout& L);
+long pnp_tc_extra_floats(const Layout& L, long rows, int nbr);       // workspace floats beyond etw_floats()
+int pnp_enc_fwd_tc_launch(const EncFwdArgs& a, float* extra, int grid, cudaStream_t st);
+int pnp_enc_bwd_tc_launch(const EncBwdArgs& a, float* extra, int grid, cudaStream_t st);
 
 // pcvae_wgrad_tc.cu: dWaug[m][n] = sum_rows AT[m][row] * BT[n][row] for up to three layers in one launch
 struct WgradJob {
