@@ -148,7 +148,7 @@ def rand_case(family, B, D, K, seed, mask_float=False):
 SHAPES = [("mlp", 1, 4, 0), ("mlp", 129, 8, 0), ("mlp", 300, 100, 0), ("mlp", 257, 104, 0), ("pnp", 131, 12, 10),
           ("mlp", 1, 2, 0), ("mlp", 63, 13, 0), ("mlp", 65, 50, 0), ("mlp", 200, 100, 0), ("mlp", 130, 101, 0),
           ("mlp", 70, 128, 0), ("pnp", 1, 2, 10), ("pnp", 65, 13, 20), ("pnp", 200, 100, 20), ("pnp", 97, 50, 7),
-          ("pnp", 64, 128, 20), ("pnp", 300, 40, 4), ("pnp", 129, 100, 32), ("pnp", 1000, 100, 8),
+          ("pnp", 64, 128, 20), ("pnp", 300, 40, 4), ("pnp", 129, 60, 32), ("pnp", 1000, 100, 8),
           ("mlp_mask", 1, 2, 0), ("mlp_mask", 65, 13, 0), ("mlp_mask", 130, 50, 0), ("mlp_mask", 200, 100, 0),
           ("mlp_mask", 97, 21, 0)]
 

@@ -14,15 +14,19 @@
 //                                chain rule through the collapsed tables to type_pars1, type_bias1, pnp_encoder1
 //
 // Parameter offsets are those of the PNP layout, so every gradient lands where the FFMA path puts it.
+#include <cooperative_groups.h>
 #include <cuda_pipeline.h>
 
 #include "pcvae_train.cuh"
 
 namespace pcvae {
 
-constexpr int TMP = 64;           // rows per tile of the two element-wise kernels
+// The two element-wise kernels are latency-bound (a tile is load -> barrier -> compute -> barrier -> combine): 32-row
+// tiles keep their shared memory under 100 KB so that two CTAs share an SM and one's barriers hide under the other's math.
+constexpr int TMP = 32;           // rows per tile of the two element-wise kernels
 constexpr int PP = TMP + 4;       // feature-major pitch in shared memory
-constexpr int EMB_SEG = 8;        // feature segments pnp_embed may split D into (partial sums in shared memory)
+constexpr int EMB_SEG = 12;       // feature segments pnp_embed may split D into (partial sums in shared memory)
+constexpr int EMB_CTAS = 2;       // CTAs per SM
 
 struct PnpEmbArgs {
     Layout L;
@@ -37,7 +41,7 @@ struct PnpEmbArgs {
     float* gp;                // backward: [grid][P]
 };
 
-__global__ void __launch_bounds__(NT, 1) k_pnp_embed_fwd(const PnpEmbArgs a) {
+__global__ void __launch_bounds__(NT, EMB_CTAS) k_pnp_embed_fwd(const PnpEmbArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(NT, 1) k_pnp_embed_fwd(const PnpEmbArgs a) {
                 prefetch_l2((const char*)a.mask[nbr_] + (long)nrow0 * D * msz, nrows * D * msz, tid);
             }
         }
-        tile_elems<TMP, 16, XM>(D, row0, a.B, tid,
+        tile_elems<TMP, 8, XM>(D, row0, a.B, tid,
             [&](int d, int r, bool ok) {
                 XM v{0.f, 0.f};
                 if (ok) {
@@ -90,7 +94,10 @@ __global__ void __launch_bounds__(NT, 1) k_pnp_embed_fwd(const PnpEmbArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(NT, 1) k_pnp_embed_bwd(const PnpEmbArgs a) {
+// Launched as clusters of EMB_CTAS CTAs: the gradient partials are [grid][P] with grid = one row per SM-sized slot
+// (pcvae_grid_ctas), so the CTAs of a cluster add their dA / dC tables into rank 0's shared memory (distributed shared
+// memory, fixed order) and rank 0 writes the cluster's row.
+__global__ void __cluster_dims__(EMB_CTAS, 1, 1) __launch_bounds__(NT, EMB_CTAS) k_pnp_embed_bwd(const PnpEmbArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int RB = 1;
     const int tid = threadIdx.x;
@@ -113,15 +120,16 @@ __global__ void __launch_bounds__(NT, 1) k_pnp_embed_bwd(const PnpEmbArgs a) {
         const int br = vt / ntiles, t64 = vt - br * ntiles, row0 = t64 * TMP;
         const float* __restrict__ x = a.x;
         const void* __restrict__ mk = a.mask[br];
-        {   // the dpre1 rows of this tile: half of a 128-row tile of the tensor-core scratch, 32-row slabs feature-major
-            const float* src = a.dp1T + ((long)br * nt128 + (t64 >> 1)) * (ETW_H1 * 128) + (long)((t64 & 1) * 2) * (32 * ETW_H1);
+        {   // the dpre1 rows of this tile: one 32-row slab [feature][32] of a 128-row tile of the tensor-core scratch
+            static_assert(TMP == 32, "one slab per tile");
+            const float* src = a.dp1T + ((long)br * nt128 + (t64 >> 2)) * (ETW_H1 * 128) + (long)(t64 & 3) * (32 * ETW_H1);
             for (int i = tid; i < H1 * (TMP / 4); i += NT) {
-                const int f = i / (TMP / 4), c = i - f * (TMP / 4), r = 4 * c;
-                __pipeline_memcpy_async(dp1_s + f * PP + r, src + (long)(r >> 5) * (32 * ETW_H1) + f * 32 + (r & 31), 16);
+                const int f = i / (TMP / 4), c = i - f * (TMP / 4);
+                __pipeline_memcpy_async(dp1_s + f * PP + 4 * c, src + f * 32 + 4 * c, 16);
             }
             __pipeline_commit();
         }
-        tile_elems<TMP, 16, XM>(D, row0, a.B, tid,
+        tile_elems<TMP, 8, XM>(D, row0, a.B, tid,
             [&](int d, int r, bool ok) {
                 XM v{0.f, 0.f};
                 if (ok) {
@@ -139,8 +147,21 @@ __global__ void __launch_bounds__(NT, 1) k_pnp_embed_bwd(const PnpEmbArgs a) {
         pnp_embed_bwd<TMP>(in_s, ms_s, agg_s, A_s, C_s, dA_s, dC_s, D, K, K4, tid);
         __syncthreads();
     }
+    {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();                                         // every CTA of the cluster has finished its tiles
+        for (unsigned rk = 1; rk < cl.num_blocks(); ++rk) {
+            if (cl.block_rank() == rk) {
+                float* dst = cl.map_shared_rank(dA_s, 0);
+                for (int i = tid; i < 2 * D * K4; i += NT) dst[i] += dA_s[i];
+            }
+            cl.sync();
+        }
+        if (cl.block_rank() != 0) return;
+    }
     // chain rule through the collapsed tables back to type_pars1, type_bias1, pnp_encoder1 (as k_enc_bwd<PNP>)
-    float* gp = a.gp + (long)blockIdx.x * a.L.total;
+    float* gp = a.gp + (long)(blockIdx.x / EMB_CTAS) * a.L.total;
     const float* th = a.theta;
     for (int i = tid; i < D * K; i += NT) {           // dE[d][q] = sum_j dA[d][j] We[j][1+q]
         const int d = i / K, q = i - d * K;
@@ -201,7 +222,7 @@ template <typename Kern>
 static int emb_go(Kern kern, const PnpEmbArgs& args, size_t sm, int grid, cudaStream_t st, const char* name) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
-    kern<<<grid, NT, sm, st>>>(args);
+    kern<<<EMB_CTAS * grid, NT, sm, st>>>(args);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: launch: %s", name, cudaGetErrorString(e));
     return PCVAE_OK;
