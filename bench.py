@@ -419,7 +419,7 @@ def gpu_mnar(args, dev, ffma_tflops, with_cpu):
     # the same step replayed from a CUDA graph (train.py does this under PCVAE_MODE=throughput): batch assembly,
     # sub-mask and noise draws stay outside the graph, forward + loss + backward + Adam are one graph launch
     from vae_posterior_consistency_b200.graphed import GraphedTrainer
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)      # as train() builds it for the graph
     gt = GraphedTrainer(model, lambda: fwd_loss, opt, VAE.fill_normal_)
     for _ in range(warm):
         gt.step(*batch())

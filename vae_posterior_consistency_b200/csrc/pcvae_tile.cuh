@@ -14,6 +14,7 @@
 // thread keeps an 8x4 (rows x outputs) block and per reduction step issues 3 LDS.128
 // for 32 FFMA (RB=2) or a 4x4 block with 2 LDS.128 per 16 FFMA (RB=1, twice the warps).
 #pragma once
+#include <cstdint>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,9 +49,43 @@ __device__ __forceinline__ void stage_linear(float* W_s, float* b_s, const float
             int k = i / (NP - N), n = N + i % (NP - N);
             W_s[k * NP + n] = 0.0f;
         }
-    for (int i = tid; i < N * K; i += NT) {
-        int n = i / K, k = i - n * K;
-        W_s[k * NP + n] = __ldg(W + i);
+    // Lanes run along n: the shared-memory stores of a warp are 32 consecutive floats (a scatter with lanes along k puts
+    // the whole warp into one bank when NP % 32 == 0 -- 8 us per launch for the 128 x 128 layers of the MNAR networks).
+    // Each thread reads four consecutive k of its row (one 16-byte load when aligned); the loads of four items are in
+    // flight before the first store.
+    const int lane = tid & 31, warp = tid >> 5;
+    const int kq = (K + 3) >> 2, ng = (N + 31) >> 5, items = kq * ng;
+    const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    for (int base = warp; base < items; base += 4 * NWARP) {
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = base + u * NWARP;
+            const int q = it / ng, n = (it - q * ng) * 32 + lane, k0 = 4 * q;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[u][j] = 0.f;
+            if (it < items && n < N) {
+                const float* w = W + (long)n * K + k0;
+                if (vec) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(w));
+                    v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (k0 + j < K) v[u][j] = __ldg(w + j);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = base + u * NWARP;
+            const int q = it / ng, n = (it - q * ng) * 32 + lane, k0 = 4 * q;
+            if (it < items && n < N) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k0 + j < K) W_s[(k0 + j) * NP + n] = v[u][j];
+            }
+        }
     }
     if (b_s)
         for (int n = tid; n < NP; n += NT) b_s[n] = (n < N) ? __ldg(b + n) : 0.0f;
@@ -279,9 +314,25 @@ __device__ __forceinline__ void bias_dw(const float* __restrict__ dY_s, float* _
 // nn.Linear [N][K] layout (coalesced stores).
 __device__ __forceinline__ void flush_linear_grad(const float* dW_s, const float* db_s, float* __restrict__ gW,
                                                   float* __restrict__ gb, int K, int N, int NP, int tid) {
-    for (int i = tid; i < N * K; i += NT) {
-        int n = i / K, k = i - n * K;
-        gW[i] = dW_s[k * NP + n];
+    // lanes along n (conflict-free shared-memory reads, see stage_linear), four consecutive k per thread and store
+    const int lane = tid & 31, warp = tid >> 5;
+    const int kq = (K + 3) >> 2, ng = (N + 31) >> 5, items = kq * ng;
+    const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(gW) & 15) == 0);
+    for (int it = warp; it < items; it += NWARP) {
+        const int q = it / ng, n = (it - q * ng) * 32 + lane, k0 = 4 * q;
+        if (n < N) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (k0 + j < K) ? dW_s[(k0 + j) * NP + n] : 0.f;
+            float* g = gW + (long)n * K + k0;
+            if (vec) {
+                *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k0 + j < K) g[j] = v[j];
+            }
+        }
     }
     if (gb)
         for (int n = tid; n < N; n += NT) gb[n] = db_s[n];

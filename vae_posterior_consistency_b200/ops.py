@@ -333,18 +333,25 @@ def _mnar_setup(ctx, inputs, output):
     ctx.reg = inputs[2] is not None
     ctx.has_grads = inputs[15]
     ctx.save_for_backward(*output[3:])
+    # 12 of the 13 outputs never take part in a loss: without this autograd fills a zero tensor for each of them
+    # (among them four [B, S, D] ones) on every backward
+    ctx.set_materialize_grads(False)
 
 
 def _mnar_backward(ctx, d_loss, *unused):
     if not ctx.has_grads:
         raise RuntimeError("pcvae::mnar_loss was run with want_grads=False")
-    g = ctx.saved_tensors
-    sc = lambda t: t * d_loss
     out = [None] * 17
-    out[3], out[4], out[7], out[8] = sc(g[0]), sc(g[1]), sc(g[2]), sc(g[3])
+    if d_loss is None:
+        return tuple(out)
+    g = ctx.saved_tensors
+    n = 8 if ctx.reg else 4
+    live = list(g[:n]) + [g[8], g[9]]
+    scaled = torch._foreach_mul(live, d_loss)           # one multi-tensor launch instead of ten element-wise ones
+    out[3], out[4], out[7], out[8] = scaled[0], scaled[1], scaled[2], scaled[3]
     if ctx.reg:
-        out[5], out[6], out[9], out[10] = sc(g[4]), sc(g[5]), sc(g[6]), sc(g[7])
-    out[11], out[12] = sc(g[8]), sc(g[9])
+        out[5], out[6], out[9], out[10] = scaled[4], scaled[5], scaled[6], scaled[7]
+    out[11], out[12] = scaled[n], scaled[n + 1]
     return tuple(out)
 
 

@@ -202,7 +202,9 @@ def train(data_loader_train, missing_rate, obs_dim, hid_dim, K, M, latent_dim, d
     else:
         # throughput mode: the launch-bound MNAR step is replayed from a CUDA graph (graphed.py)
         graphed = throughput and 'notMIWAE' in vae_type and not beta_annealing
-        optimizer = optim.Adam(model.parameters(), lr=0.001, capturable=graphed)
+        # the graph replays ONE fused multi-tensor Adam launch instead of the ~14 of the for-each implementation
+        optimizer = (optim.Adam(model.parameters(), lr=0.001, capturable=True, fused=True) if graphed
+                     else optim.Adam(model.parameters(), lr=0.001))
         if graphed:
             def make_fn():
                 if regularised:
