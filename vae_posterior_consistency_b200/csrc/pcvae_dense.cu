@@ -4,6 +4,14 @@
 
 namespace pcvae {
 
+// Padded output count = pitch of the weight image W_s[K][NP].  A pitch that is a multiple of 32 floats puts W_s[k][n] for
+// consecutive k into one bank: gemm_dx / gemm_dw then serialise 32-way (128-wide layers: 40 us for ONE 64-row tile).
+// With pitch % 32 == 4 the eight 16-byte reads of a quarter-warp hit eight different bank groups (as 100 and 52 do).
+__host__ __device__ inline int dense_pitch(int N) {
+    const int np = round4(N);
+    return (np % 32 == 0) ? np + 4 : np;
+}
+
 struct DenseArgs {
     int R, K, N, act;
     const float* x;
@@ -18,11 +26,13 @@ struct DenseArgs {
     float* dbp;
 };
 
-template <int ACT>
+// TM rows per tile: 64, or 32 when the batch has so few rows that 64-row tiles would leave most SMs idle (a CTA's time is
+// rows x K x N on one SM: the 256-row encoder layers of the MNAR networks take half as long on twice as many SMs)
+template <int ACT, int TM>
 __global__ void __launch_bounds__(NT, 1) k_dense_fwd(const DenseArgs a) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int TM = TM_TRAIN, P = TM + 4, RB = 1;
-    const int tid = threadIdx.x, K = a.K, N = a.N, NP = round4(N);
+    constexpr int P = TM + 4, RB = 1;
+    const int tid = threadIdx.x, K = a.K, N = a.N, NP = dense_pitch(N);
     float* W_s = smem;                 // [K][NP]
     float* b_s = W_s + K * NP;         // [NP]
     float* in_s = b_s + NP;            // [K][P]
@@ -60,10 +70,11 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
     return 1.f;
 }
 
+template <int TM>
 __global__ void __launch_bounds__(NT, 1) k_dense_bwd(const DenseArgs a) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int TM = TM_TRAIN, P = TM + 4, RB = 1;
-    const int tid = threadIdx.x, K = a.K, N = a.N, NP = round4(N);
+    constexpr int P = TM + 4, RB = 1;
+    const int tid = threadIdx.x, K = a.K, N = a.N, NP = dense_pitch(N);
     float* W_s = smem;                 // [K][NP]
     float* dW_s = W_s + K * NP;        // [K][NP]
     float* db_s = dW_s + K * NP;       // [NP]
@@ -142,18 +153,20 @@ __global__ void k_dense_reduce(const float* __restrict__ dWp, const float* __res
 
 using namespace pcvae;
 
-static size_t dense_fwd_smem(int K, int N) {
-    const int NP = round4(N), P = TM_TRAIN + 4;
+static size_t dense_fwd_smem(int K, int N, int TM) {
+    const int NP = dense_pitch(N), P = TM + 4;
     return ((size_t)K * NP + NP + (size_t)K * P + (size_t)NP * P) * sizeof(float);
 }
-static size_t dense_bwd_smem(int K, int N) {
-    const int NP = round4(N), P = TM_TRAIN + 4;
+static size_t dense_bwd_smem(int K, int N, int TM) {
+    const int NP = dense_pitch(N), P = TM + 4;
     return (2 * (size_t)K * NP + NP + (size_t)K * P + (size_t)NP * P) * sizeof(float);
 }
 
-// CTAs that own at least one 64-row tile (one CTA still runs for rows == 0 so that the partials are zeroed)
+// rows per tile: 32 when 64-row tiles would occupy at most half of the SMs
+static int tile_rows(int grid, int rows) { return 2 * ((rows + TM_TRAIN - 1) / TM_TRAIN) <= grid ? 32 : TM_TRAIN; }
+// CTAs that own at least one tile (one CTA still runs for rows == 0 so that the partials are zeroed)
 static int live_ctas(int grid, int rows) {
-    const int ntiles = (rows + TM_TRAIN - 1) / TM_TRAIN;
+    const int tm = tile_rows(grid, rows), ntiles = (rows + tm - 1) / tm;
     return ntiles < 1 ? 1 : (ntiles < grid ? ntiles : grid);
 }
 
@@ -181,14 +194,18 @@ int pcvae_dense_fwd(const pcvae_dense_fwd_params* p, void* stream) {
     DenseArgs a{};
     a.R = p->rows; a.K = p->in_dim; a.N = p->out_dim; a.act = p->act; a.x = p->x; a.mask = p->mask; a.W = p->W; a.b = p->b; a.y = p->y;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t sm = dense_fwd_smem(a.K, a.N);
+    const int tm = tile_rows(grid, a.R), live = live_ctas(grid, a.R);
+    const size_t sm = dense_fwd_smem(a.K, a.N, tm);
+#define PCVAE_DENSE_FWD(ACT) (tm == 32 ? launch_dense(k_dense_fwd<ACT, 32>, sm, live, st, "dense_fwd", a) \
+                                       : launch_dense(k_dense_fwd<ACT, TM_TRAIN>, sm, live, st, "dense_fwd", a))
     switch (p->act) {
-        case PCVAE_ACT_NONE: return launch_dense(k_dense_fwd<ACT_NONE>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
-        case PCVAE_ACT_RELU: return launch_dense(k_dense_fwd<ACT_RELU>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
-        case PCVAE_ACT_SIGMOID: return launch_dense(k_dense_fwd<ACT_SIGMOID>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
-        case PCVAE_ACT_ELU: return launch_dense(k_dense_fwd<ACT_ELU>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
-        case PCVAE_ACT_HARDTANH_M10_0: return launch_dense(k_dense_fwd<ACT_HARDTANH>, sm, live_ctas(grid, a.R), st, "dense_fwd", a);
+        case PCVAE_ACT_NONE: return PCVAE_DENSE_FWD(ACT_NONE);
+        case PCVAE_ACT_RELU: return PCVAE_DENSE_FWD(ACT_RELU);
+        case PCVAE_ACT_SIGMOID: return PCVAE_DENSE_FWD(ACT_SIGMOID);
+        case PCVAE_ACT_ELU: return PCVAE_DENSE_FWD(ACT_ELU);
+        case PCVAE_ACT_HARDTANH_M10_0: return PCVAE_DENSE_FWD(ACT_HARDTANH);
     }
+#undef PCVAE_DENSE_FWD
     return fail(PCVAE_EINVAL, "dense_fwd: unknown activation %d", p->act);
 }
 
@@ -205,8 +222,10 @@ int pcvae_dense_bwd(const pcvae_dense_bwd_params* p, void* stream) {
     a.R = p->rows; a.K = p->in_dim; a.N = p->out_dim; a.act = p->act; a.x = p->x; a.mask = p->mask; a.W = p->W;
     a.yin = p->y; a.dy = p->dy; a.dx = p->dx; a.dWp = p->dW_partials; a.dbp = p->db_partials;
     if ((p->dW == nullptr) != (p->db == nullptr)) return fail(PCVAE_EINVAL, "dense_bwd: give both dW and db or neither");
-    const int live = live_ctas(grid, a.R);
-    if (int rc = launch_dense(k_dense_bwd, dense_bwd_smem(a.K, a.N), live, (cudaStream_t)stream, "dense_bwd", a)) return rc;
+    const int tm = tile_rows(grid, a.R), live = live_ctas(grid, a.R);
+    if (int rc = tm == 32 ? launch_dense(k_dense_bwd<32>, dense_bwd_smem(a.K, a.N, tm), live, (cudaStream_t)stream, "dense_bwd", a)
+                          : launch_dense(k_dense_bwd<TM_TRAIN>, dense_bwd_smem(a.K, a.N, tm), live, (cudaStream_t)stream, "dense_bwd", a))
+        return rc;
     if (p->dW) {
         const int nW = a.N * a.K, n = nW + a.N;
         k_dense_reduce<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.dWp, a.dbp, live, nW, a.N, p->dW, p->db);
