@@ -18,8 +18,12 @@
  *    failure on the calling thread is pcvae_last_error().  Never throws/exits.
  *  - there is NO CPU fallback and no multi-backend dispatch: a device that is not
  *    compute capability 10.x yields PCVAE_EDEVICE.
- *  - fp32 arithmetic throughout (no TF32/BF16); masks are 0/1 valued, either
- *    uint8 (torch.bool) or float32.
+ *  - fp32 storage, fp32 accumulation and fp32-ACCURATE products everywhere.  The tensor-core kernels (default for the
+ *    zero-impute MLP family, the MLP tail of the PNP family and the reward of the MLP family) issue every dense
+ *    product as three tcgen05.mma.kind::tf32 instructions on hi / lo operand splits (a*b ~= a_hi*b_hi + a_hi*b_lo +
+ *    a_lo*b_hi, ~2^-21 relative per product); the FFMA kernels (other shapes and families, and the cross-check of the
+ *    tensor-core ones: pcvae_set_train_tensor_cores / pcvae_set_reward_tensor_cores) use plain fp32 FMAs.  No result
+ *    is ever computed at TF32 / BF16 precision.  Masks are 0/1 valued, either uint8 (torch.bool) or float32.
  *
  * Flat parameter vector `theta` (and the gradient / Adam vectors of the same
  * layout): the reference's trainable parameters in state_dict order
