@@ -362,7 +362,7 @@ def test_prep_packed_equals_prep_batch_on_the_same_rows(B, D):
 
 
 @pytest.mark.parametrize("B,D,T", [(64, 20, 455), (4096, 100, 20000)])
-def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D, T):
+def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D, T, monkeypatch):
     """GraphedFusedTrainer: the whole step (prep_batch_dev + six kernels + reduce_adam_dev, per-step scalars from a device
     counter) replayed from a CUDA graph == the same launches issued eagerly, bit for bit; and == the host-counted
     sequence pcvae_prep_batch(offset = 8 step) -> FusedTrainer.step up to the rounding of Adam's bias correction."""
@@ -377,7 +377,9 @@ def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D,
     p = O.init_params("mlp", D, 0, seed=7)
     mk = lambda: KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, KR.flatten_params(p, L.FAMILY_MLP, dev), table, mtable, B, nb,
                                         keep=0.7, seed=99)
+    monkeypatch.setenv("PCVAE_PREP_AHEAD", "1")
     a, b = mk(), mk()
+    monkeypatch.delenv("PCVAE_PREP_AHEAD")
     a.set_batches(idx); b.set_batches(idx)
     a.capture()                                            # three eager warm-up steps, then the capture
     for _ in range(steps):
@@ -387,7 +389,22 @@ def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D,
     torch.cuda.synchronize()
     assert a.step_count == b.step_count == 3 + steps and int(a.state[0]) == int(b.state[0]) == 3 + steps
     assert torch.equal(a.theta, b.theta) and torch.equal(a.exp_avg_sq, b.exp_avg_sq) and torch.equal(a.total, b.total)
-    # host-counted reference sequence
+    # a and b prepare the batch of step n + 1 on a forked stream during step n (PCVAE_PREP_AHEAD=1); c runs the default
+    # prep -> step order; new index lists in the middle of the run
+    assert a.ahead == (D % 4 == 0 and D <= 100)
+    c = mk()
+    assert not c.ahead
+    c.set_batches(idx)
+    for _ in range(3 + steps):
+        c.step_eager_dev()
+    assert torch.equal(a.theta, c.theta) and torch.equal(a.total, c.total)
+    idx2 = torch.stack([torch.randperm(T, device=dev, generator=g)[:B] for _ in range(nb)])
+    a.set_batches(idx2); c.set_batches(idx2)
+    for _ in range(nb + 2):
+        a.step_graph(); c.step_eager_dev()
+    torch.cuda.synchronize()
+    assert torch.equal(a.theta, c.theta) and torch.equal(a.total, c.total)
+    # host-counted reference sequence (against b, which stopped after 3 + steps steps and equalled a there bit for bit)
     tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, KR.flatten_params(p, L.FAMILY_MLP, dev), regularised=True)
     x = torch.empty(B, D, device=dev); m = torch.empty(B, D, device=dev, dtype=torch.bool); mp = torch.empty_like(m)
     eps = torch.empty(2, B, 10, device=dev)
@@ -397,8 +414,8 @@ def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D,
                                      mp.data_ptr(), eps.data_ptr(), B, D, 2, 0.7, 99, 8 * s_,
                                      torch.cuda.current_stream().cuda_stream), "pcvae_prep_batch")
         total += float(tr.step(x, m, mp, eps[0], eps[1]))
-    torch.testing.assert_close(a.theta, tr.theta, rtol=0, atol=1e-6)
-    assert abs(float(a.total) - total) <= 1e-6 * abs(total)
+    torch.testing.assert_close(b.theta, tr.theta, rtol=0, atol=1e-6)
+    assert abs(float(b.total) - total) <= 1e-6 * abs(total)
 
 
 def test_empty_batch_is_a_no_op():

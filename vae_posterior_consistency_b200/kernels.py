@@ -658,7 +658,9 @@ class FusedTrainer:
             from .dist import PeerExchange
             self.xch = PeerExchange.create_or_none(self.eng.P, dist_group, theta.device)
 
-    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True):
+    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True, after_dec=None):
+        """`after_dec` (optional callable) runs between the decoder call and the encoder backward: the last point at
+        which x, the masks and the noise are read when the encoder runs on the tensor-core kernels."""
         e = self.eng
         B = x.shape[0]
         rows = B if global_rows is None else global_rows
@@ -668,6 +670,8 @@ class FusedTrainer:
         mean, logvar, z, ws = e.enc_fwd(self.theta, x, masks, eps, save=True)
         out = e.dec(L.DEC_TRAIN, self.theta, z, x=x, masks=masks, mean=mean, logvar=logvar, eps=eps, alpha=alpha,
                     beta_w=self.beta_w, loss_scale=1.0 / rows)
+        if after_dec is not None:
+            after_dec()
         e.enc_bwd(self.theta, x, masks, ws, out["d_mean"], out["d_logvar"])
         if not reduce:
             return None
@@ -717,8 +721,19 @@ class GraphedFusedTrainer(FusedTrainer):
         dev = theta.device
         self.table, self.mtable = _f32(table), mask_table.contiguous()
         self.B, self.n_batches, self.keep, self.seed = int(batch_rows), int(n_batches), float(keep), int(seed)
-        self.idx = torch.zeros(self.n_batches, self.B, dtype=torch.int64, device=dev)
+        # one extra list: a copy of list 0, for the batch that is prepared one step ahead at the wrap-around
+        self.idx = torch.zeros(self.n_batches + 1, self.B, dtype=torch.int64, device=dev)
         self.state = torch.zeros(2, dtype=torch.int64, device=dev)          # [completed steps, ticket]
+        # Prepare-ahead (PCVAE_PREP_AHEAD=1; MLP family on the tensor-core kernels; off by default: measured gain 0.6 %,
+        # 0.3632 -> 0.3610 ms at cfg4 -- the gather only fits beside the weight-gradient kernel): the batch of step
+        # n + 1 is gathered on a forked stream while the encoder backward and its weight gradients of step n run -- from
+        # the decoder call on, nothing of step n reads x, the masks or the noise -- and joined before reduce + Adam
+        # advances the step counter.  Same lists, same Philox offsets, same buffers: the step sequence is unchanged.
+        self.ahead = (family == L.FAMILY_MLP and os.environ.get("PCVAE_PREP_AHEAD", "0") == "1" and
+                      self.eng.lib.pcvae_enc_tc_workspace_floats(C.byref(self.eng.model), int(batch_rows),
+                                                                 2 if regularised else 1) > 0)
+        self._prepped = False
+        self._fork = torch.cuda.Stream(device=dev) if self.ahead else None
         self.x = torch.empty(self.B, obs_dim, device=dev)
         self.mask = torch.empty(self.B, obs_dim, device=dev, dtype=mask_table.dtype)
         self.mask_p = torch.empty_like(self.mask)
@@ -733,7 +748,11 @@ class GraphedFusedTrainer(FusedTrainer):
         step_count + j."""
         assert idx_batches.shape == (self.n_batches, self.B)
         rot = self.step_count % self.n_batches
-        self.idx.copy_(torch.roll(idx_batches.to(self.idx.device), rot, 0))
+        self.idx[:self.n_batches].copy_(torch.roll(idx_batches.to(self.idx.device), rot, 0))
+        self.idx[self.n_batches].copy_(self.idx[0])
+        if self.ahead:                                    # the batch of the coming step, from the new lists
+            self._prep(False)
+            self._prepped = True
 
     def reset_total(self):
         self.sums2[L.NSUMS:].zero_()
@@ -743,13 +762,34 @@ class GraphedFusedTrainer(FusedTrainer):
         """Sum of the step losses since reset_total() (every step of the sum had B rows: the loss is linear in the sums)."""
         return loss_from_sums(self.sums2[L.NSUMS:], self.global_rows or self.B, self.alpha, self.beta_w, self.regularised)
 
-    def _launch_step(self):
+    def _prep(self, ahead):
+        """Batch of step number state[0] (ahead = False) or state[0] + 1 (ahead = True: the list after the current one --
+        the extra list covers the wrap-around -- and the Philox offset of the next step) into x / mask / mask_p / eps."""
         with torch.cuda.device(self.theta.device):
-            L.check(self.eng.lib.pcvae_prep_batch_dev(_p(self.table), _p(self.mtable), _p(self.idx), self.n_batches, _p(self.x),
-                                                      _p(self.mask), _p(self.mask_p), _p(self.eps), self.B, self.eng.D, self.n_eps,
-                                                      self.keep, self.seed, 0, _p(self.state), _stream()), "pcvae_prep_batch_dev")
-        self.forward_backward(self.x, self.mask, self.mask_p if self.regularised else None, self.eps[0],
-                              self.eps[1] if self.regularised else None, global_rows=self.global_rows, reduce=False)
+            L.check(self.eng.lib.pcvae_prep_batch_dev(_p(self.table), _p(self.mtable),
+                                                      self.idx.data_ptr() + (self.B * 8 if ahead else 0), self.n_batches,
+                                                      _p(self.x), _p(self.mask), _p(self.mask_p), _p(self.eps), self.B,
+                                                      self.eng.D, self.n_eps, self.keep, self.seed, 8 if ahead else 0,
+                                                      _p(self.state), _stream()), "pcvae_prep_batch_dev")
+
+    def _launch_step(self):
+        args = (self.x, self.mask, self.mask_p if self.regularised else None, self.eps[0],
+                self.eps[1] if self.regularised else None)
+        if self.ahead:
+            if not self._prepped:
+                self._prep(False)
+                self._prepped = True
+            main = torch.cuda.current_stream()
+
+            def fork():
+                self._fork.wait_stream(main)
+                with torch.cuda.stream(self._fork):
+                    self._prep(True)
+            self.forward_backward(*args, global_rows=self.global_rows, reduce=False, after_dec=fork)
+            main.wait_stream(self._fork)                  # before reduce + Adam advances the step counter
+        else:
+            self._prep(False)
+            self.forward_backward(*args, global_rows=self.global_rows, reduce=False)
         e = self.eng
         sums = self.sums2
         if self.xch is not None:                          # data parallel: reduce + NVLink exchange + Adam, device-counted
@@ -764,7 +804,9 @@ class GraphedFusedTrainer(FusedTrainer):
 
     def capture(self, warmup=3):
         """Warm up on a side stream (`warmup` real steps, they count), then capture one step."""
-        side = torch.cuda.Stream(device=self.theta.device)
+        # high priority: the kernels of the step are placed before the blocks of the forked batch preparation, which then
+        # fill what the weight-gradient kernel leaves free on every SM (the stream priority is recorded in the graph's nodes)
+        side = torch.cuda.Stream(device=self.theta.device, priority=-1)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
@@ -785,6 +827,9 @@ class GraphedFusedTrainer(FusedTrainer):
         """One training step (replay).  Returns the step's loss sums (a static buffer: read or clone before the next step)."""
         if self.graph is None:
             raise L.PcvaeError("GraphedFusedTrainer: capture() first")
+        if self.ahead and not self._prepped:              # after sync_counter() without new lists
+            self._prep(False)
+            self._prepped = True
         self.graph.replay()
         self.step_count += 1
         if self.xch is not None:
@@ -802,3 +847,4 @@ class GraphedFusedTrainer(FusedTrainer):
     def sync_counter(self):
         """After steps taken through the inherited host-counted `step` (a ragged last batch): publish the host step count."""
         self.state[0] = self.step_count
+        self._prepped = False                             # the buffers hold the batch of a step number that has passed
