@@ -174,21 +174,26 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
             float* dp6T = a.ws_dp6T + (long)vt * (TCW_H5 * ROWS) + (row >> 5) * (32 * TCW_H5) + (row & 31);
             unsigned* reluT = a.ws_relu + (vt * ROWS + row) * 8;
             // ---- z | 1 -> RA, HBM ----
+            // (the scratch copies of every stage go out under the MMA batch the stage starts: in front of the barrier the
+            // LSU queue throttles the warps on their way to it)
+            float zv[16];
             if (cg == 0) {
-                float v[16], lo[16];
+                float lo[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                for (int j = 0; j < 16; ++j) zv[j] = 0.f;
 #pragma unroll
-                for (int j = 0; j < LAT / 2; ++j) { v[2 * j] = zreg[j].x; v[2 * j + 1] = zreg[j].y; }     // zero for rows past the batch
-                v[LAT] = 1.0f;
+                for (int j = 0; j < LAT / 2; ++j) { zv[2 * j] = zreg[j].x; zv[2 * j + 1] = zreg[j].y; }     // zero for rows past the batch
+                zv[LAT] = 1.0f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) lo[j] = tf32_lo(v[j]);
-                tmem_st16(lane_addr + RA_HI, v);
+                for (int j = 0; j < 16; ++j) lo[j] = tf32_lo(zv[j]);
+                tmem_st16(lane_addr + RA_HI, zv);
                 tmem_st16(lane_addr + RA_HI + 16, lo);
-#pragma unroll
-                for (int j = 0; j < TCW_Z; ++j) zT[j * 32] = v[j];
             }
             mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_HI + 16, r_f4h, r_f4l, fs4, F4_C / 2, idF4); });
+            if (cg == 0) {
+#pragma unroll
+                for (int j = 0; j < TCW_Z; ++j) zT[j * 32] = zv[j];
+            }
             // the barrier inside mma_kick ends the previous item's loss epilogue: the staging buffer is free
             const bool staged = issue_in(t);
             mma_wait(cx, &bar_s);
@@ -205,9 +210,10 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
                 }
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
+                mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, r_f5h, r_f5l, fs5, F5_C / 2, idF5); });
                 scratch_store(h4T, c16, TCW_H4, v, 16);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, r_f5h, r_f5l, fs5, F5_C / 2, idF5); });
+            mma_wait(cx, &bar_s);
 
             // ---- h5 = relu(acc5) | 1 -> RA, HBM ----
             uint32_t m5 = 0;                                  // relu mask of this thread's 28 h5 columns
@@ -216,23 +222,24 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
-                float v[16], lo[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < cnt) v[j] = acc[j0 + j];
+                float lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
-                        if (v[j] > 0.f) m5 |= 1u << (j0 + j); else v[j] = 0.f;
-                        lo[j] = tf32_lo(v[j]);
+                        if (acc[j0 + j] > 0.f) m5 |= 1u << (j0 + j); else acc[j0 + j] = 0.f;
+                        lo[j] = tf32_lo(acc[j0 + j]);
                     }
-                st_part(lane_addr + RA_HI + c28, part, v);
+                st_part(lane_addr + RA_HI + c28, part, acc + j0);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                scratch_store(h5T, c28 + j0, TCW_H5, v, cnt);
+            }
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_f6h, r_f6l, fs6, F6_C / 2, idF6); });
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                scratch_store(h5T, c28 + j0, TCW_H5, acc + j0, cnt);
             }
             reluT[cg] = m5;
             reluT[4 + cg] = m4;
-            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_f6h, r_f6l, fs6, F6_C / 2, idF6); });
             // while the tensor pipe runs F6: this thread's 28 entries of x and of the two masks (as bits)
             if (staged) { mbar_wait(&in_bar, in_ph, a.status, 3); in_ph ^= 1u; }
             float xr[28];
@@ -468,21 +475,24 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
-                float v[16], lo[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < cnt) v[j] = acc[j0 + j];
+                float lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
-                        if (!(k5 & (1u << (j0 + j)))) v[j] = 0.f;
-                        lo[j] = tf32_lo(v[j]);
+                        if (!(k5 & (1u << (j0 + j)))) acc[j0 + j] = 0.f;
+                        lo[j] = tf32_lo(acc[j0 + j]);
                     }
-                st_part(lane_addr + RA_HI + c28, part, v);
+                st_part(lane_addr + RA_HI + c28, part, acc + j0);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                scratch_store(dp5T, c28 + j0, TCW_H5, v, cnt);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, r_x5h, r_x5l, xs5, X5_C / 2, idX5); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, r_x5h, r_x5l, xs5, X5_C / 2, idX5); });
+            // scratch copies under the MMA batch (see k_dec_fwd_tc)
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                scratch_store(dp5T, c28 + j0, TCW_H5, acc + j0, cnt);
+            }
+            mma_wait(cx, &bar_s);
 
             // ---- dpre4 = dh4 * relu'(h4) -> RB, HBM ----
             {
@@ -496,9 +506,10 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
                 }
                 if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
                 else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
+                mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, r_x4h, r_x4l, xs4, X4_C / 2, idX4); });
                 scratch_store(dp4T, c16, TCW_H4, v, 16);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RB_HI, tmem + RB_LO, r_x4h, r_x4l, xs4, X4_C / 2, idX4); });
+            mma_wait(cx, &bar_s);
 
             // ---- latent-space terms: KL sums, d_mean / d_logvar; the row's 10 latents are split over its column
             //      groups (4 + 4 + 2 + 0) so that no warp waits for a single group doing all of them ----

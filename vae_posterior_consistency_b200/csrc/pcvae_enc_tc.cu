@@ -180,54 +180,63 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                         if (j < cnt) { v[j] = xm[j0 + j]; lo[j] = tf32_lo(v[j]); }
                     st_part(lane_addr + RA_HI + c28, part, v);
                     st_part(lane_addr + RA_LO + c28, part, lo);
-                    if (save) scratch_store(inT, c28 + j0, D + 1, v, cnt);
+                }
+                mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_e1h, r_e1l, es1, K1 / 8, idE1); });
+                // The scratch copies for the weight-gradient kernel go out UNDER the MMA batch they do not feed (the values are
+                // still in registers): issued in front of the barrier they cost 13 of this kernel's 67 us -- the LSU queue
+                // throttles the warps on their way to the barrier.
+                if (save) {
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                        scratch_store(inT, c28 + j0, D + 1, xm + j0, cnt);
+                    }
                 }
             }
-            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RA_HI, tmem + RA_LO, r_e1h, r_e1l, es1, K1 / 8, idE1); });
             // every thread has read its inputs (barrier inside mma_kick): the staging buffer is free for the next item
             staged = has_next ? issue_in(tn, bn) : false;
             mma_wait(cx, &bar_s);
 
-            // ---- h1 = relu(acc1) | 1 -> RA, HBM ----
+            // ---- h1 = relu(acc1) | 1 -> RA, HBM (scratch stores under the E2 MMAs) ----
             uint32_t m1 = 0;                                  // relu mask of this thread's 28 h1 columns
             float acc[28];
             tmem_ld28(lane_addr + ACC1 + c28, acc);
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
-                float v[16], lo[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < cnt) v[j] = acc[j0 + j];
+                float lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (j < cnt) {
-                        if (v[j] > 0.f) m1 |= 1u << (j0 + j); else v[j] = 0.f;
-                        lo[j] = tf32_lo(v[j]);
+                        if (acc[j0 + j] > 0.f) m1 |= 1u << (j0 + j); else acc[j0 + j] = 0.f;
+                        lo[j] = tf32_lo(acc[j0 + j]);
                     }
-                st_part(lane_addr + RA_HI + c28, part, v);
+                st_part(lane_addr + RA_HI + c28, part, acc + j0);
                 st_part(lane_addr + RA_LO + c28, part, lo);
-                if (save) scratch_store(h1T, c28 + j0, ETW_H1, v, cnt);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, r_e2h, r_e2l, es2, E2_C / 2, idE2); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC2, tmem + RA_HI, tmem + RA_LO, r_e2h, r_e2l, es2, E2_C / 2, idE2); });
+            if (save) {
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    const int j0 = part == 0 ? 0 : (part == 1 ? 16 : 24), cnt = part == 0 ? 16 : (part == 1 ? 8 : 4);
+                    scratch_store(h1T, c28 + j0, ETW_H1, acc + j0, cnt);
+                }
+            }
+            mma_wait(cx, &bar_s);
 
-            // ---- h2 = relu(acc2) | 1 -> RB, HBM ----
+            // ---- h2 = relu(acc2) | 1 -> RB, HBM (scratch stores under the E3 MMAs) ----
             uint32_t m2 = 0;                                  // relu mask of this thread's 16 h2 columns
+            float h2v[16];
             {
-                float v[16], lo[16];
-                tmem_ld16(lane_addr + ACC2 + c16, v);
+                float lo[16];
+                tmem_ld16(lane_addr + ACC2 + c16, h2v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    if (v[j] > 0.f) m2 |= 1u << j; else v[j] = 0.f;
-                    lo[j] = tf32_lo(v[j]);
+                    if (h2v[j] > 0.f) m2 |= 1u << j; else h2v[j] = 0.f;
+                    lo[j] = tf32_lo(h2v[j]);
                 }
-                if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, v); tmem_st16(lane_addr + RB_LO + c16, lo); }
-                else { tmem_st8(lane_addr + RB_HI + c16, v); tmem_st8(lane_addr + RB_LO + c16, lo); }
-                if (save) {
-                    scratch_store(h2T, c16, ETW_H2, v, 16);
-                    reluT[cg] = m1;
-                    reluT[4 + cg] = m2;
-                }
+                if (cg < 3) { tmem_st16(lane_addr + RB_HI + c16, h2v); tmem_st16(lane_addr + RB_LO + c16, lo); }
+                else { tmem_st8(lane_addr + RB_HI + c16, h2v); tmem_st8(lane_addr + RB_LO + c16, lo); }
             }
             // the row's 10 latents are split over its column groups (4 + 4 + 2 + 0) so that no warp waits for one group
             // doing all of them; the noise of the thread's latents is requested before the E3 MMAs are waited for
@@ -238,7 +247,13 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
                 e01 = *reinterpret_cast<const float2*>(a.eps[br] + gl);
                 if (cg < 2) e23 = *reinterpret_cast<const float2*>(a.eps[br] + gl + 2);
             }
-            run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, r_e3h, r_e3l, es3, E3_C / 2, idE3); });
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + ACC1, tmem + RB_HI, tmem + RB_LO, r_e3h, r_e3l, es3, E3_C / 2, idE3); });
+            if (save) {
+                scratch_store(h2T, c16, ETW_H2, h2v, 16);
+                reluT[cg] = m1;
+                reluT[4 + cg] = m2;
+            }
+            mma_wait(cx, &bar_s);
 
             // ---- mean | logvar, reparameterisation ----
             if (cg < 3) {
@@ -323,11 +338,12 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
         const unsigned* reluT = tw.relu + ((long)vt * ROWS + row) * 8;
         uint32_t m1 = 0, m2 = 0;
         if (ok) { m1 = reluT[cg]; m2 = reluT[4 + cg]; }
-        // ---- dpre3 = (d_mean | d_logvar) -> TMEM, HBM ----
+        // ---- dpre3 = (d_mean | d_logvar) -> TMEM, HBM (the scratch stores of a stage go out under its MMA batch) ----
+        float v3[24];
         if (cg == 0) {
-            float v[24], lo[24];
+            float lo[24];
 #pragma unroll
-            for (int j = 0; j < 24; ++j) v[j] = 0.f;
+            for (int j = 0; j < 24; ++j) v3[j] = 0.f;
             if (ok) {
                 const long gi = (long)grow * LAT;
                 const float2* dm = reinterpret_cast<const float2*>(a.d_mean[br] + gi);
@@ -335,27 +351,30 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
 #pragma unroll
                 for (int l = 0; l < LAT / 2; ++l) {
                     const float2 p = dm[l], q2 = dv[l];
-                    v[2 * l] = p.x; v[2 * l + 1] = p.y; v[LAT + 2 * l] = q2.x; v[LAT + 2 * l + 1] = q2.y;
+                    v3[2 * l] = p.x; v3[2 * l + 1] = p.y; v3[LAT + 2 * l] = q2.x; v3[LAT + 2 * l + 1] = q2.y;
                 }
                 if (a.d_z[br]) {          // reparameterisation backward folded in (z = mean + eps * exp(logvar / 2))
 #pragma unroll
                     for (int l = 0; l < LAT; ++l) {
                         const float dz = a.d_z[br][gi + l];
-                        v[l] += dz;
-                        if (a.eps[br]) v[LAT + l] = fmaf(dz * 0.5f * expf(a.logvar[br][gi + l] * 0.5f), a.eps[br][gi + l], v[LAT + l]);
+                        v3[l] += dz;
+                        if (a.eps[br]) v3[LAT + l] = fmaf(dz * 0.5f * expf(a.logvar[br][gi + l] * 0.5f), a.eps[br][gi + l], v3[LAT + l]);
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 24; ++j) lo[j] = tf32_lo(v[j]);
-            tmem_st16(lane_addr + B_D3H, v);
-            tmem_st8(lane_addr + B_D3H + 16, v + 16);
+            for (int j = 0; j < 24; ++j) lo[j] = tf32_lo(v3[j]);
+            tmem_st16(lane_addr + B_D3H, v3);
+            tmem_st8(lane_addr + B_D3H + 16, v3 + 16);
             tmem_st16(lane_addr + B_D3L, lo);
             tmem_st8(lane_addr + B_D3L + 16, lo + 16);
-#pragma unroll
-            for (int j = 0; j < LAT2; ++j) dp3T[j * 32] = v[j];
         }
-        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC2, tmem + B_D3H, tmem + B_D3L, r_y3h, r_y3l, ys3, Y3_C / 2, idY3); });
+        mma_kick(&bar_s, warp, [&] { issue_3x(tmem + B_AC2, tmem + B_D3H, tmem + B_D3L, r_y3h, r_y3l, ys3, Y3_C / 2, idY3); });
+        if (cg == 0) {
+#pragma unroll
+            for (int j = 0; j < LAT2; ++j) dp3T[j * 32] = v3[j];
+        }
+        mma_wait(cx, &bar_s);
 
         // ---- dpre2 = dh2 * relu'(h2) -> TMEM, HBM ----
         {
@@ -369,9 +388,10 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
             }
             if (cg < 3) { tmem_st16(lane_addr + B_RBH + c16, v); tmem_st16(lane_addr + B_RBL + c16, lo); }
             else { tmem_st8(lane_addr + B_RBH + c16, v); tmem_st8(lane_addr + B_RBL + c16, lo); }
+            mma_kick(&bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, r_y2h, r_y2l, ys2, Y2_C / 2, idY2); });
             scratch_store(dp2T, c16, ETW_H2, v, 16);
         }
-        run_mma(cx, &bar_s, warp, [&] { issue_3x(tmem + B_AC1, tmem + B_RBH, tmem + B_RBL, r_y2h, r_y2l, ys2, Y2_C / 2, idY2); });
+        mma_wait(cx, &bar_s);
 
         // ---- dpre1 = dh1 * relu'(h1) -> HBM ----
         const uint32_t k1 = m1 & col_bits(c28, H1);                      // column H1 is the bias column
