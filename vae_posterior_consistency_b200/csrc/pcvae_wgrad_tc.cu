@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
         for (int j = 0; j < a.njobs; ++j) {
             const int Nb = a.job[j].Nb;
             const uint32_t acc = tmem + (uint32_t)((j & 1) * 256);
-            const uint32_t id2 = make_idesc(128, 2 * Nb), id1 = make_idesc(128, Nb);
+            // M = 64 for the layers with at most 64 outputs: the tensor core fetches shared-memory operands at ~64 B/cycle
+            // and the A tile (M x 8 rows x 4 B per k-step, twice: hi and lo) is most of what a k-step reads for these
+            // layers -- an M = 128 tile that is half padding costs the same fetch as a full one
+            const int Mm = a.job[j].Ma <= 64 ? 64 : 128;
+            const uint32_t id2 = make_idesc(Mm, 2 * Nb), id1 = make_idesc(Mm, Nb);
             constexpr uint64_t sa = (2 * WG_ACS * 4) >> 4, sb = (2 * WG_BCS * 4) >> 4;
             if (j >= 2) {                                // this accumulator buffer was layer j-2's: wait until it is drained
                 mbar_wait(&drained_bar[j & 1], (uint32_t)(((j >> 1) - 1) & 1), a.status, 5);
@@ -174,14 +178,18 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
             mbar_wait(&done_bar[j & 1], (uint32_t)((j >> 1) & 1), a.status, 5);
             tc_fence_after();
             const int q = warp & 3;
-            const int m = 32 * q + lane;
+            // M = 128: accumulator row m is TMEM lane m; M = 64: row 16 i + r (r < 16) is lane 32 i + r (the first 16
+            // lanes of every lane quarter)
+            const bool m64 = J.Ma <= 64;
+            const int m = m64 ? 16 * q + lane : 32 * q + lane;
+            const bool mine = m64 ? (lane < 16 && m < J.Ma) : (m < J.Ma);
             const uint32_t acc = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((j & 1) * 256);
             float* wrow = gp + J.W_off + m * J.Kin;
             for (int c = 0; c < J.Kin + 1; c += 4) {
                 float x[4], w[4];
                 tmem_ld4(acc + c, x);
                 tmem_ld4(acc + J.Nb + c, w);
-                if (m < J.Ma) {
+                if (mine) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int n = c + e;
