@@ -118,6 +118,9 @@ typedef struct {
      * and everything pcvae_enc_bwd needs is saved there instead of act_ws (which may then be NULL). */
     float* tc_workspace;
     long tc_workspace_floats;
+    /* optional, tensor-core path: the buffer pcvae_build_weight_images() filled from THIS theta (see below); NULL = every
+     * CTA builds the operand images of the weights from theta at launch */
+    const float* weight_images;
 } pcvae_enc_fwd_params;
 
 size_t pcvae_enc_act_ws_floats(const pcvae_model* m, int rows, int n_branch);
@@ -153,6 +156,7 @@ typedef struct {
     /* the tc_workspace pcvae_enc_fwd filled for these rows (then act_ws is not read), or NULL */
     float* tc_workspace;
     long tc_workspace_floats;
+    const float* weight_images; /* optional, as in pcvae_enc_fwd_params */
 } pcvae_enc_bwd_params;
 int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream);
 
@@ -196,12 +200,22 @@ typedef struct {
      * rounding -- and the pre-activation gradients / activations for the weight-gradient GEMMs go through it. */
     float* tc_workspace;
     long tc_workspace_floats;
+    const float* weight_images; /* TRAIN, optional, as in pcvae_enc_fwd_params */
 } pcvae_dec_params;
 int pcvae_dec(const pcvae_dec_params* p, void* stream);
 /* floats of tc_workspace for `rows` x `n_branch`; 0 when this (family, obs_dim) has no tensor-core decoder */
 long pcvae_dec_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch);
 /* process-wide switch for the tcgen05 training kernels (default 1); returns the previous value */
 int pcvae_set_train_tensor_cores(int enable);
+/* Prebuilt weight images for the tensor-core training kernels.  Each of the four row-tile kernels of a step keeps the hi / lo
+ * tf32 operand images of three weight matrices in shared memory; built from theta by every CTA at launch that is ~5 us
+ * of a 60 us kernel (dependent L2 round trips, splits, scattered stores).  pcvae_build_weight_images() builds all of them
+ * ONCE per theta into `images` (pcvae_weight_images_floats() floats; two launches of two CTAs -- run it on a side stream
+ * while the batch is prepared); the kernels then fetch their block with bulk async copies.  Pass the buffer in the
+ * weight_images field of the encoder / decoder calls that run with the same theta.  Results are bit-identical with and
+ * without.  pcvae_weight_images_floats() is 0 when the model has no tensor-core training kernels. */
+long pcvae_weight_images_floats(const pcvae_model* m);
+int pcvae_build_weight_images(const pcvae_model* m, const float* theta, float* images, void* stream);
 /* Per-kernel timing hooks for benchmarks: arm `n` caller-created CUDA events (cudaEvent_t[n], timing enabled) on the
  * calling thread.  Each tensor-core launcher (pcvae_enc_fwd, pcvae_dec TRAIN, pcvae_enc_bwd) then records the next
  * event on its stream before its first kernel and after every kernel, until the events run out.  Pass NULL to

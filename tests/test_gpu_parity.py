@@ -3,6 +3,8 @@ run with `pytest -m gpu` under gpurun.  Tolerances: north_star's 1e-4 relative o
 losses / ELBO / RMSE; masks bit-exact (the kernels read the mask bytes as given)."""
 import math
 
+import ctypes as C
+
 import pytest
 import torch
 
@@ -537,6 +539,26 @@ def test_warp_specialised_reward_kernel_against_lockstep_kernel(N, D, M):
     # and a second call reproduces it (no state left in the barriers' phases, no race between the roles)
     R_again, _ = eng.reward(theta, x, mask, im)
     assert torch.equal(R_again, R_ws)
+
+
+@pytest.mark.parametrize("family,B,D,K", [("mlp", 300, 100, 0), ("mlp", 64, 20, 0), ("pnp", 200, 100, 20), ("mlp_mask", 130, 52, 0)])
+def test_prebuilt_weight_images_give_bit_identical_steps(family, B, D, K, monkeypatch):
+    """pcvae_build_weight_images: the operand images of the weights built once per theta and fetched by the tensor-core
+    kernels with bulk copies == the images every CTA builds for itself (the builder runs the kernels' own build code)."""
+    KR, L = _mods()
+    p, x, mask, mask_p, eq, ep = rand_case(family, B, D, K, seed=B + D)
+    eng, theta, fam = engine_for(p)
+    args = (x.cuda(), mask.cuda(), mask_p.cuda(), eq.cuda(), ep.cuda())
+    tr = KR.FusedTrainer(fam, D, K, theta.clone(), regularised=True)
+    assert (tr.wimg is not None) == (L.load().pcvae_weight_images_floats(C.byref(tr.eng.model)) > 0)
+    monkeypatch.setenv("PCVAE_WEIGHT_IMAGES", "0")
+    tr0 = KR.FusedTrainer(fam, D, K, theta.clone(), regularised=True)
+    monkeypatch.delenv("PCVAE_WEIGHT_IMAGES")
+    assert tr0.wimg is None
+    for _ in range(3):                                    # theta changes every step: the images must follow it
+        l1, l0 = tr.step(*args), tr0.step(*args)
+        assert torch.equal(l1, l0)
+    assert torch.equal(tr.theta, tr0.theta) and torch.equal(tr.grad, tr0.grad)
 
 
 def test_large_batch_properties(train_tc):

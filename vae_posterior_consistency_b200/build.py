@@ -8,7 +8,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpcvae_b200.so")
 SOURCES = ["pcvae_common.cu", "pcvae_train.cu", "pcvae_reward.cu", "pcvae_data.cu", "pcvae_dense.cu",
-           "pcvae_mnar.cu", "pcvae_miwae.cu", "pcvae_impute.cu", "pcvae_reward_tc.cu", "pcvae_reward_ws.cu", "pcvae_dec_tc.cu", "pcvae_enc_tc.cu", "pcvae_pnp_tc.cu", "pcvae_wgrad_tc.cu", "pcvae_dp.cu"]
+           "pcvae_mnar.cu", "pcvae_miwae.cu", "pcvae_impute.cu", "pcvae_reward_tc.cu", "pcvae_reward_ws.cu", "pcvae_dec_tc.cu", "pcvae_enc_tc.cu", "pcvae_pnp_tc.cu", "pcvae_tc_images.cu", "pcvae_wgrad_tc.cu", "pcvae_dp.cu"]
 HEADERS = ["pcvae_internal.cuh", "pcvae_tile.cuh", "pcvae_reward.cuh", "pcvae_tc.cuh", "pcvae_tc_tile.cuh", "pcvae_train.cuh", "pcvae_special.cuh", "pcvae_philox.cuh", os.path.join(ROOT, "include", "pcvae_b200.h")]
 
 NVCC_FLAGS = [

@@ -36,16 +36,6 @@
 namespace pcvae {
 namespace tc {
 
-// forward images  [K/4 chunks][N rows][4]
-constexpr int F4_C = 4, F4_N = 64;        // K = 16 (z|1), 50 outputs + the constant-1 generator
-constexpr int F5_C = 14, F5_N = 112;      // K = 56 (h4|1), 100 outputs + the constant-1 generator
-constexpr int F6_C = 26;                  // K = 104 (h5|1), round16(D) outputs
-// data-gradient images (transposed weights)
-constexpr int X6_C = 26, X6_N = 112;      // K = 104 (d), 100 inputs k
-constexpr int X5_C = 26, X5_N = 64;       // K = 104 (n), 50 inputs k
-constexpr int X4_C = 14, X4_N = 16;       // K = 56 (n), 10 inputs k
-
-
 // sigmoid with the two special-function instructions only: ex2.approx(-v log2 e) and rcp.approx(1 + t).  1 + t lies in
 // [1, inf], so no denormal handling is needed; relative error ~2^-21 (the loss tolerance is 1e-4 relative)
 __device__ __forceinline__ float sigmoid_fast(float v) {
@@ -55,10 +45,41 @@ __device__ __forceinline__ float sigmoid_fast(float v) {
     return r;
 }
 
+// weight images of k_dec_fwd_tc at `base`: W4 hi | lo, W5 hi | lo, W6 hi | lo
+__device__ __forceinline__ void dec_fwd_images(float* base, const float* __restrict__ th, const Layout& L, int tid) {
+    const int D = L.D, N6 = (D + 15) & ~15;
+    float* W4h = base;
+    float* W4l = W4h + F4_C * F4_N * 4;
+    float* W5h = W4l + F4_C * F4_N * 4;
+    float* W5l = W5h + F5_C * F5_N * 4;
+    float* W6h = W5l + F5_C * F5_N * 4;
+    float* W6l = W6h + F6_C * N6 * 4;
+    zero_images(base, 2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * N6 * 4), tid);
+    __syncthreads();
+    image_linear(W4h, W4l, F4_N, th + L.W4, th + L.b4, G1, LAT, true, tid);      // constant-1 output -> bias column of layer 5
+    image_linear(W5h, W5l, F5_N, th + L.W5, th + L.b5, G2, G1, true, tid);       // constant-1 output -> bias column of layer 6
+    image_linear(W6h, W6l, N6, th + L.W6, th + L.b6, D, G2, false, tid);
+}
+// weight images of k_dec_bwd_tc at `base`: W6^T hi | lo, W5^T hi | lo, W4^T hi | lo
+__device__ __forceinline__ void dec_bwd_images(float* base, const float* __restrict__ th, const Layout& L, int tid) {
+    float* T6h = base;
+    float* T6l = T6h + X6_C * X6_N * 4;
+    float* T5h = T6l + X6_C * X6_N * 4;
+    float* T5l = T5h + X5_C * X5_N * 4;
+    float* T4h = T5l + X5_C * X5_N * 4;
+    float* T4l = T4h + X4_C * X4_N * 4;
+    zero_images(base, 2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4), tid);
+    __syncthreads();
+    image_linear_T(T6h, T6l, X6_N, th + L.W6, L.D, G2, tid);
+    image_linear_T(T5h, T5l, X5_N, th + L.W5, G2, G1, tid);
+    image_linear_T(T4h, T4l, X4_N, th + L.W4, G1, LAT, tid);
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward + loss
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int stage_inputs) {
+    __shared__ __align__(8) uint64_t img_bar;
     extern __shared__ __align__(128) float smem[];
     __shared__ float red_s[NWARP][PCVAE_NSUMS];
     __shared__ __align__(8) uint64_t bar_s;
@@ -81,11 +102,8 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
     const float* th = a.theta;
     const Layout L = a.L;
     if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&in_bar)), "r"(1));
-    zero_images(smem, 2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * N6 * 4), tid);
-    __syncthreads();
-    image_linear(W4h, W4l, F4_N, th + L.W4, th + L.b4, G1, LAT, true, tid);      // constant-1 output -> bias column of layer 5
-    image_linear(W5h, W5l, F5_N, th + L.W5, th + L.b5, G2, G1, true, tid);       // constant-1 output -> bias column of layer 6
-    image_linear(W6h, W6l, N6, th + L.W6, th + L.b6, D, G2, false, tid);
+    if (a.wimg_fwd) fetch_images(smem, a.wimg_fwd, (uint32_t)dec_fwd_image_floats(D) * 4, &img_bar, tid, a.status);
+    else dec_fwd_images(smem, th, L, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid, a.status);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
@@ -349,6 +367,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
 // data gradients + latent-space terms
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
+    __shared__ __align__(8) uint64_t img_bar;
     extern __shared__ __align__(128) float smem[];
     __shared__ float red_s[NWARP][3];
     __shared__ __align__(8) uint64_t bar_s;
@@ -385,11 +404,8 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
         fence_async_smem();
     }
     issue_in(blockIdx.x);                                   // overlaps the weight-image build
-    zero_images(smem, 2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4), tid);
-    __syncthreads();
-    image_linear_T(T6h, T6l, X6_N, th + L.W6, D, G2, tid);
-    image_linear_T(T5h, T5l, X5_N, th + L.W5, G2, G1, tid);
-    image_linear_T(T4h, T4l, X4_N, th + L.W4, G1, LAT, tid);
+    if (a.wimg_bwd) fetch_images(smem, a.wimg_bwd, (uint32_t)dec_bwd_image_floats() * 4, &img_bar, tid, a.status);
+    else dec_bwd_images(smem, th, L, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid, a.status);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;

@@ -18,13 +18,6 @@
 namespace pcvae {
 namespace tc {
 
-// forward images  [K/4 chunks][N rows][4]
-constexpr int E1_N = 112;                  // 100 outputs + the constant-1 generator; K = round8(D + 1)
-constexpr int E2_C = 26, E2_N = 64;        // K = 104 (h1|1), 50 outputs + the constant-1 generator
-constexpr int E3_C = 14, E3_N = 32;        // K = 56 (h2|1), mean | logvar
-// data-gradient images (transposed weights)
-constexpr int Y3_C = 6, Y3_N = 64;         // K = 24 (n over 2L), 50 inputs k
-constexpr int Y2_C = 14, Y2_N = 112;       // K = 56 (n over 50), 100 inputs k
 // TMEM map of the backward kernel (256 columns): d3 hi [0,24) lo [32,56); acc of X3 [64,128); dpre2 hi [128,184)
 // lo [184,240); acc of X2 [0,112) -- it aliases d3 and the X3 accumulator, both dead by then
 constexpr int B_D3H = 0, B_D3L = 32, B_AC2 = 64, B_RBH = 128, B_RBL = 184, B_AC1 = 0, B_COLS = 256;
@@ -32,6 +25,36 @@ constexpr int B_D3H = 0, B_D3L = 32, B_AC2 = 64, B_RBH = 128, B_RBL = 184, B_AC1
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// weight images of k_enc_bwd_tc at `base`: W3^T hi | lo, W2^T hi | lo
+__device__ __forceinline__ void enc_bwd_images(float* base, const float* __restrict__ th, const Layout& L, int tid) {
+    float* T3h = base;
+    float* T3l = T3h + Y3_C * Y3_N * 4;
+    float* T2h = T3l + Y3_C * Y3_N * 4;
+    float* T2l = T2h + Y2_C * Y2_N * 4;
+    zero_images(base, 2 * (Y3_C * Y3_N * 4 + Y2_C * Y2_N * 4), tid);
+    __syncthreads();
+    image_linear_T(T3h, T3l, Y3_N, th + L.W3, LAT2, H2, tid);
+    image_linear_T(T2h, T2l, Y2_N, th + L.W2, H2, H1, tid);
+}
+
+// weight images of k_enc_fwd_tc at `base` (shared memory): W1 hi | lo, W2 hi | lo, W3 hi | lo
+__device__ __forceinline__ void enc_fwd_images(float* base, const float* __restrict__ th, const Layout& L, int tid) {
+    const int D = L.D, K1 = (D + 8) & ~7, C1 = K1 / 4;
+    float* W1h = base;
+    float* W1l = W1h + C1 * E1_N * 4;
+    float* W2h = W1l + C1 * E1_N * 4;
+    float* W2l = W2h + E2_C * E2_N * 4;
+    float* W3h = W2l + E2_C * E2_N * 4;
+    float* W3l = W3h + E3_C * E3_N * 4;
+    zero_images(base, 2 * (C1 * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4), tid);
+    __syncthreads();
+    image_linear(W1h, W1l, E1_N, th + L.W1, th + L.b1, H1, D, true, tid);        // constant-1 output -> bias column of layer 2
+    image_linear(W2h, W2l, E2_N, th + L.W2, th + L.b2, H2, H1, true, tid);       // constant-1 output -> bias column of layer 3
+    // mean rows -> accumulator columns [0, 10), logvar rows -> [16, 26): both start on a 4-column boundary, so the latent
+    // epilogue can be split over the column groups with aligned 4-column TMEM loads
+    image_linear(W3h, W3l, E3_N, th + L.W3, th + L.b3, LAT, H2, false, tid);
+    image_linear(W3h + 16 * 4, W3l + 16 * 4, E3_N, th + L.W3 + LAT * H2, th + L.b3 + LAT, LAT, H2, false, tid);
+}
 __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const int stage_inputs_mode) {
     const int stage_inputs = stage_inputs_mode & 1;
     extern __shared__ __align__(128) float smem[];
@@ -53,15 +76,10 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
     const uint8_t* min_ = reinterpret_cast<const uint8_t*>(xin + ROWS * D);
     const float* th = a.theta;
     const Layout L = a.L;
+    __shared__ __align__(8) uint64_t img_bar;
     if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&in_bar)), "r"(1));
-    zero_images(smem, 2 * (C1 * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4), tid);
-    __syncthreads();
-    image_linear(W1h, W1l, E1_N, th + L.W1, th + L.b1, H1, D, true, tid);        // constant-1 output -> bias column of layer 2
-    image_linear(W2h, W2l, E2_N, th + L.W2, th + L.b2, H2, H1, true, tid);       // constant-1 output -> bias column of layer 3
-    // mean rows -> accumulator columns [0, 10), logvar rows -> [16, 26): both start on a 4-column boundary, so the latent
-    // epilogue can be split over the column groups with aligned 4-column TMEM loads
-    image_linear(W3h, W3l, E3_N, th + L.W3, th + L.b3, LAT, H2, false, tid);
-    image_linear(W3h + 16 * 4, W3l + 16 * 4, E3_N, th + L.W3 + LAT * H2, th + L.b3 + LAT, LAT, H2, false, tid);
+    if (a.wimg) fetch_images(smem, a.wimg, (uint32_t)enc_fwd_image_floats(D) * 4, &img_bar, tid, a.tw.status);
+    else enc_fwd_images(smem, th, L, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid, a.tw.status);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;
@@ -292,6 +310,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
 // backward: data gradients down to the first layer's pre-activation
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
+    __shared__ __align__(8) uint64_t img_bar;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar_s;
     __shared__ __align__(8) uint64_t desc_s[6];
@@ -303,10 +322,8 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
     float* T2l = T2h + Y2_C * Y2_N * 4;
     const float* th = a.theta;
     const Layout L = a.L;
-    zero_images(smem, 2 * (Y3_C * Y3_N * 4 + Y2_C * Y2_N * 4), tid);
-    __syncthreads();
-    image_linear_T(T3h, T3l, Y3_N, th + L.W3, LAT2, H2, tid);
-    image_linear_T(T2h, T2l, Y2_N, th + L.W2, H2, H1, tid);
+    if (a.wimg) fetch_images(smem, a.wimg, (uint32_t)enc_bwd_image_floats() * 4, &img_bar, tid, a.tw.status);
+    else enc_bwd_images(smem, th, L, tid);
     TileCtx cx;
     tc_setup(cx, &bar_s, &tmem_slot, tid, a.tw.status, B_COLS);
     const uint32_t tmem = cx.tmem, lane_addr = cx.lane_addr;

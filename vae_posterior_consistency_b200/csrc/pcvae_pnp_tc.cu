@@ -208,6 +208,8 @@ static Layout tail_layout(const Layout& L) {
     return T;
 }
 
+Layout pnp_tail_layout(const Layout& L) { return tail_layout(L); }
+
 bool pnp_tc_supported(const Layout& L) {
     return L.fam == PCVAE_FAMILY_PNP && L.K % 4 == 0 && L.K >= 4 && L.K <= MAX_K && enc_tc_supported(tail_layout(L)) &&
            emb_fwd_smem(L) <= (size_t)MAX_SMEM && emb_bwd_smem(L) <= (size_t)MAX_SMEM;

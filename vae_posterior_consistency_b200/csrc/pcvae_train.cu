@@ -733,6 +733,35 @@ using namespace pcvae;
 
 static int g_train_tc = 1;
 
+// block `which` (0 enc fwd, 1 enc bwd, 2 dec fwd, 3 dec bwd) of a caller's weight-image buffer, or nullptr
+static const float* img_block(const Layout& L, const float* images, int which) {
+    if (!images) return nullptr;
+    WeightImages w;
+    Layout Lenc;
+    bool enc, dec;
+    if (!pcvae::weight_images_plan(L, &w, &Lenc, &enc, &dec)) return nullptr;
+    if (which < 2 && !enc) return nullptr;
+    if (which >= 2 && !dec) return nullptr;
+    const long off[4] = {w.enc_fwd, w.enc_bwd, w.dec_fwd, w.dec_bwd};
+    return images + off[which];
+}
+
+// which blocks exist for this model and where they start (every block is a multiple of 4 floats)
+bool pcvae::weight_images_plan(const Layout& L, WeightImages* w, Layout* Lenc, bool* enc, bool* dec) {
+    *enc = false;
+    *Lenc = L;
+    if (pnp_tc_supported(L)) { *Lenc = pnp_tail_layout(L); *enc = true; }
+    else if (enc_tc_supported(L)) *enc = true;
+    *dec = dec_tc_supported(L);
+    long o = 0;
+    w->enc_fwd = o; if (*enc) o += tc::enc_fwd_image_floats(Lenc->D);
+    w->enc_bwd = o; if (*enc) o += tc::enc_bwd_image_floats();
+    w->dec_fwd = o; if (*dec) o += tc::dec_fwd_image_floats(L.D);
+    w->dec_bwd = o; if (*dec) o += tc::dec_bwd_image_floats();
+    w->total = o;
+    return *enc || *dec;
+}
+
 static size_t enc_fwd_smem(const Layout& L) {
     const int P = TM_TRAIN + 4, K4 = round4(L.K);
     const int in1 = L.fam == PCVAE_FAMILY_MLP ? (L.aug ? 2 * L.D : L.D) : L.K;
@@ -830,6 +859,7 @@ int pcvae_enc_fwd(const pcvae_enc_fwd_params* p, void* stream) {
             return fail(PCVAE_EINVAL, "enc_fwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
         if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_fwd: PNP family needs pnp_ac workspace");
         enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        a.wimg = img_block(L, p->weight_images, 0);
         pnp_tables_launch(L, p->theta, p->pnp_ac, st);
         return pnp_enc_fwd_tc_launch(a, p->tc_workspace + base, grid, st);
     }
@@ -838,6 +868,7 @@ int pcvae_enc_fwd(const pcvae_enc_fwd_params* p, void* stream) {
         if (p->tc_workspace_floats < need)
             return fail(PCVAE_EINVAL, "enc_fwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
         enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        a.wimg = img_block(L, p->weight_images, 0);
         return enc_fwd_tc_launch(a, grid, st);
     }
     if (L.fam == PCVAE_FAMILY_PNP) {
@@ -876,6 +907,7 @@ int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
             return fail(PCVAE_EINVAL, "enc_bwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
         if (!p->pnp_ac) return fail(PCVAE_EINVAL, "enc_bwd: PNP family needs pnp_ac tables");
         enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        a.wimg = img_block(L, p->weight_images, 1);
         return pnp_enc_bwd_tc_launch(a, p->tc_workspace + base, grid, st);
     }
     if (use_tc) {
@@ -883,6 +915,7 @@ int pcvae_enc_bwd(const pcvae_enc_bwd_params* p, void* stream) {
         if (p->tc_workspace_floats < need)
             return fail(PCVAE_EINVAL, "enc_bwd: tc_workspace has %ld floats, needs %ld", p->tc_workspace_floats, need);
         enc_tc_carve(p->tc_workspace, p->rows, p->n_branch, &a.tw);
+        a.wimg = img_block(L, p->weight_images, 1);
         return enc_bwd_tc_launch(a, grid, st);
     }
     if (L.fam == PCVAE_FAMILY_PNP) {
@@ -936,6 +969,8 @@ int pcvae_dec(const pcvae_dec_params* p, void* stream) {
         a.ws_dp5T = w; w += R2P * TCW_H5;
         a.ws_dp4T = w; w += R2P * TCW_H4;
         a.ws_relu = reinterpret_cast<unsigned*>(w);
+        a.wimg_fwd = img_block(L, p->weight_images, 2);
+        a.wimg_bwd = img_block(L, p->weight_images, 3);
         return dec_tc_launch(a, grid, (cudaStream_t)stream);
     }
     return launch(k_dec<TM_TRAIN>, dec_smem(L, bwd), grid, (cudaStream_t)stream, "dec", a);
@@ -953,6 +988,26 @@ long pcvae_enc_tc_workspace_floats(const pcvae_model* m, int rows, int n_branch)
     if (pnp_tc_supported(L)) return etw_floats(rows, n_branch) + pnp_tc_extra_floats(L, rows, n_branch);
     if (!enc_tc_supported(L)) return 0;
     return etw_floats(rows, n_branch);
+}
+
+long pcvae_weight_images_floats(const pcvae_model* m) {
+    Layout L, Lenc;
+    WeightImages w;
+    bool enc, dec;
+    if (!g_train_tc || !m || !make_layout(m, &L) || !weight_images_plan(L, &w, &Lenc, &enc, &dec)) return 0;
+    return w.total;
+}
+
+int pcvae_build_weight_images(const pcvae_model* m, const float* theta, float* images, void* stream) {
+    if (!m || !theta || !images) return fail(PCVAE_EINVAL, "build_weight_images: null pointer");
+    Layout L, Lenc;
+    if (!make_layout(m, &L)) return PCVAE_EINVAL;
+    int grid;
+    if (int rc = device_ok(&grid)) return rc;
+    WeightImages w;
+    bool enc, dec;
+    if (!weight_images_plan(L, &w, &Lenc, &enc, &dec)) return fail(PCVAE_EINVAL, "build_weight_images: this model has no tensor-core training kernels");
+    return build_weight_images_launch(L, Lenc, enc, dec, w, theta, images, (cudaStream_t)stream);
 }
 
 int pcvae_set_train_tensor_cores(int enable) {

@@ -34,6 +34,8 @@ struct DecArgs {
     unsigned* ws_relu; // [nvt*128][8]: bit masks of h5 > 0 (4 column groups x 28) and h4 > 0 (4 x 16)
     long nvt;
     int* status;      // tensor-core status word (tc_status_ptr), set by the launchers
+    const float* wimg_fwd;   // tensor-core path, optional: prebuilt weight images of k_dec_fwd_tc / k_dec_bwd_tc
+    const float* wimg_bwd;   // (pcvae_build_weight_images); nullptr: every CTA builds them from theta
 };
 
 // tensor-core encoder scratch (pcvae_enc_tc.cu): tile-blocked feature-major [vt][feature][128 rows] like the decoder's
@@ -64,6 +66,7 @@ struct EncFwdArgs {
     EncTcWs tw;       // tensor-core path only
     long x_bs;        // tensor-core path only: floats between the x of branch 0 and of branch 1 (0: both branches read
                       // the same x; PNP family: the pooled embeddings differ per branch, pcvae_pnp_tc.cu)
+    const float* wimg;   // tensor-core path, optional: prebuilt weight images of k_enc_fwd_tc
 };
 
 struct EncBwdArgs {
@@ -81,7 +84,42 @@ struct EncBwdArgs {
     const float* eps[2];
     const float* logvar[2];
     EncTcWs tw;       // tensor-core path only
+    const float* wimg;   // tensor-core path, optional: prebuilt weight images of k_enc_bwd_tc
 };
+
+// Shapes of the weight images of the row-tile kernels ([K / 4 chunks][N rows][4], K-major no-swizzle core-matrix order)
+namespace tc {
+// pcvae_enc_tc.cu, forward images
+constexpr int E1_N = 112;                  // 100 outputs + the constant-1 generator; K = round8(D + 1)
+constexpr int E2_C = 26, E2_N = 64;        // K = 104 (h1|1), 50 outputs + the constant-1 generator
+constexpr int E3_C = 14, E3_N = 32;        // K = 56 (h2|1), mean | logvar
+// pcvae_enc_tc.cu, data-gradient images (transposed weights)
+constexpr int Y3_C = 6, Y3_N = 64;         // K = 24 (n over 2L), 50 inputs k
+constexpr int Y2_C = 14, Y2_N = 112;       // K = 56 (n over 50), 100 inputs k
+// pcvae_dec_tc.cu, forward images
+constexpr int F4_C = 4, F4_N = 64;        // K = 16 (z|1), 50 outputs + the constant-1 generator
+constexpr int F5_C = 14, F5_N = 112;      // K = 56 (h4|1), 100 outputs + the constant-1 generator
+constexpr int F6_C = 26;                  // K = 104 (h5|1), round16(D) outputs
+// pcvae_dec_tc.cu, data-gradient images (transposed weights)
+constexpr int X6_C = 26, X6_N = 112;      // K = 104 (d), 100 inputs k
+constexpr int X5_C = 26, X5_N = 64;       // K = 104 (n), 50 inputs k
+constexpr int X4_C = 14, X4_N = 16;       // K = 56 (n), 10 inputs k
+__host__ __device__ inline int enc_fwd_image_floats(int D) { return 2 * ((((D + 8) & ~7) / 4) * E1_N * 4 + E2_C * E2_N * 4 + E3_C * E3_N * 4); }
+__host__ __device__ inline int enc_bwd_image_floats() { return 2 * (Y3_C * Y3_N * 4 + Y2_C * Y2_N * 4); }
+__host__ __device__ inline int dec_fwd_image_floats(int D) { return 2 * (F4_C * F4_N * 4 + F5_C * F5_N * 4 + F6_C * ((D + 15) & ~15) * 4); }
+__host__ __device__ inline int dec_bwd_image_floats() { return 2 * (X6_C * X6_N * 4 + X5_C * X5_N * 4 + X4_C * X4_N * 4); }
+}  // namespace tc
+
+// Prebuilt weight images (pcvae_weight_images_floats / pcvae_build_weight_images): one buffer, four blocks in this order,
+// each exactly the shared-memory weight region of its kernel.  `Lenc` is the layout the encoder kernels run with (the
+// MLP tail of the PNP family: pcvae_pnp_tc.cu).
+struct WeightImages {
+    long enc_fwd, enc_bwd, dec_fwd, dec_bwd, total;      // float offsets
+};
+bool weight_images_plan(const Layout& L, WeightImages* w, Layout* Lenc, bool* enc, bool* dec);
+// pcvae_tc_images.cu: all blocks in ONE launch, a thread per 16-byte chunk of an image
+int build_weight_images_launch(const Layout& L, const Layout& Lenc, bool enc, bool dec, const WeightImages& w, const float* theta,
+                               float* images, cudaStream_t st);
 
 // pcvae_dec_tc.cu
 constexpr int TCW_Z = 16, TCW_H4 = 56, TCW_H5 = 104;            // pitches of the buffers above
@@ -103,6 +141,7 @@ int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st);
 // pcvae_pnp_tc.cu: PNP (EDDI) set encoder = masked pooled embedding on the CUDA cores + the MLP tail on the tensor-core
 // encoder kernels (the tail sees obs_dim = emb_dim, x = pooled embedding per branch, mask = ones)
 bool pnp_tc_supported(const Layout& L);
+Layout pnp_tail_layout(const Layout& L);                                // the MLP tail as the tensor-core encoder kernels see it
 long pnp_tc_extra_floats(const Layout& L, long rows, int nbr);       // workspace floats beyond etw_floats()
 int pnp_enc_fwd_tc_launch(const EncFwdArgs& a, float* extra, int grid, cudaStream_t st);
 int pnp_enc_bwd_tc_launch(const EncBwdArgs& a, float* extra, int grid, cudaStream_t st);

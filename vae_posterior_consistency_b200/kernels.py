@@ -136,6 +136,20 @@ class Engine:
             self._sp = torch.zeros(self.grid, L.NSUMS, device=self.device, dtype=torch.float32)
         return self._sp
 
+    def build_weight_images(self, theta, out=None):
+        """Operand images of the weights for the tensor-core training kernels, built once from `theta`
+        (pcvae_build_weight_images); pass the result as `wimg` to enc_fwd / dec / enc_bwd calls that use the same theta.
+        None when this model has no tensor-core training kernels."""
+        n = self.lib.pcvae_weight_images_floats(C.byref(self.model))
+        if n <= 0:
+            return None
+        if out is None:
+            out = torch.empty(n, device=theta.device, dtype=torch.float32)
+        with torch.cuda.device(theta.device):
+            L.check(self.lib.pcvae_build_weight_images(C.byref(self.model), _p(theta), _p(out), _stream()),
+                    "pcvae_build_weight_images")
+        return out
+
     def pnp_ac(self):
         if self.family != L.FAMILY_PNP:
             return None
@@ -161,7 +175,7 @@ class Engine:
                                                self.D, n_eps, float(keep), seed, offset, _stream()), "pcvae_prep_packed")
 
     # ---- encoder ----------------------------------------------------------------
-    def enc_fwd(self, theta, x, masks, eps=None, save=False, want_z=True):
+    def enc_fwd(self, theta, x, masks, eps=None, save=False, want_z=True, wimg=None):
         _need_cuda(theta, x, *masks)
         x = _f32(x)
         nb = len(masks)
@@ -185,12 +199,13 @@ class Engine:
         p = L.EncFwdParams(model=self.model, rows=B, n_branch=nb, mask_kind=kind, theta=_p(theta), x=_p(x),
                            mask=_pair(masks), eps=_pair(eps), mean=_pair(mean), logvar=_pair(logvar), z=_pair(z),
                            act_ws=_p(act), pnp_ac=_p(self.pnp_ac()),
-                           tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel())
+                           tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel(),
+                           weight_images=_p(wimg))
         with torch.cuda.device(x.device):
             L.check(self.lib.pcvae_enc_fwd(C.byref(p), _stream()), "pcvae_enc_fwd")
         return mean, logvar, z, (tcw if tcw is not None else act)
 
-    def enc_bwd(self, theta, x, masks, ws, d_mean, d_logvar, d_z=None, eps=None, logvar=None):
+    def enc_bwd(self, theta, x, masks, ws, d_mean, d_logvar, d_z=None, eps=None, logvar=None, wimg=None):
         x = _f32(x)
         kind, masks = prep_masks(masks)
         gp = self.grad_partials()
@@ -205,14 +220,15 @@ class Engine:
                            x=_p(x), mask=_pair(masks), act_ws=_p(act), d_mean=_pair(d_mean),
                            d_logvar=_pair(d_logvar), pnp_ac=_p(self.pnp_ac()), grad_partials=_p(gp),
                            d_z=_pair(d_z), eps=_pair(eps), logvar=_pair(logvar),
-                           tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel())
+                           tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel(),
+                           weight_images=_p(wimg))
         with torch.cuda.device(x.device):
             L.check(self.lib.pcvae_enc_bwd(C.byref(p), _stream()), "pcvae_enc_bwd")
         return gp
 
     # ---- decoder ----------------------------------------------------------------
     def dec(self, mode, theta, z, *, x=None, masks=(), mean=(), logvar=(), eps=(), alpha=0.0, beta_w=1.0,
-            loss_scale=1.0, d_xhat=(), want_xhat=False, x_logvar=X_LOGVAR):
+            loss_scale=1.0, d_xhat=(), want_xhat=False, x_logvar=X_LOGVAR, wimg=None):
         _need_cuda(theta, *z)
         z = [_f32(t) for t in z]
         nb = len(z)
@@ -241,7 +257,8 @@ class Engine:
                         sums_partials=_p(self.sums_partials()), d_mean=_pair(d_mean), d_logvar=_pair(d_logvar),
                         d_xhat=_pair(dxh_c), d_z=_pair(d_z),
                         grad_partials=_p(self.grad_partials() if mode in (L.DEC_TRAIN, L.DEC_BWD) else None),
-                        tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel())
+                        tc_workspace=_p(tcw), tc_workspace_floats=0 if tcw is None else tcw.numel(),
+                        weight_images=_p(wimg))
         with torch.cuda.device(dev):
             L.check(self.lib.pcvae_dec(C.byref(p), _stream()), "pcvae_dec")
         self._last_tcw = tcw      # kept alive until the next call (also lets tests inspect the scratch)
@@ -653,26 +670,37 @@ class FusedTrainer:
         self.dist_group, self.world_size = dist_group, world_size
         # data parallel: the fused reduce + NVLink exchange + Adam kernel unless PCVAE_DP=nccl asks for the plain
         # reduce -> NCCL all-reduce -> Adam sequence (kept as the cross-check of the fused kernel)
+        # operand images of the weights for the tensor-core kernels, rebuilt from theta once per step (two tiny launches)
+        # instead of by every CTA of the four row-tile kernels (PCVAE_WEIGHT_IMAGES=0: per launch, as before)
+        self.wimg = None
+        if os.environ.get("PCVAE_WEIGHT_IMAGES", "1") != "0":
+            n = self.eng.lib.pcvae_weight_images_floats(C.byref(self.eng.model))
+            if n > 0:
+                self.wimg = torch.empty(n, device=theta.device, dtype=torch.float32)
         self.xch = None
         if dist_group is not None and world_size > 1 and os.environ.get("PCVAE_DP", "peer") != "nccl":
             from .dist import PeerExchange
             self.xch = PeerExchange.create_or_none(self.eng.P, dist_group, theta.device)
 
-    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True, after_dec=None):
+    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True, after_dec=None,
+                         images_ready=False):
         """`after_dec` (optional callable) runs between the decoder call and the encoder backward: the last point at
-        which x, the masks and the noise are read when the encoder runs on the tensor-core kernels."""
+        which x, the masks and the noise are read when the encoder runs on the tensor-core kernels.  `images_ready`: the
+        caller has already rebuilt self.wimg from the current theta (on a forked stream, joined)."""
         e = self.eng
+        if self.wimg is not None and not images_ready:
+            e.build_weight_images(self.theta, self.wimg)
         B = x.shape[0]
         rows = B if global_rows is None else global_rows
         masks = [mask, mask_p] if self.regularised else [mask]
         eps = [eps_q, eps_p] if self.regularised else [eps_q]
         alpha = self.alpha if self.regularised else 0.0
-        mean, logvar, z, ws = e.enc_fwd(self.theta, x, masks, eps, save=True)
+        mean, logvar, z, ws = e.enc_fwd(self.theta, x, masks, eps, save=True, wimg=self.wimg)
         out = e.dec(L.DEC_TRAIN, self.theta, z, x=x, masks=masks, mean=mean, logvar=logvar, eps=eps, alpha=alpha,
-                    beta_w=self.beta_w, loss_scale=1.0 / rows)
+                    beta_w=self.beta_w, loss_scale=1.0 / rows, wimg=self.wimg)
         if after_dec is not None:
             after_dec()
-        e.enc_bwd(self.theta, x, masks, ws, out["d_mean"], out["d_logvar"])
+        e.enc_bwd(self.theta, x, masks, ws, out["d_mean"], out["d_logvar"], wimg=self.wimg)
         if not reduce:
             return None
         e.reduce_grads(self.grad)
@@ -734,6 +762,7 @@ class GraphedFusedTrainer(FusedTrainer):
                                                                  2 if regularised else 1) > 0)
         self._prepped = False
         self._fork = torch.cuda.Stream(device=dev) if self.ahead else None
+        self._img_stream = torch.cuda.Stream(device=dev) if self.wimg is not None else None
         self.x = torch.empty(self.B, obs_dim, device=dev)
         self.mask = torch.empty(self.B, obs_dim, device=dev, dtype=mask_table.dtype)
         self.mask_p = torch.empty_like(self.mask)
@@ -775,21 +804,29 @@ class GraphedFusedTrainer(FusedTrainer):
     def _launch_step(self):
         args = (self.x, self.mask, self.mask_p if self.regularised else None, self.eps[0],
                 self.eps[1] if self.regularised else None)
+        main = torch.cuda.current_stream()
+        if self.wimg is not None:                         # the weight images of this step, beside the batch preparation
+            self._img_stream.wait_stream(main)
+            with torch.cuda.stream(self._img_stream):
+                self.eng.build_weight_images(self.theta, self.wimg)
         if self.ahead:
             if not self._prepped:
                 self._prep(False)
                 self._prepped = True
-            main = torch.cuda.current_stream()
+            if self.wimg is not None:
+                main.wait_stream(self._img_stream)
 
             def fork():
                 self._fork.wait_stream(main)
                 with torch.cuda.stream(self._fork):
                     self._prep(True)
-            self.forward_backward(*args, global_rows=self.global_rows, reduce=False, after_dec=fork)
+            self.forward_backward(*args, global_rows=self.global_rows, reduce=False, after_dec=fork, images_ready=True)
             main.wait_stream(self._fork)                  # before reduce + Adam advances the step counter
         else:
             self._prep(False)
-            self.forward_backward(*args, global_rows=self.global_rows, reduce=False)
+            if self.wimg is not None:
+                main.wait_stream(self._img_stream)
+            self.forward_backward(*args, global_rows=self.global_rows, reduce=False, images_ready=True)
         e = self.eng
         sums = self.sums2
         if self.xch is not None:                          # data parallel: reduce + NVLink exchange + Adam, device-counted

@@ -28,6 +28,7 @@ SYMBOLS = [
     "pcvae_draw_submask", "pcvae_draw_normal", "pcvae_dense_fwd", "pcvae_dense_bwd", "pcvae_mnar_sample_z",
     "pcvae_mnar_sample_z_bwd", "pcvae_mnar_loss_workspace_bytes", "pcvae_mnar_loss", "pcvae_set_reward_tensor_cores",
     "pcvae_dec_tc_workspace_floats", "pcvae_set_train_tensor_cores", "pcvae_enc_tc_workspace_floats",
+    "pcvae_weight_images_floats", "pcvae_build_weight_images",
     "pcvae_prep_batch", "pcvae_reduce_adam", "pcvae_profile_events", "pcvae_prep_packed",
     "pcvae_dp_exchange_bytes", "pcvae_dp_exchange_alloc", "pcvae_dp_exchange_open", "pcvae_dp_exchange_close",
     "pcvae_dp_exchange_free", "pcvae_dp_reduce_adam", "pcvae_prep_batch_dev", "pcvae_reduce_adam_dev",
@@ -65,7 +66,7 @@ class EncFwdParams(C.Structure):
     _fields_ = [("model", Model), ("rows", C.c_int), ("n_branch", C.c_int), ("mask_kind", C.c_int),
                 ("theta", C.c_void_p), ("x", C.c_void_p), ("mask", _P2), ("eps", _P2), ("mean", _P2),
                 ("logvar", _P2), ("z", _P2), ("act_ws", C.c_void_p), ("pnp_ac", C.c_void_p),
-                ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long)]
+                ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long), ("weight_images", C.c_void_p)]
 
 
 class EncBwdParams(C.Structure):
@@ -73,7 +74,7 @@ class EncBwdParams(C.Structure):
                 ("theta", C.c_void_p), ("x", C.c_void_p), ("mask", _P2), ("act_ws", C.c_void_p),
                 ("d_mean", _P2), ("d_logvar", _P2), ("pnp_ac", C.c_void_p), ("grad_partials", C.c_void_p),
                 ("d_z", _P2), ("eps", _P2), ("logvar", _P2),
-                ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long)]
+                ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long), ("weight_images", C.c_void_p)]
 
 
 class DecParams(C.Structure):
@@ -82,7 +83,8 @@ class DecParams(C.Structure):
                 ("mask", _P2), ("mean", _P2), ("logvar", _P2), ("eps", _P2),
                 ("alpha", C.c_float), ("beta_w", C.c_float), ("x_logvar", C.c_float), ("loss_scale", C.c_float),
                 ("sums_partials", C.c_void_p), ("d_mean", _P2), ("d_logvar", _P2), ("d_xhat", _P2),
-                ("d_z", _P2), ("grad_partials", C.c_void_p), ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long)]
+                ("d_z", _P2), ("grad_partials", C.c_void_p), ("tc_workspace", C.c_void_p), ("tc_workspace_floats", C.c_long),
+                ("weight_images", C.c_void_p)]
 
 
 class LossParams(C.Structure):
@@ -178,6 +180,9 @@ def load():
     lib.pcvae_dec_tc_workspace_floats.restype = C.c_long
     lib.pcvae_dec_tc_workspace_floats.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
     lib.pcvae_set_train_tensor_cores.argtypes = [C.c_int]
+    lib.pcvae_weight_images_floats.restype = C.c_long
+    lib.pcvae_weight_images_floats.argtypes = [C.POINTER(Model)]
+    lib.pcvae_build_weight_images.argtypes = [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pcvae_set_reward_tensor_cores.argtypes = [C.c_int]
     lib.pcvae_profile_events.argtypes = [C.c_void_p, C.c_int]
     lib.pcvae_loss_terms.argtypes = [C.POINTER(LossParams), C.c_void_p]
