@@ -628,10 +628,14 @@ def run_ours(args):
         if timed:
             evs, arr = new_events()
             lib.pcvae_profile_events(arr, 9)
-        mean, logvar, z, ws = eng.enc_fwd(theta, xs, masks, e, save=True)
+        wimg = getattr(tr, "wimg", None)                 # the weight images of this step's theta, as the trainers build them
+        if wimg is not None:
+            eng.build_weight_images(theta, wimg)
+            launches[0] += 1
+        mean, logvar, z, ws = eng.enc_fwd(theta, xs, masks, e, save=True, wimg=wimg)
         out = eng.dec(L.DEC_TRAIN, theta, z, x=xs, masks=masks, mean=mean, logvar=logvar, eps=e, alpha=1.0,
-                      beta_w=1.0, loss_scale=1.0 / (B * world))
-        eng.enc_bwd(theta, xs, masks, ws, out["d_mean"], out["d_logvar"])
+                      beta_w=1.0, loss_scale=1.0 / (B * world), wimg=wimg)
+        eng.enc_bwd(theta, xs, masks, ws, out["d_mean"], out["d_logvar"], wimg=wimg)
         if timed:
             if lib.pcvae_profile_events(None, 0) == 9:   # all nine marks were recorded (tensor-core path taken)
                 ev_sets.append(evs)
@@ -657,7 +661,8 @@ def run_ours(args):
         for s in range(args.warmup - w_graph):
             tr.step_graph()
         train_ms, sums = timed_graph_steps(tr, args.steps, world, clocks)
-        train_launches = 8 * args.steps                  # the eight kernels of the captured step, per replay
+        # the kernels of the captured step, per replay: prep, [weight images], six training kernels, reduce + Adam
+        train_launches = (9 if tr.wimg is not None else 8) * args.steps
         sums = sums.clone()
         if n_long > 0:                                   # the same step over a longer window (the contract's K can be small)
             long_ms, _ = timed_graph_steps(tr, n_long, world, clocks)
