@@ -379,9 +379,7 @@ def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D,
     p = O.init_params("mlp", D, 0, seed=7)
     mk = lambda: KR.GraphedFusedTrainer(L.FAMILY_MLP, D, 0, KR.flatten_params(p, L.FAMILY_MLP, dev), table, mtable, B, nb,
                                         keep=0.7, seed=99)
-    monkeypatch.setenv("PCVAE_PREP_AHEAD", "1")
     a, b = mk(), mk()
-    monkeypatch.delenv("PCVAE_PREP_AHEAD")
     a.set_batches(idx); b.set_batches(idx)
     a.capture()                                            # three eager warm-up steps, then the capture
     for _ in range(steps):
@@ -391,10 +389,12 @@ def test_graph_replay_of_the_fused_step_is_bit_identical_to_eager_launches(B, D,
     torch.cuda.synchronize()
     assert a.step_count == b.step_count == 3 + steps and int(a.state[0]) == int(b.state[0]) == 3 + steps
     assert torch.equal(a.theta, b.theta) and torch.equal(a.exp_avg_sq, b.exp_avg_sq) and torch.equal(a.total, b.total)
-    # a and b prepare the batch of step n + 1 on a forked stream during step n (PCVAE_PREP_AHEAD=1); c runs the default
-    # prep -> step order; new index lists in the middle of the run
-    assert a.ahead == (D % 4 == 0 and D <= 100)
+    # a and b prepare the batch of step n + 1 on a forked stream beside the last launch of step n (the default); c runs the
+    # plain prep -> step order (PCVAE_PREP_AHEAD=0); new index lists in the middle of the run
+    assert a.ahead and b.ahead
+    monkeypatch.setenv("PCVAE_PREP_AHEAD", "0")
     c = mk()
+    monkeypatch.delenv("PCVAE_PREP_AHEAD")
     assert not c.ahead
     c.set_batches(idx)
     for _ in range(3 + steps):

@@ -749,17 +749,17 @@ class GraphedFusedTrainer(FusedTrainer):
         dev = theta.device
         self.table, self.mtable = _f32(table), mask_table.contiguous()
         self.B, self.n_batches, self.keep, self.seed = int(batch_rows), int(n_batches), float(keep), int(seed)
-        # one extra list: a copy of list 0, for the batch that is prepared one step ahead at the wrap-around
-        self.idx = torch.zeros(self.n_batches + 1, self.B, dtype=torch.int64, device=dev)
+        self.idx = torch.zeros(self.n_batches, self.B, dtype=torch.int64, device=dev)
         self.state = torch.zeros(2, dtype=torch.int64, device=dev)          # [completed steps, ticket]
-        # Prepare-ahead (PCVAE_PREP_AHEAD=1; MLP family on the tensor-core kernels; off by default: measured gain 0.6 %,
-        # 0.3632 -> 0.3610 ms at cfg4 -- the gather only fits beside the weight-gradient kernel): the batch of step
-        # n + 1 is gathered on a forked stream while the encoder backward and its weight gradients of step n run -- from
-        # the decoder call on, nothing of step n reads x, the masks or the noise -- and joined before reduce + Adam
-        # advances the step counter.  Same lists, same Philox offsets, same buffers: the step sequence is unchanged.
-        self.ahead = (family == L.FAMILY_MLP and os.environ.get("PCVAE_PREP_AHEAD", "0") == "1" and
-                      self.eng.lib.pcvae_enc_tc_workspace_floats(C.byref(self.eng.model), int(batch_rows),
-                                                                 2 if regularised else 1) > 0)
+        # Prepare-ahead (default; PCVAE_PREP_AHEAD=0 for the plain prep -> step order): the batch of step n + 1 is gathered on a
+        # forked stream beside the last launch of step n -- reduce [+ NVLink gradient exchange] + Adam, which reads none of
+        # x / masks / noise and, under data parallelism, spends most of its time waiting for the other ranks' flags.  The
+        # preparation counts its own steps (`prep_count`, advanced on the forked stream) because the step counter proper is
+        # advanced by the kernel it runs beside.  Same lists, same Philox offsets, same buffers: the step sequence is
+        # unchanged (tests/test_gpu_parity.py: bit-identical to the prep -> step order).
+        # 1 GPU: 0.3432 -> 0.3372 ms at cfg4; 2 GPUs: 0.3680 -> 0.3401 ms (the exchange is hidden under the gather)
+        self.ahead = os.environ.get("PCVAE_PREP_AHEAD", "1") == "1"
+        self.prep_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self._prepped = False
         self._fork = torch.cuda.Stream(device=dev) if self.ahead else None
         self._img_stream = torch.cuda.Stream(device=dev) if self.wimg is not None else None
@@ -777,11 +777,9 @@ class GraphedFusedTrainer(FusedTrainer):
         step_count + j."""
         assert idx_batches.shape == (self.n_batches, self.B)
         rot = self.step_count % self.n_batches
-        self.idx[:self.n_batches].copy_(torch.roll(idx_batches.to(self.idx.device), rot, 0))
-        self.idx[self.n_batches].copy_(self.idx[0])
+        self.idx.copy_(torch.roll(idx_batches.to(self.idx.device), rot, 0))
         if self.ahead:                                    # the batch of the coming step, from the new lists
-            self._prep(False)
-            self._prepped = True
+            self._reprep()
 
     def reset_total(self):
         self.sums2[L.NSUMS:].zero_()
@@ -791,15 +789,20 @@ class GraphedFusedTrainer(FusedTrainer):
         """Sum of the step losses since reset_total() (every step of the sum had B rows: the loss is linear in the sums)."""
         return loss_from_sums(self.sums2[L.NSUMS:], self.global_rows or self.B, self.alpha, self.beta_w, self.regularised)
 
-    def _prep(self, ahead):
-        """Batch of step number state[0] (ahead = False) or state[0] + 1 (ahead = True: the list after the current one --
-        the extra list covers the wrap-around -- and the Philox offset of the next step) into x / mask / mask_p / eps."""
+    def _prep(self, counter):
+        """Batch of the step whose number `counter` (a device word) holds into x / mask / mask_p / eps."""
         with torch.cuda.device(self.theta.device):
-            L.check(self.eng.lib.pcvae_prep_batch_dev(_p(self.table), _p(self.mtable),
-                                                      self.idx.data_ptr() + (self.B * 8 if ahead else 0), self.n_batches,
+            L.check(self.eng.lib.pcvae_prep_batch_dev(_p(self.table), _p(self.mtable), _p(self.idx), self.n_batches,
                                                       _p(self.x), _p(self.mask), _p(self.mask_p), _p(self.eps), self.B,
-                                                      self.eng.D, self.n_eps, self.keep, self.seed, 8 if ahead else 0,
-                                                      _p(self.state), _stream()), "pcvae_prep_batch_dev")
+                                                      self.eng.D, self.n_eps, self.keep, self.seed, 0, _p(counter), _stream()),
+                    "pcvae_prep_batch_dev")
+
+    def _reprep(self):
+        """Prepare-ahead mode: (re)prepare the batch of the step about to run and point the preparation at the one after."""
+        self.prep_count.copy_(self.state[:1])
+        self._prep(self.prep_count)
+        self.prep_count += 1
+        self._prepped = True
 
     def _launch_step(self):
         args = (self.x, self.mask, self.mask_p if self.regularised else None, self.eps[0],
@@ -811,22 +814,23 @@ class GraphedFusedTrainer(FusedTrainer):
                 self.eng.build_weight_images(self.theta, self.wimg)
         if self.ahead:
             if not self._prepped:
-                self._prep(False)
-                self._prepped = True
-            if self.wimg is not None:
-                main.wait_stream(self._img_stream)
-
-            def fork():
-                self._fork.wait_stream(main)
-                with torch.cuda.stream(self._fork):
-                    self._prep(True)
-            self.forward_backward(*args, global_rows=self.global_rows, reduce=False, after_dec=fork, images_ready=True)
-            main.wait_stream(self._fork)                  # before reduce + Adam advances the step counter
+                self._reprep()
         else:
-            self._prep(False)
-            if self.wimg is not None:
-                main.wait_stream(self._img_stream)
-            self.forward_backward(*args, global_rows=self.global_rows, reduce=False, images_ready=True)
+            self._prep(self.state)
+        if self.wimg is not None:
+            main.wait_stream(self._img_stream)
+        self.forward_backward(*args, global_rows=self.global_rows, reduce=False, images_ready=True)
+        if self.ahead:                                    # the next batch, beside reduce [+ exchange] + Adam
+            self._fork.wait_stream(main)
+            with torch.cuda.stream(self._fork):
+                self._prep(self.prep_count)
+                self.prep_count += 1
+        sums = self._launch_tail()
+        if self.ahead:
+            main.wait_stream(self._fork)
+        return sums
+
+    def _launch_tail(self):
         e = self.eng
         sums = self.sums2
         if self.xch is not None:                          # data parallel: reduce + NVLink exchange + Adam, device-counted
@@ -865,8 +869,7 @@ class GraphedFusedTrainer(FusedTrainer):
         if self.graph is None:
             raise L.PcvaeError("GraphedFusedTrainer: capture() first")
         if self.ahead and not self._prepped:              # after sync_counter() without new lists
-            self._prep(False)
-            self._prepped = True
+            self._reprep()
         self.graph.replay()
         self.step_count += 1
         if self.xch is not None:
