@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cuda_pipeline.h>
 
+#include "pcvae_tc.cuh"
 #include "pcvae_train.cuh"
 
 namespace pcvae {
@@ -89,6 +90,113 @@ __global__ void __launch_bounds__(NT, EMB_CTAS) k_pnp_embed_fwd(const PnpEmbArgs
         for (int i = tid; i < TMP * K; i += NT) {
             const int r = i / K, k = i - r * K;
             if (row0 + r < a.B) out[i] = agg_s[k * PP + r];
+        }
+        __syncthreads();
+    }
+}
+
+// Forward, uint8 masks and obs_dim % 4 == 0: the tile of x and of the mask is staged ROW-MAJOR by two bulk async copies (a
+// 32-row tile of either is one contiguous block of the batch; double-buffered, requested a tile ahead), and the thread
+// mapping is chosen so that row-major is what it wants: lane = row, warp = (quad of embedding columns, segment of the
+// features).  A thread reads 4 features of its row with one LDS.128 (rows are 25 16-byte units apart: conflict-free per
+// quarter-warp) and their mask bytes with one LDS.32, the table entries as warp-wide broadcasts: 2 LDS.128 + 12
+// arithmetic instructions per feature for 4 (feature, column) pairs, no transposition, no staging instructions.  The
+// feature-major version above spends a quarter of its instructions staging the tile.  Segment partials are combined in
+// segment order.
+__global__ void __launch_bounds__(NT, EMB_CTAS) k_pnp_embed_fwd_rm(const PnpEmbArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t in_bar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = a.L.D, K = a.L.K, K4 = round4(K);
+    float* xt = smem;                                        // [2][TMP][D]
+    unsigned char* mt = reinterpret_cast<unsigned char*>(xt + 2 * TMP * D);   // [2][TMP][D] bytes
+    float* A_s = reinterpret_cast<float*>(mt + 2 * TMP * D);  // [D][K4]
+    float* C_s = A_s + D * K4;                               // [D][K4]
+    float* part_s = C_s + D * K4;                            // [nseg][K4][PP]
+    for (int i = tid; i < 2 * D * K4; i += NT) A_s[i] = a.ac[i];
+    // the mask of ones the tensor-core kernel multiplies the pooled embedding with (it is the MLP family's kernel)
+    for (long i = (long)blockIdx.x * NT + tid; i < ((long)a.B * K + 3) / 4; i += (long)gridDim.x * NT)
+        reinterpret_cast<unsigned*>(a.ones)[i] = 0x01010101u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&in_bar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&in_bar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tc::fence_async_smem();
+    }
+    __syncthreads();
+    const int ngs = K4 / 4, nseg = NWARP / ngs;               // column quads, feature segments (K <= 32: nseg >= 2)
+    const int kq = warp % ngs, sg = warp / ngs;
+    const int dq = D / 4, qper = (dq + nseg - 1) / nseg;      // feature quads per segment
+    const int q0 = sg * qper, q1 = min(dq, q0 + qper);
+    const int ntiles = (a.B + TMP - 1) / TMP, nvt = ntiles * a.nbr;
+    // full tiles arrive by bulk copies; a ragged last tile (its mask block need not be a multiple of 16 bytes) is copied by
+    // the threads when its turn comes
+    auto full_tile = [&](int vt) { return vt < nvt && ((vt % ntiles) + 1) * TMP <= a.B; };
+    auto request = [&](int vt, int buf) {
+        if (full_tile(vt) && tid == 0) {
+            const int br = vt / ntiles, row0 = (vt - br * ntiles) * TMP;
+            tc::mbar_expect_tx(&in_bar[buf], (uint32_t)(TMP * D * 5));
+            tc::bulk_g2s(xt + buf * TMP * D, a.x + (long)row0 * D, (uint32_t)(TMP * D * 4), &in_bar[buf]);
+            tc::bulk_g2s(reinterpret_cast<float*>(mt + buf * TMP * D),
+                         reinterpret_cast<const float*>(static_cast<const unsigned char*>(a.mask[br]) + (long)row0 * D),
+                         (uint32_t)(TMP * D), &in_bar[buf]);
+        }
+    };
+    request(blockIdx.x, 0);
+    uint32_t ph[2] = {0, 0};
+    int it = 0;
+    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int br = vt / ntiles, row0 = (vt - br * ntiles) * TMP;
+        request(vt + gridDim.x, buf ^ 1);                    // the other buffer was released by the barrier that ended the last tile
+        if (full_tile(vt)) {
+            tc::mbar_wait(&in_bar[buf], ph[buf], nullptr, 0);
+            ph[buf] ^= 1u;
+        } else {
+            const int nrows = a.B - row0;
+            const float* xs = a.x + (long)row0 * D;
+            const unsigned char* ms = static_cast<const unsigned char*>(a.mask[br]) + (long)row0 * D;
+            for (int i = tid; i < nrows * D; i += NT) {
+                xt[buf * TMP * D + i] = xs[i];
+                mt[buf * TMP * D + i] = ms[i];
+            }
+            __syncthreads();
+        }
+        const bool ok = row0 + lane < a.B;
+        if (sg < nseg) {
+            const float* xr = xt + (buf * TMP + lane) * D;
+            const unsigned char* mr = mt + (buf * TMP + lane) * D;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok) {
+#pragma unroll 2
+                for (int q = q0; q < q1; ++q) {
+                    const float4 x4 = lds4(xr + 4 * q);
+                    const unsigned mw = *reinterpret_cast<const unsigned*>(mr + 4 * q);
+                    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float m = ((mw >> (8 * j)) & 0xFFu) ? 1.f : 0.f;
+                        const int d = 4 * q + j;
+                        const float4 av = lds4(A_s + d * K4 + 4 * kq), cv = lds4(C_s + d * K4 + 4 * kq);
+                        acc[0] = fmaf(m, fmaxf(fmaf(xv[j], av.x, cv.x), 0.f), acc[0]);
+                        acc[1] = fmaf(m, fmaxf(fmaf(xv[j], av.y, cv.y), 0.f), acc[1]);
+                        acc[2] = fmaf(m, fmaxf(fmaf(xv[j], av.z, cv.z), 0.f), acc[2]);
+                        acc[3] = fmaf(m, fmaxf(fmaf(xv[j], av.w, cv.w), 0.f), acc[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part_s[(sg * K4 + 4 * kq + j) * PP + lane] = acc[j];
+        }
+        __syncthreads();
+        // pooled embedding of the tile, row-major [row][K]: warp = row, lane = column
+        float* out = a.agg + ((long)br * a.B + row0) * K;
+        for (int r = warp; r < TMP; r += NWARP) {
+            if (lane < K && row0 + r < a.B) {
+                float sum = part_s[lane * PP + r];
+                for (int g2 = 1; g2 < nseg; ++g2) sum += part_s[(g2 * K4 + lane) * PP + r];
+                out[(long)r * K + lane] = sum;
+            }
         }
         __syncthreads();
     }
@@ -193,6 +301,10 @@ static size_t emb_fwd_smem(const Layout& L) {
     const int K4 = round4(L.K);
     return ((size_t)2 * L.D * PP + 2 * L.D * K4 + (size_t)(1 + EMB_SEG) * K4 * PP) * sizeof(float);
 }
+static size_t emb_fwd_rm_smem(const Layout& L) {
+    const int K4 = round4(L.K), nseg = NWARP / (K4 / 4);
+    return (size_t)2 * TMP * L.D * 5 + ((size_t)2 * L.D * K4 + (size_t)nseg * K4 * PP) * sizeof(float) + 128;
+}
 static size_t emb_bwd_smem(const Layout& L) {
     const int K4 = round4(L.K);
     return ((size_t)2 * L.D * PP + (size_t)H1 * PP + K4 * PP + (size_t)L.K * H1 + 4 * L.D * K4) * sizeof(float);
@@ -242,7 +354,11 @@ int pnp_enc_fwd_tc_launch(const EncFwdArgs& a, float* extra, int grid, cudaStrea
     PnpEmbArgs e{};
     emb_args(&e, a.L, a.B, a.nbr, a.mask_kind, a.theta, a.x, a.mask, a.ac, extra);
     prof_mark(st);
-    if (int rc = emb_go(k_pnp_embed_fwd, e, emb_fwd_smem(a.L), grid, st, "pnp_embed_fwd")) return rc;
+    // row-major staging by bulk copies needs byte masks and 16-byte rows
+    const bool rm = a.mask_kind == PCVAE_MASK_U8 && a.L.D % 4 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.mask[0]) & 15) == 0 && (a.nbr < 2 || (reinterpret_cast<uintptr_t>(a.mask[1]) & 15) == 0);
+    if (rm) { if (int rc = emb_go(k_pnp_embed_fwd_rm, e, emb_fwd_rm_smem(a.L), grid, st, "pnp_embed_fwd")) return rc; }
+    else if (int rc = emb_go(k_pnp_embed_fwd, e, emb_fwd_smem(a.L), grid, st, "pnp_embed_fwd")) return rc;
     EncFwdArgs t = a;
     t.L = tail_layout(a.L);
     t.x = e.agg;

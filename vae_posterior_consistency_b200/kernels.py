@@ -682,11 +682,8 @@ class FusedTrainer:
             from .dist import PeerExchange
             self.xch = PeerExchange.create_or_none(self.eng.P, dist_group, theta.device)
 
-    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True, after_dec=None,
-                         images_ready=False):
-        """`after_dec` (optional callable) runs between the decoder call and the encoder backward: the last point at
-        which x, the masks and the noise are read when the encoder runs on the tensor-core kernels.  `images_ready`: the
-        caller has already rebuilt self.wimg from the current theta (on a forked stream, joined)."""
+    def forward_backward(self, x, mask, mask_p, eps_q, eps_p, global_rows=None, reduce=True, images_ready=False):
+        """`images_ready`: the caller has already rebuilt self.wimg from the current theta (on a forked stream, joined)."""
         e = self.eng
         if self.wimg is not None and not images_ready:
             e.build_weight_images(self.theta, self.wimg)
@@ -698,8 +695,6 @@ class FusedTrainer:
         mean, logvar, z, ws = e.enc_fwd(self.theta, x, masks, eps, save=True, wimg=self.wimg)
         out = e.dec(L.DEC_TRAIN, self.theta, z, x=x, masks=masks, mean=mean, logvar=logvar, eps=eps, alpha=alpha,
                     beta_w=self.beta_w, loss_scale=1.0 / rows, wimg=self.wimg)
-        if after_dec is not None:
-            after_dec()
         e.enc_bwd(self.theta, x, masks, ws, out["d_mean"], out["d_logvar"], wimg=self.wimg)
         if not reduce:
             return None
