@@ -337,13 +337,29 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                     all_reduce_sum(se, group)
                 return (se / n_test).float().mean()                               # mean over rows, then over M
 
-            info[r, :, 0] = target_mse(sample_means()).cpu()
+            # The histories of this repeat stay on the device while the loop runs and go to the host once at its end (one
+            # transfer per repeat instead of three synchronising ones per acquisition step; im alone is M * rows * obs_dim
+            # floats per step): unless they would not fit comfortably, then they are copied step by step as before.
+            dev_hist = C * M * n_loc * obs_dim * 4 <= (1 << 30)
+            if dev_hist:
+                im_dev = torch.empty(C, M, n_loc, obs_dim, device=device)
+                R_dev = torch.empty(C, n_loc, C, device=device)
+                act_dev = torch.empty(n_loc, C, device=device)
+                info_dev = torch.empty(C + 1, device=device)
+            first = target_mse(sample_means())
+            if dev_hist:
+                info_dev[0] = first
+            else:
+                info[r, :, 0] = first.cpu()
             for t in range(C):
                 print("Repeat = {:.1f}".format(r))
                 print("Strategy = {:.1f}".format(2))
                 print("Step = {:.1f}".format(t))
                 im = sample_means()
-                im_hist[r, t, :, lo:hi] = im.cpu()
+                if dev_hist:
+                    im_dev[t].copy_(im)
+                else:
+                    im_hist[r, t, :, lo:hi] = im.cpu()
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
                 R, ws = eng.reward(theta, x, mask, im, ws)
@@ -358,11 +374,25 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                     for cnt in unsel.cpu().tolist():
                         for _ in range(4 * M):
                             torch.empty(int(cnt), latent_dim).normal_()
-                R_hist[r, t, lo:hi] = R.cpu()
                 i_opt = R.argmax(dim=1)
-                action[r, lo:hi, t] = i_opt.float().cpu()
+                if dev_hist:
+                    R_dev[t].copy_(R)
+                    act_dev[:, t] = i_opt.float()
+                else:
+                    R_hist[r, t, lo:hi] = R.cpu()
+                    action[r, lo:hi, t] = i_opt.float().cpu()
                 mask = mask + torch.eye(obs_dim, device=device)[i_opt]
-                info[r, :, t + 1] = target_mse(sample_means()).cpu()
+                nxt = target_mse(sample_means())
+                if dev_hist:
+                    info_dev[t + 1] = nxt
+                else:
+                    info[r, :, t + 1] = nxt.cpu()
+            if dev_hist:
+                im_hist[r, :, :, lo:hi] = im_dev.cpu()
+                R_hist[r, :, lo:hi] = R_dev.cpu()
+                action[r, lo:hi] = act_dev.cpu()
+                info[r] = info_dev.cpu().unsqueeze(0).expand(n_test, C + 1)
+                del im_dev, R_dev, act_dev, info_dev
     torch.cuda.synchronize(device)
     LAST_TIMING.update(reward_ms=sum(a.elapsed_time(b) for a, b, _ in reward_events),
                        triples=sum(n for _, _, n in reward_events), reward_calls=len(reward_events))
