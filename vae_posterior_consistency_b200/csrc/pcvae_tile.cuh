@@ -462,9 +462,11 @@ __device__ __forceinline__ void pnp_embed_bwd(const float* __restrict__ xs, cons
                 const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float tval = (fmaf(xv[i], av[jj], cv[jj]) > 0.f) ? mv[i] * gv[i] : 0.f;
-                    accC[jj] += tval;
-                    accA[jj] = fmaf(tval, xv[i], accA[jj]);
+                    const float tval = mv[i] * gv[i];
+                    if (fmaf(xv[i], av[jj], cv[jj]) > 0.f) {       // predicated adds: one select fewer per (row, feature, column)
+                        accC[jj] += tval;
+                        accA[jj] = fmaf(tval, xv[i], accA[jj]);
+                    }
                 }
             }
         }

@@ -364,7 +364,7 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                 ev0.record()
                 R, ws = eng.reward(theta, x, mask, im, ws)
                 ev1.record()
-                reward_events.append((ev0, ev1, int((mask[:, :C] == 0).sum()) * M))
+                reward_events.append((ev0, ev1, (mask[:, :C] == 0).sum() * M))      # counted on the device: no sync per step
                 if model.noise == 'host':
                     # the reference's chaini_I / chaini_II call encoder(sample=True): 4*M discarded [|loc|, L]
                     # draws per candidate (evaluate.py:562-626); burn them so the next `im` sees the same RNG state
@@ -395,7 +395,7 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                 del im_dev, R_dev, act_dev, info_dev
     torch.cuda.synchronize(device)
     LAST_TIMING.update(reward_ms=sum(a.elapsed_time(b) for a, b, _ in reward_events),
-                       triples=sum(n for _, _, n in reward_events), reward_calls=len(reward_events))
+                       triples=sum(int(n) for _, _, n in reward_events), reward_calls=len(reward_events))
     if world_size > 1:
         for tns in (action, R_hist, im_hist):
             merge_row_blocks(tns, group, device)                       # row blocks are disjoint: sum == gather
