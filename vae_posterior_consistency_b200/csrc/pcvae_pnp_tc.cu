@@ -205,14 +205,22 @@ __global__ void __launch_bounds__(NT, EMB_CTAS) k_pnp_embed_fwd_rm(const PnpEmbA
 // Launched as clusters of EMB_CTAS CTAs: the gradient partials are [grid][P] with grid = one row per SM-sized slot
 // (pcvae_grid_ctas), so the CTAs of a cluster add their dA / dC tables into rank 0's shared memory (distributed shared
 // memory, fixed order) and rank 0 writes the cluster's row.
+// RM (uint8 masks, obs_dim % 4 == 0): x and the mask are staged ROW-MAJOR by bulk async copies as in k_pnp_embed_fwd_rm --
+// the (feature, column-quad) owner threads read x[row][d] with lanes along d, which is conflict-free for any pitch -- instead
+// of being transposed into feature-major tiles by the threads (16.6 % of this kernel's instructions).
+template <bool RM>
 __global__ void __cluster_dims__(EMB_CTAS, 1, 1) __launch_bounds__(NT, EMB_CTAS) k_pnp_embed_bwd(const PnpEmbArgs a) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t in_bar[2];
     constexpr int RB = 1;
     const int tid = threadIdx.x;
     const int D = a.L.D, K = a.L.K, K4 = round4(K);
-    float* in_s = smem;                      // [D][PP]  x
-    float* ms_s = in_s + D * PP;             // [D][PP]  mask
-    float* dp1_s = ms_s + D * PP;            // [100][PP]  dL/d(pre1)
+    // RM: xt [2][TMP][D] floats | mt [2][TMP][D] bytes;  otherwise: in_s [D][PP] | ms_s [D][PP]
+    float* in_s = smem;
+    float* ms_s = in_s + D * PP;
+    float* xt = smem;
+    unsigned char* mt = reinterpret_cast<unsigned char*>(xt + 2 * TMP * D);
+    float* dp1_s = RM ? reinterpret_cast<float*>(mt + 2 * TMP * D) : ms_s + D * PP;   // [100][PP]  dL/d(pre1)
     float* agg_s = dp1_s + H1 * PP;          // [K4][PP]   dL/d(agg)
     float* W1_s = agg_s + K4 * PP;           // [K][100]
     float* A_s = W1_s + K * H1;              // [D][K4] (A then C)
@@ -222,12 +230,35 @@ __global__ void __cluster_dims__(EMB_CTAS, 1, 1) __launch_bounds__(NT, EMB_CTAS)
     stage_linear(W1_s, nullptr, a.theta + a.L.W1, nullptr, K, H1, H1, tid);
     for (int i = tid; i < 2 * D * K4; i += NT) { A_s[i] = a.ac[i]; dA_s[i] = 0.f; }
     zero_floats(agg_s, K4 * PP, tid);
+    if (RM && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&in_bar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&in_bar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tc::fence_async_smem();
+    }
     __syncthreads();
-    const int ntiles = (a.B + TMP - 1) / TMP, nt128 = (a.B + 127) / 128;
-    for (int vt = blockIdx.x; vt < ntiles * a.nbr; vt += gridDim.x) {
+    const int ngs = K4 / 4;
+    const int ntiles = (a.B + TMP - 1) / TMP, nt128 = (a.B + 127) / 128, nvt = ntiles * a.nbr;
+    auto full_tile = [&](int vt) { return vt < nvt && ((vt % ntiles) + 1) * TMP <= a.B; };
+    auto request = [&](int vt, int buf) {
+        if (RM && full_tile(vt) && tid == 0) {
+            const int br = vt / ntiles, row0 = (vt - br * ntiles) * TMP;
+            tc::mbar_expect_tx(&in_bar[buf], (uint32_t)(TMP * D * 5));
+            tc::bulk_g2s(xt + buf * TMP * D, a.x + (long)row0 * D, (uint32_t)(TMP * D * 4), &in_bar[buf]);
+            tc::bulk_g2s(reinterpret_cast<float*>(mt + buf * TMP * D),
+                         reinterpret_cast<const float*>(static_cast<const unsigned char*>(a.mask[br]) + (long)row0 * D),
+                         (uint32_t)(TMP * D), &in_bar[buf]);
+        }
+    };
+    request(blockIdx.x, 0);
+    uint32_t ph[2] = {0, 0};
+    int it = 0;
+    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x, ++it) {
+        const int buf = it & 1;
         const int br = vt / ntiles, t64 = vt - br * ntiles, row0 = t64 * TMP;
         const float* __restrict__ x = a.x;
         const void* __restrict__ mk = a.mask[br];
+        request(vt + gridDim.x, buf ^ 1);                    // released by the barrier that ended the last tile
         {   // the dpre1 rows of this tile: one 32-row slab [feature][32] of a 128-row tile of the tensor-core scratch
             static_assert(TMP == 32, "one slab per tile");
             const float* src = a.dp1T + ((long)br * nt128 + (t64 >> 2)) * (ETW_H1 * 128) + (long)(t64 & 3) * (32 * ETW_H1);
@@ -237,22 +268,69 @@ __global__ void __cluster_dims__(EMB_CTAS, 1, 1) __launch_bounds__(NT, EMB_CTAS)
             }
             __pipeline_commit();
         }
-        tile_elems<TMP, 8, XM>(D, row0, a.B, tid,
-            [&](int d, int r, bool ok) {
-                XM v{0.f, 0.f};
-                if (ok) {
-                    const long gi = (long)(row0 + r) * D + d;
-                    v.x = x[gi];
-                    v.m = load_mask(mk, gi, a.mask_kind);
-                }
-                return v;
-            },
-            [&](int d, int r, bool, XM v) { in_s[d * PP + r] = v.x; ms_s[d * PP + r] = v.m; });
+        if (!RM) {
+            tile_elems<TMP, 8, XM>(D, row0, a.B, tid,
+                [&](int d, int r, bool ok) {
+                    XM v{0.f, 0.f};
+                    if (ok) {
+                        const long gi = (long)(row0 + r) * D + d;
+                        v.x = x[gi];
+                        v.m = load_mask(mk, gi, a.mask_kind);
+                    }
+                    return v;
+                },
+                [&](int d, int r, bool, XM v) { in_s[d * PP + r] = v.x; ms_s[d * PP + r] = v.m; });
+        } else if (full_tile(vt)) {
+            tc::mbar_wait(&in_bar[buf], ph[buf], nullptr, 0);
+            ph[buf] ^= 1u;
+        } else {                                             // ragged last tile: copied by the threads, the rest masked off
+            const int nrows = a.B - row0;
+            const float* xs = x + (long)row0 * D;
+            const unsigned char* ms = static_cast<const unsigned char*>(mk) + (long)row0 * D;
+            for (int i = tid; i < TMP * D; i += NT) {
+                xt[buf * TMP * D + i] = i < nrows * D ? xs[i] : 0.f;
+                mt[buf * TMP * D + i] = i < nrows * D ? ms[i] : (unsigned char)0;
+            }
+        }
         __pipeline_wait_prior(0);
         __syncthreads();
         gemm_dx<TMP, RB, false, 2>(dp1_s, W1_s, agg_s, K, H1, tid);      // agg_s <- dL/d(agg)
         __syncthreads();
-        pnp_embed_bwd<TMP>(in_s, ms_s, agg_s, A_s, C_s, dA_s, dC_s, D, K, K4, tid);
+        if (!RM) {
+            pnp_embed_bwd<TMP>(in_s, ms_s, agg_s, A_s, C_s, dA_s, dC_s, D, K, K4, tid);
+        } else {
+            // as pnp_embed_bwd (pcvae_tile.cuh), reading x and the mask bytes row-major: lanes run along the feature
+            for (int item = tid; item < D * ngs; item += NT) {
+                const int jg = item / D, d = item - jg * D, j0 = 4 * jg;
+                const float4 a4 = lds4(A_s + d * K4 + j0), c4 = lds4(C_s + d * K4 + j0);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+                float accA[4] = {0.f, 0.f, 0.f, 0.f}, accC[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* xc = xt + buf * TMP * D + d;
+                const unsigned char* mc = mt + buf * TMP * D + d;
+#pragma unroll 2
+                for (int r = 0; r < TMP; r += 4) {
+                    float xv[4], mv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { xv[i] = xc[(r + i) * D]; mv[i] = mc[(r + i) * D] ? 1.f : 0.f; }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float4 g4 = lds4(agg_s + (j0 + jj) * PP + r);
+                        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float tval = mv[i] * gv[i];
+                            if (fmaf(xv[i], av[jj], cv[jj]) > 0.f) {
+                                accC[jj] += tval;
+                                accA[jj] = fmaf(tval, xv[i], accA[jj]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    if (j0 + jj < K) { dA_s[d * K4 + j0 + jj] += accA[jj]; dC_s[d * K4 + j0 + jj] += accC[jj]; }
+            }
+        }
         __syncthreads();
     }
     {
@@ -305,9 +383,10 @@ static size_t emb_fwd_rm_smem(const Layout& L) {
     const int K4 = round4(L.K), nseg = NWARP / (K4 / 4);
     return (size_t)2 * TMP * L.D * 5 + ((size_t)2 * L.D * K4 + (size_t)nseg * K4 * PP) * sizeof(float) + 128;
 }
-static size_t emb_bwd_smem(const Layout& L) {
+static size_t emb_bwd_smem(const Layout& L, bool rm) {
     const int K4 = round4(L.K);
-    return ((size_t)2 * L.D * PP + (size_t)H1 * PP + K4 * PP + (size_t)L.K * H1 + 4 * L.D * K4) * sizeof(float);
+    const size_t stage = rm ? (size_t)2 * TMP * L.D * 5 : (size_t)2 * L.D * PP * sizeof(float);
+    return stage + ((size_t)H1 * PP + K4 * PP + (size_t)L.K * H1 + 4 * L.D * K4) * sizeof(float) + 128;
 }
 
 // the MLP tail as the tensor-core kernels see it: obs_dim = emb_dim, weights where the PNP layout keeps them
@@ -324,7 +403,7 @@ Layout pnp_tail_layout(const Layout& L) { return tail_layout(L); }
 
 bool pnp_tc_supported(const Layout& L) {
     return L.fam == PCVAE_FAMILY_PNP && L.K % 4 == 0 && L.K >= 4 && L.K <= MAX_K && enc_tc_supported(tail_layout(L)) &&
-           emb_fwd_smem(L) <= (size_t)MAX_SMEM && emb_bwd_smem(L) <= (size_t)MAX_SMEM;
+           emb_fwd_smem(L) <= (size_t)MAX_SMEM && emb_bwd_smem(L, false) <= (size_t)MAX_SMEM;
 }
 
 // agg [nbr][rows][K] floats, then the ones mask [rows][K] bytes (both rounded up to 16 bytes)
@@ -377,7 +456,10 @@ int pnp_enc_bwd_tc_launch(const EncBwdArgs& a, float* extra, int grid, cudaStrea
     emb_args(&e, a.L, a.B, a.nbr, a.mask_kind, a.theta, a.x, a.mask, a.ac, extra);
     e.dp1T = a.tw.dp1T;
     e.gp = a.gp;
-    const int rc = emb_go(k_pnp_embed_bwd, e, emb_bwd_smem(a.L), grid, st, "pnp_embed_bwd");
+    const bool rm = a.mask_kind == PCVAE_MASK_U8 && a.L.D % 4 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.mask[0]) & 15) == 0 && (a.nbr < 2 || (reinterpret_cast<uintptr_t>(a.mask[1]) & 15) == 0);
+    const int rc = rm ? emb_go(k_pnp_embed_bwd<true>, e, emb_bwd_smem(a.L, true), grid, st, "pnp_embed_bwd")
+                      : emb_go(k_pnp_embed_bwd<false>, e, emb_bwd_smem(a.L, false), grid, st, "pnp_embed_bwd");
     prof_mark(st);
     return rc;
 }

@@ -388,9 +388,9 @@ def active_learning_func(data_loader_train, test_data, test_mask, missing_rate, 
                 else:
                     info[r, :, t + 1] = nxt.cpu()
             if dev_hist:
-                im_hist[r, :, :, lo:hi] = im_dev.cpu()
-                R_hist[r, :, lo:hi] = R_dev.cpu()
-                action[r, lo:hi] = act_dev.cpu()
+                im_hist[r, :, :, lo:hi].copy_(im_dev)           # straight into the history (no intermediate host tensor)
+                R_hist[r, :, lo:hi].copy_(R_dev)
+                action[r, lo:hi].copy_(act_dev)
                 info[r] = info_dev.cpu().unsqueeze(0).expand(n_test, C + 1)
                 del im_dev, R_dev, act_dev, info_dev
     torch.cuda.synchronize(device)
