@@ -756,6 +756,12 @@ class GraphedFusedTrainer(FusedTrainer):
         self.ahead = os.environ.get("PCVAE_PREP_AHEAD", "1") == "1"
         self.prep_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self._prepped = False
+        # prepare-ahead mode also rebuilds the weight images for the NEXT step right after Adam, under the tail of the forked
+        # gather, instead of at the start of the step where nothing hides the launch (4 us); whatever changes theta between
+        # steps (host-counted steps, new lists at an epoch boundary, a caller writing into theta) goes through
+        # invalidate_images() / sync_counter() / set_batches(), which make the next step rebuild them first
+        self._imgs_ready = False
+        self._imgs_in_tail = self.ahead and os.environ.get("PCVAE_IMAGES_IN_TAIL", "1") == "1"
         self._fork = torch.cuda.Stream(device=dev) if self.ahead else None
         self._img_stream = torch.cuda.Stream(device=dev) if self.wimg is not None else None
         self.x = torch.empty(self.B, obs_dim, device=dev)
@@ -773,8 +779,13 @@ class GraphedFusedTrainer(FusedTrainer):
         assert idx_batches.shape == (self.n_batches, self.B)
         rot = self.step_count % self.n_batches
         self.idx.copy_(torch.roll(idx_batches.to(self.idx.device), rot, 0))
+        self._imgs_ready = False
         if self.ahead:                                    # the batch of the coming step, from the new lists
             self._reprep()
+
+    def invalidate_images(self):
+        """Call after writing into `theta` between steps: the next step rebuilds the weight operand images first."""
+        self._imgs_ready = False
 
     def reset_total(self):
         self.sums2[L.NSUMS:].zero_()
@@ -803,7 +814,8 @@ class GraphedFusedTrainer(FusedTrainer):
         args = (self.x, self.mask, self.mask_p if self.regularised else None, self.eps[0],
                 self.eps[1] if self.regularised else None)
         main = torch.cuda.current_stream()
-        if self.wimg is not None:                         # the weight images of this step, beside the batch preparation
+        build_now = self.wimg is not None and not (self._imgs_in_tail and self._imgs_ready)
+        if build_now:                                     # the weight images of this step, beside the batch preparation
             self._img_stream.wait_stream(main)
             with torch.cuda.stream(self._img_stream):
                 self.eng.build_weight_images(self.theta, self.wimg)
@@ -812,7 +824,7 @@ class GraphedFusedTrainer(FusedTrainer):
                 self._reprep()
         else:
             self._prep(self.state)
-        if self.wimg is not None:
+        if build_now:
             main.wait_stream(self._img_stream)
         self.forward_backward(*args, global_rows=self.global_rows, reduce=False, images_ready=True)
         if self.ahead:                                    # the next batch, beside reduce [+ exchange] + Adam
@@ -822,6 +834,9 @@ class GraphedFusedTrainer(FusedTrainer):
                 self.prep_count += 1
         sums = self._launch_tail()
         if self.ahead:
+            if self.wimg is not None and self._imgs_in_tail:  # images of the next step from the theta Adam just wrote
+                self.eng.build_weight_images(self.theta, self.wimg)
+                self._imgs_ready = True
             main.wait_stream(self._fork)
         return sums
 
@@ -865,6 +880,9 @@ class GraphedFusedTrainer(FusedTrainer):
             raise L.PcvaeError("GraphedFusedTrainer: capture() first")
         if self.ahead and not self._prepped:              # after sync_counter() without new lists
             self._reprep()
+        if self._imgs_in_tail and self.wimg is not None and not self._imgs_ready:
+            self.eng.build_weight_images(self.theta, self.wimg)     # the recorded step builds the NEXT step's images only
+            self._imgs_ready = True
         self.graph.replay()
         self.step_count += 1
         if self.xch is not None:
@@ -882,4 +900,5 @@ class GraphedFusedTrainer(FusedTrainer):
     def sync_counter(self):
         """After steps taken through the inherited host-counted `step` (a ragged last batch): publish the host step count."""
         self.state[0] = self.step_count
+        self._imgs_ready = False                          # the host-counted steps rebuilt the images BEFORE their Adam update
         self._prepped = False                             # the buffers hold the batch of a step number that has passed
