@@ -56,6 +56,11 @@ bool make_layout(const pcvae_model* m, Layout* L) {
 static thread_local cudaEvent_t* g_prof_ev = nullptr;
 static thread_local int g_prof_n = 0, g_prof_i = 0;
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("PCVAE_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 void prof_mark(cudaStream_t st) {
     if (g_prof_ev && g_prof_i < g_prof_n) cudaEventRecord(g_prof_ev[g_prof_i++], st);
 }

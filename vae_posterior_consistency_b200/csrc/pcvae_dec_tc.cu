@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
             for (int j = 0; j < LAT / 2; ++j) zreg[j] = zp[j];
         }
     };
+    pdl_wait();                                           // z, mean, logvar come from the encoder kernel before
     load_z(blockIdx.x);
     uint32_t in_ph = 0;
     auto issue_in = [&](int ti) -> bool {                // full tiles only (a ragged last tile takes the direct global loads)
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(NT, 1) k_dec_fwd_tc(const DecArgs a, const int
     // work items = (tile, branch) pairs, tile-major, strided over the CTAs: the two branches of a tile run on
     // neighbouring CTAs at about the same time (x and the masks are shared through L2) and the load is balanced
     for (int w = blockIdx.x; w < ntiles * a.nbr; w += gridDim.x) {
+        if (w + gridDim.x >= ntiles * a.nbr) pdl_trigger();   // this CTA's last item: the next kernel may take the SM when it exits
         const int t = a.nbr == 2 ? (w >> 1) : w, br = a.nbr == 2 ? (w & 1) : 0;
         const int row0 = t * ROWS;
         const int grow = row0 + row;
@@ -403,7 +405,6 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    issue_in(blockIdx.x);                                   // overlaps the weight-image build
     if (a.wimg_bwd) fetch_images(smem, a.wimg_bwd, (uint32_t)dec_bwd_image_floats() * 4, &img_bar, tid, a.status);
     else dec_bwd_images(smem, th, L, tid);
     TileCtx cx;
@@ -430,7 +431,10 @@ __global__ void __launch_bounds__(NT, 1) k_dec_bwd_tc(const DecArgs a) {
     const float alpha = a.alpha, ls = a.loss_scale;
     float s_klq = 0.f, s_klp = 0.f, s_klr = 0.f;
 
+    pdl_wait();                                           // dpre6, the ReLU masks and the latent statistics come from the kernels before
+    issue_in(blockIdx.x);
     for (int w = blockIdx.x; w < ntiles * a.nbr; w += gridDim.x) {      // (tile, branch) items as in k_dec_fwd_tc
+        if (w + gridDim.x >= ntiles * a.nbr) pdl_trigger();   // this CTA's last item
         const int t = a.nbr == 2 ? (w >> 1) : w, br = a.nbr == 2 ? (w & 1) : 0;
         const int row0 = t * ROWS;
         const int grow = row0 + row;
@@ -613,8 +617,7 @@ static int tc_launch(Kern kern, const Args& args, size_t sm, int grid, cudaStrea
     if (sm > MAX_SMEM) return fail(PCVAE_EINVAL, "%s: shared memory %zu B exceeds %d", name, sm, MAX_SMEM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
-    kern<<<grid, NT, sm, st>>>(args);
-    e = cudaGetLastError();
+    e = launch_tc(kern, grid, NT, sm, st, true, args);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: launch: %s", name, cudaGetErrorString(e));
     return PCVAE_OK;
 }
@@ -629,8 +632,7 @@ int dec_tc_launch(const DecArgs& a_in, int grid, cudaStream_t st) {
         if (sm > MAX_SMEM) return fail(PCVAE_EINVAL, "dec_fwd_tc: shared memory %zu B exceeds %d", sm, MAX_SMEM);
         cudaError_t e = cudaFuncSetAttribute(tc::k_dec_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dec_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        tc::k_dec_fwd_tc<<<grid, NT, sm, st>>>(a, stage_inputs ? 1 : 0);
-        e = cudaGetLastError();
+        e = launch_tc(tc::k_dec_fwd_tc, grid, NT, sm, st, true, a, stage_inputs ? 1 : 0);
         if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dec_fwd_tc: launch: %s", cudaGetErrorString(e));
     }
     prof_mark(st);

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(NT, 1) k_enc_fwd_tc(const EncFwdArgs a, const 
         int t, br, tn = 0, bn = 0;
         if (!item_of(j, t, br)) break;
         const bool has_next = item_of(j + 1, tn, bn);
+        if (!has_next) pdl_trigger();                     // this CTA's last item: the next kernel may take the SM when it exits
         const int grow = t * ROWS + row;
         const bool ok = grow < a.B;
         if (has_next && (flat || bn == 0)) {   // pull the next tile of this CTA towards L2 while this one is processed
@@ -345,7 +346,9 @@ __global__ void __launch_bounds__(NT, 2) k_enc_bwd_tc(const EncBwdArgs a) {
 
     const int nvt = ((a.B + ROWS - 1) / ROWS) * a.nbr;
     const int ntiles = (a.B + ROWS - 1) / ROWS;
+    pdl_wait();                                           // d_mean / d_logvar and the ReLU masks come from the kernels before
     for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x) {
+        if (vt + gridDim.x >= nvt) pdl_trigger();         // this CTA's last tile
         const int br = vt / ntiles, t = vt - br * ntiles;
         const int grow = t * ROWS + row;
         const bool ok = grow < a.B;
@@ -458,12 +461,11 @@ void enc_tc_carve(float* w, long rows, int nbr, EncTcWs* tw) {
 }
 
 template <typename Kern, typename Args>
-static int enc_tc_go(Kern kern, const Args& args, size_t sm, int grid, cudaStream_t st, const char* name) {
+static int enc_tc_go(Kern kern, const Args& args, size_t sm, int grid, cudaStream_t st, const char* name, bool dependent = false) {
     if (sm > MAX_SMEM) return fail(PCVAE_EINVAL, "%s: shared memory %zu B exceeds %d", name, sm, MAX_SMEM);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
-    kern<<<grid, NT, sm, st>>>(args);
-    e = cudaGetLastError();
+    e = launch_tc(kern, grid, NT, sm, st, dependent, args);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "%s: launch: %s", name, cudaGetErrorString(e));
     return PCVAE_OK;
 }
@@ -487,7 +489,7 @@ int enc_fwd_tc_launch(const EncFwdArgs& a, int grid, cudaStream_t st) {
 int enc_bwd_tc_launch(const EncBwdArgs& a, int grid, cudaStream_t st) {
     prof_mark(st);
     if (a.B > 0)
-        if (int rc = enc_tc_go(tc::k_enc_bwd_tc, a, tc::enc_bwd_tc_smem(), 2 * grid, st, "enc_bwd_tc")) return rc;
+        if (int rc = enc_tc_go(tc::k_enc_bwd_tc, a, tc::enc_bwd_tc_smem(), 2 * grid, st, "enc_bwd_tc", true)) return rc;
     prof_mark(st);
     const int D = a.L.D;
     const WgradJob jobs[3] = {{a.tw.dp1T, ETW_H1, H1, a.tw.inT, ETW_IN, D, (D + 16) & ~15, a.L.W1, a.L.b1},

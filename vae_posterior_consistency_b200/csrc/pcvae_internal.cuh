@@ -43,6 +43,24 @@ int device_ok(int* n_sm);
 int* tc_status_ptr();
 // records the next armed profiling event (pcvae_profile_events) on `st`, if any
 void prof_mark(cudaStream_t st);
+// PCVAE_PDL=0 turns programmatic dependent launch off (every kernel then waits for its predecessor's completion)
+bool pdl_enabled();
+// kernel<<<grid, block, smem, st>>>(args...); with `dependent` the launch carries the programmatic-stream-serialization
+// attribute: the kernel MUST call tc::pdl_wait() before it touches anything an earlier kernel of the stream wrote
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_tc(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool dependent, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (dependent && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 // fills the PNP collapsed tables A,C (2*D*round4(K) floats) from theta
 void pnp_tables_launch(const Layout& L, const float* theta, float* ac, cudaStream_t st);
 

@@ -58,6 +58,15 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
                  "r"(__float_as_uint(v[1])) : "memory");
 }
+// Programmatic dependent launch.  Every persistent kernel of the training chain opens with pdl_trigger(): the next
+// kernel of the stream, if it was launched with launch_tc(..., dependent = true), may then take an SM as soon as this
+// kernel's CTA there has exited (their shared-memory footprints exclude co-residence) and run its prologue -- barrier
+// init, TMEM allocation, the fetch of the prebuilt weight images -- while other SMs still work on this kernel's last
+// items; it blocks in pdl_wait() before its first access to anything a predecessor wrote.  pdl_wait() returns at once in
+// a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

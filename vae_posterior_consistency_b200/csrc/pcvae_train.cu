@@ -656,6 +656,9 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const float* __restrict__ g
     __shared__ float red[8][32];
     __shared__ float bc_s[2];
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    // launched as a programmatic dependent of the weight-gradient kernel (launch_tc): its CTAs may be resident before the
+    // partials are complete; returns at once after an ordinary launch
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (DEV) {
         if (threadIdx.x == 0) {
             const double step = (double)(*reinterpret_cast<volatile unsigned long long*>(state) + 1ull);
@@ -1085,10 +1088,9 @@ int pcvae_reduce_adam(const float* grad_partials, int grid, long param_count, fl
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     const double c = 0.5 * 1.8378770664093453 * (double)rows * (double)obs_dim;   // 0.5*log(2*pi) per entry
     const int blocks = (int)((param_count + 31) / 32);
-    k_reduce_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_partials, grid, param_count, grad, theta, exp_avg, exp_avg_sq,
-                                                                   (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps,
-                                                                   sums_partials, c, sums, nullptr);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_tc(k_reduce_adam<false>, blocks, 256, 0, (cudaStream_t)stream, true, grad_partials, grid, param_count, grad,
+                              theta, exp_avg, exp_avg_sq, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps,
+                              sums_partials, c, sums, (unsigned long long*)nullptr);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reduce_adam: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }
@@ -1101,9 +1103,8 @@ int pcvae_reduce_adam_dev(const float* grad_partials, int grid, long param_count
     if ((sums_partials == nullptr) != (sums == nullptr)) return fail(PCVAE_EINVAL, "reduce_adam_dev: sums_partials and sums go together");
     const double c = 0.5 * 1.8378770664093453 * (double)rows * (double)obs_dim;
     const int blocks = (int)((param_count + 31) / 32);
-    k_reduce_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_partials, grid, param_count, grad, theta, exp_avg, exp_avg_sq,
-                                                                  lr, 1.0f, beta1, beta2, eps, sums_partials, c, sums, step_state);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_tc(k_reduce_adam<true>, blocks, 256, 0, (cudaStream_t)stream, true, grad_partials, grid, param_count, grad,
+                              theta, exp_avg, exp_avg_sq, lr, 1.0f, beta1, beta2, eps, sums_partials, c, sums, step_state);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "reduce_adam_dev: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }

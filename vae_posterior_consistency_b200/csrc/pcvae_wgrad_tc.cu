@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
     const int mine_t = blockIdx.x < a.nvt ? (int)((a.nvt - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;    // tiles of this CTA
     const int nslab = mine_t * WG_SPT;                                                                       // slabs per layer
     if (nslab == 0) {                                   // no rows for this CTA: its partials are zero
+        pdl_wait();
         for (int j = 0; j < a.njobs; ++j) {
             const WgradJob& J = a.job[j];
             for (int i = tid; i < J.Ma * (J.Kin + 1); i += NT) {
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                           // both operands come from the kernels before
     const uint32_t tmem = tmem_slot;
     // Slab g of this CTA's sequence (layer after layer) uses raw stage g % 4 and image stage g % 2; the k-th use of a
     // stage completes the phase of parity k & 1 on each of its barriers.  All cursors advance incrementally.
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(NT, 1) k_wgrad_tc(const WgradArgs a) {
                 tc_fence_after();
             }
             for (int i = 0; i < nslab; ++i) {
+                if (j == a.njobs - 1 && i == nslab - WG_SPT) pdl_trigger();   // last tile of the last layer: the next kernel may take the SM when this CTA exits
                 mbar_wait(&full_bar[im], pi, a.status, 5);
                 tc_fence_after();
                 if (elect_one()) {
@@ -274,8 +277,7 @@ int wgrad_tc_launch(const WgradJob* jobs, int njobs, long nvt, float* gp, long P
     const size_t sm = (size_t)tc::WG_SMEM_FLOATS * sizeof(float) + 128;
     cudaError_t e = cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    tc::k_wgrad_tc<<<grid, NT, sm, st>>>(a);
-    e = cudaGetLastError();
+    e = launch_tc(tc::k_wgrad_tc, grid, NT, sm, st, true, a);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "wgrad_tc: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }
