@@ -51,6 +51,9 @@ __device__ __forceinline__ void dp_block(DpArgs a, const int bid, const int nbid
     __shared__ int late_s;
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
     if (threadIdx.x == 0) late_s = 0;
+    // launched as a programmatic dependent of the weight-gradient kernel (launch_tc): blocks may be resident before the
+    // partials are complete; returns at once after an ordinary or cooperative launch
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (a.state) {                                        // replayable launch: call number and Adam step from the device
         const unsigned long long st = *reinterpret_cast<volatile unsigned long long*>(a.state) + 1ull;
         a.seq = (unsigned)st;
@@ -259,8 +262,7 @@ int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
     // every block must be resident at once (a block waits for the other ranks before it ends): at most two per SM.  All
     // ranks must launch the same grid, i.e. be the same GPU model.
     const int blocks = a.nblocks < 2 * grid ? a.nblocks : 2 * grid;
-    k_dp_reduce_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = launch_tc(k_dp_reduce_adam, blocks, 256, 0, (cudaStream_t)stream, true, a);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dp_reduce_adam: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
 }
