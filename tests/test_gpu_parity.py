@@ -2,6 +2,8 @@
 run with `pytest -m gpu` under gpurun.  Tolerances: north_star's 1e-4 relative on fp32
 losses / ELBO / RMSE; masks bit-exact (the kernels read the mask bytes as given)."""
 import math
+import os
+import sys
 
 import ctypes as C
 
@@ -559,6 +561,41 @@ def test_prebuilt_weight_images_give_bit_identical_steps(family, B, D, K, monkey
         l1, l0 = tr.step(*args), tr0.step(*args)
         assert torch.equal(l1, l0)
     assert torch.equal(tr.theta, tr0.theta) and torch.equal(tr.grad, tr0.grad)
+
+
+_PDL_SNIPPET = r"""
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+from vae_posterior_consistency_b200 import lib as L, VAE, kernels as KR
+B, D = 16384, 100
+torch.manual_seed(3)
+model = VAE.Reg_VAE(D, 500, 0, 10, {"batch_size": 64, "patience": 100}, "pdl", "kl_reg")
+tr = KR.FusedTrainer(L.FAMILY_MLP, D, 0, model.flat_theta().detach().clone().cuda(), regularised=True)
+g = torch.Generator().manual_seed(5)
+x = torch.rand(B, D, generator=g).cuda(); mask = (torch.rand(B, D, generator=g) < 0.7).cuda()
+mask_p = mask & (torch.rand(B, D, generator=g) < 0.7).cuda()
+eq, ep = torch.randn(B, 10, generator=g).cuda(), torch.randn(B, 10, generator=g).cuda()
+for _ in range(4):
+    loss = tr.step(x, mask, mask_p, eq, ep)
+torch.cuda.synchronize()
+print("HASH", hashlib.sha256(tr.theta.cpu().numpy().tobytes() + tr.exp_avg_sq.cpu().numpy().tobytes()).hexdigest(), float(loss))
+"""
+
+
+def test_dependent_launches_do_not_change_a_bit():
+    """PCVAE_PDL (programmatic dependent launch along the training chain, read once per process): four eager steps at
+    16 384 x 100 in a process with it and in one without must leave bit-identical theta and Adam state."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for v in ("0", "1"):
+        env = dict(os.environ, PCVAE_PDL=v)
+        r = subprocess.run([sys.executable, "-c", _PDL_SNIPPET % root], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("HASH")]
+        assert line, r.stdout[-500:]
+        out[v] = line[0]
+    assert out["0"] == out["1"], out
 
 
 def test_large_batch_properties(train_tc):
