@@ -55,10 +55,20 @@ __global__ void k_draw_normal(float* __restrict__ out, long n, unsigned long lon
 }
 
 // Fused batch preparation (one launch instead of three): a warp per table row copies the row of x and of the
-// mask with 16-byte / 4-byte vector accesses, draws the sub-mask for its entries and (lanes 0..4) the 2 x 10
-// standard-normal draws of the row (Box-Muller).  Philox counter = (row, lane | stream, offset), key = seed.
+// mask with 16-byte / 4-byte vector accesses and draws the sub-mask for its entries; a second, flat loop draws the
+// 2 x 10 standard-normal values of every row (Box-Muller), one thread per (row, group of four values).  Philox counter =
+// (row, lane | 64 + group, offset), key = seed: what a row gets does not depend on how rows are dealt to warps.
+// A warp has PREP_R rows in flight (their indices first, then all their loads: two dependent memory round trips per
+// PREP_R rows), and the grid is exactly what is resident at once (prep_grid) -- no second, partial wave.
 // Requires D % 4 == 0 and D <= 128, uint8 masks.
-__global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ table, const uint8_t* __restrict__ mtable,
+#ifndef PCVAE_PREP_R
+#define PCVAE_PREP_R 4
+#endif
+#ifndef PCVAE_PREP_MINB
+#define PCVAE_PREP_MINB 4
+#endif
+constexpr int PREP_R = PCVAE_PREP_R;
+__global__ void __launch_bounds__(256, PCVAE_PREP_MINB) k_prep_batch(const float* __restrict__ table, const uint8_t* __restrict__ mtable,
                                                     const long* __restrict__ idx, float* __restrict__ x,
                                                     uint8_t* __restrict__ mask, uint8_t* __restrict__ mask_p,
                                                     float* __restrict__ eps, int B, int D, int n_eps, float keep,
@@ -74,55 +84,68 @@ __global__ void __launch_bounds__(256) k_prep_batch(const float* __restrict__ ta
         offset += st * 8ull;
     }
     const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    // gather: two rows of the warp in flight per trip (index -> row is a dependent pair of HBM round trips)
-    for (int b0 = w0; b0 < B; b0 += 2 * warps) {
-        const int b1 = b0 + warps;
-        const bool two = b1 < B;
-        const long s0 = idx[b0], s1 = two ? idx[b1] : 0;
-        if (lane < D4) {
-            const float4 v0 = reinterpret_cast<const float4*>(table + s0 * D)[lane];
-            const uint32_t m0 = reinterpret_cast<const uint32_t*>(mtable + s0 * D)[lane];
-            float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t m1 = 0;
-            if (two) {
-                v1 = reinterpret_cast<const float4*>(table + s1 * D)[lane];
-                m1 = reinterpret_cast<const uint32_t*>(mtable + s1 * D)[lane];
-            }
+    for (int base = w0; base < B; base += PREP_R * warps) {
+        long s[PREP_R];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !two) break;
-                const int b = h ? b1 : b0;
-                const float4 v = h ? v1 : v0;
-                const uint32_t m = h ? m1 : m0;
-                reinterpret_cast<float4*>(x + (long)b * D)[lane] = v;
-                reinterpret_cast<uint32_t*>(mask + (long)b * D)[lane] = m;
+        for (int k = 0; k < PREP_R; ++k) {
+            const int b = base + k * warps;
+            s[k] = b < B ? idx[b] : -1;
+        }
+        if (lane < D4) {
+            float4 v[PREP_R];
+            uint32_t m[PREP_R];
+#pragma unroll
+            for (int k = 0; k < PREP_R; ++k)
+                if (s[k] >= 0) {
+                    v[k] = reinterpret_cast<const float4*>(table + s[k] * D)[lane];
+                    m[k] = reinterpret_cast<const uint32_t*>(mtable + s[k] * D)[lane];
+                }
+#pragma unroll
+            for (int k = 0; k < PREP_R; ++k) {
+                if (s[k] < 0) continue;
+                const int b = base + k * warps;
+                reinterpret_cast<float4*>(x + (long)b * D)[lane] = v[k];
+                reinterpret_cast<uint32_t*>(mask + (long)b * D)[lane] = m[k];
                 const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)lane, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
                 const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
                 uint32_t mp = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (((m >> (8 * j)) & 0xFFu) && u01(rv[j]) < keep) mp |= 1u << (8 * j);       // rand() in [0,1) < keep
+                    if (((m[k] >> (8 * j)) & 0xFFu) && u01(rv[j]) < keep) mp |= 1u << (8 * j);    // rand() in [0,1) < keep
                 reinterpret_cast<uint32_t*>(mask_p + (long)b * D)[lane] = mp;
             }
         }
     }
-    for (int b = w0; b < B; b += warps) {
-        if (lane < (10 * n_eps + 3) / 4) {               // n_eps * 10 normals per row, four per lane
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(64 + lane), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
-            float gv[4];
-            const float r0 = sqrtf(-2.0f * logf(u01_open(r.x))), r1 = sqrtf(-2.0f * logf(u01_open(r.z)));
-            float s0, c0, s1, c1;
-            sincospif(2.0f * u01(r.y), &s0, &c0);
-            sincospif(2.0f * u01(r.w), &s1, &c1);
-            gv[0] = r0 * c0; gv[1] = r0 * s0; gv[2] = r1 * c1; gv[3] = r1 * s1;
-            const int e0 = 4 * lane;                     // entry in the row's [n_eps][10] block
+    // n_eps * 10 normals per row, four per thread: item = (row, group q), the counter a lane q of the row's warp used to take
+    const int Q = (10 * n_eps + 3) / 4;
+    const long items = (long)B * Q, nthreads = (long)gridDim.x * blockDim.x;
+    for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += nthreads) {
+        const int b = (int)(it / Q), q = (int)(it - (long)b * Q);
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(64 + q), (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+        float gv[4];
+        const float r0 = sqrtf(-2.0f * logf(u01_open(r.x))), r1 = sqrtf(-2.0f * logf(u01_open(r.z)));
+        float s0, c0, s1, c1;
+        sincospif(2.0f * u01(r.y), &s0, &c0);
+        sincospif(2.0f * u01(r.w), &s1, &c1);
+        gv[0] = r0 * c0; gv[1] = r0 * s0; gv[2] = r1 * c1; gv[3] = r1 * s1;
+        const int e0 = 4 * q;                            // entry in the row's [n_eps][10] block
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = e0 + j, br = e / 10, l = e - br * 10;
-                if (br < n_eps) eps[((long)br * B + b) * 10 + l] = gv[j];
-            }
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j, br = e / 10, l = e - br * 10;
+            if (br < n_eps) eps[((long)br * B + b) * 10 + l] = gv[j];
         }
     }
+}
+
+// CTAs of k_prep_batch that are resident at once on this device
+static int prep_grid(int sms) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_prep_batch, 256, 0) != cudaSuccess || n < 1) n = 4;
+        per_sm = n;
+    }
+    return sms * per_sm;
 }
 
 // Host-streamed batches: the mask arrives bit-packed (W = ceil(D / 32) words per row, bit j of word w is
@@ -216,7 +239,7 @@ int pcvae_prep_batch(const float* table, const uint8_t* mask_table, const long* 
         return fail(PCVAE_EINVAL, "prep_batch: bad arguments (obs_dim must be a multiple of 4, <= 128; n_eps 0..2)");
     if (rows == 0) return PCVAE_OK;
     if (!table || !mask_table || !idx || !x || !mask || !mask_p || (n_eps > 0 && !eps)) return fail(PCVAE_EINVAL, "prep_batch: null pointer");
-    k_prep_batch<<<grid * 8, 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx, x, mask, mask_p, eps, rows, obs_dim, n_eps,
+    k_prep_batch<<<prep_grid(grid), 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx, x, mask, mask_p, eps, rows, obs_dim, n_eps,
                                                               keep_prob, seed, offset, nullptr, 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "prep_batch: launch: %s", cudaGetErrorString(e));
@@ -233,7 +256,7 @@ int pcvae_prep_batch_dev(const float* table, const uint8_t* mask_table, const lo
         return fail(PCVAE_EINVAL, "prep_batch_dev: bad arguments (obs_dim must be a multiple of 4, <= 128; n_eps 0..2; n_batches >= 1)");
     if (!table || !mask_table || !idx_batches || !x || !mask || !mask_p || (n_eps > 0 && !eps) || !step_state)
         return fail(PCVAE_EINVAL, "prep_batch_dev: null pointer");
-    k_prep_batch<<<grid * 8, 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx_batches, x, mask, mask_p, eps, rows, obs_dim, n_eps,
+    k_prep_batch<<<prep_grid(grid), 256, 0, (cudaStream_t)stream>>>(table, mask_table, idx_batches, x, mask, mask_p, eps, rows, obs_dim, n_eps,
                                                               keep_prob, seed, offset0, step_state, n_batches);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "prep_batch_dev: launch: %s", cudaGetErrorString(e));
