@@ -73,13 +73,20 @@ __device__ __forceinline__ void dp_block(DpArgs a, const int bid, const int nbid
         const long i = (long)c * 32 + lane;
         float s = 0.f;
         if (i < P) {
-            int q = part;
-            for (; q + 24 < a.grid; q += 32) {
-                const float v0 = a.gp[(long)q * P + i], v1 = a.gp[(long)(q + 8) * P + i], v2 = a.gp[(long)(q + 16) * P + i],
-                            v3 = a.gp[(long)(q + 24) * P + i];
-                s += v0; s += v1; s += v2; s += v3;
+            // warp `part` sums partials part, part + 8, ... in that order (the order of k_reduce_adam); all loads of up to
+            // 160 partials are in flight before the first add: a block owns only 2 - 4 chunks and they are taken one after
+            // the other, so with four loads in flight this phase was ~17 us of dependent round trips
+            for (int q0 = part; q0 < a.grid; q0 += 160) {
+                float v[20];
+#pragma unroll
+                for (int k = 0; k < 20; ++k) {
+                    const int q = q0 + 8 * k;
+                    v[k] = q < a.grid ? a.gp[(long)q * P + i] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 20; ++k)
+                    if (q0 + 8 * k < a.grid) s += v[k];
             }
-            for (; q < a.grid; q += 8) s += a.gp[(long)q * P + i];
         }
         red[part][lane] = s;
         __syncthreads();
@@ -259,9 +266,9 @@ int pcvae_dp_reduce_adam(const pcvae_dp_params* p, void* stream) {
     if (int rc = device_ok(&grid)) return rc;
     DpArgs a;
     if (int rc = dp_convert(p, a)) return rc;
-    // every block must be resident at once (a block waits for the other ranks before it ends): at most two per SM.  All
-    // ranks must launch the same grid, i.e. be the same GPU model.
-    const int blocks = a.nblocks < 2 * grid ? a.nblocks : 2 * grid;
+    // every block must be resident at once (a block waits for the other ranks before it ends): four per SM (1 024 threads,
+    // under 64 registers each).  All ranks must launch the same grid, i.e. be the same GPU model.
+    const int blocks = a.nblocks < 4 * grid ? a.nblocks : 4 * grid;
     const cudaError_t e = launch_tc(k_dp_reduce_adam, blocks, 256, 0, (cudaStream_t)stream, true, a);
     if (e != cudaSuccess) return fail(PCVAE_ECUDA, "dp_reduce_adam: launch: %s", cudaGetErrorString(e));
     return PCVAE_OK;
