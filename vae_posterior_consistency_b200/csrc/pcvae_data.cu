@@ -61,6 +61,7 @@ __global__ void k_draw_normal(float* __restrict__ out, long n, unsigned long lon
 // A warp has PREP_R rows in flight (their indices first, then all their loads: two dependent memory round trips per
 // PREP_R rows), and the grid is exactly what is resident at once (prep_grid) -- no second, partial wave.
 // Requires D % 4 == 0 and D <= 128, uint8 masks.
+// (build-time knobs for tools/build_variant.sh; measured: 4 rows, 4 CTAs per SM = 26.9 us, profiles/r02_ncu_summary.md)
 #ifndef PCVAE_PREP_R
 #define PCVAE_PREP_R 4
 #endif
